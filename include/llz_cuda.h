@@ -1,0 +1,178 @@
+/*
+ * llz_cuda.h -- libllzfilter_cuda extensions (NOT in the reference).
+ *
+ * The reference API (llz_fir.h / llz_resample.h) is one mono stream per handle with host
+ * buffers.  The entry points here are what a B200 deployment needs on top of that, kept in a
+ * separate header so the two drop-in headers stay identical to the reference's:
+ *
+ *   1. banks: n_channels independent mono streams behind one handle, planar layout
+ *      (channel c = base + c*stride elements, each channel contiguous) -- the same thing as
+ *      n_channels reference handles driven in lock-step;
+ *   2. device-resident runs on caller-owned device pointers and a caller-owned cudaStream_t,
+ *      asynchronous (so throughput can be timed on the device without PCIe);
+ *   3. whole-signal calls: one call of any length is equivalent to looping the reference's
+ *      frames (closed forms: llz_fir.c:547-584, llz_resample.c:544-609);
+ *   4. arithmetic selectors (exact FP64 / reference-order FP64 / fast FP32);
+ *   5. explicit prototype length for the resampler (k_override);
+ *   6. host-side shard planners for multi-GPU runs (channel shards, time segments with halo).
+ *
+ * All functions return 0 / a positive count on success and -1 on failure unless stated;
+ * llz_cuda_last_error() returns the message of the calling thread's last failure.
+ * A handle is bound to the CUDA device that was current when it was created.
+ */
+#ifndef _LLZ_CUDA_H
+#define _LLZ_CUDA_H
+
+#include "llz_fir.h"
+#include "llz_resample.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *llz_cuda_stream_t;            /* a cudaStream_t; NULL = the legacy default stream */
+
+/* ---- runtime --------------------------------------------------------------------------- */
+const char *llz_cuda_last_error(void);
+int         llz_cuda_device_count(void);    /* 0 when no usable CUDA device */
+const char *llz_cuda_build_info(void);      /* "libllzfilter_cuda <ver> sm_100a ..." */
+
+/* ---- selectors ------------------------------------------------------------------------- */
+enum {                                      /* FIR design kind (llz_fir.c:201-269) */
+    LLZ_CUDA_LPF = 0, LLZ_CUDA_HPF = 1, LLZ_CUDA_BPF = 2, LLZ_CUDA_BSF = 3,
+};
+enum {                                      /* FIR sample type + arithmetic */
+    LLZ_CUDA_F64        = 0,  /* double I/O, FP64 FMA (drop-in type; |err| <= 1e-12 rel. full scale) */
+    LLZ_CUDA_F64_STRICT = 1,  /* double I/O, separate mul+add in llz_conv's order: bit-identical   */
+    LLZ_CUDA_F32        = 2,  /* float I/O, FP32 FMA with 120-tap blocked partial sums (>=120 dB)  */
+};
+enum {                                      /* resampler accumulator */
+    LLZ_CUDA_ACC_F64        = 0,  /* FP64 FMA + near-integer guard -> bit-identical int16 (default) */
+    LLZ_CUDA_ACC_F64_STRICT = 1,  /* reference order, separate mul+add: bit-identical by construction */
+    LLZ_CUDA_ACC_F32        = 2,  /* FP32 FMA: |diff| <= 1 LSB, exact at single-tap (knife-edge) phases */
+};
+
+/* ======================================================================================== */
+/* FIR banks  (rows a12-a16 of SURVEY.md section 8a; replaces N x llz_fir_filter_*_init)      */
+/* ======================================================================================== */
+unsigned long llz_cuda_fir_bank_init(int kind, int flt_len, double fc1, double fc2,
+                                     win_t win_type, int n_channels, int dtype);
+/* explicit taps (h[0] multiplies the newest sample, as in llz_conv) */
+unsigned long llz_cuda_fir_bank_init_taps(const double *h, int flt_len, int n_channels, int dtype);
+void          llz_cuda_fir_bank_uninit(unsigned long handle);
+
+int llz_cuda_fir_bank_flt_len(unsigned long handle);
+int llz_cuda_fir_bank_copy_taps(unsigned long handle, double *h_out);      /* host copy, flt_len doubles */
+
+/* stream state = the last flt_len-1 samples of every channel (llz_fir.c:562-564) */
+int llz_cuda_fir_bank_reset(unsigned long handle, llz_cuda_stream_t stream);
+/* d_hist: device, planar, flt_len-1 samples per channel (the halo of a time segment) */
+int llz_cuda_fir_bank_set_history(unsigned long handle, const void *d_hist, long long stride,
+                                  llz_cuda_stream_t stream);
+
+/* y[c][t] = sum_i h[i]*x[c][t-i], t in [0,n), continuing from the stored history; then the
+ * history becomes the last flt_len-1 inputs.  d_in/d_out: device, dtype of the bank, strides in
+ * elements.  Asynchronous on `stream`.  d_in and d_out must not overlap.                     */
+int llz_cuda_fir_bank_run(unsigned long handle, const void *d_in, long long in_stride,
+                          void *d_out, long long out_stride, long long n,
+                          llz_cuda_stream_t stream);
+/* flt_len-1 tail samples per channel (llz_fir.c:590-625); history becomes zeros */
+int llz_cuda_fir_bank_flush(unsigned long handle, void *d_out, long long out_stride,
+                            llz_cuda_stream_t stream);
+/* same as _run but h_in/h_out are HOST buffers (pinned or pageable); chunked H2D / kernel /
+ * D2H pipeline on three internal streams; synchronous.                                       */
+int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in, long long in_stride,
+                               void *h_out, long long out_stride, long long n);
+
+/* ======================================================================================== */
+/* Resampler banks  (rows a9-a11, a17-a20)                                                   */
+/* ======================================================================================== */
+typedef struct {
+    int kind;            /* 0 decimate, 1 interp, 2 resample (the CLI's -t values)            */
+    int L, M;
+    int n;               /* prototype length                                                  */
+    int taps_per_phase;  /* Q (resample) or K (decimate/interp)                               */
+    int num_in, num_out; /* reference frame size in samples (llz_resample.c:291-295,338-341,394-400) */
+    int n_channels;
+    int acc;
+} llz_cuda_resample_info_t;
+
+/* k_override > 0 forces the prototype to n = 2*k_override*L + 1 taps (Q = 2*k_override+1 per
+ * phase for L>1); 0 = the reference's rule n0/(2L) (llz_resample.c:204-222).                 */
+unsigned long llz_cuda_resample_bank_init(int L, int M, double gain, win_t win_type,
+                                          int k_override, int n_channels, int acc);
+unsigned long llz_cuda_decimate_bank_init(int M, double gain, win_t win_type,
+                                          int n_channels, int acc);
+unsigned long llz_cuda_interp_bank_init(int L, double gain, win_t win_type,
+                                        int n_channels, int acc);
+void          llz_cuda_resample_bank_uninit(unsigned long handle);
+
+int llz_cuda_resample_bank_info(unsigned long handle, llz_cuda_resample_info_t *info);
+/* host copies for parity checks: prototype (n doubles) and bank (rows*taps_per_phase doubles) */
+int llz_cuda_resample_bank_copy_proto(unsigned long handle, double *h_out);
+int llz_cuda_resample_bank_copy_bank(unsigned long handle, double *bank_out);
+
+/* number of outputs the next _run(n_in) will produce (resample: ceil((consumed+n_in)*L/M) -
+ * produced; decimate: floor; interp: n_in*L) */
+long long llz_cuda_resample_bank_out_len(unsigned long handle, long long n_in);
+
+int llz_cuda_resample_bank_reset(unsigned long handle, llz_cuda_stream_t stream);
+/* halo of a time segment: taps_per_phase-1 (resample) / n (decimate) int16 samples per channel
+ * that precede the segment; also rewinds the phase to output index 0.                        */
+int llz_cuda_resample_bank_set_history(unsigned long handle, const short *d_hist,
+                                       long long stride, llz_cuda_stream_t stream);
+
+/* int16 planar in, int16 planar out, device pointers, asynchronous.  *n_out (host) receives the
+ * outputs per channel.  Equivalent to feeding the reference frame by frame when n_in is a
+ * multiple of num_in; any n_in is accepted for resample/decimate (interp: multiple of num_in,
+ * because the reference restarts its window at every frame, llz_resample.c:515-523).         */
+int llz_cuda_resample_bank_run(unsigned long handle, const short *d_in, long long in_stride,
+                               long long n_in, short *d_out, long long out_stride,
+                               long long *n_out, llz_cuda_stream_t stream);
+int llz_cuda_resample_bank_run_host(unsigned long handle, const short *h_in, long long in_stride,
+                                    long long n_in, short *h_out, long long out_stride,
+                                    long long *n_out);
+/* outputs that took the reference-order recompute (near-integer guard) since init/reset */
+long long llz_cuda_resample_bank_guard_count(unsigned long handle);
+
+/* ======================================================================================== */
+/* Shard planners (host integer arithmetic; no CUDA needed)                                  */
+/* ======================================================================================== */
+/* contiguous channel shards, remainder spread over the first ranks */
+int llz_cuda_shard_channels(int n_channels, int world, int rank, int *first, int *count);
+
+typedef struct {
+    long long in_start;    /* first input sample owned by this rank                           */
+    long long in_count;    /* owned input samples                                             */
+    long long halo;        /* samples before in_start this rank must also read (<= in_start)  */
+    long long out_start;   /* first output sample produced by this rank                       */
+    long long out_count;
+} llz_cuda_segment_t;
+
+/* FIR: split n samples into `world` contiguous segments; halo = flt_len-1 */
+int llz_cuda_shard_fir_segments(long long n, int flt_len, int world, int rank,
+                                llz_cuda_segment_t *seg);
+/* resample: split n_in (a multiple of `frame_in`, the handle's num_in) into whole-frame runs so
+ * that every segment starts at output index == 0 mod L (phase 0) and input index == 0 mod M/gcd;
+ * halo = taps_per_phase-1 */
+int llz_cuda_shard_resample_segments(long long n_in, int L, int M, int taps_per_phase,
+                                     int frame_in, int world, int rank, llz_cuda_segment_t *seg);
+
+/* ======================================================================================== */
+/* Synthetic signals and machine probes (bench / tests)                                      */
+/* ======================================================================================== */
+/* per-channel 32-bit LCG of SURVEY.md section 8d, generated on the device with jump-ahead:
+ * kind 0: double in [-1,1)   x = ((int)(s>>8) - 8388608) / 8388608.0
+ * kind 1: float, same value rounded to float
+ * kind 2: int16              x = (short)((int)(s>>17) - 16384)
+ * channel c uses seed0 + c; element i is the (i+1)-th LCG state.                             */
+int llz_cuda_synth_lcg(void *d_out, long long stride, int n_channels, long long n, int kind,
+                       unsigned seed0, llz_cuda_stream_t stream);
+/* register-resident FMA throughput of this GPU in TFLOP/s (dtype: LLZ_CUDA_F64 or LLZ_CUDA_F32) */
+int llz_cuda_probe_fma(int dtype, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* _LLZ_CUDA_H */

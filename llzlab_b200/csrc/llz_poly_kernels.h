@@ -1,0 +1,55 @@
+// llz_poly_kernels.h -- launch interface of the polyphase kernels (llz_cuda_resample.cu).
+//
+// Every resampler kind is run in the canonical form of llz_internal.h:
+//     y[o] = finish( sum_{k<ctaps} cbank[o % L][k] * X( floor(o*M/L) + shift - k ) )
+//     finish(a) = (short) clamp(a * gain, -32768, 32767)           (llz_resample.c:594-601)
+// X(s) is the stream sample with canonical index s: this call's input x[s - in0] when
+// 0 <= s - in0 < n_in, the stored history just before it, zero elsewhere; for interp
+// (frame_len > 0) samples at or beyond the end of the output's own input frame are zero.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "llz_cuda_common.cuh"
+
+namespace llz {
+
+struct PolyLaunch {
+    const int16_t *x;          // device planar input of this call (nullptr = zeros)
+    long long x_stride;
+    long long n_in;
+    const int16_t *hist;       // device [channels][hist_len]: samples just before x[0]; may be nullptr
+    int hist_len;
+    int16_t *y;
+    long long y_stride;
+    long long o0;              // canonical index of the first output of this call
+    long long n_out;
+    long long in0;             // canonical index of x[0]
+    int L, M, ctaps, shift, frame_len;
+    int acc;                   // LLZ_CUDA_ACC_*
+    double gain;
+    double guard_thr;          // |v - nearest integer| below this -> reference-order recompute
+    const double *cbank;       // [L][ctaps] row-major
+    const double *cbankT64;    // [ctaps][L]
+    const float *cbankT32;     // [ctaps][L]
+    const int *order;          // reference accumulation order, order_len canonical tap indices
+    int order_len;
+    const int *single_tap;     // [L]
+    // sliding (L == 1) kernel: per-residue tap rows, [M][slide_ntp], zero padded
+    const double *slide64;
+    const float *slide32;
+    int slide_ntp64, slide_ntp32;
+    unsigned long long *guard_count;
+};
+
+// picks the kernel (sliding for L == 1 when the tile fits, general otherwise) and launches it
+int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
+// name of the kernel poly_launch would pick ("sliding" / "general"), for reporting
+const char *poly_kernel_name(const PolyLaunch &a);
+
+// new history = last hist_len samples of (old history ++ x[0..n_in))
+int poly_update_history(const int16_t *x, long long x_stride, long long n_in, const int16_t *hist_old,
+                        int16_t *hist_new, int hist_len, int n_channels, cudaStream_t stream);
+
+}  // namespace llz

@@ -1,0 +1,80 @@
+// llz_sliding_mac.cuh -- the register-blocked sliding-window multiply-accumulate that every
+// "sliding" kernel of libllzfilter_cuda is built on (direct-form FIR, and each polyphase
+// branch of the decimating resampler).
+//
+// One thread owns R consecutive outputs  y[r] += sum_k h[k] * x[base + r - k],  r < R.
+// Taps are consumed in chunks of U = 16 bytes / sizeof(T) (one LDS.128, broadcast to the warp);
+// the R+U input samples a chunk touches live in registers as a ring of S = R/U + 1 slots of U
+// samples, and each chunk replaces exactly one slot with one LDS.128 -- so a chunk costs
+// R*U FMAs + 2 shared-memory loads (f32, R=28: 112 FFMA : 2 LDS).
+//
+// R/U is odd on purpose: neighbouring lanes start R/U 16-byte vectors apart, and an odd vector
+// stride makes every quarter-warp hit 8 distinct 16-byte bank groups -- conflict-free LDS.128
+// with a dense (unpadded, unswizzled) tile, which is what lets the tile arrive by one TMA bulk
+// copy.
+//
+// The chunk loop is unrolled S deep so every ring index is a compile-time constant.
+#pragma once
+
+#include "llz_cuda_common.cuh"
+
+namespace llz {
+
+template <typename T, int R>
+struct SlidingMac {
+    using V = typename Vec16<T>::type;
+    static constexpr int U = Vec16<T>::N;       // taps per chunk
+    static constexpr int S = R / U + 1;         // ring slots
+    static constexpr int GRAN = S * U;          // taps per unrolled iteration
+    static_assert(R % U == 0, "R must be a whole number of 16-byte vectors");
+    static_assert((R / U) % 2 == 1, "R/U must be odd (bank-conflict-free lane stride)");
+
+    // One chunk: ring slot for logical window index j (element j of the R+U samples, lowest
+    // address first) at chunk CC (mod S) is ((j/U - CC) mod S).
+    template <int CC, bool STRICT>
+    static __device__ __forceinline__ void chunk(T (&acc)[R], const T (&ring)[S * U], const T (&h)[U])
+    {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = r - u + U;                      // 1 .. R+U-1
+                const int slot = ((j / U) - CC + S) % S;
+                acc[r] = mac<T, STRICT>(h[u], ring[slot * U + (j % U)], acc[r]);
+            }
+        }
+    }
+
+    template <int CC, bool STRICT>
+    static __device__ __forceinline__ void step(T (&acc)[R], T (&ring)[S * U], const T *xp, const T *hp)
+    {
+        // refill the slot that becomes the lowest-address slot of this chunk
+        unpack(*reinterpret_cast<const V *>(xp - CC * U), &ring[((S - CC) % S) * U]);
+        T h[U];
+        unpack(*reinterpret_cast<const V *>(hp + CC * U), h);
+        chunk<CC, STRICT>(acc, ring, h);
+        if constexpr (CC + 1 < S) step<CC + 1, STRICT>(acc, ring, xp, hp);
+    }
+
+    // Accumulate `ntaps` taps (a multiple of GRAN; the tail of `taps` is zero-padded).
+    //   win  : shared-memory address of sample (base - U), i.e. one vector below the first output's
+    //          newest sample; 16-byte aligned.  Reads reach down to win - ntaps + U ... up to win+R+U-1.
+    //   taps : shared-memory tap array, taps[k] multiplies x[base + r - k]; 16-byte aligned.
+    template <bool STRICT>
+    static __device__ __forceinline__ void run(T (&acc)[R], const T *win, const T *taps, int ntaps)
+    {
+        T ring[S * U];
+#pragma unroll
+        for (int s = 1; s < S; ++s)
+            unpack(*reinterpret_cast<const V *>(win + s * U), &ring[s * U]);
+        const T *xp = win;
+        const T *hp = taps;
+        for (int k = 0; k < ntaps; k += GRAN) {
+            step<0, STRICT>(acc, ring, xp, hp);
+            xp -= GRAN;
+            hp += GRAN;
+        }
+    }
+};
+
+}  // namespace llz
