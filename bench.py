@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the llzlab FIR / resampling hot path on B200 (libllzfilter_cuda).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--dtype f64|f32]
+    python bench.py --impl reference ...        # the reference's own CPU code, all host threads
+
+One "step" = one pass of the hot path over one batch of synthetic input.  The default workload is
+BASELINE.json configs[1] (C2): llz_fir 127-tap low-pass on 1024 independent channels x 10 s @ 48 kHz,
+in the reference's sample type (double).  With N > 1 (torchrun, one rank per GPU) the channels are
+independent units: every rank runs its own 1024-channel batch, no data-path collective (weak scaling).
+
+The JSON line carries: value (device-timed, inputs resident in HBM), e2e (host buffers through the
+C-ABI, H2D + D2H inside the timed region), roofline (dominant kernel, algorithmic bytes and flops
+against measured / nominal peaks), cpu_baseline (the unmodified reference on one host core, bounded
+sample), clocks and gpu_launches.  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "output Msamples/s (device-timed)"
+UNIT = "Msamples/s"
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 37.2
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4
+
+# name -> description of the synthetic workload
+WORKLOADS = {
+    "c2": dict(kind="fir", desc="llz_fir 127-tap lowpass (fc 0.23, HAMMING), 1024 channels x 480000 samples (10 s @ 48 kHz)",
+               channels=1024, n=480_000, taps=127, fc=0.23, win=0, seed=12345),
+    "c5": dict(kind="fir", desc="llz_fir 4095-tap lowpass (fc 0.11, KAISER), 16 channels x 57.6 M samples (5 min @ 192 kHz slice of the 1 h stream)",
+               channels=16, n=57_600_000, taps=4095, fc=0.11, win=2, seed=12345),
+    "c3": dict(kind="resample", desc="llz_resample 48 kHz -> 16 kHz (L=1, M=3, BLACKMAN, Q=134), 64 channels x 28.8 M samples (10 min)",
+               channels=64, n=28_800_000, L=1, M=3, k=0, win=1, seed=777),
+    "c4": dict(kind="resample", desc="llz_resample 44.1 kHz -> 96 kHz (L=320, M=147, BLACKMAN, 256-tap bank: k=128, Q=257), 8 channels x 15.876 M samples (6 min slice of the 1 h stream)",
+               channels=8, n=47_040 * 338, L=320, M=147, k=128, win=1, seed=777),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- clocks --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons through NVML while the timed region runs"""
+
+    REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag = index, threading.Event()
+        self.samples, self.reasons, self.max_mhz, self.error = [], set(), None, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:                      # noqa: BLE001
+            self.error = repr(e)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.error:
+            out["error"] = self.error
+        return out
+
+
+# ---- the reference on host cores ---------------------------------------------------------------------------------
+def cpu_reference_rate(wl: dict, threads: int, channels_per_thread: int, n: int, repeats: int = 1):
+    """Msamples/s of the reference's own C code (oracle/_ref when present, else the oracle port) on
+    `threads` host threads, each filtering `channels_per_thread` channels of n samples frame by frame."""
+    import oracle
+    R, P = oracle.ref(), oracle.port()
+    kind = "reference" if R is not None else "port"
+    frame = 4096 if wl["kind"] == "fir" else None
+    outs = [0] * threads
+
+    def work(t):
+        total = 0
+        for c in range(channels_per_thread):
+            seed = wl["seed"] + t * channels_per_thread + c
+            if wl["kind"] == "fir":
+                nn = n // frame * frame
+                x = P.lcg_f64(nn, seed)
+                if R is not None:
+                    y = R.fir_stream(0, wl["taps"], wl["fc"], 0.0, wl["win"], x, frame)
+                else:
+                    y = P.fir_run(P.fir_design(0, wl["taps"], wl["fc"], 0.0, wl["win"]), x)
+                total += len(y)
+            else:
+                plan = P.resample_plan(wl["L"], wl["M"], wl["win"], wl["k"])
+                nn = n // plan.num_in * plan.num_in
+                x = P.lcg_s16(nn, seed)
+                if R is not None and wl["k"] == 0:
+                    y = R.resample_stream(wl["L"], wl["M"], 1.0, wl["win"], x)
+                else:                               # k_override is not expressible through the reference API
+                    y = P.resample_run(plan, 1.0, x, nn * wl["L"] // wl["M"])
+                total += len(y)
+        outs[t] = total
+
+    # inputs are generated inside the threads (LCG cost is ~1 % of the filtering cost at 127 taps)
+    best = None
+    for _ in range(repeats):
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sum(outs) / best / 1e6, kind, best
+
+
+def reference_sample_shape(wl: dict):
+    """(channels per thread, samples per channel) of one bounded reference step: ~0.5 s per thread"""
+    if wl["kind"] == "fir":
+        per_thread = 4.0e6 * 127 / wl["taps"]              # ~8 Msamples/s at 127 taps per core
+        n = min(wl["n"], 480_000)
+        return max(1, int(per_thread // n)), n
+    q = 134 if wl["L"] == 1 else (2 * wl["k"] + 1 if wl["k"] else 45)
+    per_thread_out = 2.5e6 * 134 / q
+    n_in = int(per_thread_out * wl["M"] / wl["L"])
+    return 1, max(50_000, n_in)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    cpt, n = reference_sample_shape(wl)
+    for _ in range(args.warmup):
+        cpu_reference_rate(wl, threads, 1, min(n, 65536))
+    rates, kind, total_t = [], "port", 0.0
+    for _ in range(args.steps):
+        r, kind, dt = cpu_reference_rate(wl, threads, cpt, n)
+        rates.append(r)
+        total_t += dt
+    value = statistics.mean(rates)
+    sample = f"per step: {threads} threads x {cpt} channel(s) x {n} input samples of the workload, one reference handle per channel"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if wl["kind"] == "fir" else "s16 io / f64 acc", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "timing": "host wall clock (CPU implementation, no device)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---- the CUDA arm ------------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import llzlab_b200 as z
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libllzfilter_cuda has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    z.lib()
+    wl = WORKLOADS[args.workload]
+    C_, n = wl["channels"], wl["n"]
+    stream = torch.cuda.current_stream().cuda_stream
+    hbm_peak, peak_src = peaks()
+
+    # ---- resident inputs (device LCG, the same integers the CPU arm generates) ----
+    if wl["kind"] == "fir":
+        f32 = args.dtype == "f32"
+        tdt, es = (torch.float32, 4) if f32 else (torch.float64, 8)
+        dx = torch.empty(C_, n, dtype=tdt, device="cuda")
+        z.synth_lcg(dx, n, C_, n, 1 if f32 else 0, wl["seed"], stream)
+        dy = torch.empty_like(dx)
+        bank = z.FirBank(C_, z.F32 if f32 else z.F64, kind=z.LPF, flt_len=wl["taps"], fc1=wl["fc"], win=wl["win"])
+        n_out = n
+        flop_per_out, bytes_per_out = 2.0 * wl["taps"], 2.0 * es
+        dtype_name = "f32" if f32 else "f64"
+        fma_peak_nominal = FP32_NOMINAL_TFLOPS if f32 else FP64_NOMINAL_TFLOPS
+        fma_dtype = z.F32 if f32 else z.F64
+        kernel = f"fir_tile_kernel<{'float' if f32 else 'double'}>"
+
+        def step():
+            bank.reset()
+            bank.run(dx, n, dy, n, n, stream)
+        launches_per_step = 2                       # fir_tile_kernel + fir_history_kernel
+    else:
+        acc = z.ACC_F32 if args.dtype == "f32" else z.ACC_F64
+        dx = torch.empty(C_, n, dtype=torch.int16, device="cuda")
+        z.synth_lcg(dx, n, C_, n, 2, wl["seed"], stream)
+        bank = z.ResampleBank(z.KIND_RESAMPLE, wl["L"], wl["M"], C_, win=wl["win"], k_override=wl["k"], acc=acc)
+        n_out = bank.out_len(n)
+        dy = torch.empty(C_, n_out, dtype=torch.int16, device="cuda")
+        q = bank.info.taps_per_phase
+        flop_per_out, bytes_per_out = 2.0 * q, 2.0 * (1.0 + wl["M"] / wl["L"])
+        dtype_name = "s16 io / f32 acc" if args.dtype == "f32" else "s16 io / f64 acc"
+        fma_peak_nominal = FP32_NOMINAL_TFLOPS if args.dtype == "f32" else FP64_NOMINAL_TFLOPS
+        fma_dtype = z.F32 if args.dtype == "f32" else z.F64
+        kernel = "poly_slide_kernel" if wl["L"] == 1 else "poly_general_kernel"
+
+        def step():
+            bank.reset()
+            bank.run(dx, n, n, dy, n_out, stream)
+        launches_per_step = 2
+    outs_per_step = C_ * n_out
+
+    fma_peak_measured = z.probe_fma(fma_dtype)
+
+    # ---- device-timed region ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.result()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * outs_per_step / (ms_step * 1e-3) / 1e6
+
+    # per-rank kernel figures (rank 0's own time for the roofline of the kernel)
+    ms_local = e0.elapsed_time(e1) / args.steps
+    ach_gbs = outs_per_step * bytes_per_out / (ms_local * 1e-3) / 1e9
+    ach_tf = outs_per_step * flop_per_out / (ms_local * 1e-3) / 1e12
+
+    # ---- end to end through the C-ABI with host buffers ----
+    e2e = None
+    try:
+        in_bytes, out_bytes = dx.numel() * dx.element_size(), dy.numel() * dy.element_size()
+        np_dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int16: np.int16}[dx.dtype]
+        hx = z.host_alloc(in_bytes, np_dt).reshape(C_, n)
+        hy = z.host_alloc(out_bytes, np_dt).reshape(C_, n_out)
+        torch.from_numpy(hx).copy_(dx)
+        torch.cuda.synchronize()
+        e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step():
+            bank.reset()
+            if wl["kind"] == "fir":
+                bank.run_host(hx, n, hy, n, n)
+            else:
+                bank.run_host(hx, n, n, hy, n_out)
+        e2e_step()                                  # warm-up: staging buffers, streams
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()                              # synchronous: result is in hy on return
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        # the result read back is the full output; verify it is the device-resident result
+        same = bool(np.array_equal(hy[0, :4096], dy[0, :4096].cpu().numpy()))
+        e2e = {"value": world * outs_per_step * e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+               "d2h_bytes_per_step": out_bytes, "steps": e_steps, "matches_device_result": same,
+               "api": "llz_cuda_fir_bank_run_host" if wl["kind"] == "fir" else "llz_cuda_resample_bank_run_host",
+               "host_memory": "page-locked (llz_cuda_host_alloc)"}
+        z.host_free(hx.reshape(-1))
+        z.host_free(hy.reshape(-1))
+    except Exception as ex:                         # noqa: BLE001
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline: the unmodified reference, one thread, bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        if wl["kind"] == "fir":
+            n_cpu = 480_000 if wl["taps"] < 1000 else 40_960
+            ch_cpu = max(1, int(1.0e8 * 127 / wl["taps"] / n_cpu))      # ~12 s at the probed 8.4 Msamples/s
+        else:
+            n_cpu, ch_cpu = reference_sample_shape(wl)[1] * 4, 6
+        rate, kind, dt = cpu_reference_rate(wl, 1, ch_cpu, n_cpu)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
+               "sample": f"{ch_cpu} channel(s) x {n_cpu} input samples of the workload, frame by frame through the reference API, 1 thread (the reference is single-threaded); host has {os.cpu_count()} logical cores"}
+
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(f"{args.workload}_{args.dtype}")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": dtype_name, "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload, "channels_per_gpu": C_, "samples_per_channel": n,
+                   "outputs_per_step_per_gpu": outs_per_step, "sharding": "independent channels per rank, no collective",
+                   "l2": f"inputs {dx.numel() * dx.element_size() / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
+                   "input": "integer LCG noise generated on the device (SURVEY.md 8d)"},
+        "roofline": {"kernel": kernel, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic": {"bytes_per_output": bytes_per_out, "flop_per_output": flop_per_out,
+                                     "outputs_per_launch": outs_per_step},
+                     "fma_pipe": {"achieved": ach_tf, "unit": "TFLOP/s", "peak_measured": fma_peak_measured,
+                                  "peak_nominal": fma_peak_nominal,
+                                  "frac_of_measured": ach_tf / fma_peak_measured if fma_peak_measured else None,
+                                  "frac_of_nominal": ach_tf / fma_peak_nominal,
+                                  "note": "direct-form FIR on CUDA cores: the FMA pipe, not HBM, is the binding roof "
+                                          f"(ceiling of the HBM fraction = {fma_peak_nominal * 1e12 / flop_per_out * bytes_per_out / 1e9 / hbm_peak:.3f})"}},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

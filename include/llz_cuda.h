@@ -23,6 +23,8 @@
 #ifndef _LLZ_CUDA_H
 #define _LLZ_CUDA_H
 
+#include <stddef.h>
+
 #include "llz_fir.h"
 #include "llz_resample.h"
 
@@ -36,6 +38,9 @@ typedef void *llz_cuda_stream_t;            /* a cudaStream_t; NULL = the legacy
 const char *llz_cuda_last_error(void);
 int         llz_cuda_device_count(void);    /* 0 when no usable CUDA device */
 const char *llz_cuda_build_info(void);      /* "libllzfilter_cuda <ver> sm_100a ..." */
+/* page-locked host memory for the *_run_host pipelines (pageable buffers work, but slower) */
+void       *llz_cuda_host_alloc(size_t bytes);
+void        llz_cuda_host_free(void *p);
 
 /* ---- selectors ------------------------------------------------------------------------- */
 enum {                                      /* FIR design kind (llz_fir.c:201-269) */

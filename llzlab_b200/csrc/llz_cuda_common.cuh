@@ -6,6 +6,9 @@
 
 #include "llz_internal.h"
 
+#define LLZ_STR2(x) #x
+#define LLZ_STR(x) LLZ_STR2(x)
+
 #define LLZ_CUDA_TRY(expr)                                                                    \
     do {                                                                                      \
         cudaError_t e__ = (expr);                                                             \

@@ -106,7 +106,7 @@ template <typename TA, int MODE>
 __global__ void __launch_bounds__(kPolyThreads)
 poly_general_kernel(PolyLaunch a, int tile_out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     TA *xs = reinterpret_cast<TA *>(smem_raw);
     __shared__ int s_peak;
     if (threadIdx.x == 0) s_peak = 0;

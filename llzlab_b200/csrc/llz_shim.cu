@@ -1,0 +1,1018 @@
+// llz_shim.cu -- the C-ABI of libllzfilter_cuda: handles, stream state and host<->device traffic.
+//
+// Two layers live here:
+//   * the llz_cuda_* bank entry points of include/llz_cuda.h (n_channels planar streams behind one
+//     handle, device pointers, asynchronous, plus chunked host-buffer pipelines);
+//   * the reference's own drop-in entry points (include/llz_fir.h, include/llz_resample.h): one
+//     mono stream per handle, host buffers, synchronous.  Each is a one-channel bank plus a pinned
+//     staging frame.  They replace libllzfilter/llz_fir.c:442-625 and llz_resample.c:271-617.
+//
+// Tap design and polyphase planning stay in host C (llz_design.c).  There is no CPU data path: every
+// sample goes through the kernels of llz_cuda_fir.cu / llz_cuda_resample.cu, and without a CUDA
+// device the *_init functions fail with (unsigned long)-1.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "llz_cuda_common.cuh"
+#include "llz_fir_kernels.h"
+#include "llz_poly_kernels.h"
+
+namespace {
+
+using namespace llz;
+
+constexpr unsigned long kFail = (unsigned long)-1;          // llz_resample.c:279
+constexpr uint32_t kMagicFir = 0x4C5A4649u;                 // "LZFI"
+constexpr uint32_t kMagicPoly = 0x4C5A5250u;                // "LZRP"
+
+// current-device guard: a handle always runs on the device it was created on
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            switched = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+size_t fir_elem_size(int dtype) { return dtype == LLZ_CUDA_F32 ? sizeof(float) : sizeof(double); }
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- host-buffer pipeline ------------------------------------------------------------------------
+// Three streams (H2D, compute, D2H) and kSlots staging slots on the device; chunk i uses slot
+// i % kSlots.  Events order slot reuse; the compute stream sees the chunks in time order, so the
+// bank's stream state (history, phase) advances exactly as in one long call.
+constexpr int kSlots = 3;
+
+struct Pipeline {
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    cudaEvent_t in_ready[kSlots] = {}, run_done[kSlots] = {}, out_done[kSlots] = {};
+    void *d_in[kSlots] = {}, *d_out[kSlots] = {};
+    size_t in_bytes = 0, out_bytes = 0;      // per slot
+    bool ok = false;
+
+    int create()
+    {
+        LLZ_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        LLZ_CUDA_TRY(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+        LLZ_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kSlots; ++i) {
+            LLZ_CUDA_TRY(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
+            LLZ_CUDA_TRY(cudaEventCreateWithFlags(&run_done[i], cudaEventDisableTiming));
+            LLZ_CUDA_TRY(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+        }
+        ok = true;
+        return 0;
+    }
+    int reserve(size_t need_in, size_t need_out)
+    {
+        if (!ok && create() != 0) return -1;
+        if (need_in > in_bytes) {
+            for (int i = 0; i < kSlots; ++i) {
+                if (d_in[i]) cudaFree(d_in[i]);
+                d_in[i] = nullptr;
+                LLZ_CUDA_TRY(cudaMalloc(&d_in[i], need_in));
+            }
+            in_bytes = need_in;
+        }
+        if (need_out > out_bytes) {
+            for (int i = 0; i < kSlots; ++i) {
+                if (d_out[i]) cudaFree(d_out[i]);
+                d_out[i] = nullptr;
+                LLZ_CUDA_TRY(cudaMalloc(&d_out[i], need_out));
+            }
+            out_bytes = need_out;
+        }
+        return 0;
+    }
+    void destroy()
+    {
+        for (int i = 0; i < kSlots; ++i) {
+            if (d_in[i]) cudaFree(d_in[i]);
+            if (d_out[i]) cudaFree(d_out[i]);
+            if (in_ready[i]) cudaEventDestroy(in_ready[i]);
+            if (run_done[i]) cudaEventDestroy(run_done[i]);
+            if (out_done[i]) cudaEventDestroy(out_done[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_run) cudaStreamDestroy(s_run);
+        if (s_out) cudaStreamDestroy(s_out);
+        *this = Pipeline();
+    }
+};
+
+// planar (strided rows) copy; cudaMemcpy2DAsync only takes pitches below 2 GiB, longer channels go row by row
+int copy_planar(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+                cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (width == 0 || rows == 0) return 0;
+    constexpr size_t kMaxPitch = 0x7fffffffu;
+    if (rows == 1) {
+        LLZ_CUDA_TRY(cudaMemcpyAsync(dst, src, width, kind, st));
+    } else if (dpitch <= kMaxPitch && spitch <= kMaxPitch) {
+        LLZ_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st));
+    } else {
+        for (size_t r = 0; r < rows; ++r)
+            LLZ_CUDA_TRY(cudaMemcpyAsync(static_cast<unsigned char *>(dst) + r * dpitch,
+                                         static_cast<const unsigned char *>(src) + r * spitch, width, kind, st));
+    }
+    return 0;
+}
+
+// samples per channel per chunk so that one slot (in + out) stays near 64 MiB
+long long pick_chunk(long long n, int n_channels, double bytes_per_in_sample)
+{
+    const double budget = 64.0 * 1024 * 1024;
+    long long c = (long long)(budget / (bytes_per_in_sample * n_channels));
+    c = (c / 4096) * 4096;
+    if (c < 4096) c = 4096;
+    if (c > n) c = n;
+    return c;
+}
+
+// ---- FIR bank --------------------------------------------------------------------------------------
+struct FirBank {
+    uint32_t magic = kMagicFir;
+    int device = 0;
+    int dtype = LLZ_CUDA_F64;
+    int n_channels = 1;
+    int flt_len = 0;
+    int hist_len = 0;            // flt_len - 1
+    int ntaps_pad = 0;
+    double *h_host = nullptr;    // flt_len doubles (malloc)
+    void *d_taps = nullptr;      // ntaps_pad elements of the bank's type, zero padded
+    void *d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool hist_zero = true;       // no launch needed to read zeros
+    Pipeline pipe;
+    // drop-in (mono, host buffers)
+    int frame_len = 0;
+    void *pinned = nullptr;      // frame_len elements
+    void *d_frame_in = nullptr, *d_frame_out = nullptr;
+    cudaStream_t s_frame = nullptr;
+};
+
+FirBank *as_fir(unsigned long handle)
+{
+    if (handle == 0 || handle == kFail) { llz_set_error("invalid FIR handle"); return nullptr; }
+    FirBank *b = reinterpret_cast<FirBank *>(handle);
+    if (b->magic != kMagicFir) { llz_set_error("handle is not a FIR handle"); return nullptr; }
+    return b;
+}
+
+void fir_destroy(FirBank *b)
+{
+    if (!b) return;
+    DeviceGuard g(b->device);
+    b->pipe.destroy();
+    if (b->d_taps) cudaFree(b->d_taps);
+    if (b->d_hist[0]) cudaFree(b->d_hist[0]);
+    if (b->d_hist[1]) cudaFree(b->d_hist[1]);
+    if (b->pinned) cudaFreeHost(b->pinned);
+    if (b->d_frame_in) cudaFree(b->d_frame_in);
+    if (b->d_frame_out) cudaFree(b->d_frame_out);
+    if (b->s_frame) cudaStreamDestroy(b->s_frame);
+    free(b->h_host);
+    b->magic = 0;
+    delete b;
+}
+
+int require_device(int *dev)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        llz_set_error("no usable CUDA device (%s); libllzfilter_cuda has no CPU path",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return -1;
+    }
+    LLZ_CUDA_TRY(cudaGetDevice(dev));
+    return 0;
+}
+
+// takes ownership of h (malloc'd, flt_len doubles)
+unsigned long fir_bank_create(double *h, int flt_len, int n_channels, int dtype)
+{
+    if (dtype != LLZ_CUDA_F64 && dtype != LLZ_CUDA_F64_STRICT && dtype != LLZ_CUDA_F32) {
+        llz_set_error("unknown FIR dtype %d", dtype);
+        free(h);
+        return kFail;
+    }
+    if (n_channels < 1 || n_channels > 65535 || flt_len < 1) {
+        llz_set_error("bad FIR bank shape: %d channels, %d taps", n_channels, flt_len);
+        free(h);
+        return kFail;
+    }
+    int dev = 0;
+    if (require_device(&dev) != 0) { free(h); return kFail; }
+    FirBank *b = new (std::nothrow) FirBank();
+    if (!b) { llz_set_error("out of memory"); free(h); return kFail; }
+    b->device = dev;
+    b->dtype = dtype;
+    b->n_channels = n_channels;
+    b->flt_len = flt_len;
+    b->hist_len = flt_len - 1;
+    b->h_host = h;
+    int variant = 0;
+    const size_t es = fir_elem_size(dtype);
+    b->ntaps_pad = (dtype == LLZ_CUDA_F32) ? fir_pad_taps<float>(flt_len, &variant)
+                                           : fir_pad_taps<double>(flt_len, &variant);
+    auto fail = [&](const char *what, cudaError_t e) {
+        llz_set_error("FIR bank init: %s failed: %s", what, cudaGetErrorString(e));
+        fir_destroy(b);
+        return kFail;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&b->d_taps, (size_t)b->ntaps_pad * es)) != cudaSuccess) return fail("cudaMalloc(taps)", e);
+    {
+        std::vector<unsigned char> staged((size_t)b->ntaps_pad * es, 0);
+        if (dtype == LLZ_CUDA_F32) {
+            float *t = reinterpret_cast<float *>(staged.data());
+            for (int i = 0; i < flt_len; ++i) t[i] = (float)h[i];
+        } else {
+            memcpy(staged.data(), h, sizeof(double) * (size_t)flt_len);
+        }
+        if ((e = cudaMemcpy(b->d_taps, staged.data(), staged.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return fail("cudaMemcpy(taps)", e);
+    }
+    if (b->hist_len > 0) {
+        const size_t hb = (size_t)b->hist_len * n_channels * es;
+        for (int i = 0; i < 2; ++i) {
+            if ((e = cudaMalloc(&b->d_hist[i], hb)) != cudaSuccess) return fail("cudaMalloc(history)", e);
+            if ((e = cudaMemset(b->d_hist[i], 0, hb)) != cudaSuccess) return fail("cudaMemset(history)", e);
+        }
+    }
+    return reinterpret_cast<unsigned long>(b);
+}
+
+template <typename T>
+int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride,
+                  long long n, cudaStream_t st)
+{
+    FirLaunch<T> a{};
+    a.x = static_cast<const T *>(d_in);
+    a.x_stride = in_stride;
+    a.y = static_cast<T *>(d_out);
+    a.y_stride = out_stride;
+    a.n = n;
+    a.hist = (b->hist_zero || b->hist_len == 0) ? nullptr : static_cast<const T *>(b->d_hist[b->cur]);
+    a.taps = static_cast<const T *>(b->d_taps);
+    a.ntaps = b->flt_len;
+    a.vec_ok = (d_in == nullptr || aligned16(d_in)) && aligned16(d_out) &&
+               (b->n_channels == 1 || ((in_stride * sizeof(T)) % 16 == 0 && (out_stride * sizeof(T)) % 16 == 0));
+    if (fir_launch<T>(a, b->n_channels, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) return -1;
+    if (b->hist_len > 0) {
+        const T *old = b->hist_zero ? nullptr : static_cast<const T *>(b->d_hist[b->cur]);
+        T *next = static_cast<T *>(b->d_hist[b->cur ^ 1]);
+        if (fir_update_history<T>(a.x, in_stride, n, old, next, b->hist_len, b->n_channels, st) != 0) return -1;
+        b->cur ^= 1;
+        b->hist_zero = false;
+    }
+    return 0;
+}
+
+int fir_run(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride, long long n,
+            cudaStream_t st)
+{
+    if (n < 0) { llz_set_error("negative sample count"); return -1; }
+    if (n == 0) return 0;
+    if (!d_out) { llz_set_error("null output pointer"); return -1; }
+    if (b->dtype == LLZ_CUDA_F32) return fir_run_typed<float>(b, d_in, in_stride, d_out, out_stride, n, st);
+    return fir_run_typed<double>(b, d_in, in_stride, d_out, out_stride, n, st);
+}
+
+// ---- polyphase bank ----------------------------------------------------------------------------------
+struct PolyBank {
+    uint32_t magic = kMagicPoly;
+    int device = 0;
+    int n_channels = 1;
+    int acc = LLZ_CUDA_ACC_F64;
+    double gain = 1.0;
+    llz_plan_t plan{};
+    // device copies of the plan
+    double *d_cbank = nullptr, *d_cbankT64 = nullptr, *d_slide64 = nullptr;
+    float *d_cbankT32 = nullptr, *d_slide32 = nullptr;
+    int *d_order = nullptr, *d_single = nullptr;
+    int slide_ntp64 = 0, slide_ntp32 = 0;
+    unsigned long long *d_guard = nullptr;
+    double guard_thr = 0.0;
+    // stream state
+    long long consumed = 0, produced = 0;
+    int16_t *d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool hist_zero = true;
+    Pipeline pipe;
+    // drop-in
+    int16_t *pinned_in = nullptr, *pinned_out = nullptr;
+    int16_t *d_frame_in = nullptr, *d_frame_out = nullptr;
+    cudaStream_t s_frame = nullptr;
+};
+
+PolyBank *as_poly(unsigned long handle)
+{
+    if (handle == 0 || handle == kFail) { llz_set_error("invalid resampler handle"); return nullptr; }
+    PolyBank *b = reinterpret_cast<PolyBank *>(handle);
+    if (b->magic != kMagicPoly) { llz_set_error("handle is not a resampler handle"); return nullptr; }
+    return b;
+}
+
+void poly_destroy(PolyBank *b)
+{
+    if (!b) return;
+    DeviceGuard g(b->device);
+    b->pipe.destroy();
+    cudaFree(b->d_cbank); cudaFree(b->d_cbankT64); cudaFree(b->d_slide64);
+    cudaFree(b->d_cbankT32); cudaFree(b->d_slide32);
+    cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
+    cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
+    if (b->pinned_in) cudaFreeHost(b->pinned_in);
+    if (b->pinned_out) cudaFreeHost(b->pinned_out);
+    cudaFree(b->d_frame_in); cudaFree(b->d_frame_out);
+    if (b->s_frame) cudaStreamDestroy(b->s_frame);
+    llz_plan_free(&b->plan);
+    b->magic = 0;
+    delete b;
+}
+
+template <typename T>
+int upload(T **dst, const std::vector<T> &src)
+{
+    LLZ_CUDA_TRY(cudaMalloc(dst, src.size() * sizeof(T)));
+    LLZ_CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int poly_upload_plan(PolyBank *b)
+{
+    const llz_plan_t &p = b->plan;
+    const size_t L = (size_t)p.crows, Q = (size_t)p.ctaps;
+    std::vector<double> cb(p.cbank, p.cbank + L * Q), t64(L * Q);
+    std::vector<float> t32(L * Q);
+    for (size_t r = 0; r < L; ++r)
+        for (size_t k = 0; k < Q; ++k) {
+            t64[k * L + r] = cb[r * Q + k];
+            t32[k * L + r] = (float)cb[r * Q + k];
+        }
+    if (upload(&b->d_cbank, cb) || upload(&b->d_cbankT64, t64) || upload(&b->d_cbankT32, t32)) return -1;
+    std::vector<int> order(p.order, p.order + Q), single(p.single_tap, p.single_tap + L);
+    if (upload(&b->d_order, order) || upload(&b->d_single, single)) return -1;
+
+    if (p.L == 1 && p.shift == 0 && p.frame_len == 0) {
+        // sliding kernel: row rho holds the taps k = i*M + rho, i = 0, 1, ... (llz_cuda_resample.cu)
+        const int M = p.M;
+        const int per = (int)((Q + M - 1) / M);
+        b->slide_ntp64 = (per + 15) / 16 * 16;
+        b->slide_ntp32 = (per + 31) / 32 * 32;
+        std::vector<double> s64((size_t)M * b->slide_ntp64, 0.0);
+        std::vector<float> s32((size_t)M * b->slide_ntp32, 0.f);
+        for (size_t k = 0; k < Q; ++k) {
+            const size_t rho = k % M, i = k / M;
+            s64[rho * b->slide_ntp64 + i] = cb[k];
+            s32[rho * b->slide_ntp32 + i] = (float)cb[k];
+        }
+        if (upload(&b->d_slide64, s64) || upload(&b->d_slide32, s32)) return -1;
+    }
+    LLZ_CUDA_TRY(cudaMalloc(&b->d_guard, sizeof(unsigned long long)));
+    LLZ_CUDA_TRY(cudaMemset(b->d_guard, 0, sizeof(unsigned long long)));
+    if (p.hist_len > 0) {
+        const size_t hb = (size_t)p.hist_len * b->n_channels * sizeof(int16_t);
+        for (int i = 0; i < 2; ++i) {
+            LLZ_CUDA_TRY(cudaMalloc(&b->d_hist[i], hb));
+            LLZ_CUDA_TRY(cudaMemset(b->d_hist[i], 0, hb));
+        }
+    }
+    // Guard threshold per unit of peak |sample|.  Two FP64 evaluations of the same Q-term dot
+    // product (any order, fused or not) each differ from the exact value by at most
+    // (Q+1)*u*sum|g*x| (u = 2^-53), the gain multiply adds |v|*u; so two evaluations of gain*sum
+    // differ by < 2*(Q+2)*u*|gain|*rowsum*peak.  A factor 4 of slack costs nothing (the guard fires
+    // on ~1e-9 of the outputs) and keeps the bound safe against second-order terms.
+    b->guard_thr = 4.0 * 2.0 * (double)(Q + 2) * ldexp(1.0, -53) * fabs(b->gain) * p.abs_row_sum;
+    return 0;
+}
+
+unsigned long poly_bank_create(int kind, int L, int M, double gain, win_t win, int k_override, int n_channels,
+                               int acc)
+{
+    if (acc != LLZ_CUDA_ACC_F64 && acc != LLZ_CUDA_ACC_F64_STRICT && acc != LLZ_CUDA_ACC_F32) {
+        llz_set_error("unknown accumulator mode %d", acc);
+        return kFail;
+    }
+    if (n_channels < 1 || n_channels > 65535) {
+        llz_set_error("bad channel count %d", n_channels);
+        return kFail;
+    }
+    llz_plan_t plan;
+    if (llz_plan_build(&plan, kind, L, M, win, k_override) != 0) return kFail;   // range checks first: no leak
+    int dev = 0;
+    if (require_device(&dev) != 0) { llz_plan_free(&plan); return kFail; }
+    PolyBank *b = new (std::nothrow) PolyBank();
+    if (!b) { llz_set_error("out of memory"); llz_plan_free(&plan); return kFail; }
+    b->device = dev;
+    b->n_channels = n_channels;
+    b->acc = acc;
+    b->gain = gain;
+    b->plan = plan;
+    if (poly_upload_plan(b) != 0) { poly_destroy(b); return kFail; }
+    return reinterpret_cast<unsigned long>(b);
+}
+
+long long poly_out_len(const PolyBank *b, long long n_in)
+{
+    const llz_plan_t &p = b->plan;
+    const long long total_in = b->consumed + n_in;
+    if (p.kind == LLZ_KIND_INTERP) return n_in * p.L;
+    if (p.kind == LLZ_KIND_DECIMATE) return total_in / p.M - b->produced;
+    // outputs m with floor(m*M/L) <= total_in-1  <=>  m < total_in*L/M
+    const long long total_out = (total_in * p.L + p.M - 1) / p.M;
+    return total_out - b->produced;
+}
+
+int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_in, int16_t *d_out,
+             long long out_stride, long long *n_out, cudaStream_t st)
+{
+    const llz_plan_t &p = b->plan;
+    if (n_in < 0) { llz_set_error("negative sample count"); return -1; }
+    if (p.frame_len > 0 && n_in % p.frame_len != 0) {
+        llz_set_error("interp input must be whole frames of %d samples (got %lld)", p.frame_len, n_in);
+        return -1;
+    }
+    const long long outs = poly_out_len(b, n_in);
+    if (n_out) *n_out = outs;
+    if (n_in == 0) return 0;
+    if (outs > 0 && !d_out) { llz_set_error("null output pointer"); return -1; }
+
+    PolyLaunch a{};
+    a.x = d_in;
+    a.x_stride = in_stride;
+    a.n_in = n_in;
+    a.hist = (b->hist_zero || p.hist_len == 0) ? nullptr : b->d_hist[b->cur];
+    a.hist_len = p.hist_len;
+    a.y = d_out;
+    a.y_stride = out_stride;
+    a.o0 = b->produced;
+    a.n_out = outs;
+    a.in0 = b->consumed;
+    a.L = p.L; a.M = p.M; a.ctaps = p.ctaps; a.shift = p.shift; a.frame_len = p.frame_len;
+    a.acc = b->acc;
+    a.gain = b->gain;
+    a.guard_thr = b->guard_thr;
+    a.cbank = b->d_cbank;
+    a.cbankT64 = b->d_cbankT64;
+    a.cbankT32 = b->d_cbankT32;
+    a.order = b->d_order;
+    a.order_len = p.ctaps;
+    a.single_tap = b->d_single;
+    a.slide64 = b->d_slide64;
+    a.slide32 = b->d_slide32;
+    a.slide_ntp64 = b->slide_ntp64;
+    a.slide_ntp32 = b->slide_ntp32;
+    a.guard_count = b->d_guard;
+    if (poly_launch(a, b->n_channels, st) != 0) return -1;
+    if (p.hist_len > 0) {
+        const int16_t *old = b->hist_zero ? nullptr : b->d_hist[b->cur];
+        if (poly_update_history(d_in, in_stride, n_in, old, b->d_hist[b->cur ^ 1], p.hist_len, b->n_channels, st) != 0)
+            return -1;
+        b->cur ^= 1;
+        b->hist_zero = false;
+    }
+    b->consumed += n_in;
+    b->produced += outs;
+    return 0;
+}
+
+int poly_reset(PolyBank *b)
+{
+    b->consumed = 0;
+    b->produced = 0;
+    b->hist_zero = true;
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================================================
+// runtime
+// ====================================================================================================
+extern "C" int llz_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *llz_cuda_build_info(void)
+{
+    return "libllzfilter_cuda 0.1 sm_100a (CUDA " LLZ_STR(CUDART_VERSION) "), built " __DATE__;
+}
+
+extern "C" void *llz_cuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        llz_set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void llz_cuda_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ====================================================================================================
+// FIR banks
+// ====================================================================================================
+extern "C" unsigned long llz_cuda_fir_bank_init(int kind, int flt_len, double fc1, double fc2, win_t win_type,
+                                                int n_channels, int dtype)
+{
+    double *h = nullptr;
+    const int n = llz_design_taps(&h, kind, flt_len, fc1, fc2, win_type);
+    if (n < 0) return kFail;
+    return fir_bank_create(h, n, n_channels, dtype);
+}
+
+extern "C" unsigned long llz_cuda_fir_bank_init_taps(const double *h, int flt_len, int n_channels, int dtype)
+{
+    if (!h || flt_len < 1) { llz_set_error("fir_bank_init_taps: null or empty taps"); return kFail; }
+    double *copy = (double *)malloc(sizeof(double) * (size_t)flt_len);
+    if (!copy) { llz_set_error("out of memory"); return kFail; }
+    memcpy(copy, h, sizeof(double) * (size_t)flt_len);
+    return fir_bank_create(copy, flt_len, n_channels, dtype);
+}
+
+extern "C" void llz_cuda_fir_bank_uninit(unsigned long handle)
+{
+    FirBank *b = as_fir(handle);
+    if (b) fir_destroy(b);
+}
+
+extern "C" int llz_cuda_fir_bank_flt_len(unsigned long handle)
+{
+    FirBank *b = as_fir(handle);
+    return b ? b->flt_len : -1;
+}
+
+extern "C" int llz_cuda_fir_bank_copy_taps(unsigned long handle, double *h_out)
+{
+    FirBank *b = as_fir(handle);
+    if (!b || !h_out) return -1;
+    memcpy(h_out, b->h_host, sizeof(double) * (size_t)b->flt_len);
+    return b->flt_len;
+}
+
+extern "C" int llz_cuda_fir_bank_reset(unsigned long handle, llz_cuda_stream_t stream)
+{
+    (void)stream;
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    b->hist_zero = true;
+    return 0;
+}
+
+extern "C" int llz_cuda_fir_bank_set_history(unsigned long handle, const void *d_hist, long long stride,
+                                             llz_cuda_stream_t stream)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (b->hist_len == 0) return 0;
+    if (!d_hist) { b->hist_zero = true; return 0; }
+    DeviceGuard g(b->device);
+    const size_t es = fir_elem_size(b->dtype);
+    if (copy_planar(b->d_hist[b->cur], (size_t)b->hist_len * es, d_hist, (size_t)stride * es,
+                                   (size_t)b->hist_len * es, (size_t)b->n_channels, cudaMemcpyDeviceToDevice,
+                                   (cudaStream_t)stream) != 0) return -1;
+    b->hist_zero = false;
+    return 0;
+}
+
+extern "C" int llz_cuda_fir_bank_run(unsigned long handle, const void *d_in, long long in_stride, void *d_out,
+                                     long long out_stride, long long n, llz_cuda_stream_t stream)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (!d_in && n > 0) { llz_set_error("null input pointer"); return -1; }
+    DeviceGuard g(b->device);
+    return fir_run(b, d_in, in_stride, d_out, out_stride, n, (cudaStream_t)stream);
+}
+
+extern "C" int llz_cuda_fir_bank_flush(unsigned long handle, void *d_out, long long out_stride,
+                                       llz_cuda_stream_t stream)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (b->hist_len == 0) return 0;
+    DeviceGuard g(b->device);
+    // a run over flt_len-1 zero samples: llz_fir.c:604-621
+    if (fir_run(b, nullptr, 0, d_out, out_stride, b->hist_len, (cudaStream_t)stream) != 0) return -1;
+    b->hist_zero = true;
+    return b->hist_len;
+}
+
+extern "C" int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in, long long in_stride,
+                                          void *h_out, long long out_stride, long long n)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (n < 0 || (n > 0 && (!h_in || !h_out))) { llz_set_error("run_host: bad arguments"); return -1; }
+    if (n == 0) return 0;
+    DeviceGuard g(b->device);
+    const size_t es = fir_elem_size(b->dtype);
+    const int C = b->n_channels;
+    const long long chunk = pick_chunk(n, C, 2.0 * es);
+    Pipeline &P = b->pipe;
+    if (P.reserve((size_t)chunk * C * es, (size_t)chunk * C * es) != 0) return -1;
+    const unsigned char *src = static_cast<const unsigned char *>(h_in);
+    unsigned char *dst = static_cast<unsigned char *>(h_out);
+    long long idx = 0;
+    for (long long t0 = 0; t0 < n; t0 += chunk, ++idx) {
+        const long long len = (n - t0 < chunk) ? n - t0 : chunk;
+        const int s = (int)(idx % kSlots);
+        if (idx >= kSlots) {
+            LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_in, P.run_done[s], 0));     // input slot consumed
+            LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_run, P.out_done[s], 0));    // output slot drained
+        }
+        if (copy_planar(P.d_in[s], (size_t)chunk * es, src + (size_t)t0 * es, (size_t)in_stride * es,
+                                       (size_t)len * es, (size_t)C, cudaMemcpyHostToDevice, P.s_in) != 0) return -1;
+        LLZ_CUDA_TRY(cudaEventRecord(P.in_ready[s], P.s_in));
+        LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_run, P.in_ready[s], 0));
+        if (fir_run(b, P.d_in[s], chunk, P.d_out[s], chunk, len, P.s_run) != 0) return -1;
+        LLZ_CUDA_TRY(cudaEventRecord(P.run_done[s], P.s_run));
+        LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_out, P.run_done[s], 0));
+        if (copy_planar(dst + (size_t)t0 * es, (size_t)out_stride * es, P.d_out[s], (size_t)chunk * es,
+                                       (size_t)len * es, (size_t)C, cudaMemcpyDeviceToHost, P.s_out) != 0) return -1;
+        LLZ_CUDA_TRY(cudaEventRecord(P.out_done[s], P.s_out));
+    }
+    LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_out));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_run));
+    return 0;
+}
+
+// ====================================================================================================
+// resampler banks
+// ====================================================================================================
+extern "C" unsigned long llz_cuda_resample_bank_init(int L, int M, double gain, win_t win_type, int k_override,
+                                                     int n_channels, int acc)
+{
+    return poly_bank_create(LLZ_KIND_RESAMPLE, L, M, gain, win_type, k_override, n_channels, acc);
+}
+
+extern "C" unsigned long llz_cuda_decimate_bank_init(int M, double gain, win_t win_type, int n_channels, int acc)
+{
+    return poly_bank_create(LLZ_KIND_DECIMATE, 1, M, gain, win_type, 0, n_channels, acc);
+}
+
+extern "C" unsigned long llz_cuda_interp_bank_init(int L, double gain, win_t win_type, int n_channels, int acc)
+{
+    return poly_bank_create(LLZ_KIND_INTERP, L, 1, gain, win_type, 0, n_channels, acc);
+}
+
+extern "C" void llz_cuda_resample_bank_uninit(unsigned long handle)
+{
+    PolyBank *b = as_poly(handle);
+    if (b) poly_destroy(b);
+}
+
+extern "C" int llz_cuda_resample_bank_info(unsigned long handle, llz_cuda_resample_info_t *info)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b || !info) return -1;
+    const llz_plan_t &p = b->plan;
+    info->kind = p.kind;
+    info->L = p.L;
+    info->M = p.M;
+    info->n = p.n;
+    info->taps_per_phase = p.cols;
+    info->num_in = p.num_in;
+    info->num_out = p.num_out;
+    info->n_channels = b->n_channels;
+    info->acc = b->acc;
+    return 0;
+}
+
+extern "C" int llz_cuda_resample_bank_copy_proto(unsigned long handle, double *h_out)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b || !h_out) return -1;
+    memcpy(h_out, b->plan.proto, sizeof(double) * (size_t)b->plan.n);
+    return b->plan.n;
+}
+
+extern "C" int llz_cuda_resample_bank_copy_bank(unsigned long handle, double *bank_out)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b || !bank_out) return -1;
+    const size_t cnt = (size_t)b->plan.rows * b->plan.cols;
+    memcpy(bank_out, b->plan.bank, sizeof(double) * cnt);
+    return (int)cnt;
+}
+
+extern "C" long long llz_cuda_resample_bank_out_len(unsigned long handle, long long n_in)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b || n_in < 0) return -1;
+    return poly_out_len(b, n_in);
+}
+
+extern "C" int llz_cuda_resample_bank_reset(unsigned long handle, llz_cuda_stream_t stream)
+{
+    (void)stream;
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    return poly_reset(b);
+}
+
+extern "C" int llz_cuda_resample_bank_set_history(unsigned long handle, const short *d_hist, long long stride,
+                                                  llz_cuda_stream_t stream)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    poly_reset(b);
+    if (b->plan.hist_len == 0 || !d_hist) return 0;
+    DeviceGuard g(b->device);
+    const size_t row = (size_t)b->plan.hist_len * sizeof(int16_t);
+    if (copy_planar(b->d_hist[b->cur], row, d_hist, (size_t)stride * sizeof(int16_t), row,
+                                   (size_t)b->n_channels, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != 0) return -1;
+    b->hist_zero = false;
+    return 0;
+}
+
+extern "C" int llz_cuda_resample_bank_run(unsigned long handle, const short *d_in, long long in_stride,
+                                          long long n_in, short *d_out, long long out_stride, long long *n_out,
+                                          llz_cuda_stream_t stream)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    if (!d_in && n_in > 0) { llz_set_error("null input pointer"); return -1; }
+    DeviceGuard g(b->device);
+    return poly_run(b, d_in, in_stride, n_in, d_out, out_stride, n_out, (cudaStream_t)stream);
+}
+
+extern "C" int llz_cuda_resample_bank_run_host(unsigned long handle, const short *h_in, long long in_stride,
+                                               long long n_in, short *h_out, long long out_stride,
+                                               long long *n_out)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    if (n_in < 0 || (n_in > 0 && (!h_in || !h_out))) { llz_set_error("run_host: bad arguments"); return -1; }
+    if (n_out) *n_out = poly_out_len(b, n_in);
+    if (n_in == 0) return 0;
+    DeviceGuard g(b->device);
+    const llz_plan_t &p = b->plan;
+    const int C = b->n_channels;
+    const double ratio = (double)p.L / p.M;
+    // chunk: whole reference frames (keeps interp legal and every chunk's output count exact)
+    long long chunk = pick_chunk(n_in, C, 2.0 * (1.0 + ratio));
+    if (chunk < n_in) {
+        chunk = chunk / p.num_in * p.num_in;
+        if (chunk < p.num_in) chunk = p.num_in;
+    }
+    const long long chunk_out = (long long)ceil((double)chunk * ratio) + 2;
+    Pipeline &P = b->pipe;
+    if (P.reserve((size_t)chunk * C * 2, (size_t)chunk_out * C * 2) != 0) return -1;
+    long long idx = 0, out_pos = 0;
+    for (long long t0 = 0; t0 < n_in; t0 += chunk, ++idx) {
+        const long long len = (n_in - t0 < chunk) ? n_in - t0 : chunk;
+        const int s = (int)(idx % kSlots);
+        if (idx >= kSlots) {
+            LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_in, P.run_done[s], 0));
+            LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_run, P.out_done[s], 0));
+        }
+        if (copy_planar(P.d_in[s], (size_t)chunk * 2, h_in + t0, (size_t)in_stride * 2, (size_t)len * 2,
+                                       (size_t)C, cudaMemcpyHostToDevice, P.s_in) != 0) return -1;
+        LLZ_CUDA_TRY(cudaEventRecord(P.in_ready[s], P.s_in));
+        LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_run, P.in_ready[s], 0));
+        long long outs = 0;
+        if (poly_run(b, (const int16_t *)P.d_in[s], chunk, len, (int16_t *)P.d_out[s], chunk_out, &outs, P.s_run) != 0)
+            return -1;
+        LLZ_CUDA_TRY(cudaEventRecord(P.run_done[s], P.s_run));
+        LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_out, P.run_done[s], 0));
+        if (outs > 0)
+            if (copy_planar(h_out + out_pos, (size_t)out_stride * 2, P.d_out[s], (size_t)chunk_out * 2,
+                                           (size_t)outs * 2, (size_t)C, cudaMemcpyDeviceToHost, P.s_out) != 0) return -1;
+        LLZ_CUDA_TRY(cudaEventRecord(P.out_done[s], P.s_out));
+        out_pos += outs;
+    }
+    LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_out));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_run));
+    return 0;
+}
+
+extern "C" long long llz_cuda_resample_bank_guard_count(unsigned long handle)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    DeviceGuard g(b->device);
+    unsigned long long v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return -1; }
+    LLZ_CUDA_TRY(cudaMemcpy(&v, b->d_guard, sizeof v, cudaMemcpyDeviceToHost));
+    return (long long)v;
+}
+
+// ====================================================================================================
+// drop-in FIR handles (llz_fir.h): replaces llz_fir.c:442-625
+// ====================================================================================================
+namespace {
+
+unsigned long fir_dropin_init(int kind, int frame_len, int flt_len, double fc1, double fc2, win_t win)
+{
+    if (frame_len < 1) { llz_set_error("frame_len must be positive (got %d)", frame_len); return kFail; }
+    // the reference accumulates with separate multiply and add in tap order; the strict mode does the
+    // same on the GPU, so the drop-in output is bit-identical (PCIe, not the FP64 pipe, bounds a mono handle)
+    unsigned long h = llz_cuda_fir_bank_init(kind, flt_len, fc1, fc2, win, 1, LLZ_CUDA_F64_STRICT);
+    if (h == kFail) return kFail;
+    FirBank *b = reinterpret_cast<FirBank *>(h);
+    DeviceGuard g(b->device);
+    b->frame_len = frame_len;
+    const int cap = frame_len > b->hist_len ? frame_len : b->hist_len;     // flush emits flt_len-1 samples
+    cudaError_t e;
+    if ((e = cudaHostAlloc(&b->pinned, sizeof(double) * (size_t)cap, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_frame_in, sizeof(double) * (size_t)cap)) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_frame_out, sizeof(double) * (size_t)cap)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->s_frame, cudaStreamNonBlocking)) != cudaSuccess) {
+        llz_set_error("FIR handle init: %s", cudaGetErrorString(e));
+        fir_destroy(b);
+        return kFail;
+    }
+    return h;
+}
+
+}  // namespace
+
+extern "C" unsigned long llz_fir_filter_lpf_init(int frame_len, int flt_len, double fc, win_t win_type)
+{
+    return fir_dropin_init(LLZ_CUDA_LPF, frame_len, flt_len, fc, 0.0, win_type);
+}
+
+extern "C" unsigned long llz_fir_filter_hpf_init(int frame_len, int flt_len, double fc, win_t win_type)
+{
+    return fir_dropin_init(LLZ_CUDA_HPF, frame_len, flt_len, fc, 0.0, win_type);
+}
+
+extern "C" unsigned long llz_fir_filter_bandpass_init(int frame_len, int flt_len, double fc1, double fc2,
+                                                      win_t win_type)
+{
+    return fir_dropin_init(LLZ_CUDA_BPF, frame_len, flt_len, fc1, fc2, win_type);
+}
+
+extern "C" unsigned long llz_fir_filter_bandstop_init(int frame_len, int flt_len, double fc1, double fc2,
+                                                      win_t win_type)
+{
+    return fir_dropin_init(LLZ_CUDA_BSF, frame_len, flt_len, fc1, fc2, win_type);
+}
+
+extern "C" void llz_fir_filter_uninit(unsigned long handle)
+{
+    FirBank *b = as_fir(handle);
+    if (b) fir_destroy(b);
+}
+
+extern "C" int llz_fir_filter(unsigned long handle, double *buf_in, double *buf_out, int frame_len)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (!b->pinned) { llz_set_error("llz_fir_filter needs a handle from llz_fir_filter_*_init"); return -1; }
+    if (frame_len < 0 || frame_len > b->frame_len) {           // the reference asserts (llz_fir.c:559)
+        llz_set_error("frame_len %d exceeds the handle's %d", frame_len, b->frame_len);
+        return -1;
+    }
+    if (frame_len == 0) return 0;
+    DeviceGuard g(b->device);
+    const size_t bytes = sizeof(double) * (size_t)frame_len;
+    memcpy(b->pinned, buf_in, bytes);
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->d_frame_in, b->pinned, bytes, cudaMemcpyHostToDevice, b->s_frame));
+    if (fir_run(b, b->d_frame_in, 0, b->d_frame_out, 0, frame_len, b->s_frame) != 0) return -1;
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned, b->d_frame_out, bytes, cudaMemcpyDeviceToHost, b->s_frame));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    memcpy(buf_out, b->pinned, bytes);
+    return frame_len;                                           // llz_fir.c:582
+}
+
+extern "C" int llz_fir_filter_flush(unsigned long handle, double *buf_out)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (!b->pinned) { llz_set_error("llz_fir_filter_flush needs a handle from llz_fir_filter_*_init"); return -1; }
+    if (b->hist_len == 0) return 0;
+    DeviceGuard g(b->device);
+    const size_t bytes = sizeof(double) * (size_t)b->hist_len;
+    if (fir_run(b, nullptr, 0, b->d_frame_out, 0, b->hist_len, b->s_frame) != 0) return -1;
+    b->hist_zero = true;
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned, b->d_frame_out, bytes, cudaMemcpyDeviceToHost, b->s_frame));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    memcpy(buf_out, b->pinned, bytes);
+    return b->hist_len;                                         // llz_fir.c:624
+}
+
+// ====================================================================================================
+// drop-in resampler handles (llz_resample.h): replaces llz_resample.c:271-617
+// ====================================================================================================
+namespace {
+
+unsigned long poly_dropin_init(int kind, int L, int M, double gain, win_t win)
+{
+    // FP64 FMA + near-integer guard: bit-identical int16 (see llz_cuda_resample.cu)
+    unsigned long h = poly_bank_create(kind, L, M, gain, win, 0, 1, LLZ_CUDA_ACC_F64);
+    if (h == kFail) return kFail;
+    PolyBank *b = reinterpret_cast<PolyBank *>(h);
+    DeviceGuard g(b->device);
+    const size_t in_b = sizeof(int16_t) * (size_t)b->plan.num_in, out_b = sizeof(int16_t) * (size_t)b->plan.num_out;
+    cudaError_t e;
+    if ((e = cudaHostAlloc((void **)&b->pinned_in, in_b, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&b->pinned_out, out_b, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&b->d_frame_in, in_b)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&b->d_frame_out, out_b)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->s_frame, cudaStreamNonBlocking)) != cudaSuccess) {
+        llz_set_error("resampler handle init: %s", cudaGetErrorString(e));
+        poly_destroy(b);
+        return kFail;
+    }
+    return h;
+}
+
+int poly_dropin_frame(unsigned long handle, int kind, unsigned char *sample_in, int sample_in_size,
+                      unsigned char *sample_out, int *sample_out_size)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    if (!b->pinned_in) { llz_set_error("handle was not created by a llz_*_init drop-in"); return -1; }
+    if (b->plan.kind != kind) { llz_set_error("handle kind %d used with entry point of kind %d", b->plan.kind, kind); return -1; }
+    const int bytes_in = b->plan.num_in * 2, bytes_out = b->plan.num_out * 2;
+    if (sample_in_size != bytes_in) {                           // the reference asserts (llz_resample.c:443,507,560)
+        llz_set_error("frame is %d bytes, handle expects %d", sample_in_size, bytes_in);
+        return -1;
+    }
+    DeviceGuard g(b->device);
+    memcpy(b->pinned_in, sample_in, (size_t)bytes_in);
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->d_frame_in, b->pinned_in, (size_t)bytes_in, cudaMemcpyHostToDevice, b->s_frame));
+    long long outs = 0;
+    if (poly_run(b, b->d_frame_in, 0, b->plan.num_in, b->d_frame_out, 0, &outs, b->s_frame) != 0) return -1;
+    if (outs != b->plan.num_out) { llz_set_error("internal: frame produced %lld samples, expected %d", outs, b->plan.num_out); return -1; }
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned_out, b->d_frame_out, (size_t)bytes_out, cudaMemcpyDeviceToHost, b->s_frame));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    memcpy(sample_out, b->pinned_out, (size_t)bytes_out);
+    if (sample_out_size) *sample_out_size = bytes_out;          // llz_resample.c:605
+    return 0;
+}
+
+}  // namespace
+
+extern "C" unsigned long llz_decimate_init(int M, double gain, win_t win_type)
+{
+    return poly_dropin_init(LLZ_KIND_DECIMATE, 1, M, gain, win_type);
+}
+
+extern "C" unsigned long llz_interp_init(int L, double gain, win_t win_type)
+{
+    return poly_dropin_init(LLZ_KIND_INTERP, L, 1, gain, win_type);
+}
+
+extern "C" unsigned long llz_resample_filter_init(int L, int M, double gain, win_t win_type)
+{
+    return poly_dropin_init(LLZ_KIND_RESAMPLE, L, M, gain, win_type);
+}
+
+// any *_uninit accepts any resampler handle (the reference CLI calls llz_resample_filter_uninit on all
+// three kinds, main.c:125)
+extern "C" void llz_decimate_uninit(unsigned long handle) { llz_cuda_resample_bank_uninit(handle); }
+extern "C" void llz_interp_uninit(unsigned long handle) { llz_cuda_resample_bank_uninit(handle); }
+extern "C" void llz_resample_filter_uninit(unsigned long handle) { llz_cuda_resample_bank_uninit(handle); }
+
+extern "C" int llz_get_resample_framelen_bytes(unsigned long handle)
+{
+    PolyBank *b = as_poly(handle);
+    return b ? b->plan.num_in * 2 : -1;                         // llz_resample.c:612-617
+}
+
+extern "C" int llz_decimate(unsigned long handle, unsigned char *sample_in, int sample_in_size,
+                            unsigned char *sample_out, int *sample_out_size)
+{
+    return poly_dropin_frame(handle, LLZ_KIND_DECIMATE, sample_in, sample_in_size, sample_out, sample_out_size);
+}
+
+extern "C" int llz_interp(unsigned long handle, unsigned char *sample_in, int sample_in_size,
+                          unsigned char *sample_out, int *sample_out_size)
+{
+    return poly_dropin_frame(handle, LLZ_KIND_INTERP, sample_in, sample_in_size, sample_out, sample_out_size);
+}
+
+extern "C" int llz_resample(unsigned long handle, unsigned char *sample_in, int sample_in_size,
+                            unsigned char *sample_out, int *sample_out_size)
+{
+    return poly_dropin_frame(handle, LLZ_KIND_RESAMPLE, sample_in, sample_in_size, sample_out, sample_out_size);
+}

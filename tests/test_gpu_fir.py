@@ -1,0 +1,240 @@
+"""FIR parity on the GPU, through the C-ABI of libllzfilter_cuda.so, against the oracle.
+
+Tolerances (SURVEY.md 8d note 4 / BASELINE.json north_star):
+  drop-in llz_fir_filter and F64_STRICT banks : bit-identical doubles
+  F64 banks (FMA)                             : max |err| <= 1e-12 relative to full scale
+  F32 banks                                   : SNR >= 120 dB and max |err| <= 1e-5 of full scale
+"""
+import numpy as np
+import pytest
+
+from conftest import KIND, WIN
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64 = 1e-12
+TOL_F32_ABS = 1e-5
+SNR_F32_DB = 120.0
+
+
+def snr_db(want, got):
+    err = (got.astype(np.float64) - want).ravel()
+    return 10 * np.log10((want.ravel() ** 2).sum() / max((err ** 2).sum(), 1e-300))
+
+
+def oracle_bank(port, h, x, n_out=None):
+    return np.stack([port.fir_run(h, x[c], n_out=n_out) for c in range(x.shape[0])])
+
+
+def test_dropin_streams_match_golden_hashes(zlib, port, kat, cuda):
+    """llz_fir_filter frame by frame + flush == the reference's bytes (hash from the unmodified reference)."""
+    for c in kat["fir_streams"]:
+        f = zlib.FirFilter(KIND[c["kind"]], c["frame"], c["N"], c["fc1"], c["fc2"], WIN[c["win"]])
+        x = port.lcg_f64(c["frame"] * c["frames"], c["seed"])
+        parts = [f.filter(x[i:i + c["frame"]]) for i in range(0, len(x), c["frame"])]
+        parts.append(f.flush())
+        y = np.concatenate(parts)
+        f.close()
+        assert len(y) == c["n_out"]
+        assert f"{port.fnv64(y):016x}" == c["fnv"], c
+        assert y[0] == c["y0"] and y[-1] == c["ylast"]
+
+
+def test_dropin_short_last_frame_and_aliasing(zlib, port, cuda):
+    h = port.fir_design(0, 63, 0.3, 0.0, 1)
+    x = port.lcg_f64(256 * 3 + 100, 5)
+    want = port.fir_run(h, x)
+    f = zlib.FirFilter(0, 256, 63, 0.3, 0.0, 1)
+    got = np.concatenate([f.filter(x[i:i + 256]) for i in range(0, len(x), 256)])
+    assert got.tobytes() == want.tobytes()
+    # in-place call (the reference copies the input first, llz_fir.c:565-566)
+    f2 = zlib.FirFilter(0, 256, 63, 0.3, 0.0, 1)
+    buf = x[:256].copy()
+    rc = zlib.lib().llz_fir_filter(f2.handle, buf.ctypes.data, buf.ctypes.data, 256)
+    assert rc == 256 and buf.tobytes() == want[:256].tobytes()
+    # a frame longer than the handle's is rejected, not asserted
+    big = np.zeros(300)
+    assert zlib.lib().llz_fir_filter(f2.handle, big.ctypes.data, big.ctypes.data, 300) == -1
+    f.close(); f2.close()
+
+
+@pytest.mark.parametrize("N", [1, 2, 15, 16, 17, 33, 64, 127, 128, 255, 1000, 4095])
+def test_bank_f64_all_tap_counts(zlib, port, cuda, N):
+    torch = cuda
+    rng = np.random.default_rng(N)
+    h = rng.standard_normal(N) / max(N, 1) ** 0.5
+    C_, n = 3, 9000 + N
+    x = rng.uniform(-1, 1, (C_, n))
+    want = oracle_bank(port, h, x)
+    dx = torch.from_numpy(x).cuda()
+    for dtype, exact in ((zlib.F64_STRICT, True), (zlib.F64, False)):
+        bank = zlib.FirBank(C_, dtype, taps=h)
+        dy = torch.empty_like(dx)
+        bank.run(dx, n, dy, n, n)
+        torch.cuda.synchronize()
+        got = dy.cpu().numpy()
+        if exact:
+            assert got.tobytes() == want.tobytes(), N
+        else:
+            scale = np.abs(h).sum()
+            assert np.abs(got - want).max() <= TOL_F64 * max(scale, 1.0), N
+        bank.close()
+
+
+@pytest.mark.parametrize("N,fc,win", [(127, 0.23, 0), (4095, 0.11, 2), (48, 0.4, 1)])
+def test_bank_f32_meets_snr(zlib, port, cuda, N, fc, win):
+    torch = cuda
+    h = port.fir_design(0, N, fc, 0.0, win)
+    C_, n = 4, 50000
+    x = np.stack([port.lcg_f64(n, 12345 + c) for c in range(C_)])
+    want = oracle_bank(port, h, x)
+    bank = zlib.FirBank(C_, zlib.F32, kind=zlib.LPF, flt_len=N, fc1=fc, win=win)
+    assert bank.taps().tobytes() == h.tobytes()
+    dx = torch.from_numpy(x.astype(np.float32)).cuda()
+    dy = torch.empty_like(dx)
+    bank.run(dx, n, dy, n, n)
+    torch.cuda.synchronize()
+    got = dy.cpu().numpy()
+    assert snr_db(want, got) >= SNR_F32_DB, snr_db(want, got)
+    assert np.abs(got - want).max() <= TOL_F32_ABS
+    bank.close()
+
+
+def test_bank_streaming_equals_one_shot(zlib, port, cuda):
+    """ragged chunk sizes (incl. shorter than the history) and unaligned strides keep the stream exact"""
+    torch = cuda
+    h = port.fir_design(2, 129, 0.2, 0.6, 2)
+    C_, n = 5, 40001
+    x = np.stack([port.lcg_f64(n, 100 + c) for c in range(C_)])
+    want = oracle_bank(port, h, x, n_out=n + 128)
+    stride = n + 3                                       # odd stride: the non-vector path
+    dx = torch.zeros(C_, stride, dtype=torch.float64, device="cuda")
+    dx[:, :n] = torch.from_numpy(x).cuda()
+    dy = torch.zeros(C_, stride + 200, dtype=torch.float64, device="cuda")
+    bank = zlib.FirBank(C_, zlib.F64_STRICT, taps=h)
+    pos = 0
+    for step in (1, 7, 100, 128, 129, 5000, 3, 20000, 10 ** 9):
+        m = min(step, n - pos)
+        if m <= 0:
+            break
+        bank.run(dx.data_ptr() + 8 * pos, stride, dy.data_ptr() + 8 * pos, stride + 200, m)
+        pos += m
+    assert pos == n
+    assert bank.flush(dy.data_ptr() + 8 * n, stride + 200) == 128
+    torch.cuda.synchronize()
+    got = dy.cpu().numpy()[:, :n + 128]
+    assert got.tobytes() == want.tobytes()
+    # after a flush the stream restarts from silence
+    bank.run(dx, stride, dy, stride + 200, 1000)
+    torch.cuda.synchronize()
+    assert dy.cpu().numpy()[:, :1000].tobytes() == want[:, :1000].tobytes()
+    bank.close()
+
+
+def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
+    """the multi-GPU time-segment plan, all segments run on one GPU"""
+    torch = cuda
+    N, C_, n = 255, 2, 100003
+    h = port.fir_design(0, N, 0.11, 0.0, 2)
+    x = np.stack([port.lcg_f64(n, 7 + c) for c in range(C_)])
+    dx = torch.from_numpy(x).cuda()
+    one = torch.empty_like(dx)
+    bank = zlib.FirBank(C_, zlib.F64, taps=h)
+    bank.run(dx, n, one, n, n)
+    for world in (2, 4, 8):
+        seg_out = torch.zeros_like(dx)
+        covered = 0
+        for rank in range(world):
+            s = zlib.shard_fir_segments(n, N, world, rank)
+            assert s.out_start == covered and s.in_start == s.out_start
+            covered += s.out_count
+            bank.reset()
+            if s.halo:
+                assert s.halo == N - 1
+                bank.set_history(dx.data_ptr() + 8 * (s.in_start - s.halo), n)
+            bank.run(dx.data_ptr() + 8 * s.in_start, n, seg_out.data_ptr() + 8 * s.out_start, n, s.in_count)
+        assert covered == n
+        torch.cuda.synchronize()
+        assert torch.equal(seg_out, one), world
+    want = oracle_bank(port, h, x)
+    assert np.abs(one.cpu().numpy() - want).max() <= TOL_F64
+    bank.close()
+
+
+def test_run_host_pipeline(zlib, port, cuda):
+    """host buffers -> chunked H2D / kernel / D2H; several chunks; pinned and pageable"""
+    torch = cuda
+    N, C_, n = 127, 16, 1_500_000                   # 192 MB in: three pipeline chunks
+    h = port.fir_design(0, N, 0.23, 0.0, 0)
+    x = zlib.host_alloc(C_ * n * 8, np.float64).reshape(C_, n)
+    for c in range(C_):
+        x[c] = port.lcg_f64(n, 12345 + c)
+    y = zlib.host_alloc(C_ * n * 8, np.float64).reshape(C_, n)
+    bank = zlib.FirBank(C_, zlib.F64, taps=h)
+    bank.run_host(x, n, y, n, n)
+    dx = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    dy = torch.empty_like(dx)
+    bank.reset()
+    bank.run(dx, n, dy, n, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy(), y)
+    for c in (0, 7, 15):
+        for t in (0, 126, 524288, 524289, n - 1):
+            lo = max(0, t - N + 1)
+            want = port.fir_run(h, x[c, lo:t + 1])[-1]
+            assert abs(y[c, t] - want) <= TOL_F64
+    # pageable memory takes the same path
+    xp, yp = np.array(x[:, :300000]), np.empty((C_, 300000))
+    bank.reset()
+    bank.run_host(xp, 300000, yp, 300000, 300000)
+    assert np.array_equal(yp, y[:, :300000])
+    bank.close()
+    zlib.host_free(x.reshape(-1)); zlib.host_free(y.reshape(-1))
+
+
+def test_c2_full_size_properties(zlib, port, cuda):
+    """BASELINE config 2 at full size: 1024 channels x 480,000 samples, 127-tap LPF (f64).
+    Spot checks against the oracle plus linearity and a DC-gain check (size-independent properties)."""
+    torch = cuda
+    C_, n, N = 1024, 480_000, 127
+    h = port.fir_design(0, N, 0.23, 0.0, 0)
+    dx = torch.empty(C_, n, dtype=torch.float64, device="cuda")
+    zlib.synth_lcg(dx, n, C_, n, 0, 12345)
+    bank = zlib.FirBank(C_, zlib.F64, kind=zlib.LPF, flt_len=N, fc1=0.23, win=zlib.HAMMING)
+    dy = torch.empty_like(dx)
+    bank.run(dx, n, dy, n, n)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(0)
+    for c in [0, 1, 511, 1023] + rng.integers(0, C_, 12).tolist():
+        xc = port.lcg_f64(n, 12345 + c)
+        assert np.array_equal(dx[c, :4096].cpu().numpy(), xc[:4096])        # device LCG == host LCG
+        yc = dy[c].cpu().numpy()
+        for t in [0, 1, 125, 126, 127, 3583, 3584, n - 1] + rng.integers(0, n, 40).tolist():
+            lo = max(0, t - N + 1)
+            want = port.fir_run(h, xc[lo:t + 1])[-1]
+            assert abs(yc[t] - want) <= TOL_F64, (c, t)
+    # linearity: F(2x) == 2 F(x) exactly (power-of-two scaling commutes with every rounding)
+    bank.reset()
+    dx.mul_(2.0)
+    dy2 = torch.empty_like(dy)
+    bank.run(dx, n, dy2, n, n)
+    torch.cuda.synchronize()
+    assert torch.equal(dy2, dy * 2.0)
+    # DC: a constant input settles to sum(h)
+    bank.reset()
+    dx.fill_(1.0)
+    bank.run(dx, n, dy2, n, n)
+    torch.cuda.synchronize()
+    assert torch.allclose(dy2[:, N:], torch.full_like(dy2[:, N:], float(h.sum())), rtol=0, atol=1e-13)
+    bank.close()
+
+
+def test_bad_handles_and_arguments(zlib, cuda):
+    L = zlib.lib()
+    assert L.llz_cuda_fir_bank_run(0, None, 0, None, 0, 10, None) == -1
+    assert L.llz_cuda_fir_bank_init(0, 127, 0.2, 0.0, 0, 0, 0) == zlib.FAIL
+    assert L.llz_cuda_fir_bank_init(0, 127, 0.2, 0.0, 0, 4, 9) == zlib.FAIL
+    r = zlib.ResampleBank(zlib.KIND_RESAMPLE, 2, 1, 1)
+    assert L.llz_cuda_fir_bank_run(r.handle, None, 0, None, 0, 10, None) == -1
+    assert "not a FIR handle" in zlib.last_error()
+    r.close()
