@@ -281,6 +281,8 @@ def run_cuda(args):
     # ---- end to end through the C-ABI with host buffers ----
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         in_bytes, out_bytes = dx.numel() * dx.element_size(), dy.numel() * dy.element_size()
         np_dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int16: np.int16}[dx.dtype]
         hx = z.host_alloc(in_bytes, np_dt).reshape(C_, n)
@@ -375,6 +377,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1,0 +1,93 @@
+// probe_pipes.cu -- micro-benchmarks behind the kernel design choices in DESIGN.md (not part of the library).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probe_pipes tools/probe_pipes.cu
+// Measures on one B200: register-resident DFMA / FFMA rate, FP64 tensor-core (DMMA) rate, and whether the two
+// FP64 paths overlap when interleaved in one instruction stream.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+
+template <int NF, int NM>
+__global__ void __launch_bounds__(256) mix_kernel(double *sink, int iters, double a, double b)
+{
+    double f[NF > 0 ? NF : 1];
+    double c0[NM > 0 ? NM : 1], c1[NM > 0 ? NM : 1];
+    for (int i = 0; i < NF; ++i) f[i] = threadIdx.x + i;
+    for (int i = 0; i < NM; ++i) { c0[i] = i; c1[i] = threadIdx.x; }
+    double ra = a + threadIdx.x, rb = b - threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+            for (int i = 0; i < NM; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0[i]), "+d"(c1[i]) : "d"(ra), "d"(rb));
+#pragma unroll
+            for (int i = 0; i < NF; ++i) f[i] = fma(f[i], ra, rb);
+        }
+    }
+    double t = 0;
+    for (int i = 0; i < NF; ++i) t += f[i];
+    for (int i = 0; i < NM; ++i) t += c0[i] + c1[i];
+    if (t == 123456.789) sink[0] = t;
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) ffma_kernel(float *sink, int iters, float a, float b)
+{
+    float f[NF];
+    for (int i = 0; i < NF; ++i) f[i] = threadIdx.x + i;
+    float ra = a + threadIdx.x, rb = b - threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+            for (int i = 0; i < NF; ++i) f[i] = fmaf(f[i], ra, rb);
+    }
+    float t = 0;
+    for (int i = 0; i < NF; ++i) t += f[i];
+    if (t == 123456.789f) sink[0] = t;
+}
+
+template <typename K, typename... A>
+static float time_ms(K kern, int blocks, int threads, A... args)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(e0);
+        kern<<<blocks, threads>>>(args...);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r && ms < best) best = ms;
+    }
+    return best;
+}
+
+int main()
+{
+    int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    double *sink; CK(cudaMalloc(&sink, 64));
+    const int blocks = sms * 8, threads = 256, iters = 2048;
+    const double nthreads = (double)blocks * threads, nwarps = nthreads / 32;
+    auto report = [&](const char *name, float ms, double fma_per_thread, double mma_per_warp) {
+        double flop = 2.0 * (fma_per_thread * nthreads + mma_per_warp * nwarps * 256.0) * iters * 4;
+        printf("%-28s %8.3f ms  %7.2f TFLOP/s (fma part %.2f, mma part %.2f)\n", name, ms, flop / ms / 1e9,
+               2.0 * fma_per_thread * nthreads * iters * 4 / ms / 1e9, 2.0 * mma_per_warp * nwarps * 256 * iters * 4 / ms / 1e9);
+    };
+    report("dfma x8", time_ms(mix_kernel<8, 0>, blocks, threads, sink, iters, 0.999, 0.001), 8, 0);
+    report("dfma x16", time_ms(mix_kernel<16, 0>, blocks, threads, sink, iters, 0.999, 0.001), 16, 0);
+    report("dmma x4", time_ms(mix_kernel<0, 4>, blocks, threads, sink, iters, 0.999, 0.001), 0, 4);
+    report("dmma x8", time_ms(mix_kernel<0, 8>, blocks, threads, sink, iters, 0.999, 0.001), 0, 8);
+    report("dfma x8 + dmma x1", time_ms(mix_kernel<8, 1>, blocks, threads, sink, iters, 0.999, 0.001), 8, 1);
+    report("dfma x8 + dmma x2", time_ms(mix_kernel<8, 2>, blocks, threads, sink, iters, 0.999, 0.001), 8, 2);
+    report("dfma x8 + dmma x4", time_ms(mix_kernel<8, 4>, blocks, threads, sink, iters, 0.999, 0.001), 8, 4);
+    report("dfma x16 + dmma x2", time_ms(mix_kernel<16, 2>, blocks, threads, sink, iters, 0.999, 0.001), 16, 2);
+    {
+        float ms = time_ms(ffma_kernel<16>, blocks, threads, (float *)sink, iters, 0.999f, 0.001f);
+        printf("%-28s %8.3f ms  %7.2f TFLOP/s\n", "ffma x16", ms, 2.0 * 16 * nthreads * iters * 4 / ms / 1e9);
+    }
+    return 0;
+}
