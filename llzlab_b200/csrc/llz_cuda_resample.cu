@@ -6,12 +6,14 @@
 // (floor(o*M/L)) are integer arithmetic, 64-bit, exactly the reference's sequence.
 //
 // Arithmetic modes
-//   ACC_F64         FP64 FMA in any order, then a guard: if gain*sum lies within `thr` of an integer
-//                   (thr = rounding-error bound of the two summation orders for this tile's peak
-//                   sample), the output is recomputed in the reference's order with separate
-//                   multiply and add.  Rows with a single non-zero tap (the Nyquist phase whose
-//                   centre tap is 1-2^-53: SURVEY.md "truncation knife-edge") are exact in any order
-//                   and skip the guard.  Result: bit-identical int16, proven rather than observed.
+//   ACC_F64         FP64 FMA in any order, then a guard: if gain*sum lies within `thr` of a NON-ZERO
+//                   integer (thr = bound on the difference between two FP64 evaluations of the sum for
+//                   full-scale input; truncation toward zero is continuous at 0, so 0 needs no guard
+//                   and digital silence stays on the fast path), the output is recomputed in the
+//                   reference's order with separate multiply and add.  Rows with a single non-zero tap
+//                   (the Nyquist phase whose centre tap is 1-2^-53: SURVEY.md "truncation knife-edge")
+//                   are exact in any order and skip the guard.  Result: bit-identical int16, proven
+//                   rather than observed.
 //   ACC_F64_STRICT  every output in the reference's order (verification mode).
 //   ACC_F32         FP32 FMA; single-tap rows are evaluated in FP64 so the knife-edge phase stays exact.
 //
@@ -81,21 +83,13 @@ __device__ __forceinline__ int16_t poly_emit(const PolyLaunch &a, const int16_t 
         return poly_finish(__dmul_rn(v, a.gain));
     } else {
         double v = __dmul_rn((double)acc, a.gain);
-        if (MODE == LLZ_CUDA_ACC_F64 && thr > 0.0 && fabs(v - rint(v)) < thr && a.single_tap[r] < 0) {
+        const double nearest = rint(v);
+        if (MODE == LLZ_CUDA_ACC_F64 && nearest != 0.0 && fabs(v - nearest) < thr && a.single_tap[r] < 0) {
             v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
             atomicAdd(a.guard_count, 1ULL);
         }
         return poly_finish(v);
     }
-}
-
-// block-wide max of |sample| seen while filling a tile (feeds the guard threshold)
-__device__ __forceinline__ int block_peak(int local_peak, int *slot)
-{
-    for (int d = 16; d > 0; d >>= 1) local_peak = max(local_peak, __shfl_xor_sync(0xffffffffu, local_peak, d));
-    if ((threadIdx.x & 31) == 0) atomicMax(slot, local_peak);
-    __syncthreads();
-    return *slot;
 }
 
 // ---- general kernel ----------------------------------------------------------------------------
@@ -108,9 +102,6 @@ poly_general_kernel(PolyLaunch a, int tile_out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TA *xs = reinterpret_cast<TA *>(smem_raw);
-    __shared__ int s_peak;
-    if (threadIdx.x == 0) s_peak = 0;
-    __syncthreads();
 
     const int ch = blockIdx.y;
     const long long ot = (long long)blockIdx.x * tile_out;
@@ -125,15 +116,13 @@ poly_general_kernel(PolyLaunch a, int tile_out)
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
 
-    int peak = 0;
     for (int e = threadIdx.x; e < span; e += kPolyThreads) {
         const long long s = s_lo + e;
         const int v = (s < frame_end) ? poly_sample(a, xc, hc, s) : 0;
-        peak = max(peak, abs(v));
         xs[e] = (TA)v;
     }
-    const double thr = (MODE == LLZ_CUDA_ACC_F64) ? a.guard_thr * (double)block_peak(peak, &s_peak) : 0.0;
-    if (MODE != LLZ_CUDA_ACC_F64) __syncthreads();
+    const double thr = a.guard_thr;
+    __syncthreads();
 
     int16_t *yc = a.y + (long long)ch * a.y_stride + ot;
     for (int j = threadIdx.x; j < cnt; j += kPolyThreads) {
@@ -171,68 +160,102 @@ poly_general_kernel(PolyLaunch a, int tile_out)
 // shifted by d so that the newest sample of output q always sits at element HS + (q - qt):
 // 16-byte aligned windows for every residue.
 template <typename TA, int R, int MODE>
-__global__ void __launch_bounds__(kPolyThreads, 1)
-poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */)
+__global__ void __launch_bounds__(kPolyThreads, 2)
+poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_stride /* row length of the uploaded taps */)
 {
     using SM = SlidingMac<TA, R>;
+    using V = typename Vec16<TA>::type;
     constexpr int TILE = kPolyThreads * R;
     constexpr int U = SM::U;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TA *taps_s = reinterpret_cast<TA *>(smem_raw);            // [M][ntp]
-    TA *xs = taps_s + (size_t)a.M * ntp;                      // [M][HS + TILE]
-    __shared__ int s_peak;
-    if (threadIdx.x == 0) s_peak = 0;
-
     const int M = a.M;
     const int HS = ntp;
     const int len = HS + TILE;
+    TA *taps_s = reinterpret_cast<TA *>(smem_raw);            // [M][ntp]
+    TA *xs = taps_s + (size_t)M * ntp;                        // [M][HS + TILE]
+
+    const int tid = threadIdx.x;
     const int ch = blockIdx.y;
-    const long long qt = a.o0 + (long long)blockIdx.x * TILE;    // canonical index of the tile's first output
+    const long long ot = (long long)blockIdx.x * TILE;        // first output of the tile within this call
+    const long long qt = a.o0 + ot;                           // its canonical index
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
 
-    const TA *taps_g = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.slide64)
-                                         : reinterpret_cast<const TA *>(a.slide32);
-    for (int k = threadIdx.x; k < M * ntp; k += kPolyThreads) taps_s[k] = taps_g[k];
+    {
+        const TA *src = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.slide64) : reinterpret_cast<const TA *>(a.slide32);
+        const int vpr = ntp / U;                              // vectors per row
+        for (int k = tid; k < M * vpr; k += kPolyThreads) {
+            const int rho = k / vpr, i = k - rho * vpr;
+            reinterpret_cast<V *>(taps_s + (size_t)rho * ntp)[i] = reinterpret_cast<const V *>(src + (size_t)rho * tap_stride)[i];
+        }
+    }
 
-    // de-interleave the contiguous input span into the M streams
+    // de-interleave the contiguous input span into the M streams: row jj of the span holds the samples
+    // X((qt - HS - 1 + jj) * M + sigma); thread jj writes element jj-1 (sigma = 0) / jj (sigma > 0) of each
+    // stream, so a warp's stores are contiguous within a stream (conflict-free) and its loads contiguous in x.
     const long long s_base = (qt - HS - 1) * M;
-    const int total = (len + 1) * M;
-    int peak = 0;
-    for (int u = threadIdx.x; u < total; u += kPolyThreads) {
-        const int jj = u / M, sigma = u - jj * M;
-        const int e = jj - 1 + (sigma ? 1 : 0);
-        if (e >= 0 && e < len) {
-            const int v = poly_sample(a, xc, hc, s_base + u);
-            peak = max(peak, abs(v));
-            xs[(size_t)sigma * len + e] = (TA)v;
+    const long long rel = s_base - a.in0;
+    const int rows = len + 1;
+    if (xc != nullptr && rel >= 0 && rel + (long long)rows * M <= a.n_in) {
+        const int16_t *src = xc + rel;
+        for (int jj = tid; jj < rows; jj += kPolyThreads) {
+            const int16_t *p = src + (long long)jj * M;
+            if (jj >= 1) xs[jj - 1] = (TA)p[0];
+            if (jj < len)
+                for (int sigma = 1; sigma < M; ++sigma) xs[(size_t)sigma * len + jj] = (TA)p[sigma];
+        }
+    } else {
+        for (int jj = tid; jj < rows; jj += kPolyThreads) {
+            const long long s0 = s_base + (long long)jj * M;
+            if (jj >= 1) xs[jj - 1] = (TA)poly_sample(a, xc, hc, s0);
+            if (jj < len)
+                for (int sigma = 1; sigma < M; ++sigma) xs[(size_t)sigma * len + jj] = (TA)poly_sample(a, xc, hc, s0 + sigma);
         }
     }
     __syncthreads();
-    const double thr = (MODE == LLZ_CUDA_ACC_F64) ? a.guard_thr * (double)block_peak(peak, &s_peak) : 0.0;
 
     TA acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = TA(0);
     for (int rho = 0; rho < M; ++rho) {
         const int sigma = rho ? M - rho : 0;
-        const TA *win = xs + (size_t)sigma * len + HS + threadIdx.x * R - U;
+        const TA *win = xs + (size_t)sigma * len + HS + tid * R - U;
         SM::template run<false>(acc, win, taps_s + (size_t)rho * ntp, ntp);
     }
 
-    const long long q0 = (long long)blockIdx.x * TILE + threadIdx.x * R;   // output index within this call
-    int16_t *yc = a.y + (long long)ch * a.y_stride + q0;
+    // gain / guard / saturate / truncate, staged through shared memory so the global stores are 16-byte vectors
+    __syncthreads();                                          // every thread is done reading xs
+    uint32_t *ys32 = reinterpret_cast<uint32_t *>(xs);
+    const long long q0 = ot + (long long)tid * R;             // output index within this call
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (q0 + r < a.n_out) {
-            double single_x = 0.0;
-            if constexpr (MODE == LLZ_CUDA_ACC_F32) {
-                const int st = a.single_tap[0];
-                if (st >= 0) single_x = (double)poly_sample(a, xc, hc, (a.o0 + q0 + r) * M - st);
+    for (int r = 0; r < R; r += 2) {
+        int16_t o2[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double v = __dmul_rn((double)acc[r + i], a.gain);
+            if constexpr (MODE == LLZ_CUDA_ACC_F64) {
+                const double nearest = rint(v);
+                if (nearest != 0.0 && fabs(v - nearest) < a.guard_thr && q0 + r + i < a.n_out) {
+                    v = __dmul_rn(poly_reference_order_sum(a, xc, hc, a.o0 + q0 + r + i), a.gain);
+                    atomicAdd(a.guard_count, 1ULL);
+                }
             }
-            yc[r] = poly_emit<MODE, TA>(a, xc, hc, a.o0 + q0 + r, acc[r], thr, single_x);
+            o2[i] = poly_finish(v);
         }
+        ys32[(tid * R + r) >> 1] = (uint32_t)(uint16_t)o2[0] | ((uint32_t)(uint16_t)o2[1] << 16);
+    }
+    __syncthreads();
+    const int cnt = (int)min((long long)TILE, a.n_out - ot);
+    int16_t *yc = a.y + (long long)ch * a.y_stride + ot;
+    const int16_t *ys = reinterpret_cast<const int16_t *>(xs);
+    if ((reinterpret_cast<uintptr_t>(yc) & 15u) == 0) {
+        const int nv = cnt >> 3;
+        for (int v = tid; v < nv; v += kPolyThreads)
+            reinterpret_cast<uint4 *>(yc)[v] = reinterpret_cast<const uint4 *>(ys)[v];
+        for (int j = (nv << 3) + tid; j < cnt; j += kPolyThreads) yc[j] = ys[j];
+    } else {
+        for (int j = tid; j < cnt; j += kPolyThreads) yc[j] = ys[j];
     }
 }
 
@@ -270,39 +293,59 @@ namespace {
 
 constexpr size_t kSmemBudget = 200 * 1024;
 
-template <typename TA, int R>
-size_t slide_smem(const PolyLaunch &a, int ntp)
+// taps per residue padded to the SlidingMac granularity of a tile variant
+inline int slide_pad(const PolyLaunch &a, int gran)
 {
-    return ((size_t)a.M * ntp + (size_t)a.M * (ntp + kPolyThreads * R)) * sizeof(TA);
+    const int per = (a.ctaps + a.M - 1) / a.M;
+    return (per + gran - 1) / gran * gran;
 }
 
-// 0 = general, 1 = sliding big tile, 2 = sliding small tile
-int pick_kernel(const PolyLaunch &a)
+// Tile variants of the sliding kernel: R/U in {7, 5, 3} (odd: conflict-free LDS.128), i.e. tap granularity
+// {8, 6, 4} vectors.  Pick the least padded one that fits (two CTAs per SM preferred), larger tiles on ties.
+// Returns R/U, or 0 for the general kernel.
+template <typename TA>
+int pick_slide(const PolyLaunch &a, int *ntp_out)
 {
-    if (a.L != 1 || a.shift != 0 || a.frame_len != 0 || a.acc == LLZ_CUDA_ACC_F64_STRICT) return 0;
-    if (a.acc == LLZ_CUDA_ACC_F32) {
-        if (!a.slide32) return 0;
-        if (slide_smem<float, 28>(a, a.slide_ntp32) <= kSmemBudget / 2) return 1;
-        if (slide_smem<float, 12>(a, a.slide_ntp32) <= kSmemBudget) return 2;
-        return 0;
+    constexpr int U = Vec16<TA>::N;
+    const int avail = (sizeof(TA) == 8) ? a.slide_ntp64 : a.slide_ntp32;   // row length of the uploaded taps
+    int best = 0, best_ntp = 0;
+    double best_cost = 0.0;
+    const int ru[3] = {7, 5, 3};
+    for (int i = 0; i < 3; ++i) {
+        const int R = ru[i] * U, gran = (ru[i] + 1) * U;
+        const int ntp = slide_pad(a, gran);
+        if (ntp > avail) continue;
+        const size_t smem = ((size_t)a.M * ntp + (size_t)a.M * (ntp + kPolyThreads * R)) * sizeof(TA);
+        if (smem > kSmemBudget) continue;
+        // work per output ~ padded taps; the fill / halo overhead shrinks with the tile; one CTA per SM hides less
+        double cost = (double)ntp * a.M * (1.0 + (double)ntp / (kPolyThreads * R));
+        if (smem > kSmemBudget / 2) cost *= 1.15;
+        if (best == 0 || cost < best_cost) { best = ru[i]; best_ntp = ntp; best_cost = cost; }
     }
-    if (!a.slide64) return 0;
-    if (slide_smem<double, 14>(a, a.slide_ntp64) <= kSmemBudget / 2) return 1;
-    if (slide_smem<double, 6>(a, a.slide_ntp64) <= kSmemBudget) return 2;
-    return 0;
+    *ntp_out = best_ntp;
+    return best;
+}
+
+int pick_kernel(const PolyLaunch &a, int *ntp)
+{
+    *ntp = 0;
+    if (a.L != 1 || a.shift != 0 || a.frame_len != 0 || a.acc == LLZ_CUDA_ACC_F64_STRICT) return 0;
+    if (a.acc == LLZ_CUDA_ACC_F32) return a.slide32 ? pick_slide<float>(a, ntp) : 0;
+    return a.slide64 ? pick_slide<double>(a, ntp) : 0;
 }
 
 template <typename TA, int R, int MODE>
 int launch_slide(const PolyLaunch &a, int ntp, int n_channels, cudaStream_t stream)
 {
     constexpr int TILE = kPolyThreads * R;
-    const size_t smem = slide_smem<TA, R>(a, ntp);
+    const int tap_stride = (sizeof(TA) == 8) ? a.slide_ntp64 : a.slide_ntp32;
+    const size_t smem = ((size_t)a.M * ntp + (size_t)a.M * (ntp + TILE)) * sizeof(TA);
     auto kern = poly_slide_kernel<TA, R, MODE>;
     if (smem > 48 * 1024)
         LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long tiles = (a.n_out + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
-    kern<<<dim3((unsigned)tiles, (unsigned)n_channels), kPolyThreads, smem, stream>>>(a, ntp);
+    kern<<<dim3((unsigned)tiles, (unsigned)n_channels), kPolyThreads, smem, stream>>>(a, ntp, tap_stride);
     LLZ_CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -338,24 +381,28 @@ int launch_general(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 
 const char *poly_kernel_name(const PolyLaunch &a)
 {
-    return pick_kernel(a) ? "sliding" : "general";
+    int ntp = 0;
+    return pick_kernel(a, &ntp) ? "sliding" : "general";
 }
 
 int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
     if (a.n_out <= 0 || n_channels <= 0) return 0;
     if (n_channels > 65535) { llz_set_error("too many channels for one launch (%d)", n_channels); return -1; }
-    const int which = pick_kernel(a);
+    int ntp = 0;
+    const int ru = pick_kernel(a, &ntp);
     switch (a.acc) {
     case LLZ_CUDA_ACC_F64:
-        if (which == 1) return launch_slide<double, 14, LLZ_CUDA_ACC_F64>(a, a.slide_ntp64, n_channels, stream);
-        if (which == 2) return launch_slide<double, 6, LLZ_CUDA_ACC_F64>(a, a.slide_ntp64, n_channels, stream);
+        if (ru == 7) return launch_slide<double, 14, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);
+        if (ru == 5) return launch_slide<double, 10, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);
+        if (ru == 3) return launch_slide<double, 6, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);
         return launch_general<double, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
     case LLZ_CUDA_ACC_F64_STRICT:
         return launch_general<double, LLZ_CUDA_ACC_F64_STRICT>(a, n_channels, stream);
     case LLZ_CUDA_ACC_F32:
-        if (which == 1) return launch_slide<float, 28, LLZ_CUDA_ACC_F32>(a, a.slide_ntp32, n_channels, stream);
-        if (which == 2) return launch_slide<float, 12, LLZ_CUDA_ACC_F32>(a, a.slide_ntp32, n_channels, stream);
+        if (ru == 7) return launch_slide<float, 28, LLZ_CUDA_ACC_F32>(a, ntp, n_channels, stream);
+        if (ru == 5) return launch_slide<float, 20, LLZ_CUDA_ACC_F32>(a, ntp, n_channels, stream);
+        if (ru == 3) return launch_slide<float, 12, LLZ_CUDA_ACC_F32>(a, ntp, n_channels, stream);
         return launch_general<float, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
     default:
         llz_set_error("unknown accumulator mode %d", a.acc);

@@ -370,12 +370,13 @@ int poly_upload_plan(PolyBank *b)
     std::vector<int> order(p.order, p.order + Q), single(p.single_tap, p.single_tap + L);
     if (upload(&b->d_order, order) || upload(&b->d_single, single)) return -1;
 
-    if (p.L == 1 && p.shift == 0 && p.frame_len == 0) {
-        // sliding kernel: row rho holds the taps k = i*M + rho, i = 0, 1, ... (llz_cuda_resample.cu)
+    if (p.L == 1 && p.shift == 0 && p.frame_len == 0 && p.single_tap[0] < 0) {
+        // sliding kernel: row rho holds the taps k = i*M + rho, i = 0, 1, ... (llz_cuda_resample.cu); the row
+        // length leaves room for the coarsest tap granularity of the tile variants (8 vectors), zero filled
         const int M = p.M;
         const int per = (int)((Q + M - 1) / M);
-        b->slide_ntp64 = (per + 15) / 16 * 16;
-        b->slide_ntp32 = (per + 31) / 32 * 32;
+        b->slide_ntp64 = (per / 16 + 2) * 16;
+        b->slide_ntp32 = (per / 32 + 2) * 32;
         std::vector<double> s64((size_t)M * b->slide_ntp64, 0.0);
         std::vector<float> s32((size_t)M * b->slide_ntp32, 0.f);
         for (size_t k = 0; k < Q; ++k) {
@@ -394,12 +395,12 @@ int poly_upload_plan(PolyBank *b)
             LLZ_CUDA_TRY(cudaMemset(b->d_hist[i], 0, hb));
         }
     }
-    // Guard threshold per unit of peak |sample|.  Two FP64 evaluations of the same Q-term dot
+    // Guard threshold for full-scale input (|sample| <= 32768).  Two FP64 evaluations of the same Q-term dot
     // product (any order, fused or not) each differ from the exact value by at most
     // (Q+1)*u*sum|g*x| (u = 2^-53), the gain multiply adds |v|*u; so two evaluations of gain*sum
     // differ by < 2*(Q+2)*u*|gain|*rowsum*peak.  A factor 4 of slack costs nothing (the guard fires
     // on ~1e-9 of the outputs) and keeps the bound safe against second-order terms.
-    b->guard_thr = 4.0 * 2.0 * (double)(Q + 2) * ldexp(1.0, -53) * fabs(b->gain) * p.abs_row_sum;
+    b->guard_thr = 4.0 * 2.0 * (double)(Q + 2) * ldexp(1.0, -53) * fabs(b->gain) * p.abs_row_sum * 32768.0;
     return 0;
 }
 
