@@ -159,6 +159,27 @@ poly_general_kernel(PolyLaunch a, int tile_out)
 // X_sigma[j] = X(j*M + sigma), sigma = (M - rho) % M and d = (rho > 0).  Stream sigma is stored
 // shifted by d so that the newest sample of output q always sits at element HS + (q - qt):
 // 16-byte aligned windows for every residue.
+// row jj of `src` (M samples) -> element jj-1 of stream 0 and element jj of streams 1..M-1; MC = compile-time M (0: runtime)
+template <typename TA, int MC>
+__device__ __forceinline__ void slide_deinterleave(TA *xs, const int16_t *src, int len, int m_rt, int tid)
+{
+    const int M = MC ? MC : m_rt;
+    const int rows = len + 1;
+#pragma unroll 2
+    for (int jj = tid; jj < rows; jj += kPolyThreads) {
+        const int16_t *p = src + jj * M;
+        if (jj >= 1) xs[jj - 1] = (TA)p[0];
+        if (jj < len) {
+            if constexpr (MC != 0) {
+#pragma unroll
+                for (int sigma = 1; sigma < MC; ++sigma) xs[sigma * len + jj] = (TA)p[sigma];
+            } else {
+                for (int sigma = 1; sigma < M; ++sigma) xs[sigma * len + jj] = (TA)p[sigma];
+            }
+        }
+    }
+}
+
 template <typename TA, int R, int MODE>
 __global__ void __launch_bounds__(kPolyThreads, 2)
 poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_stride /* row length of the uploaded taps */)
@@ -172,8 +193,11 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     const int M = a.M;
     const int HS = ntp;
     const int len = HS + TILE;
-    TA *taps_s = reinterpret_cast<TA *>(smem_raw);            // [M][ntp]
+    const int rows = len + 1;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    TA *taps_s = reinterpret_cast<TA *>(smem_raw + 16);       // [M][ntp]
     TA *xs = taps_s + (size_t)M * ntp;                        // [M][HS + TILE]
+    int16_t *raw = reinterpret_cast<int16_t *>(xs + (size_t)M * len);   // [rows*M + 16] input span as it lies in x
 
     const int tid = threadIdx.x;
     const int ch = blockIdx.y;
@@ -182,6 +206,20 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
 
+    // The tile's input span is contiguous in x: rows*M samples starting at canonical index s_base.  Interior
+    // tiles fetch it with one TMA bulk copy (16-byte granules around the span) while the taps are staged.
+    const long long s_base = (qt - HS - 1) * M;
+    const long long rel = s_base - a.in0;
+    const long long rel_al = rel & ~7LL;
+    const long long end_al = (rel + (long long)rows * M + 7) & ~7LL;
+    const bool inside = xc != nullptr && rel >= 0 && rel + (long long)rows * M <= a.n_in;
+    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
+    if (bulk && tid == 0) {
+        const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
+    }
     {
         const TA *src = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.slide64) : reinterpret_cast<const TA *>(a.slide32);
         const int vpr = ntp / U;                              // vectors per row
@@ -190,20 +228,24 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
             reinterpret_cast<V *>(taps_s + (size_t)rho * ntp)[i] = reinterpret_cast<const V *>(src + (size_t)rho * tap_stride)[i];
         }
     }
+    __syncthreads();                                          // barrier initialised before anyone waits on it
 
-    // de-interleave the contiguous input span into the M streams: row jj of the span holds the samples
-    // X((qt - HS - 1 + jj) * M + sigma); thread jj writes element jj-1 (sigma = 0) / jj (sigma > 0) of each
-    // stream, so a warp's stores are contiguous within a stream (conflict-free) and its loads contiguous in x.
-    const long long s_base = (qt - HS - 1) * M;
-    const long long rel = s_base - a.in0;
-    const int rows = len + 1;
-    if (xc != nullptr && rel >= 0 && rel + (long long)rows * M <= a.n_in) {
-        const int16_t *src = xc + rel;
-        for (int jj = tid; jj < rows; jj += kPolyThreads) {
-            const int16_t *p = src + (long long)jj * M;
-            if (jj >= 1) xs[jj - 1] = (TA)p[0];
-            if (jj < len)
-                for (int sigma = 1; sigma < M; ++sigma) xs[(size_t)sigma * len + jj] = (TA)p[sigma];
+    // De-interleave into the M streams: row jj of the span holds X((qt - HS - 1 + jj) * M + sigma); thread jj
+    // writes element jj-1 (sigma = 0) / jj (sigma > 0) of each stream, so a warp's stores are contiguous
+    // within a stream (conflict-free).
+    if (inside) {
+        const int16_t *src;
+        if (bulk) {
+            mbar_wait(bar, 0);
+            src = raw + (int)(rel - rel_al);
+        } else {
+            src = xc + rel;                                   // unaligned channel or the last granule of x
+        }
+        switch (M) {
+        case 2: slide_deinterleave<TA, 2>(xs, src, len, 2, tid); break;
+        case 3: slide_deinterleave<TA, 3>(xs, src, len, 3, tid); break;
+        case 4: slide_deinterleave<TA, 4>(xs, src, len, 4, tid); break;
+        default: slide_deinterleave<TA, 0>(xs, src, len, M, tid); break;
         }
     } else {
         for (int jj = tid; jj < rows; jj += kPolyThreads) {
@@ -291,7 +333,14 @@ int poly_update_history(const int16_t *x, long long x_stride, long long n_in, co
 
 namespace {
 
-constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemBudget = 226 * 1024;
+
+// barrier + taps [M][ntp] + streams [M][ntp + tile] + raw int16 span
+inline size_t slide_smem_bytes(int M, int ntp, int tile, size_t elem)
+{
+    const size_t raw = (((size_t)(ntp + tile + 1) * M + 16) * 2 + 15) & ~(size_t)15;
+    return 16 + ((size_t)M * ntp + (size_t)M * (ntp + tile)) * elem + raw;
+}
 
 // taps per residue padded to the SlidingMac granularity of a tile variant
 inline int slide_pad(const PolyLaunch &a, int gran)
@@ -315,11 +364,11 @@ int pick_slide(const PolyLaunch &a, int *ntp_out)
         const int R = ru[i] * U, gran = (ru[i] + 1) * U;
         const int ntp = slide_pad(a, gran);
         if (ntp > avail) continue;
-        const size_t smem = ((size_t)a.M * ntp + (size_t)a.M * (ntp + kPolyThreads * R)) * sizeof(TA);
+        const size_t smem = slide_smem_bytes(a.M, ntp, kPolyThreads * R, sizeof(TA));
         if (smem > kSmemBudget) continue;
         // work per output ~ padded taps; the fill / halo overhead shrinks with the tile; one CTA per SM hides less
         double cost = (double)ntp * a.M * (1.0 + (double)ntp / (kPolyThreads * R));
-        if (smem > kSmemBudget / 2) cost *= 1.15;
+        if (smem > 113 * 1024) cost *= 1.25;                   // one CTA per SM: nothing hides the fill
         if (best == 0 || cost < best_cost) { best = ru[i]; best_ntp = ntp; best_cost = cost; }
     }
     *ntp_out = best_ntp;
@@ -339,7 +388,7 @@ int launch_slide(const PolyLaunch &a, int ntp, int n_channels, cudaStream_t stre
 {
     constexpr int TILE = kPolyThreads * R;
     const int tap_stride = (sizeof(TA) == 8) ? a.slide_ntp64 : a.slide_ntp32;
-    const size_t smem = ((size_t)a.M * ntp + (size_t)a.M * (ntp + TILE)) * sizeof(TA);
+    const size_t smem = slide_smem_bytes(a.M, ntp, TILE, sizeof(TA));
     auto kern = poly_slide_kernel<TA, R, MODE>;
     if (smem > 48 * 1024)
         LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
