@@ -160,13 +160,13 @@ poly_general_kernel(PolyLaunch a, int tile_out)
 // shifted by d so that the newest sample of output q always sits at element HS + (q - qt):
 // 16-byte aligned windows for every residue.
 // row jj of `src` (M samples) -> element jj-1 of stream 0 and element jj of streams 1..M-1; MC = compile-time M (0: runtime)
-template <typename TA, int MC>
+template <typename TA, int MC, int NT>
 __device__ __forceinline__ void slide_deinterleave(TA *xs, const int16_t *src, int len, int m_rt, int tid)
 {
     const int M = MC ? MC : m_rt;
     const int rows = len + 1;
 #pragma unroll 2
-    for (int jj = tid; jj < rows; jj += kPolyThreads) {
+    for (int jj = tid; jj < rows; jj += NT) {
         const int16_t *p = src + jj * M;
         if (jj >= 1) xs[jj - 1] = (TA)p[0];
         if (jj < len) {
@@ -180,13 +180,13 @@ __device__ __forceinline__ void slide_deinterleave(TA *xs, const int16_t *src, i
     }
 }
 
-template <typename TA, int R, int MODE>
-__global__ void __launch_bounds__(kPolyThreads, 2)
+template <typename TA, int R, int MODE, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_stride /* row length of the uploaded taps */)
 {
     using SM = SlidingMac<TA, R>;
     using V = typename Vec16<TA>::type;
-    constexpr int TILE = kPolyThreads * R;
+    constexpr int TILE = NT * R;
     constexpr int U = SM::U;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -223,7 +223,7 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     {
         const TA *src = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.slide64) : reinterpret_cast<const TA *>(a.slide32);
         const int vpr = ntp / U;                              // vectors per row
-        for (int k = tid; k < M * vpr; k += kPolyThreads) {
+        for (int k = tid; k < M * vpr; k += NT) {
             const int rho = k / vpr, i = k - rho * vpr;
             reinterpret_cast<V *>(taps_s + (size_t)rho * ntp)[i] = reinterpret_cast<const V *>(src + (size_t)rho * tap_stride)[i];
         }
@@ -242,13 +242,13 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
             src = xc + rel;                                   // unaligned channel or the last granule of x
         }
         switch (M) {
-        case 2: slide_deinterleave<TA, 2>(xs, src, len, 2, tid); break;
-        case 3: slide_deinterleave<TA, 3>(xs, src, len, 3, tid); break;
-        case 4: slide_deinterleave<TA, 4>(xs, src, len, 4, tid); break;
-        default: slide_deinterleave<TA, 0>(xs, src, len, M, tid); break;
+        case 2: slide_deinterleave<TA, 2, NT>(xs, src, len, 2, tid); break;
+        case 3: slide_deinterleave<TA, 3, NT>(xs, src, len, 3, tid); break;
+        case 4: slide_deinterleave<TA, 4, NT>(xs, src, len, 4, tid); break;
+        default: slide_deinterleave<TA, 0, NT>(xs, src, len, M, tid); break;
         }
     } else {
-        for (int jj = tid; jj < rows; jj += kPolyThreads) {
+        for (int jj = tid; jj < rows; jj += NT) {
             const long long s0 = s_base + (long long)jj * M;
             if (jj >= 1) xs[jj - 1] = (TA)poly_sample(a, xc, hc, s0);
             if (jj < len)
@@ -269,12 +269,21 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     // gain / guard / saturate / truncate, staged through shared memory so the global stores are 16-byte vectors
     __syncthreads();                                          // every thread is done reading xs
     uint32_t *ys32 = reinterpret_cast<uint32_t *>(xs);
+    const float gain_f = (float)a.gain;
+    (void)gain_f;
     const long long q0 = ot + (long long)tid * R;             // output index within this call
 #pragma unroll
     for (int r = 0; r < R; r += 2) {
         int16_t o2[2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
+            if constexpr (MODE == LLZ_CUDA_ACC_F32) {
+                // fast mode: gain, saturate and truncate in FP32 (llz_resample.c:594-601 in single precision)
+                float vf = __fmul_rn((float)acc[r + i], gain_f);
+                vf = fminf(fmaxf(vf, -32768.f), 32767.f);
+                o2[i] = (int16_t)__float2int_rz(vf);
+                continue;
+            }
             double v = __dmul_rn((double)acc[r + i], a.gain);
             if constexpr (MODE == LLZ_CUDA_ACC_F64) {
                 const double nearest = rint(v);
@@ -293,11 +302,11 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     const int16_t *ys = reinterpret_cast<const int16_t *>(xs);
     if ((reinterpret_cast<uintptr_t>(yc) & 15u) == 0) {
         const int nv = cnt >> 3;
-        for (int v = tid; v < nv; v += kPolyThreads)
+        for (int v = tid; v < nv; v += NT)
             reinterpret_cast<uint4 *>(yc)[v] = reinterpret_cast<const uint4 *>(ys)[v];
-        for (int j = (nv << 3) + tid; j < cnt; j += kPolyThreads) yc[j] = ys[j];
+        for (int j = (nv << 3) + tid; j < cnt; j += NT) yc[j] = ys[j];
     } else {
-        for (int j = tid; j < cnt; j += kPolyThreads) yc[j] = ys[j];
+        for (int j = tid; j < cnt; j += NT) yc[j] = ys[j];
     }
 }
 
@@ -334,6 +343,10 @@ int poly_update_history(const int16_t *x, long long x_stride, long long n_in, co
 namespace {
 
 constexpr size_t kSmemBudget = 226 * 1024;
+#ifndef LLZ_SLIDE_THREADS
+#define LLZ_SLIDE_THREADS 128
+#endif
+constexpr int kSlideThreads = LLZ_SLIDE_THREADS;   // threads per CTA of the sliding kernel
 
 // barrier + taps [M][ntp] + streams [M][ntp + tile] + raw int16 span
 inline size_t slide_smem_bytes(int M, int ntp, int tile, size_t elem)
@@ -364,11 +377,12 @@ int pick_slide(const PolyLaunch &a, int *ntp_out)
         const int R = ru[i] * U, gran = (ru[i] + 1) * U;
         const int ntp = slide_pad(a, gran);
         if (ntp > avail) continue;
-        const size_t smem = slide_smem_bytes(a.M, ntp, kPolyThreads * R, sizeof(TA));
+        const size_t smem = slide_smem_bytes(a.M, ntp, kSlideThreads * R, sizeof(TA));
         if (smem > kSmemBudget) continue;
         // work per output ~ padded taps; the fill / halo overhead shrinks with the tile; one CTA per SM hides less
-        double cost = (double)ntp * a.M * (1.0 + (double)ntp / (kPolyThreads * R));
+        double cost = (double)ntp * a.M * (1.0 + (double)ntp / (kSlideThreads * R));
         if (smem > 113 * 1024) cost *= 1.25;                   // one CTA per SM: nothing hides the fill
+        else if (smem > 75 * 1024) cost *= 1.05;               // two CTAs per SM
         if (best == 0 || cost < best_cost) { best = ru[i]; best_ntp = ntp; best_cost = cost; }
     }
     *ntp_out = best_ntp;
@@ -386,15 +400,15 @@ int pick_kernel(const PolyLaunch &a, int *ntp)
 template <typename TA, int R, int MODE>
 int launch_slide(const PolyLaunch &a, int ntp, int n_channels, cudaStream_t stream)
 {
-    constexpr int TILE = kPolyThreads * R;
+    constexpr int TILE = kSlideThreads * R;
     const int tap_stride = (sizeof(TA) == 8) ? a.slide_ntp64 : a.slide_ntp32;
     const size_t smem = slide_smem_bytes(a.M, ntp, TILE, sizeof(TA));
-    auto kern = poly_slide_kernel<TA, R, MODE>;
+    auto kern = poly_slide_kernel<TA, R, MODE, kSlideThreads>;
     if (smem > 48 * 1024)
         LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long tiles = (a.n_out + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
-    kern<<<dim3((unsigned)tiles, (unsigned)n_channels), kPolyThreads, smem, stream>>>(a, ntp, tap_stride);
+    kern<<<dim3((unsigned)tiles, (unsigned)n_channels), kSlideThreads, smem, stream>>>(a, ntp, tap_stride);
     LLZ_CUDA_TRY(cudaGetLastError());
     return 0;
 }

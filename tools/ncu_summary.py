@@ -54,18 +54,38 @@ def main():
         n = int(sys.argv[sys.argv.index("--stalls") + 1])
         out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
-        # first kernel only: header row, then one row per SASS/source line
-        try:
-            h = rows[0]
-            ci = {name: i for i, name in enumerate(h)}
-            samp = next(k for k in ci if k.startswith("# Samples") or k == "Warp Stall Sampling (All Samples)")
-            body = [r for r in rows[1:] if len(r) == len(h) and r[ci[samp]].replace(',', '').isdigit()]
-            body.sort(key=lambda r: -int(r[ci[samp]].replace(',', '')))
-            print(f"\n## top {n} lines by stall samples ({samp})")
-            for r in body[:n]:
-                print(r[ci[samp]].rjust(8), r[ci.get('Source', 1)][:150])
-        except Exception as e:       # noqa: BLE001
-            print("source page not parsed:", e)
+        # blocks: ["Kernel Name", name] / header / one row per SASS instruction
+        k = 0
+        while k < len(rows):
+            if rows[k] and rows[k][0] == "Kernel Name":
+                name, h = rows[k][1], rows[k + 1]
+                ci = {c: i for i, c in enumerate(h)}
+                body = []
+                k += 2
+                while k < len(rows) and rows[k] and rows[k][0] != "Kernel Name":
+                    if len(rows[k]) >= len(h) - 2:
+                        body.append(rows[k])
+                    k += 1
+                samp = ci["# Samples"]
+                tot = sum(int(r[samp]) for r in body) or 1
+                stall_cols = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
+                print(f"\n## SASS hot spots of {name[:90]} ({tot} samples, {len(body)} instructions)")
+                agg = {c: sum(int(r[ci[c]] or 0) for r in body) for c in stall_cols}
+                print("   by reason: " + ", ".join(f"{c[6:]} {100 * v / tot:.1f}%" for c, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
+                op = {}
+                for r in body:
+                    o = r[ci["Source"]].split()[0] if r[ci["Source"]].split() else "?"
+                    if o.startswith("@"):
+                        o = r[ci["Source"]].split()[1]
+                    op[o] = op.get(o, [0, 0])
+                    op[o][0] += int(r[samp]); op[o][1] += int(r[ci["Instructions Executed"]] or 0)
+                itot = sum(v[1] for v in op.values()) or 1
+                print("   by opcode (samples%, executed%): " + ", ".join(f"{o} {100 * v[0] / tot:.1f}/{100 * v[1] / itot:.1f}" for o, v in sorted(op.items(), key=lambda kv: -kv[1][0])[:14]))
+                for r in sorted(body, key=lambda r: -int(r[samp]))[:n]:
+                    top = max(stall_cols, key=lambda c: int(r[ci[c]] or 0))
+                    print(f"{100 * int(r[samp]) / tot:6.2f}%  {top[6:]:14s} {r[ci['Source']].strip()[:110]}")
+            else:
+                k += 1
 
 
 if __name__ == "__main__":
