@@ -1,0 +1,280 @@
+// llz_cuda_polybank.cu -- register-tiled phase-bank kernel for rational L/M resampling (L > 1) on sm_100a.
+//
+// Replaces the output loop of the reference's llz_resample (libllzfilter/llz_resample.c:583-603) for banks
+// with many phases (BASELINE configs C1: L=160, Q=45 and C4: L=320, Q=257).
+//
+// Write output m = j*L + l (cycle j, phase l).  The reference's index stepping gives
+//     y[j][l] = sum_{k<Q} g[l][k] * x[j*M + c_l - k],        c_l = floor(l*M/L)          (llz_resample.c:586-592)
+// i.e. for a tile of phases every cycle j is one column of a small matrix product.  With the tap index shifted
+// per phase, k' = k + (c_hi - c_l) (c_hi = the largest c_l of the tile), all phases of the tile read the SAME
+// input column X'[k'][j] = x[j*M + c_hi - k'], and the tile becomes
+//     Y[l][j] = sum_{k'<K'} G'[k'][l] * X'[k'][j],   K' = Q + (c_hi - c_lo),   G'[k'][l] = g[l][k' - (c_hi - c_l)] or 0.
+// A CTA owns PB phases x JB cycles.  Its contiguous int16 input span arrives once in shared memory (TMA bulk
+// copy for interior tiles), then K' is walked in chunks of KC rows: each chunk of G' (gathered from the
+// transposed bank in L2) and X' (expanded from the staged span, converted to the accumulator type once) is
+// double-buffered in shared memory while every thread accumulates a TP x TJ register tile with one broadcast
+// LDS.128 pair for its phases and one LDS.128 pair for its cycles per TP*TJ FMAs.
+//
+// Phase (m mod L) and input index (floor(m*M/L)) are pure integer arithmetic, identical to the reference's
+// sequence; the FP64 mode carries the same near-integer guard as the other kernels (bit-identical int16).
+// Padding cost: K'/Q (e.g. 286/257 for C4 with 64-phase tiles).
+#include "llz_poly_device.cuh"
+
+namespace llz {
+
+namespace {
+
+constexpr int kPG = 8;             // phase groups per CTA
+constexpr int kCG = 16;            // cycle groups per CTA
+constexpr int kBankThreads = kPG * kCG;
+
+struct BankGeom {
+    long long jc0;                 // first cycle touched by this call = floor(o0 / L)
+    int n_cycle_tiles;
+    int n_phase_tiles;
+    int raw_cap;                   // int16 elements reserved for the staged span
+};
+
+template <typename TA, int TP, int TJ, int KC, int MODE>
+__global__ void __launch_bounds__(kBankThreads, 2)
+poly_bank_kernel(PolyLaunch a, BankGeom geo)
+{
+    constexpr int PB = kPG * TP;
+    constexpr int JB = kCG * TJ;
+    constexpr int VU = 16 / (int)sizeof(TA);          // elements per 16-byte vector
+    static_assert(TP % VU == 0 && TJ % VU == 0, "thread tile must be whole vectors");
+    using V = typename Vec16<TA>::type;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    TA *Xs = reinterpret_cast<TA *>(smem_raw + 16);            // [2][KC][JB]
+    TA *Gs = Xs + 2 * KC * JB;                                 // [2][KC][PB]
+    int16_t *raw = reinterpret_cast<int16_t *>(Gs + 2 * KC * PB);
+    __shared__ int s_shift[PB];                                // c_hi - c_l per phase of the tile (-1: no such phase)
+
+    const int tid = threadIdx.x;
+    const int pg = tid / kCG, cg = tid % kCG;
+    const int tile_p = blockIdx.x % geo.n_phase_tiles;         // phase tiles fastest: neighbours share the input span in L2
+    const int tile_j = blockIdx.x / geo.n_phase_tiles;
+    const int ch = blockIdx.y;
+    const int L = a.L, M = a.M, Q = a.ctaps;
+
+    const int l0 = tile_p * PB;
+    const int pbv = min(PB, L - l0);                           // phases that exist in this tile
+    const int c_lo = (int)(((long long)l0 * M) / L);
+    const int c_hi = (int)(((long long)(l0 + pbv - 1) * M) / L);
+    const int cspan = c_hi - c_lo;
+    const int KP = Q + cspan;                                  // K'
+    const long long j0 = geo.jc0 + (long long)tile_j * JB;     // first cycle of the tile
+    const int rawn = (JB - 1) * M + cspan + Q;                 // staged samples
+    const long long S0 = j0 * M + c_lo - (Q - 1);              // canonical index of raw[0]
+
+    const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
+    const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
+
+    // ---- stage the input span ---------------------------------------------------------------------------
+    const long long rel = S0 - a.in0;
+    const long long rel_al = rel & ~7LL;
+    const long long end_al = (rel + rawn + 7) & ~7LL;
+    const bool inside = xc != nullptr && rel >= 0 && rel + rawn <= a.n_in;
+    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
+    int raw_off = 0;
+    if (bulk) {
+        raw_off = (int)(rel - rel_al);
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, bytes);
+            tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
+        }
+    } else if (inside) {
+        for (int e = tid; e < rawn; e += kBankThreads) raw[e] = xc[rel + e];
+    } else {
+        for (int e = tid; e < rawn; e += kBankThreads) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+    }
+    for (int l = tid; l < PB; l += kBankThreads)
+        s_shift[l] = (l < pbv) ? c_hi - (int)(((long long)(l0 + l) * M) / L) : -1;
+    __syncthreads();
+    if (bulk) mbar_wait(bar, 0);
+    const int16_t *rawp = raw + raw_off;
+
+    // ---- chunk builders ---------------------------------------------------------------------------------
+    const TA *bankT = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.cbankT64) : reinterpret_cast<const TA *>(a.cbankT32);
+    constexpr int GE = KC * PB / kBankThreads;                 // G' elements per thread per chunk
+    constexpr int XE = KC * JB / kBankThreads;                 // X' elements per thread per chunk
+    TA gpre[GE];
+
+    auto load_g = [&](int chunk) {                             // global -> registers (latency hidden behind the MAC loop)
+#pragma unroll
+        for (int i = 0; i < GE; ++i) {
+            const int e = i * kBankThreads + tid;
+            const int kk = e / PB, l = e % PB;
+            const int sh = s_shift[l];
+            const int k = chunk * KC + kk - sh;
+            gpre[i] = (sh >= 0 && k >= 0 && k < Q) ? bankT[(long long)k * L + l0 + l] : TA(0);
+        }
+    };
+    auto store_g = [&](int buf) {
+        TA *dst = Gs + buf * KC * PB;
+#pragma unroll
+        for (int i = 0; i < GE; ++i) dst[i * kBankThreads + tid] = gpre[i];
+    };
+    auto build_x = [&](int chunk, int buf) {                   // X'[k'][j] = raw[j*M + (K'-1) - k']
+        TA *dst = Xs + buf * KC * JB;
+#pragma unroll 4
+        for (int i = 0; i < XE; ++i) {
+            const int e = i * kBankThreads + tid;
+            const int kk = e / JB, j = e % JB;
+            const int idx = j * M + (KP - 1) - (chunk * KC + kk);
+            dst[e] = (TA)rawp[max(idx, 0)];                    // rows k' >= K' only ever meet zero coefficients
+        }
+    };
+
+    // ---- main loop ----------------------------------------------------------------------------------------
+    TA acc[TP][TJ];
+#pragma unroll
+    for (int p = 0; p < TP; ++p)
+#pragma unroll
+        for (int t = 0; t < TJ; ++t) acc[p][t] = TA(0);
+
+    const int nchunks = (KP + KC - 1) / KC;
+    load_g(0);
+    store_g(0);
+    build_x(0, 0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunks) load_g(c + 1);
+        const TA *gb = Gs + buf * KC * PB + pg * TP;
+        const TA *xb = Xs + buf * KC * JB + cg * VU;
+#pragma unroll 4
+        for (int kk = 0; kk < KC; ++kk) {
+            TA g[TP], xv[TJ];
+#pragma unroll
+            for (int p = 0; p < TP; p += VU) unpack(*reinterpret_cast<const V *>(gb + kk * PB + p), &g[p]);
+#pragma unroll
+            for (int q = 0; q < TJ / VU; ++q) unpack(*reinterpret_cast<const V *>(xb + kk * JB + q * kCG * VU), &xv[q * VU]);
+#pragma unroll
+            for (int p = 0; p < TP; ++p)
+#pragma unroll
+                for (int t = 0; t < TJ; ++t) acc[p][t] = mac<TA, false>(g[p], xv[t], acc[p][t]);
+        }
+        if (c + 1 < nchunks) {
+            store_g(buf ^ 1);
+            build_x(c + 1, buf ^ 1);
+        }
+        __syncthreads();
+    }
+
+    // ---- gain / guard / saturate / truncate / store --------------------------------------------------------------
+    const long long o_end = a.o0 + a.n_out;
+#pragma unroll
+    for (int t = 0; t < TJ; ++t) {
+        const int j = ((t / VU) * kCG + cg) * VU + (t % VU);   // cycle within the tile
+        const long long obase = (j0 + j) * (long long)L + l0 + pg * TP;
+        int16_t outv[TP];
+        bool all_valid = true;
+#pragma unroll
+        for (int p = 0; p < TP; ++p) {
+            const int l = pg * TP + p;
+            const long long o = obase + p;
+            const bool valid = l < pbv && o >= a.o0 && o < o_end;
+            all_valid = all_valid && valid;
+            int16_t r16 = 0;
+            if (valid) {
+                const int st = a.single_tap[l0 + l];
+                if constexpr (MODE == LLZ_CUDA_ACC_F32) {
+                    double v = (double)acc[p][t];
+                    if (st >= 0) {                             // knife-edge phase: one exact FP64 product
+                        const long long base = (o * M) / L;
+                        v = __dmul_rn((double)poly_sample(a, xc, hc, base - st), a.cbank[(long long)(l0 + l) * Q + st]);
+                    }
+                    r16 = poly_finish(__dmul_rn(v, a.gain));
+                } else {
+                    double v = __dmul_rn((double)acc[p][t], a.gain);
+                    const double nearest = rint(v);
+                    if (nearest != 0.0 && fabs(v - nearest) < a.guard_thr && st < 0) {
+                        v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
+                        atomicAdd(a.guard_count, 1ULL);
+                    }
+                    r16 = poly_finish(v);
+                }
+            }
+            outv[p] = r16;
+        }
+        int16_t *yp = a.y + (long long)ch * a.y_stride + (obase - a.o0);
+        if (all_valid && (reinterpret_cast<uintptr_t>(yp) & (2 * TP - 1)) == 0) {
+            if constexpr (TP == 8) {
+                uint4 w;
+                w.x = (uint16_t)outv[0] | ((uint32_t)(uint16_t)outv[1] << 16);
+                w.y = (uint16_t)outv[2] | ((uint32_t)(uint16_t)outv[3] << 16);
+                w.z = (uint16_t)outv[4] | ((uint32_t)(uint16_t)outv[5] << 16);
+                w.w = (uint16_t)outv[6] | ((uint32_t)(uint16_t)outv[7] << 16);
+                *reinterpret_cast<uint4 *>(yp) = w;
+            } else {
+#pragma unroll
+                for (int p = 0; p < TP; p += 2)
+                    *reinterpret_cast<uint32_t *>(yp + p) = (uint16_t)outv[p] | ((uint32_t)(uint16_t)outv[p + 1] << 16);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < TP; ++p) {
+                const long long o = obase + p;
+                if (pg * TP + p < pbv && o >= a.o0 && o < o_end) yp[p] = outv[p];
+            }
+        }
+    }
+}
+
+template <typename TA, int TP, int TJ, int KC, int MODE>
+int launch_bank(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+{
+    constexpr int PB = kPG * TP, JB = kCG * TJ;
+    BankGeom geo{};
+    geo.jc0 = a.o0 / a.L;
+    const long long jc_last = (a.o0 + a.n_out - 1) / a.L;
+    const long long cycles = jc_last - geo.jc0 + 1;
+    geo.n_cycle_tiles = (int)((cycles + JB - 1) / JB);
+    geo.n_phase_tiles = (a.L + PB - 1) / PB;
+    const int cspan_max = (int)(((long long)PB * a.M) / a.L) + 2;
+    geo.raw_cap = (JB - 1) * a.M + cspan_max + a.ctaps + 16;
+    const size_t smem = 16 + (size_t)2 * KC * (JB + PB) * sizeof(TA) + (((size_t)geo.raw_cap * 2 + 15) & ~(size_t)15);
+    auto kern = poly_bank_kernel<TA, TP, TJ, KC, MODE>;
+    if (smem > 48 * 1024)
+        LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
+    if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
+    kern<<<dim3((unsigned)blocks, (unsigned)n_channels), kBankThreads, smem, stream>>>(a, geo);
+    LLZ_CUDA_TRY(cudaGetLastError());
+    return 1;
+}
+
+template <typename TA, int TP, int TJ, int KC>
+size_t bank_smem(const PolyLaunch &a)
+{
+    constexpr int PB = kPG * TP, JB = kCG * TJ;
+    const int cspan_max = (int)(((long long)PB * a.M) / a.L) + 2;
+    const size_t raw_cap = (size_t)(JB - 1) * a.M + cspan_max + a.ctaps + 16;
+    return 16 + (size_t)2 * KC * (JB + PB) * sizeof(TA) + ((raw_cap * 2 + 15) & ~(size_t)15);
+}
+
+}  // namespace
+
+// 1 = launched, 0 = not applicable (caller falls back to the general kernel), -1 = error
+int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+{
+    if (a.shift != 0 || a.frame_len != 0 || a.acc == LLZ_CUDA_ACC_F64_STRICT) return 0;
+    if (a.L < 16) return 0;                                    // few phases: the phase tile would be mostly padding
+    // padded work K'/Q must stay reasonable: c-span of a 64-phase tile against the taps per phase
+    const double cspan = 64.0 * a.M / a.L;
+    if ((a.ctaps + cspan) / a.ctaps > 2.5) return 0;
+    constexpr size_t kLimit = 226 * 1024;
+    if (a.acc == LLZ_CUDA_ACC_F32) {
+        if (bank_smem<float, 8, 8, 32>(a) > kLimit) return 0;
+        return launch_bank<float, 8, 8, 32, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
+    }
+    if (bank_smem<double, 8, 4, 32>(a) > kLimit) return 0;
+    return launch_bank<double, 8, 4, 32, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
+}
+
+}  // namespace llz

@@ -27,70 +27,10 @@
 #include <limits.h>
 
 #include "llz_poly_kernels.h"
+#include "llz_poly_device.cuh"
 #include "llz_sliding_mac.cuh"
 
 namespace llz {
-
-// ---- shared device helpers ---------------------------------------------------------------------
-
-__device__ __forceinline__ int poly_sample(const PolyLaunch &a, const int16_t *xc, const int16_t *hc,
-                                           long long s)
-{
-    const long long sp = s - a.in0;
-    if (sp >= 0) return (sp < a.n_in && xc) ? (int)xc[sp] : 0;
-    if (hc && sp >= -(long long)a.hist_len) return (int)hc[a.hist_len + sp];
-    return 0;
-}
-
-// gain, saturate, truncate toward zero: llz_resample.c:594-601
-__device__ __forceinline__ int16_t poly_finish(double v)
-{
-    if (v > 32767) v = 32767;
-    if (v < -32768) v = -32768;
-    return (int16_t)(int)v;
-}
-
-// The reference's own loop for one output: order[] walks the taps as llz_resample.c does, products
-// and sums rounded separately.  Reads global memory; only the guard and the strict mode call it.
-__device__ __noinline__ double poly_reference_order_sum(const PolyLaunch &a, const int16_t *xc,
-                                                        const int16_t *hc, long long o)
-{
-    const int r = (int)(o % a.L);
-    const long long base = (o * a.M) / a.L + a.shift;
-    long long frame_end = LLONG_MAX;
-    if (a.frame_len > 0) frame_end = ((o / a.L) / a.frame_len + 1) * (long long)a.frame_len;
-    const double *row = a.cbank + (long long)r * a.ctaps;
-    double acc = 0.0;
-    for (int t = 0; t < a.order_len; ++t) {
-        const int k = a.order[t];
-        const long long s = base - k;
-        const double xv = (s < frame_end) ? (double)poly_sample(a, xc, hc, s) : 0.0;
-        acc = __dadd_rn(acc, __dmul_rn(xv, row[k]));
-    }
-    return acc;
-}
-
-// turn an accumulated sum into the output sample under the selected mode
-template <int MODE, typename TA>
-__device__ __forceinline__ int16_t poly_emit(const PolyLaunch &a, const int16_t *xc, const int16_t *hc,
-                                             long long o, TA acc, double thr, double single_x)
-{
-    const int r = (int)(o % a.L);
-    if constexpr (MODE == LLZ_CUDA_ACC_F32) {
-        double v = (double)acc;
-        const int st = a.single_tap[r];
-        if (st >= 0) v = __dmul_rn(single_x, a.cbank[(long long)r * a.ctaps + st]);
-        return poly_finish(__dmul_rn(v, a.gain));
-    } else {
-        double v = __dmul_rn((double)acc, a.gain);
-        const double nearest = rint(v);
-        if (MODE == LLZ_CUDA_ACC_F64 && nearest != 0.0 && fabs(v - nearest) < thr && a.single_tap[r] < 0) {
-            v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
-            atomicAdd(a.guard_count, 1ULL);
-        }
-        return poly_finish(v);
-    }
-}
 
 // ---- general kernel ----------------------------------------------------------------------------
 
@@ -454,6 +394,10 @@ int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if (n_channels > 65535) { llz_set_error("too many channels for one launch (%d)", n_channels); return -1; }
     int ntp = 0;
     const int ru = pick_kernel(a, &ntp);
+    if (ru == 0) {
+        const int rc = poly_bank_launch(a, n_channels, stream);
+        if (rc != 0) return rc < 0 ? -1 : 0;
+    }
     switch (a.acc) {
     case LLZ_CUDA_ACC_F64:
         if (ru == 7) return launch_slide<double, 14, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);

@@ -45,6 +45,8 @@ struct PolyLaunch {
 
 // picks the kernel (sliding for L == 1 when the tile fits, general otherwise) and launches it
 int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
+// register-tiled phase-bank kernel for L > 1 (llz_cuda_polybank.cu): 1 = launched, 0 = not applicable, -1 = error
+int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 // name of the kernel poly_launch would pick ("sliding" / "general"), for reporting
 const char *poly_kernel_name(const PolyLaunch &a);
 
