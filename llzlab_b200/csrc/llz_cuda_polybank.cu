@@ -27,6 +27,7 @@ namespace {
 constexpr int kPG = 8;             // phase groups per CTA
 constexpr int kCG = 16;            // cycle groups per CTA
 constexpr int kBankThreads = kPG * kCG;
+constexpr int kRawSlack = 64;      // X' rows beyond K' index up to KC samples before the span: finite garbage times zero taps
 
 struct BankGeom {
     long long jc0;                 // first cycle touched by this call = floor(o0 / L)
@@ -36,7 +37,7 @@ struct BankGeom {
 };
 
 template <typename TA, int TP, int TJ, int KC, int MODE>
-__global__ void __launch_bounds__(kBankThreads, 2)
+__global__ void __launch_bounds__(kBankThreads, 3)
 poly_bank_kernel(PolyLaunch a, BankGeom geo)
 {
     constexpr int PB = kPG * TP;
@@ -49,8 +50,8 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     TA *Xs = reinterpret_cast<TA *>(smem_raw + 16);            // [2][KC][JB]
     TA *Gs = Xs + 2 * KC * JB;                                 // [2][KC][PB]
-    int16_t *raw = reinterpret_cast<int16_t *>(Gs + 2 * KC * PB);
-    __shared__ int s_shift[PB];                                // c_hi - c_l per phase of the tile (-1: no such phase)
+    int16_t *raw = reinterpret_cast<int16_t *>(Gs + 2 * KC * PB) + kRawSlack;   // kRawSlack elements of slack in front
+    __shared__ int s_shift[PB];                                // c_hi - c_l per phase of the tile
 
     const int tid = threadIdx.x;
     const int pg = tid / kCG, cg = tid % kCG;
@@ -93,41 +94,41 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
         for (int e = tid; e < rawn; e += kBankThreads) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
     }
     for (int l = tid; l < PB; l += kBankThreads)
-        s_shift[l] = (l < pbv) ? c_hi - (int)(((long long)(l0 + l) * M) / L) : -1;
+        s_shift[l] = (l < pbv) ? c_hi - (int)(((long long)(l0 + l) * M) / L) : 0;   // phases past L: any finite taps
     __syncthreads();
     if (bulk) mbar_wait(bar, 0);
     const int16_t *rawp = raw + raw_off;
 
     // ---- chunk builders ---------------------------------------------------------------------------------
+    // The transposed bank [k][L] is uploaded with zero rows before row 0 and after row Q-1 (PolyLaunch::bank_pad),
+    // so G'[k'][l] = bankT[(k' - shift_l)*L + l0 + l] needs no bounds checks; rows k' >= K' of X' meet only zeros.
     const TA *bankT = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.cbankT64) : reinterpret_cast<const TA *>(a.cbankT32);
-    constexpr int GE = KC * PB / kBankThreads;                 // G' elements per thread per chunk
-    constexpr int XE = KC * JB / kBankThreads;                 // X' elements per thread per chunk
+    constexpr int GR = kBankThreads / PB;                      // G' rows covered by one pass of the CTA
+    constexpr int GE = KC / GR;                                // G' elements per thread per chunk
+    constexpr int XR = kBankThreads / JB;                      // X' rows covered by one pass
+    constexpr int XE = KC / XR;
+    static_assert(kBankThreads % PB == 0 && kBankThreads % JB == 0 && KC % GR == 0 && KC % XR == 0, "tile shape");
+    const int gl = tid % PB, gk = tid / PB;                    // this thread's G' column and first row
+    const TA *gsrc = bankT + ((long long)gk - s_shift[gl]) * L + l0 + gl;
+    const int xj = tid % JB, xk = tid / JB;                    // this thread's X' column and first row
+    const int16_t *xsrc = rawp + xj * M + (KP - 1) - xk;
     TA gpre[GE];
 
     auto load_g = [&](int chunk) {                             // global -> registers (latency hidden behind the MAC loop)
+        const TA *src = gsrc + (long long)chunk * KC * L;
 #pragma unroll
-        for (int i = 0; i < GE; ++i) {
-            const int e = i * kBankThreads + tid;
-            const int kk = e / PB, l = e % PB;
-            const int sh = s_shift[l];
-            const int k = chunk * KC + kk - sh;
-            gpre[i] = (sh >= 0 && k >= 0 && k < Q) ? bankT[(long long)k * L + l0 + l] : TA(0);
-        }
+        for (int i = 0; i < GE; ++i) gpre[i] = src[(long long)i * GR * L];
     };
     auto store_g = [&](int buf) {
-        TA *dst = Gs + buf * KC * PB;
+        TA *dst = Gs + buf * KC * PB + tid;
 #pragma unroll
-        for (int i = 0; i < GE; ++i) dst[i * kBankThreads + tid] = gpre[i];
+        for (int i = 0; i < GE; ++i) dst[i * kBankThreads] = gpre[i];
     };
     auto build_x = [&](int chunk, int buf) {                   // X'[k'][j] = raw[j*M + (K'-1) - k']
-        TA *dst = Xs + buf * KC * JB;
-#pragma unroll 4
-        for (int i = 0; i < XE; ++i) {
-            const int e = i * kBankThreads + tid;
-            const int kk = e / JB, j = e % JB;
-            const int idx = j * M + (KP - 1) - (chunk * KC + kk);
-            dst[e] = (TA)rawp[max(idx, 0)];                    // rows k' >= K' only ever meet zero coefficients
-        }
+        TA *dst = Xs + buf * KC * JB + tid;
+        const int16_t *src = xsrc - chunk * KC;
+#pragma unroll
+        for (int i = 0; i < XE; ++i) dst[i * kBankThreads] = (TA)src[-i * XR];
     };
 
     // ---- main loop ----------------------------------------------------------------------------------------
@@ -226,6 +227,15 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
     }
 }
 
+template <typename TA, int TP, int TJ, int KC>
+size_t bank_smem(const PolyLaunch &a)
+{
+    constexpr int PB = kPG * TP, JB = kCG * TJ;
+    const int cspan_max = (int)(((long long)PB * a.M) / a.L) + 2;
+    const size_t raw_cap = (size_t)(JB - 1) * a.M + cspan_max + a.ctaps + 16;
+    return 16 + (size_t)2 * KC * (JB + PB) * sizeof(TA) + (((raw_cap + kRawSlack) * 2 + 15) & ~(size_t)15);
+}
+
 template <typename TA, int TP, int TJ, int KC, int MODE>
 int launch_bank(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
@@ -238,7 +248,7 @@ int launch_bank(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     geo.n_phase_tiles = (a.L + PB - 1) / PB;
     const int cspan_max = (int)(((long long)PB * a.M) / a.L) + 2;
     geo.raw_cap = (JB - 1) * a.M + cspan_max + a.ctaps + 16;
-    const size_t smem = 16 + (size_t)2 * KC * (JB + PB) * sizeof(TA) + (((size_t)geo.raw_cap * 2 + 15) & ~(size_t)15);
+    const size_t smem = bank_smem<TA, TP, TJ, KC>(a);
     auto kern = poly_bank_kernel<TA, TP, TJ, KC, MODE>;
     if (smem > 48 * 1024)
         LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -249,15 +259,6 @@ int launch_bank(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     return 1;
 }
 
-template <typename TA, int TP, int TJ, int KC>
-size_t bank_smem(const PolyLaunch &a)
-{
-    constexpr int PB = kPG * TP, JB = kCG * TJ;
-    const int cspan_max = (int)(((long long)PB * a.M) / a.L) + 2;
-    const size_t raw_cap = (size_t)(JB - 1) * a.M + cspan_max + a.ctaps + 16;
-    return 16 + (size_t)2 * KC * (JB + PB) * sizeof(TA) + ((raw_cap * 2 + 15) & ~(size_t)15);
-}
-
 }  // namespace
 
 // 1 = launched, 0 = not applicable (caller falls back to the general kernel), -1 = error
@@ -265,16 +266,17 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
     if (a.shift != 0 || a.frame_len != 0 || a.acc == LLZ_CUDA_ACC_F64_STRICT) return 0;
     if (a.L < 16) return 0;                                    // few phases: the phase tile would be mostly padding
+    if (a.bank_pad < (int)(64.0 * a.M / a.L) + 2 + 32) return 0;   // transposed bank not padded for 64-phase tiles
     // padded work K'/Q must stay reasonable: c-span of a 64-phase tile against the taps per phase
     const double cspan = 64.0 * a.M / a.L;
     if ((a.ctaps + cspan) / a.ctaps > 2.5) return 0;
     constexpr size_t kLimit = 226 * 1024;
     if (a.acc == LLZ_CUDA_ACC_F32) {
-        if (bank_smem<float, 8, 8, 32>(a) > kLimit) return 0;
-        return launch_bank<float, 8, 8, 32, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
+        if (bank_smem<float, 8, 8, 16>(a) > kLimit) return 0;
+        return launch_bank<float, 8, 8, 16, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
     }
-    if (bank_smem<double, 8, 4, 32>(a) > kLimit) return 0;
-    return launch_bank<double, 8, 4, 32, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
+    if (bank_smem<double, 8, 4, 16>(a) > kLimit) return 0;
+    return launch_bank<double, 8, 4, 16, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
 }
 
 }  // namespace llz

@@ -33,6 +33,7 @@ struct PolyLaunch {
     const double *cbank;       // [L][ctaps] row-major
     const double *cbankT64;    // [ctaps][L]
     const float *cbankT32;     // [ctaps][L]
+    int bank_pad;              // zero rows before row 0 and after row ctaps-1 of cbankT64 / cbankT32
     const int *order;          // reference accumulation order, order_len canonical tap indices
     int order_len;
     const int *single_tap;     // [L]

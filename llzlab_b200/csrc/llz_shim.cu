@@ -303,8 +303,9 @@ struct PolyBank {
     double gain = 1.0;
     llz_plan_t plan{};
     // device copies of the plan
-    double *d_cbank = nullptr, *d_cbankT64 = nullptr, *d_slide64 = nullptr;
-    float *d_cbankT32 = nullptr, *d_slide32 = nullptr;
+    double *d_cbank = nullptr, *d_cbankT64 = nullptr, *d_cbankT64_base = nullptr, *d_slide64 = nullptr;
+    float *d_cbankT32 = nullptr, *d_cbankT32_base = nullptr, *d_slide32 = nullptr;
+    int bank_pad = 0;
     int *d_order = nullptr, *d_single = nullptr;
     int slide_ntp64 = 0, slide_ntp32 = 0;
     unsigned long long *d_guard = nullptr;
@@ -334,8 +335,8 @@ void poly_destroy(PolyBank *b)
     if (!b) return;
     DeviceGuard g(b->device);
     b->pipe.destroy();
-    cudaFree(b->d_cbank); cudaFree(b->d_cbankT64); cudaFree(b->d_slide64);
-    cudaFree(b->d_cbankT32); cudaFree(b->d_slide32);
+    cudaFree(b->d_cbank); cudaFree(b->d_cbankT64_base); cudaFree(b->d_slide64);
+    cudaFree(b->d_cbankT32_base); cudaFree(b->d_slide32);
     cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     if (b->pinned_in) cudaFreeHost(b->pinned_in);
@@ -359,14 +360,20 @@ int poly_upload_plan(PolyBank *b)
 {
     const llz_plan_t &p = b->plan;
     const size_t L = (size_t)p.crows, Q = (size_t)p.ctaps;
-    std::vector<double> cb(p.cbank, p.cbank + L * Q), t64(L * Q);
-    std::vector<float> t32(L * Q);
+    // transposed bank [Q][L] with `pad` zero rows on both sides: the phase-bank kernel shifts rows per phase by up to
+    // 64*M/L + 1 and over-runs the last chunk, and must not need bounds checks (llz_cuda_polybank.cu)
+    const size_t pad = (size_t)(64.0 * p.M / p.L) + 2 + 64;
+    b->bank_pad = (int)pad;
+    std::vector<double> cb(p.cbank, p.cbank + L * Q), t64(L * (Q + 2 * pad), 0.0);
+    std::vector<float> t32(L * (Q + 2 * pad), 0.f);
     for (size_t r = 0; r < L; ++r)
         for (size_t k = 0; k < Q; ++k) {
-            t64[k * L + r] = cb[r * Q + k];
-            t32[k * L + r] = (float)cb[r * Q + k];
+            t64[(k + pad) * L + r] = cb[r * Q + k];
+            t32[(k + pad) * L + r] = (float)cb[r * Q + k];
         }
-    if (upload(&b->d_cbank, cb) || upload(&b->d_cbankT64, t64) || upload(&b->d_cbankT32, t32)) return -1;
+    if (upload(&b->d_cbank, cb) || upload(&b->d_cbankT64_base, t64) || upload(&b->d_cbankT32_base, t32)) return -1;
+    b->d_cbankT64 = b->d_cbankT64_base + pad * L;
+    b->d_cbankT32 = b->d_cbankT32_base + pad * L;
     std::vector<int> order(p.order, p.order + Q), single(p.single_tap, p.single_tap + L);
     if (upload(&b->d_order, order) || upload(&b->d_single, single)) return -1;
 
@@ -473,6 +480,7 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.cbank = b->d_cbank;
     a.cbankT64 = b->d_cbankT64;
     a.cbankT32 = b->d_cbankT32;
+    a.bank_pad = b->bank_pad;
     a.order = b->d_order;
     a.order_len = p.ctaps;
     a.single_tap = b->d_single;
