@@ -72,6 +72,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// plain arrival (release, CTA scope): publishes this thread's earlier shared-memory writes to the waiters
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // global -> shared bulk copy; dst, src and bytes are multiples of 16
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {

@@ -12,21 +12,24 @@
 // A CTA owns PB phases x JB cycles.  Its contiguous int16 input span arrives once in shared memory (TMA bulk
 // copy for interior tiles), then K' is walked in chunks of KC rows: each chunk of G' (gathered from the
 // transposed bank in L2) and X' (expanded from the staged span, converted to the accumulator type once) is
-// double-buffered in shared memory while every thread accumulates a TP x TJ register tile with one broadcast
-// LDS.128 pair for its phases and one LDS.128 pair for its cycles per TP*TJ FMAs.
+// staged in a three-deep mbarrier pipeline in shared memory while every thread accumulates a TP x TJ register
+// tile.  The binding resource is the shared-memory -> register return path (128 B/clk/SM: an LDS.128 costs four
+// cycles of it however much of it is broadcast), so the tile is large (f32 16x8, f64 8x8) and X' stays int16 in
+// shared memory (one LDS.128 = 8 cycles' worth of samples), converted in registers by the otherwise idle
+// conversion unit: 80 bytes loaded per thread per TP*TJ FMAs.
 //
 // Phase (m mod L) and input index (floor(m*M/L)) are pure integer arithmetic, identical to the reference's
 // sequence; the FP64 mode carries the same near-integer guard as the other kernels (bit-identical int16).
 // Padding cost: K'/Q (e.g. 286/257 for C4 with 64-phase tiles).
+#include <type_traits>
+
 #include "llz_poly_device.cuh"
 
 namespace llz {
 
 namespace {
 
-constexpr int kPG = 8;             // phase groups per CTA
-constexpr int kCG = 16;            // cycle groups per CTA
-constexpr int kBankThreads = kPG * kCG;
+constexpr int kStages = 3;        // chunk pipeline depth: a warp may run two chunks ahead of the slowest one
 constexpr int kRawSlack = 64;      // X' rows beyond K' index up to KC samples before the span: finite garbage times zero taps
 
 struct BankGeom {
@@ -36,22 +39,28 @@ struct BankGeom {
     int raw_cap;                   // int16 elements reserved for the staged span
 };
 
-template <typename TA, int TP, int TJ, int KC, int MODE>
-__global__ void __launch_bounds__(kBankThreads, 3)
+// CTA = PG phase groups x CG cycle groups of threads; thread tile TP phases x TJ consecutive cycles.
+template <typename TA, int TP, int TJ, int PG, int CG, int KC, bool XI16, int MODE>
+__global__ void __launch_bounds__(PG * CG, (PG * CG == 64) ? 4 : (sizeof(TA) == 4 ? 3 : 2))
 poly_bank_kernel(PolyLaunch a, BankGeom geo)
 {
+    constexpr int kPG = PG, kCG = CG, kBankThreads = PG * CG;
+    // X' element type in shared memory: int16 (converted in registers, one LDS.128 = 8 cycles) or the accumulator type
+    using XT = typename std::conditional<XI16, int16_t, TA>::type;
+    static_assert(!XI16 || TJ == 8, "int16 X': a thread's cycles are one 16-byte vector of samples");
     constexpr int PB = kPG * TP;
     constexpr int JB = kCG * TJ;
     constexpr int VU = 16 / (int)sizeof(TA);          // elements per 16-byte vector
-    static_assert(TP % VU == 0 && TJ % VU == 0, "thread tile must be whole vectors");
+    static_assert(TP % VU == 0, "a thread's phases must be whole vectors");
     using V = typename Vec16<TA>::type;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    TA *Xs = reinterpret_cast<TA *>(smem_raw + 16);            // [2][KC][JB]
-    TA *Gs = Xs + 2 * KC * JB;                                 // [2][KC][PB]
-    int16_t *raw = reinterpret_cast<int16_t *>(Gs + 2 * KC * PB) + kRawSlack;   // kRawSlack elements of slack in front
+    TA *Gs = reinterpret_cast<TA *>(smem_raw + 16);            // [kStages][KC][PB]
+    XT *Xs = reinterpret_cast<XT *>(Gs + kStages * KC * PB);   // [kStages][KC][JB]
+    int16_t *raw = reinterpret_cast<int16_t *>(Xs + kStages * KC * JB) + kRawSlack;   // kRawSlack elements of slack in front
     __shared__ int s_shift[PB];                                // c_hi - c_l per phase of the tile
+    __shared__ uint64_t s_full[kStages], s_empty[kStages];     // chunk pipeline: stage filled / stage drained
 
     const int tid = threadIdx.x;
     const int pg = tid / kCG, cg = tid % kCG;
@@ -93,6 +102,12 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
     } else {
         for (int e = tid; e < rawn; e += kBankThreads) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
     }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&s_full[i], kBankThreads);
+            mbar_init(&s_empty[i], kBankThreads);
+        }
+    }
     for (int l = tid; l < PB; l += kBankThreads)
         s_shift[l] = (l < pbv) ? c_hi - (int)(((long long)(l0 + l) * M) / L) : 0;   // phases past L: any finite taps
     __syncthreads();
@@ -103,14 +118,17 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
     // The transposed bank [k][L] is uploaded with zero rows before row 0 and after row Q-1 (PolyLaunch::bank_pad),
     // so G'[k'][l] = bankT[(k' - shift_l)*L + l0 + l] needs no bounds checks; rows k' >= K' of X' meet only zeros.
     const TA *bankT = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.cbankT64) : reinterpret_cast<const TA *>(a.cbankT32);
+    static_assert(kBankThreads % PB == 0, "G' builder: a pass of the CTA covers whole rows");
+    static_assert(kBankThreads % JB == 0 || JB % kBankThreads == 0, "X' builder: whole rows per pass or whole passes per row");
     constexpr int GR = kBankThreads / PB;                      // G' rows covered by one pass of the CTA
     constexpr int GE = KC / GR;                                // G' elements per thread per chunk
-    constexpr int XR = kBankThreads / JB;                      // X' rows covered by one pass
-    constexpr int XE = KC / XR;
-    static_assert(kBankThreads % PB == 0 && kBankThreads % JB == 0 && KC % GR == 0 && KC % XR == 0, "tile shape");
+    constexpr int XC = (JB > kBankThreads) ? JB / kBankThreads : 1;      // X' columns per thread
+    constexpr int XR = (JB > kBankThreads) ? 1 : kBankThreads / JB;      // X' rows covered by one pass
+    constexpr int XE = KC / XR;                                // X' rows per thread per chunk
+    static_assert(KC % GR == 0 && KC % XR == 0, "tile shape");
     const int gl = tid % PB, gk = tid / PB;                    // this thread's G' column and first row
     const TA *gsrc = bankT + ((long long)gk - s_shift[gl]) * L + l0 + gl;
-    const int xj = tid % JB, xk = tid / JB;                    // this thread's X' column and first row
+    const int xj = tid % JB, xk = (JB > kBankThreads) ? 0 : tid / JB;    // this thread's first X' column and first row
     const int16_t *xsrc = rawp + xj * M + (KP - 1) - xk;
     TA gpre[GE];
 
@@ -124,11 +142,13 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
 #pragma unroll
         for (int i = 0; i < GE; ++i) dst[i * kBankThreads] = gpre[i];
     };
-    auto build_x = [&](int chunk, int buf) {                   // X'[k'][j] = raw[j*M + (K'-1) - k']
-        TA *dst = Xs + buf * KC * JB + tid;
+    auto build_x = [&](int chunk, int buf) {                   // X'[k'][j] = raw[j*M + (K'-1) - k'] (still int16)
+        XT *dst = Xs + buf * KC * JB + xk * JB + xj;
         const int16_t *src = xsrc - chunk * KC;
 #pragma unroll
-        for (int i = 0; i < XE; ++i) dst[i * kBankThreads] = (TA)src[-i * XR];
+        for (int i = 0; i < XE; ++i)
+#pragma unroll
+            for (int c = 0; c < XC; ++c) dst[i * XR * JB + c * kBankThreads] = (XT)src[c * kBankThreads * M - i * XR];
     };
 
     // ---- main loop ----------------------------------------------------------------------------------------
@@ -138,40 +158,79 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
 #pragma unroll
         for (int t = 0; t < TJ; ++t) acc[p][t] = TA(0);
 
+    // Chunk c lives in stage c % kStages.  Every thread builds its share of chunk c+2 after its own MACs of chunk c
+    // and signals s_full; it starts chunk c when all shares have arrived.  No CTA-wide barrier in the loop: warps
+    // drift up to two chunks apart, so one warp's build / shared-memory latency is covered by the others' FMAs.
     const int nchunks = (KP + KC - 1) / KC;
-    load_g(0);
-    store_g(0);
-    build_x(0, 0);
-    __syncthreads();
+#pragma unroll
+    for (int c0 = 0; c0 < 2; ++c0) {
+        if (c0 < nchunks) {
+            load_g(c0);
+            store_g(c0);
+            build_x(c0, c0);
+            mbar_arrive(&s_full[c0]);
+        }
+    }
     for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        if (c + 1 < nchunks) load_g(c + 1);
+        const int buf = c % kStages;
+        const int nxt = (c + 2) % kStages;
+        const bool produce = c + 2 < nchunks;
+        if (produce) load_g(c + 2);                            // global loads in flight during the MACs
+        mbar_wait(&s_full[buf], (c / kStages) & 1);
         const TA *gb = Gs + buf * KC * PB + pg * TP;
-        const TA *xb = Xs + buf * KC * JB + cg * VU;
-#pragma unroll 4
+        const XT *xb = Xs + buf * KC * JB + cg * TJ;
+        // fragments double-buffered in registers: the LDS of row kk+1 are in flight while row kk's FMAs issue
+        constexpr int NB = (TP * TJ <= 64) ? 2 : 1;            // big tiles: no room for a second fragment set
+        constexpr int XW = TJ * (int)sizeof(XT) / 16;          // 16-byte vectors of X' per thread per row
+        TA g[NB][TP];
+        uint4 xr[NB][XW];
+        auto load_row = [&](int kk, int slot) {
+#pragma unroll
+            for (int p = 0; p < TP; p += VU) unpack(*reinterpret_cast<const V *>(gb + kk * PB + p), &g[slot][p]);
+#pragma unroll
+            for (int q = 0; q < XW; ++q) xr[slot][q] = reinterpret_cast<const uint4 *>(xb + kk * JB)[q];
+        };
+        if (NB == 2) load_row(0, 0);
+#pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
-            TA g[TP], xv[TJ];
+            if (NB == 2) {
+                if (kk + 1 < KC) load_row(kk + 1, (kk + 1) & 1);
+            } else {
+                load_row(kk, 0);
+            }
+            TA xv[TJ];
+            if constexpr (XI16) {
+                const uint4 w = xr[kk & (NB - 1)][0];
+                xv[0] = (TA)(short)(w.x & 0xffffu); xv[1] = (TA)(short)(w.x >> 16);
+                xv[2] = (TA)(short)(w.y & 0xffffu); xv[3] = (TA)(short)(w.y >> 16);
+                xv[4] = (TA)(short)(w.z & 0xffffu); xv[5] = (TA)(short)(w.z >> 16);
+                xv[6] = (TA)(short)(w.w & 0xffffu); xv[7] = (TA)(short)(w.w >> 16);
+            } else {
 #pragma unroll
-            for (int p = 0; p < TP; p += VU) unpack(*reinterpret_cast<const V *>(gb + kk * PB + p), &g[p]);
-#pragma unroll
-            for (int q = 0; q < TJ / VU; ++q) unpack(*reinterpret_cast<const V *>(xb + kk * JB + q * kCG * VU), &xv[q * VU]);
+                for (int q = 0; q < XW; ++q) unpack(*reinterpret_cast<const V *>(&xr[kk & (NB - 1)][q]), &xv[q * VU]);
+            }
 #pragma unroll
             for (int p = 0; p < TP; ++p)
 #pragma unroll
-                for (int t = 0; t < TJ; ++t) acc[p][t] = mac<TA, false>(g[p], xv[t], acc[p][t]);
+                for (int t = 0; t < TJ; ++t) acc[p][t] = mac<TA, false>(g[kk & (NB - 1)][p], xv[t], acc[p][t]);
         }
-        if (c + 1 < nchunks) {
-            store_g(buf ^ 1);
-            build_x(c + 1, buf ^ 1);
+        mbar_arrive(&s_empty[buf]);                            // this thread is done reading stage buf
+        if (produce) {
+            // stage nxt last held chunk c-1: wait until every thread has drained it
+            if (c >= 1) mbar_wait(&s_empty[nxt], ((c - 1) / kStages) & 1);
+            store_g(nxt);
+            build_x(c + 2, nxt);
+            mbar_arrive(&s_full[nxt]);
         }
-        __syncthreads();
     }
 
     // ---- gain / guard / saturate / truncate / store --------------------------------------------------------------
     const long long o_end = a.o0 + a.n_out;
+    const bool unit_gain = a.gain == 1.0;                      // x * 1.0 == x exactly: skip the FP64 multiply
+    (void)unit_gain;
 #pragma unroll
     for (int t = 0; t < TJ; ++t) {
-        const int j = ((t / VU) * kCG + cg) * VU + (t % VU);   // cycle within the tile
+        const int j = cg * TJ + t;                             // cycle within the tile
         const long long obase = (j0 + j) * (long long)L + l0 + pg * TP;
         int16_t outv[TP];
         bool all_valid = true;
@@ -192,9 +251,8 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
                     }
                     r16 = poly_finish(__dmul_rn(v, a.gain));
                 } else {
-                    double v = __dmul_rn((double)acc[p][t], a.gain);
-                    const double nearest = rint(v);
-                    if (nearest != 0.0 && fabs(v - nearest) < a.guard_thr && st < 0) {
+                    double v = unit_gain ? (double)acc[p][t] : __dmul_rn((double)acc[p][t], a.gain);
+                    if (st < 0 && poly_near_nonzero_integer(v, a.guard_thr)) {
                         v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
                         atomicAdd(a.guard_count, 1ULL);
                     }
@@ -204,15 +262,18 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
             outv[p] = r16;
         }
         int16_t *yp = a.y + (long long)ch * a.y_stride + (obase - a.o0);
-        if (all_valid && (reinterpret_cast<uintptr_t>(yp) & (2 * TP - 1)) == 0) {
-            if constexpr (TP == 8) {
+        if (all_valid && (reinterpret_cast<uintptr_t>(yp) & 15u) == 0 && TP % 8 == 0) {
+#pragma unroll
+            for (int p = 0; p + 8 <= TP; p += 8) {
                 uint4 w;
-                w.x = (uint16_t)outv[0] | ((uint32_t)(uint16_t)outv[1] << 16);
-                w.y = (uint16_t)outv[2] | ((uint32_t)(uint16_t)outv[3] << 16);
-                w.z = (uint16_t)outv[4] | ((uint32_t)(uint16_t)outv[5] << 16);
-                w.w = (uint16_t)outv[6] | ((uint32_t)(uint16_t)outv[7] << 16);
-                *reinterpret_cast<uint4 *>(yp) = w;
-            } else {
+                w.x = (uint16_t)outv[p + 0] | ((uint32_t)(uint16_t)outv[p + 1] << 16);
+                w.y = (uint16_t)outv[p + 2] | ((uint32_t)(uint16_t)outv[p + 3] << 16);
+                w.z = (uint16_t)outv[p + 4] | ((uint32_t)(uint16_t)outv[p + 5] << 16);
+                w.w = (uint16_t)outv[p + 6] | ((uint32_t)(uint16_t)outv[p + 7] << 16);
+                *reinterpret_cast<uint4 *>(yp + p) = w;
+            }
+        } else if (all_valid && (reinterpret_cast<uintptr_t>(yp) & 3u) == 0) {
+            {
 #pragma unroll
                 for (int p = 0; p < TP; p += 2)
                     *reinterpret_cast<uint32_t *>(yp + p) = (uint16_t)outv[p] | ((uint32_t)(uint16_t)outv[p + 1] << 16);
@@ -227,19 +288,19 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
     }
 }
 
-template <typename TA, int TP, int TJ, int KC>
+template <typename TA, int TP, int TJ, int PG, int CG, int KC, bool XI16>
 size_t bank_smem(const PolyLaunch &a)
 {
-    constexpr int PB = kPG * TP, JB = kCG * TJ;
+    constexpr int PB = PG * TP, JB = CG * TJ;
     const int cspan_max = (int)(((long long)PB * a.M) / a.L) + 2;
     const size_t raw_cap = (size_t)(JB - 1) * a.M + cspan_max + a.ctaps + 16;
-    return 16 + (size_t)2 * KC * (JB + PB) * sizeof(TA) + (((raw_cap + kRawSlack) * 2 + 15) & ~(size_t)15);
+    return 16 + (size_t)kStages * KC * (PB * sizeof(TA) + JB * (XI16 ? 2 : sizeof(TA))) + (((raw_cap + kRawSlack) * 2 + 15) & ~(size_t)15);
 }
 
-template <typename TA, int TP, int TJ, int KC, int MODE>
+template <typename TA, int TP, int TJ, int PG, int CG, int KC, bool XI16, int MODE>
 int launch_bank(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
-    constexpr int PB = kPG * TP, JB = kCG * TJ;
+    constexpr int PB = PG * TP, JB = CG * TJ, kBankThreads = PG * CG;
     BankGeom geo{};
     geo.jc0 = a.o0 / a.L;
     const long long jc_last = (a.o0 + a.n_out - 1) / a.L;
@@ -248,8 +309,8 @@ int launch_bank(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     geo.n_phase_tiles = (a.L + PB - 1) / PB;
     const int cspan_max = (int)(((long long)PB * a.M) / a.L) + 2;
     geo.raw_cap = (JB - 1) * a.M + cspan_max + a.ctaps + 16;
-    const size_t smem = bank_smem<TA, TP, TJ, KC>(a);
-    auto kern = poly_bank_kernel<TA, TP, TJ, KC, MODE>;
+    const size_t smem = bank_smem<TA, TP, TJ, PG, CG, KC, XI16>(a);
+    auto kern = poly_bank_kernel<TA, TP, TJ, PG, CG, KC, XI16, MODE>;
     if (smem > 48 * 1024)
         LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
@@ -272,11 +333,13 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if ((a.ctaps + cspan) / a.ctaps > 2.5) return 0;
     constexpr size_t kLimit = 226 * 1024;
     if (a.acc == LLZ_CUDA_ACC_F32) {
-        if (bank_smem<float, 8, 8, 16>(a) > kLimit) return 0;
-        return launch_bank<float, 8, 8, 16, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
+        // f32: X' as float (the conversion unit cannot feed 8 I2F per 64 FFMA), 16 phases x 4 cycles per thread
+        if (bank_smem<float, 16, 4, 4, 32, 16, false>(a) > kLimit) return 0;
+        return launch_bank<float, 16, 4, 4, 32, 16, false, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
     }
-    if (bank_smem<double, 8, 4, 16>(a) > kLimit) return 0;
-    return launch_bank<double, 8, 4, 16, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
+    // f64: X' as int16 (I2F.F64 in registers), 8 phases x 8 cycles per thread: 80 bytes loaded per 64 DFMA
+    if (bank_smem<double, 8, 8, 8, 16, 8, true>(a) > kLimit) return 0;
+    return launch_bank<double, 8, 8, 8, 16, 8, true, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
 }
 
 }  // namespace llz

@@ -25,6 +25,7 @@
 //                        the M de-interleaved input streams; register-blocked SlidingMac core shared
 //                        with the FIR kernel (R outputs per thread, 2 LDS.128 per R*U FMAs).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "llz_poly_kernels.h"
 #include "llz_poly_device.cuh"
@@ -99,22 +100,33 @@ poly_general_kernel(PolyLaunch a, int tile_out)
 // X_sigma[j] = X(j*M + sigma), sigma = (M - rho) % M and d = (rho > 0).  Stream sigma is stored
 // shifted by d so that the newest sample of output q always sits at element HS + (q - qt):
 // 16-byte aligned windows for every residue.
-// row jj of `src` (M samples) -> element jj-1 of stream 0 and element jj of streams 1..M-1; MC = compile-time M (0: runtime)
-template <typename TA, int MC, int NT>
-__device__ __forceinline__ void slide_deinterleave(TA *xs, const int16_t *src, int len, int m_rt, int tid)
+// int16 -> accumulator type.  float: 2^23-biased integer add + one FADD (full-rate pipes) instead of I2F (1/8 rate).
+template <typename TA>
+__device__ __forceinline__ TA s16_to(int v)
 {
+    if constexpr (sizeof(TA) == 4) return __int_as_float(0x4B400000 + v) - 12582912.0f;   // exact for |v| < 2^22
+    else return (TA)v;
+}
+
+// row jj of `src` (M samples) -> element jj-1 of stream 0 and element jj of streams 1..M-1; MC = compile-time M (0: runtime).
+// SHARED tells the compiler the address space of src (LDS instead of generic loads).
+template <typename TA, int MC, int NT, bool SHARED>
+__device__ __forceinline__ void slide_deinterleave(TA *xs, const int16_t *src_generic, int len, int m_rt, int tid)
+{
+    const int16_t *src = src_generic;
+    if constexpr (SHARED) src = reinterpret_cast<const int16_t *>(__cvta_shared_to_generic(__cvta_generic_to_shared(src_generic)));
     const int M = MC ? MC : m_rt;
     const int rows = len + 1;
 #pragma unroll 2
     for (int jj = tid; jj < rows; jj += NT) {
         const int16_t *p = src + jj * M;
-        if (jj >= 1) xs[jj - 1] = (TA)p[0];
+        if (jj >= 1) xs[jj - 1] = s16_to<TA>(p[0]);
         if (jj < len) {
             if constexpr (MC != 0) {
 #pragma unroll
-                for (int sigma = 1; sigma < MC; ++sigma) xs[sigma * len + jj] = (TA)p[sigma];
+                for (int sigma = 1; sigma < MC; ++sigma) xs[sigma * len + jj] = s16_to<TA>(p[sigma]);
             } else {
-                for (int sigma = 1; sigma < M; ++sigma) xs[sigma * len + jj] = (TA)p[sigma];
+                for (int sigma = 1; sigma < M; ++sigma) xs[sigma * len + jj] = s16_to<TA>(p[sigma]);
             }
         }
     }
@@ -174,18 +186,17 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     // writes element jj-1 (sigma = 0) / jj (sigma > 0) of each stream, so a warp's stores are contiguous
     // within a stream (conflict-free).
     if (inside) {
-        const int16_t *src;
         if (bulk) {
             mbar_wait(bar, 0);
-            src = raw + (int)(rel - rel_al);
-        } else {
-            src = xc + rel;                                   // unaligned channel or the last granule of x
-        }
-        switch (M) {
-        case 2: slide_deinterleave<TA, 2, NT>(xs, src, len, 2, tid); break;
-        case 3: slide_deinterleave<TA, 3, NT>(xs, src, len, 3, tid); break;
-        case 4: slide_deinterleave<TA, 4, NT>(xs, src, len, 4, tid); break;
-        default: slide_deinterleave<TA, 0, NT>(xs, src, len, M, tid); break;
+            const int16_t *src = raw + (int)(rel - rel_al);
+            switch (M) {
+            case 2: slide_deinterleave<TA, 2, NT, true>(xs, src, len, 2, tid); break;
+            case 3: slide_deinterleave<TA, 3, NT, true>(xs, src, len, 3, tid); break;
+            case 4: slide_deinterleave<TA, 4, NT, true>(xs, src, len, 4, tid); break;
+            default: slide_deinterleave<TA, 0, NT, true>(xs, src, len, M, tid); break;
+            }
+        } else {                                              // unaligned channel or the last granule of x
+            slide_deinterleave<TA, 0, NT, false>(xs, xc + rel, len, M, tid);
         }
     } else {
         for (int jj = tid; jj < rows; jj += NT) {
@@ -210,7 +221,8 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     __syncthreads();                                          // every thread is done reading xs
     uint32_t *ys32 = reinterpret_cast<uint32_t *>(xs);
     const float gain_f = (float)a.gain;
-    (void)gain_f;
+    const bool unit_gain = a.gain == 1.0;                     // x * 1.0 == x exactly: skip the FP64 multiply
+    (void)gain_f; (void)unit_gain;
     const long long q0 = ot + (long long)tid * R;             // output index within this call
 #pragma unroll
     for (int r = 0; r < R; r += 2) {
@@ -224,10 +236,9 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
                 o2[i] = (int16_t)__float2int_rz(vf);
                 continue;
             }
-            double v = __dmul_rn((double)acc[r + i], a.gain);
+            double v = unit_gain ? (double)acc[r + i] : __dmul_rn((double)acc[r + i], a.gain);
             if constexpr (MODE == LLZ_CUDA_ACC_F64) {
-                const double nearest = rint(v);
-                if (nearest != 0.0 && fabs(v - nearest) < a.guard_thr && q0 + r + i < a.n_out) {
+                if (poly_near_nonzero_integer(v, a.guard_thr) && q0 + r + i < a.n_out) {
                     v = __dmul_rn(poly_reference_order_sum(a, xc, hc, a.o0 + q0 + r + i), a.gain);
                     atomicAdd(a.guard_count, 1ULL);
                 }
@@ -313,7 +324,9 @@ int pick_slide(const PolyLaunch &a, int *ntp_out)
     int best = 0, best_ntp = 0;
     double best_cost = 0.0;
     const int ru[3] = {7, 5, 3};
+    const char *force = getenv("LLZ_SLIDE_RU");               // tuning knob: force a tile variant (7, 5 or 3)
     for (int i = 0; i < 3; ++i) {
+        if (force && atoi(force) != ru[i]) continue;
         const int R = ru[i] * U, gran = (ru[i] + 1) * U;
         const int ntp = slide_pad(a, gran);
         if (ntp > avail) continue;

@@ -20,12 +20,21 @@ __device__ __forceinline__ int poly_sample(const PolyLaunch &a, const int16_t *x
     return 0;
 }
 
-// gain, saturate, truncate toward zero: llz_resample.c:594-601
+// saturate, truncate toward zero: llz_resample.c:596-601.  Truncating first (F2I.TRUNC saturates at the int32
+// range) and clamping the integer gives the same result as the reference's clamp-then-cast for every finite v,
+// and keeps the FP64 pipe free for the multiply-accumulates.
 __device__ __forceinline__ int16_t poly_finish(double v)
 {
-    if (v > 32767) v = 32767;
-    if (v < -32768) v = -32768;
-    return (int16_t)(int)v;
+    const int t = __double2int_rz(v);
+    return (int16_t)min(max(t, -32768), 32767);
+}
+
+// |v - nearest integer| < thr for a NON-ZERO nearest integer: the outputs whose truncation could differ between
+// two FP64 evaluation orders (truncation toward zero is continuous at 0)
+__device__ __forceinline__ bool poly_near_nonzero_integer(double v, double thr)
+{
+    const int n = __double2int_rn(v);                          // saturates: |v| >= 2^31 is far from n
+    return n != 0 && fabs(v - (double)n) < thr;
 }
 
 // The reference's own loop for one output: order[] walks the taps as llz_resample.c does, products
@@ -61,8 +70,7 @@ __device__ __forceinline__ int16_t poly_emit(const PolyLaunch &a, const int16_t 
         return poly_finish(__dmul_rn(v, a.gain));
     } else {
         double v = __dmul_rn((double)acc, a.gain);
-        const double nearest = rint(v);
-        if (MODE == LLZ_CUDA_ACC_F64 && nearest != 0.0 && fabs(v - nearest) < thr && a.single_tap[r] < 0) {
+        if (MODE == LLZ_CUDA_ACC_F64 && poly_near_nonzero_integer(v, thr) && a.single_tap[r] < 0) {
             v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
             atomicAdd(a.guard_count, 1ULL);
         }
