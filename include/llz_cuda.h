@@ -164,6 +164,25 @@ int llz_cuda_shard_resample_segments(long long n_in, int L, int M, int taps_per_
                                      int frame_in, int world, int rank, llz_cuda_segment_t *seg);
 
 /* ======================================================================================== */
+/* Interleaved PCM frames <-> planar channels                           */
+/* ======================================================================================== */
+/* The reference filters a multi-channel WAV as one interleaved mono stream (quirk R7,
+ * example/llz_resample/main.c:60-62); real PCM frames are interleaved while the banks above are
+ * planar.  These HBM-bound kernels convert between the two layouts on the device, fused with
+ * the sample-format conversion.  Device pointers, asynchronous on `stream`.
+ *   s16/s24 -> f32/f64: x / 2^15 (2^23);  -> s16: copy / arithmetic shift by 8
+ *   f32 -> s16 and f32/f64 -> s16/s24: trunc(clamp(x * 2^15 (2^23)))  (the reference's saturate +
+ *   C cast, llz_resample.c:596-601)                                                          */
+enum { LLZ_CUDA_PCM_S16 = 0, LLZ_CUDA_PCM_S24 = 1 /* packed 3-byte little endian */, LLZ_CUDA_PCM_F32 = 2 };
+enum { LLZ_CUDA_PLANAR_S16 = 0, LLZ_CUDA_PLANAR_F32 = 1, LLZ_CUDA_PLANAR_F64 = 2 };
+int llz_cuda_pcm_deinterleave(const void *d_frames, int pcm_format, int n_channels, long long n_frames,
+                              void *d_planar, int planar_type, long long planar_stride,
+                              llz_cuda_stream_t stream);
+int llz_cuda_pcm_interleave(const void *d_planar, int planar_type, long long planar_stride,
+                            int n_channels, long long n_frames, void *d_frames, int pcm_format,
+                            llz_cuda_stream_t stream);
+
+/* ======================================================================================== */
 /* Synthetic signals and machine probes (bench / tests)                                      */
 /* ======================================================================================== */
 /* per-channel 32-bit LCG of SURVEY.md section 8d, generated on the device with jump-ahead:

@@ -27,6 +27,8 @@ LPF, HPF, BPF, BSF = 0, 1, 2, 3
 F64, F64_STRICT, F32 = 0, 1, 2
 ACC_F64, ACC_F64_STRICT, ACC_F32 = 0, 1, 2
 KIND_DECIMATE, KIND_INTERP, KIND_RESAMPLE = 0, 1, 2
+PCM_S16, PCM_S24, PCM_F32 = 0, 1, 2
+PLANAR_S16, PLANAR_F32, PLANAR_F64 = 0, 1, 2
 FAIL = C.c_ulong(-1).value
 
 _dp = C.POINTER(C.c_double)
@@ -126,6 +128,8 @@ _SIGNATURES = [
     ("llz_cuda_shard_fir_segments", C.c_int, [_ll, C.c_int, C.c_int, C.c_int, C.POINTER(Segment)]),
     ("llz_cuda_shard_resample_segments", C.c_int,
      [_ll, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Segment)]),
+    ("llz_cuda_pcm_deinterleave", C.c_int, [_vp, C.c_int, C.c_int, _ll, _vp, C.c_int, _ll, _vp]),
+    ("llz_cuda_pcm_interleave", C.c_int, [_vp, C.c_int, _ll, C.c_int, _ll, _vp, C.c_int, _vp]),
     ("llz_cuda_synth_lcg", C.c_int, [_vp, _ll, C.c_int, _ll, C.c_int, C.c_uint, _vp]),
     ("llz_cuda_probe_fma", C.c_int, [C.c_int, _dp]),
 ]
@@ -453,6 +457,18 @@ class ResampleBank:
             self.close()
         except Exception:
             pass
+
+
+def pcm_deinterleave(d_frames, pcm_format: int, n_channels: int, n_frames: int, d_planar, planar_type: int,
+                     planar_stride: int, stream: int = 0):
+    _check(lib().llz_cuda_pcm_deinterleave(_ptr(d_frames), pcm_format, n_channels, n_frames, _ptr(d_planar),
+                                           planar_type, planar_stride, stream), "llz_cuda_pcm_deinterleave")
+
+
+def pcm_interleave(d_planar, planar_type: int, planar_stride: int, n_channels: int, n_frames: int, d_frames,
+                   pcm_format: int, stream: int = 0):
+    _check(lib().llz_cuda_pcm_interleave(_ptr(d_planar), planar_type, planar_stride, n_channels, n_frames,
+                                         _ptr(d_frames), pcm_format, stream), "llz_cuda_pcm_interleave")
 
 
 # ---- helpers for bench / tests -------------------------------------------------------------------------------
