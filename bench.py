@@ -37,13 +37,13 @@ FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4
 # name -> description of the synthetic workload
 WORKLOADS = {
     "c2": dict(kind="fir", desc="llz_fir 127-tap lowpass (fc 0.23, HAMMING), 1024 channels x 480000 samples (10 s @ 48 kHz)",
-               channels=1024, n=480_000, taps=127, fc=0.23, win=0, seed=12345),
+               channels=1024, n=480_000, taps=127, fc=0.23, win=0, seed=12345, shard="channel"),
     "c5": dict(kind="fir", desc="llz_fir 4095-tap lowpass (fc 0.11, KAISER), 16 channels x 57.6 M samples (5 min @ 192 kHz slice of the 1 h stream)",
-               channels=16, n=57_600_000, taps=4095, fc=0.11, win=2, seed=12345),
+               channels=16, n=57_600_000, taps=4095, fc=0.11, win=2, seed=12345, shard="time"),
     "c3": dict(kind="resample", desc="llz_resample 48 kHz -> 16 kHz (L=1, M=3, BLACKMAN, Q=134), 64 channels x 28.8 M samples (10 min)",
-               channels=64, n=28_800_000, L=1, M=3, k=0, win=1, seed=777),
+               channels=64, n=28_800_000, L=1, M=3, k=0, win=1, seed=777, shard="channel"),
     "c4": dict(kind="resample", desc="llz_resample 44.1 kHz -> 96 kHz (L=320, M=147, BLACKMAN, 256-tap bank: k=128, Q=257), 8 channels x 15.876 M samples (6 min slice of the 1 h stream)",
-               channels=8, n=47_040 * 338, L=320, M=147, k=128, win=1, seed=777),
+               channels=8, n=47_040 * 338, L=320, M=147, k=128, win=1, seed=777, shard="time"),
 }
 
 
@@ -216,13 +216,25 @@ def run_cuda(args):
     stream = torch.cuda.current_stream().cuda_stream
     hbm_peak, peak_src = peaks()
 
-    # ---- resident inputs (device LCG, the same integers the CPU arm generates) ----
+    # ---- this rank's share of the job --------------------------------------------------------------
+    # channel-sharded workloads (C2, C3): every rank runs its own full batch of channels (weak scaling, no collective).
+    # time-sharded workloads (C4, C5) at N > 1: the stated stream is cut into N segments; a rank owns
+    # [seg.in_start, +in_count) and reads `halo` samples before it (strong scaling, no collective: the halo comes
+    # with the rank's own slice of the input).
+    time_sharded = wl["shard"] == "time" and world > 1
+    scaling = "strong" if time_sharded else "weak"
+    seg_first, halo = 0, 0
     if wl["kind"] == "fir":
         f32 = args.dtype == "f32"
         tdt, es = (torch.float32, 4) if f32 else (torch.float64, 8)
-        dx = torch.empty(C_, n, dtype=tdt, device="cuda")
-        z.synth_lcg(dx, n, C_, n, 1 if f32 else 0, wl["seed"], stream)
-        dy = torch.empty_like(dx)
+        if time_sharded:
+            seg = z.shard_fir_segments(n, wl["taps"], world, rank)
+            seg_first, halo, n = seg.in_start - seg.halo, seg.halo, seg.in_count
+        dx_all = torch.empty(C_, halo + n, dtype=tdt, device="cuda")
+        z.synth_lcg_at(dx_all, halo + n, C_, seg_first, halo + n, 1 if f32 else 0, wl["seed"], stream)
+        x_stride = halo + n
+        dx = dx_all[:, halo:]
+        dy = torch.empty(C_, n, dtype=tdt, device="cuda")
         bank = z.FirBank(C_, z.F32 if f32 else z.F64, kind=z.LPF, flt_len=wl["taps"], fc1=wl["fc"], win=wl["win"])
         n_out = n
         flop_per_out, bytes_per_out = 2.0 * wl["taps"], 2.0 * es
@@ -233,16 +245,23 @@ def run_cuda(args):
 
         def step():
             bank.reset()
-            bank.run(dx, n, dy, n, n, stream)
+            if halo:
+                bank.set_history(dx_all, x_stride, stream)
+            bank.run(dx_all.data_ptr() + halo * es, x_stride, dy, n, n, stream)
         launches_per_step = 2                       # fir_tile_kernel + fir_history_kernel
     else:
         acc = z.ACC_F32 if args.dtype == "f32" else z.ACC_F64
-        dx = torch.empty(C_, n, dtype=torch.int16, device="cuda")
-        z.synth_lcg(dx, n, C_, n, 2, wl["seed"], stream)
         bank = z.ResampleBank(z.KIND_RESAMPLE, wl["L"], wl["M"], C_, win=wl["win"], k_override=wl["k"], acc=acc)
+        q = bank.info.taps_per_phase
+        if time_sharded:
+            seg = z.shard_resample_segments(n, wl["L"], wl["M"], q, bank.info.num_in, world, rank)
+            seg_first, halo, n = seg.in_start - seg.halo, seg.halo, seg.in_count
+        dx_all = torch.empty(C_, halo + n, dtype=torch.int16, device="cuda")
+        z.synth_lcg_at(dx_all, halo + n, C_, seg_first, halo + n, 2, wl["seed"], stream)
+        x_stride = halo + n
+        dx = dx_all[:, halo:]
         n_out = bank.out_len(n)
         dy = torch.empty(C_, n_out, dtype=torch.int16, device="cuda")
-        q = bank.info.taps_per_phase
         flop_per_out, bytes_per_out = 2.0 * q, 2.0 * (1.0 + wl["M"] / wl["L"])
         dtype_name = "s16 io / f32 acc" if args.dtype == "f32" else "s16 io / f64 acc"
         fma_peak_nominal = FP32_NOMINAL_TFLOPS if args.dtype == "f32" else FP64_NOMINAL_TFLOPS
@@ -250,8 +269,11 @@ def run_cuda(args):
         kernel = "poly_slide_kernel" if wl["L"] == 1 else "poly_bank_kernel"
 
         def step():
-            bank.reset()
-            bank.run(dx, n, n, dy, n_out, stream)
+            if halo:
+                bank.set_history(dx_all, x_stride, stream)        # also rewinds the phase to output index 0
+            else:
+                bank.reset()
+            bank.run(dx_all.data_ptr() + halo * 2, x_stride, n, dy, n_out, stream)
         launches_per_step = 2
     outs_per_step = C_ * n_out
 
@@ -282,7 +304,12 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = world * outs_per_step / (ms_step * 1e-3) / 1e6
+    outs_all = outs_per_step
+    if world > 1:
+        t = torch.tensor([float(outs_per_step)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        outs_all = int(t.item())
+    value = outs_all / (ms_step * 1e-3) / 1e6
 
     # per-rank kernel figures (rank 0's own time for the roofline of the kernel)
     ms_local = e0.elapsed_time(e1) / args.steps
@@ -298,12 +325,16 @@ def run_cuda(args):
         np_dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int16: np.int16}[dx.dtype]
         hx = z.host_alloc(in_bytes, np_dt).reshape(C_, n)
         hy = z.host_alloc(out_bytes, np_dt).reshape(C_, n_out)
-        torch.from_numpy(hx).copy_(dx)
+        torch.from_numpy(hx).copy_(dx)                # this rank's own samples (the halo stays in the bank's history)
         torch.cuda.synchronize()
         e_steps = max(1, min(args.steps, 5))
 
         def e2e_step():
-            bank.reset()
+            if halo:
+                bank.set_history(dx_all, x_stride, stream)
+                torch.cuda.synchronize()
+            else:
+                bank.reset()
             if wl["kind"] == "fir":
                 bank.run_host(hx, n, hy, n, n)
             else:
@@ -321,7 +352,7 @@ def run_cuda(args):
             dt = float(t.item())
         # the result read back is the full output; verify it is the device-resident result
         same = bool(np.array_equal(hy[0, :4096], dy[0, :4096].cpu().numpy()))
-        e2e = {"value": world * outs_per_step * e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+        e2e = {"value": outs_all * e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                "d2h_bytes_per_step": out_bytes, "steps": e_steps, "matches_device_result": same,
                "api": "llz_cuda_fir_bank_run_host" if wl["kind"] == "fir" else "llz_cuda_resample_bank_run_host",
                "host_memory": "page-locked (llz_cuda_host_alloc)"}
@@ -355,10 +386,13 @@ def run_cuda(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": dtype_name, "data": "synthetic",
         "config": {"workload": wl["desc"], "name": args.workload, "channels_per_gpu": C_, "samples_per_channel": n,
-                   "outputs_per_step_per_gpu": outs_per_step, "sharding": "independent channels per rank, no collective",
+                   "outputs_per_step_per_gpu": outs_per_step,
+                   "sharding": ("time segments, each rank reads a %d-sample halo before its segment, no collective"
+                                % (wl["taps"] - 1 if wl["kind"] == "fir" else q - 1)) if time_sharded
+                   else "independent channels per rank, no collective",
                    "l2": f"inputs {dx.numel() * dx.element_size() / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
                    "input": "integer LCG noise generated on the device (SURVEY.md 8d)"},
         "roofline": {"kernel": kernel, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -192,6 +192,9 @@ int llz_cuda_pcm_interleave(const void *d_planar, int planar_type, long long pla
  * channel c uses seed0 + c; element i is the (i+1)-th LCG state.                             */
 int llz_cuda_synth_lcg(void *d_out, long long stride, int n_channels, long long n, int kind,
                        unsigned seed0, llz_cuda_stream_t stream);
+/* the same sequence from element `first` on (a rank's time segment of a longer stream) */
+int llz_cuda_synth_lcg_at(void *d_out, long long stride, int n_channels, long long first, long long n,
+                          int kind, unsigned seed0, llz_cuda_stream_t stream);
 /* register-resident FMA throughput of this GPU in TFLOP/s (dtype: LLZ_CUDA_F64 or LLZ_CUDA_F32) */
 int llz_cuda_probe_fma(int dtype, double *tflops);
 

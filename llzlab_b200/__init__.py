@@ -131,6 +131,7 @@ _SIGNATURES = [
     ("llz_cuda_pcm_deinterleave", C.c_int, [_vp, C.c_int, C.c_int, _ll, _vp, C.c_int, _ll, _vp]),
     ("llz_cuda_pcm_interleave", C.c_int, [_vp, C.c_int, _ll, C.c_int, _ll, _vp, C.c_int, _vp]),
     ("llz_cuda_synth_lcg", C.c_int, [_vp, _ll, C.c_int, _ll, C.c_int, C.c_uint, _vp]),
+    ("llz_cuda_synth_lcg_at", C.c_int, [_vp, _ll, C.c_int, _ll, _ll, C.c_int, C.c_uint, _vp]),
     ("llz_cuda_probe_fma", C.c_int, [C.c_int, _dp]),
 ]
 
@@ -474,6 +475,10 @@ def pcm_interleave(d_planar, planar_type: int, planar_stride: int, n_channels: i
 # ---- helpers for bench / tests -------------------------------------------------------------------------------
 def synth_lcg(d_out, stride: int, n_channels: int, n: int, kind: int, seed0: int, stream: int = 0):
     _check(lib().llz_cuda_synth_lcg(_ptr(d_out), stride, n_channels, n, kind, seed0, stream), "synth_lcg")
+
+
+def synth_lcg_at(d_out, stride: int, n_channels: int, first: int, n: int, kind: int, seed0: int, stream: int = 0):
+    _check(lib().llz_cuda_synth_lcg_at(_ptr(d_out), stride, n_channels, first, n, kind, seed0, stream), "synth_lcg_at")
 
 
 def probe_fma(dtype: int) -> float:

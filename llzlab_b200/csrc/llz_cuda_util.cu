@@ -24,13 +24,13 @@ __device__ __forceinline__ void lcg_jump(unsigned long long steps, uint32_t &s)
 constexpr int kLcgRun = 16;
 
 template <typename T, int KIND>
-__global__ void lcg_kernel(T *out, long long stride, long long n, uint32_t seed0)
+__global__ void lcg_kernel(T *out, long long stride, long long first, long long n, uint32_t seed0)
 {
     const int ch = blockIdx.y;
     const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kLcgRun;
     if (i0 >= n) return;
     uint32_t s = seed0 + (uint32_t)ch;
-    lcg_jump((unsigned long long)i0, s);
+    lcg_jump((unsigned long long)(first + i0), s);
     T *dst = out + (long long)ch * stride + i0;
     const int cnt = (int)min((long long)kLcgRun, n - i0);
     for (int j = 0; j < cnt; ++j) {
@@ -99,16 +99,23 @@ static int probe(double *tflops)
 extern "C" int llz_cuda_synth_lcg(void *d_out, long long stride, int n_channels, long long n, int kind,
                                   unsigned seed0, llz_cuda_stream_t stream)
 {
+    return llz_cuda_synth_lcg_at(d_out, stride, n_channels, 0, n, kind, seed0, stream);
+}
+
+extern "C" int llz_cuda_synth_lcg_at(void *d_out, long long stride, int n_channels, long long first, long long n,
+                                     int kind, unsigned seed0, llz_cuda_stream_t stream)
+{
     using namespace llz;
+    if (first < 0) { llz_set_error("synth_lcg: negative start index"); return -1; }
     if (n <= 0 || n_channels <= 0) return 0;
     if (n_channels > 65535) { llz_set_error("synth_lcg: too many channels"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     const long long runs = (n + kLcgRun - 1) / kLcgRun;
     dim3 grid((unsigned)((runs + 255) / 256), (unsigned)n_channels);
     switch (kind) {
-    case 0: lcg_kernel<double, 0><<<grid, 256, 0, st>>>((double *)d_out, stride, n, seed0); break;
-    case 1: lcg_kernel<float, 1><<<grid, 256, 0, st>>>((float *)d_out, stride, n, seed0); break;
-    case 2: lcg_kernel<int16_t, 2><<<grid, 256, 0, st>>>((int16_t *)d_out, stride, n, seed0); break;
+    case 0: lcg_kernel<double, 0><<<grid, 256, 0, st>>>((double *)d_out, stride, first, n, seed0); break;
+    case 1: lcg_kernel<float, 1><<<grid, 256, 0, st>>>((float *)d_out, stride, first, n, seed0); break;
+    case 2: lcg_kernel<int16_t, 2><<<grid, 256, 0, st>>>((int16_t *)d_out, stride, first, n, seed0); break;
     default: llz_set_error("synth_lcg: unknown kind %d", kind); return -1;
     }
     LLZ_CUDA_TRY(cudaGetLastError());
