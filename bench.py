@@ -413,17 +413,64 @@ def run_cuda(args):
     return 0
 
 
+def run_c1(args):
+    """BASELINE configs[0]: the example CLI's job (60 s mono 44.1 kHz s16 sweep -> 48 kHz) through the reference's
+    own frame-by-frame entry points (llz_resample_filter_init / llz_resample) with host buffers.  It is 113 frames
+    of 23,520 samples: a latency-bound drop-in path (one H2D, two launches and one D2H per frame), reported for
+    completeness; the roofline discussion belongs to C2-C5."""
+    import torch
+    import llzlab_b200 as z
+    import oracle
+    torch.cuda.set_device(0)
+    P, R = oracle.port(), oracle.ref()
+    seconds, rate = 60, 44100
+    t = np.arange(seconds * rate, dtype=np.float64) / rate
+    pcm = np.round(0.5 * 32767 * np.sin(2 * np.pi * (20.0 * t + (20000.0 - 20.0) / (2 * seconds) * t * t))).astype(np.int16)
+    r = z.Resampler(z.KIND_RESAMPLE, 160, 147, 1.0, z.BLACKMAN)
+    num_in = r.bytes_in // 2
+    frames = len(pcm) // num_in + 1                          # main.c:91-119
+    x = np.zeros(frames * num_in, np.int16)
+    x[:len(pcm)] = pcm
+    times = []
+    for it in range(args.warmup + args.steps):
+        h = z.Resampler(z.KIND_RESAMPLE, 160, 147, 1.0, z.BLACKMAN)
+        t0 = time.perf_counter()
+        y = h.stream(x)
+        dt = time.perf_counter() - t0
+        h.close()
+        if it >= args.warmup:
+            times.append(dt)
+    dt = statistics.median(times)
+    t0 = time.perf_counter()
+    ref_y = R.resample_stream(160, 147, 1.0, 1, x) if R is not None else P.resample_run(P.resample_plan(160, 147, 1), 1.0, x, len(y))
+    ref_dt = time.perf_counter() - t0
+    line = {"metric": METRIC, "value": len(y) / dt / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None,
+            "dtype": "s16 io / f64 acc", "data": "synthetic",
+            "config": {"workload": "example/llz_resample job: 60 s mono 44.1 kHz s16 sine sweep -> 48 kHz (L=160, M=147, BLACKMAN, Q=45), "
+                                   "113 frames through llz_resample with host buffers", "name": "c1", "timing": "host wall clock around the frame loop (synchronous API)"},
+            "bit_identical_to_reference": bool(np.array_equal(y, ref_y)),
+            "cpu_baseline": {"value": len(ref_y) / ref_dt / 1e6, "unit": UNIT, "cores": 1, "kind": "reference" if R is not None else "port",
+                             "sample": "the whole job (2,892,800 outputs)"},
+            "e2e": {"value": len(y) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(y.nbytes)},
+            "gpu_launches": 2 * frames * args.steps}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=["c1"] + sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
+    if args.workload == "c1":
+        return run_c1(args) if int(os.environ.get("RANK", "0")) == 0 else 0
     if args.impl == "reference":
         return run_reference(args)
     return run_cuda(args)
