@@ -2,7 +2,12 @@
  * llz_resample_cuda -- command-line harness over libllzfilter_cuda with the flags and the output-length
  * semantics of the reference's example/llz_resample (main.c:22-130, llz_parseopt.c:164-297):
  *
- *   llz_resample_cuda -i in.wav -o out.wav [-t 0|1|2] [-u up] [-d down] [-g gain]
+ *   llz_resample_cuda -i in.wav -o out.wav [-t 0|1|2] [-u up] [-d down] [-g gain] [-w]
+ *
+ *   -w  whole-file mode: read all samples, zero-pad to the same frame count, and run them through the handle in
+ *       ONE call of the batched entry point (llz_cuda_resample_bank_run_host) instead of one llz_resample call
+ *       per frame.  The bytes written are identical (a call of any length continues the stream exactly like
+ *       the frame loop); it only removes the per-frame PCIe round trips.
  *
  *   -t 0 decimate by -d, 1 interpolate by -u, 2 (default) resample by -u/-d; defaults 160/147, gain 1.
  *   Giving only -u sets down = 1, only -d sets up = 1 (llz_parseopt.c:137-141).  Window: BLACKMAN (main.c:67-75).
@@ -72,12 +77,12 @@ static void wav_write_header(FILE *fp, const wav_info_t *w, uint32_t data_bytes)
 int main(int argc, char **argv)
 {
     const char *in = NULL, *out = NULL;
-    int type = 2, up = 160, down = 147, got_up = 0, got_down = 0, quiet = 0;
+    int type = 2, up = 160, down = 147, got_up = 0, got_down = 0, quiet = 0, whole = 0;
     double gain = 1.0;
     static struct option lopts[] = {{"help", 0, 0, 'h'}, {"input", 1, 0, 'i'}, {"output", 1, 0, 'o'}, {"type", 1, 0, 't'},
-                                    {"down", 1, 0, 'd'}, {"up", 1, 0, 'u'}, {"gain", 1, 0, 'g'}, {"quiet", 0, 0, 'q'}, {0, 0, 0, 0}};
+                                    {"down", 1, 0, 'd'}, {"up", 1, 0, 'u'}, {"gain", 1, 0, 'g'}, {"quiet", 0, 0, 'q'}, {"whole", 0, 0, 'w'}, {0, 0, 0, 0}};
     int c;
-    while ((c = getopt_long(argc, argv, "hqi:o:t:d:u:g:", lopts, NULL)) != -1) {
+    while ((c = getopt_long(argc, argv, "hqwi:o:t:d:u:g:", lopts, NULL)) != -1) {
         switch (c) {
         case 'i': in = optarg; break;
         case 'o': out = optarg; break;
@@ -86,6 +91,7 @@ int main(int argc, char **argv)
         case 'u': up = atoi(optarg); got_up = 1; break;
         case 'g': gain = atof(optarg); break;
         case 'q': quiet = 1; break;
+        case 'w': whole = 1; break;
         default:
             fprintf(stderr, "usage: %s -i in.wav -o out.wav [-t 0|1|2] [-u up] [-d down] [-g gain]\n", argv[0]);
             return c == 'h' ? 0 : -1;
@@ -126,7 +132,28 @@ int main(int argc, char **argv)
 
     uint32_t total = 0;
     int frames = 0;
-    for (int last = 0; !last;) {
+    if (whole) {
+        /* same frame count as the loop below: floor(bytes / in_bytes) + 1, zero padded (main.c:91-119) */
+        long pos = ftell(fi);
+        fseek(fi, 0, SEEK_END);
+        long data_bytes = ftell(fi) - pos;
+        fseek(fi, pos, SEEK_SET);
+        if (data_bytes < 0) data_bytes = 0;
+        frames = (int)(data_bytes / in_bytes) + 1;
+        size_t n_in = (size_t)frames * info.num_in, n_out_cap = (size_t)frames * info.num_out;
+        short *xi = calloc(n_in, 2), *xo = malloc(n_out_cap * 2);
+        if (!xi || !xo) { fprintf(stderr, "out of memory\n"); return -1; }
+        if (fread(xi, 1, (size_t)data_bytes, fi) != (size_t)data_bytes) { fprintf(stderr, "short read\n"); return -1; }
+        long long n_out = 0;
+        if (llz_cuda_resample_bank_run_host(h, xi, (long long)n_in, (long long)n_in, xo, (long long)n_out_cap, &n_out) != 0) {
+            fprintf(stderr, "run failed: %s\n", llz_cuda_last_error());
+            return -1;
+        }
+        fwrite(xo, 2, (size_t)n_out, fo);
+        total = (uint32_t)(n_out * 2);
+        free(xi); free(xo);
+    }
+    for (int last = whole; !last;) {
         memset(bi, 0, (size_t)in_bytes);
         if ((int)fread(bi, 1, (size_t)in_bytes, fi) < in_bytes) last = 1;
         int rc = type == 0 ? llz_decimate(h, bi, in_bytes, bo, &out_bytes)

@@ -62,6 +62,9 @@ def test_config1_cli_is_byte_identical(sweep, port, cuda):
     x[:len(pcm)] = pcm
     want = port.resample_run(plan, 1.0, x, 2_892_800)
     assert np.array_equal(np.frombuffer(ours[44:], dtype="<i2"), want)
+    # whole-file mode: one batched call instead of 113 frame calls, same bytes
+    run(OUR_CLI, ["-i", "sweep.wav", "-o", "ours_whole.wav", "-q", "-w"], d)
+    assert open(d / "ours_whole.wav", "rb").read() == ours
     if os.path.exists(REF_CLI):
         run(REF_CLI, ["-i", "sweep.wav", "-o", "ref.wav"], d)
         assert open(d / "ref.wav", "rb").read() == ours
@@ -84,6 +87,8 @@ def test_other_cli_modes(sweep, args, port, cuda):
     tag = "_".join(a.strip("-") for a in args)
     run(OUR_CLI, ["-i", "short.wav", "-o", f"o_{tag}.wav", "-q"] + args, d)
     ours = open(d / f"o_{tag}.wav", "rb").read()
+    run(OUR_CLI, ["-i", "short.wav", "-o", f"w_{tag}.wav", "-q", "-w"] + args, d)
+    assert open(d / f"w_{tag}.wav", "rb").read() == ours
     opt = dict(zip(args[::2], args[1::2]))
     mode = int(opt.get("-t", 2))
     gain = float(opt.get("-g", 1.0))
