@@ -17,10 +17,13 @@
 
 namespace llz {
 
-constexpr int kFirThreads = 256;
+#ifndef LLZ_FIR_THREADS
+#define LLZ_FIR_THREADS 128
+#endif
+constexpr int kFirThreads = LLZ_FIR_THREADS;
 
 template <typename T, int R, bool STRICT, bool BLOCKED>
-__global__ void __launch_bounds__(kFirThreads, 2)
+__global__ void __launch_bounds__(kFirThreads, 512 / kFirThreads)
 fir_tile_kernel(FirLaunch<T> a)
 {
     using SM = SlidingMac<T, R>;

@@ -295,7 +295,7 @@ namespace {
 
 constexpr size_t kSmemBudget = 226 * 1024;
 #ifndef LLZ_SLIDE_THREADS
-#define LLZ_SLIDE_THREADS 128
+#define LLZ_SLIDE_THREADS 64
 #endif
 constexpr int kSlideThreads = LLZ_SLIDE_THREADS;   // threads per CTA of the sliding kernel
 
