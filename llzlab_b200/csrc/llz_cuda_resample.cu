@@ -100,18 +100,10 @@ poly_general_kernel(PolyLaunch a, int tile_out)
 // X_sigma[j] = X(j*M + sigma), sigma = (M - rho) % M and d = (rho > 0).  Stream sigma is stored
 // shifted by d so that the newest sample of output q always sits at element HS + (q - qt):
 // 16-byte aligned windows for every residue.
-// int16 -> accumulator type.  float: 2^23-biased integer add + one FADD (full-rate pipes) instead of I2F (1/8 rate).
-template <typename TA>
-__device__ __forceinline__ TA s16_to(int v)
-{
-    if constexpr (sizeof(TA) == 4) return __int_as_float(0x4B400000 + v) - 12582912.0f;   // exact for |v| < 2^22
-    else return (TA)v;
-}
-
 // row jj of `src` (M samples) -> element jj-1 of stream 0 and element jj of streams 1..M-1; MC = compile-time M (0: runtime).
 // SHARED tells the compiler the address space of src (LDS instead of generic loads).
-template <typename TA, int MC, int NT, bool SHARED>
-__device__ __forceinline__ void slide_deinterleave(TA *xs, const int16_t *src_generic, int len, int m_rt, int tid)
+template <int MC, int NT, bool SHARED>
+__device__ __forceinline__ void slide_deinterleave(int16_t *xs, const int16_t *src_generic, int len, int m_rt, int tid)
 {
     const int16_t *src = src_generic;
     if constexpr (SHARED) src = reinterpret_cast<const int16_t *>(__cvta_shared_to_generic(__cvta_generic_to_shared(src_generic)));
@@ -120,13 +112,13 @@ __device__ __forceinline__ void slide_deinterleave(TA *xs, const int16_t *src_ge
 #pragma unroll 2
     for (int jj = tid; jj < rows; jj += NT) {
         const int16_t *p = src + jj * M;
-        if (jj >= 1) xs[jj - 1] = s16_to<TA>(p[0]);
+        if (jj >= 1) xs[jj - 1] = p[0];
         if (jj < len) {
             if constexpr (MC != 0) {
 #pragma unroll
-                for (int sigma = 1; sigma < MC; ++sigma) xs[sigma * len + jj] = s16_to<TA>(p[sigma]);
+                for (int sigma = 1; sigma < MC; ++sigma) xs[sigma * len + jj] = p[sigma];
             } else {
-                for (int sigma = 1; sigma < M; ++sigma) xs[sigma * len + jj] = s16_to<TA>(p[sigma]);
+                for (int sigma = 1; sigma < M; ++sigma) xs[sigma * len + jj] = p[sigma];
             }
         }
     }
@@ -136,7 +128,7 @@ template <typename TA, int R, int MODE, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT)
 poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_stride /* row length of the uploaded taps */)
 {
-    using SM = SlidingMac<TA, R>;
+    using SM = SlidingMac<TA, R, int16_t>;                   // streams stay int16 in shared memory
     using V = typename Vec16<TA>::type;
     constexpr int TILE = NT * R;
     constexpr int U = SM::U;
@@ -148,8 +140,8 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     const int rows = len + 1;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     TA *taps_s = reinterpret_cast<TA *>(smem_raw + 16);       // [M][ntp]
-    TA *xs = taps_s + (size_t)M * ntp;                        // [M][HS + TILE]
-    int16_t *raw = reinterpret_cast<int16_t *>(xs + (size_t)M * len);   // [rows*M + 16] input span as it lies in x
+    int16_t *xs = reinterpret_cast<int16_t *>(taps_s + (size_t)M * ntp);   // [M][HS + TILE] de-interleaved streams
+    int16_t *raw = xs + (((size_t)M * len + 7) & ~(size_t)7);            // [rows*M + 16] input span as it lies in x
 
     const int tid = threadIdx.x;
     const int ch = blockIdx.y;
@@ -190,20 +182,20 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
             mbar_wait(bar, 0);
             const int16_t *src = raw + (int)(rel - rel_al);
             switch (M) {
-            case 2: slide_deinterleave<TA, 2, NT, true>(xs, src, len, 2, tid); break;
-            case 3: slide_deinterleave<TA, 3, NT, true>(xs, src, len, 3, tid); break;
-            case 4: slide_deinterleave<TA, 4, NT, true>(xs, src, len, 4, tid); break;
-            default: slide_deinterleave<TA, 0, NT, true>(xs, src, len, M, tid); break;
+            case 2: slide_deinterleave<2, NT, true>(xs, src, len, 2, tid); break;
+            case 3: slide_deinterleave<3, NT, true>(xs, src, len, 3, tid); break;
+            case 4: slide_deinterleave<4, NT, true>(xs, src, len, 4, tid); break;
+            default: slide_deinterleave<0, NT, true>(xs, src, len, M, tid); break;
             }
         } else {                                              // unaligned channel or the last granule of x
-            slide_deinterleave<TA, 0, NT, false>(xs, xc + rel, len, M, tid);
+            slide_deinterleave<0, NT, false>(xs, xc + rel, len, M, tid);
         }
     } else {
         for (int jj = tid; jj < rows; jj += NT) {
             const long long s0 = s_base + (long long)jj * M;
-            if (jj >= 1) xs[jj - 1] = (TA)poly_sample(a, xc, hc, s0);
+            if (jj >= 1) xs[jj - 1] = (int16_t)poly_sample(a, xc, hc, s0);
             if (jj < len)
-                for (int sigma = 1; sigma < M; ++sigma) xs[(size_t)sigma * len + jj] = (TA)poly_sample(a, xc, hc, s0 + sigma);
+                for (int sigma = 1; sigma < M; ++sigma) xs[(size_t)sigma * len + jj] = (int16_t)poly_sample(a, xc, hc, s0 + sigma);
         }
     }
     __syncthreads();
@@ -213,7 +205,7 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     for (int r = 0; r < R; ++r) acc[r] = TA(0);
     for (int rho = 0; rho < M; ++rho) {
         const int sigma = rho ? M - rho : 0;
-        const TA *win = xs + (size_t)sigma * len + HS + tid * R - U;
+        const int16_t *win = xs + (size_t)sigma * len + HS + tid * R - U;
         SM::template run<false>(acc, win, taps_s + (size_t)rho * ntp, ntp);
     }
 
@@ -299,11 +291,12 @@ constexpr size_t kSmemBudget = 226 * 1024;
 #endif
 constexpr int kSlideThreads = LLZ_SLIDE_THREADS;   // threads per CTA of the sliding kernel
 
-// barrier + taps [M][ntp] + streams [M][ntp + tile] + raw int16 span
+// barrier + taps [M][ntp] (accumulator type) + int16 streams [M][ntp + tile] + raw int16 span
 inline size_t slide_smem_bytes(int M, int ntp, int tile, size_t elem)
 {
     const size_t raw = (((size_t)(ntp + tile + 1) * M + 16) * 2 + 15) & ~(size_t)15;
-    return 16 + ((size_t)M * ntp + (size_t)M * (ntp + tile)) * elem + raw;
+    const size_t streams = ((((size_t)M * (ntp + tile) + 7) & ~(size_t)7)) * 2;      // int16
+    return 16 + (size_t)M * ntp * elem + streams + raw;
 }
 
 // taps per residue padded to the SlidingMac granularity of a tile variant
@@ -313,8 +306,8 @@ inline int slide_pad(const PolyLaunch &a, int gran)
     return (per + gran - 1) / gran * gran;
 }
 
-// Tile variants of the sliding kernel: R/U in {7, 5, 3} (odd: conflict-free LDS.128), i.e. tap granularity
-// {8, 6, 4} vectors.  Pick the least padded one that fits (two CTAs per SM preferred), larger tiles on ties.
+// Tile variants of the sliding kernel: R/U in {11, 7, 5, 3} (odd: conflict-free loads), i.e. tap granularity
+// {12, 8, 6, 4} vectors.  Larger R amortises the per-chunk loads and conversions over more FMAs.  Pick the least padded one that fits (two CTAs per SM preferred), larger tiles on ties.
 // Returns R/U, or 0 for the general kernel.
 template <typename TA>
 int pick_slide(const PolyLaunch &a, int *ntp_out)
@@ -323,10 +316,11 @@ int pick_slide(const PolyLaunch &a, int *ntp_out)
     const int avail = (sizeof(TA) == 8) ? a.slide_ntp64 : a.slide_ntp32;   // row length of the uploaded taps
     int best = 0, best_ntp = 0;
     double best_cost = 0.0;
-    const int ru[3] = {7, 5, 3};
-    const char *force = getenv("LLZ_SLIDE_RU");               // tuning knob: force a tile variant (7, 5 or 3)
-    for (int i = 0; i < 3; ++i) {
+    const int ru[4] = {11, 7, 5, 3};
+    const char *force = getenv("LLZ_SLIDE_RU");               // tuning knob: force a tile variant (11, 7, 5 or 3)
+    for (int i = 0; i < 4; ++i) {
         if (force && atoi(force) != ru[i]) continue;
+        if (!force && ru[i] == 11 && sizeof(TA) == 4) continue;   // measured: the 44-output float tile is slower than 20 (C3: 4.9 vs 3.9 ms)
         const int R = ru[i] * U, gran = (ru[i] + 1) * U;
         const int ntp = slide_pad(a, gran);
         if (ntp > avail) continue;
@@ -413,6 +407,7 @@ int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     }
     switch (a.acc) {
     case LLZ_CUDA_ACC_F64:
+        if (ru == 11) return launch_slide<double, 22, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);
         if (ru == 7) return launch_slide<double, 14, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);
         if (ru == 5) return launch_slide<double, 10, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);
         if (ru == 3) return launch_slide<double, 6, LLZ_CUDA_ACC_F64>(a, ntp, n_channels, stream);
@@ -420,6 +415,7 @@ int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     case LLZ_CUDA_ACC_F64_STRICT:
         return launch_general<double, LLZ_CUDA_ACC_F64_STRICT>(a, n_channels, stream);
     case LLZ_CUDA_ACC_F32:
+        if (ru == 11) return launch_slide<float, 44, LLZ_CUDA_ACC_F32>(a, ntp, n_channels, stream);
         if (ru == 7) return launch_slide<float, 28, LLZ_CUDA_ACC_F32>(a, ntp, n_channels, stream);
         if (ru == 5) return launch_slide<float, 20, LLZ_CUDA_ACC_F32>(a, ntp, n_channels, stream);
         if (ru == 3) return launch_slide<float, 12, LLZ_CUDA_ACC_F32>(a, ntp, n_channels, stream);
