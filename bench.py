@@ -185,6 +185,23 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Run this rank on the CPUs NVML reports as local to its GPU, so that the page-locked host buffers of the
+    end-to-end leg are first-touched on the GPU's own NUMA node (with N ranks on a two-socket host, buffers on the
+    wrong socket push every DMA across the inter-socket link)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:                               # noqa: BLE001  (affinity is an optimisation, never a requirement)
+        pass
+
+
 # ---- the CUDA arm ------------------------------------------------------------------------------------------------------
 def run_cuda(args):
     import torch
@@ -196,6 +213,7 @@ def run_cuda(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libllzfilter_cuda has no CPU path (use --impl reference for the CPU arm)")
+    bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator comes up; keep stdout for the JSON line
