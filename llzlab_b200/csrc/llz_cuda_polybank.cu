@@ -21,6 +21,8 @@
 // Phase (m mod L) and input index (floor(m*M/L)) are pure integer arithmetic, identical to the reference's
 // sequence; the FP64 mode carries the same near-integer guard as the other kernels (bit-identical int16).
 // Padding cost: K'/Q (e.g. 286/257 for C4 with 64-phase tiles).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "llz_poly_device.cuh"
@@ -288,6 +290,219 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
     }
 }
 
+// ---- FP64 tensor-core variant (exact mode) -----------------------------------------------------------------------
+//
+// Same tile, staging and chunk pipeline as poly_bank_kernel, but the 64-phase x 128-cycle product Y = G'^T X' is
+// issued as DMMA.8x8x4 (mma.sync.m8n8k4.f64).  Why, on B200: (1) tools/probe_pipes.cu measures DMMA at 37.1 TFLOP/s
+// against 34.1 for DFMA, and the two do not overlap, so the tensor path is simply the faster way into the same FP64
+// units; (2) a warp tile of 32 phases x 32 cycles needs only 32 accumulator doubles (64 registers) and loads 64
+// bytes per thread per 128 FMAs (0.5 B/FMA against 1.25 for the 8x8 register tile), which lifts both limiters ncu
+// found for the scalar version: the shared-memory -> register return path and, through the register count, the
+// number of resident warps.  The result is still IEEE FP64 multiply-add in some order, so the near-integer guard
+// makes the int16 output bit-identical exactly as before.
+//
+// 8 warps = 2 (phases) x 4 (cycles).  Per k4 step a thread loads 4 A values (G'[k0 + lane%4][m0 + 8*mi + lane/4])
+// and one 8-byte vector of 4 int16 B values (X'[k0 + lane%4][n0 + 4*(lane/4) .. +4]); n-tile `ni` of a warp owns the
+// cycles n0 + 4*col + ni, so those four samples are the thread's B operand for ni = 0..3.  Row pitches of G' (PB + 4
+// doubles) and X' (JB + 8 int16) make both loads bank-conflict-free.
+constexpr int kDmmaThreads = 256;
+constexpr int kDPB = 64, kDJB = 128;                             // CTA tile: phases x cycles
+constexpr int kGP = kDPB + 4;                                    // G' row pitch in doubles  (== 4 mod 16)
+constexpr int kXP = kDJB + 8;                                    // X' row pitch in int16    (== 4 words mod 32)
+
+template <int KC>
+constexpr size_t dmma_stage_bytes() { return (size_t)KC * (kGP * 8 + kXP * 2); }
+
+template <int KC, int MODE>
+__global__ void __launch_bounds__(kDmmaThreads, 2)
+poly_bank_dmma_kernel(PolyLaunch a, BankGeom geo)
+{
+    constexpr int PB = kDPB, JB = kDJB, NT = kDmmaThreads;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *Gs = reinterpret_cast<double *>(smem_raw + 16);               // [kStages][KC][kGP]
+    int16_t *Xs = reinterpret_cast<int16_t *>(Gs + kStages * KC * kGP);   // [kStages][KC][kXP]
+    int16_t *raw = Xs + kStages * KC * kXP + kRawSlack;
+    __shared__ int s_shift[PB];
+    __shared__ uint64_t s_full[kStages], s_empty[kStages];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;                               // warp tile: phases [32*wm, +32) x cycles [32*wn, +32)
+    const int tile_p = blockIdx.x % geo.n_phase_tiles;
+    const int tile_j = blockIdx.x / geo.n_phase_tiles;
+    const int ch = blockIdx.y;
+    const int L = a.L, M = a.M, Q = a.ctaps;
+
+    const int l0 = tile_p * PB;
+    const int pbv = min(PB, L - l0);
+    const int c_lo = (int)(((long long)l0 * M) / L);
+    const int c_hi = (int)(((long long)(l0 + pbv - 1) * M) / L);
+    const int cspan = c_hi - c_lo;
+    const int KP = Q + cspan;
+    const long long j0 = geo.jc0 + (long long)tile_j * JB;
+    const int rawn = (JB - 1) * M + cspan + Q;
+    const long long S0 = j0 * M + c_lo - (Q - 1);
+
+    const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
+    const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
+
+    // ---- stage the input span (as in poly_bank_kernel) ----
+    const long long rel = S0 - a.in0;
+    const long long rel_al = rel & ~7LL;
+    const long long end_al = (rel + rawn + 7) & ~7LL;
+    const bool inside = xc != nullptr && rel >= 0 && rel + rawn <= a.n_in;
+    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
+    int raw_off = 0;
+    if (bulk) {
+        raw_off = (int)(rel - rel_al);
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, bytes);
+            tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
+        }
+    } else if (inside) {
+        for (int e = tid; e < rawn; e += NT) raw[e] = xc[rel + e];
+    } else {
+        for (int e = tid; e < rawn; e += NT) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&s_full[i], NT);
+            mbar_init(&s_empty[i], NT);
+        }
+    }
+    for (int l = tid; l < PB; l += NT)
+        s_shift[l] = (l < pbv) ? c_hi - (int)(((long long)(l0 + l) * M) / L) : 0;
+    __syncthreads();
+    if (bulk) mbar_wait(bar, 0);
+    const int16_t *rawp = raw + raw_off;
+
+    // ---- chunk builders: thread -> one G' column (4 rows apart) and one X' column (2 rows apart) ----
+    constexpr int GR = NT / PB, GE = KC / GR;                              // 4 rows per pass
+    constexpr int XR = NT / JB, XE = KC / XR;                              // 2 rows per pass
+    static_assert(KC % GR == 0 && KC % XR == 0 && KC % 4 == 0, "chunk shape");
+    const int gl = tid % PB, gk = tid / PB;
+    const double *gsrc = a.cbankT64 + ((long long)gk - s_shift[gl]) * L + l0 + gl;
+    const int xj = tid % JB, xk = tid / JB;
+    const int16_t *xsrc = rawp + xj * M + (KP - 1) - xk;
+    double gpre[GE];
+    auto load_g = [&](int chunk) {
+        const double *src = gsrc + (long long)chunk * KC * L;
+#pragma unroll
+        for (int i = 0; i < GE; ++i) gpre[i] = src[(long long)i * GR * L];
+    };
+    auto store_g = [&](int buf) {
+        double *dst = Gs + buf * KC * kGP + gk * kGP + gl;
+#pragma unroll
+        for (int i = 0; i < GE; ++i) dst[i * GR * kGP] = gpre[i];
+    };
+    auto build_x = [&](int chunk, int buf) {
+        int16_t *dst = Xs + buf * KC * kXP + xk * kXP + xj;
+        const int16_t *src = xsrc - chunk * KC;
+#pragma unroll
+        for (int i = 0; i < XE; ++i) dst[i * XR * kXP] = src[-i * XR];
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    const int nchunks = (KP + KC - 1) / KC;
+#pragma unroll
+    for (int c0 = 0; c0 < 2; ++c0) {
+        if (c0 < nchunks) {
+            load_g(c0);
+            store_g(c0);
+            build_x(c0, c0);
+            mbar_arrive(&s_full[c0]);
+        }
+    }
+    const int a_off = (lane & 3) * kGP + wm * 32 + (lane >> 2);          // A: row k0 + lane%4, phase 32*wm + 8*mi + lane/4
+    const int b_off = (lane & 3) * kXP + wn * 32 + 4 * (lane >> 2);      // B: row k0 + lane%4, cycles 32*wn + 4*(lane/4) + ni
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c % kStages;
+        const int nxt = (c + 2) % kStages;
+        const bool produce = c + 2 < nchunks;
+        if (produce) load_g(c + 2);
+        mbar_wait(&s_full[buf], (c / kStages) & 1);
+        const double *gb = Gs + buf * KC * kGP + a_off;
+        const int16_t *xb = Xs + buf * KC * kXP + b_off;
+#pragma unroll
+        for (int k0 = 0; k0 < KC; k0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) af[mi] = gb[k0 * kGP + 8 * mi];
+            const uint2 w = *reinterpret_cast<const uint2 *>(xb + k0 * kXP);
+            bf[0] = (double)(short)(w.x & 0xffffu); bf[1] = (double)(short)(w.x >> 16);
+            bf[2] = (double)(short)(w.y & 0xffffu); bf[3] = (double)(short)(w.y >> 16);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[mi][ni][0]), "+d"(acc[mi][ni][1]) : "d"(af[mi]), "d"(bf[ni]));
+        }
+        mbar_arrive(&s_empty[buf]);
+        if (produce) {
+            if (c >= 1) mbar_wait(&s_empty[nxt], ((c - 1) / kStages) & 1);
+            store_g(nxt);
+            build_x(c + 2, nxt);
+            mbar_arrive(&s_full[nxt]);
+        }
+    }
+
+    // ---- gain / guard / saturate / truncate / store: C[row = lane/4][col = 2*(lane%4) + e] of tile (mi, ni) ----
+    const long long o_end = a.o0 + a.n_out;
+    const bool unit_gain = a.gain == 1.0;
+    int16_t *ych = a.y + (long long)ch * a.y_stride;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int l = wm * 32 + 8 * mi + (lane >> 2);                      // phase within the tile
+        const bool l_ok = l < pbv;
+        const int st = l_ok ? a.single_tap[l0 + l] : 0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = wn * 32 + 4 * (2 * (lane & 3) + e) + ni;    // cycle within the tile
+                const long long o = (j0 + j) * (long long)L + l0 + l;
+                if (!l_ok || o < a.o0 || o >= o_end) continue;
+                double v = unit_gain ? acc[mi][ni][e] : __dmul_rn(acc[mi][ni][e], a.gain);
+                if (MODE == LLZ_CUDA_ACC_F64 && st < 0 && poly_near_nonzero_integer(v, a.guard_thr)) {
+                    v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
+                    atomicAdd(a.guard_count, 1ULL);
+                }
+                ych[o - a.o0] = poly_finish(v);
+            }
+        }
+    }
+}
+
+template <int KC, int MODE>
+int launch_bank_dmma(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+{
+    BankGeom geo{};
+    geo.jc0 = a.o0 / a.L;
+    const long long jc_last = (a.o0 + a.n_out - 1) / a.L;
+    geo.n_cycle_tiles = (int)((jc_last - geo.jc0 + 1 + kDJB - 1) / kDJB);
+    geo.n_phase_tiles = (a.L + kDPB - 1) / kDPB;
+    const int cspan_max = (int)(((long long)kDPB * a.M) / a.L) + 2;
+    geo.raw_cap = (kDJB - 1) * a.M + cspan_max + a.ctaps + 16;
+    const size_t smem = 16 + kStages * dmma_stage_bytes<KC>() + ((((size_t)geo.raw_cap + kRawSlack) * 2 + 15) & ~(size_t)15);
+    if (smem > 226 * 1024) return 0;
+    auto kern = poly_bank_dmma_kernel<KC, MODE>;
+    if (smem > 48 * 1024)
+        LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
+    if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
+    kern<<<dim3((unsigned)blocks, (unsigned)n_channels), kDmmaThreads, smem, stream>>>(a, geo);
+    LLZ_CUDA_TRY(cudaGetLastError());
+    return 1;
+}
+
 template <typename TA, int TP, int TJ, int PG, int CG, int KC, bool XI16>
 size_t bank_smem(const PolyLaunch &a)
 {
@@ -337,7 +552,12 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         if (bank_smem<float, 16, 4, 4, 32, 16, false>(a) > kLimit) return 0;
         return launch_bank<float, 16, 4, 4, 32, 16, false, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
     }
-    // f64: X' as int16 (I2F.F64 in registers), 8 phases x 8 cycles per thread: 80 bytes loaded per 64 DFMA
+    // f64: FP64 tensor-core tiles (DMMA.8x8x4) unless LLZ_BANK_NO_DMMA asks for the scalar DFMA tile
+    if (!getenv("LLZ_BANK_NO_DMMA")) {
+        const int rc = launch_bank_dmma<16, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
+        if (rc != 0) return rc;
+    }
+    // scalar tile: X' as int16 (I2F.F64 in registers), 8 phases x 8 cycles per thread: 80 bytes loaded per 64 DFMA
     if (bank_smem<double, 8, 8, 8, 16, 8, true>(a) > kLimit) return 0;
     return launch_bank<double, 8, 8, 8, 16, 8, true, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
 }
