@@ -25,6 +25,8 @@
 
 #include <type_traits>
 
+#include <cuda_fp16.h>
+
 #include "llz_poly_device.cuh"
 
 namespace llz {
@@ -503,6 +505,253 @@ int launch_bank_dmma(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     return 1;
 }
 
+// ---- FP16 tensor-core variant (fast mode, ACC_F32) --------------------------------------------------------------
+//
+// The fast mode of the same 64 x 128 tile on the tensor cores (mma.sync.m16n8k16, f16 operands, f32 accumulate), used
+// because ncu shows the CUDA-core f32 version bound by the shared-memory return path and issue slots at 40 % of the
+// FFMA pipe (profiles/r01_c4_f32_ncu_full.txt), i.e. the long-tap bank is FMA-side bound, not HBM bound.
+// Operands are split so that every product is EXACT: a sample x = xh + xl with xh = x & ~255 and xl = x & 255, both
+// exactly representable in fp16; a tap g*2^e = gh + gl (two fp16 planes prepared by the host, 22 significant bits).
+// Four MMAs (xh*gh, xh*gl, xl*gh, xl*gl) accumulate into one f32 tile, so the only inexact steps are the f32
+// accumulation -- the same as the CUDA-core fast mode -- and the 2^-22 tap truncation.  Knife-edge (single-tap)
+// phases are recomputed exactly in the epilogue as in the other fast kernels.  Tolerance: |diff| <= 1 LSB.
+// B200 rate of this legacy tensor path: 558 TFLOP/s (tools/probe_pipes.cu), i.e. 139 TFLOP/s of useful FMAs after
+// the four-way split, against 72 TFLOP/s for the FFMA pipe.
+//
+// 8 warps = 2 (phases) x 4 (cycles), warp tile 32 x 32 = 2 m16 x 4 n8.  G' planes are staged [k][phase] and X' planes
+// [k][cycle] (k-major rows), both read with ldmatrix.trans; row pitches (72 / 136 halves) keep ldmatrix conflict-free.
+constexpr int kHGP = kDPB + 8;                                   // G' fp16 row pitch (144 B: 4 banks per row)
+constexpr int kHXP = kDJB + 8;                                   // X' fp16 row pitch (272 B: 4 banks per row)
+
+template <int KC>
+constexpr size_t hmma_stage_bytes() { return (size_t)KC * (2 * kHGP + 2 * kHXP) * 2; }
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void *p)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+
+__device__ __forceinline__ void hmma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kDmmaThreads, 2)
+poly_bank_hmma_kernel(PolyLaunch a, BankGeom geo)
+{
+    constexpr int PB = kDPB, JB = kDJB, NT = kDmmaThreads;
+    static_assert(KC == 16, "one m16n8k16 step per chunk row block");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint16_t *Gh = reinterpret_cast<uint16_t *>(smem_raw + 16);           // per stage: Gh[KC][kHGP], Gl, Xh[KC][kHXP], Xl
+    constexpr int kStageHalves = KC * (2 * kHGP + 2 * kHXP);
+    int16_t *raw = reinterpret_cast<int16_t *>(Gh + kStages * kStageHalves) + kRawSlack;
+    __shared__ int s_shift[PB];
+    __shared__ uint64_t s_full[kStages], s_empty[kStages];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int tile_p = blockIdx.x % geo.n_phase_tiles;
+    const int tile_j = blockIdx.x / geo.n_phase_tiles;
+    const int ch = blockIdx.y;
+    const int L = a.L, M = a.M, Q = a.ctaps;
+
+    const int l0 = tile_p * PB;
+    const int pbv = min(PB, L - l0);
+    const int c_lo = (int)(((long long)l0 * M) / L);
+    const int c_hi = (int)(((long long)(l0 + pbv - 1) * M) / L);
+    const int cspan = c_hi - c_lo;
+    const int KP = Q + cspan;
+    const long long j0 = geo.jc0 + (long long)tile_j * JB;
+    const int rawn = (JB - 1) * M + cspan + Q;
+    const long long S0 = j0 * M + c_lo - (Q - 1);
+
+    const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
+    const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
+
+    // ---- stage the input span (as in poly_bank_kernel) ----
+    const long long rel = S0 - a.in0;
+    const long long rel_al = rel & ~7LL;
+    const long long end_al = (rel + rawn + 7) & ~7LL;
+    const bool inside = xc != nullptr && rel >= 0 && rel + rawn <= a.n_in;
+    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
+    int raw_off = 0;
+    if (bulk) {
+        raw_off = (int)(rel - rel_al);
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, bytes);
+            tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
+        }
+    } else if (inside) {
+        for (int e = tid; e < rawn; e += NT) raw[e] = xc[rel + e];
+    } else {
+        for (int e = tid; e < rawn; e += NT) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&s_full[i], NT);
+            mbar_init(&s_empty[i], NT);
+        }
+    }
+    for (int l = tid; l < PB; l += NT)
+        s_shift[l] = (l < pbv) ? c_hi - (int)(((long long)(l0 + l) * M) / L) : 0;
+    __syncthreads();
+    if (bulk) mbar_wait(bar, 0);
+    const int16_t *rawp = raw + raw_off;
+
+    // ---- chunk builders ----
+    constexpr int GR = NT / PB, GE = KC / GR;                              // 4 rows per pass, 4 passes
+    constexpr int XR = NT / JB, XE = KC / XR;                              // 2 rows per pass, 8 passes
+    const int gl = tid % PB, gk = tid / PB;
+    const long long goff = ((long long)gk - s_shift[gl]) * L + l0 + gl;
+    const int xj = tid % JB, xk = tid / JB;
+    const int16_t *xsrc = rawp + xj * M + (KP - 1) - xk;
+    uint16_t gph[GE], gpl[GE];
+    auto load_g = [&](int chunk) {
+        const long long o = goff + (long long)chunk * KC * L;
+#pragma unroll
+        for (int i = 0; i < GE; ++i) {
+            gph[i] = a.cbankT16h[o + (long long)i * GR * L];
+            gpl[i] = a.cbankT16l[o + (long long)i * GR * L];
+        }
+    };
+    auto store_g = [&](int buf) {
+        uint16_t *dh = Gh + buf * kStageHalves + gk * kHGP + gl;
+        uint16_t *dl = dh + KC * kHGP;
+#pragma unroll
+        for (int i = 0; i < GE; ++i) {
+            dh[i * GR * kHGP] = gph[i];
+            dl[i * GR * kHGP] = gpl[i];
+        }
+    };
+    auto build_x = [&](int chunk, int buf) {
+        __half *dh = reinterpret_cast<__half *>(Gh + buf * kStageHalves + 2 * KC * kHGP) + xk * kHXP + xj;
+        __half *dl = dh + KC * kHXP;
+        const int16_t *src = xsrc - chunk * KC;
+#pragma unroll
+        for (int i = 0; i < XE; ++i) {
+            const int x = src[-i * XR];
+            dh[i * XR * kHXP] = __short2half_rn((short)(x & ~255));       // multiple of 256, |.| <= 32768: exact in fp16
+            dl[i * XR * kHXP] = __ushort2half_rn((unsigned short)(x & 255));
+        }
+    };
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+
+    const int nchunks = (KP + KC - 1) / KC;
+#pragma unroll
+    for (int c0 = 0; c0 < 2; ++c0) {
+        if (c0 < nchunks) {
+            load_g(c0);
+            store_g(c0);
+            build_x(c0, c0);
+            mbar_arrive(&s_full[c0]);
+        }
+    }
+    // ldmatrix row addresses.  A (m16 x k16, from [k][phase]): matrix id = lane/8 -> (m block = id&1, k block = id>>1).
+    const int a_row = ((lane >> 4) << 3) + (lane & 7), a_col = wm * 32 + (((lane >> 3) & 1) << 3);
+    // B (k16 x n8 pairs, from [k][cycle]): one x4 covers two n-tiles: id -> (k block = id&1, n tile = id>>1)
+    const int b_row = (((lane >> 3) & 1) << 3) + (lane & 7), b_col = wn * 32 + ((lane >> 4) << 3);
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c % kStages;
+        const int nxt = (c + 2) % kStages;
+        const bool produce = c + 2 < nchunks;
+        if (produce) load_g(c + 2);
+        mbar_wait(&s_full[buf], (c / kStages) & 1);
+        const uint16_t *sGh = Gh + buf * kStageHalves, *sGl = sGh + KC * kHGP;
+        const uint16_t *sXh = sGl + KC * kHGP, *sXl = sXh + KC * kHXP;
+        uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            ldsm_x4_trans(ah[mi], sGh + a_row * kHGP + a_col + 16 * mi);
+            ldsm_x4_trans(al[mi], sGl + a_row * kHGP + a_col + 16 * mi);
+        }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {                                   // n-tile pair (2*np, 2*np+1)
+            ldsm_x4_trans(bh[np], sXh + b_row * kHXP + b_col + 16 * np);
+            ldsm_x4_trans(bl[np], sXl + b_row * kHXP + b_col + 16 * np);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int np = ni >> 1, q = (ni & 1) * 2;
+                hmma_16816(acc[mi][ni], al[mi], bl[np][q], bl[np][q + 1]);   // smallest products first
+                hmma_16816(acc[mi][ni], al[mi], bh[np][q], bh[np][q + 1]);
+                hmma_16816(acc[mi][ni], ah[mi], bl[np][q], bl[np][q + 1]);
+                hmma_16816(acc[mi][ni], ah[mi], bh[np][q], bh[np][q + 1]);
+            }
+        mbar_arrive(&s_empty[buf]);
+        if (produce) {
+            if (c >= 1) mbar_wait(&s_empty[nxt], ((c - 1) / kStages) & 1);
+            store_g(nxt);
+            build_x(c + 2, nxt);
+            mbar_arrive(&s_full[nxt]);
+        }
+    }
+
+    // ---- epilogue: C[row = lane/4 (+8)][col = 2*(lane%4) + {0,1}] of tile (mi, ni) ----
+    const long long o_end = a.o0 + a.n_out;
+    const double unscale = ldexp(a.gain, -a.bank16_exp);
+    int16_t *ych = a.y + (long long)ch * a.y_stride;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = wm * 32 + 16 * mi + 8 * h + (lane >> 2);
+            const bool l_ok = l < pbv;
+            const int st = l_ok ? a.single_tap[l0 + l] : -1;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = wn * 32 + 8 * ni + 2 * (lane & 3) + e;
+                    const long long o = (j0 + j) * (long long)L + l0 + l;
+                    if (!l_ok || o < a.o0 || o >= o_end) continue;
+                    double v = (double)acc[mi][ni][2 * h + e] * unscale;
+                    if (st >= 0) {                                         // knife-edge phase: one exact FP64 product
+                        const long long base = (o * M) / L;
+                        v = __dmul_rn(__dmul_rn((double)poly_sample(a, xc, hc, base - st), a.cbank[(long long)(l0 + l) * Q + st]), a.gain);
+                    }
+                    ych[o - a.o0] = poly_finish(v);
+                }
+        }
+}
+
+template <int KC>
+int launch_bank_hmma(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+{
+    BankGeom geo{};
+    geo.jc0 = a.o0 / a.L;
+    const long long jc_last = (a.o0 + a.n_out - 1) / a.L;
+    geo.n_cycle_tiles = (int)((jc_last - geo.jc0 + 1 + kDJB - 1) / kDJB);
+    geo.n_phase_tiles = (a.L + kDPB - 1) / kDPB;
+    const int cspan_max = (int)(((long long)kDPB * a.M) / a.L) + 2;
+    geo.raw_cap = (kDJB - 1) * a.M + cspan_max + a.ctaps + 16;
+    const size_t smem = 16 + kStages * hmma_stage_bytes<KC>() + ((((size_t)geo.raw_cap + kRawSlack) * 2 + 15) & ~(size_t)15);
+    if (smem > 226 * 1024) return 0;
+    auto kern = poly_bank_hmma_kernel<KC>;
+    if (smem > 48 * 1024)
+        LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
+    if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
+    kern<<<dim3((unsigned)blocks, (unsigned)n_channels), kDmmaThreads, smem, stream>>>(a, geo);
+    LLZ_CUDA_TRY(cudaGetLastError());
+    return 1;
+}
+
 template <typename TA, int TP, int TJ, int PG, int CG, int KC, bool XI16>
 size_t bank_smem(const PolyLaunch &a)
 {
@@ -548,6 +797,11 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if ((a.ctaps + cspan) / a.ctaps > 2.5) return 0;
     constexpr size_t kLimit = 226 * 1024;
     if (a.acc == LLZ_CUDA_ACC_F32) {
+        // fast mode: exact-product fp16 split on the tensor cores unless LLZ_BANK_NO_HMMA asks for the FFMA tile
+        if (a.cbankT16h && a.cbankT16l && !getenv("LLZ_BANK_NO_HMMA")) {
+            const int rc = launch_bank_hmma<16>(a, n_channels, stream);
+            if (rc != 0) return rc;
+        }
         // f32: X' as float (the conversion unit cannot feed 8 I2F per 64 FFMA), 16 phases x 4 cycles per thread
         if (bank_smem<float, 16, 4, 4, 32, 16, false>(a) > kLimit) return 0;
         return launch_bank<float, 16, 4, 4, 32, 16, false, LLZ_CUDA_ACC_F32>(a, n_channels, stream);

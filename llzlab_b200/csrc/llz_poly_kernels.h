@@ -33,7 +33,12 @@ struct PolyLaunch {
     const double *cbank;       // [L][ctaps] row-major
     const double *cbankT64;    // [ctaps][L]
     const float *cbankT32;     // [ctaps][L]
-    int bank_pad;              // zero rows before row 0 and after row ctaps-1 of cbankT64 / cbankT32
+    int bank_pad;              // zero rows before row 0 and after row ctaps-1 of cbankT64 / cbankT32 / cbankT16*
+    // the bank as two fp16 planes for the tensor-core fast mode: g * 2^bank16_exp = hi + lo (22 significant bits),
+    // same [ctaps][L] layout and padding; nullptr when the bank was not split
+    const uint16_t *cbankT16h;
+    const uint16_t *cbankT16l;
+    int bank16_exp;
     const int *order;          // reference accumulation order, order_len canonical tap indices
     int order_len;
     const int *single_tap;     // [L]

@@ -17,6 +17,8 @@
 #include <new>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "llz_cuda_common.cuh"
 #include "llz_fir_kernels.h"
 #include "llz_poly_kernels.h"
@@ -305,6 +307,8 @@ struct PolyBank {
     // device copies of the plan
     double *d_cbank = nullptr, *d_cbankT64 = nullptr, *d_cbankT64_base = nullptr, *d_slide64 = nullptr;
     float *d_cbankT32 = nullptr, *d_cbankT32_base = nullptr, *d_slide32 = nullptr;
+    uint16_t *d_cbankT16h = nullptr, *d_cbankT16l = nullptr, *d_cbankT16h_base = nullptr, *d_cbankT16l_base = nullptr;
+    int bank16_exp = 0;
     int bank_pad = 0;
     int *d_order = nullptr, *d_single = nullptr;
     int slide_ntp64 = 0, slide_ntp32 = 0;
@@ -337,6 +341,7 @@ void poly_destroy(PolyBank *b)
     b->pipe.destroy();
     cudaFree(b->d_cbank); cudaFree(b->d_cbankT64_base); cudaFree(b->d_slide64);
     cudaFree(b->d_cbankT32_base); cudaFree(b->d_slide32);
+    cudaFree(b->d_cbankT16h_base); cudaFree(b->d_cbankT16l_base);
     cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     if (b->pinned_in) cudaFreeHost(b->pinned_in);
@@ -374,6 +379,27 @@ int poly_upload_plan(PolyBank *b)
     if (upload(&b->d_cbank, cb) || upload(&b->d_cbankT64_base, t64) || upload(&b->d_cbankT32_base, t32)) return -1;
     b->d_cbankT64 = b->d_cbankT64_base + pad * L;
     b->d_cbankT32 = b->d_cbankT32_base + pad * L;
+    if (b->acc == LLZ_CUDA_ACC_F32 && p.L >= 16) {
+        // fp16 hi/lo planes for the tensor-core fast mode (llz_cuda_polybank.cu): scale so the largest tap sits in
+        // [2^14, 2^15), then g*2^e = hi + lo with hi = fp16(g*2^e), lo = fp16(g*2^e - hi): 22 significant bits
+        double gmax = 0.0;
+        for (double v : cb) gmax = fmax(gmax, fabs(v));
+        int e2 = 0;
+        if (gmax > 0.0) { frexp(gmax, &e2); e2 = 15 - e2; }
+        b->bank16_exp = e2;
+        std::vector<uint16_t> th(L * (Q + 2 * pad), 0), tl(L * (Q + 2 * pad), 0);
+        for (size_t r = 0; r < L; ++r)
+            for (size_t k = 0; k < Q; ++k) {
+                const double g = ldexp(cb[r * Q + k], e2);
+                const __half hi = __double2half(g);
+                const __half lo = __double2half(g - (double)__half2float(hi));
+                th[(k + pad) * L + r] = __half_as_ushort(hi);
+                tl[(k + pad) * L + r] = __half_as_ushort(lo);
+            }
+        if (upload(&b->d_cbankT16h_base, th) || upload(&b->d_cbankT16l_base, tl)) return -1;
+        b->d_cbankT16h = b->d_cbankT16h_base + pad * L;
+        b->d_cbankT16l = b->d_cbankT16l_base + pad * L;
+    }
     std::vector<int> order(p.order, p.order + Q), single(p.single_tap, p.single_tap + L);
     if (upload(&b->d_order, order) || upload(&b->d_single, single)) return -1;
 
@@ -481,6 +507,9 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.cbankT64 = b->d_cbankT64;
     a.cbankT32 = b->d_cbankT32;
     a.bank_pad = b->bank_pad;
+    a.cbankT16h = b->d_cbankT16h;
+    a.cbankT16l = b->d_cbankT16l;
+    a.bank16_exp = b->bank16_exp;
     a.order = b->d_order;
     a.order_len = p.ctaps;
     a.single_tap = b->d_single;

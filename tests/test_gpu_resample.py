@@ -89,7 +89,7 @@ def test_bank_exact_modes(zlib, port, cuda, L, M, win, k):
     bank.close(); strict.close()
 
 
-@pytest.mark.parametrize("L,M,win,k", CASES)
+@pytest.mark.parametrize("L,M,win,k", CASES + [(320, 147, 1, 128), (441, 320, 1, 0)])
 def test_bank_f32_within_one_lsb(zlib, port, cuda, L, M, win, k):
     torch = cuda
     C_ = 2
@@ -104,7 +104,8 @@ def test_bank_f32_within_one_lsb(zlib, port, cuda, L, M, win, k):
     torch.cuda.synchronize()
     diff = np.abs(dy.cpu().numpy().astype(np.int32) - want)
     assert diff.max() <= 1
-    assert (diff != 0).mean() <= 0.02
+    assert (diff != 0).mean() <= 0.02, (diff != 0).mean()
+    print(f"f32 mismatch rate L={L} M={M} Q={bank.info.taps_per_phase}: {(diff != 0).mean():.5f}")
     if L > 1 and L >= M:                               # knife-edge phase stays exact in the fast mode
         assert not diff[:, ::L].any()
     bank.close()
