@@ -284,7 +284,7 @@ def run_cuda(args):
         dtype_name = "s16 io / f32 acc" if args.dtype == "f32" else "s16 io / f64 acc"
         fma_peak_nominal = FP32_NOMINAL_TFLOPS if args.dtype == "f32" else FP64_NOMINAL_TFLOPS
         fma_dtype = z.F32 if args.dtype == "f32" else z.F64
-        kernel = "poly_slide_kernel" if wl["L"] == 1 else "poly_bank_kernel"
+        kernel = "poly_slide_kernel" if wl["L"] == 1 else ("poly_bank_hmma_kernel" if args.dtype == "f32" else "poly_bank_dmma_kernel")
 
         def step():
             if halo:
