@@ -17,13 +17,15 @@
 //   ACC_F64_STRICT  every output in the reference's order (verification mode).
 //   ACC_F32         FP32 FMA; single-tap rows are evaluated in FP64 so the knife-edge phase stays exact.
 //
-// Kernels
-//   poly_general_kernel  any L, M: one output per thread iteration, input span staged in shared
-//                        memory already converted to the accumulator type, bank read transposed
-//                        ([tap][phase]) so a warp's loads are contiguous.
+// Kernels (poly_launch picks one)
 //   poly_slide_kernel    L == 1 (decimation): taps split by residue k mod M into M sliding FIRs over
-//                        the M de-interleaved input streams; register-blocked SlidingMac core shared
-//                        with the FIR kernel (R outputs per thread, 2 LDS.128 per R*U FMAs).
+//                        the M de-interleaved input streams, which stay int16 in shared memory;
+//                        register-blocked SlidingMac core shared with the FIR kernel.
+//   poly_bank_*_kernel   L >= 16 rational banks: llz_cuda_polybank.cu (register-tiled / DMMA / HMMA).
+//   poly_general_kernel  everything else (interp, strict mode, few phases) and the correctness
+//                        baseline: one output per thread iteration, input span staged in shared
+//                        memory already converted, bank read transposed ([tap][phase]) so a warp's
+//                        coefficient loads are contiguous.
 #include <limits.h>
 #include <stdlib.h>
 
