@@ -110,9 +110,20 @@ pcm_transpose_kernel(unsigned char *frames, TP *planar, long long planar_stride,
             const bool vec = (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
             const int nv = vec ? nf / VP : 0;
             const int key = (c >> 3) & 7;
-            for (int v = lane; v < nv; v += 32) {
-                if (TO_PLANAR) reinterpret_cast<uint4 *>(row)[v] = reinterpret_cast<const uint4 *>(trow)[v ^ key];
-                else reinterpret_cast<uint4 *>(trow)[v ^ key] = reinterpret_cast<const uint4 *>(row)[v];
+            if (TO_PLANAR) {
+                for (int v = lane; v < nv; v += 32)
+                    reinterpret_cast<uint4 *>(row)[v] = reinterpret_cast<const uint4 *>(trow)[v ^ key];
+            } else {
+                // global -> shared: four independent 16-byte loads in flight per lane before the first store
+                int v = lane;
+                for (; v + 96 < nv; v += 128) {
+                    uint4 w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) w[u] = reinterpret_cast<const uint4 *>(row)[v + 32 * u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) reinterpret_cast<uint4 *>(trow)[(v + 32 * u) ^ key] = w[u];
+                }
+                for (; v < nv; v += 32) reinterpret_cast<uint4 *>(trow)[v ^ key] = reinterpret_cast<const uint4 *>(row)[v];
             }
             for (int f = nv * VP + lane; f < nf; f += 32) {
                 if (TO_PLANAR) row[f] = trow[col(c, f)];
