@@ -25,6 +25,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 HAMMING, BLACKMAN, KAISER = 0, 1, 2
 LPF, HPF, BPF, BSF = 0, 1, 2, 3
 F64, F64_STRICT, F32 = 0, 1, 2
+FIR_AUTO, FIR_DIRECT, FIR_FFT = 0, 1, 2
 ACC_F64, ACC_F64_STRICT, ACC_F32 = 0, 1, 2
 KIND_DECIMATE, KIND_INTERP, KIND_RESAMPLE = 0, 1, 2
 PCM_S16, PCM_S24, PCM_F32 = 0, 1, 2
@@ -105,6 +106,8 @@ _SIGNATURES = [
     ("llz_cuda_fir_bank_init_taps", _ul, [_dp, C.c_int, C.c_int, C.c_int]),
     ("llz_cuda_fir_bank_uninit", None, [_ul]),
     ("llz_cuda_fir_bank_flt_len", C.c_int, [_ul]),
+    ("llz_cuda_fir_bank_set_algo", C.c_int, [_ul, C.c_int]),
+    ("llz_cuda_fir_bank_get_algo", C.c_int, [_ul]),
     ("llz_cuda_fir_bank_copy_taps", C.c_int, [_ul, _dp]),
     ("llz_cuda_fir_bank_reset", C.c_int, [_ul, _vp]),
     ("llz_cuda_fir_bank_set_history", C.c_int, [_ul, _vp, _ll, _vp]),
@@ -349,7 +352,8 @@ def bank_info(handle: int) -> ResampleInfo:
 # ---- banks (device pointers; torch tensors or raw addresses) ----------------------------------------------
 class FirBank:
     def __init__(self, n_channels: int, dtype: int = F64, *, kind: int = LPF, flt_len: int = 0,
-                 fc1: float = 0.0, fc2: float = 0.0, win: int = HAMMING, taps: np.ndarray | None = None):
+                 fc1: float = 0.0, fc2: float = 0.0, win: int = HAMMING, taps: np.ndarray | None = None,
+                 algo: int = FIR_AUTO):
         L = lib()
         if taps is not None:
             taps = np.ascontiguousarray(taps, dtype=np.float64)
@@ -360,6 +364,16 @@ class FirBank:
         self.n_channels = n_channels
         self.dtype = dtype
         self.flt_len = L.llz_cuda_fir_bank_flt_len(self.handle)
+        if algo != FIR_AUTO:
+            self.set_algo(algo)
+
+    def set_algo(self, algo: int):
+        _check(lib().llz_cuda_fir_bank_set_algo(self.handle, algo), "llz_cuda_fir_bank_set_algo")
+
+    @property
+    def algo(self) -> int:
+        """kernel family the next run uses: FIR_DIRECT or FIR_FFT"""
+        return _check(lib().llz_cuda_fir_bank_get_algo(self.handle), "llz_cuda_fir_bank_get_algo")
 
     def taps(self) -> np.ndarray:
         h = np.empty(self.flt_len, dtype=np.float64)

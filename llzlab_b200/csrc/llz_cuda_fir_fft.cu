@@ -1,0 +1,211 @@
+// llz_cuda_fir_fft.cu -- overlap-save FIR banks for sm_100a: the tolerance-mode arithmetic of
+// llz_fir_filter / llz_conv (libllzfilter/llz_fir.c:411-426, 547-584) when the direct form is
+// bound by the FMA pipe rather than by HBM.
+//
+//   y[c][t] = sum_{i<N} h[i] * x[c][t-i]
+//
+// A 127-tap filter in direct form is 254 flop per output against 16 bytes (f64): 15.9 flop/B, three
+// times the FP64 ridge of a B200, so the direct kernel (llz_cuda_fir.cu) tops out at 36 % of HBM no
+// matter how well it feeds the pipe.  Overlap-save with a 1024-point transform does the same
+// convolution in ~35 FMA-pipe instructions per output instead of 127:
+//
+//   * one WARP owns one work item = two consecutive blocks of B = 1024 - (N-1) outputs of one
+//     channel, packed as one complex signal  z[n] = xA[n] + i*xB[n]  (h is real, so the real and
+//     imaginary parts of  ifft(fft(z) * H)  are the two filtered blocks: no real-FFT split pass);
+//   * the 1024-point transform is 32 x 32 (llz_fft32.cuh): each lane holds 32 complex points in
+//     registers; lane t loads  x[s + t + 32 j]  straight from global memory (256 contiguous bytes per
+//     warp instruction) -- DFT-32 over j -- twiddle -- transpose through shared memory -- DFT-32
+//     over t -- multiply by H -- inverse DFT-32 -- conjugate twiddle -- transpose -- inverse DFT-32,
+//     which leaves lane t holding outputs  t + 32 j  again: coalesced streaming stores;
+//   * only two transposes per item go through shared memory; the spectrum H (1/1024 folded in) is
+//     read through L1, the 32 x 32 inter-pass twiddles sit in shared memory once per CTA;
+//   * no CTA-wide barrier after the table load: warps are independent and loop over items
+//     (persistent grid of one CTA per SM), so one warp's loads hide behind the others' butterflies.
+//
+// Arithmetic stays in the bank's own type (FP64 for double banks): this is a cheaper algorithm, not a
+// lower precision; the error against the reference's direct sum is ~1e-15 of full scale (f64) and
+// the result is NOT bit-identical -- LLZ_CUDA_F64_STRICT and the drop-in llz_fir_filter keep the
+// direct kernel.
+//
+// Algorithmic cost per item (2B outputs), per lane: 4 x 388 (DFT-32) + 2 x 124 (twiddles) + 128 (H)
+// = 1928 FMA-pipe instructions; shared memory: 2 x (32 + 32) x 2 accesses of sizeof(T).
+#include "llz_fft32.cuh"
+#include "llz_fir_kernels.h"
+
+namespace llz {
+
+template <typename T> struct Cplx;
+template <> struct Cplx<float>  { using type = float2; };
+template <> struct Cplx<double> { using type = double2; };
+
+// row pitch of the per-warp transpose buffer: 33 elements keeps both the row-wise stores (lane = row)
+// and the column-wise loads (lane = column) bank-conflict-free for 4- and 8-byte elements
+constexpr int kFftPitch = kFftR + 1;
+
+template <typename T>
+__device__ __forceinline__ void warp_transpose(T (&v)[32], T *buf, int lane)
+{
+#pragma unroll
+    for (int k = 0; k < 32; ++k) buf[lane * kFftPitch + k] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = buf[k * kFftPitch + lane];
+    __syncwarp();
+}
+
+template <typename T>
+__device__ __forceinline__ T fir_fft_sample(const FirFftLaunch<T> &a, const T *xc, const T *hc, long long g)
+{
+    if (g >= 0) return (g < a.n && xc) ? __ldg(xc + g) : T(0);
+    if (hc && g >= -(long long)(a.ntaps - 1)) return __ldg(hc + (a.ntaps - 1) + g);
+    return T(0);
+}
+
+// EDGE = false: every item is interior (its 1024 + B input samples and 2B outputs lie inside this call's
+// buffers): unguarded loads and stores.  EDGE = true: the first / last items of a channel (history splice,
+// zero fill past the end, flush).  Two instantiations rather than one branch: the compiler would otherwise
+// clone the whole forward half of the transform behind each load path.
+template <typename T, int WARPS, bool EDGE>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+fir_fft_kernel(FirFftLaunch<T> a)
+{
+    using C = typename Cplx<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *tw_s = reinterpret_cast<C *>(smem_raw);                        // [32][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *buf = reinterpret_cast<T *>(tw_s + kFftR * kFftR) + warp * (kFftR * kFftPitch);
+
+    for (int i = threadIdx.x; i < kFftR * kFftR; i += WARPS * 32) tw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
+    __syncthreads();
+
+    const C *Hc = reinterpret_cast<const C *>(a.H);
+    const int hl = a.ntaps - 1;
+    const int B = a.B;
+    const long long total = a.items_per_channel * a.n_channels;
+
+    for (long long item = (long long)blockIdx.x * WARPS + warp; item < total; item += (long long)gridDim.x * WARPS) {
+        const int ch = (int)(item / a.items_per_channel);
+        long long pair = a.first_pair + (item - (long long)ch * a.items_per_channel);
+        if (pair >= a.gap_start) pair += a.gap_len;
+        const long long o = pair * (2LL * B);          // first output of block A
+        const long long s = o - hl;                    // first input of block A
+        const T *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
+        T *yc = a.y + (long long)ch * a.y_stride;
+
+        T re[32], im[32];
+        // ---- gather: lane t holds z[t + 32 j] ------------------------------------------------------
+        if constexpr (!EDGE) {
+            const T *p = xc + s + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { re[j] = __ldg(p + 32 * j); im[j] = __ldg(p + B + 32 * j); }
+        } else {
+            const T *hc = a.hist ? a.hist + (long long)ch * hl : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const long long g = s + lane + 32 * j;
+                re[j] = fir_fft_sample(a, xc, hc, g);
+                im[j] = fir_fft_sample(a, xc, hc, g + B);
+            }
+        }
+
+        // ---- forward pass 1: DFT over j, twiddle W_1024^(t*k2) -----------------------------------------
+        dft32<T, false>(re, im);
+#pragma unroll
+        for (int k = 1; k < 32; ++k) {
+            const C w = tw_s[k * kFftR + lane];
+            cmul_inplace<T, false>(re[k], im[k], w.x, w.y);
+        }
+        warp_transpose(re, buf, lane);
+        warp_transpose(im, buf, lane);
+
+        // ---- lane k2: DFT over t -> Z[k2 + 32 k1]; times H; inverse DFT over k1; conj twiddle ------------
+        dft32<T, false>(re, im);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const C h = __ldg(Hc + k * kFftR + lane);
+            cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
+        }
+        dft32<T, true>(re, im);
+#pragma unroll
+        for (int k = 1; k < 32; ++k) {
+            const C w = tw_s[k * kFftR + lane];
+            cmul_inplace<T, true>(re[k], im[k], w.x, w.y);
+        }
+        warp_transpose(re, buf, lane);
+        warp_transpose(im, buf, lane);
+
+        // ---- lane t: inverse DFT over k2 -> y[t + 32 j] ------------------------------------------------
+        dft32<T, true>(re, im);
+
+        // ---- scatter: circular positions m >= N-1 are the valid outputs -----------------------------------
+        T *q = yc + o - hl + lane;
+        if constexpr (!EDGE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int m = lane + 32 * j;
+                if (m >= hl) { __stcs(q + 32 * j, re[j]); __stcs(q + B + 32 * j, im[j]); }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int m = lane + 32 * j;
+                const long long tA = o - hl + m;
+                if (m >= hl) {
+                    if (tA < a.n) __stcs(q + 32 * j, re[j]);
+                    if (tA + B < a.n) __stcs(q + B + 32 * j, im[j]);
+                }
+            }
+        }
+    }
+}
+
+template <typename T> struct FftCfg;
+template <> struct FftCfg<double> { static constexpr int WARPS = 8; };
+template <> struct FftCfg<float>  { static constexpr int WARPS = 16; };
+
+template <typename T>
+int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
+{
+    if (a.n <= 0 || n_channels <= 0) return 0;
+    if (a.ntaps < 1 || a.ntaps > kFirFftMaxTaps) {
+        llz_set_error("overlap-save FIR kernel takes 1..%d taps, got %d", kFirFftMaxTaps, a.ntaps);
+        return -1;
+    }
+    constexpr int WARPS = FftCfg<T>::WARPS;
+    a.B = kFftN - (a.ntaps - 1);
+    a.n_channels = n_channels;
+    const long long two_b = 2LL * a.B;
+    const long long ppc = (a.n + two_b - 1) / two_b;
+    // interior pairs p: p*2B - (N-1) >= 0 and (p+1)*2B <= n, and there is an input buffer at all
+    long long p_lo = (a.ntaps - 1 + two_b - 1) / two_b, p_hi = a.n / two_b;
+    if (!a.x || p_hi < p_lo) { p_lo = 0; p_hi = 0; }
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0, sms = 0;
+        LLZ_CUDA_TRY(cudaGetDevice(&dev));
+        LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        sm_count = sms;
+    }
+    const size_t smem = (size_t)kFftR * kFftR * 2 * sizeof(T) + (size_t)WARPS * kFftR * kFftPitch * sizeof(T);
+    auto run = [&](auto kern, long long first, long long count, long long gap_start, long long gap_len) -> int {
+        if (count <= 0) return 0;
+        FirFftLaunch<T> b = a;
+        b.first_pair = first;
+        b.items_per_channel = count;
+        b.gap_start = gap_start;
+        b.gap_len = gap_len;
+        LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long ctas_needed = (count * n_channels + WARPS - 1) / WARPS;
+        const unsigned grid = (unsigned)(ctas_needed < sm_count ? ctas_needed : sm_count);
+        kern<<<grid, WARPS * 32, smem, stream>>>(b);
+        LLZ_CUDA_TRY(cudaGetLastError());
+        return 0;
+    };
+    if (run(fir_fft_kernel<T, WARPS, false>, p_lo, p_hi - p_lo, ppc, 0) != 0) return -1;
+    return run(fir_fft_kernel<T, WARPS, true>, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo);
+}
+
+template int fir_fft_launch<float>(FirFftLaunch<float>, int, cudaStream_t);
+template int fir_fft_launch<double>(FirFftLaunch<double>, int, cudaStream_t);
+
+}  // namespace llz

@@ -31,4 +31,28 @@ template <typename T>
 int fir_update_history(const T *x, long long x_stride, long long n, const T *hist_old, T *hist_new,
                        int hlen, int n_channels, cudaStream_t stream);
 
+// ---- overlap-save (1024-point FFT) FIR, llz_cuda_fir_fft.cu -----------------------------------------
+constexpr int kFirFftMinTapsAuto = 48;   // below this the direct kernel is at least as fast
+constexpr int kFirFftMaxTaps = 897;      // leaves B = 1024 - (N-1) >= 128 valid outputs per block
+
+template <typename T>
+struct FirFftLaunch {
+    const T *x;            // device, planar; nullptr = all-zero input (flush)
+    long long x_stride;
+    T *y;
+    long long y_stride;
+    long long n;
+    const T *hist;         // device [channels][ntaps-1] or nullptr
+    int ntaps;
+    const T *H;            // device [32][32] complex: spectrum of the taps / 1024, H[k1][k2] = bin k2 + 32*k1
+    const T *tw;           // device [32][32] complex: exp(-2*pi*i*k*t/1024)
+    // filled in by fir_fft_launch: item i of a channel is pair first_pair + i, skipping [gap_start, gap_start + gap_len)
+    int B;
+    int n_channels;
+    long long first_pair, items_per_channel, gap_start, gap_len;
+};
+
+template <typename T>
+int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
+
 }  // namespace llz

@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 
 #include "llz_cuda_common.cuh"
+#include "llz_fft32.cuh"
 #include "llz_fir_kernels.h"
 #include "llz_poly_kernels.h"
 
@@ -158,6 +159,9 @@ struct FirBank {
     void *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     bool hist_zero = true;       // no launch needed to read zeros
+    // overlap-save kernel (llz_cuda_fir_fft.cu): spectrum of the taps and inter-pass twiddles, bank's type
+    int algo = LLZ_CUDA_FIR_ALGO_AUTO;
+    void *d_fft_H = nullptr, *d_fft_tw = nullptr;
     Pipeline pipe;
     // drop-in (mono, host buffers)
     int frame_len = 0;
@@ -180,6 +184,8 @@ void fir_destroy(FirBank *b)
     DeviceGuard g(b->device);
     b->pipe.destroy();
     if (b->d_taps) cudaFree(b->d_taps);
+    if (b->d_fft_H) cudaFree(b->d_fft_H);
+    if (b->d_fft_tw) cudaFree(b->d_fft_tw);
     if (b->d_hist[0]) cudaFree(b->d_hist[0]);
     if (b->d_hist[1]) cudaFree(b->d_hist[1]);
     if (b->pinned) cudaFreeHost(b->pinned);
@@ -260,6 +266,63 @@ unsigned long fir_bank_create(double *h, int flt_len, int n_channels, int dtype)
     return reinterpret_cast<unsigned long>(b);
 }
 
+// which kernel family the next run uses: LLZ_CUDA_FIR_ALGO_DIRECT or _FFT (-1: the forced choice is impossible).
+// AUTO: overlap-save when the arithmetic is tolerance-mode and the tap count is where it wins (llz_cuda_fir_fft.cu);
+// the environment variable LLZ_FIR_ALGO=direct|fft overrides AUTO (tuning / A-B measurements).
+int fir_effective_algo(const FirBank *b)
+{
+    int algo = b->algo;
+    if (algo == LLZ_CUDA_FIR_ALGO_AUTO) {
+        const char *env = getenv("LLZ_FIR_ALGO");
+        if (env && strcmp(env, "direct") == 0) algo = LLZ_CUDA_FIR_ALGO_DIRECT;
+        else if (env && strcmp(env, "fft") == 0 && b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len <= kFirFftMaxTaps)
+            algo = LLZ_CUDA_FIR_ALGO_FFT;
+    }
+    if (algo == LLZ_CUDA_FIR_ALGO_AUTO)
+        algo = (b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len >= kFirFftMinTapsAuto && b->flt_len <= kFirFftMaxTaps)
+                   ? LLZ_CUDA_FIR_ALGO_FFT : LLZ_CUDA_FIR_ALGO_DIRECT;
+    if (algo == LLZ_CUDA_FIR_ALGO_FFT && (b->dtype == LLZ_CUDA_F64_STRICT || b->flt_len > kFirFftMaxTaps)) {
+        llz_set_error("the overlap-save FIR kernel is not available for this bank (strict arithmetic or > %d taps)",
+                      kFirFftMaxTaps);
+        return -1;
+    }
+    return algo;
+}
+
+// lazily build and upload the spectrum of the taps (1/1024 folded in) and the 32 x 32 twiddles
+int fir_fft_tables(FirBank *b)
+{
+    if (b->d_fft_H) return 0;
+    std::vector<double> H(2 * kFftN), tw(2 * kFftR * kFftR);
+    fft1024_make_spectrum(b->h_host, b->flt_len, H.data());
+    fft1024_make_twiddles(tw.data());
+    const size_t es = fir_elem_size(b->dtype);
+    void *dH = nullptr, *dT = nullptr;
+    LLZ_CUDA_TRY(cudaMalloc(&dH, H.size() * es));
+    if (cudaMalloc(&dT, tw.size() * es) != cudaSuccess) {
+        cudaFree(dH);
+        llz_set_error("cudaMalloc(FFT twiddles) failed");
+        return -1;
+    }
+    cudaError_t e1, e2;
+    if (b->dtype == LLZ_CUDA_F32) {
+        std::vector<float> Hf(H.begin(), H.end()), tf(tw.begin(), tw.end());
+        e1 = cudaMemcpy(dH, Hf.data(), Hf.size() * es, cudaMemcpyHostToDevice);
+        e2 = cudaMemcpy(dT, tf.data(), tf.size() * es, cudaMemcpyHostToDevice);
+    } else {
+        e1 = cudaMemcpy(dH, H.data(), H.size() * es, cudaMemcpyHostToDevice);
+        e2 = cudaMemcpy(dT, tw.data(), tw.size() * es, cudaMemcpyHostToDevice);
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaFree(dH); cudaFree(dT);
+        llz_set_error("upload of the FFT tables failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        return -1;
+    }
+    b->d_fft_H = dH;
+    b->d_fft_tw = dT;
+    return 0;
+}
+
 template <typename T>
 int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride,
                   long long n, cudaStream_t st)
@@ -275,7 +338,19 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
     a.ntaps = b->flt_len;
     a.vec_ok = (d_in == nullptr || aligned16(d_in)) && aligned16(d_out) &&
                (b->n_channels == 1 || ((in_stride * sizeof(T)) % 16 == 0 && (out_stride * sizeof(T)) % 16 == 0));
-    if (fir_launch<T>(a, b->n_channels, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) return -1;
+    const int algo = fir_effective_algo(b);
+    if (algo < 0) return -1;
+    if (algo == LLZ_CUDA_FIR_ALGO_FFT) {
+        if (fir_fft_tables(b) != 0) return -1;
+        FirFftLaunch<T> f{};
+        f.x = a.x; f.x_stride = in_stride; f.y = a.y; f.y_stride = out_stride; f.n = n;
+        f.hist = a.hist; f.ntaps = b->flt_len;
+        f.H = static_cast<const T *>(b->d_fft_H);
+        f.tw = static_cast<const T *>(b->d_fft_tw);
+        if (fir_fft_launch<T>(f, b->n_channels, st) != 0) return -1;
+    } else if (fir_launch<T>(a, b->n_channels, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) {
+        return -1;
+    }
     if (b->hist_len > 0) {
         const T *old = b->hist_zero ? nullptr : static_cast<const T *>(b->d_hist[b->cur]);
         T *next = static_cast<T *>(b->d_hist[b->cur ^ 1]);
@@ -604,6 +679,27 @@ extern "C" int llz_cuda_fir_bank_flt_len(unsigned long handle)
 {
     FirBank *b = as_fir(handle);
     return b ? b->flt_len : -1;
+}
+
+extern "C" int llz_cuda_fir_bank_set_algo(unsigned long handle, int algo)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (algo != LLZ_CUDA_FIR_ALGO_AUTO && algo != LLZ_CUDA_FIR_ALGO_DIRECT && algo != LLZ_CUDA_FIR_ALGO_FFT) {
+        llz_set_error("unknown FIR algorithm %d", algo);
+        return -1;
+    }
+    const int prev = b->algo;
+    b->algo = algo;
+    if (fir_effective_algo(b) < 0) { b->algo = prev; return -1; }
+    return 0;
+}
+
+extern "C" int llz_cuda_fir_bank_get_algo(unsigned long handle)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    return fir_effective_algo(b);
 }
 
 extern "C" int llz_cuda_fir_bank_copy_taps(unsigned long handle, double *h_out)

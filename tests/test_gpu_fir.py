@@ -67,8 +67,12 @@ def test_bank_f64_all_tap_counts(zlib, port, cuda, N):
     x = rng.uniform(-1, 1, (C_, n))
     want = oracle_bank(port, h, x)
     dx = torch.from_numpy(x).cuda()
-    for dtype, exact in ((zlib.F64_STRICT, True), (zlib.F64, False)):
-        bank = zlib.FirBank(C_, dtype, taps=h)
+    cases = [(zlib.F64_STRICT, zlib.FIR_AUTO, True), (zlib.F64, zlib.FIR_DIRECT, False)]
+    if N <= 897:
+        cases.append((zlib.F64, zlib.FIR_FFT, False))
+    for dtype, algo, exact in cases:
+        bank = zlib.FirBank(C_, dtype, taps=h, algo=algo)
+        assert bank.algo == (zlib.FIR_FFT if algo == zlib.FIR_FFT else zlib.FIR_DIRECT)
         dy = torch.empty_like(dx)
         bank.run(dx, n, dy, n, n)
         torch.cuda.synchronize()
@@ -81,14 +85,15 @@ def test_bank_f64_all_tap_counts(zlib, port, cuda, N):
         bank.close()
 
 
-@pytest.mark.parametrize("N,fc,win", [(127, 0.23, 0), (4095, 0.11, 2), (48, 0.4, 1)])
-def test_bank_f32_meets_snr(zlib, port, cuda, N, fc, win):
+@pytest.mark.parametrize("N,fc,win,algo", [(127, 0.23, 0, 1), (4095, 0.11, 2, 1), (48, 0.4, 1, 1),
+                                          (127, 0.23, 0, 2), (48, 0.4, 1, 2), (513, 0.11, 2, 2), (897, 0.05, 1, 2)])
+def test_bank_f32_meets_snr(zlib, port, cuda, N, fc, win, algo):
     torch = cuda
     h = port.fir_design(0, N, fc, 0.0, win)
     C_, n = 4, 50000
     x = np.stack([port.lcg_f64(n, 12345 + c) for c in range(C_)])
     want = oracle_bank(port, h, x)
-    bank = zlib.FirBank(C_, zlib.F32, kind=zlib.LPF, flt_len=N, fc1=fc, win=win)
+    bank = zlib.FirBank(C_, zlib.F32, kind=zlib.LPF, flt_len=N, fc1=fc, win=win, algo=algo)
     assert bank.taps().tobytes() == h.tobytes()
     dx = torch.from_numpy(x.astype(np.float32)).cuda()
     dy = torch.empty_like(dx)
@@ -139,7 +144,7 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
     x = np.stack([port.lcg_f64(n, 7 + c) for c in range(C_)])
     dx = torch.from_numpy(x).cuda()
     one = torch.empty_like(dx)
-    bank = zlib.FirBank(C_, zlib.F64, taps=h)
+    bank = zlib.FirBank(C_, zlib.F64, taps=h, algo=zlib.FIR_DIRECT)
     bank.run(dx, n, one, n, n)
     for world in (2, 4, 8):
         seg_out = torch.zeros_like(dx)
@@ -159,6 +164,74 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
     want = oracle_bank(port, h, x)
     assert np.abs(one.cpu().numpy() - want).max() <= TOL_F64
     bank.close()
+    # overlap-save kernel: the block grid moves with the segment start, so segments agree with the one-shot run
+    # to rounding (not bit for bit)
+    fbank = zlib.FirBank(C_, zlib.F64, taps=h, algo=zlib.FIR_FFT)
+    for world in (2, 8):
+        seg_out = torch.zeros_like(dx)
+        for rank in range(world):
+            s = zlib.shard_fir_segments(n, N, world, rank)
+            fbank.reset()
+            if s.halo:
+                fbank.set_history(dx.data_ptr() + 8 * (s.in_start - s.halo), n)
+            fbank.run(dx.data_ptr() + 8 * s.in_start, n, seg_out.data_ptr() + 8 * s.out_start, n, s.in_count)
+        torch.cuda.synchronize()
+        assert np.abs(seg_out.cpu().numpy() - want).max() <= TOL_F64, world
+    fbank.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_fft_bank_streaming_ragged_chunks(zlib, port, cuda, dtype):
+    """overlap-save kernel: chunk sizes below / around the history and the block size, odd strides, flush, restart"""
+    torch = cuda
+    h = port.fir_design(2, 129, 0.2, 0.6, 2)
+    C_, n = 5, 40001
+    x = np.stack([port.lcg_f64(n, 100 + c) for c in range(C_)])
+    want = oracle_bank(port, h, x, n_out=n + 128)
+    tdt, npdt, es = (torch.float64, np.float64, 8) if dtype == "f64" else (torch.float32, np.float32, 4)
+    tol = TOL_F64 if dtype == "f64" else TOL_F32_ABS
+    stride = n + 3
+    dx = torch.zeros(C_, stride, dtype=tdt, device="cuda")
+    dx[:, :n] = torch.from_numpy(x.astype(npdt)).cuda()
+    dy = torch.full((C_, stride + 200), 7.0, dtype=tdt, device="cuda")
+    bank = zlib.FirBank(C_, zlib.F64 if dtype == "f64" else zlib.F32, taps=h, algo=zlib.FIR_FFT)
+    pos = 0
+    for step in (1, 7, 100, 128, 129, 895, 896, 1792, 1793, 5000, 3, 20000, 10 ** 9):
+        m = min(step, n - pos)
+        if m <= 0:
+            break
+        bank.run(dx.data_ptr() + es * pos, stride, dy.data_ptr() + es * pos, stride + 200, m)
+        pos += m
+    assert pos == n
+    assert bank.flush(dy.data_ptr() + es * n, stride + 200) == 128
+    torch.cuda.synchronize()
+    got = dy.cpu().numpy()
+    assert np.abs(got[:, :n + 128] - want).max() <= tol
+    assert (got[:, n + 128:] == 7.0).all()                   # nothing written past the end
+    if dtype == "f32":
+        assert snr_db(want, got[:, :n + 128]) >= SNR_F32_DB
+    bank.run(dx, stride, dy, stride + 200, 1000)
+    torch.cuda.synchronize()
+    assert np.abs(dy.cpu().numpy()[:, :1000] - want[:, :1000]).max() <= tol
+    bank.close()
+
+
+def test_fft_algo_selection(zlib, cuda):
+    """AUTO picks overlap-save for tolerance-mode banks of 48..897 taps; STRICT and long filters stay direct"""
+    h = np.ones(127) / 127
+    for dtype, N, want in ((zlib.F64, 127, zlib.FIR_FFT), (zlib.F32, 127, zlib.FIR_FFT), (zlib.F64, 47, zlib.FIR_DIRECT),
+                           (zlib.F64, 898, zlib.FIR_DIRECT), (zlib.F64_STRICT, 127, zlib.FIR_DIRECT)):
+        b = zlib.FirBank(2, dtype, taps=np.ones(N) / N)
+        assert b.algo == want, (dtype, N)
+        b.close()
+    b = zlib.FirBank(2, zlib.F64_STRICT, taps=h)
+    assert zlib.lib().llz_cuda_fir_bank_set_algo(b.handle, zlib.FIR_FFT) == -1
+    assert zlib.lib().llz_cuda_fir_bank_set_algo(b.handle, 9) == -1
+    assert b.algo == zlib.FIR_DIRECT
+    b.close()
+    b = zlib.FirBank(2, zlib.F64, taps=np.ones(898) / 898)
+    assert zlib.lib().llz_cuda_fir_bank_set_algo(b.handle, zlib.FIR_FFT) == -1
+    b.close()
 
 
 def test_run_host_pipeline(zlib, port, cuda):
@@ -170,7 +243,7 @@ def test_run_host_pipeline(zlib, port, cuda):
     for c in range(C_):
         x[c] = port.lcg_f64(n, 12345 + c)
     y = zlib.host_alloc(C_ * n * 8, np.float64).reshape(C_, n)
-    bank = zlib.FirBank(C_, zlib.F64, taps=h)
+    bank = zlib.FirBank(C_, zlib.F64, taps=h, algo=zlib.FIR_DIRECT)
     bank.run_host(x, n, y, n, n)
     dx = torch.from_numpy(np.ascontiguousarray(x)).cuda()
     dy = torch.empty_like(dx)
@@ -189,6 +262,13 @@ def test_run_host_pipeline(zlib, port, cuda):
     bank.run_host(xp, 300000, yp, 300000, 300000)
     assert np.array_equal(yp, y[:, :300000])
     bank.close()
+    # the overlap-save kernel through the same pipeline: chunk boundaries move its block grid -> rounding-level
+    fbank = zlib.FirBank(C_, zlib.F64, taps=h)
+    assert fbank.algo == zlib.FIR_FFT
+    y2 = np.empty_like(np.asarray(y))
+    fbank.run_host(x, n, y2, n, n)
+    assert np.abs(y2 - y).max() <= TOL_F64
+    fbank.close()
     zlib.host_free(x.reshape(-1)); zlib.host_free(y.reshape(-1))
 
 
