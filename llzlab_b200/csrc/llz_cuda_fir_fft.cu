@@ -9,8 +9,8 @@
 // matter how well it feeds the pipe.  Overlap-save with a 1024-point transform does the same
 // convolution in ~35 FMA-pipe instructions per output instead of 127:
 //
-//   * one WARP owns one work item = two consecutive blocks of B = 1024 - (N-1) outputs of one
-//     channel, packed as one complex signal  z[n] = xA[n] + i*xB[n]  (h is real, so the real and
+//   * one WARP owns one work item = two consecutive blocks of B = 1024 - halo outputs of one channel
+//     (halo = N-1 rounded up to 32 samples, so every 32-lane row of loads and stores is 32-sample aligned), packed as one complex signal  z[n] = xA[n] + i*xB[n]  (h is real, so the real and
 //     imaginary parts of  ifft(fft(z) * H)  are the two filtered blocks: no real-FFT split pass);
 //   * the 1024-point transform is 32 x 32 (llz_fft32.cuh): each lane holds 32 complex points in
 //     registers; lane t loads  x[s + t + 32 j]  straight from global memory (256 contiguous bytes per
@@ -29,6 +29,8 @@
 //
 // Algorithmic cost per item (2B outputs), per lane: 4 x 388 (DFT-32) + 2 x 124 (twiddles) + 128 (H)
 // = 1928 FMA-pipe instructions; shared memory: 2 x (32 + 32) x 2 accesses of sizeof(T).
+#include <stdlib.h>
+
 #include "llz_fft32.cuh"
 #include "llz_fir_kernels.h"
 
@@ -42,15 +44,36 @@ template <> struct Cplx<double> { using type = double2; };
 // and the column-wise loads (lane = column) bank-conflict-free for 4- and 8-byte elements
 constexpr int kFftPitch = kFftR + 1;
 
-template <typename T>
-__device__ __forceinline__ void warp_transpose(T (&v)[32], T *buf, int lane)
+// PACK = false: one array at a time through a [32][33] buffer of T (two round trips per exchange);
+// PACK = true: (re, im) pairs through a [32][33] buffer of complex elements (one round trip, half the
+// shared-memory instructions, twice the buffer).  Both patterns are bank-conflict-free.
+template <typename T, bool PACK>
+__device__ __forceinline__ void warp_exchange(T (&re)[32], T (&im)[32], void *buf_raw, int lane)
 {
+    if constexpr (PACK) {
+        using C = typename Cplx<T>::type;
+        C *buf = reinterpret_cast<C *>(buf_raw);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) buf[lane * kFftPitch + k] = v[k];
-    __syncwarp();
+        for (int k = 0; k < 32; ++k) { C v; v.x = re[k]; v.y = im[k]; buf[lane * kFftPitch + k] = v; }
+        __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = buf[k * kFftPitch + lane];
-    __syncwarp();
+        for (int k = 0; k < 32; ++k) { const C v = buf[k * kFftPitch + lane]; re[k] = v.x; im[k] = v.y; }
+        __syncwarp();
+    } else {
+        T *buf = reinterpret_cast<T *>(buf_raw);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) buf[lane * kFftPitch + k] = re[k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) re[k] = buf[k * kFftPitch + lane];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) buf[lane * kFftPitch + k] = im[k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) im[k] = buf[k * kFftPitch + lane];
+        __syncwarp();
+    }
 }
 
 template <typename T>
@@ -65,7 +88,7 @@ __device__ __forceinline__ T fir_fft_sample(const FirFftLaunch<T> &a, const T *x
 // buffers): unguarded loads and stores.  EDGE = true: the first / last items of a channel (history splice,
 // zero fill past the end, flush).  Two instantiations rather than one branch: the compiler would otherwise
 // clone the whole forward half of the transform behind each load path.
-template <typename T, int WARPS, bool EDGE>
+template <typename T, int WARPS, bool PACK, bool EDGE>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fir_fft_kernel(FirFftLaunch<T> a)
 {
@@ -73,13 +96,14 @@ fir_fft_kernel(FirFftLaunch<T> a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *tw_s = reinterpret_cast<C *>(smem_raw);                        // [32][32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    T *buf = reinterpret_cast<T *>(tw_s + kFftR * kFftR) + warp * (kFftR * kFftPitch);
+    unsigned char *buf = reinterpret_cast<unsigned char *>(tw_s + kFftR * kFftR) +
+                         (size_t)warp * (kFftR * kFftPitch) * sizeof(T) * (PACK ? 2 : 1);
 
     for (int i = threadIdx.x; i < kFftR * kFftR; i += WARPS * 32) tw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
     __syncthreads();
 
     const C *Hc = reinterpret_cast<const C *>(a.H);
-    const int hl = a.ntaps - 1;
+    const int hl = a.halo;              // N-1 rounded up to 32 samples: every row of 32 lanes is 32-sample aligned
     const int B = a.B;
     const long long total = a.items_per_channel * a.n_channels;
 
@@ -98,8 +122,20 @@ fir_fft_kernel(FirFftLaunch<T> a)
             const T *p = xc + s + lane;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { re[j] = __ldg(p + 32 * j); im[j] = __ldg(p + B + 32 * j); }
+            if (a.prefetch) {
+                // pull this warp's next item (same channel in the common case) into L2 while this one computes
+                const long long nitem = item + (long long)gridDim.x * WARPS;
+                if (nitem < total) {
+                    const int nch = (int)(nitem / a.items_per_channel);
+                    const long long npair = a.first_pair + (nitem - (long long)nch * a.items_per_channel);
+                    const char *np = reinterpret_cast<const char *>(a.x + (long long)nch * a.x_stride + npair * (2LL * B) - hl);
+                    const int span = (kFftN + B) * (int)sizeof(T);
+                    for (int off = lane * 128; off < span; off += 32 * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(np + off));
+                }
+            }
         } else {
-            const T *hc = a.hist ? a.hist + (long long)ch * hl : nullptr;
+            const T *hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const long long g = s + lane + 32 * j;
@@ -115,8 +151,7 @@ fir_fft_kernel(FirFftLaunch<T> a)
             const C w = tw_s[k * kFftR + lane];
             cmul_inplace<T, false>(re[k], im[k], w.x, w.y);
         }
-        warp_transpose(re, buf, lane);
-        warp_transpose(im, buf, lane);
+        warp_exchange<T, PACK>(re, im, buf, lane);
 
         // ---- lane k2: DFT over t -> Z[k2 + 32 k1]; times H; inverse DFT over k1; conj twiddle ------------
         dft32<T, false>(re, im);
@@ -131,26 +166,23 @@ fir_fft_kernel(FirFftLaunch<T> a)
             const C w = tw_s[k * kFftR + lane];
             cmul_inplace<T, true>(re[k], im[k], w.x, w.y);
         }
-        warp_transpose(re, buf, lane);
-        warp_transpose(im, buf, lane);
+        warp_exchange<T, PACK>(re, im, buf, lane);
 
         // ---- lane t: inverse DFT over k2 -> y[t + 32 j] ------------------------------------------------
         dft32<T, true>(re, im);
 
-        // ---- scatter: circular positions m >= N-1 are the valid outputs -----------------------------------
+        // ---- scatter: circular positions m >= halo (whole rows j >= halo/32) are the valid outputs -------------
         T *q = yc + o - hl + lane;
+        const int j0 = hl >> 5;
         if constexpr (!EDGE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int m = lane + 32 * j;
-                if (m >= hl) { __stcs(q + 32 * j, re[j]); __stcs(q + B + 32 * j, im[j]); }
-            }
+            for (int j = 0; j < 32; ++j)
+                if (j >= j0) { __stcs(q + 32 * j, re[j]); __stcs(q + B + 32 * j, im[j]); }
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int m = lane + 32 * j;
-                const long long tA = o - hl + m;
-                if (m >= hl) {
+                const long long tA = o - hl + lane + 32 * j;
+                if (j >= j0) {
                     if (tA < a.n) __stcs(q + 32 * j, re[j]);
                     if (tA + B < a.n) __stcs(q + B + 32 * j, im[j]);
                 }
@@ -159,34 +191,12 @@ fir_fft_kernel(FirFftLaunch<T> a)
     }
 }
 
-template <typename T> struct FftCfg;
-template <> struct FftCfg<double> { static constexpr int WARPS = 8; };
-template <> struct FftCfg<float>  { static constexpr int WARPS = 16; };
-
-template <typename T>
-int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
+template <typename T, int WARPS, bool PACK>
+static int fir_fft_launch_cfg(const FirFftLaunch<T> &a, int n_channels, long long ppc, long long p_lo, long long p_hi,
+                              int sm_count, cudaStream_t stream)
 {
-    if (a.n <= 0 || n_channels <= 0) return 0;
-    if (a.ntaps < 1 || a.ntaps > kFirFftMaxTaps) {
-        llz_set_error("overlap-save FIR kernel takes 1..%d taps, got %d", kFirFftMaxTaps, a.ntaps);
-        return -1;
-    }
-    constexpr int WARPS = FftCfg<T>::WARPS;
-    a.B = kFftN - (a.ntaps - 1);
-    a.n_channels = n_channels;
-    const long long two_b = 2LL * a.B;
-    const long long ppc = (a.n + two_b - 1) / two_b;
-    // interior pairs p: p*2B - (N-1) >= 0 and (p+1)*2B <= n, and there is an input buffer at all
-    long long p_lo = (a.ntaps - 1 + two_b - 1) / two_b, p_hi = a.n / two_b;
-    if (!a.x || p_hi < p_lo) { p_lo = 0; p_hi = 0; }
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0, sms = 0;
-        LLZ_CUDA_TRY(cudaGetDevice(&dev));
-        LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        sm_count = sms;
-    }
-    const size_t smem = (size_t)kFftR * kFftR * 2 * sizeof(T) + (size_t)WARPS * kFftR * kFftPitch * sizeof(T);
+    const size_t smem = (size_t)kFftR * kFftR * 2 * sizeof(T) +
+                        (size_t)WARPS * kFftR * kFftPitch * sizeof(T) * (PACK ? 2 : 1);
     auto run = [&](auto kern, long long first, long long count, long long gap_start, long long gap_len) -> int {
         if (count <= 0) return 0;
         FirFftLaunch<T> b = a;
@@ -201,8 +211,55 @@ int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
         LLZ_CUDA_TRY(cudaGetLastError());
         return 0;
     };
-    if (run(fir_fft_kernel<T, WARPS, false>, p_lo, p_hi - p_lo, ppc, 0) != 0) return -1;
-    return run(fir_fft_kernel<T, WARPS, true>, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo);
+    if (run(fir_fft_kernel<T, WARPS, PACK, false>, p_lo, p_hi - p_lo, ppc, 0) != 0) return -1;
+    return run(fir_fft_kernel<T, WARPS, PACK, true>, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo);
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <typename T>
+int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
+{
+    if (a.n <= 0 || n_channels <= 0) return 0;
+    if (a.ntaps < 1 || a.ntaps > kFirFftMaxTaps) {
+        llz_set_error("overlap-save FIR kernel takes 1..%d taps, got %d", kFirFftMaxTaps, a.ntaps);
+        return -1;
+    }
+    a.halo = (a.ntaps - 1 + 31) / 32 * 32;
+    a.B = kFftN - a.halo;
+    a.n_channels = n_channels;
+    const long long two_b = 2LL * a.B;
+    const long long ppc = (a.n + two_b - 1) / two_b;
+    // interior pairs p: p*2B - halo >= 0 and (p+1)*2B <= n, and there is an input buffer at all
+    long long p_lo = (a.halo + two_b - 1) / two_b, p_hi = a.n / two_b;
+    if (!a.x || p_hi < p_lo) { p_lo = 0; p_hi = 0; }
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0, sms = 0;
+        LLZ_CUDA_TRY(cudaGetDevice(&dev));
+        LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        sm_count = sms;
+    }
+    // tuning knobs (measurements only): resident warps per SM, packed exchange, L2 prefetch of the next item
+    const int warps = env_int("LLZ_FFT_WARPS", sizeof(T) == 8 ? 12 : 20);
+    const int pack = env_int("LLZ_FFT_PACK", 1);
+    a.prefetch = env_int("LLZ_FFT_PREFETCH", 1);
+#define LLZ_FFT_CASE(W, P) \
+    if (warps == W && pack == P) return fir_fft_launch_cfg<T, W, P != 0>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream)
+    if constexpr (sizeof(T) == 8) {
+        LLZ_FFT_CASE(8, 0); LLZ_FFT_CASE(8, 1); LLZ_FFT_CASE(10, 0); LLZ_FFT_CASE(10, 1);
+        LLZ_FFT_CASE(12, 0); LLZ_FFT_CASE(12, 1);
+    } else {
+        LLZ_FFT_CASE(16, 0); LLZ_FFT_CASE(16, 1); LLZ_FFT_CASE(20, 0); LLZ_FFT_CASE(20, 1);
+        LLZ_FFT_CASE(24, 0); LLZ_FFT_CASE(24, 1);
+    }
+#undef LLZ_FFT_CASE
+    llz_set_error("no overlap-save kernel variant for LLZ_FFT_WARPS=%d LLZ_FFT_PACK=%d", warps, pack);
+    return -1;
 }
 
 template int fir_fft_launch<float>(FirFftLaunch<float>, int, cudaStream_t);

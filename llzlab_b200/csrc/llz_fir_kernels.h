@@ -33,7 +33,7 @@ int fir_update_history(const T *x, long long x_stride, long long n, const T *his
 
 // ---- overlap-save (1024-point FFT) FIR, llz_cuda_fir_fft.cu -----------------------------------------
 constexpr int kFirFftMinTapsAuto = 48;   // below this the direct kernel is at least as fast
-constexpr int kFirFftMaxTaps = 897;      // leaves B = 1024 - (N-1) >= 128 valid outputs per block
+constexpr int kFirFftMaxTaps = 897;      // leaves B = 1024 - halo >= 128 valid outputs per block
 
 template <typename T>
 struct FirFftLaunch {
@@ -47,7 +47,8 @@ struct FirFftLaunch {
     const T *H;            // device [32][32] complex: spectrum of the taps / 1024, H[k1][k2] = bin k2 + 32*k1
     const T *tw;           // device [32][32] complex: exp(-2*pi*i*k*t/1024)
     // filled in by fir_fft_launch: item i of a channel is pair first_pair + i, skipping [gap_start, gap_start + gap_len)
-    int B;
+    int halo, B;           // halo = N-1 rounded up to 32; B = 1024 - halo valid outputs per block
+    int prefetch;          // L2 prefetch of the warp's next item
     int n_channels;
     long long first_pair, items_per_channel, gap_start, gap_len;
 };
