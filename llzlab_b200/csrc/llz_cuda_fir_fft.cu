@@ -17,8 +17,8 @@
 //     warp instruction) -- DFT-32 over j -- twiddle -- transpose through shared memory -- DFT-32
 //     over t -- multiply by H -- inverse DFT-32 -- conjugate twiddle -- transpose -- inverse DFT-32,
 //     which leaves lane t holding outputs  t + 32 j  again: coalesced streaming stores;
-//   * only two transposes per item go through shared memory; the spectrum H (1/1024 folded in) is
-//     read through L1, the 32 x 32 inter-pass twiddles sit in shared memory once per CTA;
+//   * only two transposes per item go through shared memory; the spectrum H (1/1024 folded in) and the
+//     32 x 32 inter-pass twiddles sit in shared memory once per CTA (fixed latency, no L1 misses);
 //   * no CTA-wide barrier after the table load: warps are independent and loop over items
 //     (persistent grid of one CTA per SM), so one warp's loads hide behind the others' butterflies.
 //
@@ -84,33 +84,74 @@ __device__ __forceinline__ T fir_fft_sample(const FirFftLaunch<T> &a, const T *x
     return T(0);
 }
 
-// EDGE = false: every item is interior (its 1024 + B input samples and 2B outputs lie inside this call's
-// buffers): unguarded loads and stores.  EDGE = true: the first / last items of a channel (history splice,
-// zero fill past the end, flush).  Two instantiations rather than one branch: the compiler would otherwise
-// clone the whole forward half of the transform behind each load path.
-template <typename T, int WARPS, bool PACK, bool EDGE>
+// MODE 0 (kGather): every item is interior (its 1024 + B input samples and 2B outputs lie inside this call's
+//   buffers): unguarded loads straight from global memory, optional L2 prefetch of the warp's next item.
+// MODE 1 (kStaged): interior items; the warp's NEXT item arrives in a per-warp staging buffer by one TMA bulk copy
+//   (cp.async.bulk + mbarrier) issued as soon as the current item has been gathered into registers, so the DRAM
+//   latency of the input hides behind a whole item of butterflies.  Needs 16-byte aligned channel rows.
+// MODE 2 (kEdge): the first / last items of a channel (history splice, zero fill past the end, flush).
+// Separate instantiations rather than branches: the compiler would otherwise clone the forward half of the
+// transform behind each load path.
+constexpr int kGather = 0, kStaged = 1, kEdge = 2;
+
+template <typename T, int WARPS, bool PACK, int MODE>
+struct FftSmem {
+    static constexpr size_t tables = (size_t)kFftR * kFftR * 2 * sizeof(T) * 2;                   // tw + H
+    static constexpr size_t exch = (size_t)kFftR * kFftPitch * sizeof(T) * (PACK ? 2 : 1);        // per warp
+    static constexpr size_t stage = MODE == kStaged ? (size_t)(2 * kFftN - 32) * sizeof(T) : 0;   // per warp, halo >= 32
+    static constexpr size_t bars = 128;
+    static constexpr size_t total = tables + bars + WARPS * (exch + stage);
+};
+
+template <typename T, int WARPS, bool PACK, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 fir_fft_kernel(FirFftLaunch<T> a)
 {
     using C = typename Cplx<T>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using SM = FftSmem<T, WARPS, PACK, MODE>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     C *tw_s = reinterpret_cast<C *>(smem_raw);                        // [32][32]
+    C *H_s = tw_s + kFftR * kFftR;                                    // [32][32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *buf = reinterpret_cast<unsigned char *>(tw_s + kFftR * kFftR) +
-                         (size_t)warp * (kFftR * kFftPitch) * sizeof(T) * (PACK ? 2 : 1);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM::tables) + warp;
+    unsigned char *buf = smem_raw + SM::tables + SM::bars + (size_t)warp * SM::exch;
+    [[maybe_unused]] T *stage = reinterpret_cast<T *>(smem_raw + SM::tables + SM::bars + WARPS * SM::exch + (size_t)warp * SM::stage);
 
-    for (int i = threadIdx.x; i < kFftR * kFftR; i += WARPS * 32) tw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
+    for (int i = threadIdx.x; i < kFftR * kFftR; i += WARPS * 32) {
+        tw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
+        H_s[i] = reinterpret_cast<const C *>(a.H)[i];
+    }
     __syncthreads();
 
-    const C *Hc = reinterpret_cast<const C *>(a.H);
     const int hl = a.halo;              // N-1 rounded up to 32 samples: every row of 32 lanes is 32-sample aligned
     const int B = a.B;
     const long long total = a.items_per_channel * a.n_channels;
+    const long long item_step = (long long)gridDim.x * WARPS;
+    long long item = (long long)blockIdx.x * WARPS + warp;
 
-    for (long long item = (long long)blockIdx.x * WARPS + warp; item < total; item += (long long)gridDim.x * WARPS) {
+    // first input sample (block A) of an interior item
+    auto item_src = [&](long long it) -> const T * {
+        const int c = (int)(it / a.items_per_channel);
+        const long long p = a.first_pair + (it - (long long)c * a.items_per_channel);
+        return a.x + (long long)c * a.x_stride + p * (2LL * B) - hl;
+    };
+    [[maybe_unused]] const uint32_t span_bytes = (uint32_t)((kFftN + B) * sizeof(T));
+    [[maybe_unused]] uint32_t phase = 0;
+    if constexpr (MODE == kStaged) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            if (item < total) {
+                mbar_expect_tx(bar, span_bytes);
+                tma_bulk_g2s(stage, item_src(item), span_bytes, bar);
+            }
+        }
+        __syncwarp();
+    }
+
+    for (; item < total; item += item_step) {
         const int ch = (int)(item / a.items_per_channel);
         long long pair = a.first_pair + (item - (long long)ch * a.items_per_channel);
-        if (pair >= a.gap_start) pair += a.gap_len;
+        if constexpr (MODE == kEdge) { if (pair >= a.gap_start) pair += a.gap_len; }
         const long long o = pair * (2LL * B);          // first output of block A
         const long long s = o - hl;                    // first input of block A
         const T *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
@@ -118,21 +159,25 @@ fir_fft_kernel(FirFftLaunch<T> a)
 
         T re[32], im[32];
         // ---- gather: lane t holds z[t + 32 j] ------------------------------------------------------
-        if constexpr (!EDGE) {
+        if constexpr (MODE == kGather) {
             const T *p = xc + s + lane;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { re[j] = __ldg(p + 32 * j); im[j] = __ldg(p + B + 32 * j); }
-            if (a.prefetch) {
-                // pull this warp's next item (same channel in the common case) into L2 while this one computes
-                const long long nitem = item + (long long)gridDim.x * WARPS;
-                if (nitem < total) {
-                    const int nch = (int)(nitem / a.items_per_channel);
-                    const long long npair = a.first_pair + (nitem - (long long)nch * a.items_per_channel);
-                    const char *np = reinterpret_cast<const char *>(a.x + (long long)nch * a.x_stride + npair * (2LL * B) - hl);
-                    const int span = (kFftN + B) * (int)sizeof(T);
-                    for (int off = lane * 128; off < span; off += 32 * 128)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(np + off));
-                }
+            if (a.prefetch && item + item_step < total) {
+                // pull this warp's next item into L2 while this one computes
+                const char *np = reinterpret_cast<const char *>(item_src(item + item_step));
+                for (int off = lane * 128; off < (int)span_bytes; off += 32 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(np + off));
+            }
+        } else if constexpr (MODE == kStaged) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { re[j] = stage[lane + 32 * j]; im[j] = stage[B + lane + 32 * j]; }
+            __syncwarp();                              // every lane has its samples: the buffer may be refilled
+            if (lane == 0 && item + item_step < total) {
+                mbar_expect_tx(bar, span_bytes);
+                tma_bulk_g2s(stage, item_src(item + item_step), span_bytes, bar);
             }
         } else {
             const T *hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
@@ -157,7 +202,7 @@ fir_fft_kernel(FirFftLaunch<T> a)
         dft32<T, false>(re, im);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-            const C h = __ldg(Hc + k * kFftR + lane);
+            const C h = H_s[k * kFftR + lane];
             cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
         }
         dft32<T, true>(re, im);
@@ -174,7 +219,7 @@ fir_fft_kernel(FirFftLaunch<T> a)
         // ---- scatter: circular positions m >= halo (whole rows j >= halo/32) are the valid outputs -------------
         T *q = yc + o - hl + lane;
         const int j0 = hl >> 5;
-        if constexpr (!EDGE) {
+        if constexpr (MODE != kEdge) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j >= j0) { __stcs(q + 32 * j, re[j]); __stcs(q + B + 32 * j, im[j]); }
@@ -191,28 +236,33 @@ fir_fft_kernel(FirFftLaunch<T> a)
     }
 }
 
-template <typename T, int WARPS, bool PACK>
+template <typename T, int WARPS, bool PACK, int MODE>
+static int fir_fft_run(FirFftLaunch<T> b, int n_channels, long long first, long long count, long long gap_start,
+                       long long gap_len, int sm_count, cudaStream_t stream)
+{
+    if (count <= 0) return 0;
+    constexpr size_t smem = FftSmem<T, WARPS, PACK, MODE>::total;
+    static_assert(smem <= 227 * 1024, "overlap-save kernel variant exceeds the shared memory of an SM");
+    b.first_pair = first;
+    b.items_per_channel = count;
+    b.gap_start = gap_start;
+    b.gap_len = gap_len;
+    auto kern = fir_fft_kernel<T, WARPS, PACK, MODE>;
+    LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ctas_needed = (count * n_channels + WARPS - 1) / WARPS;
+    const unsigned grid = (unsigned)(ctas_needed < sm_count ? ctas_needed : sm_count);
+    kern<<<grid, WARPS * 32, smem, stream>>>(b);
+    LLZ_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int WARPS, bool PACK, bool STAGE>
 static int fir_fft_launch_cfg(const FirFftLaunch<T> &a, int n_channels, long long ppc, long long p_lo, long long p_hi,
                               int sm_count, cudaStream_t stream)
 {
-    const size_t smem = (size_t)kFftR * kFftR * 2 * sizeof(T) +
-                        (size_t)WARPS * kFftR * kFftPitch * sizeof(T) * (PACK ? 2 : 1);
-    auto run = [&](auto kern, long long first, long long count, long long gap_start, long long gap_len) -> int {
-        if (count <= 0) return 0;
-        FirFftLaunch<T> b = a;
-        b.first_pair = first;
-        b.items_per_channel = count;
-        b.gap_start = gap_start;
-        b.gap_len = gap_len;
-        LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const long long ctas_needed = (count * n_channels + WARPS - 1) / WARPS;
-        const unsigned grid = (unsigned)(ctas_needed < sm_count ? ctas_needed : sm_count);
-        kern<<<grid, WARPS * 32, smem, stream>>>(b);
-        LLZ_CUDA_TRY(cudaGetLastError());
-        return 0;
-    };
-    if (run(fir_fft_kernel<T, WARPS, PACK, false>, p_lo, p_hi - p_lo, ppc, 0) != 0) return -1;
-    return run(fir_fft_kernel<T, WARPS, PACK, true>, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo);
+    if (fir_fft_run<T, WARPS, PACK, STAGE ? kStaged : kGather>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0)
+        return -1;
+    return fir_fft_run<T, WARPS, PACK, kEdge>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
 }
 
 static int env_int(const char *name, int dflt)
@@ -244,21 +294,26 @@ int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
         LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         sm_count = sms;
     }
-    // tuning knobs (measurements only): resident warps per SM, packed exchange, L2 prefetch of the next item
-    const int warps = env_int("LLZ_FFT_WARPS", sizeof(T) == 8 ? 12 : 20);
-    const int pack = env_int("LLZ_FFT_PACK", 1);
+    // tuning knobs (measurements only): resident warps per SM, packed exchange, TMA staging / L2 prefetch of the next item
+    // measured on C2 (profiles/r01_sweep_fft.txt): f64 -- 8 warps, plain exchange, TMA staging (packed exchange when
+    // the rows are not 16-byte aligned); f32 -- 20 warps, packed exchange, direct gather + L2 prefetch
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 && (a.x_stride * sizeof(T)) % 16 == 0;
+    const int stage = env_int("LLZ_FFT_STAGE", sizeof(T) == 8 ? 1 : 0) && aligned;
+    const int warps = env_int("LLZ_FFT_WARPS", sizeof(T) == 8 ? 8 : 20);
+    const int pack = env_int("LLZ_FFT_PACK", sizeof(T) == 8 ? (stage ? 0 : 1) : 1);
     a.prefetch = env_int("LLZ_FFT_PREFETCH", 1);
-#define LLZ_FFT_CASE(W, P) \
-    if (warps == W && pack == P) return fir_fft_launch_cfg<T, W, P != 0>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream)
+#define LLZ_FFT_CASE(W, P, S) \
+    if (warps == W && pack == P && stage == S) \
+        return fir_fft_launch_cfg<T, W, P != 0, S != 0>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream)
     if constexpr (sizeof(T) == 8) {
-        LLZ_FFT_CASE(8, 0); LLZ_FFT_CASE(8, 1); LLZ_FFT_CASE(10, 0); LLZ_FFT_CASE(10, 1);
-        LLZ_FFT_CASE(12, 0); LLZ_FFT_CASE(12, 1);
+        LLZ_FFT_CASE(8, 0, 0); LLZ_FFT_CASE(8, 0, 1); LLZ_FFT_CASE(8, 1, 0);
+        LLZ_FFT_CASE(12, 0, 0);
     } else {
-        LLZ_FFT_CASE(16, 0); LLZ_FFT_CASE(16, 1); LLZ_FFT_CASE(20, 0); LLZ_FFT_CASE(20, 1);
-        LLZ_FFT_CASE(24, 0); LLZ_FFT_CASE(24, 1);
+        LLZ_FFT_CASE(16, 0, 0); LLZ_FFT_CASE(16, 0, 1); LLZ_FFT_CASE(16, 1, 0);
+        LLZ_FFT_CASE(12, 1, 1); LLZ_FFT_CASE(20, 1, 0);
     }
 #undef LLZ_FFT_CASE
-    llz_set_error("no overlap-save kernel variant for LLZ_FFT_WARPS=%d LLZ_FFT_PACK=%d", warps, pack);
+    llz_set_error("no overlap-save kernel variant for LLZ_FFT_WARPS=%d LLZ_FFT_PACK=%d LLZ_FFT_STAGE=%d", warps, pack, stage);
     return -1;
 }
 
