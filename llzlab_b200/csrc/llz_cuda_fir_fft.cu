@@ -13,12 +13,13 @@
 //     (halo = N-1 rounded up to 32 samples, so every 32-lane row of loads and stores is 32-sample aligned), packed as one complex signal  z[n] = xA[n] + i*xB[n]  (h is real, so the real and
 //     imaginary parts of  ifft(fft(z) * H)  are the two filtered blocks: no real-FFT split pass);
 //   * the 1024-point transform is 32 x 32 (llz_fft32.cuh): each lane holds 32 complex points in
-//     registers; lane t loads  x[s + t + 32 j]  straight from global memory (256 contiguous bytes per
-//     warp instruction) -- DFT-32 over j -- twiddle -- transpose through shared memory -- DFT-32
-//     over t -- multiply by H -- inverse DFT-32 -- conjugate twiddle -- transpose -- inverse DFT-32,
-//     which leaves lane t holding outputs  t + 32 j  again: coalesced streaming stores;
+//     registers; lane t gathers  x[s + t + 32 j]  (256 contiguous bytes per warp instruction) -- DFT-32
+//     over j -- transpose through shared memory -- DFT-32 over t with the four-step twiddle folded
+//     into its butterflies -- multiply by H -- inverse DFT-32 -- transpose -- inverse DFT-32 with the
+//     conjugate twiddle folded in, which leaves lane t holding outputs  t + 32 j  again: coalesced
+//     streaming stores;
 //   * only two transposes per item go through shared memory; the spectrum H (1/1024 folded in) and the
-//     32 x 32 inter-pass twiddles sit in shared memory once per CTA (fixed latency, no L1 misses);
+//     16 x 32 folded twiddles sit in shared memory once per CTA (fixed latency, no L1 misses);
 //   * no CTA-wide barrier after the table load: warps are independent and loop over items
 //     (persistent grid of one CTA per SM), so one warp's loads hide behind the others' butterflies.
 //
@@ -27,8 +28,11 @@
 // the result is NOT bit-identical -- LLZ_CUDA_F64_STRICT and the drop-in llz_fir_filter keep the
 // direct kernel.
 //
-// Algorithmic cost per item (2B outputs), per lane: 4 x 388 (DFT-32) + 2 x 124 (twiddles) + 128 (H)
-// = 1928 FMA-pipe instructions; shared memory: 2 x (32 + 32) x 2 accesses of sizeof(T).
+// Algorithmic cost per item (2B outputs), per lane: 2 x 388 (plain DFT-32) + 2 x 512 (DFT-32 with folded
+// twiddles) + 128 (H) = 1928 FMA-pipe instructions.  Shared-memory / LSU wavefronts per item (f64): 512 for the
+// two transposes, 128 folded twiddles, 128 spectrum, 128 staged input, 114 global stores: ~1010 against 964
+// FP64-pipe cycles -- the two pipes are co-limiters, which is why the twiddles are folded (31 -> 16 table
+// reads per pass) rather than multiplied in a separate pass.
 #include <stdlib.h>
 
 #include "llz_fft32.cuh"
@@ -96,7 +100,7 @@ constexpr int kGather = 0, kStaged = 1, kEdge = 2;
 
 template <typename T, int WARPS, bool PACK, int MODE>
 struct FftSmem {
-    static constexpr size_t tables = (size_t)kFftR * kFftR * 2 * sizeof(T) * 2;                   // tw + H
+    static constexpr size_t tables = (size_t)(kTwistEntries + kFftR) * kFftR * 2 * sizeof(T);     // twist table + H
     static constexpr size_t exch = (size_t)kFftR * kFftPitch * sizeof(T) * (PACK ? 2 : 1);        // per warp
     static constexpr size_t stage = MODE == kStaged ? (size_t)(2 * kFftN - 32) * sizeof(T) : 0;   // per warp, halo >= 32
     static constexpr size_t bars = 128;
@@ -110,15 +114,15 @@ fir_fft_kernel(FirFftLaunch<T> a)
     using C = typename Cplx<T>::type;
     using SM = FftSmem<T, WARPS, PACK, MODE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    C *tw_s = reinterpret_cast<C *>(smem_raw);                        // [32][32]
-    C *H_s = tw_s + kFftR * kFftR;                                    // [32][32]
+    C *tw_s = reinterpret_cast<C *>(smem_raw);                        // [16][32] folded twiddles (llz_fft32.cuh)
+    C *H_s = tw_s + kTwistEntries * kFftR;                            // [32][32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + SM::tables) + warp;
     unsigned char *buf = smem_raw + SM::tables + SM::bars + (size_t)warp * SM::exch;
     [[maybe_unused]] T *stage = reinterpret_cast<T *>(smem_raw + SM::tables + SM::bars + WARPS * SM::exch + (size_t)warp * SM::stage);
 
     for (int i = threadIdx.x; i < kFftR * kFftR; i += WARPS * 32) {
-        tw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
+        if (i < kTwistEntries * kFftR) tw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
         H_s[i] = reinterpret_cast<const C *>(a.H)[i];
     }
     __syncthreads();
@@ -189,32 +193,22 @@ fir_fft_kernel(FirFftLaunch<T> a)
             }
         }
 
-        // ---- forward pass 1: DFT over j, twiddle W_1024^(t*k2) -----------------------------------------
+        // ---- forward pass 1: DFT over j -------------------------------------------------------------------
         dft32<T, false>(re, im);
-#pragma unroll
-        for (int k = 1; k < 32; ++k) {
-            const C w = tw_s[k * kFftR + lane];
-            cmul_inplace<T, false>(re[k], im[k], w.x, w.y);
-        }
         warp_exchange<T, PACK>(re, im, buf, lane);
 
-        // ---- lane k2: DFT over t -> Z[k2 + 32 k1]; times H; inverse DFT over k1; conj twiddle ------------
-        dft32<T, false>(re, im);
+        // ---- lane k2: twiddle W_1024^(t*k2) folded into the DFT over t -> Z[k2 + 32 k1]; times H; inverse DFT over k1
+        dft32_twisted<T, false>(re, im, tw_s + lane, kFftR);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
             const C h = H_s[k * kFftR + lane];
             cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
         }
         dft32<T, true>(re, im);
-#pragma unroll
-        for (int k = 1; k < 32; ++k) {
-            const C w = tw_s[k * kFftR + lane];
-            cmul_inplace<T, true>(re[k], im[k], w.x, w.y);
-        }
         warp_exchange<T, PACK>(re, im, buf, lane);
 
-        // ---- lane t: inverse DFT over k2 -> y[t + 32 j] ------------------------------------------------
-        dft32<T, true>(re, im);
+        // ---- lane t: conjugate twiddle folded into the inverse DFT over k2 -> y[t + 32 j] ----------------------
+        dft32_twisted<T, true>(re, im, tw_s + lane, kFftR);
 
         // ---- scatter: circular positions m >= halo (whole rows j >= halo/32) are the valid outputs -------------
         T *q = yc + o - hl + lane;

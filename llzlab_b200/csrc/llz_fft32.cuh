@@ -137,6 +137,83 @@ LLZ_HD void dft32(T (&re)[32], T (&im)[32])
     for (int i = 0; i < 32; ++i) { re[i] = ar[i]; im[i] = ai[i]; }
 }
 
+// ---- DFT-32 with the four-step twiddle folded in ------------------------------------------------------
+// X[k] = sum_t (x[t] * w^t) * exp(-+ 2*pi*i*t*k/32),   w = exp(-+ 2*pi*i*l/1024)  (l = the lane's index in the
+// other dimension of the 32 x 32 split).  In the decimation-in-time network the factor w^t turns the stage-`len`
+// twiddle W_len^k into  T_len[k] = w^(32/len) * W_len^k  = exp(-+ i*theta),  theta = 2*pi*(l + 32 k)/(32 len):
+// every butterfly is "general" (6 instructions), but there is no separate twiddle pass (31 complex multiplies)
+// and only 16 table entries per lane instead of 31, because T_len[k + len/4] = -+i * T_len[k] (a free swap).
+// For len >= 4 and k < len/4, theta < pi/2, so the (cos, tan) form is safe (|cos * tan| <= 1: no error growth);
+// the single len = 2 twiddle reaches theta = pi/2 (l = 16) and uses the (cos, sin) form (8 instructions).
+// tab: 16 entries for this lane, stride `ts` elements of C = {x, y}:
+//   [0] (cos, sin) len 2 | [1] len 4 k0 | [2..3] len 8 k0..1 | [4..7] len 16 k0..3 | [8..15] len 32 k0..7, (cos, tan)
+constexpr int kTwistEntries = 16;
+
+template <typename T, bool INV, bool PARTNER>
+LLZ_HD void bfly_tan(T &ur, T &ui, T &vr, T &vi, T c, T t)
+{
+    // forward: T v = c (1 - i t)(vr + i vi) = c (p + i q),  p = vr + t vi,  q = vi - t vr;   inverse: t -> -t
+    const T p = fma_t<T>(INV ? -t : t, vi, vr);
+    const T q = fma_t<T>(INV ? t : -t, vr, vi);
+    const T ar = ur, ai = ui;
+    if (!PARTNER) {
+        ur = fma_t<T>(c, p, ar);  ui = fma_t<T>(c, q, ai);
+        vr = fma_t<T>(-c, p, ar); vi = fma_t<T>(-c, q, ai);
+    } else if (!INV) {
+        // twiddle -i*T:  c (q - i p)
+        ur = fma_t<T>(c, q, ar);  ui = fma_t<T>(-c, p, ai);
+        vr = fma_t<T>(-c, q, ar); vi = fma_t<T>(c, p, ai);
+    } else {
+        // twiddle +i*T:  c (-q + i p)
+        ur = fma_t<T>(-c, q, ar); ui = fma_t<T>(c, p, ai);
+        vr = fma_t<T>(c, q, ar);  vi = fma_t<T>(-c, p, ai);
+    }
+}
+
+template <typename T, bool INV, int LEN, int TAB0, typename C>
+LLZ_HD void dft32_twisted_stage(T (&ar)[32], T (&ai)[32], const C *tab, int ts)
+{
+    constexpr int quarter = LEN / 4, half = LEN / 2;
+#pragma unroll
+    for (int k = 0; k < quarter; ++k) {
+        const C w = tab[(TAB0 + k) * ts];
+#pragma unroll
+        for (int b = 0; b < 32; b += LEN) {
+            bfly_tan<T, INV, false>(ar[b + k], ai[b + k], ar[b + k + half], ai[b + k + half], w.x, w.y);
+            bfly_tan<T, INV, true>(ar[b + k + quarter], ai[b + k + quarter], ar[b + k + quarter + half],
+                                   ai[b + k + quarter + half], w.x, w.y);
+        }
+    }
+}
+
+template <typename T, bool INV, typename C>
+LLZ_HD void dft32_twisted(T (&re)[32], T (&im)[32], const C *tab, int ts)
+{
+    T ar[32], ai[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { ar[i] = re[brev5(i)]; ai[i] = im[brev5(i)]; }
+    {
+        // len 2: twiddle (c -+ i s) on the odd element
+        const C w = tab[0];
+        const T c = w.x, s = INV ? -w.y : w.y;
+#pragma unroll
+        for (int b = 0; b < 32; b += 2) {
+            const T ur = ar[b], ui = ai[b], vr = ar[b + 1], vi = ai[b + 1];
+            // (c - i s)(vr + i vi) = (c vr + s vi) + i (c vi - s vr)
+            ar[b]     = fma_t<T>(s, vi, fma_t<T>(c, vr, ur));
+            ai[b]     = fma_t<T>(-s, vr, fma_t<T>(c, vi, ui));
+            ar[b + 1] = fma_t<T>(-s, vi, fma_t<T>(-c, vr, ur));
+            ai[b + 1] = fma_t<T>(s, vr, fma_t<T>(-c, vi, ui));
+        }
+    }
+    dft32_twisted_stage<T, INV, 4, 1>(ar, ai, tab, ts);
+    dft32_twisted_stage<T, INV, 8, 2>(ar, ai, tab, ts);
+    dft32_twisted_stage<T, INV, 16, 4>(ar, ai, tab, ts);
+    dft32_twisted_stage<T, INV, 32, 8>(ar, ai, tab, ts);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { re[i] = ar[i]; im[i] = ai[i]; }
+}
+
 // (r + i*s) *= (c + i*d)        [CONJ: *= (c - i*d)]
 template <typename T, bool CONJ>
 LLZ_HD void cmul_inplace(T &r, T &s, T c, T d)
@@ -148,15 +225,20 @@ LLZ_HD void cmul_inplace(T &r, T &s, T c, T d)
 }
 
 // ---- host-side tables ---------------------------------------------------------------------------
-// tw[k][t] = exp(-2*pi*i*k*t/1024), k, t < 32, interleaved (re, im)
-inline void fft1024_make_twiddles(double *tw /* 32*32*2 */)
+// tab[e][l], e < 16, l < 32: the folded twiddles of dft32_twisted for lane l, interleaved pairs (see above)
+inline void fft1024_make_twist_table(double *tab /* 16*32*2 */)
 {
-    const long double w = -2.0L * 3.14159265358979323846264338327950288L / (long double)kFftN;
-    for (int k = 0; k < kFftR; ++k)
-        for (int t = 0; t < kFftR; ++t) {
-            tw[2 * (k * kFftR + t)] = (double)cosl(w * (long double)(k * t));
-            tw[2 * (k * kFftR + t) + 1] = (double)sinl(w * (long double)(k * t));
-        }
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+    int e = 0;
+    for (int len = 2; len <= 32; len <<= 1) {
+        const int nk = len == 2 ? 1 : len / 4;
+        for (int k = 0; k < nk; ++k, ++e)
+            for (int l = 0; l < kFftR; ++l) {
+                const long double th = two_pi * (long double)(l + 32 * k) / (long double)(32 * len);
+                tab[2 * (e * kFftR + l)] = (double)cosl(th);
+                tab[2 * (e * kFftR + l) + 1] = (double)(len == 2 ? sinl(th) : tanl(th));
+            }
+    }
 }
 
 // H[k1][k2] = (1/1024) * sum_n h[n] * exp(-2*pi*i*n*k/1024),  k = k2 + 32*k1, interleaved (re, im).

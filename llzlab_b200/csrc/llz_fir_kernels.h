@@ -45,7 +45,7 @@ struct FirFftLaunch {
     const T *hist;         // device [channels][ntaps-1] or nullptr
     int ntaps;
     const T *H;            // device [32][32] complex: spectrum of the taps / 1024, H[k1][k2] = bin k2 + 32*k1
-    const T *tw;           // device [32][32] complex: exp(-2*pi*i*k*t/1024)
+    const T *tw;           // device [16][32] pairs: folded twiddles of dft32_twisted (llz_fft32.cuh)
     // filled in by fir_fft_launch: item i of a channel is pair first_pair + i, skipping [gap_start, gap_start + gap_len)
     int halo, B;           // halo = N-1 rounded up to 32; B = 1024 - halo valid outputs per block
     int prefetch;          // L2 prefetch of the warp's next item

@@ -289,13 +289,13 @@ int fir_effective_algo(const FirBank *b)
     return algo;
 }
 
-// lazily build and upload the spectrum of the taps (1/1024 folded in) and the 32 x 32 twiddles
+// lazily build and upload the spectrum of the taps (1/1024 folded in) and the 16 x 32 folded twiddles
 int fir_fft_tables(FirBank *b)
 {
     if (b->d_fft_H) return 0;
-    std::vector<double> H(2 * kFftN), tw(2 * kFftR * kFftR);
+    std::vector<double> H(2 * kFftN), tw(2 * kTwistEntries * kFftR);
     fft1024_make_spectrum(b->h_host, b->flt_len, H.data());
-    fft1024_make_twiddles(tw.data());
+    fft1024_make_twist_table(tw.data());
     const size_t es = fir_elem_size(b->dtype);
     void *dH = nullptr, *dT = nullptr;
     LLZ_CUDA_TRY(cudaMalloc(&dH, H.size() * es));

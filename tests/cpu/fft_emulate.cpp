@@ -1,5 +1,5 @@
 // Host emulation of the warp-level overlap-save algorithm of llzlab_b200/csrc/llz_cuda_fir_fft.cu: the same
-// dft32 / twiddle / spectrum code (llz_fft32.cuh compiles for the host), lanes run one after another and the
+// dft32 / dft32_twisted / spectrum code (llz_fft32.cuh compiles for the host), lanes run one after another and the
 // shared-memory transposes become array transposes.  Checks one work item (two blocks) against the direct sum.
 // Usage: fft_emulate <ntaps> <f32:0|1>   -> prints max |err| relative to full scale, exit 0 if within bound.
 #include <stdio.h>
@@ -20,30 +20,28 @@ static double run(int ntaps)
     double hsum = 0;
     for (auto &v : h) { v = rnd() / ntaps * 4; hsum += fabs(v); }
     for (auto &v : x) v = rnd();
-    std::vector<double> Hd(2 * kFftN), twd(2 * kFftR * kFftR);
+    std::vector<double> Hd(2 * kFftN), twd(2 * kTwistEntries * kFftR);
     fft1024_make_spectrum(h.data(), ntaps, Hd.data());
-    fft1024_make_twiddles(twd.data());
+    fft1024_make_twist_table(twd.data());
     std::vector<T> H(Hd.begin(), Hd.end()), tw(twd.begin(), twd.end());
+    struct C2 { T x, y; };
+    const C2 *tab = reinterpret_cast<const C2 *>(tw.data());
 
     static T re[32][32], im[32][32], tr[32][32], ti[32][32];
     // gather: lane t holds z[t + 32 j];  block A starts at input index 0, block B at B
     for (int t = 0; t < 32; ++t)
         for (int j = 0; j < 32; ++j) { re[t][j] = (T)x[t + 32 * j]; im[t][j] = (T)x[B + t + 32 * j]; }
-    for (int t = 0; t < 32; ++t) {
-        dft32<T, false>(re[t], im[t]);
-        for (int k = 1; k < 32; ++k) cmul_inplace<T, false>(re[t][k], im[t][k], tw[2 * (k * 32 + t)], tw[2 * (k * 32 + t) + 1]);
-    }
+    for (int t = 0; t < 32; ++t) dft32<T, false>(re[t], im[t]);
     for (int a = 0; a < 32; ++a) for (int b = 0; b < 32; ++b) { tr[a][b] = re[b][a]; ti[a][b] = im[b][a]; }
     for (int k2 = 0; k2 < 32; ++k2) {
-        dft32<T, false>(tr[k2], ti[k2]);
+        dft32_twisted<T, false>(tr[k2], ti[k2], tab + k2, 32);
         for (int k = 0; k < 32; ++k) cmul_inplace<T, false>(tr[k2][k], ti[k2][k], H[2 * (k * 32 + k2)], H[2 * (k * 32 + k2) + 1]);
         dft32<T, true>(tr[k2], ti[k2]);
-        for (int k = 1; k < 32; ++k) cmul_inplace<T, true>(tr[k2][k], ti[k2][k], tw[2 * (k * 32 + k2)], tw[2 * (k * 32 + k2) + 1]);
     }
     for (int a = 0; a < 32; ++a) for (int b = 0; b < 32; ++b) { re[a][b] = tr[b][a]; im[a][b] = ti[b][a]; }
     double worst = 0;
     for (int t = 0; t < 32; ++t) {
-        dft32<T, true>(re[t], im[t]);
+        dft32_twisted<T, true>(re[t], im[t], tab + t, 32);
         for (int j = 0; j < 32; ++j) {
             const int m = t + 32 * j;
             if (m < hl) continue;
