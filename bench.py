@@ -261,10 +261,18 @@ def run_cuda(args):
         fma_peak_nominal = FP32_NOMINAL_TFLOPS if f32 else FP64_NOMINAL_TFLOPS
         fma_dtype = z.F32 if f32 else z.F64
         fir_fft = bank.algo == z.FIR_FFT
-        if fir_fft:
+        if fir_fft and wl["taps"] >= 641:
+            # 8192-point overlap-save kernel (llz_cuda_fir_fft8k.cu): one CTA of 256 threads turns 2*B outputs out of
+            # 2580 FMA-pipe instructions per thread
+            halo_pad = (wl["taps"] - 1 + 255) // 256 * 256
+            fft_instr_per_out = 2580.0 * 256 / (2 * (8192 - halo_pad))
+            fft_desc = "8192-point FFT per CTA"
+            kernel = f"fir_fft8k_kernel<{'float' if f32 else 'double'}>"
+        elif fir_fft:
             # overlap-save kernel (llz_cuda_fir_fft.cu): one warp turns 2*B outputs out of 1928 FMA-pipe instructions per lane
             halo_pad = (wl["taps"] - 1 + 31) // 32 * 32
             fft_instr_per_out = 1928.0 * 32 / (2 * (1024 - halo_pad))
+            fft_desc = "1024-point FFT per warp"
             kernel = f"fir_fft_kernel<{'float' if f32 else 'double'}>"
         else:
             kernel = f"fir_tile_kernel<{'float' if f32 else 'double'}>"
@@ -428,7 +436,7 @@ def run_cuda(args):
                     "frac_of_measured": ginstr / (fma_peak_measured / 2) if fma_peak_measured else None,
                     "frac_of_nominal": ginstr / (fma_peak_nominal / 2),
                     "direct_form_equivalent_tflops": ach_tf,
-                    "note": "overlap-save (1024-point FFT per warp, arithmetic in the bank's type): "
+                    "note": f"overlap-save ({fft_desc}, arithmetic in the bank's type): "
                             f"{fft_instr_per_out:.1f} FMA-pipe instructions per output instead of {wl['taps']} FMAs; "
                             "the FMA pipe and the shared-memory/LSU pipe are co-limiters below the HBM roof (DESIGN.md 4.1b)"}
     else:
@@ -450,7 +458,7 @@ def run_cuda(args):
                    else "independent channels per rank, no collective",
                    "l2": f"inputs {dx.numel() * dx.element_size() / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
                    "input": "integer LCG noise generated on the device (SURVEY.md 8d)",
-                   **({"fir_algo": "overlap-save, 1024-point FFT" if fir_fft else "direct form"} if wl["kind"] == "fir" else {})},
+                   **({"fir_algo": f"overlap-save, {fft_desc}" if fir_fft else "direct form"} if wl["kind"] == "fir" else {})},
         "roofline": {"kernel": kernel, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic": {"bytes_per_output": bytes_per_out, "flop_per_output": flop_per_out,

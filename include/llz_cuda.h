@@ -52,11 +52,13 @@ enum {                                      /* FIR sample type + arithmetic */
     LLZ_CUDA_F32        = 2,  /* float I/O, FP32 FMA with 120-tap blocked partial sums (>=120 dB)  */
 };
 enum {                                      /* FIR kernel family (tolerance-mode banks only; STRICT is always direct) */
-    LLZ_CUDA_FIR_ALGO_AUTO   = 0, /* overlap-save for 48..897 taps, direct form otherwise (default)          */
+    LLZ_CUDA_FIR_ALGO_AUTO   = 0, /* overlap-save for 48..6145 taps, direct form otherwise (default)         */
     LLZ_CUDA_FIR_ALGO_DIRECT = 1, /* register-blocked sliding MAC: 2*N flop per output                       */
-    LLZ_CUDA_FIR_ALGO_FFT    = 2, /* overlap-save, 1024-point transform in the bank's own type: ~35 FMA-pipe
-                                     instructions per output at 127 taps; |err| ~1e-15 (f64) / ~3e-7 (f32)
-                                     of full scale against the direct sum, not bit-identical               */
+    LLZ_CUDA_FIR_ALGO_FFT    = 2, /* overlap-save in the bank's own type: a 1024-point transform per warp up
+                                     to 640 taps (~35 FMA-pipe instructions per output at 127 taps), an
+                                     8192-point transform per CTA up to 6145 taps (~81 at 4095 taps);
+                                     |err| ~1e-15 (f64) / ~3e-7 (f32) of full scale against the direct sum,
+                                     not bit-identical                                                      */
 };
 enum {                                      /* resampler accumulator */
     LLZ_CUDA_ACC_F64        = 0,  /* FP64 FMA + near-integer guard -> bit-identical int16 (default) */
@@ -74,7 +76,7 @@ unsigned long llz_cuda_fir_bank_init_taps(const double *h, int flt_len, int n_ch
 void          llz_cuda_fir_bank_uninit(unsigned long handle);
 
 int llz_cuda_fir_bank_flt_len(unsigned long handle);
-/* choose the kernel family; fails (-1) for FFT on a STRICT bank or beyond 897 taps */
+/* choose the kernel family; fails (-1) for FFT on a STRICT bank or beyond 6145 taps */
 int llz_cuda_fir_bank_set_algo(unsigned long handle, int algo);
 /* the family the next _run will use: LLZ_CUDA_FIR_ALGO_DIRECT or LLZ_CUDA_FIR_ALGO_FFT */
 int llz_cuda_fir_bank_get_algo(unsigned long handle);

@@ -224,6 +224,61 @@ LLZ_HD void cmul_inplace(T &r, T &s, T c, T d)
     r = nr; s = ns;
 }
 
+// ---- 8-point transforms (the outer radix of the 8192-point transform, llz_cuda_fir_fft8k.cu) -------------
+LLZ_HD constexpr int brev3(int i) { return ((i & 1) << 2) | (i & 2) | ((i & 4) >> 2); }
+
+// X[k] = sum_a x[a] * exp(-+ 2*pi*i*a*k/8) on the strided slice v[O + a], a < 8; natural order in and out
+template <typename T, bool INV, int O>
+LLZ_HD void dft8(T (&re)[32], T (&im)[32])
+{
+    T ar[8], ai[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ar[i] = re[O + brev3(i)]; ai[i] = im[O + brev3(i)]; }
+#pragma unroll
+    for (int b = 0; b < 8; b += 2) bfly32<T, INV>(ar[b], ai[b], ar[b + 1], ai[b + 1], 0);
+#pragma unroll
+    for (int b = 0; b < 8; b += 4) {
+        bfly32<T, INV>(ar[b], ai[b], ar[b + 2], ai[b + 2], 0);
+        bfly32<T, INV>(ar[b + 1], ai[b + 1], ar[b + 3], ai[b + 3], 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bfly32<T, INV>(ar[k], ai[k], ar[k + 4], ai[k + 4], 4 * k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { re[O + i] = ar[i]; im[O + i] = ai[i]; }
+}
+
+// X[k] = sum_a (x[a] * w^a) * exp(-+ 2*pi*i*a*k/8) with the twiddle folded in as in dft32_twisted:
+// e0 = (cos, sin) of the len-2 twiddle w^4, e1 = (cos, tan) of w^2, e2 / e3 = (cos, tan) of w and w*W_8
+template <typename T, bool INV, int O, typename C>
+LLZ_HD void dft8_twisted(T (&re)[32], T (&im)[32], C e0, C e1, C e2, C e3)
+{
+    T ar[8], ai[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ar[i] = re[O + brev3(i)]; ai[i] = im[O + brev3(i)]; }
+    {
+        const T c = e0.x, s = INV ? -e0.y : e0.y;
+#pragma unroll
+        for (int b = 0; b < 8; b += 2) {
+            const T ur = ar[b], ui = ai[b], vr = ar[b + 1], vi = ai[b + 1];
+            ar[b]     = fma_t<T>(s, vi, fma_t<T>(c, vr, ur));
+            ai[b]     = fma_t<T>(-s, vr, fma_t<T>(c, vi, ui));
+            ar[b + 1] = fma_t<T>(-s, vi, fma_t<T>(-c, vr, ur));
+            ai[b + 1] = fma_t<T>(s, vr, fma_t<T>(-c, vi, ui));
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; b += 4) {
+        bfly_tan<T, INV, false>(ar[b], ai[b], ar[b + 2], ai[b + 2], e1.x, e1.y);
+        bfly_tan<T, INV, true>(ar[b + 1], ai[b + 1], ar[b + 3], ai[b + 3], e1.x, e1.y);
+    }
+    bfly_tan<T, INV, false>(ar[0], ai[0], ar[4], ai[4], e2.x, e2.y);
+    bfly_tan<T, INV, false>(ar[1], ai[1], ar[5], ai[5], e3.x, e3.y);
+    bfly_tan<T, INV, true>(ar[2], ai[2], ar[6], ai[6], e2.x, e2.y);
+    bfly_tan<T, INV, true>(ar[3], ai[3], ar[7], ai[7], e3.x, e3.y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { re[O + i] = ar[i]; im[O + i] = ai[i]; }
+}
+
 // ---- host-side tables ---------------------------------------------------------------------------
 // tab[e][l], e < 16, l < 32: the folded twiddles of dft32_twisted for lane l, interleaved pairs (see above)
 inline void fft1024_make_twist_table(double *tab /* 16*32*2 */)
@@ -259,6 +314,66 @@ inline void fft1024_make_spectrum(const double *h, int ntaps, double *H /* 1024*
         H[2 * (k1 * kFftR + k2)] = (double)(sr / kFftN);
         H[2 * (k1 * kFftR + k2) + 1] = (double)(si / kFftN);
     }
+}
+
+// ---- tables of the 8192-point transform (8 x 1024, llz_cuda_fir_fft8k.cu) -----------------------------------
+constexpr int kFft8kN = 8192;
+
+// tab2[b][e][k2]: folded twiddles of the second DFT-32 of warp b (base exp(-2*pi*i*(8*k2 + b)/8192))
+inline void fft8k_make_twist2(double *tab /* 8*16*32*2 */)
+{
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int b = 0; b < 8; ++b) {
+        int e = 0;
+        for (int len = 2; len <= 32; len <<= 1) {
+            const int nk = len == 2 ? 1 : len / 4;
+            for (int k = 0; k < nk; ++k, ++e)
+                for (int l = 0; l < kFftR; ++l) {
+                    const long double th = two_pi * (long double)(8 * l + b + 256 * k) / (long double)(256 * len);
+                    double *o = tab + 2 * ((b * kTwistEntries + e) * kFftR + l);
+                    o[0] = (double)cosl(th);
+                    o[1] = (double)(len == 2 ? sinl(th) : tanl(th));
+                }
+        }
+    }
+}
+
+// tab3[q][e][tid], q < 4, e < 4, tid < 256: folded twiddles of the last 8-point transform for n_lo = tid + 256 q
+// (base exp(-2*pi*i*n_lo/8192)); e as in dft8_twisted
+inline void fft8k_make_twist3(double *tab /* 4*4*256*2 */)
+{
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int q = 0; q < 4; ++q)
+        for (int tid = 0; tid < 256; ++tid) {
+            const long double base = (long double)(tid + 256 * q) / (long double)kFft8kN;     // turns
+            const long double th[4] = {two_pi * base * 4, two_pi * base * 2, two_pi * base, two_pi * (base + 0.125L)};
+            for (int e = 0; e < 4; ++e) {
+                double *o = tab + 2 * ((q * 4 + e) * 256 + tid);
+                o[0] = (double)cosl(th[e]);
+                o[1] = (double)(e == 0 ? sinl(th[e]) : tanl(th[e]));
+            }
+        }
+}
+
+// H[b][k1][k2] = (1/8192) * sum_n h[n] * exp(-2*pi*i*n*k/8192),  k = b + 8*(k2 + 32*k1)
+inline void fft8k_make_spectrum(const double *h, int ntaps, double *H /* 8192*2 */)
+{
+    long double *ct = new long double[kFft8kN], *st = new long double[kFft8kN];
+    const long double w = -2.0L * 3.14159265358979323846264338327950288L / (long double)kFft8kN;
+    for (int i = 0; i < kFft8kN; ++i) { ct[i] = cosl(w * i); st[i] = sinl(w * i); }
+    for (int k = 0; k < kFft8kN; ++k) {
+        long double sr = 0.0L, si = 0.0L;
+        for (int n = 0; n < ntaps; ++n) {
+            const int idx = (int)(((long long)n * k) % kFft8kN);
+            sr += (long double)h[n] * ct[idx];
+            si += (long double)h[n] * st[idx];
+        }
+        const int b = k % 8, khi = k / 8, k2 = khi % kFftR, k1 = khi / kFftR;
+        H[2 * ((b * kFftR + k1) * kFftR + k2)] = (double)(sr / kFft8kN);
+        H[2 * ((b * kFftR + k1) * kFftR + k2) + 1] = (double)(si / kFft8kN);
+    }
+    delete[] ct;
+    delete[] st;
 }
 
 }  // namespace llz

@@ -34,6 +34,8 @@ int fir_update_history(const T *x, long long x_stride, long long n, const T *his
 // ---- overlap-save (1024-point FFT) FIR, llz_cuda_fir_fft.cu -----------------------------------------
 constexpr int kFirFftMinTapsAuto = 48;   // below this the direct kernel is at least as fast
 constexpr int kFirFftMaxTaps = 897;      // leaves B = 1024 - halo >= 128 valid outputs per block
+constexpr int kFirFft8kMinTapsAuto = 641;  // from here on the 8192-point kernel (llz_cuda_fir_fft8k.cu) wins
+constexpr int kFirFft8kMaxTaps = 6145;   // leaves B = 8192 - halo >= 2048
 
 template <typename T>
 struct FirFftLaunch {
@@ -46,6 +48,7 @@ struct FirFftLaunch {
     int ntaps;
     const T *H;            // device [32][32] complex: spectrum of the taps / 1024, H[k1][k2] = bin k2 + 32*k1
     const T *tw;           // device [16][32] pairs: folded twiddles of dft32_twisted (llz_fft32.cuh)
+    const T *tw2, *tw3;    // 8192-point kernel only: [8][16][32] and [4][4][256] pairs (llz_fft32.cuh)
     // filled in by fir_fft_launch: item i of a channel is pair first_pair + i, skipping [gap_start, gap_start + gap_len)
     int halo, B;           // halo = N-1 rounded up to 32; B = 1024 - halo valid outputs per block
     int prefetch;          // L2 prefetch of the warp's next item
@@ -55,5 +58,9 @@ struct FirFftLaunch {
 
 template <typename T>
 int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
+
+// 8192-point variant for long filters; a.H is the 8192-bin spectrum in the kernel's [8][32][32] layout
+template <typename T>
+int fir_fft8k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
 
 }  // namespace llz

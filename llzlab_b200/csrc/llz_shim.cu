@@ -162,6 +162,8 @@ struct FirBank {
     // overlap-save kernel (llz_cuda_fir_fft.cu): spectrum of the taps and inter-pass twiddles, bank's type
     int algo = LLZ_CUDA_FIR_ALGO_AUTO;
     void *d_fft_H = nullptr, *d_fft_tw = nullptr;
+    void *d_fft_tw2 = nullptr, *d_fft_tw3 = nullptr;     // 8192-point kernel (llz_cuda_fir_fft8k.cu)
+    bool fft8k = false;
     Pipeline pipe;
     // drop-in (mono, host buffers)
     int frame_len = 0;
@@ -186,6 +188,8 @@ void fir_destroy(FirBank *b)
     if (b->d_taps) cudaFree(b->d_taps);
     if (b->d_fft_H) cudaFree(b->d_fft_H);
     if (b->d_fft_tw) cudaFree(b->d_fft_tw);
+    if (b->d_fft_tw2) cudaFree(b->d_fft_tw2);
+    if (b->d_fft_tw3) cudaFree(b->d_fft_tw3);
     if (b->d_hist[0]) cudaFree(b->d_hist[0]);
     if (b->d_hist[1]) cudaFree(b->d_hist[1]);
     if (b->pinned) cudaFreeHost(b->pinned);
@@ -271,56 +275,73 @@ unsigned long fir_bank_create(double *h, int flt_len, int n_channels, int dtype)
 // the environment variable LLZ_FIR_ALGO=direct|fft overrides AUTO (tuning / A-B measurements).
 int fir_effective_algo(const FirBank *b)
 {
+    const bool fft_ok = b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len <= kFirFft8kMaxTaps;
     int algo = b->algo;
     if (algo == LLZ_CUDA_FIR_ALGO_AUTO) {
         const char *env = getenv("LLZ_FIR_ALGO");
         if (env && strcmp(env, "direct") == 0) algo = LLZ_CUDA_FIR_ALGO_DIRECT;
-        else if (env && strcmp(env, "fft") == 0 && b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len <= kFirFftMaxTaps)
-            algo = LLZ_CUDA_FIR_ALGO_FFT;
+        else if (env && strcmp(env, "fft") == 0 && fft_ok) algo = LLZ_CUDA_FIR_ALGO_FFT;
     }
     if (algo == LLZ_CUDA_FIR_ALGO_AUTO)
-        algo = (b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len >= kFirFftMinTapsAuto && b->flt_len <= kFirFftMaxTaps)
-                   ? LLZ_CUDA_FIR_ALGO_FFT : LLZ_CUDA_FIR_ALGO_DIRECT;
-    if (algo == LLZ_CUDA_FIR_ALGO_FFT && (b->dtype == LLZ_CUDA_F64_STRICT || b->flt_len > kFirFftMaxTaps)) {
-        llz_set_error("the overlap-save FIR kernel is not available for this bank (strict arithmetic or > %d taps)",
-                      kFirFftMaxTaps);
+        algo = (fft_ok && b->flt_len >= kFirFftMinTapsAuto) ? LLZ_CUDA_FIR_ALGO_FFT : LLZ_CUDA_FIR_ALGO_DIRECT;
+    if (algo == LLZ_CUDA_FIR_ALGO_FFT && !fft_ok) {
+        llz_set_error("the overlap-save FIR kernels are not available for this bank (strict arithmetic or > %d taps)",
+                      kFirFft8kMaxTaps);
         return -1;
     }
     return algo;
 }
 
-// lazily build and upload the spectrum of the taps (1/1024 folded in) and the 16 x 32 folded twiddles
+// transform length the overlap-save path uses for this bank: 1024 (one warp per item) or 8192 (one CTA per item)
+bool fir_use_fft8k(const FirBank *b)
+{
+    const char *env = getenv("LLZ_FIR_FFT_SIZE");
+    if (env && atoi(env) == 8192) return true;
+    if (env && atoi(env) == 1024 && b->flt_len <= kFirFftMaxTaps) return false;
+    return b->flt_len >= kFirFft8kMinTapsAuto;
+}
+
+int upload_as(void **dst, const std::vector<double> &src, bool f32)
+{
+    void *d = nullptr;
+    const size_t es = f32 ? sizeof(float) : sizeof(double);
+    LLZ_CUDA_TRY(cudaMalloc(&d, src.size() * es));
+    cudaError_t e;
+    if (f32) {
+        std::vector<float> f(src.begin(), src.end());
+        e = cudaMemcpy(d, f.data(), f.size() * es, cudaMemcpyHostToDevice);
+    } else {
+        e = cudaMemcpy(d, src.data(), src.size() * es, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        llz_set_error("upload of an FFT table failed: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    *dst = d;
+    return 0;
+}
+
+// lazily build and upload the spectrum of the taps (1/N folded in) and the folded twiddle tables
 int fir_fft_tables(FirBank *b)
 {
     if (b->d_fft_H) return 0;
-    std::vector<double> H(2 * kFftN), tw(2 * kTwistEntries * kFftR);
-    fft1024_make_spectrum(b->h_host, b->flt_len, H.data());
+    const bool f32 = b->dtype == LLZ_CUDA_F32;
+    b->fft8k = fir_use_fft8k(b);
+    std::vector<double> tw(2 * kTwistEntries * kFftR);
     fft1024_make_twist_table(tw.data());
-    const size_t es = fir_elem_size(b->dtype);
-    void *dH = nullptr, *dT = nullptr;
-    LLZ_CUDA_TRY(cudaMalloc(&dH, H.size() * es));
-    if (cudaMalloc(&dT, tw.size() * es) != cudaSuccess) {
-        cudaFree(dH);
-        llz_set_error("cudaMalloc(FFT twiddles) failed");
-        return -1;
-    }
-    cudaError_t e1, e2;
-    if (b->dtype == LLZ_CUDA_F32) {
-        std::vector<float> Hf(H.begin(), H.end()), tf(tw.begin(), tw.end());
-        e1 = cudaMemcpy(dH, Hf.data(), Hf.size() * es, cudaMemcpyHostToDevice);
-        e2 = cudaMemcpy(dT, tf.data(), tf.size() * es, cudaMemcpyHostToDevice);
+    if (upload_as(&b->d_fft_tw, tw, f32) != 0) return -1;
+    std::vector<double> H(2 * (b->fft8k ? kFft8kN : kFftN));
+    if (b->fft8k) {
+        std::vector<double> t2(2 * 8 * kTwistEntries * kFftR), t3(2 * 16 * 256);
+        fft8k_make_twist2(t2.data());
+        fft8k_make_twist3(t3.data());
+        if (upload_as(&b->d_fft_tw2, t2, f32) != 0 || upload_as(&b->d_fft_tw3, t3, f32) != 0) return -1;
+        fft8k_make_spectrum(b->h_host, b->flt_len, H.data());
     } else {
-        e1 = cudaMemcpy(dH, H.data(), H.size() * es, cudaMemcpyHostToDevice);
-        e2 = cudaMemcpy(dT, tw.data(), tw.size() * es, cudaMemcpyHostToDevice);
+        fft1024_make_spectrum(b->h_host, b->flt_len, H.data());
     }
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        cudaFree(dH); cudaFree(dT);
-        llz_set_error("upload of the FFT tables failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-        return -1;
-    }
-    b->d_fft_H = dH;
-    b->d_fft_tw = dT;
-    return 0;
+    return upload_as(&b->d_fft_H, H, f32);
 }
 
 template <typename T>
@@ -347,7 +368,9 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
         f.hist = a.hist; f.ntaps = b->flt_len;
         f.H = static_cast<const T *>(b->d_fft_H);
         f.tw = static_cast<const T *>(b->d_fft_tw);
-        if (fir_fft_launch<T>(f, b->n_channels, st) != 0) return -1;
+        f.tw2 = static_cast<const T *>(b->d_fft_tw2);
+        f.tw3 = static_cast<const T *>(b->d_fft_tw3);
+        if ((b->fft8k ? fir_fft8k_launch<T>(f, b->n_channels, st) : fir_fft_launch<T>(f, b->n_channels, st)) != 0) return -1;
     } else if (fir_launch<T>(a, b->n_channels, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) {
         return -1;
     }

@@ -68,7 +68,7 @@ def test_bank_f64_all_tap_counts(zlib, port, cuda, N):
     want = oracle_bank(port, h, x)
     dx = torch.from_numpy(x).cuda()
     cases = [(zlib.F64_STRICT, zlib.FIR_AUTO, True), (zlib.F64, zlib.FIR_DIRECT, False)]
-    if N <= 897:
+    if N <= 6145:
         cases.append((zlib.F64, zlib.FIR_FFT, False))
     for dtype, algo, exact in cases:
         bank = zlib.FirBank(C_, dtype, taps=h, algo=algo)
@@ -86,7 +86,8 @@ def test_bank_f64_all_tap_counts(zlib, port, cuda, N):
 
 
 @pytest.mark.parametrize("N,fc,win,algo", [(127, 0.23, 0, 1), (4095, 0.11, 2, 1), (48, 0.4, 1, 1),
-                                          (127, 0.23, 0, 2), (48, 0.4, 1, 2), (513, 0.11, 2, 2), (897, 0.05, 1, 2)])
+                                          (127, 0.23, 0, 2), (48, 0.4, 1, 2), (513, 0.11, 2, 2), (897, 0.05, 1, 2),
+                                          (4095, 0.11, 2, 2), (6145, 0.02, 1, 2)])
 def test_bank_f32_meets_snr(zlib, port, cuda, N, fc, win, algo):
     torch = cuda
     h = port.fir_design(0, N, fc, 0.0, win)
@@ -180,47 +181,79 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
     fbank.close()
 
 
-@pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_fft_bank_streaming_ragged_chunks(zlib, port, cuda, dtype):
-    """overlap-save kernel: chunk sizes below / around the history and the block size, odd strides, flush, restart"""
+@pytest.mark.parametrize("N", [898, 2049, 4095, 6145])
+def test_fft8k_bank_interior_and_edge_items(zlib, port, cuda, N):
+    """8192-point overlap-save kernel (one CTA per item): several interior items, history splice, ragged end"""
     torch = cuda
-    h = port.fir_design(2, 129, 0.2, 0.6, 2)
+    rng = np.random.default_rng(N)
+    h = rng.standard_normal(N) / N ** 0.5
+    C_, n = 3, 70001
+    x = rng.uniform(-1, 1, (C_, n))
+    want = oracle_bank(port, h, x)
+    scale = max(np.abs(h).sum(), 1.0)
+    for dtype, tdt, npdt, tol in ((zlib.F64, torch.float64, np.float64, TOL_F64 * scale),
+                                  (zlib.F32, torch.float32, np.float32, TOL_F32_ABS * scale)):
+        dx = torch.from_numpy(x.astype(npdt)).cuda()
+        bank = zlib.FirBank(C_, dtype, taps=h, algo=zlib.FIR_FFT)
+        dy = torch.full((C_, n + 64), 7.0, dtype=tdt, device="cuda")
+        bank.run(dx, n, dy, n + 64, n)
+        # second call continues the stream from the stored history: same samples again -> history splice
+        dy2 = torch.empty(C_, 20000, dtype=tdt, device="cuda")
+        bank.run(dx, n, dy2, 20000, 20000)
+        torch.cuda.synchronize()
+        got = dy.cpu().numpy()
+        assert np.abs(got[:, :n] - want).max() <= tol, (N, dtype)
+        assert (got[:, n:] == 7.0).all()
+        if dtype == zlib.F32:
+            assert snr_db(want, got[:, :n]) >= SNR_F32_DB
+        want2 = oracle_bank(port, h, np.concatenate([x, x[:, :20000]], axis=1))[:, n:]
+        assert np.abs(dy2.cpu().numpy() - want2).max() <= tol, (N, dtype)
+        bank.close()
+
+
+@pytest.mark.parametrize("dtype,N", [("f64", 129), ("f32", 129), ("f64", 2049)])
+def test_fft_bank_streaming_ragged_chunks(zlib, port, cuda, dtype, N):
+    """overlap-save kernels: chunk sizes below / around the history and the block size, odd strides, flush, restart"""
+    torch = cuda
+    h = port.fir_design(2, N, 0.2, 0.6, 2)
     C_, n = 5, 40001
     x = np.stack([port.lcg_f64(n, 100 + c) for c in range(C_)])
-    want = oracle_bank(port, h, x, n_out=n + 128)
+    want = oracle_bank(port, h, x, n_out=n + N - 1)
     tdt, npdt, es = (torch.float64, np.float64, 8) if dtype == "f64" else (torch.float32, np.float32, 4)
     tol = TOL_F64 if dtype == "f64" else TOL_F32_ABS
     stride = n + 3
     dx = torch.zeros(C_, stride, dtype=tdt, device="cuda")
     dx[:, :n] = torch.from_numpy(x.astype(npdt)).cuda()
-    dy = torch.full((C_, stride + 200), 7.0, dtype=tdt, device="cuda")
+    ostride = stride + 200 + N
+    dy = torch.full((C_, ostride), 7.0, dtype=tdt, device="cuda")
     bank = zlib.FirBank(C_, zlib.F64 if dtype == "f64" else zlib.F32, taps=h, algo=zlib.FIR_FFT)
     pos = 0
     for step in (1, 7, 100, 128, 129, 895, 896, 1792, 1793, 5000, 3, 20000, 10 ** 9):
         m = min(step, n - pos)
         if m <= 0:
             break
-        bank.run(dx.data_ptr() + es * pos, stride, dy.data_ptr() + es * pos, stride + 200, m)
+        bank.run(dx.data_ptr() + es * pos, stride, dy.data_ptr() + es * pos, ostride, m)
         pos += m
     assert pos == n
-    assert bank.flush(dy.data_ptr() + es * n, stride + 200) == 128
+    assert bank.flush(dy.data_ptr() + es * n, ostride) == N - 1
     torch.cuda.synchronize()
     got = dy.cpu().numpy()
-    assert np.abs(got[:, :n + 128] - want).max() <= tol
-    assert (got[:, n + 128:] == 7.0).all()                   # nothing written past the end
+    assert np.abs(got[:, :n + N - 1] - want).max() <= tol
+    assert (got[:, n + N - 1:] == 7.0).all()                 # nothing written past the end
     if dtype == "f32":
-        assert snr_db(want, got[:, :n + 128]) >= SNR_F32_DB
-    bank.run(dx, stride, dy, stride + 200, 1000)
+        assert snr_db(want, got[:, :n + N - 1]) >= SNR_F32_DB
+    bank.run(dx, stride, dy, ostride, 1000)
     torch.cuda.synchronize()
     assert np.abs(dy.cpu().numpy()[:, :1000] - want[:, :1000]).max() <= tol
     bank.close()
 
 
 def test_fft_algo_selection(zlib, cuda):
-    """AUTO picks overlap-save for tolerance-mode banks of 48..897 taps; STRICT and long filters stay direct"""
+    """AUTO picks overlap-save for tolerance-mode banks of 48..6145 taps; STRICT and longer filters stay direct"""
     h = np.ones(127) / 127
     for dtype, N, want in ((zlib.F64, 127, zlib.FIR_FFT), (zlib.F32, 127, zlib.FIR_FFT), (zlib.F64, 47, zlib.FIR_DIRECT),
-                           (zlib.F64, 898, zlib.FIR_DIRECT), (zlib.F64_STRICT, 127, zlib.FIR_DIRECT)):
+                           (zlib.F64, 898, zlib.FIR_FFT), (zlib.F64, 4095, zlib.FIR_FFT), (zlib.F64, 6146, zlib.FIR_DIRECT),
+                           (zlib.F64_STRICT, 127, zlib.FIR_DIRECT)):
         b = zlib.FirBank(2, dtype, taps=np.ones(N) / N)
         assert b.algo == want, (dtype, N)
         b.close()
@@ -229,7 +262,7 @@ def test_fft_algo_selection(zlib, cuda):
     assert zlib.lib().llz_cuda_fir_bank_set_algo(b.handle, 9) == -1
     assert b.algo == zlib.FIR_DIRECT
     b.close()
-    b = zlib.FirBank(2, zlib.F64, taps=np.ones(898) / 898)
+    b = zlib.FirBank(2, zlib.F64, taps=np.ones(6146) / 6146)
     assert zlib.lib().llz_cuda_fir_bank_set_algo(b.handle, zlib.FIR_FFT) == -1
     b.close()
 
