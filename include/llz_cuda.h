@@ -47,9 +47,11 @@ enum {                                      /* FIR design kind (llz_fir.c:201-26
     LLZ_CUDA_LPF = 0, LLZ_CUDA_HPF = 1, LLZ_CUDA_BPF = 2, LLZ_CUDA_BSF = 3,
 };
 enum {                                      /* FIR sample type + arithmetic */
-    LLZ_CUDA_F64        = 0,  /* double I/O, FP64 FMA (drop-in type; |err| <= 1e-12 rel. full scale) */
+    LLZ_CUDA_F64        = 0,  /* double I/O, FP64 arithmetic, any order (|err| <= 1e-12 rel. full scale);
+                                 kernel family per LLZ_CUDA_FIR_ALGO_* below                        */
     LLZ_CUDA_F64_STRICT = 1,  /* double I/O, separate mul+add in llz_conv's order: bit-identical   */
-    LLZ_CUDA_F32        = 2,  /* float I/O, FP32 FMA with 120-tap blocked partial sums (>=120 dB)  */
+    LLZ_CUDA_F32        = 2,  /* float I/O, FP32 arithmetic (>= 120 dB SNR); the direct kernel folds
+                                 partial sums every 128 taps                                        */
 };
 enum {                                      /* FIR kernel family (tolerance-mode banks only; STRICT is always direct) */
     LLZ_CUDA_FIR_ALGO_AUTO   = 0, /* overlap-save for 48..6145 taps, direct form otherwise (default)         */
