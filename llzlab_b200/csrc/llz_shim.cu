@@ -58,6 +58,7 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 // i % kSlots.  Events order slot reuse; the compute stream sees the chunks in time order, so the
 // bank's stream state (history, phase) advances exactly as in one long call.
 constexpr int kSlots = 3;
+constexpr double kPipeSlotMiB = 64.0;
 
 struct Pipeline {
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -134,10 +135,12 @@ int copy_planar(void *dst, size_t dpitch, const void *src, size_t spitch, size_t
     return 0;
 }
 
-// samples per channel per chunk so that one slot (in + out) stays near 64 MiB
+// samples per channel per chunk so that one slot (in + out) stays near the slot budget (LLZ_PIPE_SLOT_MB, tuning)
 long long pick_chunk(long long n, int n_channels, double bytes_per_in_sample)
 {
-    const double budget = 64.0 * 1024 * 1024;
+    const char *env = getenv("LLZ_PIPE_SLOT_MB");
+    const double mb = (env && atof(env) >= 1.0) ? atof(env) : kPipeSlotMiB;
+    const double budget = mb * 1024 * 1024;
     long long c = (long long)(budget / (bytes_per_in_sample * n_channels));
     c = (c / 4096) * 4096;
     if (c < 4096) c = 4096;

@@ -56,12 +56,25 @@ def test_c5_full_length_one_channel(zlib, port, cuda):
         want = port.fir_run(h, xw)[t0 - lo:]
         got = dy[t0:t0 + 200].cpu().numpy()
         assert np.abs(got - want).max() <= 1e-12, t0
-    # the same stream in two time segments with halo gives the same bytes (C5's multi-GPU plan)
+    # the same stream in two time segments with halo (C5's multi-GPU plan): the overlap-save kernel (AUTO picks the
+    # 8192-point one here) agrees to rounding -- its block grid starts at the segment -- and the direct kernel bit for bit
+    assert bank.algo == zlib.FIR_FFT
     seg = zlib.shard_fir_segments(n, N, 2, 1)
     bank.reset()
     bank.set_history(dx.data_ptr() + 8 * (seg.in_start - seg.halo), n)
     tail = torch.empty(1_000_000, dtype=torch.float64, device="cuda")
     bank.run(dx.data_ptr() + 8 * seg.in_start, n, tail, 1_000_000, 1_000_000)
     torch.cuda.synchronize()
-    assert torch.equal(tail, dy[seg.out_start:seg.out_start + 1_000_000])
+    assert (tail - dy[seg.out_start:seg.out_start + 1_000_000]).abs().max().item() <= 1e-12
     bank.close()
+    direct = zlib.FirBank(1, zlib.F64, kind=zlib.LPF, flt_len=N, fc1=0.11, win=zlib.KAISER, algo=zlib.FIR_DIRECT)
+    lead = 8192                                            # one-shot run over a window that starts before the segment
+    whole = torch.empty(lead + 1_000_000, dtype=torch.float64, device="cuda")
+    direct.run(dx.data_ptr() + 8 * (seg.in_start - lead), n, whole, whole.numel(), whole.numel())
+    direct.reset()
+    direct.set_history(dx.data_ptr() + 8 * (seg.in_start - seg.halo), n)
+    direct.run(dx.data_ptr() + 8 * seg.in_start, n, tail, 1_000_000, 1_000_000)
+    torch.cuda.synchronize()
+    assert torch.equal(tail, whole[lead:])
+    assert (tail - dy[seg.out_start:seg.out_start + 1_000_000]).abs().max().item() <= 1e-12
+    direct.close()
