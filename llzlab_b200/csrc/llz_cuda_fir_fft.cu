@@ -180,6 +180,7 @@ fir_fft_kernel(FirFftLaunch<T> a)
             for (int j = 0; j < 32; ++j) { re[j] = stage[lane + 32 * j]; im[j] = stage[B + lane + 32 * j]; }
             __syncwarp();                              // every lane has its samples: the buffer may be refilled
             if (lane == 0 && item + item_step < total) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before the async-proxy refill
                 mbar_expect_tx(bar, span_bytes);
                 tma_bulk_g2s(stage, item_src(item + item_step), span_bytes, bar);
             }

@@ -23,7 +23,10 @@
 //                 coalesced streaming stores of the rows at or beyond the halo.
 //   * the 128 KB exchange buffer is used as eight 16 KB warp slices for the warp-local exchanges (XOR-swizzled
 //     columns, conflict-free) and as [b][j][t] for the CTA-wide ones; three __syncthreads per item;
-//   * the next item's 96 KB of input is prefetched into L2 while the current one computes.
+//   * the buffer's idle phases carry the loads: the NEXT item's 96 KB input span arrives in it by TMA bulk copies
+//     (cp.async.bulk + mbarrier) while the current item runs its last DFT-8s and stores, and each warp's 16 KB
+//     slice of the spectrum arrives in the warp's own slice while the warp runs its second forward DFT-32; the
+//     item after next is prefetched into L2.
 //
 // Arithmetic stays in the bank's own type; error against the direct sum ~1e-16 of sum|h| (f64), ~1e-8 (f32);
 // results are not bit-identical to the reference -- LLZ_CUDA_F64_STRICT keeps the direct kernel.
@@ -45,11 +48,19 @@ constexpr int kFft8kThreads = 256;
 
 template <typename T>
 struct Fft8kSmem {
+    static constexpr size_t bars = 128;                       // [0] input staging, [1 + b] spectrum slice of warp b
     static constexpr size_t tabw = (size_t)kTwistEntries * kFftR * 2 * sizeof(T);
     static constexpr size_t tab2 = (size_t)8 * kTwistEntries * kFftR * 2 * sizeof(T);
     static constexpr size_t xbuf = (size_t)kFft8kN * 2 * sizeof(T);
-    static constexpr size_t total = tabw + tab2 + xbuf;
+    static constexpr size_t total = bars + tabw + tab2 + xbuf;
 };
+
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    // orders this thread's (and, after a barrier, the CTA's) generic-proxy shared-memory accesses before later
+    // async-proxy (TMA) accesses to the same locations
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 template <typename T>
 __device__ __forceinline__ T fir_fft8k_sample(const FirFftLaunch<T> &a, const T *xc, const T *hc, long long g)
@@ -59,18 +70,27 @@ __device__ __forceinline__ T fir_fft8k_sample(const FirFftLaunch<T> &a, const T 
     return T(0);
 }
 
-// EDGE = false: interior items only (unguarded loads and stores); EDGE = true: first / last items of a channel
-template <typename T, bool EDGE>
+// EDGE = false: interior items only (unguarded stores; the input span of the NEXT item and the warp's slice of the
+// spectrum arrive in the exchange buffer by TMA bulk copies while it is idle); EDGE = true: first / last items of a
+// channel (guarded global loads and stores).  STAGE needs 16-byte aligned channel rows.
+template <typename T, bool EDGE, bool STAGE>
 __global__ void __launch_bounds__(kFft8kThreads, sizeof(T) == 4 ? 2 : 1)
 fir_fft8k_kernel(FirFftLaunch<T> a)
 {
     using C = typename Cplx8k<T>::type;
     using SM = Fft8kSmem<T>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    C *tabw_s = reinterpret_cast<C *>(smem_raw);                                  // [16][32]
-    C *tab2_s = reinterpret_cast<C *>(smem_raw + SM::tabw);                       // [8][16][32]
-    C *xbuf = reinterpret_cast<C *>(smem_raw + SM::tabw + SM::tab2);              // 8192 complex
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    C *tabw_s = reinterpret_cast<C *>(smem_raw + SM::bars);                                  // [16][32]
+    C *tab2_s = reinterpret_cast<C *>(smem_raw + SM::bars + SM::tabw);                       // [8][16][32]
+    C *xbuf = reinterpret_cast<C *>(smem_raw + SM::bars + SM::tabw + SM::tab2);              // 8192 complex
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if constexpr (STAGE) {
+        if (tid == 0) {
+            mbar_init(&bars[0], 1);
+            for (int b = 0; b < 8; ++b) mbar_init(&bars[1 + b], 1);
+        }
+    }
 
     for (int i = tid; i < 8 * kTwistEntries * kFftR; i += kFft8kThreads) {
         if (i < kTwistEntries * kFftR) tabw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
@@ -84,6 +104,26 @@ fir_fft8k_kernel(FirFftLaunch<T> a)
     const int hl = a.halo, B = a.B;
     const long long total = a.items_per_channel * a.n_channels;
     const int span_bytes = (kFft8kN + B) * (int)sizeof(T);
+    [[maybe_unused]] uint32_t in_phase = 0, h_phase = 0;
+
+    // first input sample (block A) of an interior item
+    auto item_src = [&](long long it) -> const T * {
+        const int c = (int)(it / a.items_per_channel);
+        const long long p = a.first_pair + (it - (long long)c * a.items_per_channel);
+        return a.x + (long long)c * a.x_stride + p * (2LL * B) - hl;
+    };
+    // one thread: bring an item's contiguous input span into the (idle) exchange buffer, four bulk copies
+    auto stage_input = [&](long long it) {
+        const char *src = reinterpret_cast<const char *>(item_src(it));
+        char *dst = reinterpret_cast<char *>(xbuf);
+        mbar_expect_tx(&bars[0], (uint32_t)span_bytes);
+        const int piece = (span_bytes / 4 + 15) & ~15;
+        for (int off = 0; off < span_bytes; off += piece)
+            tma_bulk_g2s(dst + off, src + off, (uint32_t)min(piece, span_bytes - off), &bars[0]);
+    };
+    if constexpr (STAGE) {
+        if (tid == 0 && (long long)blockIdx.x < total) stage_input(blockIdx.x);
+    }
 
     for (long long item = blockIdx.x; item < total; item += gridDim.x) {
         const int ch = (int)(item / a.items_per_channel);
@@ -97,19 +137,30 @@ fir_fft8k_kernel(FirFftLaunch<T> a)
         T re[32], im[32];
         // ---- gather: register q*8 + a holds z[tid + 256 q + 1024 a] ----------------------------------------
         if constexpr (!EDGE) {
-            const T *p = xc + s + tid;
+            if constexpr (STAGE) {
+                mbar_wait(&bars[0], in_phase);
+                in_phase ^= 1;
+                const T *p = reinterpret_cast<const T *>(xbuf) + tid;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int aa = 0; aa < 8; ++aa) {
-                    re[q * 8 + aa] = __ldg(p + 256 * q + 1024 * aa);
-                    im[q * 8 + aa] = __ldg(p + B + 256 * q + 1024 * aa);
-                }
+                    for (int aa = 0; aa < 8; ++aa) {
+                        re[q * 8 + aa] = p[256 * q + 1024 * aa];
+                        im[q * 8 + aa] = p[B + 256 * q + 1024 * aa];
+                    }
+                __syncthreads();                           // everyone holds its samples: the buffer turns into the exchange buffer
+            } else {
+                const T *p = xc + s + tid;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int aa = 0; aa < 8; ++aa) {
+                        re[q * 8 + aa] = __ldg(p + 256 * q + 1024 * aa);
+                        im[q * 8 + aa] = __ldg(p + B + 256 * q + 1024 * aa);
+                    }
+            }
             if (a.prefetch && item + gridDim.x < total) {
-                const long long nit = item + gridDim.x;
-                const int nch = (int)(nit / a.items_per_channel);
-                const long long np = a.first_pair + (nit - (long long)nch * a.items_per_channel);
-                const char *src = reinterpret_cast<const char *>(a.x + (long long)nch * a.x_stride + np * (2LL * B) - hl);
+                const char *src = reinterpret_cast<const char *>(item_src(item + gridDim.x));
                 for (int off = tid * 128; off < span_bytes; off += kFft8kThreads * 128)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
             }
@@ -147,13 +198,32 @@ fir_fft8k_kernel(FirFftLaunch<T> a)
 #pragma unroll
         for (int k = 0; k < 32; ++k) { const C v = slice[k * kFftR + (lane ^ k)]; re[k] = v.x; im[k] = v.y; }
         __syncwarp();
+        if constexpr (STAGE) {
+            // the slice is idle until the next exchange: fetch this warp's 32 x 32 bins of the spectrum into it
+            if (lane == 0) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(&bars[1 + warp], (uint32_t)(kFftR * kFftR * sizeof(C)));
+                tma_bulk_g2s(slice, Hc - lane, (uint32_t)(kFftR * kFftR * sizeof(C)), &bars[1 + warp]);
+            }
+        }
         dft32_twisted<T, false>(re, im, tab2_s + warp * (kTwistEntries * kFftR) + lane, kFftR);
 
         // ---- spectrum, inverse 1024-point transform ---------------------------------------------------------------
+        if constexpr (STAGE) {
+            mbar_wait(&bars[1 + warp], h_phase);
+            h_phase ^= 1;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const C h = __ldg(Hc + k * kFftR);
-            cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
+            for (int k = 0; k < 32; ++k) {
+                const C h = slice[k * kFftR + lane];
+                cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
+            }
+            __syncwarp();                                  // all lanes are done with the spectrum before the slice is reused
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const C h = __ldg(Hc + k * kFftR);
+                cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
+            }
         }
         dft32<T, true>(re, im);
 #pragma unroll
@@ -176,6 +246,12 @@ fir_fft8k_kernel(FirFftLaunch<T> a)
                 re[q * 8 + b] = v.x; im[q * 8 + b] = v.y;
             }
         __syncthreads();                                   // the next item's exchange overwrites every slice
+        if constexpr (STAGE) {
+            if (tid == 0 && item + gridDim.x < total) {
+                fence_proxy_async_smem();
+                stage_input(item + gridDim.x);             // lands while this item's last DFT-8s and stores run
+            }
+        }
         dft8_twisted<T, true, 0>(re, im, __ldg(tab3 + 0 * 256), __ldg(tab3 + 1 * 256), __ldg(tab3 + 2 * 256), __ldg(tab3 + 3 * 256));
         dft8_twisted<T, true, 8>(re, im, __ldg(tab3 + 4 * 256), __ldg(tab3 + 5 * 256), __ldg(tab3 + 6 * 256), __ldg(tab3 + 7 * 256));
         dft8_twisted<T, true, 16>(re, im, __ldg(tab3 + 8 * 256), __ldg(tab3 + 9 * 256), __ldg(tab3 + 10 * 256), __ldg(tab3 + 11 * 256));
@@ -203,7 +279,7 @@ fir_fft8k_kernel(FirFftLaunch<T> a)
     }
 }
 
-template <typename T, bool EDGE>
+template <typename T, bool EDGE, bool STAGE>
 static int fir_fft8k_run(FirFftLaunch<T> b, int n_channels, long long first, long long count, long long gap_start,
                          long long gap_len, int sm_count, cudaStream_t stream)
 {
@@ -214,7 +290,7 @@ static int fir_fft8k_run(FirFftLaunch<T> b, int n_channels, long long first, lon
     b.items_per_channel = count;
     b.gap_start = gap_start;
     b.gap_len = gap_len;
-    auto kern = fir_fft8k_kernel<T, EDGE>;
+    auto kern = fir_fft8k_kernel<T, EDGE, STAGE>;
     LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long items = count * n_channels;
     const long long slots = (long long)sm_count * (sizeof(T) == 4 ? 2 : 1);
@@ -248,8 +324,14 @@ int fir_fft8k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     }
     const char *pf = getenv("LLZ_FFT_PREFETCH");
     a.prefetch = (pf && *pf) ? atoi(pf) : 1;
-    if (fir_fft8k_run<T, false>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
-    return fir_fft8k_run<T, true>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
+    const char *st = getenv("LLZ_FFT_STAGE");
+    const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 && (a.x_stride * sizeof(T)) % 16 == 0;
+    // measured on C5: staging gains 2.5 % in f64 (one CTA per SM) and loses 4 % in f32 (two CTAs per SM hide the loads)
+    const bool stage = aligned && ((st && *st) ? atoi(st) != 0 : sizeof(T) == 8);
+    const int rc = stage ? fir_fft8k_run<T, false, true>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream)
+                         : fir_fft8k_run<T, false, false>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream);
+    if (rc != 0) return -1;
+    return fir_fft8k_run<T, true, false>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
 }
 
 template int fir_fft8k_launch<float>(FirFftLaunch<float>, int, cudaStream_t);
