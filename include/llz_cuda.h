@@ -82,6 +82,10 @@ int llz_cuda_fir_bank_flt_len(unsigned long handle);
 int llz_cuda_fir_bank_set_algo(unsigned long handle, int algo);
 /* the family the next _run will use: LLZ_CUDA_FIR_ALGO_DIRECT or LLZ_CUDA_FIR_ALGO_FFT */
 int llz_cuda_fir_bank_get_algo(unsigned long handle);
+/* samples per work item of the kernel the next _run will use: 2*(1024 - halo) or 2*(8192 - halo) for the
+ * overlap-save kernels, 1 for the direct form.  A stream cut at multiples of this length (time segments with
+ * their flt_len-1 halo, pipeline chunks) reproduces the one-shot result bit for bit.                        */
+long long llz_cuda_fir_bank_block_len(unsigned long handle);
 int llz_cuda_fir_bank_copy_taps(unsigned long handle, double *h_out);      /* host copy, flt_len doubles */
 
 /* stream state = the last flt_len-1 samples of every channel (llz_fir.c:562-564) */
@@ -172,6 +176,10 @@ typedef struct {
 /* FIR: split n samples into `world` contiguous segments; halo = flt_len-1 */
 int llz_cuda_shard_fir_segments(long long n, int flt_len, int world, int rank,
                                 llz_cuda_segment_t *seg);
+/* same, with every internal boundary at a multiple of `granule` samples (llz_cuda_fir_bank_block_len): the
+ * concatenated segment outputs are then byte-identical to the one-shot run for the overlap-save kernels too */
+int llz_cuda_shard_fir_segments_aligned(long long n, int flt_len, long long granule, int world, int rank,
+                                        llz_cuda_segment_t *seg);
 /* resample: split n_in (a multiple of `frame_in`, the handle's num_in) into whole-frame runs so
  * that every segment starts at output index == 0 mod L (phase 0) and input index == 0 mod M/gcd;
  * halo = taps_per_phase-1 */

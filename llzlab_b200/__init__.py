@@ -108,6 +108,7 @@ _SIGNATURES = [
     ("llz_cuda_fir_bank_flt_len", C.c_int, [_ul]),
     ("llz_cuda_fir_bank_set_algo", C.c_int, [_ul, C.c_int]),
     ("llz_cuda_fir_bank_get_algo", C.c_int, [_ul]),
+    ("llz_cuda_fir_bank_block_len", _ll, [_ul]),
     ("llz_cuda_fir_bank_copy_taps", C.c_int, [_ul, _dp]),
     ("llz_cuda_fir_bank_reset", C.c_int, [_ul, _vp]),
     ("llz_cuda_fir_bank_set_history", C.c_int, [_ul, _vp, _ll, _vp]),
@@ -129,6 +130,7 @@ _SIGNATURES = [
     ("llz_cuda_resample_bank_guard_count", _ll, [_ul]),
     ("llz_cuda_shard_channels", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("llz_cuda_shard_fir_segments", C.c_int, [_ll, C.c_int, C.c_int, C.c_int, C.POINTER(Segment)]),
+    ("llz_cuda_shard_fir_segments_aligned", C.c_int, [_ll, C.c_int, _ll, C.c_int, C.c_int, C.POINTER(Segment)]),
     ("llz_cuda_shard_resample_segments", C.c_int,
      [_ll, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Segment)]),
     ("llz_cuda_pcm_deinterleave", C.c_int, [_vp, C.c_int, C.c_int, _ll, _vp, C.c_int, _ll, _vp]),
@@ -246,6 +248,13 @@ def shard_channels(n_channels: int, world: int, rank: int) -> tuple[int, int]:
 def shard_fir_segments(n: int, flt_len: int, world: int, rank: int) -> Segment:
     seg = Segment()
     _check(lib().llz_cuda_shard_fir_segments(n, flt_len, world, rank, C.byref(seg)), "shard_fir_segments")
+    return seg
+
+
+def shard_fir_segments_aligned(n: int, flt_len: int, granule: int, world: int, rank: int) -> Segment:
+    seg = Segment()
+    _check(lib().llz_cuda_shard_fir_segments_aligned(n, flt_len, granule, world, rank, C.byref(seg)),
+           "shard_fir_segments_aligned")
     return seg
 
 
@@ -374,6 +383,11 @@ class FirBank:
     def algo(self) -> int:
         """kernel family the next run uses: FIR_DIRECT or FIR_FFT"""
         return _check(lib().llz_cuda_fir_bank_get_algo(self.handle), "llz_cuda_fir_bank_get_algo")
+
+    @property
+    def block_len(self) -> int:
+        """samples per work item of the kernel in use (1 for the direct form); see llz_cuda_fir_bank_block_len"""
+        return _check(lib().llz_cuda_fir_bank_block_len(self.handle), "llz_cuda_fir_bank_block_len")
 
     def taps(self) -> np.ndarray:
         h = np.empty(self.flt_len, dtype=np.float64)

@@ -194,6 +194,11 @@ fir_fft_kernel(FirFftLaunch<T> a)
             }
         }
 
+        // the first halo - (N-1) samples of a block reach only discarded outputs; zeroing them makes every kept output
+        // a function of its own N-1 predecessors alone, bit for bit: a stream cut at multiples of the block length
+        // (time segments with an N-1 halo, pipeline chunks) reproduces the one-shot result exactly
+        if (lane < hl - (a.ntaps - 1)) { re[0] = T(0); im[0] = T(0); }
+
         // ---- forward pass 1: DFT over j -------------------------------------------------------------------
         dft32<T, false>(re, im);
         warp_exchange<T, PACK>(re, im, buf, lane);

@@ -176,6 +176,10 @@ fir_fft8k_kernel(FirFftLaunch<T> a)
                 }
         }
 
+        // the first halo - (N-1) samples of a block reach only discarded outputs; zeroing them makes every kept output a
+        // function of its own N-1 predecessors alone, bit for bit (see llz_cuda_fir_fft.cu)
+        if (tid < hl - (a.ntaps - 1)) { re[0] = T(0); im[0] = T(0); }
+
         // ---- DFT-8 over a; CTA-wide exchange: warp b receives n_lo = t + 32 j of residue b --------------------
         dft8<T, false, 0>(re, im); dft8<T, false, 8>(re, im); dft8<T, false, 16>(re, im); dft8<T, false, 24>(re, im);
 #pragma unroll

@@ -409,6 +409,25 @@ int llz_cuda_shard_fir_segments(long long n, int flt_len, int world, int rank,
     return 0;
 }
 
+int llz_cuda_shard_fir_segments_aligned(long long n, int flt_len, long long granule, int world, int rank,
+                                        llz_cuda_segment_t *seg)
+{
+    if (n < 0 || flt_len < 1 || granule < 1 || world < 1 || rank < 0 || rank >= world || !seg) {
+        llz_set_error("shard_fir_segments_aligned: bad arguments");
+        return -1;
+    }
+    long long units = (n + granule - 1) / granule, u0, uc;
+    split_even(units, world, rank, &u0, &uc);
+    long long start = u0 * granule, end = (u0 + uc) * granule;
+    if (start > n) start = n;
+    if (end > n) end = n;
+    seg->in_start = seg->out_start = start;
+    seg->in_count = seg->out_count = end - start;
+    seg->halo = flt_len - 1;
+    if (seg->halo > seg->in_start) seg->halo = seg->in_start;
+    return 0;
+}
+
 int llz_cuda_shard_resample_segments(long long n_in, int L, int M, int taps_per_phase,
                                      int frame_in, int world, int rank, llz_cuda_segment_t *seg)
 {

@@ -728,6 +728,20 @@ extern "C" int llz_cuda_fir_bank_get_algo(unsigned long handle)
     return fir_effective_algo(b);
 }
 
+long long fir_block_len(const FirBank *b)
+{
+    if (fir_effective_algo(b) != LLZ_CUDA_FIR_ALGO_FFT) return 1;
+    if (fir_use_fft8k(b)) return 2LL * (kFft8kN - (b->flt_len - 1 + 255) / 256 * 256);
+    return 2LL * (kFftN - (b->flt_len - 1 + 31) / 32 * 32);
+}
+
+extern "C" long long llz_cuda_fir_bank_block_len(unsigned long handle)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    return fir_block_len(b);
+}
+
 extern "C" int llz_cuda_fir_bank_copy_taps(unsigned long handle, double *h_out)
 {
     FirBank *b = as_fir(handle);
@@ -794,7 +808,12 @@ extern "C" int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in
     DeviceGuard g(b->device);
     const size_t es = fir_elem_size(b->dtype);
     const int C = b->n_channels;
-    const long long chunk = pick_chunk(n, C, 2.0 * es);
+    long long chunk = pick_chunk(n, C, 2.0 * es);
+    {
+        // whole work items per chunk: the overlap-save kernels then reproduce the one-shot result bit for bit
+        const long long blk = fir_block_len(b);
+        if (chunk < n && blk > 1) chunk = (chunk >= blk) ? chunk / blk * blk : blk;
+    }
     Pipeline &P = b->pipe;
     if (P.reserve((size_t)chunk * C * es, (size_t)chunk * C * es) != 0) return -1;
     const unsigned char *src = static_cast<const unsigned char *>(h_in);

@@ -58,7 +58,7 @@ def test_c5_full_length_one_channel(zlib, port, cuda):
         assert np.abs(got - want).max() <= 1e-12, t0
     # the same stream in two time segments with halo (C5's multi-GPU plan): the overlap-save kernel (AUTO picks the
     # 8192-point one here) agrees to rounding -- its block grid starts at the segment -- and the direct kernel bit for bit
-    assert bank.algo == zlib.FIR_FFT
+    assert bank.algo == zlib.FIR_FFT and bank.block_len == 8192
     seg = zlib.shard_fir_segments(n, N, 2, 1)
     bank.reset()
     bank.set_history(dx.data_ptr() + 8 * (seg.in_start - seg.halo), n)
@@ -66,6 +66,15 @@ def test_c5_full_length_one_channel(zlib, port, cuda):
     bank.run(dx.data_ptr() + 8 * seg.in_start, n, tail, 1_000_000, 1_000_000)
     torch.cuda.synchronize()
     assert (tail - dy[seg.out_start:seg.out_start + 1_000_000]).abs().max().item() <= 1e-12
+    # ... and bit for bit when the cut is a multiple of the kernel's work-item length (bench.py's plan for C5)
+    aseg = zlib.shard_fir_segments_aligned(n, N, bank.block_len, 8, 5)
+    assert aseg.in_start % 8192 == 0 and aseg.halo == N - 1
+    bank.reset()
+    bank.set_history(dx.data_ptr() + 8 * (aseg.in_start - aseg.halo), n)
+    m = 8192 * 100
+    bank.run(dx.data_ptr() + 8 * aseg.in_start, n, tail, m, m)
+    torch.cuda.synchronize()
+    assert torch.equal(tail[:m], dy[aseg.out_start:aseg.out_start + m])
     bank.close()
     direct = zlib.FirBank(1, zlib.F64, kind=zlib.LPF, flt_len=N, fc1=0.11, win=zlib.KAISER, algo=zlib.FIR_DIRECT)
     lead = 8192                                            # one-shot run over a window that starts before the segment

@@ -165,20 +165,35 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
     want = oracle_bank(port, h, x)
     assert np.abs(one.cpu().numpy() - want).max() <= TOL_F64
     bank.close()
-    # overlap-save kernel: the block grid moves with the segment start, so segments agree with the one-shot run
-    # to rounding (not bit for bit)
-    fbank = zlib.FirBank(C_, zlib.F64, taps=h, algo=zlib.FIR_FFT)
-    for world in (2, 8):
-        seg_out = torch.zeros_like(dx)
-        for rank in range(world):
-            s = zlib.shard_fir_segments(n, N, world, rank)
-            fbank.reset()
-            if s.halo:
-                fbank.set_history(dx.data_ptr() + 8 * (s.in_start - s.halo), n)
-            fbank.run(dx.data_ptr() + 8 * s.in_start, n, seg_out.data_ptr() + 8 * s.out_start, n, s.in_count)
-        torch.cuda.synchronize()
-        assert np.abs(seg_out.cpu().numpy() - want).max() <= TOL_F64, world
-    fbank.close()
+    # overlap-save kernels: arbitrary cuts agree with the one-shot run to rounding (the block grid moves with the
+    # segment start); cuts at multiples of the work-item length are byte-identical (llz_cuda_fir_bank_block_len)
+    for taps, n2 in ((h, n), (port.fir_design(0, 1025, 0.11, 0.0, 2), 300_001)):
+        N2 = len(taps)
+        x2 = np.stack([port.lcg_f64(n2, 7 + c) for c in range(C_)])
+        dx2 = torch.from_numpy(x2).cuda()
+        fbank = zlib.FirBank(C_, zlib.F64, taps=taps, algo=zlib.FIR_FFT)
+        blk = fbank.block_len
+        assert blk == (2 * (1024 - 256) if N2 == 255 else 2 * (8192 - 1024))
+        one2 = torch.empty_like(dx2)
+        fbank.run(dx2, n2, one2, n2, n2)
+        want2 = oracle_bank(port, taps, x2)
+        assert np.abs(one2.cpu().numpy() - want2).max() <= TOL_F64
+        for world in (2, 8):
+            for aligned in (False, True):
+                seg_out = torch.zeros_like(dx2)
+                for rank in range(world):
+                    s = (zlib.shard_fir_segments_aligned(n2, N2, blk, world, rank) if aligned
+                         else zlib.shard_fir_segments(n2, N2, world, rank))
+                    fbank.reset()
+                    if s.halo:
+                        fbank.set_history(dx2.data_ptr() + 8 * (s.in_start - s.halo), n2)
+                    fbank.run(dx2.data_ptr() + 8 * s.in_start, n2, seg_out.data_ptr() + 8 * s.out_start, n2, s.in_count)
+                torch.cuda.synchronize()
+                if aligned:
+                    assert torch.equal(seg_out, one2), (N2, world)
+                else:
+                    assert np.abs(seg_out.cpu().numpy() - want2).max() <= TOL_F64, (N2, world)
+        fbank.close()
 
 
 @pytest.mark.parametrize("N", [898, 2049, 4095, 6145])
@@ -295,12 +310,16 @@ def test_run_host_pipeline(zlib, port, cuda):
     bank.run_host(xp, 300000, yp, 300000, 300000)
     assert np.array_equal(yp, y[:, :300000])
     bank.close()
-    # the overlap-save kernel through the same pipeline: chunk boundaries move its block grid -> rounding-level
+    # the overlap-save kernel through the same pipeline: chunks are whole work items -> the one-shot bytes
     fbank = zlib.FirBank(C_, zlib.F64, taps=h)
     assert fbank.algo == zlib.FIR_FFT
     y2 = np.empty_like(np.asarray(y))
     fbank.run_host(x, n, y2, n, n)
     assert np.abs(y2 - y).max() <= TOL_F64
+    fbank.reset()
+    fbank.run(dx, n, dy, n, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy(), y2)
     fbank.close()
     zlib.host_free(x.reshape(-1)); zlib.host_free(y.reshape(-1))
 

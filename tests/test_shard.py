@@ -36,6 +36,23 @@ def test_fir_segments(zlib, n, N, world):
     assert pos == n
 
 
+@pytest.mark.parametrize("n,N,g,world", [(691_200_000, 4095, 8192, 8), (100_003, 255, 1536, 4), (1000, 127, 1792, 2),
+                                         (5, 3, 1, 8), (480_000, 127, 1792, 8)])
+def test_fir_segments_aligned(zlib, n, N, g, world):
+    """every internal boundary is a multiple of the kernel's work-item length; the segments tile [0, n)"""
+    pos, counts = 0, []
+    for r in range(world):
+        s = zlib.shard_fir_segments_aligned(n, N, g, world, r)
+        assert s.in_start == pos == s.out_start and s.in_count == s.out_count
+        assert s.in_start % g == 0 or s.in_start == n
+        assert s.halo == min(N - 1, s.in_start)
+        pos += s.in_count
+        counts.append(s.in_count)
+    assert pos == n
+    full = [c for c in counts if c and c % g == 0]
+    assert not full or max(full) - min(full) <= g
+
+
 @pytest.mark.parametrize("L,M,Q,frames,world", [(320, 147, 257, 3375, 8), (160, 147, 45, 113, 2), (1, 3, 134, 18750, 8),
                                                (3, 2, 77, 5, 8)])
 def test_resample_segments(zlib, port, L, M, Q, frames, world):
