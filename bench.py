@@ -68,25 +68,35 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag = index, threading.Event()
         self.samples, self.reasons, self.max_mhz, self.error = [], set(), None, None
-
-    def run(self):
-        try:
+        self.nv, self.h = None, None
+        try:                                        # NVML is initialised before the timed region, not inside it
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            while not self.stop_flag.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                try:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:                      # noqa: BLE001
             self.error = repr(e)
+
+    def sample_now(self):
+        """one sample from the calling thread (the main thread calls it while the timed launches are in flight)"""
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception as e:                      # noqa: BLE001
+            self.error = repr(e)
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            self.sample_now()
+            time.sleep(0.002)
 
     def result(self):
         self.stop_flag.set()
@@ -320,17 +330,18 @@ def run_cuda(args):
     # ---- device-timed region ----
     for _ in range(max(args.warmup, 3)):
         step()
+    sampler = ClockSampler(local)                   # NVML init happens here, outside the bracket
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
+    sampler.sample_now()                            # the launches above are still running: a sample under load
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

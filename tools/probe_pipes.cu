@@ -49,6 +49,57 @@ __global__ void __launch_bounds__(256) ffma_kernel(float *sink, int iters, float
     if (t == 123456.789f) sink[0] = t;
 }
 
+// packed FP32 (fma.rn.f32x2 -> SASS FFMA2): NF independent 2-wide accumulators; NL shared-memory loads per NF FFMA2
+// show whether the packed form frees issue slots for other pipes
+template <int NF, int NL>
+__global__ void __launch_bounds__(256) ffma2_kernel(float *sink, int iters, float a, float b)
+{
+    __shared__ float sm[256 * 4];
+    for (int i = threadIdx.x; i < 1024; i += 256) sm[i] = i;
+    __syncthreads();
+    unsigned long long f[NF];
+    for (int i = 0; i < NF; ++i) f[i] = ((unsigned long long)__float_as_uint(threadIdx.x + i) << 32) | __float_as_uint(i + 1.f);
+    const unsigned long long ra = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a + 1e-3f);
+    const unsigned long long rb = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(b - 1e-3f);
+    float acc = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(f[i]) : "l"(ra), "l"(rb));
+#pragma unroll
+            for (int i = 0; i < NL; ++i) acc += sm[(threadIdx.x + 32 * i + it) & 1023];
+        }
+    }
+    float t = acc;
+    for (int i = 0; i < NF; ++i) t += __uint_as_float((unsigned)f[i]) + __uint_as_float((unsigned)(f[i] >> 32));
+    if (t == 123456.789f) sink[0] = t;
+}
+
+// scalar FFMA with the same shared-memory load mix, for comparison
+template <int NF, int NL>
+__global__ void __launch_bounds__(256) ffma_lds_kernel(float *sink, int iters, float a, float b)
+{
+    __shared__ float sm[256 * 4];
+    for (int i = threadIdx.x; i < 1024; i += 256) sm[i] = i;
+    __syncthreads();
+    float f[NF];
+    for (int i = 0; i < NF; ++i) f[i] = threadIdx.x + i;
+    float ra = a + threadIdx.x, rb = b - threadIdx.x, acc = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) f[i] = fmaf(f[i], ra, rb);
+#pragma unroll
+            for (int i = 0; i < NL; ++i) acc += sm[(threadIdx.x + 32 * i + it) & 1023];
+        }
+    }
+    float t = acc;
+    for (int i = 0; i < NF; ++i) t += f[i];
+    if (t == 123456.789f) sink[0] = t;
+}
+
 // legacy tensor-core path: mma.sync m16n8k16 f16 x f16 -> f32, NM independent accumulator tiles per warp
 template <int NM>
 __global__ void __launch_bounds__(256) hmma_kernel(float *sink, int iters, unsigned a0, unsigned b0)
@@ -109,6 +160,16 @@ int main()
     {
         float ms = time_ms(ffma_kernel<16>, blocks, threads, (float *)sink, iters, 0.999f, 0.001f);
         printf("%-28s %8.3f ms  %7.2f TFLOP/s\n", "ffma x16", ms, 2.0 * 16 * nthreads * iters * 4 / ms / 1e9);
+    }
+    {
+        float ms = time_ms(ffma2_kernel<16, 0>, blocks, threads, (float *)sink, iters, 0.999f, 0.001f);
+        printf("%-28s %8.3f ms  %7.2f TFLOP/s (packed fma.rn.f32x2, 2 FMA per lane per instruction)\n", "ffma2 x16", ms,
+               2.0 * 2 * 16 * nthreads * iters * 4 / ms / 1e9);
+        ms = time_ms(ffma_lds_kernel<16, 8>, blocks, threads, (float *)sink, iters, 0.999f, 0.001f);
+        printf("%-28s %8.3f ms  %7.2f TFLOP/s\n", "ffma x16 + 8 lds+fadd", ms, 2.0 * 16 * nthreads * iters * 4 / ms / 1e9);
+        ms = time_ms(ffma2_kernel<8, 8>, blocks, threads, (float *)sink, iters, 0.999f, 0.001f);
+        printf("%-28s %8.3f ms  %7.2f TFLOP/s (same FMA count as the line above)\n", "ffma2 x8 + 8 lds+fadd", ms,
+               2.0 * 2 * 8 * nthreads * iters * 4 / ms / 1e9);
     }
     for (int pass = 0; pass < 2; ++pass) {
         const int nm = pass ? 16 : 8;
