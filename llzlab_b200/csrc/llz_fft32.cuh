@@ -84,25 +84,22 @@ template <> LLZ_HD double fma_t<double>(double a, double b, double c) { return f
 template <typename T, bool INV>
 LLZ_HD void bfly32(T &ur, T &ui, T &vr, T &vi, int m)
 {
-    T pr, pi;
     if (m == 0) {
-        pr = vr; pi = vi;
+        const T pr = vr, pi = vi;
         const T ar = ur, ai = ui;
         ur = ar + pr; ui = ai + pi;
         vr = ar - pr; vi = ai - pi;
     } else if (m == 8) {
-        // forward w = -i: w*v = (v.im, -v.re);  inverse w = +i: w*v = (-v.im, v.re)
-        pr = INV ? -vi : vi;
-        pi = INV ? vr : -vr;
-        const T ar = ur, ai = ui;
-        ur = ar + pr; ui = ai + pi;
-        vr = ar - pr; vi = ai - pi;
+        // forward w = -i: w*v = (v.im, -v.re);  inverse w = +i: w*v = (-v.im, v.re)   (no negation of data: add / sub)
+        const T ar = ur, ai = ui, br = vr, bi = vi;
+        if (!INV) { ur = ar + bi; ui = ai - br; vr = ar - bi; vi = ai + br; }
+        else      { ur = ar - bi; ui = ai + br; vr = ar + bi; vi = ai - br; }
     } else {
         const T c = (T)tw32_cos(m);
         const T t = (T)(INV ? -tw32_tan(m) : tw32_tan(m));
         // forward: (1 - i t)(vr + i vi) = (vr + t vi) + i (vi - t vr)
-        pr = fma_t<T>(t, vi, vr);
-        pi = fma_t<T>(-t, vr, vi);
+        const T pr = fma_t<T>(t, vi, vr);
+        const T pi = fma_t<T>(-t, vr, vi);
         const T ar = ur, ai = ui;
         ur = fma_t<T>(c, pr, ar);  ui = fma_t<T>(c, pi, ai);
         vr = fma_t<T>(-c, pr, ar); vi = fma_t<T>(-c, pi, ai);
@@ -218,9 +215,10 @@ LLZ_HD void dft32_twisted(T (&re)[32], T (&im)[32], const C *tab, int ts)
 template <typename T, bool CONJ>
 LLZ_HD void cmul_inplace(T &r, T &s, T c, T d)
 {
-    if (CONJ) d = -d;
-    const T nr = fma_t<T>(-s, d, r * c);
-    const T ns = fma_t<T>(s, c, r * d);
+    // only the table value d is negated (once), never the data
+    const T dp = CONJ ? -d : d, dn = CONJ ? d : -d;
+    const T nr = fma_t<T>(s, dn, r * c);
+    const T ns = fma_t<T>(s, c, r * dp);
     r = nr; s = ns;
 }
 

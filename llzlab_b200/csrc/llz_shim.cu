@@ -166,6 +166,7 @@ struct FirBank {
     int algo = LLZ_CUDA_FIR_ALGO_AUTO;
     void *d_fft_H = nullptr, *d_fft_tw = nullptr;
     void *d_fft_tw2 = nullptr, *d_fft_tw3 = nullptr;     // 8192-point kernel (llz_cuda_fir_fft8k.cu)
+    void *d_fft_Hx = nullptr, *d_fft_twx = nullptr;      // float banks: tables with duplicated values (packed FP32)
     bool fft8k = false;
     Pipeline pipe;
     // drop-in (mono, host buffers)
@@ -193,6 +194,8 @@ void fir_destroy(FirBank *b)
     if (b->d_fft_tw) cudaFree(b->d_fft_tw);
     if (b->d_fft_tw2) cudaFree(b->d_fft_tw2);
     if (b->d_fft_tw3) cudaFree(b->d_fft_tw3);
+    if (b->d_fft_Hx) cudaFree(b->d_fft_Hx);
+    if (b->d_fft_twx) cudaFree(b->d_fft_twx);
     if (b->d_hist[0]) cudaFree(b->d_hist[0]);
     if (b->d_hist[1]) cudaFree(b->d_hist[1]);
     if (b->pinned) cudaFreeHost(b->pinned);
@@ -343,6 +346,16 @@ int fir_fft_tables(FirBank *b)
         fft8k_make_spectrum(b->h_host, b->flt_len, H.data());
     } else {
         fft1024_make_spectrum(b->h_host, b->flt_len, H.data());
+        const char *px = getenv("LLZ_FFT_F32X2");
+        if (f32 && px && atoi(px) != 0) {
+            // the packed-FP32 kernel (an experiment, llz_cuda_fir_fft.cu) reads (re, re, im, im) / (cos, cos, tan, tan): one value for both halves
+            auto dup = [](const std::vector<double> &v) {
+                std::vector<double> d(2 * v.size());
+                for (size_t i = 0; i < v.size(); ++i) d[2 * i] = d[2 * i + 1] = v[i];
+                return d;
+            };
+            if (upload_as(&b->d_fft_Hx, dup(H), true) != 0 || upload_as(&b->d_fft_twx, dup(tw), true) != 0) return -1;
+        }
     }
     return upload_as(&b->d_fft_H, H, f32);
 }
@@ -371,6 +384,8 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
         f.hist = a.hist; f.ntaps = b->flt_len;
         f.H = static_cast<const T *>(b->d_fft_H);
         f.tw = static_cast<const T *>(b->d_fft_tw);
+        f.Hx = static_cast<const T *>(b->d_fft_Hx);
+        f.twx = static_cast<const T *>(b->d_fft_twx);
         f.tw2 = static_cast<const T *>(b->d_fft_tw2);
         f.tw3 = static_cast<const T *>(b->d_fft_tw3);
         if ((b->fft8k ? fir_fft8k_launch<T>(f, b->n_channels, st) : fir_fft_launch<T>(f, b->n_channels, st)) != 0) return -1;

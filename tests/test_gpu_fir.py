@@ -263,6 +263,43 @@ def test_fft_bank_streaming_ragged_chunks(zlib, port, cuda, dtype, N):
     bank.close()
 
 
+def test_fft_f32_packed_kernel_matches_scalar_kernel_bits(zlib, port, cuda, monkeypatch):
+    """LLZ_FFT_F32X2=1 runs the float overlap-save transform on packed FP32 (two items per warp, FFMA2); each half is
+    the same IEEE operation sequence as the scalar-float kernel, so the bytes agree -- with the scalar kernel, and
+    between a one-shot run and aligned time segments (interior items packed, edge items scalar)"""
+    torch = cuda
+    N, C_, n = 127, 3, 200_003
+    h = port.fir_design(0, N, 0.23, 0.0, 0)
+    x = np.stack([port.lcg_f64(n, 31 + c) for c in range(C_)]).astype(np.float32)
+    dx = torch.from_numpy(x).cuda()
+    monkeypatch.setenv("LLZ_FFT_F32X2", "1")                 # the packed kernel is an opt-in experiment
+    bank = zlib.FirBank(C_, zlib.F32, taps=h, algo=zlib.FIR_FFT)
+    packed = torch.empty_like(dx)
+    bank.run(dx, n, packed, n, n)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("LLZ_FFT_F32X2", "0")
+    scalar = torch.empty_like(dx)
+    bank.reset()
+    bank.run(dx, n, scalar, n, n)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("LLZ_FFT_F32X2", "1")
+    assert torch.equal(packed, scalar)
+    want = oracle_bank(port, h, x.astype(np.float64))
+    assert snr_db(want, packed.cpu().numpy()) >= SNR_F32_DB
+    blk = bank.block_len
+    for world in (2, 7):
+        seg_out = torch.zeros_like(dx)
+        for rank in range(world):
+            s = zlib.shard_fir_segments_aligned(n, N, blk, world, rank)
+            bank.reset()
+            if s.halo:
+                bank.set_history(dx.data_ptr() + 4 * (s.in_start - s.halo), n)
+            bank.run(dx.data_ptr() + 4 * s.in_start, n, seg_out.data_ptr() + 4 * s.out_start, n, s.in_count)
+        torch.cuda.synchronize()
+        assert torch.equal(seg_out, packed), world
+    bank.close()
+
+
 def test_fft_algo_selection(zlib, cuda):
     """AUTO picks overlap-save for tolerance-mode banks of 48..6145 taps; STRICT and longer filters stay direct"""
     h = np.ones(127) / 127
