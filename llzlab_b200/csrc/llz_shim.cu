@@ -360,9 +360,11 @@ int fir_fft_tables(FirBank *b)
     return upload_as(&b->d_fft_H, H, f32);
 }
 
+// channels [c0, c0 + cc) of the bank; d_in / d_out point at channel c0.  `last` = the call completes the bank's
+// step: the history ping-pong flips once every channel has been run (the host pipeline runs channel groups).
 template <typename T>
 int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride,
-                  long long n, cudaStream_t st)
+                  long long n, cudaStream_t st, int c0, int cc, bool last)
 {
     FirLaunch<T> a{};
     a.x = static_cast<const T *>(d_in);
@@ -370,11 +372,12 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
     a.y = static_cast<T *>(d_out);
     a.y_stride = out_stride;
     a.n = n;
-    a.hist = (b->hist_zero || b->hist_len == 0) ? nullptr : static_cast<const T *>(b->d_hist[b->cur]);
+    a.hist = (b->hist_zero || b->hist_len == 0) ? nullptr
+                                                 : static_cast<const T *>(b->d_hist[b->cur]) + (size_t)c0 * b->hist_len;
     a.taps = static_cast<const T *>(b->d_taps);
     a.ntaps = b->flt_len;
     a.vec_ok = (d_in == nullptr || aligned16(d_in)) && aligned16(d_out) &&
-               (b->n_channels == 1 || ((in_stride * sizeof(T)) % 16 == 0 && (out_stride * sizeof(T)) % 16 == 0));
+               (cc == 1 || ((in_stride * sizeof(T)) % 16 == 0 && (out_stride * sizeof(T)) % 16 == 0));
     const int algo = fir_effective_algo(b);
     if (algo < 0) return -1;
     if (algo == LLZ_CUDA_FIR_ALGO_FFT) {
@@ -388,18 +391,26 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
         f.twx = static_cast<const T *>(b->d_fft_twx);
         f.tw2 = static_cast<const T *>(b->d_fft_tw2);
         f.tw3 = static_cast<const T *>(b->d_fft_tw3);
-        if ((b->fft8k ? fir_fft8k_launch<T>(f, b->n_channels, st) : fir_fft_launch<T>(f, b->n_channels, st)) != 0) return -1;
-    } else if (fir_launch<T>(a, b->n_channels, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) {
+        if ((b->fft8k ? fir_fft8k_launch<T>(f, cc, st) : fir_fft_launch<T>(f, cc, st)) != 0) return -1;
+    } else if (fir_launch<T>(a, cc, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) {
         return -1;
     }
     if (b->hist_len > 0) {
-        const T *old = b->hist_zero ? nullptr : static_cast<const T *>(b->d_hist[b->cur]);
-        T *next = static_cast<T *>(b->d_hist[b->cur ^ 1]);
-        if (fir_update_history<T>(a.x, in_stride, n, old, next, b->hist_len, b->n_channels, st) != 0) return -1;
-        b->cur ^= 1;
-        b->hist_zero = false;
+        T *next = static_cast<T *>(b->d_hist[b->cur ^ 1]) + (size_t)c0 * b->hist_len;
+        if (fir_update_history<T>(a.x, in_stride, n, a.hist, next, b->hist_len, cc, st) != 0) return -1;
+        if (last) {
+            b->cur ^= 1;
+            b->hist_zero = false;
+        }
     }
     return 0;
+}
+
+int fir_run_part(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride, long long n,
+                 cudaStream_t st, int c0, int cc, bool last)
+{
+    if (b->dtype == LLZ_CUDA_F32) return fir_run_typed<float>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last);
+    return fir_run_typed<double>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last);
 }
 
 int fir_run(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride, long long n,
@@ -408,8 +419,7 @@ int fir_run(FirBank *b, const void *d_in, long long in_stride, void *d_out, long
     if (n < 0) { llz_set_error("negative sample count"); return -1; }
     if (n == 0) return 0;
     if (!d_out) { llz_set_error("null output pointer"); return -1; }
-    if (b->dtype == LLZ_CUDA_F32) return fir_run_typed<float>(b, d_in, in_stride, d_out, out_stride, n, st);
-    return fir_run_typed<double>(b, d_in, in_stride, d_out, out_stride, n, st);
+    return fir_run_part(b, d_in, in_stride, d_out, out_stride, n, st, 0, b->n_channels, true);
 }
 
 // ---- polyphase bank ----------------------------------------------------------------------------------
@@ -823,16 +833,58 @@ extern "C" int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in
     DeviceGuard g(b->device);
     const size_t es = fir_elem_size(b->dtype);
     const int C = b->n_channels;
+    Pipeline &P = b->pipe;
+    const unsigned char *src = static_cast<const unsigned char *>(h_in);
+    unsigned char *dst = static_cast<unsigned char *>(h_out);
+    {
+        // Many short channels (C2: 1024 x 3.84 MB): pipeline over GROUPS OF WHOLE CHANNELS.  With dense rows a group
+        // is one contiguous span, so every copy is 1-D: tools/pcie_probe2d.cu measures 44.2 GB/s H2D for contiguous
+        // copies against 37.8 GB/s for the row-wise shape a time chunk of all channels needs (D2H 48.5 / 47.0), and
+        // the kernels see whole channels (no per-chunk edge items).  Long channels fall through to time chunks.
+        const char *env = getenv("LLZ_PIPE_SLOT_MB");
+        const double budget = ((env && atof(env) >= 1.0) ? atof(env) : kPipeSlotMiB) * 1024 * 1024;
+        const double per_channel = 2.0 * (double)es * (double)n;
+        long long group = (long long)(budget / per_channel);
+        if (group >= 2 && C > 2 * group) {
+            if (group > C) group = C;
+            const size_t row = (size_t)n * es;
+            if (P.reserve((size_t)group * row, (size_t)group * row) != 0) return -1;
+            const bool dense_in = in_stride == n, dense_out = out_stride == n;
+            long long idx = 0;
+            for (long long c0 = 0; c0 < C; c0 += group, ++idx) {
+                const long long cc = (C - c0 < group) ? C - c0 : group;
+                const int s = (int)(idx % kSlots);
+                if (idx >= kSlots) {
+                    LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_in, P.run_done[s], 0));
+                    LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_run, P.out_done[s], 0));
+                }
+                const unsigned char *hs = src + (size_t)c0 * in_stride * es;
+                unsigned char *hd = dst + (size_t)c0 * out_stride * es;
+                if (dense_in) LLZ_CUDA_TRY(cudaMemcpyAsync(P.d_in[s], hs, (size_t)cc * row, cudaMemcpyHostToDevice, P.s_in));
+                else if (copy_planar(P.d_in[s], row, hs, (size_t)in_stride * es, row, (size_t)cc, cudaMemcpyHostToDevice,
+                                     P.s_in) != 0) return -1;
+                LLZ_CUDA_TRY(cudaEventRecord(P.in_ready[s], P.s_in));
+                LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_run, P.in_ready[s], 0));
+                if (fir_run_part(b, P.d_in[s], n, P.d_out[s], n, n, P.s_run, (int)c0, (int)cc, c0 + cc >= C) != 0) return -1;
+                LLZ_CUDA_TRY(cudaEventRecord(P.run_done[s], P.s_run));
+                LLZ_CUDA_TRY(cudaStreamWaitEvent(P.s_out, P.run_done[s], 0));
+                if (dense_out) LLZ_CUDA_TRY(cudaMemcpyAsync(hd, P.d_out[s], (size_t)cc * row, cudaMemcpyDeviceToHost, P.s_out));
+                else if (copy_planar(hd, (size_t)out_stride * es, P.d_out[s], row, row, (size_t)cc, cudaMemcpyDeviceToHost,
+                                     P.s_out) != 0) return -1;
+                LLZ_CUDA_TRY(cudaEventRecord(P.out_done[s], P.s_out));
+            }
+            LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_out));
+            LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_run));
+            return 0;
+        }
+    }
     long long chunk = pick_chunk(n, C, 2.0 * es);
     {
         // whole work items per chunk: the overlap-save kernels then reproduce the one-shot result bit for bit
         const long long blk = fir_block_len(b);
         if (chunk < n && blk > 1) chunk = (chunk >= blk) ? chunk / blk * blk : blk;
     }
-    Pipeline &P = b->pipe;
     if (P.reserve((size_t)chunk * C * es, (size_t)chunk * C * es) != 0) return -1;
-    const unsigned char *src = static_cast<const unsigned char *>(h_in);
-    unsigned char *dst = static_cast<unsigned char *>(h_out);
     long long idx = 0;
     for (long long t0 = 0; t0 < n; t0 += chunk, ++idx) {
         const long long len = (n - t0 < chunk) ? n - t0 : chunk;
