@@ -361,6 +361,39 @@ def test_run_host_pipeline(zlib, port, cuda):
     zlib.host_free(x.reshape(-1)); zlib.host_free(y.reshape(-1))
 
 
+@pytest.mark.parametrize("algo", [1, 2])
+def test_run_host_channel_groups_with_padded_rows(zlib, port, cuda, monkeypatch, algo):
+    """many short channels -> the host pipeline runs groups of whole channels; padded (non-dense) rows take the
+    row-wise copy inside a group; the stream state carries over to the next call for every group"""
+    torch = cuda
+    monkeypatch.setenv("LLZ_PIPE_SLOT_MB", "4")                 # 4 MiB slots: groups of 2 channels, 21 groups
+    N, C_, n = 127, 41, 100_003
+    h = port.fir_design(0, N, 0.23, 0.0, 0)
+    xs, ys = n + 5, n + 9
+    x = np.zeros((C_, xs))
+    for c in range(C_):
+        x[c, :n] = port.lcg_f64(n, 500 + c)
+    y = np.full((C_, ys), 7.0)
+    bank = zlib.FirBank(C_, zlib.F64, taps=h, algo=algo)
+    half = 60_000
+    bank.run_host(x, xs, y, ys, half)                           # two calls: history of every channel group carries over
+    bank.run_host(x[:, half:], xs, y[:, half:], ys, n - half)
+    want = oracle_bank(port, h, x[:, :n])
+    assert np.abs(y[:, :n] - want).max() <= TOL_F64
+    assert (y[:, n:] == 7.0).all()
+    # dense rows, same bank: one contiguous copy per group; equals the device-resident run bit for bit
+    xd, yd = np.ascontiguousarray(x[:, :n]), np.empty((C_, n))
+    bank.reset()
+    bank.run_host(xd, n, yd, n, n)
+    dx = torch.from_numpy(xd).cuda()
+    dy = torch.empty_like(dx)
+    bank.reset()
+    bank.run(dx, n, dy, n, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(dy.cpu().numpy(), yd)
+    bank.close()
+
+
 def test_c2_full_size_properties(zlib, port, cuda):
     """BASELINE config 2 at full size: 1024 channels x 480,000 samples, 127-tap LPF (f64).
     Spot checks against the oracle plus linearity and a DC-gain check (size-independent properties)."""
