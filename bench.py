@@ -273,7 +273,7 @@ def run_cuda(args):
         fma_peak_nominal = FP32_NOMINAL_TFLOPS if f32 else FP64_NOMINAL_TFLOPS
         fma_dtype = z.F32 if f32 else z.F64
         fir_fft = bank.algo == z.FIR_FFT
-        if fir_fft and wl["taps"] >= 641:
+        if fir_fft and wl["taps"] >= 545:
             # 8192-point overlap-save kernel (llz_cuda_fir_fft8k.cu): one CTA of 256 threads turns 2*B outputs out of
             # 2580 FMA-pipe instructions per thread
             halo_pad = (wl["taps"] - 1 + 255) // 256 * 256

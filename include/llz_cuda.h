@@ -57,7 +57,7 @@ enum {                                      /* FIR kernel family (tolerance-mode
     LLZ_CUDA_FIR_ALGO_AUTO   = 0, /* overlap-save for 48..6145 taps, direct form otherwise (default)         */
     LLZ_CUDA_FIR_ALGO_DIRECT = 1, /* register-blocked sliding MAC: 2*N flop per output                       */
     LLZ_CUDA_FIR_ALGO_FFT    = 2, /* overlap-save in the bank's own type: a 1024-point transform per warp up
-                                     to 640 taps (~35 FMA-pipe instructions per output at 127 taps), an
+                                     to 544 taps (~35 FMA-pipe instructions per output at 127 taps), an
                                      8192-point transform per CTA up to 6145 taps (~81 at 4095 taps);
                                      |err| ~1e-15 (f64) / ~3e-7 (f32) of full scale against the direct sum,
                                      not bit-identical                                                      */

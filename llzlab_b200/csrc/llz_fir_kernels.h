@@ -34,7 +34,7 @@ int fir_update_history(const T *x, long long x_stride, long long n, const T *his
 // ---- overlap-save (1024-point FFT) FIR, llz_cuda_fir_fft.cu -----------------------------------------
 constexpr int kFirFftMinTapsAuto = 48;   // below this the direct kernel is at least as fast
 constexpr int kFirFftMaxTaps = 897;      // leaves B = 1024 - halo >= 128 valid outputs per block
-constexpr int kFirFft8kMinTapsAuto = 641;  // from here on the 8192-point kernel (llz_cuda_fir_fft8k.cu) wins
+constexpr int kFirFft8kMinTapsAuto = 545;  // from here on the 8192-point kernel wins (profiles/r01_crossover_fft.txt)
 constexpr int kFirFft8kMaxTaps = 6145;   // leaves B = 8192 - halo >= 2048
 
 template <typename T>
