@@ -1,4 +1,4 @@
-// llz_cuda_fir_fft8k.cu -- overlap-save FIR banks for long filters (898 .. 6145 taps) on sm_100a:
+// llz_cuda_fir_fft8k.cu -- overlap-save FIR banks for long filters (545 .. 6145 taps) on sm_100a:
 // the tolerance-mode arithmetic of llz_fir_filter / llz_conv (libllzfilter/llz_fir.c:411-426, 547-584).
 //
 //   y[c][t] = sum_{i<N} h[i] * x[c][t-i]
