@@ -436,6 +436,7 @@ struct PolyBank {
     uint16_t *d_cbankT16h = nullptr, *d_cbankT16l = nullptr, *d_cbankT16h_base = nullptr, *d_cbankT16l_base = nullptr;
     int bank16_exp = 0;
     int bank_pad = 0;
+    int rep = 1;             // device tables hold the bank's rows `rep` times: kernels see L*rep phases, M*rep step
     int *d_order = nullptr, *d_single = nullptr;
     int slide_ntp64 = 0, slide_ntp32 = 0;
     unsigned long long *d_guard = nullptr;
@@ -490,22 +491,29 @@ int upload(T **dst, const std::vector<T> &src)
 int poly_upload_plan(PolyBank *b)
 {
     const llz_plan_t &p = b->plan;
-    const size_t L = (size_t)p.crows, Q = (size_t)p.ctaps;
+    // Few phases (2 <= L < 16: 2/1, 3/2, 3/1 ...) would leave the 64-phase tiles of the phase-bank kernels mostly
+    // padding.  y[o] = sum_k g[o % L][k] x[floor(o*M/L) - k] is unchanged when L and M are both multiplied by r and
+    // the bank's rows are repeated r times (o % (rL) selects the same row, floor(o*rM/(rL)) the same sample), so the
+    // device tables carry r = floor(64/L) copies and every kernel sees one nearly full 64-phase tile.
+    b->rep = (p.crows >= 2 && p.crows < 16 && p.shift == 0 && p.frame_len == 0) ? 64 / p.crows : 1;
+    const size_t L0 = (size_t)p.crows, L = L0 * (size_t)b->rep, Q = (size_t)p.ctaps;
     // transposed bank [Q][L] with `pad` zero rows on both sides: the phase-bank kernel shifts rows per phase by up to
     // 64*M/L + 1 and over-runs the last chunk, and must not need bounds checks (llz_cuda_polybank.cu)
     const size_t pad = (size_t)(64.0 * p.M / p.L) + 2 + 64;
     b->bank_pad = (int)pad;
-    std::vector<double> cb(p.cbank, p.cbank + L * Q), t64(L * (Q + 2 * pad), 0.0);
+    std::vector<double> cb(L * Q), t64(L * (Q + 2 * pad), 0.0);
     std::vector<float> t32(L * (Q + 2 * pad), 0.f);
     for (size_t r = 0; r < L; ++r)
         for (size_t k = 0; k < Q; ++k) {
-            t64[(k + pad) * L + r] = cb[r * Q + k];
-            t32[(k + pad) * L + r] = (float)cb[r * Q + k];
+            const double g = p.cbank[(r % L0) * Q + k];
+            cb[r * Q + k] = g;
+            t64[(k + pad) * L + r] = g;
+            t32[(k + pad) * L + r] = (float)g;
         }
     if (upload(&b->d_cbank, cb) || upload(&b->d_cbankT64_base, t64) || upload(&b->d_cbankT32_base, t32)) return -1;
     b->d_cbankT64 = b->d_cbankT64_base + pad * L;
     b->d_cbankT32 = b->d_cbankT32_base + pad * L;
-    if (b->acc == LLZ_CUDA_ACC_F32 && p.L >= 16) {
+    if (b->acc == LLZ_CUDA_ACC_F32 && L >= 16) {
         // fp16 hi/lo planes for the tensor-core fast mode (llz_cuda_polybank.cu): scale so the largest tap sits in
         // [2^14, 2^15), then g*2^e = hi + lo with hi = fp16(g*2^e), lo = fp16(g*2^e - hi): 22 significant bits
         double gmax = 0.0;
@@ -526,7 +534,8 @@ int poly_upload_plan(PolyBank *b)
         b->d_cbankT16h = b->d_cbankT16h_base + pad * L;
         b->d_cbankT16l = b->d_cbankT16l_base + pad * L;
     }
-    std::vector<int> order(p.order, p.order + Q), single(p.single_tap, p.single_tap + L);
+    std::vector<int> order(p.order, p.order + Q), single(L);
+    for (size_t r = 0; r < L; ++r) single[r] = p.single_tap[r % L0];
     if (upload(&b->d_order, order) || upload(&b->d_single, single)) return -1;
 
     if (p.L == 1 && p.shift == 0 && p.frame_len == 0 && p.single_tap[0] < 0) {
@@ -625,7 +634,8 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.o0 = b->produced;
     a.n_out = outs;
     a.in0 = b->consumed;
-    a.L = p.L; a.M = p.M; a.ctaps = p.ctaps; a.shift = p.shift; a.frame_len = p.frame_len;
+    a.L = p.L * b->rep; a.M = p.M * b->rep;          // repeated rows: the same outputs (poly_upload_plan)
+    a.ctaps = p.ctaps; a.shift = p.shift; a.frame_len = p.frame_len;
     a.acc = b->acc;
     a.gain = b->gain;
     a.guard_thr = b->guard_thr;
