@@ -365,6 +365,45 @@ def run_cuda(args):
     ach_gbs = outs_per_step * bytes_per_out / (ms_local * 1e-3) / 1e9
     ach_tf = outs_per_step * flop_per_out / (ms_local * 1e-3) / 1e12
 
+    # ---- optional exchange step: every rank's output to every rank with NCCL over NVLink ----
+    # The path itself needs no collective (independent channels / segments that carry their own halo); a job that
+    # wants the whole result on one device adds this gather.  It is reported separately, never inside the timed step.
+    gather = None
+    if world > 1 and not args.no_gather:
+        try:
+            cnt = torch.tensor([dy.numel()], device="cuda", dtype=torch.int64)
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+            m = int(cnt.item())                                      # time segments may differ by one work item
+            es_out = dy.element_size()
+            if world * m * es_out > 48e9:
+                gather = {"skipped": f"gathered result would be {world * m * es_out / 1e9:.1f} GB per rank"}
+            else:
+                flat = dy.reshape(-1)
+                if flat.numel() < m:
+                    flat = torch.cat([flat, flat.new_zeros(m - flat.numel())])
+                full = torch.empty(world * m, dtype=dy.dtype, device="cuda")
+                dist.all_gather_into_tensor(full, flat)              # warm-up: communicator channels, buffers
+                torch.cuda.synchronize()
+                dist.barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                dist.all_gather_into_tensor(full, flat)
+                g1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([g0.elapsed_time(g1)], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                gms = float(t.item())
+                own_ok = bool(torch.equal(full[rank * m: rank * m + dy.numel()], dy.reshape(-1)))
+                gather = {"collective": "NCCL all-gather of the planar outputs (torch.distributed.all_gather_into_tensor)",
+                          "ms": gms, "bytes_per_rank": m * es_out, "gathered_bytes": world * m * es_out,
+                          "algbw_gbs": world * m * es_out / (gms * 1e-3) / 1e9,
+                          "busbw_gbs": (world - 1) * m * es_out / (gms * 1e-3) / 1e9,
+                          "own_slice_intact": own_ok, "compute_ms_per_step": ms_step,
+                          "note": "not part of the timed step; the filter itself needs no collective; shards land rank-major"}
+                del full
+        except Exception as ex:                     # noqa: BLE001
+            gather = {"error": repr(ex)}
+
     # ---- end to end through the C-ABI with host buffers ----
     e2e = None
     try:
@@ -476,6 +515,8 @@ def run_cuda(args):
                      "fma_pipe": fma_pipe},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
     }
+    if gather is not None:
+        line["gather"] = gather
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -538,6 +579,7 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "direct", "fft"],
                     help="FIR kernel family (c2/c5): auto = overlap-save where it applies, else direct form")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL all-gather of the outputs at N > 1")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.workload == "c1":
