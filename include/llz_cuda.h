@@ -54,11 +54,12 @@ enum {                                      /* FIR sample type + arithmetic */
                                  partial sums every 128 taps                                        */
 };
 enum {                                      /* FIR kernel family (tolerance-mode banks only; STRICT is always direct) */
-    LLZ_CUDA_FIR_ALGO_AUTO   = 0, /* overlap-save for 48..6145 taps, direct form otherwise (default)         */
+    LLZ_CUDA_FIR_ALGO_AUTO   = 0, /* overlap-save for 48..12289 taps, direct form otherwise (default)        */
     LLZ_CUDA_FIR_ALGO_DIRECT = 1, /* register-blocked sliding MAC: 2*N flop per output                       */
     LLZ_CUDA_FIR_ALGO_FFT    = 2, /* overlap-save in the bank's own type: a 1024-point transform per warp up
                                      to 544 taps (~35 FMA-pipe instructions per output at 127 taps), an
-                                     8192-point transform per CTA up to 6145 taps (~81 at 4095 taps);
+                                     8192-point transform per CTA up to 4608 taps, a 16384-point transform
+                                     per cluster of two CTAs up to 12289 taps (~57 at 4095 taps);
                                      |err| ~1e-15 (f64) / ~3e-7 (f32) of full scale against the direct sum,
                                      not bit-identical                                                      */
 };
@@ -78,11 +79,11 @@ unsigned long llz_cuda_fir_bank_init_taps(const double *h, int flt_len, int n_ch
 void          llz_cuda_fir_bank_uninit(unsigned long handle);
 
 int llz_cuda_fir_bank_flt_len(unsigned long handle);
-/* choose the kernel family; fails (-1) for FFT on a STRICT bank or beyond 6145 taps */
+/* choose the kernel family; fails (-1) for FFT on a STRICT bank or beyond 12289 taps */
 int llz_cuda_fir_bank_set_algo(unsigned long handle, int algo);
 /* the family the next _run will use: LLZ_CUDA_FIR_ALGO_DIRECT or LLZ_CUDA_FIR_ALGO_FFT */
 int llz_cuda_fir_bank_get_algo(unsigned long handle);
-/* samples per work item of the kernel the next _run will use: 2*(1024 - halo) or 2*(8192 - halo) for the
+/* samples per work item of the kernel the next _run will use: 2*(1024 - halo), 2*(8192 - halo) or 2*(16384 - halo) for the
  * overlap-save kernels, 1 for the direct form.  A stream cut at multiples of this length (time segments with
  * their flt_len-1 halo, pipeline chunks) reproduces the one-shot result bit for bit.                        */
 long long llz_cuda_fir_bank_block_len(unsigned long handle);

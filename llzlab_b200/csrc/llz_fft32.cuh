@@ -277,6 +277,73 @@ LLZ_HD void dft8_twisted(T (&re)[32], T (&im)[32], C e0, C e1, C e2, C e3)
     for (int i = 0; i < 8; ++i) { re[O + i] = ar[i]; im[O + i] = ai[i]; }
 }
 
+// ---- 16-point transforms (the outer radix of the 16384-point transform, llz_cuda_fir_fft16k.cu) ----------
+LLZ_HD constexpr int brev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
+
+// X[k] = sum_a x[a] * exp(-+ 2*pi*i*a*k/16) on the slice v[O + a], a < 16; natural order in and out
+template <typename T, bool INV, int O>
+LLZ_HD void dft16(T (&re)[32], T (&im)[32])
+{
+    T ar[16], ai[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ar[i] = re[O + brev4(i)]; ai[i] = im[O + brev4(i)]; }
+#pragma unroll
+    for (int b = 0; b < 16; b += 2) bfly32<T, INV>(ar[b], ai[b], ar[b + 1], ai[b + 1], 0);
+#pragma unroll
+    for (int b = 0; b < 16; b += 4) {
+        bfly32<T, INV>(ar[b], ai[b], ar[b + 2], ai[b + 2], 0);
+        bfly32<T, INV>(ar[b + 1], ai[b + 1], ar[b + 3], ai[b + 3], 8);
+    }
+#pragma unroll
+    for (int b = 0; b < 16; b += 8)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bfly32<T, INV>(ar[b + k], ai[b + k], ar[b + k + 4], ai[b + k + 4], 4 * k);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bfly32<T, INV>(ar[k], ai[k], ar[k + 8], ai[k + 8], 2 * k);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { re[O + i] = ar[i]; im[O + i] = ai[i]; }
+}
+
+// X[k] = sum_a (x[a] * w^a) * exp(-+ 2*pi*i*a*k/16), twiddle folded in as in dft32_twisted.  e[0] = (cos, sin) of the
+// len-2 twiddle w^8; e[1] = (cos, tan) of w^4; e[2..3] of w^2 * W_8^{0,1}; e[4..7] of w * W_16^{0..3}
+template <typename T, bool INV, int O, typename C>
+LLZ_HD void dft16_twisted(T (&re)[32], T (&im)[32], const C (&e)[8])
+{
+    T ar[16], ai[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ar[i] = re[O + brev4(i)]; ai[i] = im[O + brev4(i)]; }
+    {
+        const T c = e[0].x, s = INV ? -e[0].y : e[0].y;
+#pragma unroll
+        for (int b = 0; b < 16; b += 2) {
+            const T ur = ar[b], ui = ai[b], vr = ar[b + 1], vi = ai[b + 1];
+            ar[b]     = fma_t<T>(s, vi, fma_t<T>(c, vr, ur));
+            ai[b]     = fma_t<T>(-s, vr, fma_t<T>(c, vi, ui));
+            ar[b + 1] = fma_t<T>(-s, vi, fma_t<T>(-c, vr, ur));
+            ai[b + 1] = fma_t<T>(s, vr, fma_t<T>(-c, vi, ui));
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 16; b += 4) {
+        bfly_tan<T, INV, false>(ar[b], ai[b], ar[b + 2], ai[b + 2], e[1].x, e[1].y);
+        bfly_tan<T, INV, true>(ar[b + 1], ai[b + 1], ar[b + 3], ai[b + 3], e[1].x, e[1].y);
+    }
+#pragma unroll
+    for (int b = 0; b < 16; b += 8)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            bfly_tan<T, INV, false>(ar[b + k], ai[b + k], ar[b + k + 4], ai[b + k + 4], e[2 + k].x, e[2 + k].y);
+            bfly_tan<T, INV, true>(ar[b + k + 2], ai[b + k + 2], ar[b + k + 6], ai[b + k + 6], e[2 + k].x, e[2 + k].y);
+        }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        bfly_tan<T, INV, false>(ar[k], ai[k], ar[k + 8], ai[k + 8], e[4 + k].x, e[4 + k].y);
+        bfly_tan<T, INV, true>(ar[k + 4], ai[k + 4], ar[k + 12], ai[k + 12], e[4 + k].x, e[4 + k].y);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { re[O + i] = ar[i]; im[O + i] = ai[i]; }
+}
+
 // ---- host-side tables ---------------------------------------------------------------------------
 // tab[e][l], e < 16, l < 32: the folded twiddles of dft32_twisted for lane l, interleaved pairs (see above)
 inline void fft1024_make_twist_table(double *tab /* 16*32*2 */)
@@ -369,6 +436,67 @@ inline void fft8k_make_spectrum(const double *h, int ntaps, double *H /* 8192*2 
         const int b = k % 8, khi = k / 8, k2 = khi % kFftR, k1 = khi / kFftR;
         H[2 * ((b * kFftR + k1) * kFftR + k2)] = (double)(sr / kFft8kN);
         H[2 * ((b * kFftR + k1) * kFftR + k2) + 1] = (double)(si / kFft8kN);
+    }
+    delete[] ct;
+    delete[] st;
+}
+
+// ---- tables of the 16384-point transform (16 x 1024 across a cluster of two CTAs, llz_cuda_fir_fft16k.cu) ------
+constexpr int kFft16kN = 16384;
+
+// tab2[b][e][k2], b < 16: folded twiddles of the second DFT-32 of residue b (base exp(-2*pi*i*(16*k2 + b)/16384))
+inline void fft16k_make_twist2(double *tab /* 16*16*32*2 */)
+{
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int b = 0; b < 16; ++b) {
+        int e = 0;
+        for (int len = 2; len <= 32; len <<= 1) {
+            const int nk = len == 2 ? 1 : len / 4;
+            for (int k = 0; k < nk; ++k, ++e)
+                for (int l = 0; l < kFftR; ++l) {
+                    const long double th = two_pi * (long double)(16 * l + b + 512 * k) / (long double)(512 * len);
+                    double *o = tab + 2 * ((b * kTwistEntries + e) * kFftR + l);
+                    o[0] = (double)cosl(th);
+                    o[1] = (double)(len == 2 ? sinl(th) : tanl(th));
+                }
+        }
+    }
+}
+
+// tab3[q][e][t], q < 2, e < 8, t < 512: folded twiddles of the last 16-point transform for n_lo = t + 512 q
+// (base exp(-2*pi*i*n_lo/16384)); e as in dft16_twisted
+inline void fft16k_make_twist3(double *tab /* 2*8*512*2 */)
+{
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
+    for (int q = 0; q < 2; ++q)
+        for (int t = 0; t < 512; ++t) {
+            const long double base = (long double)(t + 512 * q) / (long double)kFft16kN;        // turns
+            const long double th[8] = {base * 8, base * 4, base * 2, base * 2 + 0.125L,
+                                       base, base + 0.0625L, base + 0.125L, base + 0.1875L};
+            for (int e = 0; e < 8; ++e) {
+                double *o = tab + 2 * ((q * 8 + e) * 512 + t);
+                o[0] = (double)cosl(two_pi * th[e]);
+                o[1] = (double)(e == 0 ? sinl(two_pi * th[e]) : tanl(two_pi * th[e]));
+            }
+        }
+}
+
+// H[b][k1][k2] = (1/16384) * sum_n h[n] * exp(-2*pi*i*n*k/16384),  k = b + 16*(k2 + 32*k1)
+inline void fft16k_make_spectrum(const double *h, int ntaps, double *H /* 16384*2 */)
+{
+    long double *ct = new long double[kFft16kN], *st = new long double[kFft16kN];
+    const long double w = -2.0L * 3.14159265358979323846264338327950288L / (long double)kFft16kN;
+    for (int i = 0; i < kFft16kN; ++i) { ct[i] = cosl(w * i); st[i] = sinl(w * i); }
+    for (int k = 0; k < kFft16kN; ++k) {
+        long double sr = 0.0L, si = 0.0L;
+        for (int n = 0; n < ntaps; ++n) {
+            const int idx = (int)(((long long)n * k) % kFft16kN);
+            sr += (long double)h[n] * ct[idx];
+            si += (long double)h[n] * st[idx];
+        }
+        const int b = k % 16, khi = k / 16, k2 = khi % kFftR, k1 = khi / kFftR;
+        H[2 * ((b * kFftR + k1) * kFftR + k2)] = (double)(sr / kFft16kN);
+        H[2 * ((b * kFftR + k1) * kFftR + k2) + 1] = (double)(si / kFft16kN);
     }
     delete[] ct;
     delete[] st;

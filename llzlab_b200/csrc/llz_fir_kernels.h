@@ -36,6 +36,8 @@ constexpr int kFirFftMinTapsAuto = 48;   // below this the direct kernel is at l
 constexpr int kFirFftMaxTaps = 897;      // leaves B = 1024 - halo >= 128 valid outputs per block
 constexpr int kFirFft8kMinTapsAuto = 545;  // from here on the 8192-point kernel wins (profiles/r01_crossover_fft.txt)
 constexpr int kFirFft8kMaxTaps = 6145;   // leaves B = 8192 - halo >= 2048
+constexpr int kFirFft16kMinTapsAuto = 4609;  // from here on the 16384-point cluster kernel wins (profiles/r01_crossover_fft16k.txt)
+constexpr int kFirFft16kMaxTaps = 12289; // leaves B = 16384 - halo >= 4096
 
 template <typename T>
 struct FirFftLaunch {
@@ -63,5 +65,9 @@ int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
 // 8192-point variant for long filters; a.H is the 8192-bin spectrum in the kernel's [8][32][32] layout
 template <typename T>
 int fir_fft8k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
+
+// 16384-point variant (cluster of two CTAs); a.H is [16][32][32], a.tw2 [16][16][32], a.tw3 [2][8][512]
+template <typename T>
+int fir_fft16k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
 
 }  // namespace llz

@@ -167,7 +167,7 @@ struct FirBank {
     void *d_fft_H = nullptr, *d_fft_tw = nullptr;
     void *d_fft_tw2 = nullptr, *d_fft_tw3 = nullptr;     // 8192-point kernel (llz_cuda_fir_fft8k.cu)
     void *d_fft_Hx = nullptr, *d_fft_twx = nullptr;      // float banks: tables with duplicated values (packed FP32)
-    bool fft8k = false;
+    int fft_size = 0;            // transform length the tables were built for: 1024, 8192 or 16384
     Pipeline pipe;
     // drop-in (mono, host buffers)
     int frame_len = 0;
@@ -281,7 +281,7 @@ unsigned long fir_bank_create(double *h, int flt_len, int n_channels, int dtype)
 // the environment variable LLZ_FIR_ALGO=direct|fft overrides AUTO (tuning / A-B measurements).
 int fir_effective_algo(const FirBank *b)
 {
-    const bool fft_ok = b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len <= kFirFft8kMaxTaps;
+    const bool fft_ok = b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len <= kFirFft16kMaxTaps;
     int algo = b->algo;
     if (algo == LLZ_CUDA_FIR_ALGO_AUTO) {
         const char *env = getenv("LLZ_FIR_ALGO");
@@ -292,19 +292,23 @@ int fir_effective_algo(const FirBank *b)
         algo = (fft_ok && b->flt_len >= kFirFftMinTapsAuto) ? LLZ_CUDA_FIR_ALGO_FFT : LLZ_CUDA_FIR_ALGO_DIRECT;
     if (algo == LLZ_CUDA_FIR_ALGO_FFT && !fft_ok) {
         llz_set_error("the overlap-save FIR kernels are not available for this bank (strict arithmetic or > %d taps)",
-                      kFirFft8kMaxTaps);
+                      kFirFft16kMaxTaps);
         return -1;
     }
     return algo;
 }
 
-// transform length the overlap-save path uses for this bank: 1024 (one warp per item) or 8192 (one CTA per item)
-bool fir_use_fft8k(const FirBank *b)
+// transform length the overlap-save path uses for this bank: 1024 (one warp per item), 8192 (one CTA per item) or
+// 16384 (one cluster of two CTAs per item); LLZ_FIR_FFT_SIZE overrides the choice where the tap count allows it
+int fir_fft_size(const FirBank *b)
 {
     const char *env = getenv("LLZ_FIR_FFT_SIZE");
-    if (env && atoi(env) == 8192) return true;
-    if (env && atoi(env) == 1024 && b->flt_len <= kFirFftMaxTaps) return false;
-    return b->flt_len >= kFirFft8kMinTapsAuto;
+    const int want = env ? atoi(env) : 0;
+    if (want == 16384) return 16384;
+    if (want == 8192 && b->flt_len <= kFirFft8kMaxTaps) return 8192;
+    if (want == 1024 && b->flt_len <= kFirFftMaxTaps) return 1024;
+    if (b->flt_len >= kFirFft16kMinTapsAuto) return 16384;
+    return b->flt_len >= kFirFft8kMinTapsAuto ? 8192 : 1024;
 }
 
 int upload_as(void **dst, const std::vector<double> &src, bool f32)
@@ -333,12 +337,18 @@ int fir_fft_tables(FirBank *b)
 {
     if (b->d_fft_H) return 0;
     const bool f32 = b->dtype == LLZ_CUDA_F32;
-    b->fft8k = fir_use_fft8k(b);
+    b->fft_size = fir_fft_size(b);
     std::vector<double> tw(2 * kTwistEntries * kFftR);
     fft1024_make_twist_table(tw.data());
     if (upload_as(&b->d_fft_tw, tw, f32) != 0) return -1;
-    std::vector<double> H(2 * (b->fft8k ? kFft8kN : kFftN));
-    if (b->fft8k) {
+    std::vector<double> H(2 * (size_t)b->fft_size);
+    if (b->fft_size == 16384) {
+        std::vector<double> t2(2 * 16 * kTwistEntries * kFftR), t3(2 * 16 * 512);
+        fft16k_make_twist2(t2.data());
+        fft16k_make_twist3(t3.data());
+        if (upload_as(&b->d_fft_tw2, t2, f32) != 0 || upload_as(&b->d_fft_tw3, t3, f32) != 0) return -1;
+        fft16k_make_spectrum(b->h_host, b->flt_len, H.data());
+    } else if (b->fft_size == 8192) {
         std::vector<double> t2(2 * 8 * kTwistEntries * kFftR), t3(2 * 16 * 256);
         fft8k_make_twist2(t2.data());
         fft8k_make_twist3(t3.data());
@@ -391,7 +401,9 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
         f.twx = static_cast<const T *>(b->d_fft_twx);
         f.tw2 = static_cast<const T *>(b->d_fft_tw2);
         f.tw3 = static_cast<const T *>(b->d_fft_tw3);
-        if ((b->fft8k ? fir_fft8k_launch<T>(f, cc, st) : fir_fft_launch<T>(f, cc, st)) != 0) return -1;
+        const int rc = b->fft_size == 16384 ? fir_fft16k_launch<T>(f, cc, st)
+                       : b->fft_size == 8192 ? fir_fft8k_launch<T>(f, cc, st) : fir_fft_launch<T>(f, cc, st);
+        if (rc != 0) return -1;
     } else if (fir_launch<T>(a, cc, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) {
         return -1;
     }
@@ -766,7 +778,9 @@ extern "C" int llz_cuda_fir_bank_get_algo(unsigned long handle)
 long long fir_block_len(const FirBank *b)
 {
     if (fir_effective_algo(b) != LLZ_CUDA_FIR_ALGO_FFT) return 1;
-    if (fir_use_fft8k(b)) return 2LL * (kFft8kN - (b->flt_len - 1 + 255) / 256 * 256);
+    const int size = b->fft_size ? b->fft_size : fir_fft_size(b);
+    if (size == 16384) return 2LL * (kFft16kN - (b->flt_len - 1 + 511) / 512 * 512);
+    if (size == 8192) return 2LL * (kFft8kN - (b->flt_len - 1 + 255) / 256 * 256);
     return 2LL * (kFftN - (b->flt_len - 1 + 31) / 32 * 32);
 }
 

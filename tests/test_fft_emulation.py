@@ -46,3 +46,16 @@ def test_cta_level_8192_point_overlap_save(emu8k, ntaps, f32):
     r = subprocess.run([emu8k, str(ntaps), str(f32)], capture_output=True, text=True)
     err = float(r.stdout.strip())
     assert r.returncode == 0 and err < (2e-6 if f32 else 1e-14), (ntaps, f32, err)
+
+
+@pytest.fixture(scope="module")
+def emu16k(tmp_path_factory):
+    return build(tmp_path_factory, "fft16k_emulate")
+
+
+@pytest.mark.parametrize("ntaps", [2305, 4095, 12289])
+@pytest.mark.parametrize("f32", [0, 1])
+def test_cluster_level_16384_point_overlap_save(emu16k, ntaps, f32):
+    r = subprocess.run([emu16k, str(ntaps), str(f32)], capture_output=True, text=True)
+    err = float(r.stdout.strip())
+    assert r.returncode == 0 and err < (2e-6 if f32 else 1e-14), (ntaps, f32, err)

@@ -57,8 +57,9 @@ def test_c5_full_length_one_channel(zlib, port, cuda):
         got = dy[t0:t0 + 200].cpu().numpy()
         assert np.abs(got - want).max() <= 1e-12, t0
     # the same stream in two time segments with halo (C5's multi-GPU plan): the overlap-save kernel (AUTO picks the
-    # 8192-point one here) agrees to rounding -- its block grid starts at the segment -- and the direct kernel bit for bit
-    assert bank.algo == zlib.FIR_FFT and bank.block_len == 8192
+    # 16384-point one here) agrees to rounding -- its block grid starts at the segment -- and the direct kernel bit for bit
+    blk = bank.block_len
+    assert bank.algo == zlib.FIR_FFT and blk == 2 * (16384 - 4096)      # the 16384-point cluster kernel
     seg = zlib.shard_fir_segments(n, N, 2, 1)
     bank.reset()
     bank.set_history(dx.data_ptr() + 8 * (seg.in_start - seg.halo), n)
@@ -67,11 +68,11 @@ def test_c5_full_length_one_channel(zlib, port, cuda):
     torch.cuda.synchronize()
     assert (tail - dy[seg.out_start:seg.out_start + 1_000_000]).abs().max().item() <= 1e-12
     # ... and bit for bit when the cut is a multiple of the kernel's work-item length (bench.py's plan for C5)
-    aseg = zlib.shard_fir_segments_aligned(n, N, bank.block_len, 8, 5)
-    assert aseg.in_start % 8192 == 0 and aseg.halo == N - 1
+    aseg = zlib.shard_fir_segments_aligned(n, N, blk, 8, 5)
+    assert aseg.in_start % blk == 0 and aseg.halo == N - 1
     bank.reset()
     bank.set_history(dx.data_ptr() + 8 * (aseg.in_start - aseg.halo), n)
-    m = 8192 * 100
+    m = blk * 40
     bank.run(dx.data_ptr() + 8 * aseg.in_start, n, tail, m, m)
     torch.cuda.synchronize()
     assert torch.equal(tail[:m], dy[aseg.out_start:aseg.out_start + m])

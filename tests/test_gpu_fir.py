@@ -68,7 +68,7 @@ def test_bank_f64_all_tap_counts(zlib, port, cuda, N):
     want = oracle_bank(port, h, x)
     dx = torch.from_numpy(x).cuda()
     cases = [(zlib.F64_STRICT, zlib.FIR_AUTO, True), (zlib.F64, zlib.FIR_DIRECT, False)]
-    if N <= 6145:
+    if N <= 12289:
         cases.append((zlib.F64, zlib.FIR_FFT, False))
     for dtype, algo, exact in cases:
         bank = zlib.FirBank(C_, dtype, taps=h, algo=algo)
@@ -174,6 +174,7 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
         fbank = zlib.FirBank(C_, zlib.F64, taps=taps, algo=zlib.FIR_FFT)
         blk = fbank.block_len
         assert blk == (2 * (1024 - 256) if N2 == 255 else 2 * (8192 - 1024))
+        assert blk == fbank.block_len
         one2 = torch.empty_like(dx2)
         fbank.run(dx2, n2, one2, n2, n2)
         want2 = oracle_bank(port, taps, x2)
@@ -196,13 +197,16 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
         fbank.close()
 
 
-@pytest.mark.parametrize("N", [898, 2049, 4095, 6145])
-def test_fft8k_bank_interior_and_edge_items(zlib, port, cuda, N):
-    """8192-point overlap-save kernel (one CTA per item): several interior items, history splice, ragged end"""
+@pytest.mark.parametrize("N,size", [(898, 8192), (2049, 8192), (4095, 8192), (6145, 8192),
+                                    (2305, 16384), (4095, 16384), (8191, 16384), (12289, 16384)])
+def test_fft8k_16k_bank_interior_and_edge_items(zlib, port, cuda, monkeypatch, N, size):
+    """8192-point (one CTA per item) and 16384-point (one two-CTA cluster per item, distributed shared memory)
+    overlap-save kernels: several interior items, history splice, ragged end"""
     torch = cuda
+    monkeypatch.setenv("LLZ_FIR_FFT_SIZE", str(size))
     rng = np.random.default_rng(N)
     h = rng.standard_normal(N) / N ** 0.5
-    C_, n = 3, 70001
+    C_, n = 3, 70001 if size == 8192 else 150001
     x = rng.uniform(-1, 1, (C_, n))
     want = oracle_bank(port, h, x)
     scale = max(np.abs(h).sum(), 1.0)
@@ -210,6 +214,7 @@ def test_fft8k_bank_interior_and_edge_items(zlib, port, cuda, N):
                                   (zlib.F32, torch.float32, np.float32, TOL_F32_ABS * scale)):
         dx = torch.from_numpy(x.astype(npdt)).cuda()
         bank = zlib.FirBank(C_, dtype, taps=h, algo=zlib.FIR_FFT)
+        assert bank.block_len == 2 * (size - (N - 1 + size // 32 - 1) // (size // 32) * (size // 32))
         dy = torch.full((C_, n + 64), 7.0, dtype=tdt, device="cuda")
         bank.run(dx, n, dy, n + 64, n)
         # second call continues the stream from the stored history: same samples again -> history splice
@@ -301,10 +306,11 @@ def test_fft_f32_packed_kernel_matches_scalar_kernel_bits(zlib, port, cuda, monk
 
 
 def test_fft_algo_selection(zlib, cuda):
-    """AUTO picks overlap-save for tolerance-mode banks of 48..6145 taps; STRICT and longer filters stay direct"""
+    """AUTO picks overlap-save for tolerance-mode banks of 48..12289 taps; STRICT and longer filters stay direct"""
     h = np.ones(127) / 127
     for dtype, N, want in ((zlib.F64, 127, zlib.FIR_FFT), (zlib.F32, 127, zlib.FIR_FFT), (zlib.F64, 47, zlib.FIR_DIRECT),
-                           (zlib.F64, 898, zlib.FIR_FFT), (zlib.F64, 4095, zlib.FIR_FFT), (zlib.F64, 6146, zlib.FIR_DIRECT),
+                           (zlib.F64, 898, zlib.FIR_FFT), (zlib.F64, 4095, zlib.FIR_FFT), (zlib.F64, 6146, zlib.FIR_FFT),
+                           (zlib.F64, 12290, zlib.FIR_DIRECT),
                            (zlib.F64_STRICT, 127, zlib.FIR_DIRECT)):
         b = zlib.FirBank(2, dtype, taps=np.ones(N) / N)
         assert b.algo == want, (dtype, N)
@@ -314,7 +320,7 @@ def test_fft_algo_selection(zlib, cuda):
     assert zlib.lib().llz_cuda_fir_bank_set_algo(b.handle, 9) == -1
     assert b.algo == zlib.FIR_DIRECT
     b.close()
-    b = zlib.FirBank(2, zlib.F64, taps=np.ones(6146) / 6146)
+    b = zlib.FirBank(2, zlib.F64, taps=np.ones(12290) / 12290)
     assert zlib.lib().llz_cuda_fir_bank_set_algo(b.handle, zlib.FIR_FFT) == -1
     b.close()
 
