@@ -192,6 +192,11 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
         };
         if (rank == 0) push(std::integral_constant<int, 0>{}); else push(std::integral_constant<int, 1>{});
         cluster_sync_ra();
+        // warps 4..7 trail their scheduler partners 0..3 by about one transform phase (see llz_cuda_fir_fft8k.cu)
+        if (a.skew > 0 && warp >= 4) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < a.skew) { }
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const C v = slice[j * kFftR + lane]; re[j] = v.x; im[j] = v.y; }
         __syncwarp();
@@ -329,6 +334,8 @@ int fir_fft16k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     }
     const char *pf = getenv("LLZ_FFT_PREFETCH");
     a.prefetch = (pf && *pf) ? atoi(pf) : 1;
+    const char *sk = getenv("LLZ_FFT16K_SKEW");
+    a.skew = (sk && *sk) ? atoi(sk) : (sizeof(T) == 8 ? 1300 : 0);     // f64 +5 %, f32 none (profiles/r01_sweep_skew.txt)
     if (fir_fft16k_run<T, false>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
     return fir_fft16k_run<T, true>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
 }

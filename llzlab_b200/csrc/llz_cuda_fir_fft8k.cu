@@ -190,6 +190,13 @@ fir_fft8k_kernel(FirFftLaunch<T> a)
                 xbuf[(b * kFftR + warp + 8 * q) * kFftR + lane] = v;
             }
         __syncthreads();
+        // Warps w and w + 4 share a scheduler and leave the barrier in the same phase, so they load together and then
+        // queue on the FMA pipe together.  Holding warps 4..7 back by about one transform phase lets one warp of every
+        // scheduler move data while the other transforms (measured: f64 +7..8 %, f32 +3 %; profiles/r01_sweep_skew.txt).
+        if (a.skew > 0 && warp >= 4) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < a.skew) { }
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const C v = slice[j * kFftR + lane]; re[j] = v.x; im[j] = v.y; }
         __syncwarp();
@@ -328,6 +335,8 @@ int fir_fft8k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     }
     const char *pf = getenv("LLZ_FFT_PREFETCH");
     a.prefetch = (pf && *pf) ? atoi(pf) : 1;
+    const char *sk = getenv("LLZ_FFT8K_SKEW");
+    a.skew = (sk && *sk) ? atoi(sk) : (sizeof(T) == 8 ? 1300 : 1500);
     const char *st = getenv("LLZ_FFT_STAGE");
     const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 && (a.x_stride * sizeof(T)) % 16 == 0;
     // measured on C5: staging gains 2.5 % in f64 (one CTA per SM) and loses 4 % in f32 (two CTAs per SM hide the loads)

@@ -55,6 +55,7 @@ struct FirFftLaunch {
     // filled in by fir_fft_launch: item i of a channel is pair first_pair + i, skipping [gap_start, gap_start + gap_len)
     int halo, B;           // halo = N-1 rounded up to 32; B = 1024 - halo valid outputs per block
     int prefetch;          // L2 prefetch of the warp's next item
+    int skew;              // 8192- / 16384-point kernels: cycles by which warps 4..7 of a CTA trail warps 0..3 after the first exchange
     int n_channels;
     long long first_pair, items_per_channel, gap_start, gap_len;
 };
