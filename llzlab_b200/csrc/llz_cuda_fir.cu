@@ -4,9 +4,9 @@
 // (libllzfilter/llz_fir.c:411-426, 547-584):   y[c][t] = sum_{i<N} h[i] * x[c][t-i].
 //
 // Grid: x = time tiles of TILE = 256*R outputs, y = channels.  One CTA stages its
-// HALO + TILE input samples (HALO = padded tap count) and the taps in shared memory -- interior
-// tiles with a single TMA bulk copy each (cp.async.bulk + mbarrier), edge tiles (stream start,
-// history splice, ragged end) with a guarded scalar fill -- then every thread runs the
+// HALO + TILE input samples (HALO = padded tap count) and the taps in shared memory -- a single
+// TMA bulk copy each (cp.async.bulk + mbarrier); on edge tiles (stream start, history splice,
+// ragged end) the threads fill only the fringes outside the call's input -- then every thread runs the
 // register-blocked sliding MAC of llz_sliding_mac.cuh over its R outputs and stores them with
 // 16-byte vector stores.
 //
@@ -42,32 +42,43 @@ fir_tile_kernel(FirLaunch<T> a)
     const int span = halo + TILE;
 
     // ---- stage taps + input span --------------------------------------------------------------
-    const bool interior = a.vec_ok && xc != nullptr && t0 >= halo && t0 + TILE <= a.n;
-    if (interior) {
+    // Sample e of the span is stream position g0 + e.  The run that lies inside this call's input arrives by one TMA
+    // bulk copy (for an interior tile that is the whole span), the taps by another; only the fringes of an edge tile
+    // -- the history before x[0], zeros past the end, an odd last sample -- are filled by the threads.  (Edge tiles
+    // used to be filled sample by sample; a drop-in frame is mostly edge tiles.)
+    {
+        constexpr int VU = 16 / (int)sizeof(T);
+        const long long g0 = t0 - halo;                     // a multiple of VU: TILE and the padded tap count are
+        const long long lo = g0 > 0 ? g0 : 0;
+        const long long hi = (g0 + span < a.n) ? g0 + span : a.n;
+        long long lo_al = lo, hi_al = hi & ~(long long)(VU - 1);
+        const bool tma_x = a.vec_ok && xc != nullptr && hi_al > lo_al;
+        if (!tma_x) lo_al = hi_al = lo;
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
             const uint32_t tap_bytes = (uint32_t)(a.ntaps_pad * sizeof(T));
-            const uint32_t x_bytes = (uint32_t)(span * sizeof(T));
+            const uint32_t x_bytes = tma_x ? (uint32_t)((hi_al - lo_al) * sizeof(T)) : 0u;
             mbar_expect_tx(bar, tap_bytes + x_bytes);
             tma_bulk_g2s(taps_s, a.taps, tap_bytes, bar);
-            tma_bulk_g2s(xs, xc + (t0 - halo), x_bytes, bar);
+            if (tma_x) tma_bulk_g2s(xs + (lo_al - g0), xc + lo_al, x_bytes, bar);
         }
-        __syncthreads();          // barrier init visible to the waiters
+        const int e_lo = (int)min(max(lo_al - g0, 0LL), (long long)span);
+        const int e_hi = (int)min(max(hi_al - g0, (long long)e_lo), (long long)span);
+        if (e_lo > 0 || e_hi < span) {
+            const T *hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
+            auto sample = [&](int e) -> T {
+                const long long g = g0 + e;                 // stream position of this sample
+                if (g >= 0) return (g < a.n && xc) ? xc[g] : T(0);
+                if (hc && g >= -(long long)(a.ntaps - 1)) return hc[(a.ntaps - 1) + g];   // the flt_len-1 samples before this call
+                return T(0);
+            };
+#pragma unroll 4
+            for (int e = threadIdx.x; e < e_lo; e += kFirThreads) xs[e] = sample(e);
+#pragma unroll 4
+            for (int e = e_hi + threadIdx.x; e < span; e += kFirThreads) xs[e] = sample(e);
+        }
+        __syncthreads();          // barrier init visible to the waiters, fringes written
         mbar_wait(bar, 0);
-    } else {
-        for (int k = threadIdx.x; k < a.ntaps_pad; k += kFirThreads) taps_s[k] = a.taps[k];
-        const T *hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
-        for (int e = threadIdx.x; e < span; e += kFirThreads) {
-            const long long g = t0 - halo + e;          // stream position of this sample
-            T v = T(0);
-            if (g >= 0) {
-                if (g < a.n && xc) v = xc[g];
-            } else if (hc && g >= -(long long)(a.ntaps - 1)) {
-                v = hc[(a.ntaps - 1) + g];              // the flt_len-1 samples before this call
-            }
-            xs[e] = v;
-        }
-        __syncthreads();
     }
 
     // ---- R outputs per thread -----------------------------------------------------------------

@@ -87,25 +87,12 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
 
     // ---- stage the input span ---------------------------------------------------------------------------
-    const long long rel = S0 - a.in0;
-    const long long rel_al = rel & ~7LL;
-    const long long end_al = (rel + rawn + 7) & ~7LL;
-    const bool inside = xc != nullptr && rel >= 0 && rel + rawn <= a.n_in;
-    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
-    int raw_off = 0;
-    if (bulk) {
-        raw_off = (int)(rel - rel_al);
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
-        }
-    } else if (inside) {
-        for (int e = tid; e < rawn; e += kBankThreads) raw[e] = xc[rel + e];
-    } else {
-        for (int e = tid; e < rawn; e += kBankThreads) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
-    }
+    // cycles of this tile that hold outputs of the call, and the samples they read
+    const long long jc_last = (a.o0 + a.n_out - 1) / L;
+    const int jv = (int)min((long long)JB, jc_last - j0 + 1);
+    const int need = min(rawn, (jv - 1) * M + cspan + Q);
+    bool bulk;
+    const int raw_off = poly_stage_span<kBankThreads>(a, xc, hc, S0, need, raw, bar, tid, &bulk);
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&s_full[i], kBankThreads);
@@ -307,19 +294,25 @@ poly_bank_kernel(PolyLaunch a, BankGeom geo)
 // and one 8-byte vector of 4 int16 B values (X'[k0 + lane%4][n0 + 4*(lane/4) .. +4]); n-tile `ni` of a warp owns the
 // cycles n0 + 4*col + ni, so those four samples are the thread's B operand for ni = 0..3.  Row pitches of G' (PB + 4
 // doubles) and X' (JB + 8 int16) make both loads bank-conflict-free.
+//
+// WN = warps along the cycle axis (4, 2 or 1: CTA tile 64 phases x 128 / 64 / 32 cycles, 256 / 128 / 64 threads).  The
+// narrow tiles exist for small calls -- one drop-in frame of config C1 is 160 phases x 160 cycles, six 64 x 128 tiles
+// on 148 SMs -- where the launch is latency-bound and more, smaller CTAs finish sooner (launch_bank_dmma picks).
 constexpr int kDmmaThreads = 256;
-constexpr int kDPB = 64, kDJB = 128;                             // CTA tile: phases x cycles
+constexpr int kDPB = 64, kDJB = 128;                             // CTA tile: phases x cycles (WN = 4; also the fp16 variant's)
 constexpr int kGP = kDPB + 4;                                    // G' row pitch in doubles  (== 4 mod 16)
-constexpr int kXP = kDJB + 8;                                    // X' row pitch in int16    (== 4 words mod 32)
+template <int WN>
+struct DmmaXP { static constexpr int value = WN == 4 ? 136 : 72; };   // X' row pitch in int16 (== 4 words mod 32)
 
-template <int KC>
-constexpr size_t dmma_stage_bytes() { return (size_t)KC * (kGP * 8 + kXP * 2); }
+template <int KC, int WN>
+constexpr size_t dmma_stage_bytes() { return (size_t)KC * (kGP * 8 + DmmaXP<WN>::value * 2); }
 
-template <int KC, int MODE>
-__global__ void __launch_bounds__(kDmmaThreads, 2)
+template <int KC, int MODE, int WN>
+__global__ void __launch_bounds__(64 * WN, 8 / WN)
 poly_bank_dmma_kernel(PolyLaunch a, BankGeom geo)
 {
-    constexpr int PB = kDPB, JB = kDJB, NT = kDmmaThreads;
+    constexpr int PB = kDPB, JB = 32 * WN, NT = 64 * WN, kXP = DmmaXP<WN>::value;
+    static_assert(WN == 4 || WN == 2 || WN == 1, "cycle-axis warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *Gs = reinterpret_cast<double *>(smem_raw + 16);               // [kStages][KC][kGP]
@@ -329,7 +322,7 @@ poly_bank_dmma_kernel(PolyLaunch a, BankGeom geo)
     __shared__ uint64_t s_full[kStages], s_empty[kStages];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;                               // warp tile: phases [32*wm, +32) x cycles [32*wn, +32)
+    const int wm = warp / WN, wn = warp % WN;                              // warp tile: phases [32*wm, +32) x cycles [32*wn, +32)
     const int tile_p = blockIdx.x % geo.n_phase_tiles;
     const int tile_j = blockIdx.x / geo.n_phase_tiles;
     const int ch = blockIdx.y;
@@ -348,26 +341,13 @@ poly_bank_dmma_kernel(PolyLaunch a, BankGeom geo)
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
 
-    // ---- stage the input span (as in poly_bank_kernel) ----
-    const long long rel = S0 - a.in0;
-    const long long rel_al = rel & ~7LL;
-    const long long end_al = (rel + rawn + 7) & ~7LL;
-    const bool inside = xc != nullptr && rel >= 0 && rel + rawn <= a.n_in;
-    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
-    int raw_off = 0;
-    if (bulk) {
-        raw_off = (int)(rel - rel_al);
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
-        }
-    } else if (inside) {
-        for (int e = tid; e < rawn; e += NT) raw[e] = xc[rel + e];
-    } else {
-        for (int e = tid; e < rawn; e += NT) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
-    }
+    // ---- stage the input span (as in poly_bank_kernel) ----  [dmma]
+    // cycles of this tile that hold outputs of the call, and the samples they read
+    const long long jc_last = (a.o0 + a.n_out - 1) / L;
+    const int jv = (int)min((long long)JB, jc_last - j0 + 1);
+    const int need = min(rawn, (jv - 1) * M + cspan + Q);
+    bool bulk;
+    const int raw_off = poly_stage_span<NT>(a, xc, hc, S0, need, raw, bar, tid, &bulk);
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&s_full[i], NT);
@@ -381,7 +361,7 @@ poly_bank_dmma_kernel(PolyLaunch a, BankGeom geo)
     const int16_t *rawp = raw + raw_off;
 
     // ---- chunk builders: thread -> one G' column (4 rows apart) and one X' column (2 rows apart) ----
-    constexpr int GR = NT / PB, GE = KC / GR;                              // 4 rows per pass
+    constexpr int GR = NT / PB, GE = KC / GR;                              // WN rows per pass
     constexpr int XR = NT / JB, XE = KC / XR;                              // 2 rows per pass
     static_assert(KC % GR == 0 && KC % XR == 0 && KC % 4 == 0, "chunk shape");
     const int gl = tid % PB, gk = tid / PB;
@@ -457,9 +437,14 @@ poly_bank_dmma_kernel(PolyLaunch a, BankGeom geo)
     }
 
     // ---- gain / guard / saturate / truncate / store: C[row = lane/4][col = 2*(lane%4) + e] of tile (mi, ni) ----
+    // Two passes: the first is straight-line (every output finished and stored, near-integer hits only noted), so its
+    // 64 outputs overlap in the pipes; the guard's reference-order recompute, which fires on ~1e-8 of the outputs, runs
+    // in a second pass that almost no thread enters.  (One pass with the recompute inside made every output a
+    // serial chain behind a branch: 11 k cycles of a 30 k-cycle drop-in frame.)
     const long long o_end = a.o0 + a.n_out;
     const bool unit_gain = a.gain == 1.0;
     int16_t *ych = a.y + (long long)ch * a.y_stride;
+    uint32_t guard_hits = 0;                                               // bit (mi*4 + ni)*2 + e
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         const int l = wm * 32 + 8 * mi + (lane >> 2);                      // phase within the tile
@@ -471,38 +456,71 @@ poly_bank_dmma_kernel(PolyLaunch a, BankGeom geo)
             for (int e = 0; e < 2; ++e) {
                 const int j = wn * 32 + 4 * (2 * (lane & 3) + e) + ni;    // cycle within the tile
                 const long long o = (j0 + j) * (long long)L + l0 + l;
-                if (!l_ok || o < a.o0 || o >= o_end) continue;
-                double v = unit_gain ? acc[mi][ni][e] : __dmul_rn(acc[mi][ni][e], a.gain);
-                if (MODE == LLZ_CUDA_ACC_F64 && st < 0 && poly_near_nonzero_integer(v, a.guard_thr)) {
-                    v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
-                    atomicAdd(a.guard_count, 1ULL);
-                }
-                ych[o - a.o0] = poly_finish(v);
+                const bool valid = l_ok && o >= a.o0 && o < o_end;
+                const double v = unit_gain ? acc[mi][ni][e] : __dmul_rn(acc[mi][ni][e], a.gain);
+                if (MODE == LLZ_CUDA_ACC_F64 && valid && st < 0 && poly_near_nonzero_integer(v, a.guard_thr))
+                    guard_hits |= 1u << ((mi * 4 + ni) * 2 + e);
+                if (valid) ych[o - a.o0] = poly_finish(v);
             }
         }
     }
+    while (guard_hits) {
+        const int idx = __ffs(guard_hits) - 1;
+        guard_hits &= guard_hits - 1;
+        const int mi = idx >> 3, ni = (idx >> 1) & 3, e = idx & 1;
+        const int l = wm * 32 + 8 * mi + (lane >> 2);
+        const int j = wn * 32 + 4 * (2 * (lane & 3) + e) + ni;
+        const long long o = (j0 + j) * (long long)L + l0 + l;
+        ych[o - a.o0] = poly_finish(__dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain));
+        atomicAdd(a.guard_count, 1ULL);
+    }
 }
 
-template <int KC, int MODE>
-int launch_bank_dmma(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+template <int KC, int MODE, int WN>
+int launch_bank_dmma_tile(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
+    constexpr int JB = 32 * WN;
     BankGeom geo{};
     geo.jc0 = a.o0 / a.L;
     const long long jc_last = (a.o0 + a.n_out - 1) / a.L;
-    geo.n_cycle_tiles = (int)((jc_last - geo.jc0 + 1 + kDJB - 1) / kDJB);
+    geo.n_cycle_tiles = (int)((jc_last - geo.jc0 + 1 + JB - 1) / JB);
     geo.n_phase_tiles = (a.L + kDPB - 1) / kDPB;
     const int cspan_max = (int)(((long long)kDPB * a.M) / a.L) + 2;
-    geo.raw_cap = (kDJB - 1) * a.M + cspan_max + a.ctaps + 16;
-    const size_t smem = 16 + kStages * dmma_stage_bytes<KC>() + ((((size_t)geo.raw_cap + kRawSlack) * 2 + 15) & ~(size_t)15);
+    geo.raw_cap = (JB - 1) * a.M + cspan_max + a.ctaps + 16;
+    const size_t smem = 16 + kStages * dmma_stage_bytes<KC, WN>() + ((((size_t)geo.raw_cap + kRawSlack) * 2 + 15) & ~(size_t)15);
     if (smem > 226 * 1024) return 0;
-    auto kern = poly_bank_dmma_kernel<KC, MODE>;
+    auto kern = poly_bank_dmma_kernel<KC, MODE, WN>;
     if (smem > 48 * 1024)
         LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
     if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
-    kern<<<dim3((unsigned)blocks, (unsigned)n_channels), kDmmaThreads, smem, stream>>>(a, geo);
+    kern<<<dim3((unsigned)blocks, (unsigned)n_channels), 64 * WN, smem, stream>>>(a, geo);
     LLZ_CUDA_TRY(cudaGetLastError());
     return 1;
+}
+
+// Cycle tile by size of the call: 128 cycles when that already gives every SM a few CTAs (the throughput shape), else 64
+// or 32 cycles so that a small call -- a drop-in frame -- spreads over more SMs.  LLZ_BANK_DMMA_WN forces one (tuning).
+template <int KC, int MODE>
+int launch_bank_dmma(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+{
+    const long long cycles = (a.o0 + a.n_out - 1) / a.L - a.o0 / a.L + 1;
+    const long long per_cycle_tile = (long long)((a.L + kDPB - 1) / kDPB) * n_channels;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = 148;
+    }
+    const char *env = getenv("LLZ_BANK_DMMA_WN");
+    int wn = env ? atoi(env) : 0;
+    if (wn != 1 && wn != 2 && wn != 4) {
+        wn = 4;
+        while (wn > 1 && (cycles + 32 * wn - 1) / (32 * wn) * per_cycle_tile < 2LL * sms) wn >>= 1;
+    }
+    if (wn == 4) return launch_bank_dmma_tile<KC, MODE, 4>(a, n_channels, stream);
+    if (wn == 2) return launch_bank_dmma_tile<KC, MODE, 2>(a, n_channels, stream);
+    return launch_bank_dmma_tile<KC, MODE, 1>(a, n_channels, stream);
 }
 
 // ---- FP16 tensor-core variant (fast mode, ACC_F32) --------------------------------------------------------------
@@ -574,25 +592,12 @@ poly_bank_hmma_kernel(PolyLaunch a, BankGeom geo)
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
 
     // ---- stage the input span (as in poly_bank_kernel) ----
-    const long long rel = S0 - a.in0;
-    const long long rel_al = rel & ~7LL;
-    const long long end_al = (rel + rawn + 7) & ~7LL;
-    const bool inside = xc != nullptr && rel >= 0 && rel + rawn <= a.n_in;
-    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
-    int raw_off = 0;
-    if (bulk) {
-        raw_off = (int)(rel - rel_al);
-        if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
-        }
-    } else if (inside) {
-        for (int e = tid; e < rawn; e += NT) raw[e] = xc[rel + e];
-    } else {
-        for (int e = tid; e < rawn; e += NT) raw[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
-    }
+    // cycles of this tile that hold outputs of the call, and the samples they read
+    const long long jc_last = (a.o0 + a.n_out - 1) / L;
+    const int jv = (int)min((long long)JB, jc_last - j0 + 1);
+    const int need = min(rawn, (jv - 1) * M + cspan + Q);
+    bool bulk;
+    const int raw_off = poly_stage_span<NT>(a, xc, hc, S0, need, raw, bar, tid, &bulk);
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&s_full[i], NT);

@@ -152,20 +152,12 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
 
-    // The tile's input span is contiguous in x: rows*M samples starting at canonical index s_base.  Interior
-    // tiles fetch it with one TMA bulk copy (16-byte granules around the span) while the taps are staged.
+    // The tile's input span is contiguous in the stream: rows*M samples starting at canonical index s_base.  It is
+    // staged as it lies (one TMA bulk copy for the part inside x, the threads fill history / zero fringes) while the
+    // taps are staged, then de-interleaved shared memory to shared memory.
     const long long s_base = (qt - HS - 1) * M;
-    const long long rel = s_base - a.in0;
-    const long long rel_al = rel & ~7LL;
-    const long long end_al = (rel + (long long)rows * M + 7) & ~7LL;
-    const bool inside = xc != nullptr && rel >= 0 && rel + (long long)rows * M <= a.n_in;
-    const bool bulk = inside && end_al <= a.n_in && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0;
-    if (bulk && tid == 0) {
-        const uint32_t bytes = (uint32_t)(end_al - rel_al) * 2u;
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s(raw, xc + rel_al, bytes, bar);
-    }
+    bool bulk;
+    const int raw_off = poly_stage_span<NT>(a, xc, hc, s_base, rows * M, raw, bar, tid, &bulk);
     {
         const TA *src = (sizeof(TA) == 8) ? reinterpret_cast<const TA *>(a.slide64) : reinterpret_cast<const TA *>(a.slide32);
         const int vpr = ntp / U;                              // vectors per row
@@ -174,30 +166,19 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
             reinterpret_cast<V *>(taps_s + (size_t)rho * ntp)[i] = reinterpret_cast<const V *>(src + (size_t)rho * tap_stride)[i];
         }
     }
-    __syncthreads();                                          // barrier initialised before anyone waits on it
+    __syncthreads();                                          // barrier initialised, fringes written
+    if (bulk) mbar_wait(bar, 0);
 
     // De-interleave into the M streams: row jj of the span holds X((qt - HS - 1 + jj) * M + sigma); thread jj
     // writes element jj-1 (sigma = 0) / jj (sigma > 0) of each stream, so a warp's stores are contiguous
     // within a stream (conflict-free).
-    if (inside) {
-        if (bulk) {
-            mbar_wait(bar, 0);
-            const int16_t *src = raw + (int)(rel - rel_al);
-            switch (M) {
-            case 2: slide_deinterleave<2, NT, true>(xs, src, len, 2, tid); break;
-            case 3: slide_deinterleave<3, NT, true>(xs, src, len, 3, tid); break;
-            case 4: slide_deinterleave<4, NT, true>(xs, src, len, 4, tid); break;
-            default: slide_deinterleave<0, NT, true>(xs, src, len, M, tid); break;
-            }
-        } else {                                              // unaligned channel or the last granule of x
-            slide_deinterleave<0, NT, false>(xs, xc + rel, len, M, tid);
-        }
-    } else {
-        for (int jj = tid; jj < rows; jj += NT) {
-            const long long s0 = s_base + (long long)jj * M;
-            if (jj >= 1) xs[jj - 1] = (int16_t)poly_sample(a, xc, hc, s0);
-            if (jj < len)
-                for (int sigma = 1; sigma < M; ++sigma) xs[(size_t)sigma * len + jj] = (int16_t)poly_sample(a, xc, hc, s0 + sigma);
+    {
+        const int16_t *src = raw + raw_off;
+        switch (M) {
+        case 2: slide_deinterleave<2, NT, true>(xs, src, len, 2, tid); break;
+        case 3: slide_deinterleave<3, NT, true>(xs, src, len, 3, tid); break;
+        case 4: slide_deinterleave<4, NT, true>(xs, src, len, 4, tid); break;
+        default: slide_deinterleave<0, NT, true>(xs, src, len, M, tid); break;
         }
     }
     __syncthreads();
@@ -218,6 +199,10 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     const bool unit_gain = a.gain == 1.0;                     // x * 1.0 == x exactly: skip the FP64 multiply
     (void)gain_f; (void)unit_gain;
     const long long q0 = ot + (long long)tid * R;             // output index within this call
+    // two passes (see poly_bank_dmma_kernel): a straight-line first pass notes near-integer hits, the rare
+    // reference-order recompute patches them afterwards
+    static_assert(MODE != LLZ_CUDA_ACC_F64 || R <= 32, "guard hits are one bit per output of the thread");
+    uint32_t guard_hits = 0;
 #pragma unroll
     for (int r = 0; r < R; r += 2) {
         int16_t o2[2];
@@ -230,16 +215,20 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
                 o2[i] = (int16_t)__float2int_rz(vf);
                 continue;
             }
-            double v = unit_gain ? (double)acc[r + i] : __dmul_rn((double)acc[r + i], a.gain);
+            const double v = unit_gain ? (double)acc[r + i] : __dmul_rn((double)acc[r + i], a.gain);
             if constexpr (MODE == LLZ_CUDA_ACC_F64) {
-                if (poly_near_nonzero_integer(v, a.guard_thr) && q0 + r + i < a.n_out) {
-                    v = __dmul_rn(poly_reference_order_sum(a, xc, hc, a.o0 + q0 + r + i), a.gain);
-                    atomicAdd(a.guard_count, 1ULL);
-                }
+                if (poly_near_nonzero_integer(v, a.guard_thr) && q0 + r + i < a.n_out) guard_hits |= 1u << ((r + i) & 31);
             }
             o2[i] = poly_finish(v);
         }
         ys32[(tid * R + r) >> 1] = (uint32_t)(uint16_t)o2[0] | ((uint32_t)(uint16_t)o2[1] << 16);
+    }
+    while (guard_hits) {                                      // ~1e-8 of the outputs: the reference's own order
+        const int r = __ffs(guard_hits) - 1;
+        guard_hits &= guard_hits - 1;
+        reinterpret_cast<int16_t *>(xs)[tid * R + r] =
+            poly_finish(__dmul_rn(poly_reference_order_sum(a, xc, hc, a.o0 + q0 + r), a.gain));
+        atomicAdd(a.guard_count, 1ULL);
     }
     __syncthreads();
     const int cnt = (int)min((long long)TILE, a.n_out - ot);

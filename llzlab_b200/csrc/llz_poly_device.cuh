@@ -20,6 +20,46 @@ __device__ __forceinline__ int poly_sample(const PolyLaunch &a, const int16_t *x
     return 0;
 }
 
+// Stage a tile's input span in shared memory: raw[off + e] = X(S0 + e) for e < need (X = the stream sample of
+// llz_poly_kernels.h), off = the return value (0..7).  The run of samples that lies inside this call's input arrives
+// by ONE TMA bulk copy (cp.async.bulk + mbarrier) of whole 16-byte granules -- for an interior tile that is the whole
+// span, a few samples over-read on either side -- and only the fringes (history before x[0], zeros beyond the input,
+// the last granule of an input whose length is not a multiple of 8) are filled by the threads.  `raw` must be 16-byte
+// aligned and hold need + 16 elements.  (The first version filled every tile that touched the history or the end of
+// the input sample by sample; a drop-in frame, where every tile does, spent 20-30 us in that loop.)  *bulk tells the
+// caller to mbar_wait(bar, 0) after its __syncthreads.
+template <int NT>
+__device__ __forceinline__ int poly_stage_span(const PolyLaunch &a, const int16_t *xc, const int16_t *hc, long long S0,
+                                               int need, int16_t *raw, uint64_t *bar, int tid, bool *bulk)
+{
+    const long long rel = S0 - a.in0;                          // x index of element 0 (negative: history)
+    const long long rel_al = rel & ~7LL;
+    const int off = (int)(rel - rel_al);
+    const long long lo = rel > 0 ? rel : 0;
+    const long long hi = (rel + need < a.n_in) ? rel + need : a.n_in;
+    long long lo_al = lo & ~7LL;                               // >= max(rel_al, 0): inside x, at or after raw[0]
+    long long hi_al = (hi + 7) & ~7LL;
+    if (hi_al > a.n_in) hi_al = hi & ~7LL;
+    const bool tma = xc != nullptr && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && hi_al > lo_al;
+    if (!tma) lo_al = hi_al = lo;                              // no aligned run: the two fringes meet at lo
+    if (tma && tid == 0) {
+        const uint32_t bytes = (uint32_t)(hi_al - lo_al) * 2u;
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, bytes);
+        tma_bulk_g2s(raw + (lo_al - rel_al), xc + lo_al, bytes, bar);
+    }
+    int16_t *dst = raw + off;
+    // the bulk run covers elements [e_lo, e_hi); a span that ends before x[0] or starts beyond the input has none
+    const int e_lo = (int)min(max(lo_al - rel, 0LL), (long long)need);
+    const int e_hi = (int)min(max(hi_al - rel, (long long)e_lo), (long long)need);
+#pragma unroll 4
+    for (int e = tid; e < e_lo; e += NT) dst[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+#pragma unroll 4
+    for (int e = e_hi + tid; e < need; e += NT) dst[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+    *bulk = tma;
+    return off;
+}
+
 // saturate, truncate toward zero: llz_resample.c:596-601.  Truncating first (F2I.TRUNC saturates at the int32
 // range) and clamping the integer gives the same result as the reference's clamp-then-cast for every finite v,
 // and keeps the FP64 pipe free for the multiply-accumulates.

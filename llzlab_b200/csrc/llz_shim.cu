@@ -172,7 +172,11 @@ struct FirBank {
     // drop-in (mono, host buffers)
     int frame_len = 0;
     void *pinned = nullptr;      // frame_len elements
-    void *d_frame_in = nullptr, *d_frame_out = nullptr;
+    void *d_frame_in = nullptr, *d_frame_in2 = nullptr, *d_frame_out = nullptr;
+    int frame_flip = 0;          // which of the two frame buffers the next drop-in frame lands in
+    // deferred history (drop-in frames): the last hist_len samples still sit at the end of the previous frame's device
+    // buffer; the next call reads them there, so no history kernel runs between full frames
+    const void *chain_src = nullptr;
     cudaStream_t s_frame = nullptr;
 };
 
@@ -200,6 +204,7 @@ void fir_destroy(FirBank *b)
     if (b->d_hist[1]) cudaFree(b->d_hist[1]);
     if (b->pinned) cudaFreeHost(b->pinned);
     if (b->d_frame_in) cudaFree(b->d_frame_in);
+    if (b->d_frame_in2) cudaFree(b->d_frame_in2);
     if (b->d_frame_out) cudaFree(b->d_frame_out);
     if (b->s_frame) cudaStreamDestroy(b->s_frame);
     free(b->h_host);
@@ -374,7 +379,7 @@ int fir_fft_tables(FirBank *b)
 // step: the history ping-pong flips once every channel has been run (the host pipeline runs channel groups).
 template <typename T>
 int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride,
-                  long long n, cudaStream_t st, int c0, int cc, bool last)
+                  long long n, cudaStream_t st, int c0, int cc, bool last, bool defer_history)
 {
     FirLaunch<T> a{};
     a.x = static_cast<const T *>(d_in);
@@ -382,8 +387,9 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
     a.y = static_cast<T *>(d_out);
     a.y_stride = out_stride;
     a.n = n;
-    a.hist = (b->hist_zero || b->hist_len == 0) ? nullptr
-                                                 : static_cast<const T *>(b->d_hist[b->cur]) + (size_t)c0 * b->hist_len;
+    a.hist = b->chain_src ? static_cast<const T *>(b->chain_src)
+             : (b->hist_zero || b->hist_len == 0) ? nullptr
+                                                   : static_cast<const T *>(b->d_hist[b->cur]) + (size_t)c0 * b->hist_len;
     a.taps = static_cast<const T *>(b->d_taps);
     a.ntaps = b->flt_len;
     a.vec_ok = (d_in == nullptr || aligned16(d_in)) && aligned16(d_out) &&
@@ -407,31 +413,35 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
     } else if (fir_launch<T>(a, cc, b->dtype == LLZ_CUDA_F64_STRICT, st) != 0) {
         return -1;
     }
-    if (b->hist_len > 0) {
+    if (defer_history && b->hist_len > 0 && a.x && n >= b->hist_len && b->n_channels == 1) {
+        b->chain_src = a.x + (n - b->hist_len);                // the caller keeps d_in intact until the next call
+    } else if (b->hist_len > 0) {
         T *next = static_cast<T *>(b->d_hist[b->cur ^ 1]) + (size_t)c0 * b->hist_len;
         if (fir_update_history<T>(a.x, in_stride, n, a.hist, next, b->hist_len, cc, st) != 0) return -1;
         if (last) {
             b->cur ^= 1;
             b->hist_zero = false;
+            b->chain_src = nullptr;                            // a deferred history has been folded into d_hist
         }
     }
     return 0;
 }
 
 int fir_run_part(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride, long long n,
-                 cudaStream_t st, int c0, int cc, bool last)
+                 cudaStream_t st, int c0, int cc, bool last, bool defer_history = false)
 {
-    if (b->dtype == LLZ_CUDA_F32) return fir_run_typed<float>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last);
-    return fir_run_typed<double>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last);
+    if (b->dtype == LLZ_CUDA_F32)
+        return fir_run_typed<float>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last, defer_history);
+    return fir_run_typed<double>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last, defer_history);
 }
 
 int fir_run(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride, long long n,
-            cudaStream_t st)
+            cudaStream_t st, bool defer_history = false)
 {
     if (n < 0) { llz_set_error("negative sample count"); return -1; }
     if (n == 0) return 0;
     if (!d_out) { llz_set_error("null output pointer"); return -1; }
-    return fir_run_part(b, d_in, in_stride, d_out, out_stride, n, st, 0, b->n_channels, true);
+    return fir_run_part(b, d_in, in_stride, d_out, out_stride, n, st, 0, b->n_channels, true, defer_history);
 }
 
 // ---- polyphase bank ----------------------------------------------------------------------------------
@@ -461,7 +471,11 @@ struct PolyBank {
     Pipeline pipe;
     // drop-in
     int16_t *pinned_in = nullptr, *pinned_out = nullptr;
-    int16_t *d_frame_in = nullptr, *d_frame_out = nullptr;
+    int16_t *d_frame_in = nullptr, *d_frame_in2 = nullptr, *d_frame_out = nullptr;
+    int frame_flip = 0;                    // which of the two frame buffers the next drop-in frame lands in
+    // deferred history (drop-in frames): the stream's last hist_len samples still sit at the end of the previous
+    // frame's device buffer, so the next frame reads them there and no history kernel runs between frames
+    const int16_t *chain_src = nullptr;
     cudaStream_t s_frame = nullptr;
 };
 
@@ -485,7 +499,7 @@ void poly_destroy(PolyBank *b)
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     if (b->pinned_in) cudaFreeHost(b->pinned_in);
     if (b->pinned_out) cudaFreeHost(b->pinned_out);
-    cudaFree(b->d_frame_in); cudaFree(b->d_frame_out);
+    cudaFree(b->d_frame_in); cudaFree(b->d_frame_in2); cudaFree(b->d_frame_out);
     if (b->s_frame) cudaStreamDestroy(b->s_frame);
     llz_plan_free(&b->plan);
     b->magic = 0;
@@ -621,8 +635,10 @@ long long poly_out_len(const PolyBank *b, long long n_in)
     return total_out - b->produced;
 }
 
+// defer_history (single-channel drop-in frames with n_in >= hist_len): leave the history where it is -- the tail of
+// d_in, which the caller keeps intact until the next call -- instead of copying it into d_hist
 int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_in, int16_t *d_out,
-             long long out_stride, long long *n_out, cudaStream_t st)
+             long long out_stride, long long *n_out, cudaStream_t st, bool defer_history = false)
 {
     const llz_plan_t &p = b->plan;
     if (n_in < 0) { llz_set_error("negative sample count"); return -1; }
@@ -635,11 +651,18 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     if (n_in == 0) return 0;
     if (outs > 0 && !d_out) { llz_set_error("null output pointer"); return -1; }
 
+    if (b->chain_src && !defer_history) {
+        // a deferred history meets an ordinary run: materialise it first
+        LLZ_CUDA_TRY(cudaMemcpyAsync(b->d_hist[b->cur], b->chain_src, (size_t)p.hist_len * sizeof(int16_t),
+                                     cudaMemcpyDeviceToDevice, st));
+        b->hist_zero = false;
+        b->chain_src = nullptr;
+    }
     PolyLaunch a{};
     a.x = d_in;
     a.x_stride = in_stride;
     a.n_in = n_in;
-    a.hist = (b->hist_zero || p.hist_len == 0) ? nullptr : b->d_hist[b->cur];
+    a.hist = b->chain_src ? b->chain_src : (b->hist_zero || p.hist_len == 0) ? nullptr : b->d_hist[b->cur];
     a.hist_len = p.hist_len;
     a.y = d_out;
     a.y_stride = out_stride;
@@ -667,7 +690,9 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.slide_ntp32 = b->slide_ntp32;
     a.guard_count = b->d_guard;
     if (poly_launch(a, b->n_channels, st) != 0) return -1;
-    if (p.hist_len > 0) {
+    if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
+        b->chain_src = d_in + (n_in - p.hist_len);
+    } else if (p.hist_len > 0) {
         const int16_t *old = b->hist_zero ? nullptr : b->d_hist[b->cur];
         if (poly_update_history(d_in, in_stride, n_in, old, b->d_hist[b->cur ^ 1], p.hist_len, b->n_channels, st) != 0)
             return -1;
@@ -684,6 +709,7 @@ int poly_reset(PolyBank *b)
     b->consumed = 0;
     b->produced = 0;
     b->hist_zero = true;
+    b->chain_src = nullptr;
     return 0;
 }
 
@@ -805,6 +831,7 @@ extern "C" int llz_cuda_fir_bank_reset(unsigned long handle, llz_cuda_stream_t s
     FirBank *b = as_fir(handle);
     if (!b) return -1;
     b->hist_zero = true;
+    b->chain_src = nullptr;
     return 0;
 }
 
@@ -814,6 +841,7 @@ extern "C" int llz_cuda_fir_bank_set_history(unsigned long handle, const void *d
     FirBank *b = as_fir(handle);
     if (!b) return -1;
     if (b->hist_len == 0) return 0;
+    b->chain_src = nullptr;
     if (!d_hist) { b->hist_zero = true; return 0; }
     DeviceGuard g(b->device);
     const size_t es = fir_elem_size(b->dtype);
@@ -1113,6 +1141,7 @@ unsigned long fir_dropin_init(int kind, int frame_len, int flt_len, double fc1, 
     cudaError_t e;
     if ((e = cudaHostAlloc(&b->pinned, sizeof(double) * (size_t)cap, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaMalloc(&b->d_frame_in, sizeof(double) * (size_t)cap)) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_frame_in2, sizeof(double) * (size_t)cap)) != cudaSuccess ||
         (e = cudaMalloc(&b->d_frame_out, sizeof(double) * (size_t)cap)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&b->s_frame, cudaStreamNonBlocking)) != cudaSuccess) {
         llz_set_error("FIR handle init: %s", cudaGetErrorString(e));
@@ -1165,8 +1194,11 @@ extern "C" int llz_fir_filter(unsigned long handle, double *buf_in, double *buf_
     DeviceGuard g(b->device);
     const size_t bytes = sizeof(double) * (size_t)frame_len;
     memcpy(b->pinned, buf_in, bytes);
-    LLZ_CUDA_TRY(cudaMemcpyAsync(b->d_frame_in, b->pinned, bytes, cudaMemcpyHostToDevice, b->s_frame));
-    if (fir_run(b, b->d_frame_in, 0, b->d_frame_out, 0, frame_len, b->s_frame) != 0) return -1;
+    // frames alternate between two device buffers: the previous frame's tail stays readable as this frame's history
+    void *d_frame = b->frame_flip ? b->d_frame_in2 : b->d_frame_in;
+    b->frame_flip ^= 1;
+    LLZ_CUDA_TRY(cudaMemcpyAsync(d_frame, b->pinned, bytes, cudaMemcpyHostToDevice, b->s_frame));
+    if (fir_run(b, d_frame, 0, b->d_frame_out, 0, frame_len, b->s_frame, /*defer_history=*/true) != 0) return -1;
     LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned, b->d_frame_out, bytes, cudaMemcpyDeviceToHost, b->s_frame));
     LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
     memcpy(buf_out, b->pinned, bytes);
@@ -1206,6 +1238,7 @@ unsigned long poly_dropin_init(int kind, int L, int M, double gain, win_t win)
     if ((e = cudaHostAlloc((void **)&b->pinned_in, in_b, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaHostAlloc((void **)&b->pinned_out, out_b, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaMalloc((void **)&b->d_frame_in, in_b)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&b->d_frame_in2, in_b)) != cudaSuccess ||
         (e = cudaMalloc((void **)&b->d_frame_out, out_b)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&b->s_frame, cudaStreamNonBlocking)) != cudaSuccess) {
         llz_set_error("resampler handle init: %s", cudaGetErrorString(e));
@@ -1229,9 +1262,12 @@ int poly_dropin_frame(unsigned long handle, int kind, unsigned char *sample_in, 
     }
     DeviceGuard g(b->device);
     memcpy(b->pinned_in, sample_in, (size_t)bytes_in);
-    LLZ_CUDA_TRY(cudaMemcpyAsync(b->d_frame_in, b->pinned_in, (size_t)bytes_in, cudaMemcpyHostToDevice, b->s_frame));
+    // frames alternate between two device buffers: the previous frame's tail stays readable as this frame's history
+    int16_t *d_frame = b->frame_flip ? b->d_frame_in2 : b->d_frame_in;
+    b->frame_flip ^= 1;
+    LLZ_CUDA_TRY(cudaMemcpyAsync(d_frame, b->pinned_in, (size_t)bytes_in, cudaMemcpyHostToDevice, b->s_frame));
     long long outs = 0;
-    if (poly_run(b, b->d_frame_in, 0, b->plan.num_in, b->d_frame_out, 0, &outs, b->s_frame) != 0) return -1;
+    if (poly_run(b, d_frame, 0, b->plan.num_in, b->d_frame_out, 0, &outs, b->s_frame, /*defer_history=*/true) != 0) return -1;
     if (outs != b->plan.num_out) { llz_set_error("internal: frame produced %lld samples, expected %d", outs, b->plan.num_out); return -1; }
     LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned_out, b->d_frame_out, (size_t)bytes_out, cudaMemcpyDeviceToHost, b->s_frame));
     LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));

@@ -123,3 +123,30 @@ def test_two_handles_on_two_host_threads(zlib, port, cuda):
     p = port.resample_plan(160, 147, 1)
     for seed, (x, y) in out.items():
         assert np.array_equal(y, port.resample_run(p, 1.0, x, len(y)))
+
+
+@pytest.mark.parametrize("kind,L_,M", [(2, 160, 147), (2, 1, 3), (0, 1, 3), (2, 3, 2)])
+def test_dropin_frames_then_bank_run_on_the_same_handle(zlib, port, cuda, kind, L_, M):
+    """Drop-in frames leave their history in the previous frame's device buffer (no history kernel between frames);
+    a bank run on the same handle must pick the stream up from there, and a reset must forget it."""
+    torch = cuda
+    r = zlib.Resampler(kind, L_, M, 1.0, zlib.BLACKMAN)
+    nf = r.bytes_in // 2
+    plan = port.decimate_plan(M, 1) if kind == zlib.KIND_DECIMATE else port.resample_plan(L_, M, 1)
+    run = port.decimate_run if kind == zlib.KIND_DECIMATE else port.resample_run
+    x = port.lcg_s16(nf * 5, 99)
+    total = plan.num_out * 5
+    want = run(plan, 1.0, x, total)
+    got = [r.frame(x[i * nf:(i + 1) * nf]) for i in range(3)]
+    dx = torch.from_numpy(x[3 * nf:]).cuda()
+    dy = torch.zeros(2 * plan.num_out + 8, dtype=torch.int16, device="cuda")
+    n_out = zlib.ResampleBank.run(r, dx, 2 * nf, 2 * nf, dy, dy.numel())      # same handle through the bank entry point
+    torch.cuda.synchronize()
+    assert n_out == 2 * plan.num_out
+    got.append(dy.cpu().numpy()[:n_out])
+    assert np.array_equal(np.concatenate(got), want)
+    # ... and frames again after the bank run continue the same stream state machine from a reset
+    zlib.ResampleBank.reset(r)
+    again = np.concatenate([r.frame(x[i * nf:(i + 1) * nf]) for i in range(2)])
+    assert np.array_equal(again, want[:2 * plan.num_out])
+    r.close()

@@ -58,6 +58,33 @@ def test_dropin_short_last_frame_and_aliasing(zlib, port, cuda):
     f.close(); f2.close()
 
 
+@pytest.mark.parametrize("frame,N,tail", [(256, 200, 100), (32, 63, 32), (512, 127, 1), (256, 257, 256)])
+def test_dropin_history_between_frames(zlib, port, cuda, frame, N, tail):
+    """Full frames leave their history in the previous frame's device buffer (no history kernel in between); frames
+    shorter than flt_len-1, a short last frame and the flush must still see the right flt_len-1 predecessors."""
+    h = port.fir_design(0, N, 0.2, 0.0, 0)
+    x = port.lcg_f64(frame * 4 + tail, 11)
+    want = port.fir_run(h, np.concatenate([x, np.zeros(N - 1)]))
+    f = zlib.FirFilter(0, frame, N, 0.2, 0.0, 0)
+    parts = [f.filter(x[i:i + frame]) for i in range(0, len(x), frame)]
+    if frame >= N - 1:                                     # the reference's flush needs frame_len >= flt_len-1 (quirk F2)
+        parts.append(f.flush())
+    got = np.concatenate(parts)
+    assert got.tobytes() == want[:len(got)].tobytes()
+    # the bank entry points continue a handle's stream from the deferred history, and a reset forgets it
+    torch = cuda
+    f2 = zlib.FirFilter(0, frame, N, 0.2, 0.0, 0)
+    head = np.concatenate([f2.filter(x[i:i + frame]) for i in range(0, 2 * frame, frame)])
+    dx = torch.from_numpy(x[2 * frame:]).cuda()
+    dy = torch.empty_like(dx)
+    zlib.FirBank.run(f2, dx, len(dx), dy, len(dx), len(dx))
+    torch.cuda.synchronize()
+    assert np.concatenate([head, dy.cpu().numpy()]).tobytes() == want[:len(x)].tobytes()
+    zlib.FirBank.reset(f2)
+    assert f2.filter(x[:frame]).tobytes() == want[:frame].tobytes()
+    f.close(); f2.close()
+
+
 @pytest.mark.parametrize("N", [1, 2, 15, 16, 17, 33, 64, 127, 128, 255, 1000, 4095])
 def test_bank_f64_all_tap_counts(zlib, port, cuda, N):
     torch = cuda
