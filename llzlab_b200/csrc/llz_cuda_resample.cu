@@ -189,7 +189,7 @@ poly_slide_kernel(PolyLaunch a, int ntp /* padded taps per residue */, int tap_s
     for (int rho = 0; rho < M; ++rho) {
         const int sigma = rho ? M - rho : 0;
         const int16_t *win = xs + (size_t)sigma * len + HS + tid * R - U;
-        SM::template run<false>(acc, win, taps_s + (size_t)rho * ntp, ntp);
+        SM::template run<false, true>(acc, win, taps_s + (size_t)rho * ntp, ntp);
     }
 
     // gain / guard / saturate / truncate, staged through shared memory so the global stores are 16-byte vectors
@@ -290,11 +290,14 @@ inline size_t slide_smem_bytes(int M, int ntp, int tile, size_t elem)
     return 16 + (size_t)M * ntp * elem + streams + raw;
 }
 
-// taps per residue padded to the SlidingMac granularity of a tile variant
-inline int slide_pad(const PolyLaunch &a, int gran)
+// taps per residue padded to whole tap vectors (the kernel runs the last, partial unrolled iteration chunk by chunk);
+// LLZ_SLIDE_FULL_GRAN=1 pads to the SlidingMac granularity of the tile variant instead (A/B measurements)
+inline int slide_pad(const PolyLaunch &a, int gran, int vec)
 {
     const int per = (a.ctaps + a.M - 1) / a.M;
-    return (per + gran - 1) / gran * gran;
+    const char *full = getenv("LLZ_SLIDE_FULL_GRAN");
+    if (full && atoi(full) != 0) return (per + gran - 1) / gran * gran;
+    return (per + vec - 1) / vec * vec;
 }
 
 // Tile variants of the sliding kernel: R/U in {11, 7, 5, 3} (odd: conflict-free loads), i.e. tap granularity
@@ -313,7 +316,8 @@ int pick_slide(const PolyLaunch &a, int *ntp_out)
         if (force && atoi(force) != ru[i]) continue;
         if (!force && ru[i] == 11 && sizeof(TA) == 4) continue;   // measured: the 44-output float tile is slower than 20 (C3: 4.9 vs 3.9 ms)
         const int R = ru[i] * U, gran = (ru[i] + 1) * U;
-        const int ntp = slide_pad(a, gran);
+        // f64: whole tap vectors (+2.4 % on C3); f32: the variant's own granularity (the tail costs the float tiles 7 %)
+        const int ntp = slide_pad(a, gran, sizeof(TA) == 8 ? U : gran);
         if (ntp > avail) continue;
         const size_t smem = slide_smem_bytes(a.M, ntp, kSlideThreads * R, sizeof(TA));
         if (smem > kSmemBudget) continue;

@@ -78,11 +78,26 @@ struct SlidingMac {
         if constexpr (CC + 1 < NS) step<CC + 1, STRICT>(acc, ring, xp, hp);
     }
 
-    // Accumulate `ntaps` taps (a multiple of GRAN; the tail of `taps` is zero-padded).
+    // the last, partial iteration: the first `chunks` (< NS) chunks of step<0>; the ring is not used afterwards
+    template <int CC, bool STRICT>
+    static __device__ __forceinline__ void tail(T (&acc)[R], T (&ring)[NS * U], const S *xp, const T *hp, int chunks)
+    {
+        load_samples(xp - CC * U, &ring[((NS - CC) % NS) * U]);
+        T h[U];
+        unpack(*reinterpret_cast<const V *>(hp + CC * U), h);
+        chunk<CC, STRICT>(acc, ring, h);
+        if constexpr (CC + 2 < NS) {
+            if (CC + 1 < chunks) tail<CC + 1, STRICT>(acc, ring, xp, hp, chunks);
+        }
+    }
+
+    // Accumulate `ntaps` taps; the tail of `taps` is zero-padded to a multiple of GRAN, or -- TAIL = true, which
+    // costs a second copy of the unrolled code -- only to a multiple of U (45 taps per residue of config C3 run as
+    // 46 instead of 48).
     //   win  : shared-memory address of sample (base - U), i.e. one vector below the first output's
-    //          newest sample; 16-byte aligned.  Reads reach down to win - ntaps + U ... up to win+R+U-1.
+    //          newest sample; aligned to U samples.  Reads reach down to win - ntaps + U ... up to win+R+U-1.
     //   taps : shared-memory tap array, taps[k] multiplies x[base + r - k]; 16-byte aligned.
-    template <bool STRICT>
+    template <bool STRICT, bool TAIL = false>
     static __device__ __forceinline__ void run(T (&acc)[R], const S *win, const T *taps, int ntaps)
     {
         T ring[NS * U];
@@ -90,10 +105,14 @@ struct SlidingMac {
         for (int s = 1; s < NS; ++s) load_samples(win + s * U, &ring[s * U]);
         const S *xp = win;
         const T *hp = taps;
-        for (int k = 0; k < ntaps; k += GRAN) {
+        int k = 0;
+        for (; k + GRAN <= ntaps; k += GRAN) {
             step<0, STRICT>(acc, ring, xp, hp);
             xp -= GRAN;
             hp += GRAN;
+        }
+        if constexpr (TAIL) {
+            if (k < ntaps) tail<0, STRICT>(acc, ring, xp, hp, (ntaps - k) / U);
         }
     }
 };
