@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "llz_cuda_common.cuh"
 
 namespace llz {
@@ -47,12 +49,22 @@ struct PolyLaunch {
     const float *slide32;
     int slide_ntp64, slide_ntp32;
     unsigned long long *guard_count;
+    // integer tensor-core exact mode (llz_cuda_polybank_imma.cu): the bank as int8 digit planes in the kernel's tile
+    // layout, g ~ q * imma_scale (imma_scale = 2^-s); nullptr when the bank was not split
+    const signed char *imma_tiles;
+    int imma_nchunks;          // chunks of 32 taps per phase tile
+    double imma_scale;
+    double imma_thr;           // guard band: guard_thr + |gain| * (tap rounding bound)
 };
 
 // picks the kernel (sliding for L == 1 when the tile fits, general otherwise) and launches it
 int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 // register-tiled phase-bank kernel for L > 1 (llz_cuda_polybank.cu): 1 = launched, 0 = not applicable, -1 = error
 int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
+// exact mode on the integer tensor cores (llz_cuda_polybank_imma.cu): same return convention
+int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
+// host side of the same: the bank [L][Q] as int8 digit planes in the kernel's tile layout; returns chunks per tile (0: n/a)
+int poly_imma_build_tables(const double *cb, int L, int M, int Q, std::vector<signed char> *out, int *shift, double *eps);
 // name of the kernel poly_launch would pick ("sliding" / "general"), for reporting
 const char *poly_kernel_name(const PolyLaunch &a);
 

@@ -457,6 +457,9 @@ struct PolyBank {
     float *d_cbankT32 = nullptr, *d_cbankT32_base = nullptr, *d_slide32 = nullptr;
     uint16_t *d_cbankT16h = nullptr, *d_cbankT16l = nullptr, *d_cbankT16h_base = nullptr, *d_cbankT16l_base = nullptr;
     int bank16_exp = 0;
+    signed char *d_imma_tiles = nullptr;   // int8 digit planes of the bank (llz_cuda_polybank_imma.cu)
+    int imma_nchunks = 0, imma_shift = 0;
+    double imma_eps = 0.0;                 // bound on the tap-rounding error of a full-scale dot product
     int bank_pad = 0;
     int rep = 1;             // device tables hold the bank's rows `rep` times: kernels see L*rep phases, M*rep step
     int *d_order = nullptr, *d_single = nullptr;
@@ -495,6 +498,7 @@ void poly_destroy(PolyBank *b)
     cudaFree(b->d_cbank); cudaFree(b->d_cbankT64_base); cudaFree(b->d_slide64);
     cudaFree(b->d_cbankT32_base); cudaFree(b->d_slide32);
     cudaFree(b->d_cbankT16h_base); cudaFree(b->d_cbankT16l_base);
+    cudaFree(b->d_imma_tiles);
     cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     if (b->pinned_in) cudaFreeHost(b->pinned_in);
@@ -559,6 +563,13 @@ int poly_upload_plan(PolyBank *b)
         if (upload(&b->d_cbankT16h_base, th) || upload(&b->d_cbankT16l_base, tl)) return -1;
         b->d_cbankT16h = b->d_cbankT16h_base + pad * L;
         b->d_cbankT16l = b->d_cbankT16l_base + pad * L;
+    }
+    const char *imma = getenv("LLZ_BANK_IMMA");
+    if (imma && atoi(imma) != 0 && b->acc == LLZ_CUDA_ACC_F64 && L >= 16 && p.shift == 0 && p.frame_len == 0) {
+        // exact mode on the integer tensor cores: int8 digit planes of the taps in the kernel's tile layout
+        std::vector<signed char> tiles;
+        b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, &tiles, &b->imma_shift, &b->imma_eps);
+        if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
     }
     std::vector<int> order(p.order, p.order + Q), single(L);
     for (size_t r = 0; r < L; ++r) single[r] = p.single_tap[r % L0];
@@ -689,6 +700,10 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.slide_ntp64 = b->slide_ntp64;
     a.slide_ntp32 = b->slide_ntp32;
     a.guard_count = b->d_guard;
+    a.imma_tiles = b->d_imma_tiles;
+    a.imma_nchunks = b->imma_nchunks;
+    a.imma_scale = ldexp(1.0, -b->imma_shift);
+    a.imma_thr = b->guard_thr + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
     if (poly_launch(a, b->n_channels, st) != 0) return -1;
     if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
         b->chain_src = d_in + (n_in - p.hist_len);

@@ -259,3 +259,32 @@ def test_c3_shape_spot_checks(zlib, port, cuda):
             want = port.resample_run(p, 1.0, xc, 2000, m0=m0)
             assert np.array_equal(yc[m0:m0 + 2000], want), (c, m0)
     bank.close()
+
+
+@pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0)])
+def test_bank_exact_mode_on_the_integer_tensor_cores(zlib, port, cuda, monkeypatch, L_, M, k):
+    """LLZ_BANK_IMMA=1: taps as five int8 digit planes, samples as two byte planes, exact s32 accumulation on the INT8
+    tensor cores, a two-level near-integer guard -- the int16 output must still be the reference's, bit for bit."""
+    torch = cuda
+    monkeypatch.setenv("LLZ_BANK_IMMA", "1")
+    C_ = 3
+    bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, C_, k_override=k)
+    plan = port.resample_plan(L_, M, 1, k)
+    n_in = plan.num_in * 2 + 777
+    x = np.stack([port.lcg_s16(n_in, 4000 + c) for c in range(C_)])
+    x[0, :5000] = 32767                                  # full scale, saturating outputs
+    x[1, 100:4000] = -32768
+    n_out = bank.out_len(n_in)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(C_, n_out + 8, dtype=torch.int16, device="cuda")
+    # in two ragged calls: the second one starts inside the history and off the tile grid
+    cut = plan.num_in + 123
+    o1 = bank.run(dx, n_in, cut, dy, n_out + 8)
+    o2 = bank.run(dx.data_ptr() + 2 * cut, n_in, n_in - cut, dy.data_ptr() + 2 * o1, n_out + 8)
+    torch.cuda.synchronize()
+    assert o1 + o2 == n_out
+    got = dy.cpu().numpy()[:, :n_out]
+    for c in range(C_):
+        want = port.resample_run(plan, 1.0, x[c], n_out)
+        assert np.array_equal(got[c], want), (L_, M, c, int(np.abs(got[c].astype(np.int32) - want).max()))
+    bank.close()

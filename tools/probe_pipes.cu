@@ -121,6 +121,27 @@ __global__ void __launch_bounds__(256) hmma_kernel(float *sink, int iters, unsig
     if (t == 123456.789f) sink[0] = t;
 }
 
+// legacy integer tensor-core path: mma.sync m16n8k32 u8 x s8 -> s32 (exact), NM independent accumulator tiles per warp
+template <int NM>
+__global__ void __launch_bounds__(256) imma_kernel(float *sink, int iters, unsigned a0, unsigned b0)
+{
+    int c[NM][4];
+    for (int i = 0; i < NM; ++i) for (int j = 0; j < 4; ++j) c[i][j] = (int)(threadIdx.x + i + j);
+    unsigned a[4] = {a0 + threadIdx.x, a0 ^ 0x1234u, a0 + 7u, a0 * 3u}, b[2] = {b0 + threadIdx.x, b0 ^ 0x4321u};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+            for (int i = 0; i < NM; ++i)
+                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+r"(c[i][0]), "+r"(c[i][1]), "+r"(c[i][2]), "+r"(c[i][3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    int t = 0;
+    for (int i = 0; i < NM; ++i) for (int j = 0; j < 4; ++j) t += c[i][j];
+    if (t == 123456789) sink[0] = (float)t;
+}
+
 template <typename K, typename... A>
 static float time_ms(K kern, int blocks, int threads, A... args)
 {
@@ -177,6 +198,13 @@ int main()
                         : time_ms(hmma_kernel<8>, blocks, threads, (float *)sink, iters, 0x3c003c00u, 0x3c003c00u);
         printf("hmma m16n8k16 f16 x%-2d           %8.3f ms  %7.2f TFLOP/s (legacy mma.sync path)\n", nm, ms,
                2.0 * 16 * 8 * 16 * nm * nwarps * iters * 4 / ms / 1e9);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const int nm = pass ? 16 : 8;
+        float ms = pass ? time_ms(imma_kernel<16>, blocks, threads, (float *)sink, iters, 0x01020304u, 0x04030201u)
+                        : time_ms(imma_kernel<8>, blocks, threads, (float *)sink, iters, 0x01020304u, 0x04030201u);
+        printf("imma m16n8k32 u8*s8 x%-2d          %8.3f ms  %7.2f TOP/s (legacy mma.sync path, exact s32 accumulate)\n", nm, ms,
+               2.0 * 16 * 8 * 32 * nm * nwarps * iters * 4 / ms / 1e9);
     }
     return 0;
 }
