@@ -811,11 +811,11 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         if (bank_smem<float, 16, 4, 4, 32, 16, false>(a) > kLimit) return 0;
         return launch_bank<float, 16, 4, 4, 32, 16, false, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
     }
-    // f64, opt-in (LLZ_BANK_IMMA=1): exact integer evaluation on the INT8 tensor cores (llz_cuda_polybank_imma.cu) --
-    // bit-identical like the FP64 tiles, not yet faster (C4: 51 against 56 Gsamples/s)
+    // f64: exact integer evaluation on the INT8 tensor cores (llz_cuda_polybank_imma.cu) unless LLZ_BANK_NO_IMMA=1 asks
+    // for the FP64 tiles (or the span of a tile does not fit beside its stages: extreme M / L)
     if (a.imma_tiles) {
-        const char *im = getenv("LLZ_BANK_IMMA");
-        if (im && atoi(im) != 0) {
+        const char *no = getenv("LLZ_BANK_NO_IMMA");
+        if (!(no && atoi(no) != 0)) {
             const int rc = poly_bank_imma_launch(a, n_channels, stream);
             if (rc != 0) return rc;
         }

@@ -19,20 +19,16 @@
 // B200 rates (tools/probe_pipes.cu): IMMA 1144 TOP/s = 57 T exact MACs/s after the ten-way split, against 17-18.5 T
 // MACs/s for DFMA / DMMA.
 //
-// Status (round 1): bit-identical on every resampler test, OPT-IN (LLZ_BANK_IMMA=1) because it is not yet faster than
-// the DMMA tiles: C4 51.3 against 55.6 Gsamples/s.  In-kernel clock stamps per 64 x 64 tile: span staging + byte split
-// 3.5 k cycles, MMA loop 10.2 k (ideal 6.6 k: 65 % of the IMMA rate), epilogue 3.9 k, second look 1.1 k, ~3 k launch --
-// the six accumulator sets cost 232 registers, so ONE CTA is resident per SM and nothing overlaps a tile's prologue and
-// epilogue with another tile's MMAs.  What it needs next: a persistent CTA with a producer warp that stages and splits
-// the next tile's span during the MMA loop, and the taps of a phase tile multicast across a cluster (the G'' stream is
-// 23 B/clk/SM at the IMMA rate: L2-bound if every CTA fetches its own).
-//
-// Layout.  With the tap index reversed, k'' = K'-1-k', the operand rows are k-contiguous as mma's row.col fragments
-// want them: X''[j][k''] = span[j*M + k''] (an ascending run of the staged input span per cycle) and
-// G''[l][k''] = g[l][Q-1 + (c_l - c_lo) - k''].  G'' depends on the phase tile only, so the host lays every tile out
-// once, chunk by chunk (32 k'' bytes per row, rows padded to 48 bytes: conflict-free ldmatrix), and a chunk of all
-// five planes arrives by ONE TMA bulk copy; X'' chunks are cut from two byte planes of the span (split once per CTA)
-// with funnel shifts.  Three-stage mbarrier pipeline as in the other bank kernels.
+// Status (round 1): bit-identical on every resampler test and the default for the exact mode (LLZ_BANK_NO_IMMA=1 keeps
+// the FP64 tiles): C4 58.3 against 55.6 Gsamples/s, C1's drop-in job 531 against 490 Msamples/s -- a first step towards
+// the 3x higher roof.  History: 35.0 (every guard hit recomputed serially) -> 49.0 (warp-cooperative second look) -> 51.3
+// (integer epilogue, 64-tap chunks, taps fetched before the span) -> 56.8 (persistent CTAs: the next tile's span and
+// first tap chunks are fetched during the current tile's MMAs and epilogue) -> 58.3 (four stages).  In-kernel clock
+// stamps per 64 x 64 tile before the persistent version: span staging + byte split 3.5 k cycles, MMA loop 10.2 k (65 % of
+// the IMMA rate), epilogue 3.9 k, second look 1.1 k, launch ~3 k.  The six accumulator sets cost ~240 registers, so ONE
+// CTA is resident per SM: the MMA warps still produce their own X'' chunks and run the epilogue with the tensor pipe
+// idle.  Next: producer warps (setmaxnreg) for the X'' chunks and the next tile's span split, and the taps of a phase
+// tile multicast across a cluster (the G'' stream is 23 B/clk/SM at the IMMA rate: L2-bound if every CTA fetches its own).
 #include <math.h>
 #include <stdlib.h>
 
@@ -49,7 +45,8 @@ constexpr int kIKC = 64;                              // k'' per chunk = two IMM
 constexpr int kINT = 256;                             // 8 warps = 4 (phases) x 2 (cycles), warp tile 16 x 32
 constexpr int kIPlanes = 5;                           // signed base-256 digits of a tap
 constexpr int kIPitch = kIKC + 16;                    // bytes per operand row in shared memory (80: conflict-free ldmatrix)
-constexpr int kIStages = 3;
+constexpr int kIStages = 4;                            // chunk c + kIAhead is produced after chunk c is consumed
+constexpr int kIAhead = kIStages - 1;
 constexpr int kIGStage = kIPlanes * kIPB * kIPitch;   // 25,600 bytes: one chunk of G'', all planes
 constexpr int kIXStage = 2 * kIJB * kIPitch;          // 10,240 bytes: one chunk of X'', low and high byte planes
 constexpr int kIStage = kIGStage + kIXStage;
@@ -58,7 +55,7 @@ constexpr int kIHeader = 128;
 
 struct ImmaGeom {
     long long jc0;
-    int n_cycle_tiles, n_phase_tiles;
+    int n_cycle_tiles, n_phase_tiles, n_channels;
     int raw_cap;                                      // int16 elements reserved for the staged span (multiple of 16)
 };
 
@@ -83,222 +80,297 @@ __device__ __forceinline__ void imma_s8s8(int (&c)[4], const uint32_t (&a)[4], u
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// geometry of one tile (64 phases x 64 cycles of one channel)
+struct ImmaTile {
+    int ch, l0, pbv, cspan, KP, nchunks, need, tile_p;
+    long long j0, S0;
+};
+
+__device__ __forceinline__ ImmaTile imma_tile(const PolyLaunch &a, const ImmaGeom &geo, long long t)
+{
+    ImmaTile T;
+    T.tile_p = (int)(t % geo.n_phase_tiles);                   // phase tiles fastest: neighbours share the input span in L2
+    const long long r = t / geo.n_phase_tiles;
+    const int tile_j = (int)(r % geo.n_cycle_tiles);
+    T.ch = (int)(r / geo.n_cycle_tiles);
+    const int L = a.L, M = a.M, Q = a.ctaps;
+    T.l0 = T.tile_p * kIPB;
+    T.pbv = min(kIPB, L - T.l0);
+    const int c_lo = (int)(((long long)T.l0 * M) / L);
+    const int c_hi = (int)(((long long)(T.l0 + T.pbv - 1) * M) / L);
+    T.cspan = c_hi - c_lo;
+    T.KP = Q + T.cspan;
+    T.nchunks = (T.KP + kIKC - 1) / kIKC;
+    T.j0 = geo.jc0 + (long long)tile_j * kIJB;
+    T.S0 = T.j0 * M + c_lo - (Q - 1);
+    const long long jc_last = (a.o0 + a.n_out - 1) / L;
+    const int jv = (int)min((long long)kIJB, jc_last - T.j0 + 1);   // cycles of this tile that hold outputs of the call
+    T.need = (jv - 1) * M + T.cspan + Q;
+    return T;
+}
+
+// Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The six accumulator sets cost ~230
+// registers, so only one CTA fits an SM and nothing else would hide a tile's prologue: the NEXT tile's input span is
+// therefore fetched (TMA, second span buffer) while the current tile multiplies, and its first two tap chunks while the
+// current tile runs its epilogue.  The chunk pipeline's barriers run on a chunk counter that continues across tiles.
 template <int MODE>
 __global__ void __launch_bounds__(kINT, 1)
 poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
 {
-    constexpr int PB = kIPB, JB = kIJB, NT = kINT;
+    constexpr int PB = kIPB, NT = kINT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);                       // span staging
-    uint64_t *s_full = bar + 1, *s_empty = s_full + kIStages;
+    uint64_t *span_bar = reinterpret_cast<uint64_t *>(smem_raw);                  // [2]: one per span buffer
+    uint64_t *s_full = span_bar + 2, *s_empty = s_full + kIStages;
     unsigned char *stages = smem_raw + kIHeader;
-    int16_t *raw = reinterpret_cast<int16_t *>(stages + kIStages * kIStage);      // [raw_cap]
-    unsigned char *rawl = reinterpret_cast<unsigned char *>(raw + geo.raw_cap);   // [raw_cap + 32] low bytes, by span index
+    int16_t *raw0 = reinterpret_cast<int16_t *>(stages + kIStages * kIStage);     // [2][raw_cap]
+    unsigned char *rawl = reinterpret_cast<unsigned char *>(raw0 + 2 * geo.raw_cap);   // [raw_cap + 32] low bytes, by span index
     unsigned char *rawh = rawl + geo.raw_cap + 32;                                // [raw_cap + 32] high bytes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;                   // warp tile: phases [16*wm, +16) x cycles [32*wn, +32)
-    const int tile_p = blockIdx.x % geo.n_phase_tiles;
-    const int tile_j = blockIdx.x / geo.n_phase_tiles;
-    const int ch = blockIdx.y;
     const int L = a.L, M = a.M, Q = a.ctaps;
+    const long long total = (long long)geo.n_phase_tiles * geo.n_cycle_tiles * geo.n_channels;
 
-    const int l0 = tile_p * PB;
-    const int pbv = min(PB, L - l0);
-    const int c_lo = (int)(((long long)l0 * M) / L);
-    const int c_hi = (int)(((long long)(l0 + pbv - 1) * M) / L);
-    const int cspan = c_hi - c_lo;
-    const int KP = Q + cspan;
-    const long long j0 = geo.jc0 + (long long)tile_j * JB;
-    const int rawn = (JB - 1) * M + cspan + Q;
-    const long long S0 = j0 * M + c_lo - (Q - 1);
-
-    const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
-    const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
-
-    // ---- stage the input span, split it into byte planes --------------------------------------------------------
-    const long long jc_last = (a.o0 + a.n_out - 1) / L;
-    const int jv = (int)min((long long)JB, jc_last - j0 + 1);   // cycles of this tile that hold outputs of the call
-    const int need = min(rawn, (jv - 1) * M + cspan + Q);
-    const int nchunks = (KP + kIKC - 1) / kIKC;
-    const signed char *gt = a.imma_tiles + (size_t)tile_p * a.imma_nchunks * kIGStage;
-    auto produce_g = [&](int c, int buf) {                     // one thread: the chunk's G'' planes, one bulk copy
+    auto chan_x = [&](int ch) { return a.x ? a.x + (long long)ch * a.x_stride : nullptr; };
+    // one thread: the G'' planes of chunk c of a phase tile into the stage of global chunk g
+    auto produce_g = [&](int tile_p, int c, long long g) {
+        const int buf = (int)(g % kIStages);
+        if (g >= kIStages) mbar_wait(&s_empty[buf], (uint32_t)((g / kIStages - 1) & 1));
+        const signed char *gt = a.imma_tiles + ((size_t)tile_p * a.imma_nchunks + c) * kIGStage;
         mbar_expect_tx(&s_full[buf], (uint32_t)kIGStage);
-        tma_bulk_g2s(stages + buf * kIStage, gt + (size_t)c * kIGStage, (uint32_t)kIGStage, &s_full[buf]);
+        tma_bulk_g2s(stages + buf * kIStage, gt, (uint32_t)kIGStage, &s_full[buf]);
     };
+
     if (tid == 0) {
+        mbar_init(&span_bar[0], 1);
+        mbar_init(&span_bar[1], 1);
         for (int i = 0; i < kIStages; ++i) {
             mbar_init(&s_full[i], NT + 1);                     // every thread's share of X'' + the expect_tx of the G'' copy
             mbar_init(&s_empty[i], NT);
         }
-        produce_g(0, 0);                                       // the taps do not wait for the samples
-        if (nchunks > 1) produce_g(1, 1);
-    }
-    bool bulk;
-    const int raw_off = poly_stage_span<NT>(a, xc, hc, S0, need, raw, bar, tid, &bulk);
-    __syncthreads();
-    if (bulk) mbar_wait(bar, 0);
-    {
-        // eight samples per step: low bytes -> rawl, high bytes -> rawh, both indexed like raw
-        const int nvec = (raw_off + need + 7) >> 3;
-        for (int v = tid; v < nvec; v += NT) {
-            const uint4 w = reinterpret_cast<const uint4 *>(raw)[v];
-            uint2 lo, hi;
-            lo.x = __byte_perm(w.x, w.y, 0x6420); lo.y = __byte_perm(w.z, w.w, 0x6420);
-            hi.x = __byte_perm(w.x, w.y, 0x7531); hi.y = __byte_perm(w.z, w.w, 0x7531);
-            reinterpret_cast<uint2 *>(rawl)[v] = lo;
-            reinterpret_cast<uint2 *>(rawh)[v] = hi;
-        }
     }
     __syncthreads();
 
-    // ---- chunk producer: this thread's 2 x 16 bytes of a chunk's X'' planes ----------------------------------------
-    auto produce_x = [&](int c, int buf) {
-        unsigned char *st = stages + buf * kIStage + kIGStage;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int task = tid + t * NT;                     // (cycle, plane, 16-byte quarter)
-            const int xj = task & 63, xplane = (task >> 6) & 1, xq = task >> 7;
-            const unsigned char *src = (xplane ? rawh : rawl) + raw_off + xj * M + c * kIKC + 16 * xq;   // any alignment
-            const uint32_t addr = smem_u32(src);
-            const uint32_t sh = (addr & 3u) * 8u;
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(src - (addr & 3u));
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-            uint4 o;
-            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
-            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
-            *reinterpret_cast<uint4 *>(st + xplane * (kIJB * kIPitch) + xj * kIPitch + 16 * xq) = o;
-        }
-        mbar_arrive(&s_full[buf]);
-    };
+    long long g0 = 0;                                          // global chunk index of the current tile's chunk 0
+    uint32_t span_phase[2] = {0, 0};
+    ImmaTile T = imma_tile(a, geo, blockIdx.x);
+    if (tid == 0 && (long long)blockIdx.x < total) {           // first tile: nothing was prefetched
+        const int16_t *xc = chan_x(T.ch);
+        const PolySpanPlan sp = poly_span_plan(a, xc, T.S0, T.need);
+        if (sp.tma) poly_span_issue(sp, xc, raw0, &span_bar[0]);
+        for (int c0 = 0; c0 < kIAhead && c0 < T.nchunks; ++c0) produce_g(T.tile_p, c0, c0);
+    }
 
-    int acc[kIPlanes + 1][4][4];                               // [weight 2^(8d)][n tile][c fragment]
-#pragma unroll
-    for (int d = 0; d <= kIPlanes; ++d)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[d][ni][e] = 0;
+    int it = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int rb = it & 1;
+        int16_t *raw = raw0 + rb * geo.raw_cap;
+        const int16_t *xc = chan_x(T.ch);
+        const int16_t *hc = a.hist ? a.hist + (long long)T.ch * a.hist_len : nullptr;
+        const int l0 = T.l0, pbv = T.pbv, nchunks = T.nchunks;
+        const long long j0 = T.j0;
 
-#pragma unroll
-    for (int c0 = 0; c0 < 2; ++c0)
-        if (c0 < nchunks) produce_x(c0, c0);
-
-    // ldmatrix row addresses: lane -> matrix lane/8, row lane%8.  A (16 phases x 32 k-bytes): matrices (rows 0-7 | 8-15)
-    // x (bytes 0-15 | 16-31); B (8 cycles x 32 k-bytes per n tile, two n tiles per x4): (n tile) x (bytes 0-15 | 16-31)
-    const int mat = lane >> 3, mr = lane & 7;
-    const int a_off = (16 * wm + mr + 8 * (mat & 1)) * kIPitch + 16 * (mat >> 1);
-    const int b_off = (32 * wn + mr + 8 * (mat >> 1)) * kIPitch + 16 * (mat & 1);
-    for (int c = 0; c < nchunks; ++c) {
-        const int buf = c % kIStages;
-        const int nxt = (c + 2) % kIStages;
-        mbar_wait(&s_full[buf], (c / kIStages) & 1);
-        const unsigned char *gs = stages + buf * kIStage;
-        const unsigned char *xs = gs + kIGStage;
-#pragma unroll
-        for (int ks = 0; ks < kIKC / 32; ++ks) {
-            uint32_t bl[2][4], bh[2][4];
-#pragma unroll
-            for (int np = 0; np < 2; ++np) {
-                ldsm_x4(bl[np], xs + b_off + np * (16 * kIPitch) + 32 * ks);
-                ldsm_x4(bh[np], xs + kIJB * kIPitch + b_off + np * (16 * kIPitch) + 32 * ks);
+        // ---- the span: bulk part already in flight, fringes by the threads, then split into byte planes --------
+        const PolySpanPlan sp = poly_span_plan(a, xc, T.S0, T.need);
+        poly_span_fringes<NT>(a, xc, hc, T.S0, T.need, sp, raw, tid);
+        __syncthreads();                                       // fringes written; every thread is done with the planes of the previous tile
+        if (sp.tma) { mbar_wait(&span_bar[rb], span_phase[rb]); span_phase[rb] ^= 1; }
+        const int raw_off = sp.off;
+        {
+            // eight samples per step: low bytes -> rawl, high bytes -> rawh, both indexed like raw
+            const int nvec = (raw_off + T.need + 7) >> 3;
+            for (int v = tid; v < nvec; v += NT) {
+                const uint4 w = reinterpret_cast<const uint4 *>(raw)[v];
+                uint2 lo, hi;
+                lo.x = __byte_perm(w.x, w.y, 0x6420); lo.y = __byte_perm(w.z, w.w, 0x6420);
+                hi.x = __byte_perm(w.x, w.y, 0x7531); hi.y = __byte_perm(w.z, w.w, 0x7531);
+                reinterpret_cast<uint2 *>(rawl)[v] = lo;
+                reinterpret_cast<uint2 *>(rawh)[v] = hi;
             }
+        }
+        __syncthreads();
+
+        // prefetch the next tile's span into the other buffer (its last readers passed the barrier above)
+        const long long tn = t + gridDim.x;
+        ImmaTile Tn = T;
+        if (tn < total) {
+            Tn = imma_tile(a, geo, tn);
+            if (tid == 0) {
+                const int16_t *xn = chan_x(Tn.ch);
+                const PolySpanPlan spn = poly_span_plan(a, xn, Tn.S0, Tn.need);
+                if (spn.tma) poly_span_issue(spn, xn, raw0 + (rb ^ 1) * geo.raw_cap, &span_bar[rb ^ 1]);
+            }
+        }
+
+        // ---- chunk producer: this thread's 2 x 16 bytes of a chunk's X'' planes ----------------------------------------
+        auto produce_x = [&](int c, long long g) {
+            const int buf = (int)(g % kIStages);
+            if (g >= kIStages) mbar_wait(&s_empty[buf], (uint32_t)((g / kIStages - 1) & 1));
+            unsigned char *st = stages + buf * kIStage + kIGStage;
 #pragma unroll
-            for (int i = 0; i < kIPlanes; ++i) {
-                uint32_t af[4];
-                ldsm_x4(af, gs + i * (kIPB * kIPitch) + a_off + 32 * ks);
+            for (int q2 = 0; q2 < 2; ++q2) {
+                const int task = tid + q2 * NT;                // (cycle, plane, 16-byte quarter)
+                const int xj = task & 63, xplane = (task >> 6) & 1, xq = task >> 7;
+                const unsigned char *src = (xplane ? rawh : rawl) + raw_off + xj * M + c * kIKC + 16 * xq;   // any alignment
+                const uint32_t addr = smem_u32(src);
+                const uint32_t sh = (addr & 3u) * 8u;
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(src - (addr & 3u));
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                uint4 o;
+                o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+                o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+                *reinterpret_cast<uint4 *>(st + xplane * (kIJB * kIPitch) + xj * kIPitch + 16 * xq) = o;
+            }
+            mbar_arrive(&s_full[buf]);
+        };
+
+        int acc[kIPlanes + 1][4][4];                           // [weight 2^(8d)][n tile][c fragment]
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    const int np = ni >> 1, q = (ni & 1) * 2;
-                    imma_s8u8(acc[i][ni], af, bl[np][q], bl[np][q + 1]);
-                    imma_s8s8(acc[i + 1][ni], af, bh[np][q], bh[np][q + 1]);
+        for (int d = 0; d <= kIPlanes; ++d)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[d][ni][e] = 0;
+
+#pragma unroll
+        for (int c0 = 0; c0 < kIAhead; ++c0)
+            if (c0 < nchunks) produce_x(c0, g0 + c0);
+
+        // ldmatrix row addresses: lane -> matrix lane/8, row lane%8.  A (16 phases x 32 k-bytes): matrices (rows 0-7 | 8-15)
+        // x (bytes 0-15 | 16-31); B (8 cycles x 32 k-bytes per n tile, two n tiles per x4): (n tile) x (bytes 0-15 | 16-31)
+        const int mat = lane >> 3, mr = lane & 7;
+        const int a_off = (16 * wm + mr + 8 * (mat & 1)) * kIPitch + 16 * (mat >> 1);
+        const int b_off = (32 * wn + mr + 8 * (mat >> 1)) * kIPitch + 16 * (mat & 1);
+        for (int c = 0; c < nchunks; ++c) {
+            const long long g = g0 + c;
+            const int buf = (int)(g % kIStages);
+            mbar_wait(&s_full[buf], (uint32_t)((g / kIStages) & 1));
+            const unsigned char *gs = stages + buf * kIStage;
+            const unsigned char *xs = gs + kIGStage;
+            // the asm statements keep their order: the tap fragments are double-buffered by hand, so that plane i+1 is
+            // on its way from shared memory while plane i's eight IMMAs issue
+#pragma unroll
+            for (int ks = 0; ks < kIKC / 32; ++ks) {
+                uint32_t bl[2][4], bh[2][4], af[2][4];
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {
+                    ldsm_x4(bl[np], xs + b_off + np * (16 * kIPitch) + 32 * ks);
+                    ldsm_x4(bh[np], xs + kIJB * kIPitch + b_off + np * (16 * kIPitch) + 32 * ks);
+                }
+                ldsm_x4(af[0], gs + a_off + 32 * ks);
+#pragma unroll
+                for (int i = 0; i < kIPlanes; ++i) {
+                    if (i + 1 < kIPlanes) ldsm_x4(af[(i + 1) & 1], gs + (i + 1) * (kIPB * kIPitch) + a_off + 32 * ks);
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int np = ni >> 1, q = (ni & 1) * 2;
+                        imma_s8u8(acc[i][ni], af[i & 1], bl[np][q], bl[np][q + 1]);
+                        imma_s8s8(acc[i + 1][ni], af[i & 1], bh[np][q], bh[np][q + 1]);
+                    }
                 }
             }
-        }
-        mbar_arrive(&s_empty[buf]);
-        if (c + 2 < nchunks) {
-            if (c >= 1) mbar_wait(&s_empty[nxt], ((c - 1) / kIStages) & 1);
-            if (tid == 0) produce_g(c + 2, nxt);
-            produce_x(c + 2, nxt);
-        }
-    }
-
-    // ---- epilogue: C[row = lane/4 (+8)][col = 2*(lane%4) + {0,1}] of n tile ni ---------------------------------------
-    const long long o_end = a.o0 + a.n_out;
-    int16_t *ych = a.y + (long long)ch * a.y_stride;
-    // First pass, straight-line: sum_d acc_d 256^d fits a 64-bit integer (|.| < 2^62), so the six accumulators are
-    // combined with integer multiply-adds and converted once; every output is finished and stored, near-integer hits
-    // are only noted.  (Converting and combining in FP64 behind a branch per output cost as much as the MMA loop.)
-    uint32_t guard_hits = 0;                                   // bit ni*4 + e
-    const double out_scale = a.imma_scale * 16777216.0;        // the high half carries 256^3
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int l = 16 * wm + 8 * h + (lane >> 2);
-        const bool l_ok = l < pbv;
-        const int st = l_ok ? a.single_tap[l0 + l] : -1;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int e2 = 0; e2 < 2; ++e2) {
-                const int e = 2 * h + e2;
-                const int j = 32 * wn + 8 * ni + 2 * (lane & 3) + e2;
-                const long long o = (j0 + j) * (long long)L + l0 + l;
-                const bool valid = l_ok && o >= a.o0 && o < o_end;
-                const long long lo = (long long)acc[0][ni][e] + (long long)acc[1][ni][e] * 256 + (long long)acc[2][ni][e] * 65536;
-                const long long hi = (long long)acc[3][ni][e] + (long long)acc[4][ni][e] * 256 + (long long)acc[5][ni][e] * 65536;
-                const double s = fma((double)hi, out_scale, (double)lo * a.imma_scale);
-                const double v = __dmul_rn(s, a.gain);
-                if (MODE == LLZ_CUDA_ACC_F64 && valid && st < 0 && poly_near_nonzero_integer(v, a.imma_thr))
-                    guard_hits |= 1u << (ni * 4 + e);
-                if (valid) ych[o - a.o0] = poly_finish(v);
+            mbar_arrive(&s_empty[buf]);
+            if (c + kIAhead < nchunks) {
+                if (tid == 0) produce_g(T.tile_p, c + kIAhead, g + kIAhead);
+                produce_x(c + kIAhead, g + kIAhead);
             }
-    }
-    // knife-edge phases (one tap, 1 - 2^-53 for the L-th band prototype): one exact FP64 product per output
+        }
+        g0 += nchunks;
+        // the next tile's first tap chunks arrive during this tile's epilogue
+        if (tid == 0 && tn < total) {
+            for (int c0 = 0; c0 < kIAhead && c0 < Tn.nchunks; ++c0) produce_g(Tn.tile_p, c0, g0 + c0);
+        }
+
+        // ---- epilogue: C[row = lane/4 (+8)][col = 2*(lane%4) + {0,1}] of n tile ni ---------------------------------------
+        const long long o_end = a.o0 + a.n_out;
+        int16_t *ych = a.y + (long long)T.ch * a.y_stride;
+        // First pass, straight-line: sum_d acc_d 256^d fits a 64-bit integer (|.| < 2^62), so the six accumulators are
+        // combined with integer multiply-adds and converted once; every output is finished and stored, near-integer hits
+        // are only noted.  (Converting and combining in FP64 behind a branch per output cost as much as the MMA loop.)
+        uint32_t guard_hits = 0;                               // bit ni*4 + e
+        const double out_scale = a.imma_scale * 16777216.0;    // the high half carries 256^3
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = 16 * wm + 8 * h + (lane >> 2);
+            const bool l_ok = l < pbv;
+            const int st = l_ok ? a.single_tap[l0 + l] : -1;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    const int e = 2 * h + e2;
+                    const int j = 32 * wn + 8 * ni + 2 * (lane & 3) + e2;
+                    const long long o = (j0 + j) * (long long)L + l0 + l;
+                    const bool valid = l_ok && o >= a.o0 && o < o_end;
+                    const long long lo = (long long)acc[0][ni][e] + (long long)acc[1][ni][e] * 256 + (long long)acc[2][ni][e] * 65536;
+                    const long long hi = (long long)acc[3][ni][e] + (long long)acc[4][ni][e] * 256 + (long long)acc[5][ni][e] * 65536;
+                    const double s = fma((double)hi, out_scale, (double)lo * a.imma_scale);
+                    const double v = __dmul_rn(s, a.gain);
+                    if (MODE == LLZ_CUDA_ACC_F64 && valid && st < 0 && poly_near_nonzero_integer(v, a.imma_thr))
+                        guard_hits |= 1u << (ni * 4 + e);
+                    if (valid) ych[o - a.o0] = poly_finish(v);
+                }
+        }
+        // knife-edge phases (one tap, 1 - 2^-53 for the L-th band prototype): one exact FP64 product per output
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        const int l = 16 * wm + 8 * h + (lane >> 2);
-        const int st = (l < pbv) ? a.single_tap[l0 + l] : -1;
-        if (st < 0) continue;
-        for (int idx = 0; idx < 8; ++idx) {
-            const int j = 32 * wn + 8 * (idx >> 1) + 2 * (lane & 3) + (idx & 1);
-            const long long o = (j0 + j) * (long long)L + l0 + l;
-            if (o < a.o0 || o >= o_end) continue;
-            const long long base = (o * M) / L;
-            ych[o - a.o0] = poly_finish(__dmul_rn(__dmul_rn((double)poly_sample(a, xc, hc, base - st), a.cbank[(long long)(l0 + l) * Q + st]), a.gain));
-        }
-    }
-    __syncwarp();
-
-    // Second look at the outputs that came within the (wide) integer-evaluation band of an integer, ~3e-5 of them: the
-    // whole warp evaluates such an output again as an FP64 dot product (lane-strided FMAs, shuffle reduction), which is
-    // good to the narrow band of the FP64 kernels; only what is STILL near an integer (~1e-8) goes to the reference's
-    // own serial order.  (Sending every first-level hit to the serial recompute -- 257 dependent global loads on one
-    // lane -- cost more than the tile's tensor work.)
-    unsigned pending = __ballot_sync(0xffffffffu, guard_hits != 0);
-    while (pending) {
-        const int src = __ffs(pending) - 1;
-        int idx = (lane == src) ? __ffs(guard_hits) - 1 : 0;
-        idx = __shfl_sync(0xffffffffu, idx, src);
-        const int ni = idx >> 2, e = idx & 3;
-        const int l = 16 * wm + 8 * (e >> 1) + (src >> 2);
-        const int j = 32 * wn + 8 * ni + 2 * (src & 3) + (e & 1);
-        const long long o = (j0 + j) * (long long)L + l0 + l;             // warp-uniform
-        const long long base = (o * M) / L;
-        const double *row = a.cbank + (long long)(l0 + l) * Q;
-        double part = 0.0;
-        for (int k = lane; k < Q; k += 32) part = fma((double)poly_sample(a, xc, hc, base - k), row[k], part);
-#pragma unroll
-        for (int m = 16; m; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-        if (lane == src) {
-            double v = __dmul_rn(part, a.gain);
-            if (poly_near_nonzero_integer(v, a.guard_thr)) {
-                v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
-                atomicAdd(a.guard_count, 1ULL);
+        for (int h = 0; h < 2; ++h) {
+            const int l = 16 * wm + 8 * h + (lane >> 2);
+            const int st = (l < pbv) ? a.single_tap[l0 + l] : -1;
+            if (st < 0) continue;
+            for (int idx = 0; idx < 8; ++idx) {
+                const int j = 32 * wn + 8 * (idx >> 1) + 2 * (lane & 3) + (idx & 1);
+                const long long o = (j0 + j) * (long long)L + l0 + l;
+                if (o < a.o0 || o >= o_end) continue;
+                const long long base = (o * M) / L;
+                ych[o - a.o0] = poly_finish(__dmul_rn(__dmul_rn((double)poly_sample(a, xc, hc, base - st), a.cbank[(long long)(l0 + l) * Q + st]), a.gain));
             }
-            ych[o - a.o0] = poly_finish(v);
-            guard_hits &= guard_hits - 1;
         }
-        pending = __ballot_sync(0xffffffffu, guard_hits != 0);
+        __syncwarp();
+
+        // Second look at the outputs that came within the (wide) integer-evaluation band of an integer, ~3e-5 of them: the
+        // whole warp evaluates such an output again as an FP64 dot product (lane-strided FMAs, shuffle reduction), which is
+        // good to the narrow band of the FP64 kernels; only what is STILL near an integer (~1e-8) goes to the reference's
+        // own serial order.  (Sending every first-level hit to the serial recompute -- 257 dependent global loads on one
+        // lane -- cost more than the tile's tensor work.)
+        unsigned pending = __ballot_sync(0xffffffffu, guard_hits != 0);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            int idx = (lane == src) ? __ffs(guard_hits) - 1 : 0;
+            idx = __shfl_sync(0xffffffffu, idx, src);
+            const int ni = idx >> 2, e = idx & 3;
+            const int l = 16 * wm + 8 * (e >> 1) + (src >> 2);
+            const int j = 32 * wn + 8 * ni + 2 * (src & 3) + (e & 1);
+            const long long o = (j0 + j) * (long long)L + l0 + l;         // warp-uniform
+            const long long base = (o * M) / L;
+            const double *row = a.cbank + (long long)(l0 + l) * Q;
+            double part = 0.0;
+            for (int k = lane; k < Q; k += 128) {              // four independent sample / tap loads in flight per lane
+                int xv[4];
+                double gv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + 32 * u;
+                    const bool in = kk < Q;
+                    xv[u] = in ? poly_sample(a, xc, hc, base - kk) : 0;
+                    gv[u] = in ? row[kk] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) part = fma((double)xv[u], gv[u], part);
+            }
+#pragma unroll
+            for (int m = 16; m; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+            if (lane == src) {
+                double v = __dmul_rn(part, a.gain);
+                if (poly_near_nonzero_integer(v, a.guard_thr)) {
+                    v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
+                    atomicAdd(a.guard_count, 1ULL);
+                }
+                ych[o - a.o0] = poly_finish(v);
+                guard_hits &= guard_hits - 1;
+            }
+            pending = __ballot_sync(0xffffffffu, guard_hits != 0);
+        }
+        T = Tn;
     }
 }
 
@@ -359,14 +431,21 @@ int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
     const int cspan_max = (int)(((long long)kIPB * a.M) / a.L) + 2;
     // the byte planes are read up to 31 bytes past the last needed sample (chunk padding meets zero taps)
     geo.raw_cap = ((kIJB - 1) * a.M + cspan_max + a.ctaps + kIKC + 16 + 15) & ~15;
-    const size_t smem = kIHeader + (size_t)kIStages * kIStage + (size_t)geo.raw_cap * 2 + 2 * ((size_t)geo.raw_cap + 32);
+    geo.n_channels = n_channels;
+    const size_t smem = kIHeader + (size_t)kIStages * kIStage + 2 * (size_t)geo.raw_cap * 2 + 2 * ((size_t)geo.raw_cap + 32);
     if (smem > 226 * 1024) return 0;
     if (a.acc != LLZ_CUDA_ACC_F64) return 0;
     auto kern = poly_bank_imma_kernel<LLZ_CUDA_ACC_F64>;
     LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
-    if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
-    kern<<<dim3((unsigned)blocks, (unsigned)n_channels), kINT, smem, stream>>>(a, geo);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sms = 148;
+    }
+    const long long tiles = (long long)geo.n_cycle_tiles * geo.n_phase_tiles * n_channels;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);           // persistent: one CTA per SM
+    kern<<<grid, kINT, smem, stream>>>(a, geo);
     LLZ_CUDA_TRY(cudaGetLastError());
     return 1;
 }

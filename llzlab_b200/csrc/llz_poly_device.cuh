@@ -28,36 +28,65 @@ __device__ __forceinline__ int poly_sample(const PolyLaunch &a, const int16_t *x
 // aligned and hold need + 16 elements.  (The first version filled every tile that touched the history or the end of
 // the input sample by sample; a drop-in frame, where every tile does, spent 20-30 us in that loop.)  *bulk tells the
 // caller to mbar_wait(bar, 0) after its __syncthreads.
-template <int NT>
-__device__ __forceinline__ int poly_stage_span(const PolyLaunch &a, const int16_t *xc, const int16_t *hc, long long S0,
-                                               int need, int16_t *raw, uint64_t *bar, int tid, bool *bulk)
+struct PolySpanPlan {
+    int off;                   // raw[off + e] = X(S0 + e)
+    bool tma;                  // part of the span arrives by a bulk copy
+    long long rel_al, lo_al;   // bulk copy: raw + (lo_al - rel_al) <- xc + lo_al
+    uint32_t bytes;
+    int e_lo, e_hi;            // the bulk run covers elements [e_lo, e_hi); the threads fill the rest of [0, need)
+};
+
+__device__ __forceinline__ PolySpanPlan poly_span_plan(const PolyLaunch &a, const int16_t *xc, long long S0, int need)
 {
+    PolySpanPlan p;
     const long long rel = S0 - a.in0;                          // x index of element 0 (negative: history)
-    const long long rel_al = rel & ~7LL;
-    const int off = (int)(rel - rel_al);
+    p.rel_al = rel & ~7LL;
+    p.off = (int)(rel - p.rel_al);
     const long long lo = rel > 0 ? rel : 0;
     const long long hi = (rel + need < a.n_in) ? rel + need : a.n_in;
     long long lo_al = lo & ~7LL;                               // >= max(rel_al, 0): inside x, at or after raw[0]
     long long hi_al = (hi + 7) & ~7LL;
     if (hi_al > a.n_in) hi_al = hi & ~7LL;
-    const bool tma = xc != nullptr && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && hi_al > lo_al;
-    if (!tma) lo_al = hi_al = lo;                              // no aligned run: the two fringes meet at lo
-    if (tma && tid == 0) {
-        const uint32_t bytes = (uint32_t)(hi_al - lo_al) * 2u;
+    p.tma = xc != nullptr && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && hi_al > lo_al;
+    if (!p.tma) lo_al = hi_al = lo;                            // no aligned run: the two fringes meet at lo
+    p.lo_al = lo_al;
+    p.bytes = (uint32_t)(hi_al - lo_al) * 2u;
+    // a span that ends before x[0] or starts beyond the input has no bulk run
+    p.e_lo = (int)min(max(lo_al - rel, 0LL), (long long)need);
+    p.e_hi = (int)min(max(hi_al - rel, (long long)p.e_lo), (long long)need);
+    return p;
+}
+
+// one thread, barrier initialised (count 1)
+__device__ __forceinline__ void poly_span_issue(const PolySpanPlan &p, const int16_t *xc, int16_t *raw, uint64_t *bar)
+{
+    mbar_expect_tx(bar, p.bytes);
+    tma_bulk_g2s(raw + (p.lo_al - p.rel_al), xc + p.lo_al, p.bytes, bar);
+}
+
+template <int NT>
+__device__ __forceinline__ void poly_span_fringes(const PolyLaunch &a, const int16_t *xc, const int16_t *hc, long long S0,
+                                                  int need, const PolySpanPlan &p, int16_t *raw, int tid)
+{
+    int16_t *dst = raw + p.off;
+#pragma unroll 4
+    for (int e = tid; e < p.e_lo; e += NT) dst[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+#pragma unroll 4
+    for (int e = p.e_hi + tid; e < need; e += NT) dst[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+}
+
+template <int NT>
+__device__ __forceinline__ int poly_stage_span(const PolyLaunch &a, const int16_t *xc, const int16_t *hc, long long S0,
+                                               int need, int16_t *raw, uint64_t *bar, int tid, bool *bulk)
+{
+    const PolySpanPlan p = poly_span_plan(a, xc, S0, need);
+    if (p.tma && tid == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s(raw + (lo_al - rel_al), xc + lo_al, bytes, bar);
+        poly_span_issue(p, xc, raw, bar);
     }
-    int16_t *dst = raw + off;
-    // the bulk run covers elements [e_lo, e_hi); a span that ends before x[0] or starts beyond the input has none
-    const int e_lo = (int)min(max(lo_al - rel, 0LL), (long long)need);
-    const int e_hi = (int)min(max(hi_al - rel, (long long)e_lo), (long long)need);
-#pragma unroll 4
-    for (int e = tid; e < e_lo; e += NT) dst[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
-#pragma unroll 4
-    for (int e = e_hi + tid; e < need; e += NT) dst[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
-    *bulk = tma;
-    return off;
+    poly_span_fringes<NT>(a, xc, hc, S0, need, p, raw, tid);
+    *bulk = p.tma;
+    return p.off;
 }
 
 // saturate, truncate toward zero: llz_resample.c:596-601.  Truncating first (F2I.TRUNC saturates at the int32

@@ -564,8 +564,7 @@ int poly_upload_plan(PolyBank *b)
         b->d_cbankT16h = b->d_cbankT16h_base + pad * L;
         b->d_cbankT16l = b->d_cbankT16l_base + pad * L;
     }
-    const char *imma = getenv("LLZ_BANK_IMMA");
-    if (imma && atoi(imma) != 0 && b->acc == LLZ_CUDA_ACC_F64 && L >= 16 && p.shift == 0 && p.frame_len == 0) {
+    if (b->acc == LLZ_CUDA_ACC_F64 && L >= 16 && p.shift == 0 && p.frame_len == 0) {
         // exact mode on the integer tensor cores: int8 digit planes of the taps in the kernel's tile layout
         std::vector<signed char> tiles;
         b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, &tiles, &b->imma_shift, &b->imma_eps);

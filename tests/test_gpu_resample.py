@@ -261,12 +261,14 @@ def test_c3_shape_spot_checks(zlib, port, cuda):
     bank.close()
 
 
+@pytest.mark.parametrize("no_imma", ["0", "1"])
 @pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0)])
-def test_bank_exact_mode_on_the_integer_tensor_cores(zlib, port, cuda, monkeypatch, L_, M, k):
-    """LLZ_BANK_IMMA=1: taps as five int8 digit planes, samples as two byte planes, exact s32 accumulation on the INT8
-    tensor cores, a two-level near-integer guard -- the int16 output must still be the reference's, bit for bit."""
+def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, monkeypatch, L_, M, k, no_imma):
+    """The exact mode's two tile kernels: INT8 tensor cores (default: taps as five int8 digit planes, samples as two byte
+    planes, exact s32 accumulation, a two-level near-integer guard) and FP64 tensor cores (LLZ_BANK_NO_IMMA=1) -- the
+    int16 output must be the reference's, bit for bit, from both."""
     torch = cuda
-    monkeypatch.setenv("LLZ_BANK_IMMA", "1")
+    monkeypatch.setenv("LLZ_BANK_NO_IMMA", no_imma)
     C_ = 3
     bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, C_, k_override=k)
     plan = port.resample_plan(L_, M, 1, k)
