@@ -313,7 +313,8 @@ def run_cuda(args):
         dtype_name = "s16 io / f32 acc" if args.dtype == "f32" else "s16 io / f64 acc"
         fma_peak_nominal = FP32_NOMINAL_TFLOPS if args.dtype == "f32" else FP64_NOMINAL_TFLOPS
         fma_dtype = z.F32 if args.dtype == "f32" else z.F64
-        kernel = "poly_slide_kernel" if wl["L"] == 1 else ("poly_bank_hmma_kernel" if args.dtype == "f32" else "poly_bank_dmma_kernel")
+        exact_tiles = "poly_bank_dmma_kernel" if os.environ.get("LLZ_BANK_NO_IMMA", "0") not in ("", "0") else "poly_bank_imma_kernel"
+        kernel = "poly_slide_kernel" if wl["L"] == 1 else ("poly_bank_hmma_kernel" if args.dtype == "f32" else exact_tiles)
 
         def step():
             if halo:
@@ -495,6 +496,11 @@ def run_cuda(args):
                     "frac_of_nominal": ach_tf / fma_peak_nominal,
                     "note": "direct-form FIR on CUDA cores: the FMA pipe, not HBM, is the binding roof "
                             f"(ceiling of the HBM fraction = {fma_peak_nominal * 1e12 / flop_per_out * bytes_per_out / 1e9 / hbm_peak:.3f})"}
+        if kernel == "poly_bank_imma_kernel":
+            fma_pipe["note"] = ("exact integer evaluation on the INT8 tensor cores (ten IMMA digit products per multiply-add, "
+                                "1144 TOP/s measured = 114 TFLOP/s of exact multiply-adds): the fraction above is against the "
+                                "FP64 FMA pipe this kernel no longer uses, i.e. the speed relative to the FP64 roof")
+            fma_pipe["frac_of_imma_roof"] = ach_tf / 114.4
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
