@@ -802,7 +802,14 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if ((a.ctaps + cspan) / a.ctaps > 2.5) return 0;
     constexpr size_t kLimit = 226 * 1024;
     if (a.acc == LLZ_CUDA_ACC_F32) {
-        // fast mode: exact-product fp16 split on the tensor cores unless LLZ_BANK_NO_HMMA asks for the FFMA tile
+        // fast mode: exact-product fp16 split on the tensor cores unless LLZ_BANK_NO_HMMA asks for the FFMA tile.  (The
+        // three-digit integer evaluation of llz_cuda_polybank_imma.cu is correct here too but slower -- 82 against 91
+        // Gsamples/s on C4: its per-tile fixed cost is the same as the exact mode's -- so it stays behind
+        // LLZ_BANK_IMMA_FAST=1, which also makes the shim build its tables.)
+        if (a.imma_tiles) {
+            const int rc = poly_bank_imma_launch(a, n_channels, stream);
+            if (rc != 0) return rc;
+        }
         if (a.cbankT16h && a.cbankT16l && !getenv("LLZ_BANK_NO_HMMA")) {
             const int rc = launch_bank_hmma<16>(a, n_channels, stream);
             if (rc != 0) return rc;

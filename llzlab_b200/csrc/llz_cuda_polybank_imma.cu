@@ -43,14 +43,14 @@ namespace {
 constexpr int kIPB = 64, kIJB = 64;                   // CTA tile: phases x cycles
 constexpr int kIKC = 64;                              // k'' per chunk = two IMMA.16832 steps per pipeline round
 constexpr int kINT = 256;                             // 8 warps = 4 (phases) x 2 (cycles), warp tile 16 x 32
-constexpr int kIPlanes = 5;                           // signed base-256 digits of a tap
+constexpr int kIPlanesExact = 5, kIPlanesFast = 3;    // signed base-256 digits of a tap: exact mode / fast mode
 constexpr int kIPitch = kIKC + 16;                    // bytes per operand row in shared memory (80: conflict-free ldmatrix)
 constexpr int kIStages = 4;                            // chunk c + kIAhead is produced after chunk c is consumed
 constexpr int kIAhead = kIStages - 1;
-constexpr int kIGStage = kIPlanes * kIPB * kIPitch;   // 25,600 bytes: one chunk of G'', all planes
 constexpr int kIXStage = 2 * kIJB * kIPitch;          // 10,240 bytes: one chunk of X'', low and high byte planes
-constexpr int kIStage = kIGStage + kIXStage;
-constexpr int kITapBits = 38;                         // |g * 2^s| < 2^38: five signed digits hold +-2^39
+__host__ __device__ constexpr int imma_gstage(int planes) { return planes * kIPB * kIPitch; }   // one chunk of G'', all planes (5: 25,600 bytes)
+__host__ __device__ constexpr int imma_stage(int planes) { return imma_gstage(planes) + kIXStage; }
+constexpr int imma_tap_bits(int planes) { return 8 * planes - 2; }          // |g * 2^s| < 2^(8P-2): P signed digits hold +-2^(8P-1)
 constexpr int kIHeader = 128;
 
 struct ImmaGeom {
@@ -109,77 +109,64 @@ __device__ __forceinline__ ImmaTile imma_tile(const PolyLaunch &a, const ImmaGeo
     return T;
 }
 
-// Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The six accumulator sets cost ~230
-// registers, so only one CTA fits an SM and nothing else would hide a tile's prologue: the NEXT tile's input span is
-// therefore fetched (TMA, second span buffer) while the current tile multiplies, and its first two tap chunks while the
-// current tile runs its epilogue.  The chunk pipeline's barriers run on a chunk counter that continues across tiles.
-template <int MODE>
-__global__ void __launch_bounds__(kINT, 1)
+// Persistent and warp-specialised: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The six
+// accumulator sets cost ~230 registers, so only one CTA fits an SM and nothing else would hide a tile's prologue and
+// chunk production.  Warps 0-7 (two warpgroups, setmaxnreg 232) only wait for full stages, multiply and run the epilogue;
+// warps 8-11 (one warpgroup, setmaxnreg 40) stage and split the spans, cut the X'' chunks and issue the G'' copies, up to
+// kIStages chunks ahead of the consumers -- across tile boundaries, so the next tile's first chunks are ready while the
+// consumers still finish the current tile's outputs.  The two sides meet only on the stages' full / empty mbarriers.
+constexpr int kIConsumers = 256, kIProducers = 128;
+
+template <int MODE, int P>
+__global__ void __launch_bounds__(kIConsumers + kIProducers, 1)
 poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
 {
-    constexpr int PB = kIPB, NT = kINT;
+    constexpr int PB = kIPB, kIPlanes = P, kIGStage = imma_gstage(P), kIStage = imma_stage(P);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *span_bar = reinterpret_cast<uint64_t *>(smem_raw);                  // [2]: one per span buffer
-    uint64_t *s_full = span_bar + 2, *s_empty = s_full + kIStages;
+    uint64_t *span_bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *s_full = span_bar + 1, *s_empty = s_full + kIStages;
     unsigned char *stages = smem_raw + kIHeader;
-    int16_t *raw0 = reinterpret_cast<int16_t *>(stages + kIStages * kIStage);     // [2][raw_cap]
-    unsigned char *rawl = reinterpret_cast<unsigned char *>(raw0 + 2 * geo.raw_cap);   // [raw_cap + 32] low bytes, by span index
+    int16_t *raw = reinterpret_cast<int16_t *>(stages + kIStages * kIStage);      // [raw_cap]
+    unsigned char *rawl = reinterpret_cast<unsigned char *>(raw + geo.raw_cap);   // [raw_cap + 32] low bytes, by span index
     unsigned char *rawh = rawl + geo.raw_cap + 32;                                // [raw_cap + 32] high bytes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;                   // warp tile: phases [16*wm, +16) x cycles [32*wn, +32)
     const int L = a.L, M = a.M, Q = a.ctaps;
     const long long total = (long long)geo.n_phase_tiles * geo.n_cycle_tiles * geo.n_channels;
 
-    auto chan_x = [&](int ch) { return a.x ? a.x + (long long)ch * a.x_stride : nullptr; };
-    // one thread: the G'' planes of chunk c of a phase tile into the stage of global chunk g
-    auto produce_g = [&](int tile_p, int c, long long g) {
-        const int buf = (int)(g % kIStages);
-        if (g >= kIStages) mbar_wait(&s_empty[buf], (uint32_t)((g / kIStages - 1) & 1));
-        const signed char *gt = a.imma_tiles + ((size_t)tile_p * a.imma_nchunks + c) * kIGStage;
-        mbar_expect_tx(&s_full[buf], (uint32_t)kIGStage);
-        tma_bulk_g2s(stages + buf * kIStage, gt, (uint32_t)kIGStage, &s_full[buf]);
-    };
-
     if (tid == 0) {
-        mbar_init(&span_bar[0], 1);
-        mbar_init(&span_bar[1], 1);
+        mbar_init(span_bar, 1);
         for (int i = 0; i < kIStages; ++i) {
-            mbar_init(&s_full[i], NT + 1);                     // every thread's share of X'' + the expect_tx of the G'' copy
-            mbar_init(&s_empty[i], NT);
+            mbar_init(&s_full[i], kIProducers + 1);            // every producer thread's share of X'' + the expect_tx of the G'' copy
+            mbar_init(&s_empty[i], kIConsumers);
         }
     }
     __syncthreads();
 
-    long long g0 = 0;                                          // global chunk index of the current tile's chunk 0
-    uint32_t span_phase[2] = {0, 0};
-    ImmaTile T = imma_tile(a, geo, blockIdx.x);
-    if (tid == 0 && (long long)blockIdx.x < total) {           // first tile: nothing was prefetched
-        const int16_t *xc = chan_x(T.ch);
-        const PolySpanPlan sp = poly_span_plan(a, xc, T.S0, T.need);
-        if (sp.tma) poly_span_issue(sp, xc, raw0, &span_bar[0]);
-        for (int c0 = 0; c0 < kIAhead && c0 < T.nchunks; ++c0) produce_g(T.tile_p, c0, c0);
-    }
-
-    int it = 0;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int rb = it & 1;
-        int16_t *raw = raw0 + rb * geo.raw_cap;
-        const int16_t *xc = chan_x(T.ch);
-        const int16_t *hc = a.hist ? a.hist + (long long)T.ch * a.hist_len : nullptr;
-        const int l0 = T.l0, pbv = T.pbv, nchunks = T.nchunks;
-        const long long j0 = T.j0;
-
-        // ---- the span: bulk part already in flight, fringes by the threads, then split into byte planes --------
-        const PolySpanPlan sp = poly_span_plan(a, xc, T.S0, T.need);
-        poly_span_fringes<NT>(a, xc, hc, T.S0, T.need, sp, raw, tid);
-        __syncthreads();                                       // fringes written; every thread is done with the planes of the previous tile
-        if (sp.tma) { mbar_wait(&span_bar[rb], span_phase[rb]); span_phase[rb] ^= 1; }
-        const int raw_off = sp.off;
-        {
-            // eight samples per step: low bytes -> rawl, high bytes -> rawh, both indexed like raw
-            const int nvec = (raw_off + T.need + 7) >> 3;
-            for (int v = tid; v < nvec; v += NT) {
+    if (warp >= kIConsumers / 32) {
+        // ================================ producers ================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int ptid = tid - kIConsumers;
+        auto chan_x = [&](int ch) { return a.x ? a.x + (long long)ch * a.x_stride : nullptr; };
+        long long g = 0;                                       // global chunk counter
+        uint32_t span_phase = 0;
+        ImmaTile T = imma_tile(a, geo, blockIdx.x);
+        if (ptid == 0) {
+            const int16_t *xc = chan_x(T.ch);
+            const PolySpanPlan sp = poly_span_plan(a, xc, T.S0, T.need);
+            if (sp.tma) poly_span_issue(sp, xc, raw, span_bar);
+        }
+        for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+            const int16_t *xc = chan_x(T.ch);
+            const int16_t *hc = a.hist ? a.hist + (long long)T.ch * a.hist_len : nullptr;
+            // the span: bulk part in flight, fringes by the threads, then split into byte planes
+            const PolySpanPlan sp = poly_span_plan(a, xc, T.S0, T.need);
+            poly_span_fringes<kIProducers>(a, xc, hc, T.S0, T.need, sp, raw, ptid);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (sp.tma) { mbar_wait(span_bar, span_phase); span_phase ^= 1; }
+            const int raw_off = sp.off;
+            const int nvec = (raw_off + T.need + 7) >> 3;      // eight samples per step, both planes indexed like raw
+            for (int v = ptid; v < nvec; v += kIProducers) {
                 const uint4 w = reinterpret_cast<const uint4 *>(raw)[v];
                 uint2 lo, hi;
                 lo.x = __byte_perm(w.x, w.y, 0x6420); lo.y = __byte_perm(w.z, w.w, 0x6420);
@@ -187,42 +174,63 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
                 reinterpret_cast<uint2 *>(rawl)[v] = lo;
                 reinterpret_cast<uint2 *>(rawh)[v] = hi;
             }
-        }
-        __syncthreads();
-
-        // prefetch the next tile's span into the other buffer (its last readers passed the barrier above)
-        const long long tn = t + gridDim.x;
-        ImmaTile Tn = T;
-        if (tn < total) {
-            Tn = imma_tile(a, geo, tn);
-            if (tid == 0) {
-                const int16_t *xn = chan_x(Tn.ch);
-                const PolySpanPlan spn = poly_span_plan(a, xn, Tn.S0, Tn.need);
-                if (spn.tma) poly_span_issue(spn, xn, raw0 + (rb ^ 1) * geo.raw_cap, &span_bar[rb ^ 1]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // the next tile's span may now overwrite raw
+            const long long tn = t + gridDim.x;
+            const int tile_p = T.tile_p, nchunks = T.nchunks;
+            if (tn < total) {
+                T = imma_tile(a, geo, tn);
+                if (ptid == 0) {
+                    const int16_t *xn = chan_x(T.ch);
+                    const PolySpanPlan spn = poly_span_plan(a, xn, T.S0, T.need);
+                    if (spn.tma) poly_span_issue(spn, xn, raw, span_bar);
+                }
             }
-        }
-
-        // ---- chunk producer: this thread's 2 x 16 bytes of a chunk's X'' planes ----------------------------------------
-        auto produce_x = [&](int c, long long g) {
-            const int buf = (int)(g % kIStages);
-            if (g >= kIStages) mbar_wait(&s_empty[buf], (uint32_t)((g / kIStages - 1) & 1));
-            unsigned char *st = stages + buf * kIStage + kIGStage;
+            for (int c = 0; c < nchunks; ++c, ++g) {
+                const int buf = (int)(g % kIStages);
+                if (g >= kIStages) mbar_wait(&s_empty[buf], (uint32_t)((g / kIStages - 1) & 1));
+                unsigned char *st = stages + buf * kIStage;
+                if (ptid == 0) {                               // the chunk's G'' planes: one bulk copy
+                    mbar_expect_tx(&s_full[buf], (uint32_t)kIGStage);
+                    tma_bulk_g2s(st, a.imma_tiles + ((size_t)tile_p * a.imma_nchunks + c) * kIGStage, (uint32_t)kIGStage, &s_full[buf]);
+                }
 #pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2) {
-                const int task = tid + q2 * NT;                // (cycle, plane, 16-byte quarter)
-                const int xj = task & 63, xplane = (task >> 6) & 1, xq = task >> 7;
-                const unsigned char *src = (xplane ? rawh : rawl) + raw_off + xj * M + c * kIKC + 16 * xq;   // any alignment
-                const uint32_t addr = smem_u32(src);
-                const uint32_t sh = (addr & 3u) * 8u;
-                const uint32_t *w = reinterpret_cast<const uint32_t *>(src - (addr & 3u));
-                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-                uint4 o;
-                o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
-                o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
-                *reinterpret_cast<uint4 *>(st + xplane * (kIJB * kIPitch) + xj * kIPitch + 16 * xq) = o;
+                for (int q2 = 0; q2 < 4; ++q2) {               // this thread's 4 x 16 bytes of the chunk's X'' planes
+                    const int task = ptid + q2 * kIProducers;  // (cycle, plane, 16-byte quarter)
+                    const int xj = task & 63, xplane = (task >> 6) & 1, xq = task >> 7;
+                    const unsigned char *src = (xplane ? rawh : rawl) + raw_off + xj * M + c * kIKC + 16 * xq;   // any alignment
+                    const uint32_t addr = smem_u32(src);
+                    const uint32_t sh = (addr & 3u) * 8u;
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(src - (addr & 3u));
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                    uint4 o;
+                    o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+                    o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+                    *reinterpret_cast<uint4 *>(st + kIGStage + xplane * (kIJB * kIPitch) + xj * kIPitch + 16 * xq) = o;
+                }
+                mbar_arrive(&s_full[buf]);
             }
-            mbar_arrive(&s_full[buf]);
-        };
+            // the planes are rewritten at the top of the next iteration: every producer is past its last read of them
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        return;
+    }
+
+    // ================================ consumers ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int wm = warp >> 1, wn = warp & 1;                   // warp tile: phases [16*wm, +16) x cycles [32*wn, +32)
+    // ldmatrix row addresses: lane -> matrix lane/8, row lane%8.  A (16 phases x 32 k-bytes): matrices (rows 0-7 | 8-15)
+    // x (bytes 0-15 | 16-31); B (8 cycles x 32 k-bytes per n tile, two n tiles per x4): (n tile) x (bytes 0-15 | 16-31)
+    const int mat = lane >> 3, mr = lane & 7;
+    const int a_off = (16 * wm + mr + 8 * (mat & 1)) * kIPitch + 16 * (mat >> 1);
+    const int b_off = (32 * wn + mr + 8 * (mat >> 1)) * kIPitch + 16 * (mat & 1);
+    long long g0 = 0;                                          // global chunk index of the current tile's chunk 0
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        const ImmaTile T = imma_tile(a, geo, t);
+        const int16_t *xc = a.x ? a.x + (long long)T.ch * a.x_stride : nullptr;
+        const int16_t *hc = a.hist ? a.hist + (long long)T.ch * a.hist_len : nullptr;
+        const int l0 = T.l0, pbv = T.pbv, nchunks = T.nchunks;
+        const long long j0 = T.j0;
 
         int acc[kIPlanes + 1][4][4];                           // [weight 2^(8d)][n tile][c fragment]
 #pragma unroll
@@ -232,15 +240,6 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[d][ni][e] = 0;
 
-#pragma unroll
-        for (int c0 = 0; c0 < kIAhead; ++c0)
-            if (c0 < nchunks) produce_x(c0, g0 + c0);
-
-        // ldmatrix row addresses: lane -> matrix lane/8, row lane%8.  A (16 phases x 32 k-bytes): matrices (rows 0-7 | 8-15)
-        // x (bytes 0-15 | 16-31); B (8 cycles x 32 k-bytes per n tile, two n tiles per x4): (n tile) x (bytes 0-15 | 16-31)
-        const int mat = lane >> 3, mr = lane & 7;
-        const int a_off = (16 * wm + mr + 8 * (mat & 1)) * kIPitch + 16 * (mat >> 1);
-        const int b_off = (32 * wn + mr + 8 * (mat >> 1)) * kIPitch + 16 * (mat & 1);
         for (int c = 0; c < nchunks; ++c) {
             const long long g = g0 + c;
             const int buf = (int)(g % kIStages);
@@ -270,16 +269,8 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
                 }
             }
             mbar_arrive(&s_empty[buf]);
-            if (c + kIAhead < nchunks) {
-                if (tid == 0) produce_g(T.tile_p, c + kIAhead, g + kIAhead);
-                produce_x(c + kIAhead, g + kIAhead);
-            }
         }
         g0 += nchunks;
-        // the next tile's first tap chunks arrive during this tile's epilogue
-        if (tid == 0 && tn < total) {
-            for (int c0 = 0; c0 < kIAhead && c0 < Tn.nchunks; ++c0) produce_g(Tn.tile_p, c0, g0 + c0);
-        }
 
         // ---- epilogue: C[row = lane/4 (+8)][col = 2*(lane%4) + {0,1}] of n tile ni ---------------------------------------
         const long long o_end = a.o0 + a.n_out;
@@ -303,8 +294,14 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
                     const long long o = (j0 + j) * (long long)L + l0 + l;
                     const bool valid = l_ok && o >= a.o0 && o < o_end;
                     const long long lo = (long long)acc[0][ni][e] + (long long)acc[1][ni][e] * 256 + (long long)acc[2][ni][e] * 65536;
-                    const long long hi = (long long)acc[3][ni][e] + (long long)acc[4][ni][e] * 256 + (long long)acc[5][ni][e] * 65536;
-                    const double s = fma((double)hi, out_scale, (double)lo * a.imma_scale);
+                    double s;
+                    if constexpr (P == kIPlanesExact) {
+                        const long long hi = (long long)acc[3][ni][e] + (long long)acc[4][ni][e] * 256 + (long long)acc[5][ni][e] * 65536;
+                        s = fma((double)hi, out_scale, (double)lo * a.imma_scale);
+                    } else {
+                        static_assert(P == kIPlanesFast, "three or five tap digits");
+                        s = (double)(lo + (long long)acc[3][ni][e] * 16777216) * a.imma_scale;   // < 2^51: exact
+                    }
                     const double v = __dmul_rn(s, a.gain);
                     if (MODE == LLZ_CUDA_ACC_F64 && valid && st < 0 && poly_near_nonzero_integer(v, a.imma_thr))
                         guard_hits |= 1u << (ni * 4 + e);
@@ -370,7 +367,6 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
             }
             pending = __ballot_sync(0xffffffffu, guard_hits != 0);
         }
-        T = Tn;
     }
 }
 
@@ -379,14 +375,16 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
 // Host: the bank [L][Q] as int8 digit planes in the kernel's tile layout [phase tile][chunk][plane][64 phases][48 bytes].
 // Returns 0 when the bank cannot be split (all taps zero), else the number of chunks per tile; *shift = s, *eps = the
 // bound on |sum_k (g - q 2^-s) x| for |x| <= 32768.
-int poly_imma_build_tables(const double *cb, int L, int M, int Q, std::vector<signed char> *out, int *shift, double *eps)
+int poly_imma_build_tables(const double *cb, int L, int M, int Q, int planes, std::vector<signed char> *out, int *shift, double *eps)
 {
+    if (planes != kIPlanesExact && planes != kIPlanesFast) return 0;
+    const int kIGStage = imma_gstage(planes);
     double gmax = 0.0;
     for (size_t i = 0; i < (size_t)L * Q; ++i) gmax = fmax(gmax, fabs(cb[i]));
     if (!(gmax > 0.0) || !isfinite(gmax)) return 0;
     int e2 = 0;
     frexp(gmax, &e2);                                          // gmax < 2^e2
-    const int s = kITapBits - e2;
+    const int s = imma_tap_bits(planes) - e2;
     const int n_tiles = (L + kIPB - 1) / kIPB;
     int nchunks = 0;
     for (int t = 0; t < n_tiles; ++t) {
@@ -405,12 +403,12 @@ int poly_imma_build_tables(const double *cb, int L, int M, int Q, std::vector<si
                 long long q = llrint(ldexp(cb[(size_t)(l0 + l) * Q + k], s));
                 const int kk = Q - 1 + d - k;                  // reversed, shifted tap index k''
                 signed char *dst = out->data() + ((size_t)t * nchunks + kk / kIKC) * kIGStage + (size_t)l * kIPitch + kk % kIKC;
-                for (int p = 0; p < kIPlanes; ++p) {
+                for (int p = 0; p < planes; ++p) {
                     const int dg = (int)((((q % 256) + 256 + 128) % 256) - 128);   // signed digit in [-128, 127]
                     dst[(size_t)p * kIPB * kIPitch] = (signed char)dg;
                     q = (q - dg) / 256;
                 }
-                if (q != 0) return 0;                          // cannot happen for |g 2^s| < 2^38
+                if (q != 0) return 0;                          // cannot happen for |g 2^s| < 2^(8 planes - 2)
             }
         }
     }
@@ -432,10 +430,12 @@ int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
     // the byte planes are read up to 31 bytes past the last needed sample (chunk padding meets zero taps)
     geo.raw_cap = ((kIJB - 1) * a.M + cspan_max + a.ctaps + kIKC + 16 + 15) & ~15;
     geo.n_channels = n_channels;
-    const size_t smem = kIHeader + (size_t)kIStages * kIStage + 2 * (size_t)geo.raw_cap * 2 + 2 * ((size_t)geo.raw_cap + 32);
+    const bool exact = a.acc == LLZ_CUDA_ACC_F64;
+    if (!exact && a.acc != LLZ_CUDA_ACC_F32) return 0;
+    if (a.imma_planes != (exact ? kIPlanesExact : kIPlanesFast)) return 0;
+    const size_t smem = kIHeader + (size_t)kIStages * imma_stage(a.imma_planes) + (size_t)geo.raw_cap * 2 + 2 * ((size_t)geo.raw_cap + 32);
     if (smem > 226 * 1024) return 0;
-    if (a.acc != LLZ_CUDA_ACC_F64) return 0;
-    auto kern = poly_bank_imma_kernel<LLZ_CUDA_ACC_F64>;
+    auto kern = exact ? poly_bank_imma_kernel<LLZ_CUDA_ACC_F64, kIPlanesExact> : poly_bank_imma_kernel<LLZ_CUDA_ACC_F32, kIPlanesFast>;
     LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static int sms = 0;
     if (sms == 0) {
@@ -445,7 +445,7 @@ int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
     }
     const long long tiles = (long long)geo.n_cycle_tiles * geo.n_phase_tiles * n_channels;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);           // persistent: one CTA per SM
-    kern<<<grid, kINT, smem, stream>>>(a, geo);
+    kern<<<grid, kIConsumers + kIProducers, smem, stream>>>(a, geo);
     LLZ_CUDA_TRY(cudaGetLastError());
     return 1;
 }

@@ -52,7 +52,8 @@ struct PolyLaunch {
     // integer tensor-core exact mode (llz_cuda_polybank_imma.cu): the bank as int8 digit planes in the kernel's tile
     // layout, g ~ q * imma_scale (imma_scale = 2^-s); nullptr when the bank was not split
     const signed char *imma_tiles;
-    int imma_nchunks;          // chunks of 32 taps per phase tile
+    int imma_nchunks;          // chunks of 64 taps per phase tile
+    int imma_planes;           // 5: exact mode (ACC_F64), 3: fast mode (ACC_F32)
     double imma_scale;
     double imma_thr;           // guard band: guard_thr + |gain| * (tap rounding bound)
 };
@@ -64,7 +65,7 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 // exact mode on the integer tensor cores (llz_cuda_polybank_imma.cu): same return convention
 int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 // host side of the same: the bank [L][Q] as int8 digit planes in the kernel's tile layout; returns chunks per tile (0: n/a)
-int poly_imma_build_tables(const double *cb, int L, int M, int Q, std::vector<signed char> *out, int *shift, double *eps);
+int poly_imma_build_tables(const double *cb, int L, int M, int Q, int planes, std::vector<signed char> *out, int *shift, double *eps);
 // name of the kernel poly_launch would pick ("sliding" / "general"), for reporting
 const char *poly_kernel_name(const PolyLaunch &a);
 

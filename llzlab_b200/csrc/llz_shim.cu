@@ -458,7 +458,7 @@ struct PolyBank {
     uint16_t *d_cbankT16h = nullptr, *d_cbankT16l = nullptr, *d_cbankT16h_base = nullptr, *d_cbankT16l_base = nullptr;
     int bank16_exp = 0;
     signed char *d_imma_tiles = nullptr;   // int8 digit planes of the bank (llz_cuda_polybank_imma.cu)
-    int imma_nchunks = 0, imma_shift = 0;
+    int imma_nchunks = 0, imma_shift = 0, imma_planes = 0;
     double imma_eps = 0.0;                 // bound on the tap-rounding error of a full-scale dot product
     int bank_pad = 0;
     int rep = 1;             // device tables hold the bank's rows `rep` times: kernels see L*rep phases, M*rep step
@@ -564,10 +564,14 @@ int poly_upload_plan(PolyBank *b)
         b->d_cbankT16h = b->d_cbankT16h_base + pad * L;
         b->d_cbankT16l = b->d_cbankT16l_base + pad * L;
     }
-    if (b->acc == LLZ_CUDA_ACC_F64 && L >= 16 && p.shift == 0 && p.frame_len == 0) {
-        // exact mode on the integer tensor cores: int8 digit planes of the taps in the kernel's tile layout
+    const char *imma_fast = getenv("LLZ_BANK_IMMA_FAST");
+    const bool imma_f32 = b->acc == LLZ_CUDA_ACC_F32 && imma_fast && atoi(imma_fast) != 0;
+    if ((b->acc == LLZ_CUDA_ACC_F64 || imma_f32) && L >= 16 && p.shift == 0 && p.frame_len == 0) {
+        // integer tensor cores: int8 digit planes of the taps in the kernel's tile layout (five digits: exact mode,
+        // three: fast mode, the 22 significant bits of the fp16-split planes above)
         std::vector<signed char> tiles;
-        b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, &tiles, &b->imma_shift, &b->imma_eps);
+        b->imma_planes = b->acc == LLZ_CUDA_ACC_F64 ? 5 : 3;
+        b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->imma_planes, &tiles, &b->imma_shift, &b->imma_eps);
         if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
     }
     std::vector<int> order(p.order, p.order + Q), single(L);
@@ -701,6 +705,7 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.guard_count = b->d_guard;
     a.imma_tiles = b->d_imma_tiles;
     a.imma_nchunks = b->imma_nchunks;
+    a.imma_planes = b->imma_planes;
     a.imma_scale = ldexp(1.0, -b->imma_shift);
     a.imma_thr = b->guard_thr + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
     if (poly_launch(a, b->n_channels, st) != 0) return -1;

@@ -290,3 +290,22 @@ def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, monkeyp
         want = port.resample_run(plan, 1.0, x[c], n_out)
         assert np.array_equal(got[c], want), (L_, M, c, int(np.abs(got[c].astype(np.int32) - want).max()))
     bank.close()
+
+
+def test_bank_fast_mode_on_the_integer_tensor_cores(zlib, port, cuda, monkeypatch):
+    """LLZ_BANK_IMMA_FAST=1: the fast mode as a three-digit integer evaluation (22 significant tap bits, like the fp16 split):
+    within 1 LSB of the reference, knife-edge phase exact."""
+    torch = cuda
+    monkeypatch.setenv("LLZ_BANK_IMMA_FAST", "1")
+    L_, M, k = 320, 147, 128
+    bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, 2, k_override=k, acc=zlib.ACC_F32)
+    n_in = bank.info.num_in
+    x = np.stack([port.lcg_s16(n_in, 77 + c) for c in range(2)])
+    n_out = bank.out_len(n_in)
+    want = oracle_resample(port, L_, M, 1, k, 1.0, x, n_out).astype(np.int32)
+    dy = torch.zeros(2, n_out, dtype=torch.int16, device="cuda")
+    bank.run(torch.from_numpy(x).cuda(), n_in, n_in, dy, n_out)
+    torch.cuda.synchronize()
+    diff = np.abs(dy.cpu().numpy().astype(np.int32) - want)
+    assert diff.max() <= 1 and (diff != 0).mean() <= 0.02 and not diff[:, ::L_].any()
+    bank.close()
