@@ -20,15 +20,12 @@
 // MACs/s for DFMA / DMMA.
 //
 // Status (round 1): bit-identical on every resampler test and the default for the exact mode (LLZ_BANK_NO_IMMA=1 keeps
-// the FP64 tiles): C4 58.3 against 55.6 Gsamples/s, C1's drop-in job 531 against 490 Msamples/s -- a first step towards
-// the 3x higher roof.  History: 35.0 (every guard hit recomputed serially) -> 49.0 (warp-cooperative second look) -> 51.3
-// (integer epilogue, 64-tap chunks, taps fetched before the span) -> 56.8 (persistent CTAs: the next tile's span and
-// first tap chunks are fetched during the current tile's MMAs and epilogue) -> 58.3 (four stages).  In-kernel clock
-// stamps per 64 x 64 tile before the persistent version: span staging + byte split 3.5 k cycles, MMA loop 10.2 k (65 % of
-// the IMMA rate), epilogue 3.9 k, second look 1.1 k, launch ~3 k.  The six accumulator sets cost ~240 registers, so ONE
-// CTA is resident per SM: the MMA warps still produce their own X'' chunks and run the epilogue with the tensor pipe
-// idle.  Next: producer warps (setmaxnreg) for the X'' chunks and the next tile's span split, and the taps of a phase
-// tile multicast across a cluster (the G'' stream is 23 B/clk/SM at the IMMA rate: L2-bound if every CTA fetches its own).
+// the FP64 tiles): C4 75.0 against 55.6 Gsamples/s.  History: 35.0 (every guard hit recomputed serially) -> 49.0
+// (warp-cooperative second look) -> 51.3 (integer epilogue, 64-tap chunks, taps fetched before the span) -> 56.8
+// (persistent CTAs) -> 58.3 (four stages) -> 74.8 (producer warpgroup, see the kernel) -> 75.0 (guard band from the taps'
+// actual rounding errors).  Tensor pipe 43 % active; what is left exposed is the consumers' epilogue.  Next: two consumer
+// groups alternating tiles, and the taps of a phase tile multicast across a cluster (the G'' stream is 23 B/clk/SM at the
+// IMMA rate: L2-bound if every CTA fetches its own).
 #include <math.h>
 #include <stdlib.h>
 
@@ -413,7 +410,18 @@ int poly_imma_build_tables(const double *cb, int L, int M, int Q, int planes, st
         }
     }
     *shift = s;
-    *eps = (double)Q * 32768.0 * ldexp(1.0, -(s + 1));
+    // bound on |sum_k (g_k - q_k 2^-s) x_k| for |x| <= 32768: the taps' ACTUAL rounding errors, worst row (about half of
+    // the a-priori Q * 2^-(s+1), which halves the first-level guard hits)
+    double worst = 0.0;
+    for (int l = 0; l < L; ++l) {
+        double row = 0.0;
+        for (int k = 0; k < Q; ++k) {
+            const double g = cb[(size_t)l * Q + k];
+            row += fabs(g - ldexp((double)llrint(ldexp(g, s)), -s));
+        }
+        worst = fmax(worst, row);
+    }
+    *eps = 32768.0 * worst * (1.0 + 1e-9) + (double)Q * 32768.0 * ldexp(1.0, -(s + 40));
     return nchunks;
 }
 
