@@ -39,11 +39,9 @@ namespace {
 
 constexpr int kIPB = 64, kIJB = 64;                   // CTA tile: phases x cycles
 constexpr int kIKC = 64;                              // k'' per chunk = two IMMA.16832 steps per pipeline round
-constexpr int kINT = 256;                             // 8 warps = 4 (phases) x 2 (cycles), warp tile 16 x 32
 constexpr int kIPlanesExact = 5, kIPlanesFast = 3;    // signed base-256 digits of a tap: exact mode / fast mode
 constexpr int kIPitch = kIKC + 16;                    // bytes per operand row in shared memory (80: conflict-free ldmatrix)
-constexpr int kIStages = 4;                            // chunk c + kIAhead is produced after chunk c is consumed
-constexpr int kIAhead = kIStages - 1;
+constexpr int kIStages = 4;                           // the producers run up to four chunks ahead of the consumers
 constexpr int kIXStage = 2 * kIJB * kIPitch;          // 10,240 bytes: one chunk of X'', low and high byte planes
 __host__ __device__ constexpr int imma_gstage(int planes) { return planes * kIPB * kIPitch; }   // one chunk of G'', all planes (5: 25,600 bytes)
 __host__ __device__ constexpr int imma_stage(int planes) { return imma_gstage(planes) + kIXStage; }
@@ -112,13 +110,13 @@ __device__ __forceinline__ ImmaTile imma_tile(const PolyLaunch &a, const ImmaGeo
 // warps 8-11 (one warpgroup, setmaxnreg 40) stage and split the spans, cut the X'' chunks and issue the G'' copies, up to
 // kIStages chunks ahead of the consumers -- across tile boundaries, so the next tile's first chunks are ready while the
 // consumers still finish the current tile's outputs.  The two sides meet only on the stages' full / empty mbarriers.
-constexpr int kIConsumers = 256, kIProducers = 128;
+constexpr int kIConsumers = 256, kIProducers = 128;   // consumers: 8 warps = 4 (phases) x 2 (cycles), warp tile 16 x 32
 
 template <int MODE, int P>
 __global__ void __launch_bounds__(kIConsumers + kIProducers, 1)
 poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
 {
-    constexpr int PB = kIPB, kIPlanes = P, kIGStage = imma_gstage(P), kIStage = imma_stage(P);
+    constexpr int kIPlanes = P, kIGStage = imma_gstage(P), kIStage = imma_stage(P);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *span_bar = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *s_full = span_bar + 1, *s_empty = s_full + kIStages;
