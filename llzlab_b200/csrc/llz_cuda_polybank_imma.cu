@@ -11,13 +11,21 @@
 //   * the ten digit products p_i * {xl, xh} run as IMMA.16832 (mma.sync.m16n8k32, s8 x u8 / s8 x s8 -> s32): every
 //     product and every 32-bit sum is exact (|sum| <= 2 * 404 * 128 * 255 < 2^25); products of equal weight 2^(8(i+j))
 //     share an accumulator, so a thread carries six s32 accumulator sets;
-//   * epilogue: sum_d acc_d * 2^(8d - s) in FP64 (Horner), gain, guard, saturate, truncate.
+//   * epilogue: sum_d acc_d * 256^d as a 64-bit integer, one conversion, scale 2^-s, gain, guard, saturate, truncate.
 //
 // The only error is the tap rounding: |sum - exact| <= Q * 32768 * 2^-(s+1) (1.5e-5 for config C4's Q = 257, s = 38),
-// which widens the guard band from ~1e-9 to ~3e-5 of the outputs -- still rare enough that the reference-order
-// recompute costs a few per cent.  Single-tap (knife-edge) rows are evaluated as one exact FP64 product.
+// which widens the guard band from ~1e-9 to ~3e-5 of the outputs; those get a second look as a warp-cooperative FP64 dot
+// product, and only what is still near an integer goes to the reference's serial order.  Single-tap (knife-edge) rows
+// are evaluated as one exact FP64 product.
 // B200 rates (tools/probe_pipes.cu): IMMA 1144 TOP/s = 57 T exact MACs/s after the ten-way split, against 17-18.5 T
 // MACs/s for DFMA / DMMA.
+//
+// Layout.  With the tap index reversed, k'' = K'-1-k', the operand rows are k-contiguous as mma's row.col fragments
+// want them: X''[j][k''] = span[j*M + k''] (an ascending run of the staged input span per cycle) and
+// G''[l][k''] = g[l][Q-1 + (c_l - c_lo) - k''].  G'' depends on the phase tile only, so the host lays every tile out
+// once, chunk by chunk (64 k'' bytes per row, rows padded to 80 bytes: conflict-free ldmatrix), and a chunk of all
+// five planes arrives by ONE TMA bulk copy; X'' chunks are cut from two byte planes of the span (split once per tile)
+// with funnel shifts.  Four-stage mbarrier pipeline between a producer warpgroup and two consumer warpgroups.
 //
 // Status (round 1): bit-identical on every resampler test and the default for the exact mode (LLZ_BANK_NO_IMMA=1 keeps
 // the FP64 tiles): C4 75.0 against 55.6 Gsamples/s.  History: 35.0 (every guard hit recomputed serially) -> 49.0
