@@ -235,6 +235,14 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
         const int l0 = T.l0, pbv = T.pbv, nchunks = T.nchunks;
         const long long j0 = T.j0;
 
+        // the two phase rows of this thread: is either a single-tap row?  (fetched now, needed in the epilogue)
+        int st_row[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = 16 * wm + 8 * h + (lane >> 2);
+            st_row[h] = (l < pbv) ? __ldg(a.single_tap + l0 + l) : -1;
+        }
+
         int acc[kIPlanes + 1][4][4];                           // [weight 2^(8d)][n tile][c fragment]
 #pragma unroll
         for (int d = 0; d <= kIPlanes; ++d)
@@ -287,7 +295,7 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
         for (int h = 0; h < 2; ++h) {
             const int l = 16 * wm + 8 * h + (lane >> 2);
             const bool l_ok = l < pbv;
-            const int st = l_ok ? a.single_tap[l0 + l] : -1;
+            const int st = st_row[h];
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
@@ -315,7 +323,7 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int l = 16 * wm + 8 * h + (lane >> 2);
-            const int st = (l < pbv) ? a.single_tap[l0 + l] : -1;
+            const int st = h ? st_row[1] : st_row[0];
             if (st < 0) continue;
             for (int idx = 0; idx < 8; ++idx) {
                 const int j = 32 * wn + 8 * (idx >> 1) + 2 * (lane & 3) + (idx & 1);
