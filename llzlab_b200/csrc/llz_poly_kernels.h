@@ -64,8 +64,6 @@ int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 // exact mode on the integer tensor cores (llz_cuda_polybank_imma.cu): same return convention
 int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
-// host side of the same: the bank [L][Q] as int8 digit planes in the kernel's tile layout; returns chunks per tile (0: n/a)
-int poly_imma_build_tables(const double *cb, int L, int M, int Q, int planes, std::vector<signed char> *out, int *shift, double *eps);
 // name of the kernel poly_launch would pick ("sliding" / "general"), for reporting
 const char *poly_kernel_name(const PolyLaunch &a);
 

@@ -22,6 +22,7 @@
 #include "llz_cuda_common.cuh"
 #include "llz_fft32.cuh"
 #include "llz_fir_kernels.h"
+#include "llz_imma_tables.h"
 #include "llz_poly_kernels.h"
 
 namespace {
