@@ -47,7 +47,7 @@ int main(int argc, char **argv)
         std::vector<int16_t> span((size_t)rawn + kIKC + 64);
         for (auto &v : span) v = (int16_t)(next() >> 16);          // beyond rawn: garbage that must meet zero taps only
         for (int pass = 0; pass < 2; ++pass) {
-            for (int l = 0; l < pbv; l += (pass ? 7 : 1)) {
+            for (int l = 0; l < pbv; ++l) {
                 const int d = (int)(((long long)(l0 + l) * M) / L) - c_lo;
                 const int j = (l * 13 + t) % kIJB;
                 if (pass) {                                        // adversarial: every sample pushes its tap's rounding error the same way

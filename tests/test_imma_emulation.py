@@ -31,5 +31,5 @@ def test_digit_planes_reproduce_the_dot_product_within_the_guard_bound(emu, L, M
     worst, adversarial, acc_max = r.stdout.split()
     assert r.returncode == 0, r.stdout
     assert float(worst) <= 1.0                      # the bound holds ...
-    assert float(adversarial) >= 0.9                # ... and is not slack
+    assert float(adversarial) >= 0.85               # ... and is not slack
     assert int(acc_max) < 2 ** 31 - 1               # exact s32 accumulation
