@@ -283,33 +283,59 @@ poly_bank_imma_kernel(PolyLaunch a, ImmaGeom geo)
         // are only noted.  (Converting and combining in FP64 behind a branch per output cost as much as the MMA loop.)
         uint32_t guard_hits = 0;                               // bit ni*4 + e
         const double out_scale = a.imma_scale * 16777216.0;    // the high half carries 256^3
+        auto combine = [&](int ni, int e) -> double {          // the tile's sum for accumulator element (ni, e), times gain
+            const long long lo = (long long)acc[0][ni][e] + (long long)acc[1][ni][e] * 256 + (long long)acc[2][ni][e] * 65536;
+            double s;
+            if constexpr (P == kIPlanesExact) {
+                const long long hi = (long long)acc[3][ni][e] + (long long)acc[4][ni][e] * 256 + (long long)acc[5][ni][e] * 65536;
+                s = fma((double)hi, out_scale, (double)lo * a.imma_scale);
+            } else {
+                static_assert(P == kIPlanesFast, "three or five tap digits");
+                s = (double)(lo + (long long)acc[3][ni][e] * 16777216) * a.imma_scale;   // < 2^51: exact
+            }
+            return __dmul_rn(s, a.gain);
+        };
+        const long long tile_first = j0 * (long long)L + l0;   // output index of (cycle 0, phase 0) of the tile
+        const bool interior = pbv == kIPB && tile_first >= a.o0 && tile_first + 63LL * L + (kIPB - 1) < o_end;
+        if (interior) {
+            // every output of the tile belongs to the call (all but the first and last tiles of a channel): no validity
+            // tests, 32-bit offsets from one 64-bit row pointer, straight-line stores
+            const int jl = (32 * wn + 2 * (lane & 3)) * L;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int l = 16 * wm + 8 * h + (lane >> 2);
-            const bool l_ok = l < pbv;
-            const int st = st_row[h];
+            for (int h = 0; h < 2; ++h) {
+                const int st = st_row[h];
+                int16_t *yrow = ych + (tile_first - a.o0) + (16 * wm + 8 * h + (lane >> 2)) + jl;
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
+                for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-                for (int e2 = 0; e2 < 2; ++e2) {
-                    const int e = 2 * h + e2;
-                    const int j = 32 * wn + 8 * ni + 2 * (lane & 3) + e2;
-                    const long long o = (j0 + j) * (long long)L + l0 + l;
-                    const bool valid = l_ok && o >= a.o0 && o < o_end;
-                    const long long lo = (long long)acc[0][ni][e] + (long long)acc[1][ni][e] * 256 + (long long)acc[2][ni][e] * 65536;
-                    double s;
-                    if constexpr (P == kIPlanesExact) {
-                        const long long hi = (long long)acc[3][ni][e] + (long long)acc[4][ni][e] * 256 + (long long)acc[5][ni][e] * 65536;
-                        s = fma((double)hi, out_scale, (double)lo * a.imma_scale);
-                    } else {
-                        static_assert(P == kIPlanesFast, "three or five tap digits");
-                        s = (double)(lo + (long long)acc[3][ni][e] * 16777216) * a.imma_scale;   // < 2^51: exact
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const int e = 2 * h + e2;
+                        const double v = combine(ni, e);
+                        if (MODE == LLZ_CUDA_ACC_F64 && st < 0 && poly_near_nonzero_integer(v, a.imma_thr))
+                            guard_hits |= 1u << (ni * 4 + e);
+                        yrow[(8 * ni + e2) * L] = poly_finish(v);
                     }
-                    const double v = __dmul_rn(s, a.gain);
-                    if (MODE == LLZ_CUDA_ACC_F64 && valid && st < 0 && poly_near_nonzero_integer(v, a.imma_thr))
-                        guard_hits |= 1u << (ni * 4 + e);
-                    if (valid) ych[o - a.o0] = poly_finish(v);
-                }
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int l = 16 * wm + 8 * h + (lane >> 2);
+                const bool l_ok = l < pbv;
+                const int st = st_row[h];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const int e = 2 * h + e2;
+                        const int j = 32 * wn + 8 * ni + 2 * (lane & 3) + e2;
+                        const long long o = (j0 + j) * (long long)L + l0 + l;
+                        const bool valid = l_ok && o >= a.o0 && o < o_end;
+                        const double v = combine(ni, e);
+                        if (MODE == LLZ_CUDA_ACC_F64 && valid && st < 0 && poly_near_nonzero_integer(v, a.imma_thr))
+                            guard_hits |= 1u << (ni * 4 + e);
+                        if (valid) ych[o - a.o0] = poly_finish(v);
+                    }
+            }
         }
         // knife-edge phases (one tap, 1 - 2^-53 for the L-th band prototype): one exact FP64 product per output
 #pragma unroll 1
