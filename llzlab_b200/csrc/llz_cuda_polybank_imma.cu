@@ -31,7 +31,8 @@
 // the FP64 tiles): C4 83.3 against 55.6 Gsamples/s.  History: 35.0 (every guard hit recomputed serially) -> 49.0
 // (warp-cooperative second look) -> 51.3 (integer epilogue, 64-tap chunks, taps fetched before the span) -> 56.8
 // (persistent CTAs) -> 58.3 (four stages) -> 74.8 (producer warpgroup, see the kernel) -> 75.0 (guard band from the taps'
-// actual rounding errors) -> 83.3 (interior-tile epilogue without validity tests and 64-bit index arithmetic).  Tensor pipe 43 % active; what is left exposed is the consumers' epilogue.  Next: two consumer
+// actual rounding errors) -> 83.3 (interior-tile epilogue without validity tests and 64-bit index arithmetic).  Tensor
+// pipe ~48 % active; what is left exposed is the consumers' epilogue.  Next: two consumer
 // groups alternating tiles, and the taps of a phase tile multicast across a cluster (the G'' stream is 23 B/clk/SM at the
 // IMMA rate: L2-bound if every CTA fetches its own).
 #include <math.h>
