@@ -18,7 +18,10 @@
  *
  * All functions return 0 / a positive count on success and -1 on failure unless stated;
  * llz_cuda_last_error() returns the message of the calling thread's last failure.
- * A handle is bound to the CUDA device that was current when it was created.
+ * A handle is bound to the CUDA device that was current when it was created.  Calls on one handle may use different
+ * streams from call to call: the library orders a call after the previous call's work on the handle's stream state.
+ * Inputs must be finite: the bit-identical modes reproduce the reference for finite samples (a NaN / Inf sample
+ * spreads over up to 15 more outputs of the strict FIR kernel and over a whole block of the overlap-save kernels).
  */
 #ifndef _LLZ_CUDA_H
 #define _LLZ_CUDA_H
@@ -38,6 +41,11 @@ typedef void *llz_cuda_stream_t;            /* a cudaStream_t; NULL = the legacy
 const char *llz_cuda_last_error(void);
 int         llz_cuda_device_count(void);    /* 0 when no usable CUDA device */
 const char *llz_cuda_build_info(void);      /* "libllzfilter_cuda <ver> sm_100a ..." */
+/* Measurement knobs (process-wide; not for production code paths).  The environment is read once, when the first
+ * handle is created; this call overrides a value afterwards.  Keys: "pipe_slot_mib" (staging-slot size of the
+ * *_run_host pipelines, default 64), "slide_ru" (force a tile variant of the decimating kernel: 11, 7, 5, 3; 0 = auto),
+ * "fft8k_skew" / "fft16k_skew" (cycles, < 0 = measured default), "fir_algo" (default family of AUTO banks: 0, 1, 2). */
+int         llz_cuda_tune(const char *key, double value);
 /* page-locked host memory for the *_run_host pipelines (pageable buffers work, but slower) */
 void       *llz_cuda_host_alloc(size_t bytes);
 void        llz_cuda_host_free(void *p);
@@ -63,6 +71,12 @@ enum {                                      /* FIR kernel family (tolerance-mode
                                      |err| ~1e-15 (f64) / ~3e-7 (f32) of full scale against the direct sum,
                                      not bit-identical                                                      */
 };
+enum {                                      /* tile family of the phase-bank kernels (L >= 16); all give the same bytes */
+    LLZ_CUDA_TILES_AUTO        = 0, /* exact mode: INT8 tensor cores; fast mode: FP16 tensor cores (default)  */
+    LLZ_CUDA_TILES_INT8        = 1, /* exact mode: integer evaluation + two-level guard                       */
+    LLZ_CUDA_TILES_FP64_TENSOR = 2, /* exact mode: DMMA tiles + guard                                         */
+    LLZ_CUDA_TILES_CUDA_CORE   = 3, /* DFMA / FFMA register tiles                                             */
+};
 enum {                                      /* resampler accumulator */
     LLZ_CUDA_ACC_F64        = 0,  /* FP64 FMA + near-integer guard -> bit-identical int16 (default) */
     LLZ_CUDA_ACC_F64_STRICT = 1,  /* reference order, separate mul+add: bit-identical by construction */
@@ -83,6 +97,9 @@ int llz_cuda_fir_bank_flt_len(unsigned long handle);
 int llz_cuda_fir_bank_set_algo(unsigned long handle, int algo);
 /* the family the next _run will use: LLZ_CUDA_FIR_ALGO_DIRECT or LLZ_CUDA_FIR_ALGO_FFT */
 int llz_cuda_fir_bank_get_algo(unsigned long handle);
+/* transform length of the overlap-save family: 0 = by tap count (default), 1024, 8192 or 16384; fails when the
+ * filter does not fit.  Crossover measurements and tests use it; results agree to rounding between lengths.    */
+int llz_cuda_fir_bank_set_fft_size(unsigned long handle, int fft_size);
 /* samples per work item of the kernel the next _run will use: 2*(1024 - halo), 2*(8192 - halo) or 2*(16384 - halo) for the
  * overlap-save kernels, 1 for the direct form.  A stream cut at multiples of this length (time segments with
  * their flt_len-1 halo, pipeline chunks) reproduces the one-shot result bit for bit.                        */
@@ -157,8 +174,14 @@ int llz_cuda_resample_bank_run(unsigned long handle, const short *d_in, long lon
 int llz_cuda_resample_bank_run_host(unsigned long handle, const short *h_in, long long in_stride,
                                     long long n_in, short *h_out, long long out_stride,
                                     long long *n_out);
-/* outputs that took the reference-order recompute (near-integer guard) since init/reset */
+/* outputs that took the reference-order recompute (near-integer guard) since init */
 long long llz_cuda_resample_bank_guard_count(unsigned long handle);
+/* Verification knobs.  set_tiles picks the tile family of the phase-bank kernels (LLZ_CUDA_TILES_*).
+ * set_guard_scale multiplies the guard bands of the exact mode (1 <= scale <= 1e12): the outputs stay bit-identical
+ * -- the recompute IS the reference's own sum -- but a measurable share of them takes the recompute path, so tests
+ * can exercise the branch that the production band (about 1e-8 of the outputs) almost never enters.             */
+int llz_cuda_resample_bank_set_tiles(unsigned long handle, int tiles);
+int llz_cuda_resample_bank_set_guard_scale(unsigned long handle, double scale);
 
 /* ======================================================================================== */
 /* Shard planners (host integer arithmetic; no CUDA needed)                                  */

@@ -27,6 +27,7 @@ LPF, HPF, BPF, BSF = 0, 1, 2, 3
 F64, F64_STRICT, F32 = 0, 1, 2
 FIR_AUTO, FIR_DIRECT, FIR_FFT = 0, 1, 2
 ACC_F64, ACC_F64_STRICT, ACC_F32 = 0, 1, 2
+TILES_AUTO, TILES_INT8, TILES_FP64_TENSOR, TILES_CUDA_CORE = 0, 1, 2, 3
 KIND_DECIMATE, KIND_INTERP, KIND_RESAMPLE = 0, 1, 2
 PCM_S16, PCM_S24, PCM_F32 = 0, 1, 2
 PLANAR_S16, PLANAR_F32, PLANAR_F64 = 0, 1, 2
@@ -100,6 +101,7 @@ _SIGNATURES = [
     ("llz_cuda_last_error", C.c_char_p, []),
     ("llz_cuda_device_count", C.c_int, []),
     ("llz_cuda_build_info", C.c_char_p, []),
+    ("llz_cuda_tune", C.c_int, [C.c_char_p, C.c_double]),
     ("llz_cuda_host_alloc", _vp, [C.c_size_t]),
     ("llz_cuda_host_free", None, [_vp]),
     ("llz_cuda_fir_bank_init", _ul, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]),
@@ -108,6 +110,7 @@ _SIGNATURES = [
     ("llz_cuda_fir_bank_flt_len", C.c_int, [_ul]),
     ("llz_cuda_fir_bank_set_algo", C.c_int, [_ul, C.c_int]),
     ("llz_cuda_fir_bank_get_algo", C.c_int, [_ul]),
+    ("llz_cuda_fir_bank_set_fft_size", C.c_int, [_ul, C.c_int]),
     ("llz_cuda_fir_bank_block_len", _ll, [_ul]),
     ("llz_cuda_fir_bank_copy_taps", C.c_int, [_ul, _dp]),
     ("llz_cuda_fir_bank_reset", C.c_int, [_ul, _vp]),
@@ -128,6 +131,8 @@ _SIGNATURES = [
     ("llz_cuda_resample_bank_run", C.c_int, [_ul, _vp, _ll, _ll, _vp, _ll, C.POINTER(_ll), _vp]),
     ("llz_cuda_resample_bank_run_host", C.c_int, [_ul, _vp, _ll, _ll, _vp, _ll, C.POINTER(_ll)]),
     ("llz_cuda_resample_bank_guard_count", _ll, [_ul]),
+    ("llz_cuda_resample_bank_set_tiles", C.c_int, [_ul, C.c_int]),
+    ("llz_cuda_resample_bank_set_guard_scale", C.c_int, [_ul, C.c_double]),
     ("llz_cuda_shard_channels", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("llz_cuda_shard_fir_segments", C.c_int, [_ll, C.c_int, C.c_int, C.c_int, C.POINTER(Segment)]),
     ("llz_cuda_shard_fir_segments_aligned", C.c_int, [_ll, C.c_int, _ll, C.c_int, C.c_int, C.POINTER(Segment)]),
@@ -165,6 +170,11 @@ def lib() -> C.CDLL:
 
 def last_error() -> str:
     return lib().llz_cuda_last_error().decode()
+
+
+def tune(key: str, value: float):
+    """llz_cuda_tune: process-wide measurement knob (see include/llz_cuda.h)"""
+    _check(lib().llz_cuda_tune(key.encode(), float(value)), f"llz_cuda_tune({key})")
 
 
 def _check(rc: int, what: str) -> int:
@@ -379,6 +389,9 @@ class FirBank:
     def set_algo(self, algo: int):
         _check(lib().llz_cuda_fir_bank_set_algo(self.handle, algo), "llz_cuda_fir_bank_set_algo")
 
+    def set_fft_size(self, size: int):
+        _check(lib().llz_cuda_fir_bank_set_fft_size(self.handle, size), "llz_cuda_fir_bank_set_fft_size")
+
     @property
     def algo(self) -> int:
         """kernel family the next run uses: FIR_DIRECT or FIR_FFT"""
@@ -475,6 +488,12 @@ class ResampleBank:
 
     def guard_count(self) -> int:
         return _check(lib().llz_cuda_resample_bank_guard_count(self.handle), "guard_count")
+
+    def set_tiles(self, tiles: int):
+        _check(lib().llz_cuda_resample_bank_set_tiles(self.handle, tiles), "set_tiles")
+
+    def set_guard_scale(self, scale: float):
+        _check(lib().llz_cuda_resample_bank_set_guard_scale(self.handle, scale), "set_guard_scale")
 
     def close(self):
         if self.handle:

@@ -21,6 +21,21 @@
 
 namespace llz {
 
+// ---- per-process state (llz_cuda_util.cu) --------------------------------------------------------
+// SM count of the CURRENT device, cached per device ordinal (a handle runs under a DeviceGuard, so the current device
+// is the handle's); -1 + error message on failure.  Thread-safe.
+int device_sm_count();
+
+// Measurement knobs.  The environment is read ONCE, when the first handle is created; llz_cuda_tune() overrides a value
+// afterwards.  Nothing on a launch path calls getenv.
+struct Tunables {
+    double pipe_slot_mib;   // staging-slot size of the *_run_host pipelines (LLZ_PIPE_SLOT_MB), default 64
+    int slide_ru;           // force a tile variant of the sliding kernel: 11, 7, 5, 3; 0 = automatic (LLZ_SLIDE_RU)
+    int fft8k_skew, fft16k_skew;   // warp-group skew of the 8192- / 16384-point kernels in cycles; < 0 = measured default
+    int fir_algo;           // process default for LLZ_CUDA_FIR_ALGO_AUTO banks: 0 auto, 1 direct, 2 overlap-save (LLZ_FIR_ALGO)
+};
+Tunables &tunables();
+
 // ---- 16-byte vector views -------------------------------------------------------------------
 template <typename T> struct Vec16;
 template <> struct Vec16<float>  { using type = float4;  static constexpr int N = 4; };

@@ -35,24 +35,14 @@
 // reads per pass) rather than multiplied in a separate pass.
 #include <stdlib.h>
 
-#include "llz_f32x2.cuh"
 #include "llz_fft32.cuh"
 #include "llz_fir_kernels.h"
 
 namespace llz {
 
-template <> LLZ_HD F2 fma_t<F2>(F2 a, F2 b, F2 c) { return f2_fma(a, b, c); }
-
 template <typename T> struct Cplx;
 template <> struct Cplx<float>  { using type = float2; };
 template <> struct Cplx<double> { using type = double2; };
-template <> struct Cplx<F2>     { using type = F2x2; };
-
-// arithmetic type A of the kernel -> element type of the signal in memory, pairs of blocks per work item.
-// A = F2 (llz_f32x2.cuh): float signal, one warp carries TWO consecutive items of a channel in the two halves of
-// every register: the packed instructions halve the issue slots of the scalar-float kernel, which is issue-bound.
-template <typename A> struct FftArith { using IO = A; static constexpr int kItems = 1; };
-template <> struct FftArith<F2> { using IO = float; static constexpr int kItems = 2; };
 
 // row pitch of the per-warp transpose buffer: 33 elements keeps both the row-wise stores (lane = row)
 // and the column-wise loads (lane = column) bank-conflict-free for 4- and 8-byte elements
@@ -110,26 +100,21 @@ constexpr int kGather = 0, kStaged = 1, kEdge = 2;
 
 template <typename T, int WARPS, bool PACK, int MODE>
 struct FftSmem {
-    using IO = typename FftArith<T>::IO;
-    static constexpr int kItems = FftArith<T>::kItems;
     static constexpr size_t tables = (size_t)(kTwistEntries + kFftR) * kFftR * 2 * sizeof(T);     // twist table + H
     static constexpr size_t exch = (size_t)kFftR * kFftPitch * sizeof(T) * (PACK ? 2 : 1);        // per warp
-    // per warp: 1024 + (2*kItems - 1)*B samples, B <= 992 (halo >= 32)
-    static constexpr size_t stage = MODE == kStaged ? (size_t)(kFftN + (2 * kItems - 1) * (kFftN - 32)) * sizeof(IO) : 0;
+    // per warp: 1024 + B samples, B <= 992 (halo >= 32)
+    static constexpr size_t stage = MODE == kStaged ? (size_t)(kFftN + (kFftN - 32)) * sizeof(T) : 0;
     static constexpr size_t bars = 128;
     static constexpr size_t total = tables + bars + WARPS * (exch + stage);
 };
 
 template <typename T, int WARPS, bool PACK, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
+fir_fft_kernel(FirFftLaunch<T> a)
 {
     using C = typename Cplx<T>::type;
-    using IO = typename FftArith<T>::IO;
+    using IO = T;
     using SM = FftSmem<T, WARPS, PACK, MODE>;
-    constexpr int kItems = FftArith<T>::kItems;
-    constexpr bool kPacked = kItems == 2;
-    static_assert(!(kPacked && MODE == kEdge), "edge items run on the scalar kernel");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     C *tw_s = reinterpret_cast<C *>(smem_raw);                        // [16][32] folded twiddles (llz_fft32.cuh)
     C *H_s = tw_s + kTwistEntries * kFftR;                            // [32][32]
@@ -139,9 +124,8 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
     [[maybe_unused]] IO *stage = reinterpret_cast<IO *>(smem_raw + SM::tables + SM::bars + WARPS * SM::exch + (size_t)warp * SM::stage);
 
     {
-        // packed arithmetic reads the tables with every value duplicated into both halves
-        const C *tw_g = reinterpret_cast<const C *>(kPacked ? a.twx : a.tw);
-        const C *H_g = reinterpret_cast<const C *>(kPacked ? a.Hx : a.H);
+        const C *tw_g = reinterpret_cast<const C *>(a.tw);
+        const C *H_g = reinterpret_cast<const C *>(a.H);
         for (int i = threadIdx.x; i < kFftR * kFftR; i += WARPS * 32) {
             if (i < kTwistEntries * kFftR) tw_s[i] = tw_g[i];
             H_s[i] = H_g[i];
@@ -155,13 +139,13 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
     const long long item_step = (long long)gridDim.x * WARPS;
     long long item = (long long)blockIdx.x * WARPS + warp;
 
-    // first input sample (block A) of an interior item; an item is kItems consecutive pairs of blocks
+    // first input sample (block A) of an interior item
     auto item_src = [&](long long it) -> const IO * {
         const int c = (int)(it / a.items_per_channel);
-        const long long p = a.first_pair + kItems * (it - (long long)c * a.items_per_channel);
+        const long long p = a.first_pair + (it - (long long)c * a.items_per_channel);
         return a.x + (long long)c * a.x_stride + p * (2LL * B) - hl;
     };
-    [[maybe_unused]] const uint32_t span_bytes = (uint32_t)((kFftN + (2 * kItems - 1) * B) * sizeof(IO));
+    [[maybe_unused]] const uint32_t span_bytes = (uint32_t)((kFftN + B) * sizeof(IO));
     [[maybe_unused]] uint32_t phase = 0;
     if constexpr (MODE == kStaged) {
         if (lane == 0) {
@@ -176,7 +160,7 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
 
     for (; item < total; item += item_step) {
         const int ch = (int)(item / a.items_per_channel);
-        long long pair = a.first_pair + kItems * (item - (long long)ch * a.items_per_channel);
+        long long pair = a.first_pair + (item - (long long)ch * a.items_per_channel);
         if constexpr (MODE == kEdge) { if (pair >= a.gap_start) pair += a.gap_len; }
         const long long o = pair * (2LL * B);          // first output of block A
         const long long s = o - hl;                    // first input of block A
@@ -184,7 +168,7 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
         IO *yc = a.y + (long long)ch * a.y_stride;
 
         T re[32], im[32];
-        // ---- gather: lane t holds z[t + 32 j] (packed: the second item, 2B samples later, in the high halves) ----
+        // ---- gather: lane t holds z[t + 32 j] ----
         if constexpr (MODE == kGather || MODE == kStaged) {
             const IO *p;
             if constexpr (MODE == kStaged) {
@@ -196,18 +180,8 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                if constexpr (kPacked) {
-                    if constexpr (MODE == kStaged) {
-                        re[j] = f2_pack(p[32 * j], p[2 * B + 32 * j]);
-                        im[j] = f2_pack(p[B + 32 * j], p[3 * B + 32 * j]);
-                    } else {
-                        re[j] = f2_pack(__ldg(p + 32 * j), __ldg(p + 2 * B + 32 * j));
-                        im[j] = f2_pack(__ldg(p + B + 32 * j), __ldg(p + 3 * B + 32 * j));
-                    }
-                } else {
-                    if constexpr (MODE == kStaged) { re[j] = p[32 * j]; im[j] = p[B + 32 * j]; }
-                    else { re[j] = __ldg(p + 32 * j); im[j] = __ldg(p + B + 32 * j); }
-                }
+                if constexpr (MODE == kStaged) { re[j] = p[32 * j]; im[j] = p[B + 32 * j]; }
+                else { re[j] = __ldg(p + 32 * j); im[j] = __ldg(p + B + 32 * j); }
             }
             if constexpr (MODE == kStaged) {
                 __syncwarp();                          // every lane has its samples: the buffer may be refilled
@@ -223,14 +197,12 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(np + off));
             }
         } else {
-            if constexpr (!kPacked) {
-                const T *hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
+            const T *hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const long long g = s + lane + 32 * j;
-                    re[j] = fir_fft_sample(a, xc, hc, g);
-                    im[j] = fir_fft_sample(a, xc, hc, g + B);
-                }
+            for (int j = 0; j < 32; ++j) {
+                const long long g = s + lane + 32 * j;
+                re[j] = fir_fft_sample(a, xc, hc, g);
+                im[j] = fir_fft_sample(a, xc, hc, g + B);
             }
         }
 
@@ -259,17 +231,7 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
         // ---- scatter: circular positions m >= halo (whole rows j >= halo/32) are the valid outputs -------------
         IO *q = yc + o - hl + lane;
         const int j0 = hl >> 5;
-        if constexpr (kPacked) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j >= j0) {
-                    float a0, a1, b0, b1;
-                    f2_unpack(re[j], a0, a1);
-                    f2_unpack(im[j], b0, b1);
-                    __stcs(q + 32 * j, a0);         __stcs(q + B + 32 * j, b0);
-                    __stcs(q + 2 * B + 32 * j, a1); __stcs(q + 3 * B + 32 * j, b1);
-                }
-        } else if constexpr (MODE != kEdge) {
+        if constexpr (MODE != kEdge) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j >= j0) { __stcs(q + 32 * j, re[j]); __stcs(q + B + 32 * j, im[j]); }
@@ -287,7 +249,7 @@ fir_fft_kernel(FirFftLaunch<typename FftArith<T>::IO> a)
 }
 
 template <typename T, int WARPS, bool PACK, int MODE>
-static int fir_fft_run(FirFftLaunch<typename FftArith<T>::IO> b, int n_channels, long long first, long long count,
+static int fir_fft_run(FirFftLaunch<T> b, int n_channels, long long first, long long count,
                        long long gap_start, long long gap_len, int sm_count, cudaStream_t stream)
 {
     if (count <= 0) return 0;
@@ -315,24 +277,6 @@ static int fir_fft_launch_cfg(const FirFftLaunch<T> &a, int n_channels, long lon
     return fir_fft_run<T, WARPS, PACK, kEdge>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
 }
 
-// float signal, packed arithmetic: interior pairs two at a time on the F2 kernel, the odd one out and the edge pairs
-// on the scalar-float edge kernel (same operations on each half: the same bits)
-template <int WARPS, bool PACK, bool STAGE>
-static int fir_fft_launch_packed(const FirFftLaunch<float> &a, int n_channels, long long ppc, long long p_lo, long long p_hi,
-                                 int sm_count, cudaStream_t stream)
-{
-    const long long n2 = (p_hi - p_lo) / 2;
-    if (fir_fft_run<F2, WARPS, PACK, STAGE ? kStaged : kGather>(a, n_channels, p_lo, n2, ppc, 0, sm_count, stream) != 0)
-        return -1;
-    return fir_fft_run<float, 16, true, kEdge>(a, n_channels, 0, ppc - 2 * n2, p_lo, 2 * n2, sm_count, stream);
-}
-
-static int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 template <typename T>
 int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
 {
@@ -349,45 +293,20 @@ int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     // interior pairs p: p*2B - halo >= 0 and (p+1)*2B <= n, and there is an input buffer at all
     long long p_lo = (a.halo + two_b - 1) / two_b, p_hi = a.n / two_b;
     if (!a.x || p_hi < p_lo) { p_lo = 0; p_hi = 0; }
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0, sms = 0;
-        LLZ_CUDA_TRY(cudaGetDevice(&dev));
-        LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        sm_count = sms;
-    }
-    // tuning knobs (measurements only): resident warps per SM, packed exchange, TMA staging / L2 prefetch of the next item
-    // measured on C2 (profiles/r01_sweep_fft.txt): f64 -- 8 warps, plain exchange, TMA staging (packed exchange when
-    // the rows are not 16-byte aligned); f32 -- 20 warps, packed exchange, direct gather + L2 prefetch
+    const int sm_count = device_sm_count();
+    if (sm_count <= 0) return -1;
+    // measured on C2 (profiles/r01_sweep_fft.txt): f64 -- 8 warps, plain exchange, the next item staged by TMA (packed
+    // exchange and a direct gather when the rows are not 16-byte aligned); f32 -- 20 warps, packed exchange, direct
+    // gather + L2 prefetch of the next item.  The other points of that sweep (12 / 16 warps, packed FP32) lost and
+    // are no longer built.
     const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 && (a.x_stride * sizeof(T)) % 16 == 0;
-    const int stage = env_int("LLZ_FFT_STAGE", sizeof(T) == 8 ? 1 : 0) && aligned;
-    const int warps = env_int("LLZ_FFT_WARPS", sizeof(T) == 8 ? 8 : 20);
-    const int pack = env_int("LLZ_FFT_PACK", sizeof(T) == 8 ? (stage ? 0 : 1) : 1);
-    a.prefetch = env_int("LLZ_FFT_PREFETCH", 1);
-    if constexpr (sizeof(T) == 4) {
-        // packed FP32 (llz_f32x2.cuh) unless switched off for A/B measurements
-        // packed FP32 (llz_f32x2.cuh): measured on C2 at 559 against 568 Gsamples/s for the scalar kernel -- the float
-        // kernel is bound by LSU wavefronts (620 per item against 482 FP32-pipe cycles), which packing does not
-        // change -- so it stays an experiment behind LLZ_FFT_F32X2=1 (bit-identical results, tests/test_gpu_fir.py)
-        if (a.Hx && a.twx && env_int("LLZ_FFT_F32X2", 0)) {
-            const int st = env_int("LLZ_FFT_STAGE", 1) && aligned;
-            return st ? fir_fft_launch_packed<8, false, true>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream)
-                      : fir_fft_launch_packed<8, false, false>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream);
-        }
-    }
-#define LLZ_FFT_CASE(W, P, S) \
-    if (warps == W && pack == P && stage == S) \
-        return fir_fft_launch_cfg<T, W, P != 0, S != 0>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream)
+    a.prefetch = 1;
     if constexpr (sizeof(T) == 8) {
-        LLZ_FFT_CASE(8, 0, 0); LLZ_FFT_CASE(8, 0, 1); LLZ_FFT_CASE(8, 1, 0);
-        LLZ_FFT_CASE(12, 0, 0);
+        return aligned ? fir_fft_launch_cfg<T, 8, false, true>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream)
+                       : fir_fft_launch_cfg<T, 8, true, false>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream);
     } else {
-        LLZ_FFT_CASE(16, 0, 0); LLZ_FFT_CASE(16, 0, 1); LLZ_FFT_CASE(16, 1, 0);
-        LLZ_FFT_CASE(12, 1, 1); LLZ_FFT_CASE(20, 1, 0);
+        return fir_fft_launch_cfg<T, 20, true, false>(a, n_channels, ppc, p_lo, p_hi, sm_count, stream);
     }
-#undef LLZ_FFT_CASE
-    llz_set_error("no overlap-save kernel variant for LLZ_FFT_WARPS=%d LLZ_FFT_PACK=%d LLZ_FFT_STAGE=%d", warps, pack, stage);
-    return -1;
 }
 
 template int fir_fft_launch<float>(FirFftLaunch<float>, int, cudaStream_t);

@@ -325,17 +325,11 @@ int fir_fft16k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     const long long ppc = (a.n + two_b - 1) / two_b;
     long long p_lo = (a.halo + two_b - 1) / two_b, p_hi = a.n / two_b;
     if (!a.x || p_hi < p_lo) { p_lo = 0; p_hi = 0; }
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0, sms = 0;
-        LLZ_CUDA_TRY(cudaGetDevice(&dev));
-        LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        sm_count = sms;
-    }
-    const char *pf = getenv("LLZ_FFT_PREFETCH");
-    a.prefetch = (pf && *pf) ? atoi(pf) : 1;
-    const char *sk = getenv("LLZ_FFT16K_SKEW");
-    a.skew = (sk && *sk) ? atoi(sk) : (sizeof(T) == 8 ? 1300 : 0);     // f64 +5 %, f32 none (profiles/r01_sweep_skew.txt)
+    const int sm_count = device_sm_count();
+    if (sm_count <= 0) return -1;
+    a.prefetch = 1;
+    const int sk = tunables().fft16k_skew;                     // llz_cuda_tune("fft16k_skew", cycles); < 0: the measured default
+    a.skew = sk >= 0 ? sk : (sizeof(T) == 8 ? 1300 : 0);       // f64 +5 %, f32 none (profiles/r01_sweep_skew.txt)
     if (fir_fft16k_run<T, false>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
     return fir_fft16k_run<T, true>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
 }

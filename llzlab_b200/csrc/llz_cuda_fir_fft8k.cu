@@ -326,21 +326,14 @@ int fir_fft8k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     const long long ppc = (a.n + two_b - 1) / two_b;
     long long p_lo = (a.halo + two_b - 1) / two_b, p_hi = a.n / two_b;
     if (!a.x || p_hi < p_lo) { p_lo = 0; p_hi = 0; }
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0, sms = 0;
-        LLZ_CUDA_TRY(cudaGetDevice(&dev));
-        LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        sm_count = sms;
-    }
-    const char *pf = getenv("LLZ_FFT_PREFETCH");
-    a.prefetch = (pf && *pf) ? atoi(pf) : 1;
-    const char *sk = getenv("LLZ_FFT8K_SKEW");
-    a.skew = (sk && *sk) ? atoi(sk) : (sizeof(T) == 8 ? 1300 : 1500);
-    const char *st = getenv("LLZ_FFT_STAGE");
+    const int sm_count = device_sm_count();
+    if (sm_count <= 0) return -1;
+    a.prefetch = 1;
+    const int sk = tunables().fft8k_skew;                      // llz_cuda_tune("fft8k_skew", cycles); < 0: the measured default
+    a.skew = sk >= 0 ? sk : (sizeof(T) == 8 ? 1300 : 1500);
     const bool aligned = (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0 && (a.x_stride * sizeof(T)) % 16 == 0;
     // measured on C5: staging gains 2.5 % in f64 (one CTA per SM) and loses 4 % in f32 (two CTAs per SM hide the loads)
-    const bool stage = aligned && ((st && *st) ? atoi(st) != 0 : sizeof(T) == 8);
+    const bool stage = aligned && sizeof(T) == 8;
     const int rc = stage ? fir_fft8k_run<T, false, true>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream)
                          : fir_fft8k_run<T, false, false>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream);
     if (rc != 0) return -1;

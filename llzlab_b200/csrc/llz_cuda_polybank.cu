@@ -500,24 +500,16 @@ int launch_bank_dmma_tile(const PolyLaunch &a, int n_channels, cudaStream_t stre
 }
 
 // Cycle tile by size of the call: 128 cycles when that already gives every SM a few CTAs (the throughput shape), else 64
-// or 32 cycles so that a small call -- a drop-in frame -- spreads over more SMs.  LLZ_BANK_DMMA_WN forces one (tuning).
+// or 32 cycles so that a small call -- a drop-in frame -- spreads over more SMs.
 template <int KC, int MODE>
 int launch_bank_dmma(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
     const long long cycles = (a.o0 + a.n_out - 1) / a.L - a.o0 / a.L + 1;
     const long long per_cycle_tile = (long long)((a.L + kDPB - 1) / kDPB) * n_channels;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            sms = 148;
-    }
-    const char *env = getenv("LLZ_BANK_DMMA_WN");
-    int wn = env ? atoi(env) : 0;
-    if (wn != 1 && wn != 2 && wn != 4) {
-        wn = 4;
-        while (wn > 1 && (cycles + 32 * wn - 1) / (32 * wn) * per_cycle_tile < 2LL * sms) wn >>= 1;
-    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return -1;
+    int wn = 4;
+    while (wn > 1 && (cycles + 32 * wn - 1) / (32 * wn) * per_cycle_tile < 2LL * sms) wn >>= 1;
     if (wn == 4) return launch_bank_dmma_tile<KC, MODE, 4>(a, n_channels, stream);
     if (wn == 2) return launch_bank_dmma_tile<KC, MODE, 2>(a, n_channels, stream);
     return launch_bank_dmma_tile<KC, MODE, 1>(a, n_channels, stream);
@@ -802,15 +794,10 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if ((a.ctaps + cspan) / a.ctaps > 2.5) return 0;
     constexpr size_t kLimit = 226 * 1024;
     if (a.acc == LLZ_CUDA_ACC_F32) {
-        // fast mode: exact-product fp16 split on the tensor cores unless LLZ_BANK_NO_HMMA asks for the FFMA tile.  (The
-        // three-digit integer evaluation of llz_cuda_polybank_imma.cu is correct here too but slower -- 82 against 91
-        // Gsamples/s on C4: its per-tile fixed cost is the same as the exact mode's -- so it stays behind
-        // LLZ_BANK_IMMA_FAST=1, which also makes the shim build its tables.)
-        if (a.imma_tiles) {
-            const int rc = poly_bank_imma_launch(a, n_channels, stream);
-            if (rc != 0) return rc;
-        }
-        if (a.cbankT16h && a.cbankT16l && !getenv("LLZ_BANK_NO_HMMA")) {
+        // fast mode: exact-product fp16 split on the tensor cores unless the handle asks for the FFMA tile
+        // (llz_cuda_resample_bank_set_tiles).  A three-digit integer evaluation on the INT8 tensor cores was measured
+        // in round 1 (82 against 91 Gsamples/s on C4) and is no longer built.
+        if (a.cbankT16h && a.cbankT16l && a.tiles != LLZ_CUDA_TILES_CUDA_CORE) {
             const int rc = launch_bank_hmma<16>(a, n_channels, stream);
             if (rc != 0) return rc;
         }
@@ -818,17 +805,15 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         if (bank_smem<float, 16, 4, 4, 32, 16, false>(a) > kLimit) return 0;
         return launch_bank<float, 16, 4, 4, 32, 16, false, LLZ_CUDA_ACC_F32>(a, n_channels, stream);
     }
-    // f64: exact integer evaluation on the INT8 tensor cores (llz_cuda_polybank_imma.cu) unless LLZ_BANK_NO_IMMA=1 asks
-    // for the FP64 tiles (or the span of a tile does not fit beside its stages: extreme M / L)
-    if (a.imma_tiles) {
-        const char *no = getenv("LLZ_BANK_NO_IMMA");
-        if (!(no && atoi(no) != 0)) {
-            const int rc = poly_bank_imma_launch(a, n_channels, stream);
-            if (rc != 0) return rc;
-        }
+    // f64: exact integer evaluation on the INT8 tensor cores (llz_cuda_polybank_imma.cu) unless the handle asks for
+    // another tile family (llz_cuda_resample_bank_set_tiles) or the span of a tile does not fit beside its stages
+    // (extreme M / L)
+    if (a.imma_tiles && (a.tiles == LLZ_CUDA_TILES_AUTO || a.tiles == LLZ_CUDA_TILES_INT8)) {
+        const int rc = poly_bank_imma_launch(a, n_channels, stream);
+        if (rc != 0) return rc;
     }
-    // f64: FP64 tensor-core tiles (DMMA.8x8x4) unless LLZ_BANK_NO_DMMA asks for the scalar DFMA tile
-    if (!getenv("LLZ_BANK_NO_DMMA")) {
+    // f64: FP64 tensor-core tiles (DMMA.8x8x4) unless the handle asks for the scalar DFMA tile
+    if (a.tiles != LLZ_CUDA_TILES_CUDA_CORE) {
         const int rc = launch_bank_dmma<16, LLZ_CUDA_ACC_F64>(a, n_channels, stream);
         if (rc != 0) return rc;
     }

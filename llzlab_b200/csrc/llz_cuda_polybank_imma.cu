@@ -415,19 +415,13 @@ int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
     // the byte planes are read up to 31 bytes past the last needed sample (chunk padding meets zero taps)
     geo.raw_cap = ((kIJB - 1) * a.M + cspan_max + a.ctaps + kIKC + 16 + 15) & ~15;
     geo.n_channels = n_channels;
-    const bool exact = a.acc == LLZ_CUDA_ACC_F64;
-    if (!exact && a.acc != LLZ_CUDA_ACC_F32) return 0;
-    if (a.imma_planes != (exact ? kIPlanesExact : kIPlanesFast)) return 0;
+    if (a.acc != LLZ_CUDA_ACC_F64 || a.imma_planes != kIPlanesExact) return 0;
     const size_t smem = kIHeader + (size_t)kIStages * imma_stage(a.imma_planes) + (size_t)geo.raw_cap * 2 + 2 * ((size_t)geo.raw_cap + 32);
     if (smem > 226 * 1024) return 0;
-    auto kern = exact ? poly_bank_imma_kernel<LLZ_CUDA_ACC_F64, kIPlanesExact> : poly_bank_imma_kernel<LLZ_CUDA_ACC_F32, kIPlanesFast>;
+    auto kern = poly_bank_imma_kernel<LLZ_CUDA_ACC_F64, kIPlanesExact>;
     LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            sms = 148;
-    }
+    const int sms = device_sm_count();
+    if (sms <= 0) return -1;
     const long long tiles = (long long)geo.n_cycle_tiles * geo.n_phase_tiles * n_channels;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);           // persistent: one CTA per SM
     kern<<<grid, kIConsumers + kIProducers, smem, stream>>>(a, geo);

@@ -290,13 +290,10 @@ inline size_t slide_smem_bytes(int M, int ntp, int tile, size_t elem)
     return 16 + (size_t)M * ntp * elem + streams + raw;
 }
 
-// taps per residue padded to whole tap vectors (the kernel runs the last, partial unrolled iteration chunk by chunk);
-// LLZ_SLIDE_FULL_GRAN=1 pads to the SlidingMac granularity of the tile variant instead (A/B measurements)
-inline int slide_pad(const PolyLaunch &a, int gran, int vec)
+// taps per residue padded to whole tap vectors (the kernel runs the last, partial unrolled iteration chunk by chunk)
+inline int slide_pad(const PolyLaunch &a, int vec)
 {
     const int per = (a.ctaps + a.M - 1) / a.M;
-    const char *full = getenv("LLZ_SLIDE_FULL_GRAN");
-    if (full && atoi(full) != 0) return (per + gran - 1) / gran * gran;
     return (per + vec - 1) / vec * vec;
 }
 
@@ -311,13 +308,13 @@ int pick_slide(const PolyLaunch &a, int *ntp_out)
     int best = 0, best_ntp = 0;
     double best_cost = 0.0;
     const int ru[4] = {11, 7, 5, 3};
-    const char *force = getenv("LLZ_SLIDE_RU");               // tuning knob: force a tile variant (11, 7, 5 or 3)
+    const int force = tunables().slide_ru;                    // tuning knob: force a tile variant (11, 7, 5 or 3)
     for (int i = 0; i < 4; ++i) {
-        if (force && atoi(force) != ru[i]) continue;
+        if (force && force != ru[i]) continue;
         if (!force && ru[i] == 11 && sizeof(TA) == 4) continue;   // measured: the 44-output float tile is slower than 20 (C3: 4.9 vs 3.9 ms)
         const int R = ru[i] * U, gran = (ru[i] + 1) * U;
         // f64: whole tap vectors (+2.4 % on C3); f32: the variant's own granularity (the tail costs the float tiles 7 %)
-        const int ntp = slide_pad(a, gran, sizeof(TA) == 8 ? U : gran);
+        const int ntp = slide_pad(a, sizeof(TA) == 8 ? U : gran);
         if (ntp > avail) continue;
         const size_t smem = slide_smem_bytes(a.M, ntp, kSlideThreads * R, sizeof(TA));
         if (smem > kSmemBudget) continue;

@@ -1,8 +1,51 @@
 // llz_cuda_util.cu -- synthetic signal generators and machine probes (bench / test helpers of
 // libllzfilter_cuda; not on the filtering path).
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+
 #include "llz_cuda_common.cuh"
 
 namespace llz {
+
+// ---- per-process state ---------------------------------------------------------------------------
+int device_sm_count()
+{
+    constexpr int kMaxDev = 64;
+    static std::atomic<int> cache[kMaxDev];                   // zero-initialised
+    int dev = 0;
+    LLZ_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDev) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int sms = 0;
+    LLZ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < kMaxDev) cache[dev].store(sms, std::memory_order_relaxed);
+    return sms;
+}
+
+Tunables &tunables()
+{
+    // C++11 magic static: the lambda (and its getenv calls) runs once, thread-safely
+    static Tunables t = [] {
+        Tunables v{};
+        const char *e = getenv("LLZ_PIPE_SLOT_MB");
+        v.pipe_slot_mib = (e && atof(e) >= 1.0) ? atof(e) : 64.0;
+        e = getenv("LLZ_SLIDE_RU");
+        v.slide_ru = (e && *e) ? atoi(e) : 0;
+        e = getenv("LLZ_FFT8K_SKEW");
+        v.fft8k_skew = (e && *e) ? atoi(e) : -1;
+        e = getenv("LLZ_FFT16K_SKEW");
+        v.fft16k_skew = (e && *e) ? atoi(e) : -1;
+        e = getenv("LLZ_FIR_ALGO");
+        v.fir_algo = (e && strcmp(e, "direct") == 0) ? LLZ_CUDA_FIR_ALGO_DIRECT
+                     : (e && strcmp(e, "fft") == 0)  ? LLZ_CUDA_FIR_ALGO_FFT : LLZ_CUDA_FIR_ALGO_AUTO;
+        return v;
+    }();
+    return t;
+}
 
 // ---- per-channel LCG with jump-ahead -----------------------------------------------------------
 // s <- s*1664525 + 1013904223 (mod 2^32); element i of a channel is derived from state i+1
@@ -95,6 +138,20 @@ static int probe(double *tflops)
 }
 
 }  // namespace llz
+
+extern "C" int llz_cuda_tune(const char *key, double value)
+{
+    using namespace llz;
+    if (!key) { llz_set_error("llz_cuda_tune: null key"); return -1; }
+    Tunables &t = tunables();
+    if (strcmp(key, "pipe_slot_mib") == 0 && value >= 1.0) { t.pipe_slot_mib = value; return 0; }
+    if (strcmp(key, "slide_ru") == 0) { t.slide_ru = (int)value; return 0; }
+    if (strcmp(key, "fft8k_skew") == 0) { t.fft8k_skew = (int)value; return 0; }
+    if (strcmp(key, "fft16k_skew") == 0) { t.fft16k_skew = (int)value; return 0; }
+    if (strcmp(key, "fir_algo") == 0 && value >= 0 && value <= 2) { t.fir_algo = (int)value; return 0; }
+    llz_set_error("llz_cuda_tune: unknown key or bad value: %s = %g", key, value);
+    return -1;
+}
 
 extern "C" int llz_cuda_synth_lcg(void *d_out, long long stride, int n_channels, long long n, int kind,
                                   unsigned seed0, llz_cuda_stream_t stream)

@@ -50,7 +50,6 @@ struct FirFftLaunch {
     int ntaps;
     const T *H;            // device [32][32] complex: spectrum of the taps / 1024, H[k1][k2] = bin k2 + 32*k1
     const T *tw;           // device [16][32] pairs: folded twiddles of dft32_twisted (llz_fft32.cuh)
-    const T *Hx, *twx;     // float banks: H and tw with every value duplicated (v, v) for the packed-FP32 kernel, or null
     const T *tw2, *tw3;    // 8192-point kernel only: [8][16][32] and [4][4][256] pairs (llz_fft32.cuh)
     // filled in by fir_fft_launch: item i of a channel is pair first_pair + i, skipping [gap_start, gap_start + gap_len)
     int halo, B;           // halo = N-1 rounded up to 32; B = 1024 - halo valid outputs per block

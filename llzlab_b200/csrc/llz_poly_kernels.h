@@ -30,6 +30,7 @@ struct PolyLaunch {
     long long in0;             // canonical index of x[0]
     int L, M, ctaps, shift, frame_len;
     int acc;                   // LLZ_CUDA_ACC_*
+    int tiles;                 // LLZ_CUDA_TILES_*: tile family of the phase-bank kernels (verification / A-B runs)
     double gain;
     double guard_thr;          // |v - nearest integer| below this -> reference-order recompute
     const double *cbank;       // [L][ctaps] row-major
@@ -53,7 +54,7 @@ struct PolyLaunch {
     // layout, g ~ q * imma_scale (imma_scale = 2^-s); nullptr when the bank was not split
     const signed char *imma_tiles;
     int imma_nchunks;          // chunks of 64 taps per phase tile
-    int imma_planes;           // 5: exact mode (ACC_F64), 3: fast mode (ACC_F32)
+    int imma_planes;           // 5 digit planes
     double imma_scale;
     double imma_thr;           // guard band: guard_thr + |gain| * (tap rounding bound)
 };

@@ -59,7 +59,6 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 // i % kSlots.  Events order slot reuse; the compute stream sees the chunks in time order, so the
 // bank's stream state (history, phase) advances exactly as in one long call.
 constexpr int kSlots = 3;
-constexpr double kPipeSlotMiB = 64.0;
 
 struct Pipeline {
     cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -136,12 +135,38 @@ int copy_planar(void *dst, size_t dpitch, const void *src, size_t spitch, size_t
     return 0;
 }
 
-// samples per channel per chunk so that one slot (in + out) stays near the slot budget (LLZ_PIPE_SLOT_MB, tuning)
+// Cross-stream ordering of a handle's stream state.  History, counters and frame buffers are written by whatever
+// stream the previous call ran on; a call on a different stream (a caller switching streams, *_run_host on the internal
+// pipeline streams after a device-resident run, a drop-in frame after a bank run) must not overtake that work.
+// `pending` is cleared by the synchronous entry points once they have drained their stream.
+struct StreamTrail {
+    cudaStream_t last = nullptr;
+    bool pending = false;
+};
+
+int trail_enter(StreamTrail &t, cudaStream_t st)
+{
+    if (t.pending && t.last != st) {
+        cudaEvent_t ev = nullptr;
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, t.last);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+        if (ev) cudaEventDestroy(ev);                          // released once the recorded work has completed
+        if (e != cudaSuccess) {
+            // the previous stream no longer exists (destroyed by its owner): everything on the device is older than this call
+            cudaGetLastError();
+            LLZ_CUDA_TRY(cudaDeviceSynchronize());
+        }
+    }
+    t.last = st;
+    t.pending = true;
+    return 0;
+}
+
+// samples per channel per chunk so that one slot (in + out) stays near the slot budget (tunables().pipe_slot_mib)
 long long pick_chunk(long long n, int n_channels, double bytes_per_in_sample)
 {
-    const char *env = getenv("LLZ_PIPE_SLOT_MB");
-    const double mb = (env && atof(env) >= 1.0) ? atof(env) : kPipeSlotMiB;
-    const double budget = mb * 1024 * 1024;
+    const double budget = tunables().pipe_slot_mib * 1024 * 1024;
     long long c = (long long)(budget / (bytes_per_in_sample * n_channels));
     c = (c / 4096) * 4096;
     if (c < 4096) c = 4096;
@@ -167,8 +192,10 @@ struct FirBank {
     int algo = LLZ_CUDA_FIR_ALGO_AUTO;
     void *d_fft_H = nullptr, *d_fft_tw = nullptr;
     void *d_fft_tw2 = nullptr, *d_fft_tw3 = nullptr;     // 8192-point kernel (llz_cuda_fir_fft8k.cu)
-    void *d_fft_Hx = nullptr, *d_fft_twx = nullptr;      // float banks: tables with duplicated values (packed FP32)
     int fft_size = 0;            // transform length the tables were built for: 1024, 8192 or 16384
+    int fft_size_want = 0;       // llz_cuda_fir_bank_set_fft_size: 0 = by tap count
+    StreamTrail trail;           // which stream touched the stream state last
+    bool poisoned = false;       // a host pipeline failed half-way: the stream state is unreliable until a reset
     Pipeline pipe;
     // drop-in (mono, host buffers)
     int frame_len = 0;
@@ -199,8 +226,6 @@ void fir_destroy(FirBank *b)
     if (b->d_fft_tw) cudaFree(b->d_fft_tw);
     if (b->d_fft_tw2) cudaFree(b->d_fft_tw2);
     if (b->d_fft_tw3) cudaFree(b->d_fft_tw3);
-    if (b->d_fft_Hx) cudaFree(b->d_fft_Hx);
-    if (b->d_fft_twx) cudaFree(b->d_fft_twx);
     if (b->d_hist[0]) cudaFree(b->d_hist[0]);
     if (b->d_hist[1]) cudaFree(b->d_hist[1]);
     if (b->pinned) cudaFreeHost(b->pinned);
@@ -279,20 +304,24 @@ unsigned long fir_bank_create(double *h, int flt_len, int n_channels, int dtype)
             if ((e = cudaMemset(b->d_hist[i], 0, hb)) != cudaSuccess) return fail("cudaMemset(history)", e);
         }
     }
+    // The uploads above went through the legacy default stream (pageable cudaMemcpy may return before the DMA has
+    // landed, cudaMemset is asynchronous), while the kernels run on non-blocking streams that do not synchronise with
+    // it: drain it once here so that the first run on any stream sees complete taps and a zeroed history.
+    if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return fail("cudaStreamSynchronize(init uploads)", e);
     return reinterpret_cast<unsigned long>(b);
 }
 
 // which kernel family the next run uses: LLZ_CUDA_FIR_ALGO_DIRECT or _FFT (-1: the forced choice is impossible).
 // AUTO: overlap-save when the arithmetic is tolerance-mode and the tap count is where it wins (llz_cuda_fir_fft.cu);
-// the environment variable LLZ_FIR_ALGO=direct|fft overrides AUTO (tuning / A-B measurements).
+// the process default tunables().fir_algo (LLZ_FIR_ALGO=direct|fft, read once) overrides AUTO (A-B measurements).
 int fir_effective_algo(const FirBank *b)
 {
     const bool fft_ok = b->dtype != LLZ_CUDA_F64_STRICT && b->flt_len <= kFirFft16kMaxTaps;
     int algo = b->algo;
     if (algo == LLZ_CUDA_FIR_ALGO_AUTO) {
-        const char *env = getenv("LLZ_FIR_ALGO");
-        if (env && strcmp(env, "direct") == 0) algo = LLZ_CUDA_FIR_ALGO_DIRECT;
-        else if (env && strcmp(env, "fft") == 0 && fft_ok) algo = LLZ_CUDA_FIR_ALGO_FFT;
+        const int dflt = tunables().fir_algo;
+        if (dflt == LLZ_CUDA_FIR_ALGO_DIRECT) algo = LLZ_CUDA_FIR_ALGO_DIRECT;
+        else if (dflt == LLZ_CUDA_FIR_ALGO_FFT && fft_ok) algo = LLZ_CUDA_FIR_ALGO_FFT;
     }
     if (algo == LLZ_CUDA_FIR_ALGO_AUTO)
         algo = (fft_ok && b->flt_len >= kFirFftMinTapsAuto) ? LLZ_CUDA_FIR_ALGO_FFT : LLZ_CUDA_FIR_ALGO_DIRECT;
@@ -305,11 +334,10 @@ int fir_effective_algo(const FirBank *b)
 }
 
 // transform length the overlap-save path uses for this bank: 1024 (one warp per item), 8192 (one CTA per item) or
-// 16384 (one cluster of two CTAs per item); LLZ_FIR_FFT_SIZE overrides the choice where the tap count allows it
+// 16384 (one cluster of two CTAs per item); llz_cuda_fir_bank_set_fft_size overrides the choice where the tap count allows it
 int fir_fft_size(const FirBank *b)
 {
-    const char *env = getenv("LLZ_FIR_FFT_SIZE");
-    const int want = env ? atoi(env) : 0;
+    const int want = b->fft_size_want;
     if (want == 16384) return 16384;
     if (want == 8192 && b->flt_len <= kFirFft8kMaxTaps) return 8192;
     if (want == 1024 && b->flt_len <= kFirFftMaxTaps) return 1024;
@@ -362,18 +390,11 @@ int fir_fft_tables(FirBank *b)
         fft8k_make_spectrum(b->h_host, b->flt_len, H.data());
     } else {
         fft1024_make_spectrum(b->h_host, b->flt_len, H.data());
-        const char *px = getenv("LLZ_FFT_F32X2");
-        if (f32 && px && atoi(px) != 0) {
-            // the packed-FP32 kernel (an experiment, llz_cuda_fir_fft.cu) reads (re, re, im, im) / (cos, cos, tan, tan): one value for both halves
-            auto dup = [](const std::vector<double> &v) {
-                std::vector<double> d(2 * v.size());
-                for (size_t i = 0; i < v.size(); ++i) d[2 * i] = d[2 * i + 1] = v[i];
-                return d;
-            };
-            if (upload_as(&b->d_fft_Hx, dup(H), true) != 0 || upload_as(&b->d_fft_twx, dup(tw), true) != 0) return -1;
-        }
     }
-    return upload_as(&b->d_fft_H, H, f32);
+    if (upload_as(&b->d_fft_H, H, f32) != 0) return -1;
+    // the uploads above are pageable copies on the legacy stream; the kernels run on non-blocking streams
+    LLZ_CUDA_TRY(cudaStreamSynchronize(0));
+    return 0;
 }
 
 // channels [c0, c0 + cc) of the bank; d_in / d_out point at channel c0.  `last` = the call completes the bank's
@@ -404,8 +425,6 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
         f.hist = a.hist; f.ntaps = b->flt_len;
         f.H = static_cast<const T *>(b->d_fft_H);
         f.tw = static_cast<const T *>(b->d_fft_tw);
-        f.Hx = static_cast<const T *>(b->d_fft_Hx);
-        f.twx = static_cast<const T *>(b->d_fft_twx);
         f.tw2 = static_cast<const T *>(b->d_fft_tw2);
         f.tw3 = static_cast<const T *>(b->d_fft_tw3);
         const int rc = b->fft_size == 16384 ? fir_fft16k_launch<T>(f, cc, st)
@@ -431,6 +450,8 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
 int fir_run_part(FirBank *b, const void *d_in, long long in_stride, void *d_out, long long out_stride, long long n,
                  cudaStream_t st, int c0, int cc, bool last, bool defer_history = false)
 {
+    if (b->poisoned) { llz_set_error("FIR handle: an earlier host pipeline call failed half-way; reset the handle first"); return -1; }
+    if (trail_enter(b->trail, st) != 0) return -1;
     if (b->dtype == LLZ_CUDA_F32)
         return fir_run_typed<float>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last, defer_history);
     return fir_run_typed<double>(b, d_in, in_stride, d_out, out_stride, n, st, c0, cc, last, defer_history);
@@ -467,6 +488,10 @@ struct PolyBank {
     int slide_ntp64 = 0, slide_ntp32 = 0;
     unsigned long long *d_guard = nullptr;
     double guard_thr = 0.0;
+    double guard_scale = 1.0;    // llz_cuda_resample_bank_set_guard_scale: widens the guard bands (verification)
+    int tiles = LLZ_CUDA_TILES_AUTO;
+    StreamTrail trail;           // which stream touched the stream state last
+    bool poisoned = false;       // a host pipeline failed half-way: the stream state is unreliable until a reset
     // stream state
     long long consumed = 0, produced = 0;
     int16_t *d_hist[2] = {nullptr, nullptr};
@@ -565,13 +590,10 @@ int poly_upload_plan(PolyBank *b)
         b->d_cbankT16h = b->d_cbankT16h_base + pad * L;
         b->d_cbankT16l = b->d_cbankT16l_base + pad * L;
     }
-    const char *imma_fast = getenv("LLZ_BANK_IMMA_FAST");
-    const bool imma_f32 = b->acc == LLZ_CUDA_ACC_F32 && imma_fast && atoi(imma_fast) != 0;
-    if ((b->acc == LLZ_CUDA_ACC_F64 || imma_f32) && L >= 16 && p.shift == 0 && p.frame_len == 0) {
-        // integer tensor cores: int8 digit planes of the taps in the kernel's tile layout (five digits: exact mode,
-        // three: fast mode, the 22 significant bits of the fp16-split planes above)
+    if (b->acc == LLZ_CUDA_ACC_F64 && L >= 16 && p.shift == 0 && p.frame_len == 0) {
+        // integer tensor cores: int8 digit planes of the taps in the kernel's tile layout (five digits)
         std::vector<signed char> tiles;
-        b->imma_planes = b->acc == LLZ_CUDA_ACC_F64 ? 5 : 3;
+        b->imma_planes = 5;
         b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->imma_planes, &tiles, &b->imma_shift, &b->imma_eps);
         if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
     }
@@ -610,6 +632,9 @@ int poly_upload_plan(PolyBank *b)
     // differ by < 2*(Q+2)*u*|gain|*rowsum*peak.  A factor 4 of slack costs nothing (the guard fires
     // on ~1e-9 of the outputs) and keeps the bound safe against second-order terms.
     b->guard_thr = 4.0 * 2.0 * (double)(Q + 2) * ldexp(1.0, -53) * fabs(b->gain) * p.abs_row_sum * 32768.0;
+    // pageable uploads and memsets on the legacy default stream must have landed before a kernel on a non-blocking
+    // stream reads them (see fir_bank_create)
+    LLZ_CUDA_TRY(cudaStreamSynchronize(0));
     return 0;
 }
 
@@ -665,6 +690,8 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     if (n_out) *n_out = outs;
     if (n_in == 0) return 0;
     if (outs > 0 && !d_out) { llz_set_error("null output pointer"); return -1; }
+    if (b->poisoned) { llz_set_error("resampler handle: an earlier host pipeline call failed half-way; reset the handle first"); return -1; }
+    if (trail_enter(b->trail, st) != 0) return -1;
 
     if (b->chain_src && !defer_history) {
         // a deferred history meets an ordinary run: materialise it first
@@ -687,8 +714,9 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.L = p.L * b->rep; a.M = p.M * b->rep;          // repeated rows: the same outputs (poly_upload_plan)
     a.ctaps = p.ctaps; a.shift = p.shift; a.frame_len = p.frame_len;
     a.acc = b->acc;
+    a.tiles = b->tiles;
     a.gain = b->gain;
-    a.guard_thr = b->guard_thr;
+    a.guard_thr = b->guard_thr * b->guard_scale;
     a.cbank = b->d_cbank;
     a.cbankT64 = b->d_cbankT64;
     a.cbankT32 = b->d_cbankT32;
@@ -708,7 +736,8 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.imma_nchunks = b->imma_nchunks;
     a.imma_planes = b->imma_planes;
     a.imma_scale = ldexp(1.0, -b->imma_shift);
-    a.imma_thr = b->guard_thr + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
+    // first-level band of the integer evaluation: the (scaled) FP64 band plus the taps' rounding bound
+    a.imma_thr = b->guard_thr * b->guard_scale + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
     if (poly_launch(a, b->n_channels, st) != 0) return -1;
     if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
         b->chain_src = d_in + (n_in - p.hist_len);
@@ -730,6 +759,7 @@ int poly_reset(PolyBank *b)
     b->produced = 0;
     b->hist_zero = true;
     b->chain_src = nullptr;
+    b->poisoned = false;
     return 0;
 }
 
@@ -821,6 +851,32 @@ extern "C" int llz_cuda_fir_bank_get_algo(unsigned long handle)
     return fir_effective_algo(b);
 }
 
+extern "C" int llz_cuda_fir_bank_set_fft_size(unsigned long handle, int fft_size)
+{
+    FirBank *b = as_fir(handle);
+    if (!b) return -1;
+    if (fft_size != 0 && fft_size != 1024 && fft_size != 8192 && fft_size != 16384) {
+        llz_set_error("overlap-save transform length must be 0 (automatic), 1024, 8192 or 16384 (got %d)", fft_size);
+        return -1;
+    }
+    if ((fft_size == 1024 && b->flt_len > kFirFftMaxTaps) || (fft_size == 8192 && b->flt_len > kFirFft8kMaxTaps) ||
+        (fft_size == 16384 && b->flt_len > kFirFft16kMaxTaps)) {
+        llz_set_error("a %d-point transform cannot hold %d taps", fft_size, b->flt_len);
+        return -1;
+    }
+    if (b->d_fft_H && fir_fft_size(b) != b->fft_size) { llz_set_error("internal: stale FFT tables"); return -1; }
+    if (b->d_fft_H && fft_size != b->fft_size_want) {
+        // tables of another transform length are resident: drop them, the next run rebuilds
+        DeviceGuard g(b->device);
+        LLZ_CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(b->d_fft_H); cudaFree(b->d_fft_tw); cudaFree(b->d_fft_tw2); cudaFree(b->d_fft_tw3);
+        b->d_fft_H = b->d_fft_tw = b->d_fft_tw2 = b->d_fft_tw3 = nullptr;
+        b->fft_size = 0;
+    }
+    b->fft_size_want = fft_size;
+    return 0;
+}
+
 long long fir_block_len(const FirBank *b)
 {
     if (fir_effective_algo(b) != LLZ_CUDA_FIR_ALGO_FFT) return 1;
@@ -852,6 +908,7 @@ extern "C" int llz_cuda_fir_bank_reset(unsigned long handle, llz_cuda_stream_t s
     if (!b) return -1;
     b->hist_zero = true;
     b->chain_src = nullptr;
+    b->poisoned = false;
     return 0;
 }
 
@@ -864,6 +921,8 @@ extern "C" int llz_cuda_fir_bank_set_history(unsigned long handle, const void *d
     b->chain_src = nullptr;
     if (!d_hist) { b->hist_zero = true; return 0; }
     DeviceGuard g(b->device);
+    b->poisoned = false;
+    if (trail_enter(b->trail, (cudaStream_t)stream) != 0) return -1;
     const size_t es = fir_elem_size(b->dtype);
     if (copy_planar(b->d_hist[b->cur], (size_t)b->hist_len * es, d_hist, (size_t)stride * es,
                                    (size_t)b->hist_len * es, (size_t)b->n_channels, cudaMemcpyDeviceToDevice,
@@ -895,8 +954,8 @@ extern "C" int llz_cuda_fir_bank_flush(unsigned long handle, void *d_out, long l
     return b->hist_len;
 }
 
-extern "C" int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in, long long in_stride,
-                                          void *h_out, long long out_stride, long long n)
+static int fir_run_host_body(unsigned long handle, const void *h_in, long long in_stride,
+                             void *h_out, long long out_stride, long long n)
 {
     FirBank *b = as_fir(handle);
     if (!b) return -1;
@@ -913,8 +972,7 @@ extern "C" int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in
         // is one contiguous span, so every copy is 1-D: tools/pcie_probe2d.cu measures 44.2 GB/s H2D for contiguous
         // copies against 37.8 GB/s for the row-wise shape a time chunk of all channels needs (D2H 48.5 / 47.0), and
         // the kernels see whole channels (no per-chunk edge items).  Long channels fall through to time chunks.
-        const char *env = getenv("LLZ_PIPE_SLOT_MB");
-        const double budget = ((env && atof(env) >= 1.0) ? atof(env) : kPipeSlotMiB) * 1024 * 1024;
+        const double budget = tunables().pipe_slot_mib * 1024 * 1024;
         const double per_channel = 2.0 * (double)es * (double)n;
         long long group = (long long)(budget / per_channel);
         if (group >= 2 && C > 2 * group) {
@@ -979,6 +1037,27 @@ extern "C" int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in
     LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_out));
     LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_run));
     return 0;
+}
+
+// A failure inside the pipeline must not return while copies are still in flight (the caller owns the host buffers
+// again on return) and leaves the stream state half-advanced: drain the three streams and poison the handle until a
+// reset / set_history.
+extern "C" int llz_cuda_fir_bank_run_host(unsigned long handle, const void *h_in, long long in_stride,
+                                          void *h_out, long long out_stride, long long n)
+{
+    const int rc = fir_run_host_body(handle, h_in, in_stride, h_out, out_stride, n);
+    FirBank *b = reinterpret_cast<FirBank *>(handle);
+    if (handle == 0 || handle == kFail || b->magic != kMagicFir) return rc;
+    if (rc != 0 && b->pipe.ok) {
+        DeviceGuard g(b->device);
+        cudaStreamSynchronize(b->pipe.s_in);
+        cudaStreamSynchronize(b->pipe.s_run);
+        cudaStreamSynchronize(b->pipe.s_out);
+        cudaGetLastError();
+        b->poisoned = true;
+    }
+    b->trail.pending = false;                                  // the pipeline streams are drained on every path
+    return rc;
 }
 
 // ====================================================================================================
@@ -1063,6 +1142,7 @@ extern "C" int llz_cuda_resample_bank_set_history(unsigned long handle, const sh
     poly_reset(b);
     if (b->plan.hist_len == 0 || !d_hist) return 0;
     DeviceGuard g(b->device);
+    if (trail_enter(b->trail, (cudaStream_t)stream) != 0) return -1;
     const size_t row = (size_t)b->plan.hist_len * sizeof(int16_t);
     if (copy_planar(b->d_hist[b->cur], row, d_hist, (size_t)stride * sizeof(int16_t), row,
                                    (size_t)b->n_channels, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != 0) return -1;
@@ -1081,9 +1161,9 @@ extern "C" int llz_cuda_resample_bank_run(unsigned long handle, const short *d_i
     return poly_run(b, d_in, in_stride, n_in, d_out, out_stride, n_out, (cudaStream_t)stream);
 }
 
-extern "C" int llz_cuda_resample_bank_run_host(unsigned long handle, const short *h_in, long long in_stride,
-                                               long long n_in, short *h_out, long long out_stride,
-                                               long long *n_out)
+static int poly_run_host_body(unsigned long handle, const short *h_in, long long in_stride,
+                              long long n_in, short *h_out, long long out_stride,
+                              long long *n_out)
 {
     PolyBank *b = as_poly(handle);
     if (!b) return -1;
@@ -1128,6 +1208,43 @@ extern "C" int llz_cuda_resample_bank_run_host(unsigned long handle, const short
     }
     LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_out));
     LLZ_CUDA_TRY(cudaStreamSynchronize(P.s_run));
+    return 0;
+}
+
+extern "C" int llz_cuda_resample_bank_run_host(unsigned long handle, const short *h_in, long long in_stride,
+                                               long long n_in, short *h_out, long long out_stride,
+                                               long long *n_out)
+{
+    const int rc = poly_run_host_body(handle, h_in, in_stride, n_in, h_out, out_stride, n_out);
+    PolyBank *b = reinterpret_cast<PolyBank *>(handle);
+    if (handle == 0 || handle == kFail || b->magic != kMagicPoly) return rc;
+    if (rc != 0 && b->pipe.ok) {                               // see llz_cuda_fir_bank_run_host
+        DeviceGuard g(b->device);
+        cudaStreamSynchronize(b->pipe.s_in);
+        cudaStreamSynchronize(b->pipe.s_run);
+        cudaStreamSynchronize(b->pipe.s_out);
+        cudaGetLastError();
+        b->poisoned = true;
+    }
+    b->trail.pending = false;
+    return rc;
+}
+
+extern "C" int llz_cuda_resample_bank_set_tiles(unsigned long handle, int tiles)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    if (tiles < LLZ_CUDA_TILES_AUTO || tiles > LLZ_CUDA_TILES_CUDA_CORE) { llz_set_error("unknown tile family %d", tiles); return -1; }
+    b->tiles = tiles;
+    return 0;
+}
+
+extern "C" int llz_cuda_resample_bank_set_guard_scale(unsigned long handle, double scale)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    if (!(scale >= 1.0) || scale > 1e12) { llz_set_error("guard scale must be in [1, 1e12] (got %g)", scale); return -1; }
+    b->guard_scale = scale;
     return 0;
 }
 
@@ -1221,6 +1338,7 @@ extern "C" int llz_fir_filter(unsigned long handle, double *buf_in, double *buf_
     if (fir_run(b, d_frame, 0, b->d_frame_out, 0, frame_len, b->s_frame, /*defer_history=*/true) != 0) return -1;
     LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned, b->d_frame_out, bytes, cudaMemcpyDeviceToHost, b->s_frame));
     LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    b->trail.pending = false;
     memcpy(buf_out, b->pinned, bytes);
     return frame_len;                                           // llz_fir.c:582
 }
@@ -1237,6 +1355,7 @@ extern "C" int llz_fir_filter_flush(unsigned long handle, double *buf_out)
     b->hist_zero = true;
     LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned, b->d_frame_out, bytes, cudaMemcpyDeviceToHost, b->s_frame));
     LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    b->trail.pending = false;
     memcpy(buf_out, b->pinned, bytes);
     return b->hist_len;                                         // llz_fir.c:624
 }
@@ -1291,6 +1410,7 @@ int poly_dropin_frame(unsigned long handle, int kind, unsigned char *sample_in, 
     if (outs != b->plan.num_out) { llz_set_error("internal: frame produced %lld samples, expected %d", outs, b->plan.num_out); return -1; }
     LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned_out, b->d_frame_out, (size_t)bytes_out, cudaMemcpyDeviceToHost, b->s_frame));
     LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    b->trail.pending = false;
     memcpy(sample_out, b->pinned_out, (size_t)bytes_out);
     if (sample_out_size) *sample_out_size = bytes_out;          // llz_resample.c:605
     return 0;

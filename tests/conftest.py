@@ -65,3 +65,11 @@ def cuda(zlib):
         pytest.fail("gpu-marked test run without a usable CUDA device")
     torch.cuda.set_device(0)
     return torch
+
+
+@pytest.fixture
+def small_pipe_slots(zlib):
+    """4 MiB staging slots for the *_run_host pipelines (llz_cuda_tune), restored afterwards"""
+    zlib.tune("pipe_slot_mib", 4)
+    yield
+    zlib.tune("pipe_slot_mib", 64)

@@ -226,11 +226,10 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
 
 @pytest.mark.parametrize("N,size", [(898, 8192), (2049, 8192), (4095, 8192), (6145, 8192),
                                     (2305, 16384), (4095, 16384), (8191, 16384), (12289, 16384)])
-def test_fft8k_16k_bank_interior_and_edge_items(zlib, port, cuda, monkeypatch, N, size):
+def test_fft8k_16k_bank_interior_and_edge_items(zlib, port, cuda, N, size):
     """8192-point (one CTA per item) and 16384-point (one two-CTA cluster per item, distributed shared memory)
     overlap-save kernels: several interior items, history splice, ragged end"""
     torch = cuda
-    monkeypatch.setenv("LLZ_FIR_FFT_SIZE", str(size))
     rng = np.random.default_rng(N)
     h = rng.standard_normal(N) / N ** 0.5
     C_, n = 3, 70001 if size == 8192 else 150001
@@ -241,6 +240,7 @@ def test_fft8k_16k_bank_interior_and_edge_items(zlib, port, cuda, monkeypatch, N
                                   (zlib.F32, torch.float32, np.float32, TOL_F32_ABS * scale)):
         dx = torch.from_numpy(x.astype(npdt)).cuda()
         bank = zlib.FirBank(C_, dtype, taps=h, algo=zlib.FIR_FFT)
+        bank.set_fft_size(size)
         assert bank.block_len == 2 * (size - (N - 1 + size // 32 - 1) // (size // 32) * (size // 32))
         dy = torch.full((C_, n + 64), 7.0, dtype=tdt, device="cuda")
         bank.run(dx, n, dy, n + 64, n)
@@ -292,43 +292,6 @@ def test_fft_bank_streaming_ragged_chunks(zlib, port, cuda, dtype, N):
     bank.run(dx, stride, dy, ostride, 1000)
     torch.cuda.synchronize()
     assert np.abs(dy.cpu().numpy()[:, :1000] - want[:, :1000]).max() <= tol
-    bank.close()
-
-
-def test_fft_f32_packed_kernel_matches_scalar_kernel_bits(zlib, port, cuda, monkeypatch):
-    """LLZ_FFT_F32X2=1 runs the float overlap-save transform on packed FP32 (two items per warp, FFMA2); each half is
-    the same IEEE operation sequence as the scalar-float kernel, so the bytes agree -- with the scalar kernel, and
-    between a one-shot run and aligned time segments (interior items packed, edge items scalar)"""
-    torch = cuda
-    N, C_, n = 127, 3, 200_003
-    h = port.fir_design(0, N, 0.23, 0.0, 0)
-    x = np.stack([port.lcg_f64(n, 31 + c) for c in range(C_)]).astype(np.float32)
-    dx = torch.from_numpy(x).cuda()
-    monkeypatch.setenv("LLZ_FFT_F32X2", "1")                 # the packed kernel is an opt-in experiment
-    bank = zlib.FirBank(C_, zlib.F32, taps=h, algo=zlib.FIR_FFT)
-    packed = torch.empty_like(dx)
-    bank.run(dx, n, packed, n, n)
-    torch.cuda.synchronize()
-    monkeypatch.setenv("LLZ_FFT_F32X2", "0")
-    scalar = torch.empty_like(dx)
-    bank.reset()
-    bank.run(dx, n, scalar, n, n)
-    torch.cuda.synchronize()
-    monkeypatch.setenv("LLZ_FFT_F32X2", "1")
-    assert torch.equal(packed, scalar)
-    want = oracle_bank(port, h, x.astype(np.float64))
-    assert snr_db(want, packed.cpu().numpy()) >= SNR_F32_DB
-    blk = bank.block_len
-    for world in (2, 7):
-        seg_out = torch.zeros_like(dx)
-        for rank in range(world):
-            s = zlib.shard_fir_segments_aligned(n, N, blk, world, rank)
-            bank.reset()
-            if s.halo:
-                bank.set_history(dx.data_ptr() + 4 * (s.in_start - s.halo), n)
-            bank.run(dx.data_ptr() + 4 * s.in_start, n, seg_out.data_ptr() + 4 * s.out_start, n, s.in_count)
-        torch.cuda.synchronize()
-        assert torch.equal(seg_out, packed), world
     bank.close()
 
 
@@ -395,11 +358,11 @@ def test_run_host_pipeline(zlib, port, cuda):
 
 
 @pytest.mark.parametrize("algo", [1, 2])
-def test_run_host_channel_groups_with_padded_rows(zlib, port, cuda, monkeypatch, algo):
+def test_run_host_channel_groups_with_padded_rows(zlib, port, cuda, small_pipe_slots, algo):
     """many short channels -> the host pipeline runs groups of whole channels; padded (non-dense) rows take the
     row-wise copy inside a group; the stream state carries over to the next call for every group"""
     torch = cuda
-    monkeypatch.setenv("LLZ_PIPE_SLOT_MB", "4")                 # 4 MiB slots: groups of 2 channels, 21 groups
+    # small_pipe_slots: 4 MiB slots -> groups of 2 channels, 21 groups
     N, C_, n = 127, 41, 100_003
     h = port.fir_design(0, N, 0.23, 0.0, 0)
     xs, ys = n + 5, n + 9

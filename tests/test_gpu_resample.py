@@ -261,16 +261,16 @@ def test_c3_shape_spot_checks(zlib, port, cuda):
     bank.close()
 
 
-@pytest.mark.parametrize("no_imma", ["0", "1"])
+@pytest.mark.parametrize("tiles", [1, 2, 3])
 @pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0)])
-def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, monkeypatch, L_, M, k, no_imma):
-    """The exact mode's two tile kernels: INT8 tensor cores (default: taps as five int8 digit planes, samples as two byte
-    planes, exact s32 accumulation, a two-level near-integer guard) and FP64 tensor cores (LLZ_BANK_NO_IMMA=1) -- the
-    int16 output must be the reference's, bit for bit, from both."""
+def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, L_, M, k, tiles):
+    """The exact mode's three tile kernels: INT8 tensor cores (default: taps as five int8 digit planes, samples as two
+    byte planes, exact s32 accumulation, a two-level near-integer guard), FP64 tensor cores and the DFMA register tile
+    (llz_cuda_resample_bank_set_tiles) -- the int16 output must be the reference's, bit for bit, from all of them."""
     torch = cuda
-    monkeypatch.setenv("LLZ_BANK_NO_IMMA", no_imma)
     C_ = 3
     bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, C_, k_override=k)
+    bank.set_tiles(tiles)
     plan = port.resample_plan(L_, M, 1, k)
     n_in = plan.num_in * 2 + 777
     x = np.stack([port.lcg_s16(n_in, 4000 + c) for c in range(C_)])
@@ -289,23 +289,4 @@ def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, monkeyp
     for c in range(C_):
         want = port.resample_run(plan, 1.0, x[c], n_out)
         assert np.array_equal(got[c], want), (L_, M, c, int(np.abs(got[c].astype(np.int32) - want).max()))
-    bank.close()
-
-
-def test_bank_fast_mode_on_the_integer_tensor_cores(zlib, port, cuda, monkeypatch):
-    """LLZ_BANK_IMMA_FAST=1: the fast mode as a three-digit integer evaluation (22 significant tap bits, like the fp16 split):
-    within 1 LSB of the reference, knife-edge phase exact."""
-    torch = cuda
-    monkeypatch.setenv("LLZ_BANK_IMMA_FAST", "1")
-    L_, M, k = 320, 147, 128
-    bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, 2, k_override=k, acc=zlib.ACC_F32)
-    n_in = bank.info.num_in
-    x = np.stack([port.lcg_s16(n_in, 77 + c) for c in range(2)])
-    n_out = bank.out_len(n_in)
-    want = oracle_resample(port, L_, M, 1, k, 1.0, x, n_out).astype(np.int32)
-    dy = torch.zeros(2, n_out, dtype=torch.int16, device="cuda")
-    bank.run(torch.from_numpy(x).cuda(), n_in, n_in, dy, n_out)
-    torch.cuda.synchronize()
-    diff = np.abs(dy.cpu().numpy().astype(np.int32) - want)
-    assert diff.max() <= 1 and (diff != 0).mean() <= 0.02 and not diff[:, ::L_].any()
     bank.close()

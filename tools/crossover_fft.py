@@ -16,11 +16,10 @@ for dtype, tdt in ((z.F64, torch.float64), (z.F32, torch.float32)):
         row = [f"{'f64' if dtype == z.F64 else 'f32'} taps {taps:4d}:"]
         for size in ("1024", "8192", "direct"):
             if size == "direct":
-                os.environ.pop("LLZ_FIR_FFT_SIZE", None)
                 bank = z.FirBank(C_, dtype, kind=z.LPF, flt_len=taps, fc1=0.2, algo=z.FIR_DIRECT)
             else:
-                os.environ["LLZ_FIR_FFT_SIZE"] = size
                 bank = z.FirBank(C_, dtype, kind=z.LPF, flt_len=taps, fc1=0.2, algo=z.FIR_FFT)
+                bank.set_fft_size(int(size))
             for _ in range(3):
                 bank.run(dx, n, dy, n, n)
             torch.cuda.synchronize()

@@ -17,8 +17,8 @@ for dtype, tdt in ((z.F64, torch.float64), (z.F32, torch.float32)):
         for size in ("8192", "16384"):
             if size == "8192" and taps > 6145:
                 continue
-            os.environ["LLZ_FIR_FFT_SIZE"] = size
             bank = z.FirBank(C_, dtype, kind=z.LPF, flt_len=taps, fc1=0.2, algo=z.FIR_FFT)
+            bank.set_fft_size(int(size))
             for _ in range(3):
                 bank.run(dx, n, dy, n, n)
             torch.cuda.synchronize()
