@@ -211,6 +211,72 @@ int llz_cuda_shard_resample_segments(long long n_in, int L, int M, int taps_per_
                                      int frame_in, int world, int rank, llz_cuda_segment_t *seg);
 
 /* ======================================================================================== */
+/* Multi-GPU contexts and sharded jobs (SURVEY.md 8b extension 4, 8e)                        */
+/* ======================================================================================== */
+/* The reference is one mono stream per handle; what it offers for partitioning is its frame streaming with a history
+ * prefix (llz_fir.c:561-566, llz_resample.c:570-576).  A job here is ONE whole-signal call over n_channels planar
+ * channels, cut either by channel (independent handles) or into time segments that carry their flt_len-1 / Q-1 halo;
+ * the concatenated result is byte-identical to the single-GPU call.  No exchange happens during the computation; the
+ * optional gather puts the whole planar result into one rank's device memory.
+ *
+ * Two process models share the API: ONE process driving n GPUs (init_all) or one process PER GPU (init_rank with a
+ * shared 128-byte NCCL id: torchrun / MPI).  A context has `local_count` local slots (n or 1); per-slot arguments are
+ * arrays of local_count entries.  NCCL is loaded at run time (libnccl.so.2) when the first context is created.        */
+enum { LLZ_CUDA_SHARD_CHANNEL = 0, LLZ_CUDA_SHARD_TIME = 1 };
+enum {
+    LLZ_CUDA_GATHER_NONE = 0,  /* every rank keeps its shard in d_out                                               */
+    LLZ_CUDA_GATHER_NCCL = 1,  /* shards are computed in `chunks` pieces; piece c travels to the root by grouped
+                                  ncclSend/ncclRecv on a second stream while piece c+1 is computed                   */
+    LLZ_CUDA_GATHER_PEER = 2,  /* the kernels store straight into the root's buffer over NVLink (peer mapping / CUDA
+                                  IPC): compute and gather are one kernel, nothing is staged                         */
+};
+typedef struct {
+    int first_channel, n_channels;   /* channels owned by the rank                                                  */
+    llz_cuda_segment_t seg;          /* samples owned by the rank (the whole signal for channel shards)             */
+} llz_cuda_shard_t;
+
+int           llz_cuda_mgpu_unique_id(unsigned char id[128]);               /* rank 0 makes it, everybody gets a copy */
+unsigned long llz_cuda_mgpu_init_rank(const unsigned char id[128], int world, int rank);   /* uses the current device */
+unsigned long llz_cuda_mgpu_init_all(int n_gpus, const int *devices /* NULL = 0..n_gpus-1 */);
+void          llz_cuda_mgpu_uninit(unsigned long ctx);
+int           llz_cuda_mgpu_world(unsigned long ctx);
+int           llz_cuda_mgpu_local_count(unsigned long ctx);
+int           llz_cuda_mgpu_local_rank(unsigned long ctx, int local_idx);
+int           llz_cuda_mgpu_local_device(unsigned long ctx, int local_idx);
+/* The gathered result lives in a buffer of `bytes` on rank `root`'s device, owned by the context (collective call:
+ * every process, same arguments).  result_ptr is the address under which local slot `local_idx` reaches it: the
+ * allocation itself on the root, a peer / IPC mapping elsewhere (NULL when the device has no P2P path to the root).  */
+int           llz_cuda_mgpu_result_alloc(unsigned long ctx, int root, size_t bytes);
+void         *llz_cuda_mgpu_result_ptr(unsigned long ctx, int local_idx);
+int           llz_cuda_mgpu_result_free(unsigned long ctx);
+
+/* one bank per local slot, sized for the slot's shard (channel mode: its share of n_channels; time mode: all of them) */
+unsigned long llz_cuda_mgpu_fir_init(unsigned long ctx, int kind, int flt_len, double fc1, double fc2,
+                                     win_t win_type, int n_channels, int dtype, int shard_mode);
+unsigned long llz_cuda_mgpu_resample_init(unsigned long ctx, int L, int M, double gain, win_t win_type,
+                                          int k_override, int n_channels, int acc, int shard_mode);
+void          llz_cuda_mgpu_job_uninit(unsigned long job);
+unsigned long llz_cuda_mgpu_job_bank(unsigned long job, int local_idx);      /* the slot's bank (set_algo, info ...)  */
+/* what `rank` owns of a job over n_total input samples per channel, and the outputs per channel of the whole job;
+ * time mode: FIR boundaries fall on multiples of the bank's work-item length, resampler boundaries on whole frames
+ * (n_total must be a multiple of num_in)                                                                             */
+int           llz_cuda_mgpu_job_plan(unsigned long job, long long n_total, int rank, llz_cuda_shard_t *shard);
+long long     llz_cuda_mgpu_job_out_len(unsigned long job, long long n_total);
+/* One whole-signal call, sharded.  Per local slot i (rank r, shard s = job_plan(r)):
+ *   d_in[i]   the rank's input: channel s.first_channel, sample s.seg.in_start - s.seg.halo (the halo comes with the
+ *             rank's own slice: no exchange), in_stride[i] elements between channels;
+ *   d_out[i]  the rank's shard [s.n_channels][s.seg.out_count] (GATHER_NONE; GATHER_NCCL: dense, out_stride ==
+ *             out_count; ignored by the root and by GATHER_PEER);
+ *   streams[i] the caller's stream on the slot's device; everything the call enqueues -- on the root including the
+ *             arrival of every other rank's outputs -- is ordered before later work on that stream.
+ * gather != NONE: the whole planar result [n_channels][result_stride] lands in the context's result buffer.
+ * chunks: pieces per shard for GATHER_NCCL (1..8, 0 = 4).  Asynchronous; multi-process: collective.                   */
+int           llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const void *const *d_in,
+                                    const long long *in_stride, void *const *d_out, const long long *out_stride,
+                                    long long result_stride, int gather, int chunks,
+                                    const llz_cuda_stream_t *streams);
+
+/* ======================================================================================== */
 /* Interleaved PCM frames <-> planar channels                           */
 /* ======================================================================================== */
 /* The reference filters a multi-channel WAV as one interleaved mono stream (quirk R7,

@@ -28,6 +28,8 @@ F64, F64_STRICT, F32 = 0, 1, 2
 FIR_AUTO, FIR_DIRECT, FIR_FFT = 0, 1, 2
 ACC_F64, ACC_F64_STRICT, ACC_F32 = 0, 1, 2
 TILES_AUTO, TILES_INT8, TILES_FP64_TENSOR, TILES_CUDA_CORE = 0, 1, 2, 3
+SHARD_CHANNEL, SHARD_TIME = 0, 1
+GATHER_NONE, GATHER_NCCL, GATHER_PEER = 0, 1, 2
 KIND_DECIMATE, KIND_INTERP, KIND_RESAMPLE = 0, 1, 2
 PCM_S16, PCM_S24, PCM_F32 = 0, 1, 2
 PLANAR_S16, PLANAR_F32, PLANAR_F64 = 0, 1, 2
@@ -52,6 +54,10 @@ class ResampleInfo(C.Structure):
 class Segment(C.Structure):
     _fields_ = [("in_start", _ll), ("in_count", _ll), ("halo", _ll), ("out_start", _ll),
                 ("out_count", _ll)]
+
+
+class Shard(C.Structure):
+    _fields_ = [("first_channel", C.c_int), ("n_channels", C.c_int), ("seg", Segment)]
 
 
 def build(verbose: bool = False) -> str:
@@ -138,6 +144,25 @@ _SIGNATURES = [
     ("llz_cuda_shard_fir_segments_aligned", C.c_int, [_ll, C.c_int, _ll, C.c_int, C.c_int, C.POINTER(Segment)]),
     ("llz_cuda_shard_resample_segments", C.c_int,
      [_ll, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Segment)]),
+    ("llz_cuda_mgpu_unique_id", C.c_int, [C.c_char_p]),
+    ("llz_cuda_mgpu_init_rank", _ul, [C.c_char_p, C.c_int, C.c_int]),
+    ("llz_cuda_mgpu_init_all", _ul, [C.c_int, C.POINTER(C.c_int)]),
+    ("llz_cuda_mgpu_uninit", None, [_ul]),
+    ("llz_cuda_mgpu_world", C.c_int, [_ul]),
+    ("llz_cuda_mgpu_local_count", C.c_int, [_ul]),
+    ("llz_cuda_mgpu_local_rank", C.c_int, [_ul, C.c_int]),
+    ("llz_cuda_mgpu_local_device", C.c_int, [_ul, C.c_int]),
+    ("llz_cuda_mgpu_result_alloc", C.c_int, [_ul, C.c_int, C.c_size_t]),
+    ("llz_cuda_mgpu_result_ptr", _vp, [_ul, C.c_int]),
+    ("llz_cuda_mgpu_result_free", C.c_int, [_ul]),
+    ("llz_cuda_mgpu_fir_init", _ul, [_ul, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("llz_cuda_mgpu_resample_init", _ul, [_ul, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("llz_cuda_mgpu_job_uninit", None, [_ul]),
+    ("llz_cuda_mgpu_job_bank", _ul, [_ul, C.c_int]),
+    ("llz_cuda_mgpu_job_plan", C.c_int, [_ul, _ll, C.c_int, C.POINTER(Shard)]),
+    ("llz_cuda_mgpu_job_out_len", _ll, [_ul, _ll]),
+    ("llz_cuda_mgpu_job_run", C.c_int, [_ul, _ll, C.POINTER(_vp), C.POINTER(_ll), C.POINTER(_vp), C.POINTER(_ll), _ll,
+                                        C.c_int, C.c_int, C.POINTER(_vp)]),
     ("llz_cuda_pcm_deinterleave", C.c_int, [_vp, C.c_int, C.c_int, _ll, _vp, C.c_int, _ll, _vp]),
     ("llz_cuda_pcm_interleave", C.c_int, [_vp, C.c_int, _ll, C.c_int, _ll, _vp, C.c_int, _vp]),
     ("llz_cuda_synth_lcg", C.c_int, [_vp, _ll, C.c_int, _ll, C.c_int, C.c_uint, _vp]),
@@ -505,6 +530,89 @@ class ResampleBank:
             self.close()
         except Exception:
             pass
+
+
+# ---- multi-GPU contexts and sharded jobs ------------------------------------------------------------------
+def mgpu_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().llz_cuda_mgpu_unique_id(buf), "llz_cuda_mgpu_unique_id")
+    return buf.raw
+
+
+class Mgpu:
+    """llz_cuda_mgpu_init_all (one process, n GPUs) or llz_cuda_mgpu_init_rank (one process per GPU)."""
+
+    def __init__(self, n_gpus: int = 0, devices=None, *, unique_id: bytes | None = None, world: int = 0, rank: int = 0):
+        L = lib()
+        if unique_id is not None:
+            h = L.llz_cuda_mgpu_init_rank(unique_id, world, rank)
+        else:
+            arr = (C.c_int * n_gpus)(*devices) if devices is not None else None
+            h = L.llz_cuda_mgpu_init_all(n_gpus, arr)
+        self.handle = _handle(h, "llz_cuda_mgpu_init")
+        self.world = L.llz_cuda_mgpu_world(self.handle)
+        self.nlocal = L.llz_cuda_mgpu_local_count(self.handle)
+        self.ranks = [L.llz_cuda_mgpu_local_rank(self.handle, i) for i in range(self.nlocal)]
+        self.devices = [L.llz_cuda_mgpu_local_device(self.handle, i) for i in range(self.nlocal)]
+
+    def result_alloc(self, root: int, nbytes: int):
+        _check(lib().llz_cuda_mgpu_result_alloc(self.handle, root, nbytes), "llz_cuda_mgpu_result_alloc")
+
+    def result_ptr(self, local_idx: int) -> int | None:
+        return lib().llz_cuda_mgpu_result_ptr(self.handle, local_idx)
+
+    def result_free(self):
+        _check(lib().llz_cuda_mgpu_result_free(self.handle), "llz_cuda_mgpu_result_free")
+
+    def close(self):
+        if self.handle:
+            lib().llz_cuda_mgpu_uninit(self.handle)
+            self.handle = 0
+
+
+class MgpuJob:
+    """A sharded FIR or resampler job (llz_cuda_mgpu_fir_init / llz_cuda_mgpu_resample_init)."""
+
+    def __init__(self, ctx: Mgpu, handle: int):
+        self.ctx = ctx
+        self.handle = _handle(handle, "llz_cuda_mgpu_*_init")
+
+    @classmethod
+    def fir(cls, ctx: Mgpu, n_channels: int, dtype: int, shard_mode: int, *, kind: int = LPF, flt_len: int,
+            fc1: float, fc2: float = 0.0, win: int = HAMMING):
+        return cls(ctx, lib().llz_cuda_mgpu_fir_init(ctx.handle, kind, flt_len, fc1, fc2, win, n_channels, dtype, shard_mode))
+
+    @classmethod
+    def resample(cls, ctx: Mgpu, L_: int, M: int, n_channels: int, shard_mode: int, *, gain: float = 1.0,
+                 win: int = BLACKMAN, k_override: int = 0, acc: int = ACC_F64):
+        return cls(ctx, lib().llz_cuda_mgpu_resample_init(ctx.handle, L_, M, gain, win, k_override, n_channels, acc, shard_mode))
+
+    def bank(self, local_idx: int = 0) -> int:
+        return _handle(lib().llz_cuda_mgpu_job_bank(self.handle, local_idx), "llz_cuda_mgpu_job_bank")
+
+    def plan(self, n_total: int, rank: int) -> Shard:
+        sh = Shard()
+        _check(lib().llz_cuda_mgpu_job_plan(self.handle, n_total, rank, C.byref(sh)), "llz_cuda_mgpu_job_plan")
+        return sh
+
+    def out_len(self, n_total: int) -> int:
+        return _check(lib().llz_cuda_mgpu_job_out_len(self.handle, n_total), "llz_cuda_mgpu_job_out_len")
+
+    def run(self, n_total: int, d_in, in_stride, d_out, out_stride, result_stride: int = 0, gather: int = GATHER_NONE,
+            chunks: int = 0, streams=None):
+        n = self.ctx.nlocal
+        vin = (_vp * n)(*[_ptr(a) for a in d_in])
+        sin = (_ll * n)(*in_stride)
+        vout = (_vp * n)(*[_ptr(a) for a in d_out]) if d_out is not None else None
+        sout = (_ll * n)(*out_stride) if out_stride is not None else None
+        vst = (_vp * n)(*streams) if streams is not None else None
+        _check(lib().llz_cuda_mgpu_job_run(self.handle, n_total, vin, sin, vout, sout, result_stride, gather, chunks, vst),
+               "llz_cuda_mgpu_job_run")
+
+    def close(self):
+        if self.handle:
+            lib().llz_cuda_mgpu_job_uninit(self.handle)
+            self.handle = 0
 
 
 def pcm_deinterleave(d_frames, pcm_format: int, n_channels: int, n_frames: int, d_planar, planar_type: int,

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -677,8 +678,12 @@ long long poly_out_len(const PolyBank *b, long long n_in)
 
 // defer_history (single-channel drop-in frames with n_in >= hist_len): leave the history where it is -- the tail of
 // d_in, which the caller keeps intact until the next call -- instead of copying it into d_hist
-int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_in, int16_t *d_out,
-             long long out_stride, long long *n_out, cudaStream_t st, bool defer_history = false)
+// channels [c0, c0 + cc) of the bank; d_in / d_out point at channel c0.  `last` = the call completes the bank's step:
+// the counters advance and the history ping-pong flips once every channel group has been run (llz_mgpu.inl runs
+// groups of whole channels so that each group's output can travel while the next one is computed).
+int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_in, int16_t *d_out,
+                  long long out_stride, long long *n_out, cudaStream_t st, int c0, int cc, bool last,
+                  bool defer_history = false)
 {
     const llz_plan_t &p = b->plan;
     if (n_in < 0) { llz_set_error("negative sample count"); return -1; }
@@ -704,7 +709,8 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.x = d_in;
     a.x_stride = in_stride;
     a.n_in = n_in;
-    a.hist = b->chain_src ? b->chain_src : (b->hist_zero || p.hist_len == 0) ? nullptr : b->d_hist[b->cur];
+    a.hist = b->chain_src ? b->chain_src
+             : (b->hist_zero || p.hist_len == 0) ? nullptr : b->d_hist[b->cur] + (size_t)c0 * p.hist_len;
     a.hist_len = p.hist_len;
     a.y = d_out;
     a.y_stride = out_stride;
@@ -738,19 +744,30 @@ int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_
     a.imma_scale = ldexp(1.0, -b->imma_shift);
     // first-level band of the integer evaluation: the (scaled) FP64 band plus the taps' rounding bound
     a.imma_thr = b->guard_thr * b->guard_scale + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
-    if (poly_launch(a, b->n_channels, st) != 0) return -1;
+    if (poly_launch(a, cc, st) != 0) return -1;
     if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
         b->chain_src = d_in + (n_in - p.hist_len);
     } else if (p.hist_len > 0) {
-        const int16_t *old = b->hist_zero ? nullptr : b->d_hist[b->cur];
-        if (poly_update_history(d_in, in_stride, n_in, old, b->d_hist[b->cur ^ 1], p.hist_len, b->n_channels, st) != 0)
+        const int16_t *old = b->hist_zero ? nullptr : b->d_hist[b->cur] + (size_t)c0 * p.hist_len;
+        if (poly_update_history(d_in, in_stride, n_in, old, b->d_hist[b->cur ^ 1] + (size_t)c0 * p.hist_len, p.hist_len, cc,
+                                st) != 0)
             return -1;
-        b->cur ^= 1;
-        b->hist_zero = false;
+        if (last) {
+            b->cur ^= 1;
+            b->hist_zero = false;
+        }
     }
-    b->consumed += n_in;
-    b->produced += outs;
+    if (last) {
+        b->consumed += n_in;
+        b->produced += outs;
+    }
     return 0;
+}
+
+int poly_run(PolyBank *b, const int16_t *d_in, long long in_stride, long long n_in, int16_t *d_out,
+             long long out_stride, long long *n_out, cudaStream_t st, bool defer_history = false)
+{
+    return poly_run_part(b, d_in, in_stride, n_in, d_out, out_stride, n_out, st, 0, b->n_channels, true, defer_history);
 }
 
 int poly_reset(PolyBank *b)
@@ -1462,3 +1479,8 @@ extern "C" int llz_resample(unsigned long handle, unsigned char *sample_in, int 
 {
     return poly_dropin_frame(handle, LLZ_KIND_RESAMPLE, sample_in, sample_in_size, sample_out, sample_out_size);
 }
+
+// ====================================================================================================
+// multi-GPU contexts and sharded jobs (same translation unit: they drive the banks' channel-group entry points)
+// ====================================================================================================
+#include "llz_mgpu.inl"

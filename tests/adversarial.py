@@ -43,8 +43,24 @@ def tune_output(rng, terms, x, gain: float, side: int, tries: int = 48, amp: int
     n = len(x)
     live = [(abs(c), c, s) for c, s in terms if 0 <= s < n and c != 0.0]
     live.sort(reverse=True)
-    (_, ca, sa), (_, cb, sb), (_, cc, sc) = live[0], live[1], live[2]
+    if len(live) < 3:
+        return None
     vals = np.arange(-amp, amp + 1, dtype=np.float64)
+
+    def max_gap(coef):
+        """largest hole in the fractional parts coef*x can supply: a tap near a small rational (1/3, 1 - eps) supplies few"""
+        f = np.sort(np.mod(coef * gain * vals, 1.0))
+        return max(float(np.diff(f).max()), float(f[0] + 1.0 - f[-1]))
+
+    # distinct magnitudes only: a symmetric prototype has its taps in equal pairs, and c*(xa + xb) is one sample's worth
+    distinct = []
+    for t in live[:12]:
+        if all(abs(t[0] - u[0]) > 1e-9 * u[0] for u in distinct):
+            distinct.append(t)
+    cand = sorted(distinct, key=lambda t: max_gap(t[1]))
+    if len(cand) < 3 or max_gap(cand[1][1]) > 1e-3:
+        return None
+    (_, ca, sa), (_, cb, sb), (_, cc, sc) = cand[0], cand[1], cand[2]
     fa = np.mod(ca * gain * vals, 1.0)
     order = np.argsort(fa)
     fa_sorted = fa[order]

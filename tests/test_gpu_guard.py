@@ -75,7 +75,7 @@ def test_widened_guard_band_takes_the_recompute_and_stays_bit_identical(zlib, po
         assert np.array_equal(got[c], want), (what, c)
     # outputs of single-tap (knife-edge) rows never take the guard; everything else hits with probability ~2*band
     assert hits >= n_out * C_ // 1000, (what, hits, n_out)
-    assert hits <= n_out * C_ // 10, (what, hits, n_out)
+    assert hits <= n_out * C_ // 2, (what, hits, n_out)         # the band grows with Q: ~17 % at Q = 257
     bank.close()
 
 
@@ -96,7 +96,7 @@ def test_widened_guard_band_interp_general_kernel(zlib, port, cuda):
 
 @pytest.mark.parametrize("kind,L_,M,k,tiles,what", CASES[:5] + CASES[6:8])
 def test_adversarial_near_integer_sums_with_the_production_band(zlib, port, cuda, kind, L_, M, k, tiles, what):
-    """24 outputs per channel tuned to within a few ulps of a non-zero integer, half of them at or just above it and half
+    """16 outputs per channel tuned to within a few ulps of a non-zero integer, half of them at or just above it and half
     just below: the fast evaluation may land on either side, the guard has to send every one of them to the
     reference-order sum"""
     torch = cuda
@@ -107,18 +107,23 @@ def test_adversarial_near_integer_sums_with_the_production_band(zlib, port, cuda
     rng = np.random.default_rng(L_ * 1000 + M + tiles)
     x = np.stack([port.lcg_s16(n_in, 3300 + c) for c in range(C_)]).copy()
     targets = []
-    n_targets = 24
+    n_targets = 16
     step = (n_out - 2 * plan.cols * max(L_, 1)) // n_targets
     for c in range(C_):
         for j in range(n_targets):
             o = plan.cols * max(L_, 1) + j * step + int(rng.integers(0, max(1, step // 4)))
-            if kind == "decimate":
-                terms = terms_decimate(plan, o)
-            else:
-                if np.count_nonzero(plan.bank[o % plan.L]) < 3:
-                    o += 1                                     # the knife-edge phase has a single tap: no guard needed
-                terms = terms_resample(plan, o)
-            r = tune_output(rng, terms, x[c], 1.0, side=1 if j % 2 == 0 else -1, tries=32)
+            r = None
+            for attempt in range(4):                           # a phase whose taps are near small rationals cannot be tuned: next
+                if kind == "decimate":
+                    terms = terms_decimate(plan, o)
+                else:
+                    if np.count_nonzero(plan.bank[o % plan.L]) < 3:
+                        o += 1                                 # the knife-edge phase has a single tap: no guard needed
+                    terms = terms_resample(plan, o)
+                r = tune_output(rng, terms, x[c], 1.0, side=1 if j % 2 == 0 else -1, tries=24)
+                if r is not None:
+                    break
+                o += 1
             assert r is not None, (what, c, j)
             targets.append((c, o, terms, r))
     # later targets never touch earlier windows' samples: re-evaluate every target on the final input
