@@ -4,10 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--dtype f64|f32]
     python bench.py --impl reference ...        # the reference's own CPU code, all host threads
 
-One "step" = one pass of the hot path over one batch of synthetic input.  The default workload is
+One "step" = one pass of the hot path over one batch of synthetic input.  The headline workload is
 BASELINE.json configs[1] (C2): llz_fir 127-tap low-pass on 1024 independent channels x 10 s @ 48 kHz,
-in the reference's sample type (double).  With N > 1 (torchrun, one rank per GPU) the channels are
-independent units: every rank runs its own 1024-channel batch, no data-path collective (weak scaling).
+in the reference's sample type (double); the default run then measures every other config (C3, C4 at
+its full hour, C5, and the f32 / fast variants) the same way and reports them under "workloads", each
+with its own roofline, clocks and an oracle parity record.  With N > 1 (torchrun, one rank per GPU)
+the BASELINE totals are SPLIT across the ranks through the library's multi-GPU job API
+(llz_cuda_mgpu_*): C2 / C3 by channel, C4 / C5 into time segments with halo (strong scaling, no
+data-path collective); the step is also timed with the result gathered on rank 0 (chunked NCCL
+send/recv overlapped with compute, and kernels storing straight into rank 0's buffer over NVLink),
+and every rank's shard is compared byte for byte with the one-GPU call.
 
 The JSON line carries: value (device-timed, inputs resident in HBM), e2e (host buffers through the
 C-ABI, H2D + D2H inside the timed region), roofline (dominant kernel, algorithmic bytes and flops
@@ -38,12 +44,15 @@ FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 74.4
 WORKLOADS = {
     "c2": dict(kind="fir", desc="llz_fir 127-tap lowpass (fc 0.23, HAMMING), 1024 channels x 480000 samples (10 s @ 48 kHz)",
                channels=1024, n=480_000, taps=127, fc=0.23, win=0, seed=12345, shard="channel"),
-    "c5": dict(kind="fir", desc="llz_fir 4095-tap lowpass (fc 0.11, KAISER), 16 channels x 57.6 M samples (5 min @ 192 kHz slice of the 1 h stream)",
-               channels=16, n=57_600_000, taps=4095, fc=0.11, win=2, seed=12345, shard="time"),
+    # C5 as doubles is 88.5 GB in + 88.5 GB out for the full hour: more than one 180 GB GPU holds beside the context, so the
+    # f64 bench line filters 16 channels x 20 min (29.5 + 29.5 GB; the same total at every N, strong scaling); the f32
+    # variant (--dtype f32) runs the same 20 min
+    "c5": dict(kind="fir", desc="llz_fir 4095-tap lowpass (fc 0.11, KAISER), 16 channels x 230.4 M samples (20 min @ 192 kHz of the 1 h stream; the full hour as f64 is 177 GB)",
+               channels=16, n=230_400_000, taps=4095, fc=0.11, win=2, seed=12345, shard="time"),
     "c3": dict(kind="resample", desc="llz_resample 48 kHz -> 16 kHz (L=1, M=3, BLACKMAN, Q=134), 64 channels x 28.8 M samples (10 min)",
                channels=64, n=28_800_000, L=1, M=3, k=0, win=1, seed=777, shard="channel"),
-    "c4": dict(kind="resample", desc="llz_resample 44.1 kHz -> 96 kHz (L=320, M=147, BLACKMAN, 256-tap bank: k=128, Q=257), 8 channels x 15.876 M samples (6 min slice of the 1 h stream)",
-               channels=8, n=47_040 * 338, L=320, M=147, k=128, win=1, seed=777, shard="time"),
+    "c4": dict(kind="resample", desc="llz_resample 44.1 kHz -> 96 kHz (L=320, M=147, BLACKMAN, 256-tap bank: k=128, Q=257), 8 channels x 158.76 M samples (the full 1 h stream, 3375 frames of 47040)",
+               channels=8, n=47_040 * 3375, L=320, M=147, k=128, win=1, seed=777, shard="time"),
 }
 
 
@@ -171,7 +180,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    wl = WORKLOADS[args.workload]
+    wl_name = args.workload or "c2"
+    wl = WORKLOADS[wl_name]
     threads = os.cpu_count() or 1
     cpt, n = reference_sample_shape(wl)
     for _ in range(args.warmup):
@@ -187,7 +197,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if wl["kind"] == "fir" else "s16 io / f64 acc", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "timing": "host wall clock (CPU implementation, no device)"},
+            "config": {"workload": wl["desc"], "name": wl_name, "timing": "host wall clock (CPU implementation, no device)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -213,254 +223,525 @@ def bind_to_gpu_numa_node(index: int):
 
 
 # ---- the CUDA arm ------------------------------------------------------------------------------------------------------
-def run_cuda(args):
-    import torch
-    import torch.distributed as dist
-    import llzlab_b200 as z
+class Dist:
+    """torch.distributed plumbing of one rank (one process per GPU under torchrun)"""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libllzfilter_cuda has no CPU path (use --impl reference for the CPU arm)")
-    bind_to_gpu_numa_node(local)
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL prints its version banner on stdout when the first communicator comes up; keep stdout for the JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def init(self):
+        torch, dist = self.torch, self.dist
+        if self.world > 1:
+            # NCCL prints its version banner on stdout when the first communicator comes up; keep stdout for the JSON line
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    z.lib()
-    wl = WORKLOADS[args.workload]
-    C_, n = wl["channels"], wl["n"]
-    stream = torch.cuda.current_stream().cuda_stream
-    hbm_peak, peak_src = peaks()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
-    # ---- this rank's share of the job --------------------------------------------------------------
-    # channel-sharded workloads (C2, C3): every rank runs its own full batch of channels (weak scaling, no collective).
-    # time-sharded workloads (C4, C5) at N > 1: the stated stream is cut into N segments; a rank owns
-    # [seg.in_start, +in_count) and reads `halo` samples before it (strong scaling, no collective: the halo comes
-    # with the rank's own slice of the input).
-    time_sharded = wl["shard"] == "time" and world > 1
-    scaling = "strong" if time_sharded else "weak"
-    seg_first, halo = 0, 0
-    if wl["kind"] == "fir":
-        f32 = args.dtype == "f32"
-        tdt, es = (torch.float32, 4) if f32 else (torch.float64, 8)
-        bank = z.FirBank(C_, z.F32 if f32 else z.F64, kind=z.LPF, flt_len=wl["taps"], fc1=wl["fc"], win=wl["win"],
-                         algo={"auto": z.FIR_AUTO, "direct": z.FIR_DIRECT, "fft": z.FIR_FFT}[args.algo])
-        if time_sharded:
-            # boundaries at multiples of the kernel's work-item length: the concatenated output is then byte-identical
-            # to the one-GPU run for the overlap-save kernels as well (tests/test_gpu_fir.py)
-            seg = z.shard_fir_segments_aligned(n, wl["taps"], bank.block_len, world, rank)
-            seg_first, halo, n = seg.in_start - seg.halo, seg.halo, seg.in_count
-        dx_all = torch.empty(C_, halo + n, dtype=tdt, device="cuda")
-        z.synth_lcg_at(dx_all, halo + n, C_, seg_first, halo + n, 1 if f32 else 0, wl["seed"], stream)
-        x_stride = halo + n
-        dx = dx_all[:, halo:]
-        dy = torch.empty(C_, n, dtype=tdt, device="cuda")
-        n_out = n
-        flop_per_out, bytes_per_out = 2.0 * wl["taps"], 2.0 * es
-        dtype_name = "f32" if f32 else "f64"
-        fma_peak_nominal = FP32_NOMINAL_TFLOPS if f32 else FP64_NOMINAL_TFLOPS
-        fma_dtype = z.F32 if f32 else z.F64
-        fir_fft = bank.algo == z.FIR_FFT
-        if fir_fft and wl["taps"] >= 545:
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_obj(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+def checksum64(t):
+    """position-weighted 64-bit checksum of a tensor's bytes, computed on the device (wraps mod 2^64)"""
+    import torch
+    v = t.contiguous().view(torch.uint8).reshape(-1)
+    pad = (-v.numel()) % 8
+    if pad:
+        v = torch.cat([v, v.new_zeros(pad)])
+    w = v.view(torch.int64)
+    idx = torch.arange(w.numel(), device=w.device, dtype=torch.int64) * 2 + 1
+    return int((w * idx).sum().item())
+
+
+class Workload:
+    """One BASELINE config on this rank: its share of the job (the whole job at N = 1; at N > 1 a channel shard or a
+    time segment with halo through the library's multi-GPU job API, include/llz_cuda.h "Multi-GPU"), the timed step,
+    the oracle window check and the byte-identity check against the one-GPU call."""
+
+    def __init__(self, z, D: Dist, name: str, dtype: str, algo: str, mg):
+        import torch
+        self.z, self.D, self.torch, self.name, self.dtype = z, D, torch, name, dtype
+        wl = self.wl = WORKLOADS[name]
+        self.fir = wl["kind"] == "fir"
+        world, rank = D.world, D.rank
+        self.stream = torch.cuda.current_stream().cuda_stream
+        C_, n = wl["channels"], wl["n"]
+        self.C_total, self.n_total = C_, n
+        f32 = dtype == "f32"
+        self.mode = z.SHARD_TIME if wl["shard"] == "time" else z.SHARD_CHANNEL
+        self.job = self.bank = None
+        if self.fir:
+            self.tdt, self.es, self.np_dt = (torch.float32, 4, np.float32) if f32 else (torch.float64, 8, np.float64)
+            self.lcg_kind = 1 if f32 else 0
+            bank_dtype = z.F32 if f32 else z.F64
+            fir_algo = {"auto": z.FIR_AUTO, "direct": z.FIR_DIRECT, "fft": z.FIR_FFT}[algo]
+            if world > 1:
+                self.job = z.MgpuJob.fir(mg, C_, bank_dtype, self.mode, kind=z.LPF, flt_len=wl["taps"], fc1=wl["fc"], win=wl["win"])
+                self.bank_handle = self.job.bank(0)
+                if fir_algo != z.FIR_AUTO:
+                    z._check(z.lib().llz_cuda_fir_bank_set_algo(self.bank_handle, fir_algo), "set_algo")
+                self.fir_fft = z.lib().llz_cuda_fir_bank_get_algo(self.bank_handle) == z.FIR_FFT
+            else:
+                self.bank = z.FirBank(C_, bank_dtype, kind=z.LPF, flt_len=wl["taps"], fc1=wl["fc"], win=wl["win"], algo=fir_algo)
+                self.fir_fft = self.bank.algo == z.FIR_FFT
+            self.flop_per_out, self.bytes_per_out = 2.0 * wl["taps"], 2.0 * self.es
+            self.dtype_name = "f32" if f32 else "f64"
+            self.halo_full = wl["taps"] - 1
+        else:
+            self.tdt, self.es, self.np_dt, self.lcg_kind = torch.int16, 2, np.int16, 2
+            acc = z.ACC_F32 if f32 else z.ACC_F64
+            if world > 1:
+                self.job = z.MgpuJob.resample(mg, wl["L"], wl["M"], C_, self.mode, win=wl["win"], k_override=wl["k"], acc=acc)
+                info = z.bank_info(self.job.bank(0))
+            else:
+                self.bank = z.ResampleBank(z.KIND_RESAMPLE, wl["L"], wl["M"], C_, win=wl["win"], k_override=wl["k"], acc=acc)
+                info = self.bank.info
+            self.q = info.taps_per_phase
+            self.flop_per_out, self.bytes_per_out = 2.0 * self.q, 2.0 * (1.0 + wl["M"] / wl["L"])
+            self.dtype_name = "s16 io / f32 acc" if f32 else "s16 io / f64 acc"
+            self.fir_fft = False
+            self.halo_full = self.q - 1
+        # ---- this rank's shard ----
+        if world > 1:
+            sh = self.job.plan(n, rank)
+            self.c0, self.cc = sh.first_channel, sh.n_channels
+            self.in_start, self.in_count, self.halo = sh.seg.in_start, sh.seg.in_count, sh.seg.halo
+            self.out_start, self.out_count = sh.seg.out_start, sh.seg.out_count
+            self.total_out = self.job.out_len(n)
+        else:
+            self.c0, self.cc, self.in_start, self.in_count, self.halo, self.out_start = 0, C_, 0, n, 0, 0
+            self.out_count = self.total_out = n if self.fir else self.bank.out_len(n)
+        self.x_stride = self.halo + self.in_count
+        self.dx_all = torch.empty(self.cc, self.x_stride, dtype=self.tdt, device="cuda")
+        z.synth_lcg_at(self.dx_all, self.x_stride, self.cc, self.in_start - self.halo, self.x_stride, self.lcg_kind,
+                       wl["seed"] + self.c0, self.stream)
+        self.dy = torch.empty(self.cc, self.out_count, dtype=self.tdt, device="cuda")
+        self.outs_rank = self.cc * self.out_count
+        self.kernel, self.fft_instr_per_out, self.fft_desc = self._kernel_name()
+        # launches per step: filter kernel(s) + history kernel (+ halo copy for a time segment)
+        self.launches_per_step = (3 if self.fir_fft else 2) + (1 if self.halo else 0)
+
+    def _kernel_name(self):
+        wl, f32 = self.wl, self.dtype == "f32"
+        if not self.fir:
+            if wl["L"] == 1:
+                return "poly_slide_kernel", None, None
+            return ("poly_bank_hmma_kernel" if f32 else "poly_bank_imma_kernel"), None, None
+        t = "float" if f32 else "double"
+        if self.fir_fft and wl["taps"] >= 545:
             # 8192-point overlap-save kernel (llz_cuda_fir_fft8k.cu): one CTA of 256 threads turns 2*B outputs out of
             # 2580 FMA-pipe instructions per thread
             halo_pad = (wl["taps"] - 1 + 255) // 256 * 256
-            fft_instr_per_out = 2580.0 * 256 / (2 * (8192 - halo_pad))
-            fft_desc = "8192-point FFT per CTA"
-            kernel = f"fir_fft8k_kernel<{'float' if f32 else 'double'}>"
-        elif fir_fft:
+            return f"fir_fft8k_kernel<{t}>", 2580.0 * 256 / (2 * (8192 - halo_pad)), "8192-point FFT per CTA"
+        if self.fir_fft:
             # overlap-save kernel (llz_cuda_fir_fft.cu): one warp turns 2*B outputs out of 1928 FMA-pipe instructions per lane
             halo_pad = (wl["taps"] - 1 + 31) // 32 * 32
-            fft_instr_per_out = 1928.0 * 32 / (2 * (1024 - halo_pad))
-            fft_desc = "1024-point FFT per warp"
-            kernel = f"fir_fft_kernel<{'float' if f32 else 'double'}>"
+            return f"fir_fft_kernel<{t}>", 1928.0 * 32 / (2 * (1024 - halo_pad)), "1024-point FFT per warp"
+        return f"fir_tile_kernel<{t}>", None, None
+
+    # ---- the timed step -------------------------------------------------------------------------------
+    def step(self, gather: int = 0, chunks: int = 4):
+        z = self.z
+        if self.job is not None:
+            self.job.run(self.n_total, [self.dx_all], [self.x_stride], [self.dy], [self.out_count], self.total_out,
+                         gather, chunks, [self.stream])
+        elif self.fir:
+            self.bank.reset()
+            self.bank.run(self.dx_all, self.x_stride, self.dy, self.out_count, self.in_count, self.stream)
         else:
-            kernel = f"fir_tile_kernel<{'float' if f32 else 'double'}>"
+            self.bank.reset()
+            self.bank.run(self.dx_all, self.x_stride, self.in_count, self.dy, self.out_count, self.stream)
 
-        def step():
-            bank.reset()
-            if halo:
-                bank.set_history(dx_all, x_stride, stream)
-            bank.run(dx_all.data_ptr() + halo * es, x_stride, dy, n, n, stream)
-        # fir_tile_kernel (or fir_fft_kernel interior + edge instantiations) + fir_history_kernel
-        launches_per_step = 3 if fir_fft else 2
-    else:
-        acc = z.ACC_F32 if args.dtype == "f32" else z.ACC_F64
-        bank = z.ResampleBank(z.KIND_RESAMPLE, wl["L"], wl["M"], C_, win=wl["win"], k_override=wl["k"], acc=acc)
-        q = bank.info.taps_per_phase
-        if time_sharded:
-            seg = z.shard_resample_segments(n, wl["L"], wl["M"], q, bank.info.num_in, world, rank)
-            seg_first, halo, n = seg.in_start - seg.halo, seg.halo, seg.in_count
-        dx_all = torch.empty(C_, halo + n, dtype=torch.int16, device="cuda")
-        z.synth_lcg_at(dx_all, halo + n, C_, seg_first, halo + n, 2, wl["seed"], stream)
-        x_stride = halo + n
-        dx = dx_all[:, halo:]
-        n_out = bank.out_len(n)
-        dy = torch.empty(C_, n_out, dtype=torch.int16, device="cuda")
-        flop_per_out, bytes_per_out = 2.0 * q, 2.0 * (1.0 + wl["M"] / wl["L"])
-        dtype_name = "s16 io / f32 acc" if args.dtype == "f32" else "s16 io / f64 acc"
-        fma_peak_nominal = FP32_NOMINAL_TFLOPS if args.dtype == "f32" else FP64_NOMINAL_TFLOPS
-        fma_dtype = z.F32 if args.dtype == "f32" else z.F64
-        exact_tiles = "poly_bank_dmma_kernel" if os.environ.get("LLZ_BANK_NO_IMMA", "0") not in ("", "0") else "poly_bank_imma_kernel"
-        kernel = "poly_slide_kernel" if wl["L"] == 1 else ("poly_bank_hmma_kernel" if args.dtype == "f32" else exact_tiles)
+    def time_steps(self, steps: int, warmup: int, gather: int = 0, sample_clocks: bool = True):
+        """CUDA events on the launching stream around `steps` steps, barrier + synchronize on both sides, max over ranks"""
+        torch, D = self.torch, self.D
+        for _ in range(max(warmup, 3)):
+            self.step(gather)
+        sampler = ClockSampler(D.local) if sample_clocks else None   # NVML init happens here, outside the bracket
+        D.barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step(gather)
+        e1.record()
+        if sampler:
+            sampler.sample_now()                    # the launches above are still running: a sample under load
+        D.barrier()
+        clocks = sampler.result() if sampler else None
+        ms_local = e0.elapsed_time(e1) / steps
+        return D.max(ms_local), ms_local, clocks
 
-        def step():
-            if halo:
-                bank.set_history(dx_all, x_stride, stream)        # also rewinds the phase to output index 0
-            else:
-                bank.reset()
-            bank.run(dx_all.data_ptr() + halo * 2, x_stride, n, dy, n_out, stream)
-        launches_per_step = 2
-        fir_fft = False
-    outs_per_step = C_ * n_out
+    # ---- checks (never inside a timed region) -------------------------------------------------------------
+    def parity(self):
+        """windows of this rank's device-resident result against the oracle (reference restatement) on the same input:
+        the first outputs of the shard (where the halo / zero history matters), the last ones, and two in between"""
+        import oracle
+        P = oracle.port()
+        wl, torch = self.wl, self.torch
+        W = 4096
+        chans = sorted({0, self.cc // 2, self.cc - 1})
+        rec = {"checked_outputs": 0, "windows": 0, "max_abs_diff": 0.0, "mismatches": 0}
+        if self.fir:
+            h = P.fir_design(0, wl["taps"], wl["fc"], 0.0, wl["win"])
+            N = wl["taps"]
+            scale = max(float(np.abs(h).sum()), 1.0)
+            tol = (TOL_F32 if self.dtype == "f32" else TOL_F64) * scale
+            rec.update(tolerance=tol, tolerance_rule="max |gpu - oracle| <= %g x max(1, sum|h|) of full scale (input in [-1, 1))"
+                       % (TOL_F32 if self.dtype == "f32" else TOL_F64))
+            starts = sorted({0, self.out_count // 3, 2 * self.out_count // 3 + 17, max(0, self.out_count - W)})
+            num = den = 0.0
+            for c in chans:
+                for t0 in starts:
+                    w = min(W, self.out_count - t0)
+                    lo = self.halo + t0 - (N - 1)                      # index into dx_all of the first needed sample
+                    xs = np.zeros(w + N - 1, np.float64)
+                    a = max(lo, 0)
+                    xs[a - lo:] = self.dx_all[c, a:self.halo + t0 + w].cpu().numpy().astype(np.float64)
+                    want = P.fir_run(h, xs)[N - 1:]
+                    got = self.dy[c, t0:t0 + w].cpu().numpy().astype(np.float64)
+                    d = np.abs(got - want)
+                    rec["max_abs_diff"] = max(rec["max_abs_diff"], float(d.max()))
+                    num += float((want ** 2).sum())
+                    den += float(((got - want) ** 2).sum())
+                    rec["checked_outputs"] += w
+                    rec["windows"] += 1
+            rec["snr_db"] = float(10 * np.log10(num / den)) if den > 0 else float("inf")
+            rec["ok"] = rec["max_abs_diff"] <= tol and (self.dtype != "f32" or rec["snr_db"] >= 120.0)
+        else:
+            L_, M, Q = wl["L"], wl["M"], self.q
+            plan = P.resample_plan(L_, M, wl["win"], wl["k"])
+            pad = (Q - 1 + M - 1) // M * M
+            fast = self.dtype == "f32"
+            rec.update(tolerance=1 if fast else 0, tolerance_rule="|diff| <= 1 LSB (fast mode)" if fast else "bit-exact int16")
+            cyc = self.out_count // L_
+            for c in chans:
+                for j0 in sorted({0, cyc // 3, 2 * cyc // 3 + 5, max(0, cyc - W // L_ - 1)}):
+                    o0 = j0 * L_
+                    w = min(W, self.out_count - o0)
+                    p0 = self.halo + j0 * M                              # dx_all index of the sample the window's phase 0 reads
+                    need = (w * M) // L_ + 2
+                    xs = np.zeros(pad + need, np.int16)
+                    a = max(p0 - pad, 0)
+                    b = min(p0 + need, self.x_stride)
+                    xs[a - (p0 - pad):b - (p0 - pad)] = self.dx_all[c, a:b].cpu().numpy()
+                    want = P.resample_run(plan, 1.0, xs, w, m0=pad // M * L_)
+                    got = self.dy[c, o0:o0 + w].cpu().numpy()
+                    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+                    rec["max_abs_diff"] = max(rec["max_abs_diff"], float(d.max()))
+                    rec["mismatches"] += int((d != 0).sum())
+                    rec["checked_outputs"] += w
+                    rec["windows"] += 1
+            rec["ok"] = rec["max_abs_diff"] <= (1 if fast else 0)
+        rec["channels_checked"] = [self.c0 + c for c in chans]
+        rec["against"] = "oracle/llz_oracle.c (restatement pinned to the compiled reference, tests/test_oracle.py)"
+        return rec
 
+    def one_gpu_identity(self):
+        """N > 1: this rank recomputes its channels from sample 0 to the end of its segment the way the one-GPU call does
+        (zero history, no segment boundary) and compares its shard with that, byte for byte"""
+        z, torch, wl = self.z, self.torch, self.wl
+        if self.D.world == 1:
+            return None
+        end_in = self.in_start + self.in_count
+        need = self.cc * end_in * self.es * (2 if self.fir else 1.0 + wl["L"] / wl["M"])
+        free, _ = torch.cuda.mem_get_info()
+        if need > 0.9 * free:
+            return {"skipped": f"needs {need / 1e9:.1f} GB on this rank"}
+        x = torch.empty(self.cc, end_in, dtype=self.tdt, device="cuda")
+        z.synth_lcg_at(x, end_in, self.cc, 0, end_in, self.lcg_kind, wl["seed"] + self.c0, self.stream)
+        if self.fir:
+            one = z.FirBank(self.cc, z.F32 if self.dtype == "f32" else z.F64, kind=z.LPF, flt_len=wl["taps"], fc1=wl["fc"], win=wl["win"])
+            z._check(z.lib().llz_cuda_fir_bank_set_algo(one.handle, z.lib().llz_cuda_fir_bank_get_algo(self.bank_handle)), "set_algo")
+            y = torch.empty(self.cc, end_in, dtype=self.tdt, device="cuda")
+            one.run(x, end_in, y, end_in, end_in, self.stream)
+            n_out = end_in
+        else:
+            one = z.ResampleBank(z.KIND_RESAMPLE, wl["L"], wl["M"], self.cc, win=wl["win"], k_override=wl["k"],
+                                 acc=z.ACC_F32 if self.dtype == "f32" else z.ACC_F64)
+            n_out = one.out_len(end_in)
+            y = torch.empty(self.cc, n_out, dtype=self.tdt, device="cuda")
+            one.run(x, end_in, end_in, y, n_out, self.stream)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(y[:, self.out_start:self.out_start + self.out_count], self.dy))
+        one.close()
+        del x, y
+        return {"bit_identical": same, "compared_outputs": self.outs_rank,
+                "against": "the one-GPU call over [0, end of this rank's segment) of the same channels"}
+
+    def close(self):
+        if self.job is not None:
+            self.job.close()
+        if self.bank is not None:
+            self.bank.close()
+        self.dx_all = self.dy = None
+        self.torch.cuda.empty_cache()
+
+
+TOL_F64, TOL_F32 = 1e-12, 1e-5
+
+
+def measure(z, D: Dist, mg, name: str, dtype: str, algo: str, steps: int, warmup: int, args, headline: bool):
+    """one workload -> the record that goes into the JSON line (headline) or under "workloads" """
+    torch = D.torch
+    W = Workload(z, D, name, dtype, algo, mg)
+    wl = W.wl
+    hbm_peak, peak_src = peaks()
+    fma_dtype = z.F32 if dtype == "f32" else z.F64
+    fma_peak_nominal = FP32_NOMINAL_TFLOPS if dtype == "f32" else FP64_NOMINAL_TFLOPS
     fma_peak_measured = z.probe_fma(fma_dtype)
 
-    # ---- device-timed region ----
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sampler = ClockSampler(local)                   # NVML init happens here, outside the bracket
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    sampler.sample_now()                            # the launches above are still running: a sample under load
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = sampler.result()
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    outs_all = outs_per_step
-    if world > 1:
-        t = torch.tensor([float(outs_per_step)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        outs_all = int(t.item())
+    ms_step, ms_local, clocks = W.time_steps(steps, warmup, z.GATHER_NONE)
+    outs_all = int(D.sum(float(W.outs_rank)))
     value = outs_all / (ms_step * 1e-3) / 1e6
+    ach_gbs = W.outs_rank * W.bytes_per_out / (ms_local * 1e-3) / 1e9
+    ach_tf = W.outs_rank * W.flop_per_out / (ms_local * 1e-3) / 1e12
 
-    # per-rank kernel figures (rank 0's own time for the roofline of the kernel)
-    ms_local = e0.elapsed_time(e1) / args.steps
-    ach_gbs = outs_per_step * bytes_per_out / (ms_local * 1e-3) / 1e9
-    ach_tf = outs_per_step * flop_per_out / (ms_local * 1e-3) / 1e12
+    parity = W.parity()
+    parity_all = D.gather_obj(parity)
+    identity = D.gather_obj(W.one_gpu_identity()) if D.world > 1 else None
 
-    # ---- optional exchange step: every rank's output to every rank with NCCL over NVLink ----
-    # The path itself needs no collective (independent channels / segments that carry their own halo); a job that
-    # wants the whole result on one device adds this gather.  It is reported separately, never inside the timed step.
+    # ---- N > 1: the same step with the result gathered on rank 0, two ways (library gather modes) ----
     gather = None
-    if world > 1 and not args.no_gather:
+    if D.world > 1 and not args.no_gather:
+        gather = {"note": "whole planar result on rank 0's device; compute_only is the timed step above (no collective: "
+                          "shards carry their halo)", "compute_only_ms": ms_step,
+                  "result_bytes": W.C_total * W.total_out * W.es, "root_ingress_bytes": (W.C_total * W.total_out - (W.outs_rank if D.rank == 0 else 0)) * W.es}
         try:
-            cnt = torch.tensor([dy.numel()], device="cuda", dtype=torch.int64)
-            dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
-            m = int(cnt.item())                                      # time segments may differ by one work item
-            es_out = dy.element_size()
-            if world * m * es_out > 48e9:
-                gather = {"skipped": f"gathered result would be {world * m * es_out / 1e9:.1f} GB per rank"}
-            else:
-                flat = dy.reshape(-1)
-                if flat.numel() < m:
-                    flat = torch.cat([flat, flat.new_zeros(m - flat.numel())])
-                full = torch.empty(world * m, dtype=dy.dtype, device="cuda")
-                dist.all_gather_into_tensor(full, flat)              # warm-up: communicator channels, buffers
-                torch.cuda.synchronize()
-                dist.barrier()
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record()
-                dist.all_gather_into_tensor(full, flat)
-                g1.record()
-                torch.cuda.synchronize()
-                t = torch.tensor([g0.elapsed_time(g1)], device="cuda", dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                gms = float(t.item())
-                own_ok = bool(torch.equal(full[rank * m: rank * m + dy.numel()], dy.reshape(-1)))
-                gather = {"collective": "NCCL all-gather of the planar outputs (torch.distributed.all_gather_into_tensor)",
-                          "ms": gms, "bytes_per_rank": m * es_out, "gathered_bytes": world * m * es_out,
-                          "algbw_gbs": world * m * es_out / (gms * 1e-3) / 1e9,
-                          "busbw_gbs": (world - 1) * m * es_out / (gms * 1e-3) / 1e9,
-                          "own_slice_intact": own_ok, "compute_ms_per_step": ms_step,
-                          "note": "not part of the timed step; the filter itself needs no collective; shards land rank-major"}
-                del full
+            mg.result_alloc(0, W.C_total * W.total_out * W.es)
+            own = checksum64(W.dy)
+            for mode, key in ((z.GATHER_NCCL, "nccl_chunked_send_recv"), (z.GATHER_PEER, "peer_store_fused")):
+                try:
+                    gms, _, _ = W.time_steps(max(3, min(steps, 10)), 2, mode, sample_clocks=False)
+                    # every rank's region of the gathered result against that rank's own shard
+                    sums = D.gather_obj((W.c0, W.cc, W.out_start, W.out_count, own))
+                    ok = None
+                    if D.rank == 0:
+                        import ctypes
+                        full = torch.empty(W.C_total, W.total_out, dtype=W.tdt, device="cuda")
+                        rt = ctypes.CDLL("libcudart.so.12")
+                        rt.cudaMemcpy(ctypes.c_void_p(full.data_ptr()), ctypes.c_void_p(mg.result_ptr(0)),
+                                      ctypes.c_size_t(full.numel() * W.es), 3)
+                        torch.cuda.synchronize()
+                        ok = [checksum64(full[c0:c0 + cc, o0:o0 + oc]) == cs for c0, cc, o0, oc, cs in sums]
+                        del full
+                    ingress = gather["root_ingress_bytes"] if D.rank == 0 else 0
+                    ingress = D.max(float(ingress))
+                    floor_ms = max(ms_step, ingress / 900e9 * 1e3)
+                    gather[key] = {"compute_plus_gather_ms": gms, "floor_ms": floor_ms, "over_floor": gms / floor_ms,
+                                   "root_ingress_gbs": ingress / (gms * 1e-3) / 1e9,
+                                   "regions_match_each_ranks_shard": ok}
+                except Exception as ex:             # noqa: BLE001
+                    gather[key] = {"error": repr(ex)}
+                    D.barrier()
+            gather["floor_rule"] = "max(compute-only step, bytes into rank 0 / 900 GB/s NVLink ingress)"
+            D.barrier()
+            mg.result_free()
         except Exception as ex:                     # noqa: BLE001
-            gather = {"error": repr(ex)}
+            gather["error"] = repr(ex)
 
-    # ---- end to end through the C-ABI with host buffers ----
+    # ---- end to end through the C-ABI with host buffers (this rank's shard through *_run_host) ----
     e2e = None
+    if headline or args.e2e_all:
+        e2e = end_to_end(z, D, W, outs_all, min(steps, 5), args)
+
+    rec_rank0 = None
+    if D.rank == 0:
+        if W.fir_fft:
+            ginstr = W.outs_rank * W.fft_instr_per_out / (ms_local * 1e-3) / 1e12
+            fma_pipe = {"achieved": ginstr, "unit": "T lane-instr/s", "instr_per_output": W.fft_instr_per_out,
+                        "peak_measured": fma_peak_measured / 2 if fma_peak_measured else None,
+                        "peak_nominal": fma_peak_nominal / 2,
+                        "frac_of_measured": ginstr / (fma_peak_measured / 2) if fma_peak_measured else None,
+                        "frac_of_nominal": ginstr / (fma_peak_nominal / 2),
+                        "direct_form_equivalent_tflops": ach_tf,
+                        "note": f"overlap-save ({W.fft_desc}, arithmetic in the bank's type): "
+                                f"{W.fft_instr_per_out:.1f} FMA-pipe instructions per output instead of {wl['taps']} FMAs"}
+        else:
+            fma_pipe = {"achieved": ach_tf, "unit": "TFLOP/s", "peak_measured": fma_peak_measured,
+                        "peak_nominal": fma_peak_nominal,
+                        "frac_of_measured": ach_tf / fma_peak_measured if fma_peak_measured else None,
+                        "frac_of_nominal": ach_tf / fma_peak_nominal,
+                        "note": f"algorithmic flops ({W.flop_per_out:.0f} per output) against the FMA pipe of the accumulator type"}
+            if W.kernel == "poly_bank_imma_kernel":
+                fma_pipe["note"] += ("; the kernel evaluates the sums exactly on the INT8 tensor cores (ten IMMA digit products per "
+                                     "multiply-add), so the fraction is its speed relative to the FP64 roof it no longer uses")
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(f"{name}_{dtype}")
+        time_sharded = D.world > 1 and W.mode == z.SHARD_TIME
+        rec_rank0 = {
+            "value": value, "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "dtype": W.dtype_name,
+            "scaling": "strong" if D.world > 1 else "weak",
+            "config": {"workload": wl["desc"], "name": name, "channels": W.C_total, "samples_per_channel": W.n_total,
+                       "outputs_per_step": outs_all, "outputs_per_step_this_rank": W.outs_rank,
+                       "sharding": ("whole job on one GPU" if D.world == 1 else
+                                    ("%d time segments (llz_cuda_mgpu_*), each rank reads a %d-sample halo before its segment, no collective"
+                                     % (D.world, W.halo_full)) if time_sharded else
+                                    "%d channel shards of %d channels (llz_cuda_mgpu_*), no collective" % (D.world, W.cc)),
+                       "l2": f"inputs {W.dx_all.numel() * W.es / 1e9:.2f} GB per GPU vs 126 MB L2"
+                             + ("" if W.dx_all.numel() * W.es > 4 * 126e6 else "; outputs + inputs of consecutive steps still exceed L2" if (W.dx_all.numel() + W.dy.numel()) * W.es > 2 * 126e6 else " (fits: strong-scaled shard)"),
+                       "input": "integer LCG noise generated on the device (SURVEY.md 8d)",
+                       **({"fir_algo": f"overlap-save, {W.fft_desc}" if W.fir_fft else "direct form"} if W.fir else {})},
+            "roofline": {"kernel": W.kernel, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gbs / hbm_peak, "traffic": traffic if D.world == 1 else None, "peak_source": peak_src,
+                         "algorithmic": {"bytes_per_output": W.bytes_per_out, "flop_per_output": W.flop_per_out,
+                                         "outputs_per_launch": W.outs_rank},
+                         "fma_pipe": fma_pipe},
+            "parity": parity_all[0] if D.world == 1 else {"ok": all(p["ok"] for p in parity_all), "per_rank": parity_all},
+            "gpu_launches": W.launches_per_step * steps, "clocks": clocks,
+        }
+        if identity is not None:
+            rec_rank0["one_gpu_identity"] = {"per_rank": identity,
+                                             "bit_identical": all(bool(i and i.get("bit_identical")) for i in identity)}
+        if gather is not None:
+            rec_rank0["gather"] = gather
+        if e2e is not None:
+            rec_rank0["e2e"] = e2e
+    W.close()
+    return rec_rank0
+
+
+def end_to_end(z, D: Dist, W: Workload, outs_all: int, e_steps: int, args):
+    """the same pass through llz_cuda_*_bank_run_host with page-locked HOST buffers: H2D, kernels and D2H of every chunk
+    inside the timed region (host wall clock around synchronous calls), this rank's shard"""
+    torch = D.torch
     try:
         if args.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
-        in_bytes, out_bytes = dx.numel() * dx.element_size(), dy.numel() * dy.element_size()
-        np_dt = {torch.float64: np.float64, torch.float32: np.float32, torch.int16: np.int16}[dx.dtype]
-        hx = z.host_alloc(in_bytes, np_dt).reshape(C_, n)
-        hy = z.host_alloc(out_bytes, np_dt).reshape(C_, n_out)
-        torch.from_numpy(hx).copy_(dx)                # this rank's own samples (the halo stays in the bank's history)
+        n, n_out, cc = W.in_count, W.out_count, W.cc
+        in_bytes, out_bytes = cc * n * W.es, cc * n_out * W.es
+        hx = z.host_alloc(in_bytes, W.np_dt).reshape(cc, n)
+        hy = z.host_alloc(out_bytes, W.np_dt).reshape(cc, n_out)
+        torch.from_numpy(hx).copy_(W.dx_all[:, W.halo:])       # this rank's own samples (the halo goes into the bank's history)
         torch.cuda.synchronize()
-        e_steps = max(1, min(args.steps, 5))
+        if W.job is not None:
+            handle = W.job.bank(0)
+            bank = (z.FirBank if W.fir else z.ResampleBank).__new__(z.FirBank if W.fir else z.ResampleBank)
+            bank.handle = handle
+        else:
+            bank = W.bank
 
         def e2e_step():
-            if halo:
-                bank.set_history(dx_all, x_stride, stream)
+            if W.halo:
+                bank.set_history(W.dx_all, W.x_stride, W.stream)
                 torch.cuda.synchronize()
             else:
                 bank.reset()
-            if wl["kind"] == "fir":
-                bank.run_host(hx, n, hy, n, n)
+            if W.fir:
+                bank.run_host(hx, n, hy, n_out, n)
             else:
                 bank.run_host(hx, n, n, hy, n_out)
         e2e_step()                                  # warm-up: staging buffers, streams
-        if world > 1:
-            dist.barrier()
+        D.barrier()
         t0 = time.perf_counter()
         for _ in range(e_steps):
             e2e_step()                              # synchronous: result is in hy on return
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        # the result read back is the full output; verify it is the device-resident result
-        dev = dy[0, :4096].cpu().numpy()
-        same = bool(np.array_equal(hy[0, :4096], dev))
+        dt = D.max(time.perf_counter() - t0)
+        # the result read back is the full output of the shard; compare a window with the device-resident result
+        dev = W.dy[0, :4096].cpu().numpy()
         max_diff = float(np.abs(hy[0, :4096].astype(np.float64) - dev.astype(np.float64)).max())
-        e2e = {"value": outs_all * e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-               "d2h_bytes_per_step": out_bytes, "steps": e_steps, "matches_device_result": same,
+        e2e = {"value": outs_all * e_steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(D.sum(float(in_bytes))), "d2h_bytes_per_step": int(D.sum(float(out_bytes))),
+               "steps": e_steps, "matches_device_result": bool(np.array_equal(hy[0, :4096], dev)),
                "max_abs_diff_vs_device": max_diff,
-               "api": "llz_cuda_fir_bank_run_host" if wl["kind"] == "fir" else "llz_cuda_resample_bank_run_host",
+               "gbs_per_direction_all_gpus": D.sum(float(in_bytes)) * e_steps / dt / 1e9,
+               "api": "llz_cuda_fir_bank_run_host" if W.fir else "llz_cuda_resample_bank_run_host",
                "host_memory": "page-locked (llz_cuda_host_alloc)"}
+        if W.job is not None:
+            bank.handle = 0
         z.host_free(hx.reshape(-1))
         z.host_free(hy.reshape(-1))
+        return e2e
     except Exception as ex:                         # noqa: BLE001
-        e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
+        return {"value": None, "unit": UNIT, "error": repr(ex)}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+
+def run_cuda(args):
+    import torch
+    import llzlab_b200 as z
+
+    D = Dist()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libllzfilter_cuda has no CPU path (use --impl reference for the CPU arm)")
+    bind_to_gpu_numa_node(D.local)
+    torch.cuda.set_device(D.local)
+    D.init()
+    z.lib()
+    mg = None
+    if D.world > 1:
+        # the library's multi-GPU context, one rank per process: rank 0's NCCL id travels through torch.distributed
+        ids = [z.mgpu_unique_id() if D.rank == 0 else None]
+        D.dist.broadcast_object_list(ids, src=0)
+        mg = z.Mgpu(unique_id=ids[0], world=D.world, rank=D.rank)
+
+    head_name = args.workload or "c2"
+    head = measure(z, D, mg, head_name, args.dtype, args.algo, args.steps, args.warmup, args, headline=True)
+
+    # ---- every other BASELINE config, same run (device-timed, parity-checked; fewer steps) ----
+    others = {}
+    if args.workload is None and not args.headline_only:
+        for name, dtype in (("c2", "f32"), ("c3", "f64"), ("c3", "f32"), ("c4", "f64"), ("c4", "f32"), ("c5", "f64"), ("c5", "f32")):
+            key = f"{name}_{'f32' if dtype == 'f32' else ('f64' if WORKLOADS[name]['kind'] == 'fir' else 'exact')}"
+            try:
+                rec = measure(z, D, mg, name, dtype, "auto", max(3, min(args.steps, 5)), 3, args, headline=False)
+            except Exception as ex:                 # noqa: BLE001
+                rec = {"error": repr(ex)}
+                D.barrier()
+            if D.rank == 0:
+                others[key] = rec
+
+    if D.rank != 0:
+        if mg is not None:
+            mg.close()
+        if D.world > 1:
+            D.dist.destroy_process_group()
         return 0
 
     # ---- CPU baseline: the unmodified reference, one thread, bounded sample ----
+    wl = WORKLOADS[head_name]
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if D.world == 1 and not args.no_cpu:
         if wl["kind"] == "fir":
             n_cpu = 480_000 if wl["taps"] < 1000 else 40_960
             ch_cpu = max(1, int(1.0e8 * 127 / wl["taps"] / n_cpu))      # ~12 s at the probed 8.4 Msamples/s
@@ -470,62 +751,23 @@ def run_cuda(args):
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
                "sample": f"{ch_cpu} channel(s) x {n_cpu} input samples of the workload, frame by frame through the reference API, 1 thread (the reference is single-threaded); host has {os.cpu_count()} logical cores"}
 
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get(f"{args.workload}_{args.dtype}")
-
-    if fir_fft:
-        # FMA-pipe instructions (DFMA/DADD/DMUL or FFMA/FADD/FMUL, one lane) the kernel executes, against the measured
-        # FMA issue rate (probe TFLOP/s / 2 flop per FMA)
-        ginstr = outs_per_step * fft_instr_per_out / (ms_local * 1e-3) / 1e12
-        fma_pipe = {"achieved": ginstr, "unit": "T lane-instr/s", "instr_per_output": fft_instr_per_out,
-                    "peak_measured": fma_peak_measured / 2 if fma_peak_measured else None,
-                    "peak_nominal": fma_peak_nominal / 2,
-                    "frac_of_measured": ginstr / (fma_peak_measured / 2) if fma_peak_measured else None,
-                    "frac_of_nominal": ginstr / (fma_peak_nominal / 2),
-                    "direct_form_equivalent_tflops": ach_tf,
-                    "note": f"overlap-save ({fft_desc}, arithmetic in the bank's type): "
-                            f"{fft_instr_per_out:.1f} FMA-pipe instructions per output instead of {wl['taps']} FMAs; "
-                            "the FMA pipe and the shared-memory/LSU pipe are co-limiters below the HBM roof (DESIGN.md 4.1b)"}
-    else:
-        fma_pipe = {"achieved": ach_tf, "unit": "TFLOP/s", "peak_measured": fma_peak_measured,
-                    "peak_nominal": fma_peak_nominal,
-                    "frac_of_measured": ach_tf / fma_peak_measured if fma_peak_measured else None,
-                    "frac_of_nominal": ach_tf / fma_peak_nominal,
-                    "note": "direct-form FIR on CUDA cores: the FMA pipe, not HBM, is the binding roof "
-                            f"(ceiling of the HBM fraction = {fma_peak_nominal * 1e12 / flop_per_out * bytes_per_out / 1e9 / hbm_peak:.3f})"}
-        if kernel == "poly_bank_imma_kernel":
-            fma_pipe["note"] = ("exact integer evaluation on the INT8 tensor cores (ten IMMA digit products per multiply-add, "
-                                "1144 TOP/s measured = 114 TFLOP/s of exact multiply-adds): the fraction above is against the "
-                                "FP64 FMA pipe this kernel no longer uses, i.e. the speed relative to the FP64 roof")
-            fma_pipe["frac_of_imma_roof"] = ach_tf / 114.4
-
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": dtype_name, "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload, "channels_per_gpu": C_, "samples_per_channel": n,
-                   "outputs_per_step_per_gpu": outs_per_step,
-                   "sharding": ("time segments, each rank reads a %d-sample halo before its segment, no collective"
-                                % (wl["taps"] - 1 if wl["kind"] == "fir" else q - 1)) if time_sharded
-                   else "independent channels per rank, no collective",
-                   "l2": f"inputs {dx.numel() * dx.element_size() / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
-                   "input": "integer LCG noise generated on the device (SURVEY.md 8d)",
-                   **({"fir_algo": f"overlap-save, {fft_desc}" if fir_fft else "direct form"} if wl["kind"] == "fir" else {})},
-        "roofline": {"kernel": kernel, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ach_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic": {"bytes_per_output": bytes_per_out, "flop_per_output": flop_per_out,
-                                     "outputs_per_launch": outs_per_step},
-                     "fma_pipe": fma_pipe},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None,
+        "dtype": head["dtype"], "data": "synthetic", "config": head["config"], "roofline": head["roofline"],
+        "cpu_baseline": cpu, "e2e": head.get("e2e"), "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+        "parity": head["parity"],
     }
-    if gather is not None:
-        line["gather"] = gather
+    for k in ("one_gpu_identity", "gather"):
+        if k in head:
+            line[k] = head[k]
+    if others:
+        line["workloads"] = others
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if mg is not None:
+        mg.close()
+    if D.world > 1:
+        D.dist.destroy_process_group()
     return 0
 
 
@@ -580,12 +822,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1"] + sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=["c1"] + sorted(WORKLOADS),
+                    help="run ONE config as the headline; default: C2 as the headline and every other config under 'workloads'")
+    ap.add_argument("--headline-only", action="store_true", help="default run without the other configs")
+    ap.add_argument("--e2e-all", action="store_true", help="host-buffer end-to-end leg for the non-headline configs too")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--algo", default="auto", choices=["auto", "direct", "fft"],
                     help="FIR kernel family (c2/c5): auto = overlap-save where it applies, else direct form")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL all-gather of the outputs at N > 1")
+    ap.add_argument("--no-gather", action="store_true", help="skip the compute+gather measurements at N > 1")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.workload == "c1":
