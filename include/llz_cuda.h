@@ -44,7 +44,8 @@ const char *llz_cuda_build_info(void);      /* "libllzfilter_cuda <ver> sm_100a 
 /* Measurement knobs (process-wide; not for production code paths).  The environment is read once, when the first
  * handle is created; this call overrides a value afterwards.  Keys: "pipe_slot_mib" (staging-slot size of the
  * *_run_host pipelines, default 64), "slide_ru" (force a tile variant of the decimating kernel: 11, 7, 5, 3; 0 = auto),
- * "fft8k_skew" / "fft16k_skew" (cycles, < 0 = measured default), "fir_algo" (default family of AUTO banks: 0, 1, 2). */
+ * "fft8k_skew" / "fft16k_skew" (cycles, < 0 = measured default), "fir_algo" (default family of AUTO banks: 0, 1, 2),
+ * "umma_slab_mib" (expanded-row workspace per slab of the tcgen05 phase-bank kernel). */
 int         llz_cuda_tune(const char *key, double value);
 /* page-locked host memory for the *_run_host pipelines (pageable buffers work, but slower) */
 void       *llz_cuda_host_alloc(size_t bytes);
@@ -72,10 +73,13 @@ enum {                                      /* FIR kernel family (tolerance-mode
                                      not bit-identical                                                      */
 };
 enum {                                      /* tile family of the phase-bank kernels (L >= 16); all give the same bytes */
-    LLZ_CUDA_TILES_AUTO        = 0, /* exact mode: INT8 tensor cores; fast mode: FP16 tensor cores (default)  */
-    LLZ_CUDA_TILES_INT8        = 1, /* exact mode: integer evaluation + two-level guard                       */
+    LLZ_CUDA_TILES_AUTO        = 0, /* exact mode: INT8 tensor cores (tcgen05 for large calls, mma.sync for
+                                       frame-sized ones); fast mode: FP16 tensor cores (default)              */
+    LLZ_CUDA_TILES_INT8        = 1, /* exact mode: integer evaluation on mma.sync IMMA + two-level guard      */
     LLZ_CUDA_TILES_FP64_TENSOR = 2, /* exact mode: DMMA tiles + guard                                         */
     LLZ_CUDA_TILES_CUDA_CORE   = 3, /* DFMA / FFMA register tiles                                             */
+    LLZ_CUDA_TILES_INT8_TCGEN05 = 4, /* exact mode: integer evaluation on tcgen05.mma.kind::i8, accumulators in
+                                        TMEM, whatever the size of the call                                   */
 };
 enum {                                      /* resampler accumulator */
     LLZ_CUDA_ACC_F64        = 0,  /* FP64 FMA + near-integer guard -> bit-identical int16 (default) */

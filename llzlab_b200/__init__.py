@@ -27,7 +27,7 @@ LPF, HPF, BPF, BSF = 0, 1, 2, 3
 F64, F64_STRICT, F32 = 0, 1, 2
 FIR_AUTO, FIR_DIRECT, FIR_FFT = 0, 1, 2
 ACC_F64, ACC_F64_STRICT, ACC_F32 = 0, 1, 2
-TILES_AUTO, TILES_INT8, TILES_FP64_TENSOR, TILES_CUDA_CORE = 0, 1, 2, 3
+TILES_AUTO, TILES_INT8, TILES_FP64_TENSOR, TILES_CUDA_CORE, TILES_INT8_TCGEN05 = 0, 1, 2, 3, 4
 SHARD_CHANNEL, SHARD_TIME = 0, 1
 GATHER_NONE, GATHER_NCCL, GATHER_PEER = 0, 1, 2
 KIND_DECIMATE, KIND_INTERP, KIND_RESAMPLE = 0, 1, 2

@@ -57,6 +57,12 @@ struct PolyLaunch {
     int imma_planes;           // 5 digit planes
     double imma_scale;
     double imma_thr;           // guard band: guard_thr + |gain| * (tap rounding bound)
+    // tcgen05 exact mode (llz_cuda_polybank_umma.cu): the same digit planes in the K-major SWIZZLE_128B layout of
+    // llz_umma_tables.h, and the workspace of the call's expanded input rows; nullptr = not selected for this call
+    const signed char *umma_tiles;
+    int umma_nchunks;          // chunks of 128 k bytes per phase tile
+    unsigned char *umma_rows;  // workspace: poly_bank_umma_rows_bytes(a, channels, umma_slab_cycles) bytes
+    int umma_slab_cycles;      // cycles per slab (multiple of 128)
 };
 
 // picks the kernel (sliding for L == 1 when the tile fits, general otherwise) and launches it
@@ -65,6 +71,10 @@ int poly_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
 // exact mode on the integer tensor cores (llz_cuda_polybank_imma.cu): same return convention
 int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
+// exact mode on tcgen05 / TMEM (llz_cuda_polybank_umma.cu): same return convention; the workspace must hold
+// poly_bank_umma_rows_bytes(a, n_channels, a.umma_slab_cycles) bytes
+int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream);
+size_t poly_bank_umma_rows_bytes(const PolyLaunch &a, int n_channels, long long cycles);
 // name of the kernel poly_launch would pick ("sliding" / "general"), for reporting
 const char *poly_kernel_name(const PolyLaunch &a);
 

@@ -25,6 +25,7 @@
 #include "llz_fir_kernels.h"
 #include "llz_imma_tables.h"
 #include "llz_poly_kernels.h"
+#include "llz_umma_tables.h"
 
 namespace {
 
@@ -480,6 +481,10 @@ struct PolyBank {
     float *d_cbankT32 = nullptr, *d_cbankT32_base = nullptr, *d_slide32 = nullptr;
     uint16_t *d_cbankT16h = nullptr, *d_cbankT16l = nullptr, *d_cbankT16h_base = nullptr, *d_cbankT16l_base = nullptr;
     int bank16_exp = 0;
+    signed char *d_umma_tiles = nullptr;   // the same digit planes in the tcgen05 kernel's layout (llz_cuda_polybank_umma.cu)
+    int umma_nchunks = 0;
+    unsigned char *d_umma_rows = nullptr;  // workspace: expanded input rows of one slab
+    size_t umma_rows_cap = 0;
     signed char *d_imma_tiles = nullptr;   // int8 digit planes of the bank (llz_cuda_polybank_imma.cu)
     int imma_nchunks = 0, imma_shift = 0, imma_planes = 0;
     double imma_eps = 0.0;                 // bound on the tap-rounding error of a full-scale dot product
@@ -526,6 +531,8 @@ void poly_destroy(PolyBank *b)
     cudaFree(b->d_cbankT32_base); cudaFree(b->d_slide32);
     cudaFree(b->d_cbankT16h_base); cudaFree(b->d_cbankT16l_base);
     cudaFree(b->d_imma_tiles);
+    cudaFree(b->d_umma_tiles);
+    cudaFree(b->d_umma_rows);
     cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     if (b->pinned_in) cudaFreeHost(b->pinned_in);
@@ -597,6 +604,13 @@ int poly_upload_plan(PolyBank *b)
         b->imma_planes = 5;
         b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->imma_planes, &tiles, &b->imma_shift, &b->imma_eps);
         if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
+        // the same digits for tcgen05.mma.kind::i8 (same scale 2^-s and rounding bound: both builders round g * 2^38)
+        std::vector<signed char> utiles;
+        int ushift = 0;
+        double ueps = 0.0;
+        b->umma_nchunks = llz::poly_umma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, &utiles, &ushift, &ueps);
+        if (b->umma_nchunks > 0 && (ushift != b->imma_shift || b->imma_nchunks <= 0)) b->umma_nchunks = 0;
+        if (b->umma_nchunks > 0 && upload(&b->d_umma_tiles, utiles)) return -1;
     }
     std::vector<int> order(p.order, p.order + Q), single(L);
     for (size_t r = 0; r < L; ++r) single[r] = p.single_tap[r % L0];
@@ -744,6 +758,33 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
     a.imma_scale = ldexp(1.0, -b->imma_shift);
     // first-level band of the integer evaluation: the (scaled) FP64 band plus the taps' rounding bound
     a.imma_thr = b->guard_thr * b->guard_scale + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
+    // tcgen05 exact mode for calls that fill the machine (a frame-sized call keeps the mma.sync tiles: no pre-pass,
+    // no workspace, lower latency); LLZ_CUDA_TILES_INT8_TCGEN05 forces it
+    if (b->d_umma_tiles && outs > 0 && (b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
+        const long long cycles = (a.o0 + outs - 1) / a.L - a.o0 / a.L + 1;
+        const long long n_tiles = (cycles + llz::kUJB - 1) / llz::kUJB * ((a.L + llz::kUPB - 1) / llz::kUPB) * cc;
+        const int sms = device_sm_count();
+        if (sms <= 0) return -1;
+        if (b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05 || n_tiles >= 4LL * sms) {
+            const size_t per_cycle = poly_bank_umma_rows_bytes(a, cc, 1);
+            long long slab = (long long)(tunables().umma_slab_mib * 1024 * 1024 / (double)per_cycle) / llz::kUJB * llz::kUJB;
+            if (slab < llz::kUJB) slab = llz::kUJB;
+            if (slab > cycles) slab = (cycles + llz::kUJB - 1) / llz::kUJB * llz::kUJB;
+            const size_t need = per_cycle * (size_t)slab;
+            if (need > b->umma_rows_cap) {
+                LLZ_CUDA_TRY(cudaDeviceSynchronize());                 // an earlier call may still read the old workspace
+                cudaFree(b->d_umma_rows);
+                b->d_umma_rows = nullptr;
+                b->umma_rows_cap = 0;
+                LLZ_CUDA_TRY(cudaMalloc(&b->d_umma_rows, need));
+                b->umma_rows_cap = need;
+            }
+            a.umma_tiles = b->d_umma_tiles;
+            a.umma_nchunks = b->umma_nchunks;
+            a.umma_rows = b->d_umma_rows;
+            a.umma_slab_cycles = (int)slab;
+        }
+    }
     if (poly_launch(a, cc, st) != 0) return -1;
     if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
         b->chain_src = d_in + (n_in - p.hist_len);
@@ -1251,7 +1292,7 @@ extern "C" int llz_cuda_resample_bank_set_tiles(unsigned long handle, int tiles)
 {
     PolyBank *b = as_poly(handle);
     if (!b) return -1;
-    if (tiles < LLZ_CUDA_TILES_AUTO || tiles > LLZ_CUDA_TILES_CUDA_CORE) { llz_set_error("unknown tile family %d", tiles); return -1; }
+    if (tiles < LLZ_CUDA_TILES_AUTO || tiles > LLZ_CUDA_TILES_INT8_TCGEN05) { llz_set_error("unknown tile family %d", tiles); return -1; }
     b->tiles = tiles;
     return 0;
 }

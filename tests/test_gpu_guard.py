@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 # (kind, L, M, k_override, tiles, kernel the call lands on)
 CASES = [
     ("resample", 160, 147, 0, 1, "poly_bank_imma_kernel: second look -> third level"),
+    ("resample", 160, 147, 0, 4, "poly_bank_umma_kernel (tcgen05): second look -> third level"),
     ("resample", 160, 147, 0, 2, "poly_bank_dmma_kernel"),
     ("resample", 160, 147, 0, 3, "poly_bank_kernel (DFMA register tile)"),
     ("resample", 320, 147, 128, 1, "poly_bank_imma_kernel, Q = 257"),
@@ -94,7 +95,7 @@ def test_widened_guard_band_interp_general_kernel(zlib, port, cuda):
     bank.close()
 
 
-@pytest.mark.parametrize("kind,L_,M,k,tiles,what", CASES[:5] + CASES[6:8])
+@pytest.mark.parametrize("kind,L_,M,k,tiles,what", CASES[:6] + CASES[7:9])
 def test_adversarial_near_integer_sums_with_the_production_band(zlib, port, cuda, kind, L_, M, k, tiles, what):
     """16 outputs per channel tuned to within a few ulps of a non-zero integer, half of them at or just above it and half
     just below: the fast evaluation may land on either side, the guard has to send every one of them to the

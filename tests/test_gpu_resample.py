@@ -261,12 +261,13 @@ def test_c3_shape_spot_checks(zlib, port, cuda):
     bank.close()
 
 
-@pytest.mark.parametrize("tiles", [1, 2, 3])
+@pytest.mark.parametrize("tiles", [1, 2, 3, 4])
 @pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0)])
 def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, L_, M, k, tiles):
-    """The exact mode's three tile kernels: INT8 tensor cores (default: taps as five int8 digit planes, samples as two
-    byte planes, exact s32 accumulation, a two-level near-integer guard), FP64 tensor cores and the DFMA register tile
-    (llz_cuda_resample_bank_set_tiles) -- the int16 output must be the reference's, bit for bit, from all of them."""
+    """The exact mode's four tile kernels: INT8 tensor cores through mma.sync (1) and through tcgen05 with TMEM
+    accumulators (4) -- taps as five int8 digit planes, samples as two byte planes, exact s32 accumulation, a two-level
+    near-integer guard --, FP64 tensor cores (2) and the DFMA register tile (3), llz_cuda_resample_bank_set_tiles: the
+    int16 output must be the reference's, bit for bit, from all of them."""
     torch = cuda
     C_ = 3
     bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, C_, k_override=k)
