@@ -363,7 +363,8 @@ class Workload:
         if not self.fir:
             if wl["L"] == 1:
                 return "poly_slide_kernel", None, None
-            return ("poly_bank_hmma_kernel" if f32 else "poly_bank_imma_kernel"), None, None
+            # large calls run the tcgen05 kernel (llz_cuda_polybank_umma.cu): 3 digit planes in the fast mode, 5 in the exact mode
+            return ("poly_bank_umma_kernel<3>" if f32 else "poly_bank_umma_kernel<5>"), None, None
         t = "float" if f32 else "double"
         if self.fir_fft and wl["taps"] >= 545:
             # 8192-point overlap-save kernel (llz_cuda_fir_fft8k.cu): one CTA of 256 threads turns 2*B outputs out of
@@ -601,9 +602,10 @@ def measure(z, D: Dist, mg, name: str, dtype: str, algo: str, steps: int, warmup
                         "frac_of_measured": ach_tf / fma_peak_measured if fma_peak_measured else None,
                         "frac_of_nominal": ach_tf / fma_peak_nominal,
                         "note": f"algorithmic flops ({W.flop_per_out:.0f} per output) against the FMA pipe of the accumulator type"}
-            if W.kernel == "poly_bank_imma_kernel":
-                fma_pipe["note"] += ("; the kernel evaluates the sums exactly on the INT8 tensor cores (ten IMMA digit products per "
-                                     "multiply-add), so the fraction is its speed relative to the FP64 roof it no longer uses")
+            if W.kernel.startswith("poly_bank_umma_kernel"):
+                fma_pipe["note"] += ("; the kernel evaluates the sums as exact integers on the tensor cores (tcgen05.mma.kind::i8, "
+                                     "%d digit products per multiply-add), so the fraction is its speed relative to the FMA roof "
+                                     "it no longer uses" % (6 if W.dtype == "f32" else 10))
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):

@@ -795,8 +795,13 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     constexpr size_t kLimit = 226 * 1024;
     if (a.acc == LLZ_CUDA_ACC_F32) {
         // fast mode: exact-product fp16 split on the tensor cores unless the handle asks for the FFMA tile
-        // (llz_cuda_resample_bank_set_tiles).  A three-digit integer evaluation on the INT8 tensor cores was measured
-        // in round 1 (82 against 91 Gsamples/s on C4) and is no longer built.
+        // (llz_cuda_resample_bank_set_tiles).
+        // large calls: a three-digit integer evaluation as tcgen05.mma.kind::i8 (llz_cuda_polybank_umma.cu); the shim
+        // selects it by filling a.umma_rows
+        if (a.umma_rows && (a.tiles == LLZ_CUDA_TILES_AUTO || a.tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
+            const int rc = poly_bank_umma_launch(a, n_channels, stream);
+            if (rc != 0) return rc;
+        }
         if (a.cbankT16h && a.cbankT16l && a.tiles != LLZ_CUDA_TILES_CUDA_CORE) {
             const int rc = launch_bank_hmma<16>(a, n_channels, stream);
             if (rc != 0) return rc;

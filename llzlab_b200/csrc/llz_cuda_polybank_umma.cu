@@ -16,10 +16,14 @@
 //     ends, so the tile kernel has no edge cases on its input side.  The call is cut into slabs of cycles so that the
 //     expanded rows of a slab stay small (tunable; they are re-read by the five phase tiles of a cycle tile).
 //   * B operand (taps): host-built digit planes in the same swizzled layout (llz_umma_tables.h), one bulk copy per chunk.
-//   * Warp roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) and TMEM owner, warps 2-5 =
-//     epilogue (tcgen05.ld 32x32b: one accumulator row = one cycle per thread, 64 consecutive phases = 128 contiguous
-//     output bytes).  Three-stage full/empty mbarrier ring between producer and issuer (tcgen05.commit frees a stage),
-//     a full/empty pair on the accumulators between issuer and epilogue.  Persistent grid, phase tiles fastest.
+//   * Warp roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) and TMEM owner, warps 4-11 =
+//     epilogue (tcgen05.ld 32x32b: one accumulator row = one cycle per thread, 32 consecutive phases = 64 contiguous
+//     output bytes; the accumulators are released as soon as they are combined in registers, so the rest of the
+//     epilogue overlaps the next tile's MMAs).  Three-stage full/empty mbarrier ring between producer and issuer
+//     (tcgen05.commit frees a stage), a full/empty pair on the accumulators between issuer and epilogue.  Persistent
+//     grid, phase tiles fastest.
+//   * The fast mode (LLZ_CUDA_ACC_F32) is the same kernel with three digit planes (22-bit taps, four accumulators) and
+//     no guard: every product and sum is still exact, the only error is the tap rounding (<= 1 LSB of the output).
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -40,50 +44,98 @@ struct UmmaGeom {
     int n_cycle_tiles, n_phase_tiles, n_channels;
     int nchunk_max;                // chunks per phase tile in the tap tables
     int row_len;                   // RL
+    int n_stages;                  // A-operand stages that fit beside the resident taps (2..4)
 };
 
-constexpr int kUThreads = 192;
+constexpr int kUThreads = 384, kUEpiThreads = 256;
 constexpr int kUTmemCols = 512;
+constexpr int kUMaxStages = 4;
 
 // ---- pre-pass: expanded rows -----------------------------------------------------------------------------------------
 // rows[plane][channel][j][b] = byte `plane` of X((jc0 + j)*M - (Q-1) + b),  X = the stream sample of llz_poly_kernels.h
-constexpr int kERows = 8, kEThreads = 256;
+// One CTA writes kERows consecutive rows of one channel: its contiguous input span arrives by a bulk copy
+// (poly_stage_span: history, zeros and ragged ends are resolved there), is split into two byte planes in shared
+// memory, every lane then cuts one row out of the planes 16 bytes at a time (funnel shifts: rows start at any byte
+// offset), and the block of rows -- contiguous in the workspace -- leaves by one bulk store per plane.
+constexpr int kERows = 32, kEThreads = 256;
+
+struct ExpandSmem {
+    int raw_bytes, plane_bytes, total;
+};
+__host__ __device__ inline ExpandSmem expand_smem(int M, int RL)
+{
+    ExpandSmem e;
+    const int need_cap = (kERows - 1) * M + RL;
+    e.raw_bytes = ((need_cap + 16) * 2 + 15) & ~15;
+    e.plane_bytes = (need_cap + 8 + 15) & ~15;                 // the funnel reads one word beyond the last byte
+    e.total = e.raw_bytes + 2 * e.plane_bytes + 2 * kERows * RL;
+    return e;
+}
 
 __global__ void __launch_bounds__(kEThreads)
 poly_expand_rows_kernel(PolyLaunch a, UmmaGeom geo, unsigned char *rows)
 {
-    extern __shared__ __align__(16) int16_t span[];
+    extern __shared__ __align__(128) unsigned char esm[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ch = blockIdx.y;
     const int j_first = blockIdx.x * kERows;
     const int nrows = min(kERows, geo.n_cycles - j_first);
-    const int RL = geo.row_len;
+    const int RL = geo.row_len, M = a.M;
+    const ExpandSmem lay = expand_smem(M, RL);
+    int16_t *raw = reinterpret_cast<int16_t *>(esm);
+    unsigned char *plane[2] = {esm + lay.raw_bytes, esm + lay.raw_bytes + lay.plane_bytes};
+    unsigned char *outp[2] = {plane[1] + lay.plane_bytes, plane[1] + lay.plane_bytes + kERows * RL};
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
-    const long long S0 = (geo.jc0 + j_first) * (long long)a.M - (a.ctaps - 1);
-    const int need = (nrows - 1) * a.M + RL;
-    for (int e = threadIdx.x; e < need; e += kEThreads) span[e] = (int16_t)poly_sample(a, xc, hc, S0 + e);
+    const long long S0 = (geo.jc0 + j_first) * (long long)M - (a.ctaps - 1);
+    const int need = (nrows - 1) * M + RL;
+    bool bulk;
+    const int off = poly_stage_span<kEThreads>(a, xc, hc, S0, need, raw, &bar, tid, &bulk);
     __syncthreads();
-    const size_t plane_stride = (size_t)geo.n_channels * geo.n_cycles * RL;
-    unsigned char *lo = rows + ((size_t)ch * geo.n_cycles + j_first) * RL;
-    unsigned char *hi = lo + plane_stride;
-    const int vec_per_row = RL >> 4;
-    for (int v = threadIdx.x; v < nrows * vec_per_row; v += kEThreads) {
-        const int r = v / vec_per_row, c = v - r * vec_per_row;
-        const int16_t *src = span + r * a.M + 16 * c;
-        uint32_t l[4], h[4];
+    if (bulk) mbar_wait(&bar, 0);
+    // byte planes: plane[p][e] = byte p of X(S0 + e)
+    for (int e = 4 * tid; e < need + 4; e += 4 * kEThreads) {
+        uint32_t lw = 0, hw = 0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            uint32_t lw = 0, hw = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t s = (uint16_t)src[4 * w + b];
-                lw |= (s & 255u) << (8 * b);
-                hw |= (s >> 8) << (8 * b);
-            }
-            l[w] = lw; h[w] = hw;
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t v = (e + b < need) ? (uint32_t)(uint16_t)raw[off + e + b] : 0u;
+            lw |= (v & 255u) << (8 * b);
+            hw |= (v >> 8) << (8 * b);
         }
-        *reinterpret_cast<uint4 *>(lo + (size_t)r * RL + 16 * c) = make_uint4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<uint4 *>(hi + (size_t)r * RL + 16 * c) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint32_t *>(plane[0] + e) = lw;
+        *reinterpret_cast<uint32_t *>(plane[1] + e) = hw;
+    }
+    __syncthreads();
+    // lane = row: row r starts at byte r*M of the planes
+    const int vec_per_row = RL >> 4;
+    if (lane < nrows) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(plane[p]);
+            for (int c = warp; c < vec_per_row; c += kEThreads / 32) {
+                const int b = lane * M + 16 * c;
+                const int w = b >> 2, sh = (b & 3) * 8;
+                uint32_t x[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) x[i] = src[w + i];
+                uint4 o;
+                o.x = __funnelshift_r(x[0], x[1], sh); o.y = __funnelshift_r(x[1], x[2], sh);
+                o.z = __funnelshift_r(x[2], x[3], sh); o.w = __funnelshift_r(x[3], x[4], sh);
+                *reinterpret_cast<uint4 *>(outp[p] + lane * RL + 16 * c) = o;
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        const size_t plane_stride = (size_t)geo.n_channels * geo.n_cycles * RL;
+        unsigned char *dst = rows + ((size_t)ch * geo.n_cycles + j_first) * RL;
+        const uint32_t bytes = (uint32_t)(nrows * RL);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(outp[0])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + plane_stride), "r"(smem_u32(outp[1])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads of the store
     }
 }
 
@@ -106,10 +158,23 @@ __host__ __device__ constexpr uint32_t umma_idesc(int a_signed)
     return (2u << 4) | ((uint32_t)a_signed << 7) | (1u << 10) | ((uint32_t)(kUPB >> 3) << 17) | ((uint32_t)(kUJB >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+// The descriptors differ in their low word only (start address >> 4, LBO); the high word (SBO, version, swizzle) is the
+// same for every operand.  Passing 32-bit words keeps the per-MMA address arithmetic in 32-bit uniform registers.
+constexpr uint32_t kUDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo, uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n}\n"
+                 ::"r"(tmem_d), "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "r"(kUDescHi) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 // arrives on the barrier once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
@@ -124,11 +189,10 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, i
                  ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
 {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
 
@@ -137,34 +201,60 @@ struct UmmaTile {
     UmmaPhaseTile pt;
 };
 
+// tiles in phase-major order: t = (tile_p * n_channels + ch) * n_cycle_tiles + tile_j.  A CTA walks a contiguous range, so
+// it changes its phase tile -- and reloads the resident taps -- at most once or twice per launch, and the CTAs that share a
+// block of expanded rows (one per phase tile) sweep the slab at the same pace (the rows are read from L2).
 __device__ __forceinline__ UmmaTile umma_tile(const PolyLaunch &a, const UmmaGeom &geo, long long t)
 {
     UmmaTile T;
-    T.tile_p = (int)(t % geo.n_phase_tiles);                   // phase tiles fastest: neighbours share the expanded rows in L2
-    const long long r = t / geo.n_phase_tiles;
-    T.tile_j = (int)(r % geo.n_cycle_tiles);
-    T.ch = (int)(r / geo.n_cycle_tiles);
+    T.tile_j = (int)(t % geo.n_cycle_tiles);
+    const long long r = t / geo.n_cycle_tiles;
+    T.ch = (int)(r % geo.n_channels);
+    T.tile_p = (int)(r / geo.n_channels);
     T.pt = umma_phase_tile(a.L, a.M, a.ctaps, T.tile_p);
     return T;
 }
 
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer and TMEM owner (both walk their loops as whole
+// warps -- warp-uniform control flow keeps descriptors and coordinates in uniform registers -- and one elected lane
+// issues), warps 4-11 = epilogue.
+//
+// Shared memory: the taps of the CTA's current phase tile stay RESIDENT (nchunks x PLANES x 8 KB: 120 KB for C4's exact
+// mode), only the sample operand streams through a ring of 32 KB stages.  (The first versions streamed the taps with the
+// samples: 221 KB from L2 per 8192 outputs, and clock stamps showed the issuer waiting ~2400 cycles for every 74 KB
+// stage -- 30 B/clk/SM, the whole chip at the L2's throughput limit -- while the MMAs of a stage take 1900.)
+//
+// Epilogue warp e reads TMEM lane quarter e & 3 (= warp index % 4, the quarter the hardware lets it read) and the column
+// half e >> 2: one accumulator row = one cycle per thread, 32 consecutive phases = 64 contiguous output bytes.  A pass
+// has two parts: DRAIN -- tcgen05.ld the PLANES + 1 accumulators, combine them into one 64-bit integer per output and
+// convert once (32 doubles per thread stay in registers) -- after which the thread releases the accumulators, and
+// FINISH -- near-integer test, truncation, stores, the guard's second look -- which runs while the issuer is already
+// multiplying the next tile.  (The first version ran the whole epilogue on four warps between two tiles.)
+template <int PLANES, bool GUARD>
 __global__ void __launch_bounds__(kUThreads, 1)
 poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a, UmmaGeom geo)
 {
+    constexpr int kBStage = umma_b_stage(PLANES);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *stages = smem_raw;                                          // kUStages x [A lo | A hi | B planes]
-    uint64_t *s_full = reinterpret_cast<uint64_t *>(smem_raw + kUStages * kUStage);
-    uint64_t *s_empty = s_full + kUStages;
-    uint64_t *t_full = s_empty + kUStages, *t_empty = t_full + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 1);
+    unsigned char *taps = smem_raw;                                            // nchunk_max x [PLANES x 8 KB]
+    unsigned char *stages = smem_raw + (size_t)geo.nchunk_max * kBStage;        // n_stages x [A lo | A hi]
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(stages + (size_t)geo.n_stages * kUAStage);
+    uint64_t *s_empty = s_full + kUMaxStages;
+    uint64_t *t_full = s_empty + kUMaxStages, *t_empty = t_full + 1, *b_full = t_full + 2, *b_free = t_full + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_full + 4);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform for the compiler, too
     const long long total = (long long)geo.n_phase_tiles * geo.n_cycle_tiles * geo.n_channels;
+    const long long t_begin = total * blockIdx.x / gridDim.x, t_end = total * (blockIdx.x + 1) / gridDim.x;
+    const int S = geo.n_stages;
 
     if (tid == 0) {
-        for (int i = 0; i < kUStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < kUMaxStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         mbar_init(t_full, 1);
-        mbar_init(t_empty, 128);
+        mbar_init(t_empty, kUEpiThreads);
+        mbar_init(b_full, 1);
+        mbar_init(b_free, 1);
     }
     __syncwarp();
     if (warp == 1) {
@@ -178,136 +268,166 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            long long g = 0;                                                   // global chunk counter
-            for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-                const UmmaTile T = umma_tile(a, geo, t);
-                for (int c = 0; c < T.pt.nchunks; ++c, ++g) {
-                    const int buf = (int)(g % kUStages);
-                    if (g >= kUStages) mbar_wait(&s_empty[buf], (uint32_t)((g / kUStages - 1) & 1));
-                    unsigned char *st = stages + (size_t)buf * kUStage;
-                    mbar_expect_tx(&s_full[buf], (uint32_t)kUStage);
-                    const int b0 = T.pt.w0 + kUKC * c, j0 = T.tile_j * kUJB;
+        const bool leader = elect_one();
+        int buf = 0, run = 0, prev_p = -1;
+        uint32_t ph = 0;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const UmmaTile T = umma_tile(a, geo, t);
+            if (T.tile_p != prev_p) {
+                // new phase tile: its taps replace the resident ones once every MMA of the previous run has read them
+                if (run > 0) mbar_wait(b_free, (uint32_t)((run - 1) & 1));
+                if (leader) {
+                    mbar_expect_tx(b_full, (uint32_t)(T.pt.nchunks * kBStage));
+                    for (int c = 0; c < T.pt.nchunks; ++c)
+                        tma_bulk_g2s(taps + (size_t)c * kBStage, a.umma_tiles + ((size_t)T.tile_p * geo.nchunk_max + c) * kBStage,
+                                     (uint32_t)kBStage, b_full);
+                }
+                __syncwarp();
+                prev_p = T.tile_p;
+                ++run;
+            }
+            const int j0 = T.tile_j * kUJB;
+            for (int c = 0; c < T.pt.nchunks; ++c) {
+                mbar_wait(&s_empty[buf], ph ^ 1u);                             // passes at once on the first lap
+                if (leader) {
+                    unsigned char *st = stages + (size_t)buf * kUAStage;
+                    mbar_expect_tx(&s_full[buf], (uint32_t)kUAStage);
+                    const int b0 = T.pt.w0 + kUKC * c;
                     tma_load_4d(st, &rows_map, b0, j0, T.ch, 0, &s_full[buf]);
                     tma_load_4d(st + kUAPlane, &rows_map, b0, j0, T.ch, 1, &s_full[buf]);
-                    tma_bulk_g2s(st + kUAStage, a.umma_tiles + ((size_t)T.tile_p * geo.nchunk_max + c) * kUBStage, (uint32_t)kUBStage,
-                                 &s_full[buf]);
                 }
+                __syncwarp();
+                if (++buf == S) { buf = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
-            long long g = 0;
-            uint32_t tile_n = 0;
-            for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tile_n) {
-                const UmmaTile T = umma_tile(a, geo, t);
-                // the epilogue has drained the accumulators of the previous tile (passes at once for the first tile)
-                mbar_wait(t_empty, (tile_n & 1u) ^ 1u);
+        // With the loops inside `if (lane == 0)` every MMA sat in a divergence "waterfall" (ELECT / R2UR.BROADCAST /
+        // BRA.U.ANY: ~20 instructions per MMA); now ten UTCIMMA follow one another.
+        const bool leader = elect_one();
+        int buf = 0, run = 0, prev_p = -1;
+        uint32_t ph = 0, tile_n = 0;
+        const uint32_t taps_desc = umma_desc_lo(smem_u32(taps));
+        for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
+            const UmmaTile T = umma_tile(a, geo, t);
+            if (T.tile_p != prev_p) {
+                if (run > 0 && leader) umma_commit(b_free);                    // the old taps are free once the MMAs so far are done
+                __syncwarp();
+                mbar_wait(b_full, (uint32_t)(run & 1));
+                prev_p = T.tile_p;
+                ++run;
+            }
+            // the epilogue has drained the accumulators of the previous tile (passes at once for the first tile)
+            mbar_wait(t_empty, (tile_n & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int c = 0; c < T.pt.nchunks; ++c) {
+                mbar_wait(&s_full[buf], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                for (int c = 0; c < T.pt.nchunks; ++c, ++g) {
-                    const int buf = (int)(g % kUStages);
-                    mbar_wait(&s_full[buf], (uint32_t)((g / kUStages) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t sa = smem_u32(stages + (size_t)buf * kUStage);
-                    const int ks_n = min(4, T.pt.ksteps - 4 * c);
+                const uint32_t sa = smem_u32(stages) + (uint32_t)buf * kUAStage;
+                const uint32_t d_lo = umma_desc_lo(sa), d_hi = umma_desc_lo(sa + kUAPlane);
+                const uint32_t d_b = taps_desc + (uint32_t)c * (kBStage >> 4);
+                const int ks_n = min(4, T.pt.ksteps - 4 * c);
+                if (leader) {
                     for (int ks = 0; ks < ks_n; ++ks) {
-                        const uint64_t koff = (uint64_t)((32 * ks) >> 4);
-                        const uint64_t a_lo = umma_smem_desc(sa) + koff, a_hi = umma_smem_desc(sa + kUAPlane) + koff;
+                        const uint32_t koff = (uint32_t)(2 * ks);              // 32 bytes of K per step, >> 4
                         const bool first = c == 0 && ks == 0;
 #pragma unroll
-                        for (int i = 0; i < kUPlanes; ++i) {
-                            const uint64_t b_i = umma_smem_desc(sa + kUAStage + i * kUBPlane) + koff;
+                        for (int i = 0; i < PLANES; ++i) {
+                            const uint32_t b_i = d_b + (uint32_t)(i * (kUBPlane >> 4)) + koff;
                             // digit i x low byte -> weight 256^i, digit i x high byte -> weight 256^(i+1)
-                            umma_i8(tmem + kUPB * i, a_lo, b_i, umma_idesc(0), (first && i == 0) ? 0u : 1u);
-                            umma_i8(tmem + kUPB * (i + 1), a_hi, b_i, umma_idesc(1), first ? 0u : 1u);
+                            umma_i8(tmem + kUPB * i, d_lo + koff, b_i, umma_idesc(0), (first && i == 0) ? 0u : 1u);
+                            umma_i8(tmem + kUPB * (i + 1), d_hi + koff, b_i, umma_idesc(1), first ? 0u : 1u);
                         }
                     }
                     umma_commit(&s_empty[buf]);                                // the stage is free once these MMAs have read it
                 }
-                umma_commit(t_full);                                           // the tile's accumulators are complete
+                __syncwarp();
+                if (++buf == S) { buf = 0; ph ^= 1u; }
             }
+            if (leader) umma_commit(t_full);                                   // the tile's accumulators are complete
+            __syncwarp();
         }
-    } else {
+    } else if (warp >= 4) {
         // ================================ epilogue ================================
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
+        const int h = (warp - 4) >> 2;                         // column half: phases 32h .. 32h + 31 of the tile
         const int m = 32 * q + lane;                           // accumulator row = cycle within the tile
         const int L = a.L, M = a.M, Q = a.ctaps;
         const long long o_end = a.o0 + a.n_out;
-        const double out_scale = a.imma_scale * 16777216.0;    // the high half carries 256^3
+        const double sg = a.umma_scale * a.gain;               // 2^-s * gain: one rounding, like the reference's sum * gain
         uint32_t tile_n = 0;
-        for (long long t = blockIdx.x; t < total; t += gridDim.x, ++tile_n) {
+        for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
             const UmmaTile T = umma_tile(a, geo, t);
-            const int l0 = T.pt.l0, pbv = T.pt.pbv;
+            const int l0 = T.pt.l0 + 32 * h, pbv = max(0, min(32, T.pt.pbv - 32 * h));
             const long long j = geo.jc0 + (long long)T.tile_j * kUJB + m;          // this thread's cycle
             const int16_t *xc = a.x ? a.x + (long long)T.ch * a.x_stride : nullptr;
             const int16_t *hc = a.hist ? a.hist + (long long)T.ch * a.hist_len : nullptr;
             int16_t *ych = a.y + (long long)T.ch * a.y_stride;
-            // single-tap (knife-edge) phases of the tile, one bit per phase
-            const unsigned st_lo = __ballot_sync(0xffffffffu, lane < pbv && __ldg(a.single_tap + l0 + lane) >= 0);
-            const unsigned st_hi = __ballot_sync(0xffffffffu, lane + 32 < pbv && __ldg(a.single_tap + l0 + lane + 32) >= 0);
-            const unsigned long long st_mask = ((unsigned long long)st_hi << 32) | st_lo;
+            // single-tap (knife-edge) phases of this half tile, one bit per phase
+            const unsigned st_mask = __ballot_sync(0xffffffffu, lane < pbv && __ldg(a.single_tap + l0 + lane) >= 0);
 
             mbar_wait(t_full, tile_n & 1u);
             __syncwarp();                                      // the lanes leave the wait loop one by one; tcgen05.ld is .aligned
             asm volatile("tcgen05.fence::after_thread_sync;");
 
-            const long long o_row = j * (long long)L + l0;     // output index of this thread's phase l0
+            // ---- drain: accumulators -> one double per output ----
+            double v[32];
+            const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + 32 * h;
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) {
+                int acc[PLANES + 1][8];
+#pragma unroll
+                for (int d = 0; d <= PLANES; ++d) tmem_ld8(trow + kUPB * d + 8 * cg, acc[d]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    long long T64 = (long long)acc[0][e];
+#pragma unroll
+                    for (int d = 1; d <= PLANES; ++d) T64 += (long long)acc[d][e] << (8 * d);
+                    v[8 * cg + e] = __dmul_rn((double)T64, sg);
+                }
+            }
+            // the accumulators are in registers: the issuer may start the next tile
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            mbar_arrive(t_empty);
+
+            // ---- finish ----
+            const long long o_row = j * (long long)L + l0;     // output index of this thread's first phase
             const bool row_in = (m < geo.n_cycles - T.tile_j * kUJB);
-            const bool interior = row_in && pbv == kUPB && o_row >= a.o0 && o_row + (kUPB - 1) < o_end;
+            const bool interior = row_in && pbv == 32 && o_row >= a.o0 && o_row + 31 < o_end;
             int16_t *yrow = ych + (o_row - a.o0);
             const bool vec_ok = interior && ((reinterpret_cast<uintptr_t>(yrow) & 15u) == 0);
-            unsigned long long hits = 0;                       // near-integer outputs of this row, one bit per phase
-            const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
-#pragma unroll 1
-            for (int cg = 0; cg < 4; ++cg) {
-                int acc[kUPlanes + 1][16];
+            unsigned hits = 0;                                 // near-integer outputs of this row, one bit per phase
+            uint32_t packed[16];
 #pragma unroll
-                for (int d = 0; d <= kUPlanes; ++d) tmem_ld16(trow + kUPB * d + 16 * cg, acc[d]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                int16_t outv[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const long long lo = (long long)acc[0][e] + (long long)acc[1][e] * 256 + (long long)acc[2][e] * 65536;
-                    const long long hi = (long long)acc[3][e] + (long long)acc[4][e] * 256 + (long long)acc[5][e] * 65536;
-                    const double s = fma((double)hi, out_scale, (double)lo * a.imma_scale);
-                    const double v = __dmul_rn(s, a.gain);
-                    if (poly_near_nonzero_integer(v, a.imma_thr)) hits |= 1ull << (16 * cg + e);
-                    outv[e] = poly_finish(v);
+            for (int e = 0; e < 32; e += 2) {
+                if (GUARD) {
+                    if (poly_near_nonzero_integer(v[e], a.imma_thr)) hits |= 1u << e;
+                    if (poly_near_nonzero_integer(v[e + 1], a.imma_thr)) hits |= 2u << e;
                 }
-                if (vec_ok) {
-                    uint4 w0, w1;
-                    w0.x = (uint16_t)outv[0] | ((uint32_t)(uint16_t)outv[1] << 16);   w0.y = (uint16_t)outv[2] | ((uint32_t)(uint16_t)outv[3] << 16);
-                    w0.z = (uint16_t)outv[4] | ((uint32_t)(uint16_t)outv[5] << 16);   w0.w = (uint16_t)outv[6] | ((uint32_t)(uint16_t)outv[7] << 16);
-                    w1.x = (uint16_t)outv[8] | ((uint32_t)(uint16_t)outv[9] << 16);   w1.y = (uint16_t)outv[10] | ((uint32_t)(uint16_t)outv[11] << 16);
-                    w1.z = (uint16_t)outv[12] | ((uint32_t)(uint16_t)outv[13] << 16); w1.w = (uint16_t)outv[14] | ((uint32_t)(uint16_t)outv[15] << 16);
-                    reinterpret_cast<uint4 *>(yrow + 16 * cg)[0] = w0;
-                    reinterpret_cast<uint4 *>(yrow + 16 * cg)[1] = w1;
-                } else if (interior) {
+                packed[e >> 1] = (uint32_t)(uint16_t)poly_finish(v[e]) | ((uint32_t)(uint16_t)poly_finish(v[e + 1]) << 16);
+            }
+            if (vec_ok) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) yrow[16 * cg + e] = outv[e];
-                } else if (row_in) {
+                for (int w = 0; w < 4; ++w)
+                    reinterpret_cast<uint4 *>(yrow)[w] = make_uint4(packed[4 * w], packed[4 * w + 1], packed[4 * w + 2], packed[4 * w + 3]);
+            } else if (row_in) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int l = 16 * cg + e;
-                        const long long o = o_row + l;
-                        const bool valid = l < pbv && o >= a.o0 && o < o_end;
-                        if (valid) ych[o - a.o0] = outv[e];
-                        else hits &= ~(1ull << l);
-                    }
+                for (int e = 0; e < 32; ++e) {
+                    const long long o = o_row + e;
+                    const bool valid = e < pbv && o >= a.o0 && o < o_end;
+                    if (valid) ych[o - a.o0] = (int16_t)(packed[e >> 1] >> (16 * (e & 1)));
+                    else hits &= ~(1u << e);
                 }
             }
             if (!row_in) hits = 0;
-            // the accumulators are in registers / stored: the issuer may start the next tile
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            mbar_arrive(t_empty);
 
             // knife-edge phases (one tap, 1 - 2^-53 for the L-th band prototype): one exact FP64 product per output
             hits &= ~st_mask;
             if (row_in) {
-                unsigned long long sm = st_mask;
+                unsigned sm = st_mask;
                 while (sm) {
-                    const int l = __ffsll((long long)sm) - 1;
+                    const int l = __ffs((int)sm) - 1;
                     sm &= sm - 1;
                     const long long o = o_row + l;
                     if (o < a.o0 || o >= o_end) continue;
@@ -316,6 +436,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                     ych[o - a.o0] = poly_finish(__dmul_rn(__dmul_rn((double)poly_sample(a, xc, hc, base - st), a.cbank[(long long)(l0 + l) * Q + st]), a.gain));
                 }
             }
+            if (!GUARD) continue;
             __syncwarp();
 
             // Second look at the outputs that came within the (wide) band of the integer evaluation: the whole warp evaluates
@@ -324,7 +445,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             unsigned pending = __ballot_sync(0xffffffffu, hits != 0);
             while (pending) {
                 const int src = __ffs(pending) - 1;
-                int l = (lane == src) ? __ffsll((long long)hits) - 1 : 0;
+                int l = (lane == src) ? __ffs((int)hits) - 1 : 0;
                 l = __shfl_sync(0xffffffffu, l, src);
                 const long long o = (geo.jc0 + (long long)T.tile_j * kUJB + 32 * q + src) * (long long)L + l0 + l;   // warp-uniform
                 const long long base = (o * M) / L;
@@ -346,12 +467,12 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 #pragma unroll
                 for (int sh = 16; sh; sh >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sh);
                 if (lane == src) {
-                    double v = __dmul_rn(part, a.gain);
-                    if (poly_near_nonzero_integer(v, a.guard_thr)) {
-                        v = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
+                    double vv = __dmul_rn(part, a.gain);
+                    if (poly_near_nonzero_integer(vv, a.guard_thr)) {
+                        vv = __dmul_rn(poly_reference_order_sum(a, xc, hc, o), a.gain);
                         atomicAdd(a.guard_count, 1ULL);
                     }
-                    ych[o - a.o0] = poly_finish(v);
+                    ych[o - a.o0] = poly_finish(vv);
                     hits &= hits - 1;
                 }
                 pending = __ballot_sync(0xffffffffu, hits != 0);
@@ -389,20 +510,29 @@ size_t poly_bank_umma_rows_bytes(const PolyLaunch &a, int n_channels, long long 
     return (size_t)2 * n_channels * (size_t)cycles * umma_row_len(a.L, a.M, a.ctaps);
 }
 
-// 1 = launched, 0 = not applicable, -1 = error
-int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+namespace {
+
+template <int PLANES, bool GUARD>
+int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
-    if (!a.umma_tiles || a.umma_nchunks <= 0 || !a.umma_rows || a.umma_slab_cycles <= 0) return 0;
-    if (a.acc != LLZ_CUDA_ACC_F64 || a.shift != 0 || a.frame_len != 0 || a.n_out <= 0) return 0;
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { llz_set_error("cuTensorMapEncodeTiled is not available from this driver"); return -1; }
     const int sms = device_sm_count();
     if (sms <= 0) return -1;
     const int RL = umma_row_len(a.L, a.M, a.ctaps);
     const long long jc_first = a.o0 / a.L, jc_last = (a.o0 + a.n_out - 1) / a.L;
-    constexpr size_t smem = (size_t)kUStages * kUStage + 128;
-    static_assert(smem <= 227 * 1024, "pipeline stages exceed the shared memory of an SM");
-    LLZ_CUDA_TRY(cudaFuncSetAttribute(poly_bank_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // shared memory: the resident taps, then as many 32 KB sample stages as fit (at least two)
+    constexpr size_t kSmemMax = 227 * 1024, kBarBytes = 128;
+    const size_t taps_bytes = (size_t)a.umma_nchunks * umma_b_stage(PLANES);
+    if (taps_bytes + 2 * kUAStage + kBarBytes + 1024 > kSmemMax) return 0;
+    int n_stages = (int)((kSmemMax - kBarBytes - 1024 - taps_bytes) / kUAStage);
+    if (n_stages > kUMaxStages) n_stages = kUMaxStages;
+    const size_t smem = taps_bytes + (size_t)n_stages * kUAStage + kBarBytes;
+    const ExpandSmem elay = expand_smem(a.M, RL);
+    if (elay.total > 200 * 1024) return 0;
+    auto kern = poly_bank_umma_kernel<PLANES, GUARD>;
+    LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LLZ_CUDA_TRY(cudaFuncSetAttribute(poly_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, elay.total));
     for (long long jc0 = jc_first; jc0 <= jc_last; jc0 += a.umma_slab_cycles) {
         UmmaGeom geo{};
         geo.jc0 = jc0;
@@ -412,11 +542,10 @@ int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
         geo.n_channels = n_channels;
         geo.nchunk_max = a.umma_nchunks;
         geo.row_len = RL;
+        geo.n_stages = n_stages;
         // 1. expanded rows of the slab
-        const size_t esm = ((size_t)(kERows - 1) * a.M + RL) * sizeof(int16_t);
-        if (esm > 48 * 1024) return 0;
         dim3 egrid((unsigned)((geo.n_cycles + kERows - 1) / kERows), (unsigned)n_channels);
-        poly_expand_rows_kernel<<<egrid, kEThreads, esm, stream>>>(a, geo, a.umma_rows);
+        poly_expand_rows_kernel<<<egrid, kEThreads, (size_t)elay.total, stream>>>(a, geo, a.umma_rows);
         LLZ_CUDA_TRY(cudaGetLastError());
         // 2. the tensor map over them: [plane][channel][cycle][byte]
         CUtensorMap map;
@@ -429,10 +558,22 @@ int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
         // 3. the tiles
         const long long tiles = (long long)geo.n_cycle_tiles * geo.n_phase_tiles * n_channels;
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);           // persistent: one CTA per SM
-        poly_bank_umma_kernel<<<grid, kUThreads, smem, stream>>>(map, a, geo);
+        kern<<<grid, kUThreads, smem, stream>>>(map, a, geo);
         LLZ_CUDA_TRY(cudaGetLastError());
     }
     return 1;
+}
+
+}  // namespace
+
+// 1 = launched, 0 = not applicable, -1 = error
+int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
+{
+    if (!a.umma_tiles || a.umma_nchunks <= 0 || !a.umma_rows || a.umma_slab_cycles <= 0) return 0;
+    if (a.shift != 0 || a.frame_len != 0 || a.n_out <= 0) return 0;
+    if (a.acc == LLZ_CUDA_ACC_F64 && a.umma_planes == kUPlanesExact) return umma_launch_slabs<kUPlanesExact, true>(a, n_channels, stream);
+    if (a.acc == LLZ_CUDA_ACC_F32 && a.umma_planes == kUPlanesFast) return umma_launch_slabs<kUPlanesFast, false>(a, n_channels, stream);
+    return 0;
 }
 
 }  // namespace llz

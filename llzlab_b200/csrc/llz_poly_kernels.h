@@ -61,6 +61,8 @@ struct PolyLaunch {
     // llz_umma_tables.h, and the workspace of the call's expanded input rows; nullptr = not selected for this call
     const signed char *umma_tiles;
     int umma_nchunks;          // chunks of 128 k bytes per phase tile
+    int umma_planes;           // digit planes of umma_tiles: 5 (exact mode) or 3 (fast mode)
+    double umma_scale;         // g ~ q * umma_scale for those digits
     unsigned char *umma_rows;  // workspace: poly_bank_umma_rows_bytes(a, channels, umma_slab_cycles) bytes
     int umma_slab_cycles;      // cycles per slab (multiple of 128)
 };

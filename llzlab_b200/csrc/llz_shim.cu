@@ -483,6 +483,7 @@ struct PolyBank {
     int bank16_exp = 0;
     signed char *d_umma_tiles = nullptr;   // the same digit planes in the tcgen05 kernel's layout (llz_cuda_polybank_umma.cu)
     int umma_nchunks = 0;
+    int umma_planes = 0, umma_shift = 0;   // digit planes (5 exact / 3 fast) and the scale 2^-shift of those tables
     unsigned char *d_umma_rows = nullptr;  // workspace: expanded input rows of one slab
     size_t umma_rows_cap = 0;
     signed char *d_imma_tiles = nullptr;   // int8 digit planes of the bank (llz_cuda_polybank_imma.cu)
@@ -608,8 +609,18 @@ int poly_upload_plan(PolyBank *b)
         std::vector<signed char> utiles;
         int ushift = 0;
         double ueps = 0.0;
-        b->umma_nchunks = llz::poly_umma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, &utiles, &ushift, &ueps);
+        b->umma_planes = llz::kUPlanesExact;
+        b->umma_nchunks = llz::poly_umma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->umma_planes, &utiles, &ushift, &ueps);
         if (b->umma_nchunks > 0 && (ushift != b->imma_shift || b->imma_nchunks <= 0)) b->umma_nchunks = 0;
+        if (b->umma_nchunks > 0 && upload(&b->d_umma_tiles, utiles)) return -1;
+        b->umma_shift = ushift;
+    }
+    if (b->acc == LLZ_CUDA_ACC_F32 && L >= 16 && p.shift == 0 && p.frame_len == 0) {
+        // fast mode on tcgen05: three digit planes (22-bit taps), exact products and sums, no guard
+        std::vector<signed char> utiles;
+        double ueps = 0.0;
+        b->umma_planes = llz::kUPlanesFast;
+        b->umma_nchunks = llz::poly_umma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->umma_planes, &utiles, &b->umma_shift, &ueps);
         if (b->umma_nchunks > 0 && upload(&b->d_umma_tiles, utiles)) return -1;
     }
     std::vector<int> order(p.order, p.order + Q), single(L);
@@ -781,6 +792,8 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
             }
             a.umma_tiles = b->d_umma_tiles;
             a.umma_nchunks = b->umma_nchunks;
+            a.umma_planes = b->umma_planes;
+            a.umma_scale = ldexp(1.0, -b->umma_shift);
             a.umma_rows = b->d_umma_rows;
             a.umma_slab_cycles = (int)slab;
         }

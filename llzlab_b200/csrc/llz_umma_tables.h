@@ -7,7 +7,7 @@
 // row per output cycle, two byte planes), so every operand row starts at a 16-byte boundary (TMA traps on an
 // unaligned innermost box coordinate: tools/probe_umma_i8.cu).  A phase tile reads the window  b in [w0, w0 + 128*chunks)
 // of the rows, w0 = 16*floor(c_lo/16); the c_lo % 16 bytes in front of its first useful sample meet zero taps.
-// B operand: per phase tile and 128-byte chunk, five signed base-256 digit planes of the taps, each a [64 x 128 byte]
+// B operand: per phase tile and 128-byte chunk, five (exact mode) or three (fast mode) signed base-256 digit planes of the taps, each a [64 x 128 byte]
 // K-major SWIZZLE_128B block (8-row atoms of 1024 bytes, 16-byte chunk c of row r at position c ^ (r & 7)) -- the
 // layout a TMA box with CU_TENSOR_MAP_SWIZZLE_128B produces and the one the shared-memory matrix descriptor names.
 #pragma once
@@ -28,14 +28,13 @@ namespace llz {
 constexpr int kUPB = 64;                  // phases per tile (MMA N)
 constexpr int kUJB = 128;                 // cycles per tile (MMA M)
 constexpr int kUKC = 128;                 // k bytes per pipeline chunk = four K steps of 32
-constexpr int kUPlanes = 5;               // signed base-256 digits of a tap
-constexpr int kUTapBits = 8 * kUPlanes - 2;
+// signed base-256 digits of a tap: 5 planes (38 bits) for the exact mode, 3 planes (22 bits) for the fast mode
+constexpr int kUPlanesExact = 5, kUPlanesFast = 3;
 constexpr int kUBPlane = kUPB * kUKC;     // 8192 bytes: one digit plane of one chunk
-constexpr int kUBStage = kUPlanes * kUBPlane;       // 40,960 bytes of taps per chunk
 constexpr int kUAPlane = kUJB * kUKC;     // 16,384 bytes: one byte plane of the samples of one chunk
 constexpr int kUAStage = 2 * kUAPlane;
-constexpr int kUStage = kUAStage + kUBStage;        // 73,728 bytes per pipeline stage
-constexpr int kUStages = 3;
+LLZ_UMMA_HD constexpr int umma_tap_bits(int planes) { return 8 * planes - 2; }
+LLZ_UMMA_HD constexpr int umma_b_stage(int planes) { return planes * kUBPlane; }            // 40,960 / 24,576 bytes of taps per chunk
 
 // geometry of phase tile p: everything the producer, the MMA issuer and the host table builder must agree on
 struct UmmaPhaseTile {
@@ -76,21 +75,22 @@ LLZ_UMMA_HD inline int umma_b_offset(int n, int kk)
 
 // Host: the bank [L][Q] as int8 digit planes, [phase tile][chunk][plane][64 x 128 swizzled].  Returns the chunks per
 // tile (0 when the bank cannot be split); *shift = s with g ~ q * 2^-s, *eps = bound on |sum_k (g - q 2^-s) x| for |x| <= 32768.
-inline int poly_umma_build_tables(const double *cb, int L, int M, int Q, std::vector<signed char> *out, int *shift, double *eps)
+inline int poly_umma_build_tables(const double *cb, int L, int M, int Q, int planes, std::vector<signed char> *out, int *shift, double *eps)
 {
     double gmax = 0.0;
     for (size_t i = 0; i < (size_t)L * Q; ++i) gmax = fmax(gmax, fabs(cb[i]));
     if (!(gmax > 0.0) || !isfinite(gmax)) return 0;
     int e2 = 0;
     frexp(gmax, &e2);                                          // gmax < 2^e2
-    const int s = kUTapBits - e2;
+    const int s = umma_tap_bits(planes) - e2;
+    const int b_stage = umma_b_stage(planes);
     const int n_tiles = (L + kUPB - 1) / kUPB;
     int nchunks = 0;
     for (int p = 0; p < n_tiles; ++p) {
         const UmmaPhaseTile t = umma_phase_tile(L, M, Q, p);
         if (t.nchunks > nchunks) nchunks = t.nchunks;
     }
-    out->assign((size_t)n_tiles * nchunks * kUBStage, 0);
+    out->assign((size_t)n_tiles * nchunks * b_stage, 0);
     for (int p = 0; p < n_tiles; ++p) {
         const UmmaPhaseTile t = umma_phase_tile(L, M, Q, p);
         for (int l = 0; l < t.pbv; ++l) {
@@ -99,8 +99,8 @@ inline int poly_umma_build_tables(const double *cb, int L, int M, int Q, std::ve
                 long long q = llrint(ldexp(cb[(size_t)(t.l0 + l) * Q + k], s));
                 // window byte that meets tap k of phase l: sample index  j*M + c_l - k  sits at row byte  c_l + (Q-1) - k
                 const int kappa = t.off + (Q - 1) + d - k;
-                signed char *dst = out->data() + ((size_t)p * nchunks + kappa / kUKC) * kUBStage + umma_b_offset(l, kappa % kUKC);
-                for (int pl = 0; pl < kUPlanes; ++pl) {
+                signed char *dst = out->data() + ((size_t)p * nchunks + kappa / kUKC) * b_stage + umma_b_offset(l, kappa % kUKC);
+                for (int pl = 0; pl < planes; ++pl) {
                     const int dg = (int)((((q % 256) + 256 + 128) % 256) - 128);   // signed digit in [-128, 127]
                     dst[(size_t)pl * kUBPlane] = (signed char)dg;
                     q = (q - dg) / 256;

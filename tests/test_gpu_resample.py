@@ -111,6 +111,41 @@ def test_bank_f32_within_one_lsb(zlib, port, cuda, L, M, win, k):
     bank.close()
 
 
+@pytest.mark.parametrize("gain", [1.0, -2.5])
+@pytest.mark.parametrize("L,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0)])
+def test_bank_fast_mode_on_tcgen05(zlib, port, cuda, L, M, k, gain):
+    """ACC_F32 on the tcgen05 kernel (llz_cuda_polybank_umma.cu with three int8 digit planes of the taps: exact products
+    and sums, 22-bit taps, no guard): within 1 LSB of the reference, knife-edge phase exact, ragged two-call stream."""
+    torch = cuda
+    C_ = 3
+    bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L, M, C_, k_override=k, gain=gain, acc=zlib.ACC_F32)
+    bank.set_tiles(zlib.TILES_INT8_TCGEN05)
+    plan = port.resample_plan(L, M, 1, k)
+    n_in = plan.num_in * 2 + 777
+    x = np.stack([port.lcg_s16(n_in, 5000 + c) for c in range(C_)])
+    x[0, :5000] = 32767
+    x[1, 100:4000] = -32768
+    n_out = bank.out_len(n_in)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(C_, n_out + 8, dtype=torch.int16, device="cuda")
+    cut = plan.num_in + 123
+    o1 = bank.run(dx, n_in, cut, dy, n_out + 8)
+    o2 = bank.run(dx.data_ptr() + 2 * cut, n_in, n_in - cut, dy.data_ptr() + 2 * o1, n_out + 8)
+    torch.cuda.synchronize()
+    assert o1 + o2 == n_out
+    got = dy.cpu().numpy()
+    assert not got[:, n_out:].any()
+    want = np.stack([port.resample_run(plan, gain, x[c], n_out) for c in range(C_)]).astype(np.int32)
+    diff = np.abs(got[:, :n_out].astype(np.int32) - want)
+    assert diff.max() <= 1
+    # 22-bit fixed-point taps: the rounding errors of Q taps add up to ~0.02 LSB rms on full-scale noise (Q = 257), and an
+    # output is off by one when that error crosses an integer
+    assert (diff != 0).mean() <= 0.03, (diff != 0).mean()
+    if L >= M:
+        assert not diff[:, ::L].any()
+    bank.close()
+
+
 @pytest.mark.parametrize("gain", [0.5, 1.0, 3.0, -2.0, 0.0])
 def test_gain_and_saturation(zlib, port, cuda, gain):
     torch = cuda
