@@ -18,7 +18,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libllzfilter_cuda.so")
+# LLZLAB_B200_LIB: another build of the same library (profiling builds, tools/umma_trace.py)
+LIB_PATH = os.environ.get("LLZLAB_B200_LIB") or os.path.join(HERE, "libllzfilter_cuda.so")
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 

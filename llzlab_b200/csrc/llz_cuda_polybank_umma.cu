@@ -49,6 +49,8 @@ struct UmmaGeom {
 
 constexpr int kUThreads = 384, kUEpiThreads = 256;
 constexpr int kUTmemCols = 512;
+constexpr int kUParkCol = 384;              // first of the 128 columns that hold the drained sums (two per output)
+static_assert((kUPlanesExact + 1) * kUPB <= kUParkCol, "accumulators overlap the parking columns");
 constexpr int kUMaxStages = 4;
 
 // ---- pre-pass: expanded rows -----------------------------------------------------------------------------------------
@@ -189,11 +191,65 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, i
                  ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                   "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
+}
+
+// Profiling build (make EXTRA_NVFLAGS=-DLLZ_UMMA_TRACE, tools/umma_trace.py): clock stamps of CTA 0's first tiles per
+// role, read back through llz_debug_umma_trace().  Compiled out of the product library.
+#ifdef LLZ_UMMA_TRACE
+__device__ long long g_umma_trace[16 * 16 * 16];
+#define UTRACE(r, n, k) do { if (blockIdx.x == 74 && (n) < 16 && lane == 0) g_umma_trace[((r) * 16 + (n)) * 16 + (k)] = clock64(); } while (0)
+#else
+#define UTRACE(r, n, k) do { } while (0)
+#endif
+
+// The reference's finish step (llz_resample.c:594-601: scale, saturate, truncate toward zero) and the near-integer test of
+// the guard, on the exact integer sum.  The gain is folded into the digit planes (q = round(g * gain * 2^s)), so the
+// output value is T * 2^-s, a dyadic rational: shifted to 32.32 fixed point it splits into floor and fraction with integer
+// instructions only.  (The FP64 version -- I2F.F64, a multiply, F2I.F64 twice per output -- cost more than the tile's
+// MMAs: those conversions issue at a quarter of the DADD rate on B200, tools/probe_conv.cu.)  The bits dropped by the
+// shift matter only within 2^-32 of an integer, which is inside the guard band (exact mode) and below the tap rounding
+// (fast mode).
+__device__ __forceinline__ int umma_finish(uint32_t lo, uint32_t hi, int ush, uint32_t thr32, bool *near_nonzero_integer)
+{
+    const long long T = (long long)(((unsigned long long)hi << 32) | lo);
+    const long long U = ush >= 0 ? (T >> ush) : (T << -ush);   // warp-uniform choice
+    const int nf = (int)(U >> 32);                             // floor(v)
+    const uint32_t f = (uint32_t)U;                            // fraction * 2^32
+    const bool up = (int)f < 0;                                // fraction >= 1/2
+    const int n = nf + (int)up;                                // nearest integer
+    const uint32_t dist = up ? 0u - f : f;
+    *near_nonzero_integer = n != 0 && dist < thr32;
+    const int t = nf + (int)(nf < 0 && f != 0u);               // toward zero
+    return min(max(t, -32768), 32767);
+}
+
+// single-tap output: the integer sum is q * x exactly (q = round(g gain 2^s)); recover x, redo the reference's two
+// products (x * g, then * gain) and finish in FP64 like the other kernels.  One copy of the division for all call sites.
+static __device__ __noinline__ int umma_single_tap(uint32_t lo, uint32_t hi, double scale, double g, double gain)
+{
+    const long long T = (long long)(((unsigned long long)hi << 32) | lo);
+    const double xr = rint((double)T * scale / (g * gain));
+    return poly_finish(__dmul_rn(__dmul_rn(xr, g), gain));
 }
 
 struct UmmaTile {
@@ -289,6 +345,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             const int j0 = T.tile_j * kUJB;
             for (int c = 0; c < T.pt.nchunks; ++c) {
                 mbar_wait(&s_empty[buf], ph ^ 1u);                             // passes at once on the first lap
+                UTRACE(0, (int)(t - t_begin), c);
                 if (leader) {
                     unsigned char *st = stages + (size_t)buf * kUAStage;
                     mbar_expect_tx(&s_full[buf], (uint32_t)kUAStage);
@@ -319,9 +376,11 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             }
             // the epilogue has drained the accumulators of the previous tile (passes at once for the first tile)
             mbar_wait(t_empty, (tile_n & 1u) ^ 1u);
+            UTRACE(1, tile_n, 0);
             asm volatile("tcgen05.fence::after_thread_sync;");
             for (int c = 0; c < T.pt.nchunks; ++c) {
                 mbar_wait(&s_full[buf], ph);
+                UTRACE(1, tile_n, 1 + c);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t sa = smem_u32(stages) + (uint32_t)buf * kUAStage;
                 const uint32_t d_lo = umma_desc_lo(sa), d_hi = umma_desc_lo(sa + kUAPlane);
@@ -346,6 +405,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             }
             if (leader) umma_commit(t_full);                                   // the tile's accumulators are complete
             __syncwarp();
+            UTRACE(1, tile_n, 8);
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
@@ -354,7 +414,6 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         const int m = 32 * q + lane;                           // accumulator row = cycle within the tile
         const int L = a.L, M = a.M, Q = a.ctaps;
         const long long o_end = a.o0 + a.n_out;
-        const double sg = a.umma_scale * a.gain;               // 2^-s * gain: one rounding, like the reference's sum * gain
         uint32_t tile_n = 0;
         for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
             const UmmaTile T = umma_tile(a, geo, t);
@@ -363,33 +422,52 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             const int16_t *xc = a.x ? a.x + (long long)T.ch * a.x_stride : nullptr;
             const int16_t *hc = a.hist ? a.hist + (long long)T.ch * a.hist_len : nullptr;
             int16_t *ych = a.y + (long long)T.ch * a.y_stride;
-            // single-tap (knife-edge) phases of this half tile, one bit per phase
-            const unsigned st_mask = __ballot_sync(0xffffffffu, lane < pbv && __ldg(a.single_tap + l0 + lane) >= 0);
+            // Single-tap (knife-edge) phases of this half tile, one bit per phase; lane e keeps the tap of phase l0 + e.  Such
+            // an output is the reference's x * g * gain, two roundings (g = 1 - 2^-53 for an L-th band prototype: x - 1 after
+            // truncation for positive x).  The integer sum of such a row is q * x exactly, q = round(g gain 2^s), so x is
+            // recovered from it and the two products are redone in the reference's order -- no memory access.  (Fetching x
+            // and g per output from global memory made the warps that own phase 0 the slowest part of the whole kernel:
+            // 8700 cycles of finish per tile against 1800.)  A tap too small for the division to recover x exactly keeps
+            // the slow path.
+            const int my_st = lane < pbv ? __ldg(a.single_tap + l0 + lane) : -1;
+            const double my_g = my_st >= 0 ? __ldg(a.cbank + (long long)(l0 + lane) * Q + my_st) : 0.0;
+            const unsigned st_mask = __ballot_sync(0xffffffffu, my_st >= 0);
+            const unsigned st_slow = __ballot_sync(0xffffffffu, my_st >= 0 && !(fabs(my_g * a.gain) >= a.umma_scale * 1048576.0));
 
+            UTRACE(warp - 2, tile_n, 0);
             mbar_wait(t_full, tile_n & 1u);
+            UTRACE(warp - 2, tile_n, 1);
             __syncwarp();                                      // the lanes leave the wait loop one by one; tcgen05.ld is .aligned
             asm volatile("tcgen05.fence::after_thread_sync;");
 
-            // ---- drain: accumulators -> one double per output ----
-            double v[32];
+            // ---- drain: accumulators -> one 64-bit integer per output, parked in the 128 TMEM columns the accumulators
+            // leave free (two columns per output).  Parking them in registers instead needs the whole pass unrolled 32 times;
+            // that code (and the three other roles' loops) no longer fit the instruction cache, and clock stamps showed
+            // the pass taking 60 cycles per output.
             const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + 32 * h;
-#pragma unroll
+            const uint32_t tpark = tmem + ((uint32_t)(32 * q) << 16) + kUParkCol + 64 * h;
+#pragma unroll 1
             for (int cg = 0; cg < 4; ++cg) {
                 int acc[PLANES + 1][8];
 #pragma unroll
                 for (int d = 0; d <= PLANES; ++d) tmem_ld8(trow + kUPB * d + 8 * cg, acc[d]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t park[16];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    long long T64 = (long long)acc[0][e];
+                    long long t64 = (long long)acc[0][e];
 #pragma unroll
-                    for (int d = 1; d <= PLANES; ++d) T64 += (long long)acc[d][e] << (8 * d);
-                    v[8 * cg + e] = __dmul_rn((double)T64, sg);
+                    for (int d = 1; d <= PLANES; ++d) t64 += (long long)acc[d][e] << (8 * d);
+                    park[2 * e] = (uint32_t)t64;
+                    park[2 * e + 1] = (uint32_t)(t64 >> 32);
                 }
+                tmem_st16(tpark + 16 * cg, park);
             }
-            // the accumulators are in registers: the issuer may start the next tile
+            // the accumulators have been read: the issuer may start the next tile
             asm volatile("tcgen05.fence::before_thread_sync;");
             mbar_arrive(t_empty);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            UTRACE(warp - 2, tile_n, 2);
 
             // ---- finish ----
             const long long o_row = j * (long long)L + l0;     // output index of this thread's first phase
@@ -398,34 +476,49 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             int16_t *yrow = ych + (o_row - a.o0);
             const bool vec_ok = interior && ((reinterpret_cast<uintptr_t>(yrow) & 15u) == 0);
             unsigned hits = 0;                                 // near-integer outputs of this row, one bit per phase
-            uint32_t packed[16];
+            const unsigned st_fast = st_mask & ~st_slow;
+#pragma unroll 1
+            for (int cg = 0; cg < 4; ++cg) {
+                uint32_t park[16];
+                tmem_ld16(tpark + 16 * cg, park);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int y[8];
+                unsigned hit8 = 0;
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-                if (GUARD) {
-                    if (poly_near_nonzero_integer(v[e], a.imma_thr)) hits |= 1u << e;
-                    if (poly_near_nonzero_integer(v[e + 1], a.imma_thr)) hits |= 2u << e;
+                for (int e = 0; e < 8; ++e) {
+                    bool hit;
+                    y[e] = umma_finish(park[2 * e], park[2 * e + 1], a.umma_ush, a.umma_thr32, &hit);
+                    if (GUARD) hit8 |= (unsigned)hit << e;
                 }
-                packed[e >> 1] = (uint32_t)(uint16_t)poly_finish(v[e]) | ((uint32_t)(uint16_t)poly_finish(v[e + 1]) << 16);
-            }
-            if (vec_ok) {
+                if ((st_fast >> (8 * cg)) & 255u) {            // warp-uniform, one tile in L / 64
 #pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    reinterpret_cast<uint4 *>(yrow)[w] = make_uint4(packed[4 * w], packed[4 * w + 1], packed[4 * w + 2], packed[4 * w + 3]);
-            } else if (row_in) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const long long o = o_row + e;
-                    const bool valid = e < pbv && o >= a.o0 && o < o_end;
-                    if (valid) ych[o - a.o0] = (int16_t)(packed[e >> 1] >> (16 * (e & 1)));
-                    else hits &= ~(1u << e);
+                    for (int e = 0; e < 8; ++e)
+                        if ((st_fast >> (8 * cg + e)) & 1u)
+                            y[e] = umma_single_tap(park[2 * e], park[2 * e + 1], a.umma_scale, __shfl_sync(0xffffffffu, my_g, 8 * cg + e), a.gain);
                 }
+                uint32_t packed[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) packed[e >> 1] = (uint32_t)(uint16_t)y[e] | ((uint32_t)y[e + 1] << 16);
+                if (vec_ok) {
+                    reinterpret_cast<uint4 *>(yrow)[cg] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                } else if (row_in) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int l = 8 * cg + e;
+                        const long long o = o_row + l;
+                        const bool valid = l < pbv && o >= a.o0 && o < o_end;
+                        if (valid) ych[o - a.o0] = (int16_t)(packed[e >> 1] >> (16 * (e & 1)));
+                        else hit8 &= ~(1u << e);
+                    }
+                }
+                hits |= hit8 << (8 * cg);
             }
             if (!row_in) hits = 0;
 
             // knife-edge phases (one tap, 1 - 2^-53 for the L-th band prototype): one exact FP64 product per output
             hits &= ~st_mask;
-            if (row_in) {
-                unsigned sm = st_mask;
+            if (row_in && st_slow) {
+                unsigned sm = st_slow;
                 while (sm) {
                     const int l = __ffs((int)sm) - 1;
                     sm &= sm - 1;
@@ -436,6 +529,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                     ych[o - a.o0] = poly_finish(__dmul_rn(__dmul_rn((double)poly_sample(a, xc, hc, base - st), a.cbank[(long long)(l0 + l) * Q + st]), a.gain));
                 }
             }
+            UTRACE(warp - 2, tile_n, 3);
             if (!GUARD) continue;
             __syncwarp();
 
@@ -577,3 +671,10 @@ int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
 }
 
 }  // namespace llz
+
+#ifdef LLZ_UMMA_TRACE
+extern "C" int llz_debug_umma_trace(long long *host_out)
+{
+    return cudaMemcpyFromSymbol(host_out, llz::g_umma_trace, sizeof(llz::g_umma_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -40,7 +40,7 @@ Tunables &tunables()
         e = getenv("LLZ_FFT16K_SKEW");
         v.fft16k_skew = (e && *e) ? atoi(e) : -1;
         e = getenv("LLZ_UMMA_SLAB_MB");
-        v.umma_slab_mib = (e && atof(e) >= 1.0) ? atof(e) : 96.0;
+        v.umma_slab_mib = (e && atof(e) >= 1.0) ? atof(e) : 256.0;
         e = getenv("LLZ_FIR_ALGO");
         v.fir_algo = (e && strcmp(e, "direct") == 0) ? LLZ_CUDA_FIR_ALGO_DIRECT
                      : (e && strcmp(e, "fft") == 0)  ? LLZ_CUDA_FIR_ALGO_FFT : LLZ_CUDA_FIR_ALGO_AUTO;

@@ -484,6 +484,7 @@ struct PolyBank {
     signed char *d_umma_tiles = nullptr;   // the same digit planes in the tcgen05 kernel's layout (llz_cuda_polybank_umma.cu)
     int umma_nchunks = 0;
     int umma_planes = 0, umma_shift = 0;   // digit planes (5 exact / 3 fast) and the scale 2^-shift of those tables
+    double umma_eps = 0.0;                 // bound on |sum_k (g gain - q 2^-shift) x| for |x| <= 32768
     unsigned char *d_umma_rows = nullptr;  // workspace: expanded input rows of one slab
     size_t umma_rows_cap = 0;
     signed char *d_imma_tiles = nullptr;   // int8 digit planes of the bank (llz_cuda_polybank_imma.cu)
@@ -605,22 +606,21 @@ int poly_upload_plan(PolyBank *b)
         b->imma_planes = 5;
         b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->imma_planes, &tiles, &b->imma_shift, &b->imma_eps);
         if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
-        // the same digits for tcgen05.mma.kind::i8 (same scale 2^-s and rounding bound: both builders round g * 2^38)
-        std::vector<signed char> utiles;
-        int ushift = 0;
-        double ueps = 0.0;
-        b->umma_planes = llz::kUPlanesExact;
-        b->umma_nchunks = llz::poly_umma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->umma_planes, &utiles, &ushift, &ueps);
-        if (b->umma_nchunks > 0 && (ushift != b->imma_shift || b->imma_nchunks <= 0)) b->umma_nchunks = 0;
-        if (b->umma_nchunks > 0 && upload(&b->d_umma_tiles, utiles)) return -1;
-        b->umma_shift = ushift;
     }
-    if (b->acc == LLZ_CUDA_ACC_F32 && L >= 16 && p.shift == 0 && p.frame_len == 0) {
-        // fast mode on tcgen05: three digit planes (22-bit taps), exact products and sums, no guard
+    if ((b->acc == LLZ_CUDA_ACC_F64 || b->acc == LLZ_CUDA_ACC_F32) && L >= 16 && p.shift == 0 && p.frame_len == 0 &&
+        b->gain != 0.0 && isfinite(b->gain)) {
+        // tcgen05.mma.kind::i8 (llz_cuda_polybank_umma.cu): digit planes of g * gain -- five for the exact mode (38-bit taps,
+        // two-level guard), three for the fast mode (22-bit taps, no guard).  With the gain inside the taps the output
+        // value is (integer sum) * 2^-s and the kernel finishes it with integer instructions.
+        std::vector<double> cbg(cb);
+        for (double &v : cbg) v *= b->gain;
         std::vector<signed char> utiles;
-        double ueps = 0.0;
-        b->umma_planes = llz::kUPlanesFast;
-        b->umma_nchunks = llz::poly_umma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->umma_planes, &utiles, &b->umma_shift, &ueps);
+        b->umma_planes = b->acc == LLZ_CUDA_ACC_F64 ? llz::kUPlanesExact : llz::kUPlanesFast;
+        double qsum = 0.0;
+        b->umma_nchunks = llz::poly_umma_build_tables(cbg.data(), (int)L, p.M * b->rep, (int)Q, b->umma_planes, &utiles, &b->umma_shift,
+                                                      &b->umma_eps, &qsum);
+        // the 32.32 fixed-point form of the largest possible sum must fit 64 bits
+        if (b->umma_nchunks > 0 && ldexp(qsum * 32768.0, 32 - b->umma_shift) >= ldexp(1.0, 62)) b->umma_nchunks = 0;
         if (b->umma_nchunks > 0 && upload(&b->d_umma_tiles, utiles)) return -1;
     }
     std::vector<int> order(p.order, p.order + Q), single(L);
@@ -794,6 +794,10 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
             a.umma_nchunks = b->umma_nchunks;
             a.umma_planes = b->umma_planes;
             a.umma_scale = ldexp(1.0, -b->umma_shift);
+            a.umma_ush = b->umma_shift - 32;
+            // first-level band: the (scaled) FP64 band, the taps' rounding bound, the bits the 32.32 form drops
+            const double thr = b->guard_thr * b->guard_scale + 1.001 * b->umma_eps + ldexp(1.0, -31);
+            a.umma_thr32 = thr >= 0.4999 ? 0x7fffffffu : (unsigned)ceil(ldexp(thr, 32)) + 2u;
             a.umma_rows = b->d_umma_rows;
             a.umma_slab_cycles = (int)slab;
         }

@@ -74,8 +74,11 @@ LLZ_UMMA_HD inline int umma_b_offset(int n, int kk)
 }
 
 // Host: the bank [L][Q] as int8 digit planes, [phase tile][chunk][plane][64 x 128 swizzled].  Returns the chunks per
-// tile (0 when the bank cannot be split); *shift = s with g ~ q * 2^-s, *eps = bound on |sum_k (g - q 2^-s) x| for |x| <= 32768.
-inline int poly_umma_build_tables(const double *cb, int L, int M, int Q, int planes, std::vector<signed char> *out, int *shift, double *eps)
+// tile (0 when the bank cannot be split); *shift = s with g ~ q * 2^-s, *eps = bound on |sum_k (g - q 2^-s) x| for |x| <= 32768,
+// *qsum_max = the largest sum_k |q| of a row (the integer sum of a row is below 32768 times that).  The caller passes the
+// taps already multiplied by the gain.
+inline int poly_umma_build_tables(const double *cb, int L, int M, int Q, int planes, std::vector<signed char> *out, int *shift, double *eps,
+                                  double *qsum_max)
 {
     double gmax = 0.0;
     for (size_t i = 0; i < (size_t)L * Q; ++i) gmax = fmax(gmax, fabs(cb[i]));
@@ -110,15 +113,19 @@ inline int poly_umma_build_tables(const double *cb, int L, int M, int Q, int pla
         }
     }
     *shift = s;
-    double worst = 0.0;                                        // the taps' actual rounding errors, worst row
+    double worst = 0.0, qsum = 0.0;                            // the taps' actual rounding errors and sum |q|, worst row
     for (int l = 0; l < L; ++l) {
-        double row = 0.0;
+        double row = 0.0, qs = 0.0;
         for (int k = 0; k < Q; ++k) {
             const double g = cb[(size_t)l * Q + k];
-            row += fabs(g - ldexp((double)llrint(ldexp(g, s)), -s));
+            const double qd = (double)llrint(ldexp(g, s));
+            row += fabs(g - ldexp(qd, -s));
+            qs += fabs(qd);
         }
         worst = fmax(worst, row);
+        qsum = fmax(qsum, qs);
     }
+    *qsum_max = qsum;
     *eps = 32768.0 * worst * (1.0 + 1e-9) + (double)Q * 32768.0 * ldexp(1.0, -(s + 40));
     return nchunks;
 }
