@@ -796,12 +796,6 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if (a.acc == LLZ_CUDA_ACC_F32) {
         // fast mode: exact-product fp16 split on the tensor cores unless the handle asks for the FFMA tile
         // (llz_cuda_resample_bank_set_tiles).
-        // large calls: a three-digit integer evaluation as tcgen05.mma.kind::i8 (llz_cuda_polybank_umma.cu); the shim
-        // selects it by filling a.umma_rows
-        if (a.umma_rows && (a.tiles == LLZ_CUDA_TILES_AUTO || a.tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
-            const int rc = poly_bank_umma_launch(a, n_channels, stream);
-            if (rc != 0) return rc;
-        }
         if (a.cbankT16h && a.cbankT16l && a.tiles != LLZ_CUDA_TILES_CUDA_CORE) {
             const int rc = launch_bank_hmma<16>(a, n_channels, stream);
             if (rc != 0) return rc;
@@ -813,12 +807,7 @@ int poly_bank_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     // f64: exact integer evaluation on the INT8 tensor cores (llz_cuda_polybank_imma.cu) unless the handle asks for
     // another tile family (llz_cuda_resample_bank_set_tiles) or the span of a tile does not fit beside its stages
     // (extreme M / L)
-    // large calls: the same integer evaluation as tcgen05.mma.kind::i8 with TMEM accumulators (llz_cuda_polybank_umma.cu);
-    // the shim selects it (workspace, slab size) by filling a.umma_rows
-    if (a.umma_rows && (a.tiles == LLZ_CUDA_TILES_AUTO || a.tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
-        const int rc = poly_bank_umma_launch(a, n_channels, stream);
-        if (rc != 0) return rc;
-    }
+    // (large calls never get here: the shim runs them on the tcgen05 kernel, llz_cuda_polybank_umma.cu)
     if (a.imma_tiles && (a.tiles == LLZ_CUDA_TILES_AUTO || a.tiles == LLZ_CUDA_TILES_INT8 || a.tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
         const int rc = poly_bank_imma_launch(a, n_channels, stream);
         if (rc != 0) return rc;

@@ -8,13 +8,14 @@
 // 64-phase tile per CTA, M = 128, N = 64, K = 32 bytes per instruction, six accumulators of 64 TMEM columns.
 //
 //   * A operand (samples).  The MMA wants K-major rows; row j of a tile is the run of input bytes starting at sample
-//     j*M + c_lo - (Q-1), i.e. at an arbitrary byte offset, and TMA traps on an unaligned innermost box coordinate
-//     (tools/probe_umma_i8.cu).  A pre-pass (poly_expand_rows_kernel) therefore writes the input once as "expanded rows":
-//     one row of RL = c_hi_max + Q bytes per output cycle and byte plane, so that every row starts aligned and the operand
-//     of a (phase tile, chunk) is ONE box {128 bytes x 128 rows} of a plain 4-D tensor, landing in shared memory as
-//     sixteen SWIZZLE_128B atoms.  The pre-pass also resolves history, zeros beyond the input and the call's ragged
-//     ends, so the tile kernel has no edge cases on its input side.  The call is cut into slabs of cycles so that the
-//     expanded rows of a slab stay small (tunable; they are re-read by the five phase tiles of a cycle tile).
+//     j*M + c_lo - (Q-1), and TMA traps on an unaligned row start or innermost box coordinate (tools/probe_umma_i8.cu).
+//     The kernel therefore runs the bank replicated r times (llz_umma_tables.h: L' = r L, M' = r M, the same outputs) with
+//     M' a multiple of 16, which puts every row start on a 16-byte boundary of the PLAIN byte planes of the input: the
+//     operand of a (phase tile, chunk) is one box {128 bytes x 128 rows} of a 4-D tensor map whose rows overlap (row
+//     stride M' bytes), landing in shared memory as sixteen SWIZZLE_128B atoms.  A pre-pass (poly_split_planes_kernel)
+//     splits the int16 input of a slab into its low and high byte planes once -- 2 bytes written per sample -- and
+//     resolves history, zeros beyond the input and the call's ragged ends, so the tile kernel has no edge cases on its
+//     input side.  (The first versions wrote one expanded row per cycle instead: 5.7 bytes per sample for config C4.)
 //   * B operand (taps): host-built digit planes in the same swizzled layout (llz_umma_tables.h), one bulk copy per chunk.
 //   * Warp roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one thread) and TMEM owner, warps 4-11 =
 //     epilogue (tcgen05.ld 32x32b: one accumulator row = one cycle per thread, 32 consecutive phases = 64 contiguous
@@ -43,7 +44,7 @@ struct UmmaGeom {
     int n_cycles;                  // cycles of the slab = rows of the expanded operand
     int n_cycle_tiles, n_phase_tiles, n_channels;
     int nchunk_max;                // chunks per phase tile in the tap tables
-    int row_len;                   // RL
+    long long plane_len;           // bytes of one channel's byte plane of the slab (a multiple of 16)
     int n_stages;                  // A-operand stages that fit beside the resident taps (2..4)
 };
 
@@ -53,91 +54,40 @@ constexpr int kUParkCol = 384;              // first of the 128 columns that hol
 static_assert((kUPlanesExact + 1) * kUPB <= kUParkCol, "accumulators overlap the parking columns");
 constexpr int kUMaxStages = 4;
 
-// ---- pre-pass: expanded rows -----------------------------------------------------------------------------------------
-// rows[plane][channel][j][b] = byte `plane` of X((jc0 + j)*M - (Q-1) + b),  X = the stream sample of llz_poly_kernels.h
-// One CTA writes kERows consecutive rows of one channel: its contiguous input span arrives by a bulk copy
-// (poly_stage_span: history, zeros and ragged ends are resolved there), is split into two byte planes in shared
-// memory, every lane then cuts one row out of the planes 16 bytes at a time (funnel shifts: rows start at any byte
-// offset), and the block of rows -- contiguous in the workspace -- leaves by one bulk store per plane.
-constexpr int kERows = 32, kEThreads = 256;
+// ---- pre-pass: byte planes --------------------------------------------------------------------------------------------
+// planes[plane][channel][e] = byte `plane` of X(jc0*M - (Q-1) + e),  e < plane_len,  X = the stream sample of
+// llz_poly_kernels.h.  One CTA splits kSplitSpan consecutive samples of one channel: the span arrives by a bulk copy
+// (poly_stage_span: history, zeros and ragged ends are resolved there) and leaves as two coalesced byte streams.
+constexpr int kSplitSpan = 8192, kSplitThreads = 256;
 
-struct ExpandSmem {
-    int raw_bytes, plane_bytes, total;
-};
-__host__ __device__ inline ExpandSmem expand_smem(int M, int RL)
+__global__ void __launch_bounds__(kSplitThreads)
+poly_split_planes_kernel(PolyLaunch a, UmmaGeom geo, unsigned char *planes)
 {
-    ExpandSmem e;
-    const int need_cap = (kERows - 1) * M + RL;
-    e.raw_bytes = ((need_cap + 16) * 2 + 15) & ~15;
-    e.plane_bytes = (need_cap + 8 + 15) & ~15;                 // the funnel reads one word beyond the last byte
-    e.total = e.raw_bytes + 2 * e.plane_bytes + 2 * kERows * RL;
-    return e;
-}
-
-__global__ void __launch_bounds__(kEThreads)
-poly_expand_rows_kernel(PolyLaunch a, UmmaGeom geo, unsigned char *rows)
-{
-    extern __shared__ __align__(128) unsigned char esm[];
+    __shared__ __align__(16) int16_t raw[kSplitSpan + 16];
     __shared__ __align__(8) uint64_t bar;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int ch = blockIdx.y;
-    const int j_first = blockIdx.x * kERows;
-    const int nrows = min(kERows, geo.n_cycles - j_first);
-    const int RL = geo.row_len, M = a.M;
-    const ExpandSmem lay = expand_smem(M, RL);
-    int16_t *raw = reinterpret_cast<int16_t *>(esm);
-    unsigned char *plane[2] = {esm + lay.raw_bytes, esm + lay.raw_bytes + lay.plane_bytes};
-    unsigned char *outp[2] = {plane[1] + lay.plane_bytes, plane[1] + lay.plane_bytes + kERows * RL};
+    const long long e0 = (long long)blockIdx.x * kSplitSpan;
+    const int need = (int)min((long long)kSplitSpan, geo.plane_len - e0);
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
-    const long long S0 = (geo.jc0 + j_first) * (long long)M - (a.ctaps - 1);
-    const int need = (nrows - 1) * M + RL;
+    const long long S0 = geo.jc0 * (long long)a.M - (a.ctaps - 1) + e0;
     bool bulk;
-    const int off = poly_stage_span<kEThreads>(a, xc, hc, S0, need, raw, &bar, tid, &bulk);
+    const int off = poly_stage_span<kSplitThreads>(a, xc, hc, S0, need, raw, &bar, tid, &bulk);
     __syncthreads();
     if (bulk) mbar_wait(&bar, 0);
-    // byte planes: plane[p][e] = byte p of X(S0 + e)
-    for (int e = 4 * tid; e < need + 4; e += 4 * kEThreads) {
+    unsigned char *lo = planes + (size_t)ch * geo.plane_len + e0;               // plane_len and kSplitSpan are multiples of 16
+    unsigned char *hi = lo + (size_t)geo.n_channels * geo.plane_len;
+    for (int e = 4 * tid; e < need; e += 4 * kSplitThreads) {                   // need is a multiple of 16
         uint32_t lw = 0, hw = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const uint32_t v = (e + b < need) ? (uint32_t)(uint16_t)raw[off + e + b] : 0u;
+            const uint32_t v = (uint32_t)(uint16_t)raw[off + e + b];
             lw |= (v & 255u) << (8 * b);
             hw |= (v >> 8) << (8 * b);
         }
-        *reinterpret_cast<uint32_t *>(plane[0] + e) = lw;
-        *reinterpret_cast<uint32_t *>(plane[1] + e) = hw;
-    }
-    __syncthreads();
-    // lane = row: row r starts at byte r*M of the planes
-    const int vec_per_row = RL >> 4;
-    if (lane < nrows) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(plane[p]);
-            for (int c = warp; c < vec_per_row; c += kEThreads / 32) {
-                const int b = lane * M + 16 * c;
-                const int w = b >> 2, sh = (b & 3) * 8;
-                uint32_t x[5];
-#pragma unroll
-                for (int i = 0; i < 5; ++i) x[i] = src[w + i];
-                uint4 o;
-                o.x = __funnelshift_r(x[0], x[1], sh); o.y = __funnelshift_r(x[1], x[2], sh);
-                o.z = __funnelshift_r(x[2], x[3], sh); o.w = __funnelshift_r(x[3], x[4], sh);
-                *reinterpret_cast<uint4 *>(outp[p] + lane * RL + 16 * c) = o;
-            }
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-        const size_t plane_stride = (size_t)geo.n_channels * geo.n_cycles * RL;
-        unsigned char *dst = rows + ((size_t)ch * geo.n_cycles + j_first) * RL;
-        const uint32_t bytes = (uint32_t)(nrows * RL);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(outp[0])), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + plane_stride), "r"(smem_u32(outp[1])), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads of the store
+        *reinterpret_cast<uint32_t *>(lo + e) = lw;
+        *reinterpret_cast<uint32_t *>(hi + e) = hw;
     }
 }
 
@@ -599,9 +549,11 @@ EncodeTiledFn encode_tiled()
 
 }  // namespace
 
+// bytes of the byte-plane workspace for a slab of `cycles` cycles (of the replicated bank a.L / a.M)
 size_t poly_bank_umma_rows_bytes(const PolyLaunch &a, int n_channels, long long cycles)
 {
-    return (size_t)2 * n_channels * (size_t)cycles * umma_row_len(a.L, a.M, a.ctaps);
+    const long long plane_len = ((cycles * a.M + umma_row_extent(a.L, a.M, a.ctaps)) + 15) & ~15LL;
+    return (size_t)2 * n_channels * (size_t)plane_len;
 }
 
 namespace {
@@ -613,7 +565,8 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if (!enc) { llz_set_error("cuTensorMapEncodeTiled is not available from this driver"); return -1; }
     const int sms = device_sm_count();
     if (sms <= 0) return -1;
-    const int RL = umma_row_len(a.L, a.M, a.ctaps);
+    if (a.M % 16 != 0) return 0;                               // rows must start on 16-byte boundaries (umma_replication)
+    const int ext = umma_row_extent(a.L, a.M, a.ctaps);
     const long long jc_first = a.o0 / a.L, jc_last = (a.o0 + a.n_out - 1) / a.L;
     // shared memory: the resident taps, then as many 32 KB sample stages as fit (at least two)
     constexpr size_t kSmemMax = 227 * 1024, kBarBytes = 128;
@@ -622,11 +575,8 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     int n_stages = (int)((kSmemMax - kBarBytes - 1024 - taps_bytes) / kUAStage);
     if (n_stages > kUMaxStages) n_stages = kUMaxStages;
     const size_t smem = taps_bytes + (size_t)n_stages * kUAStage + kBarBytes;
-    const ExpandSmem elay = expand_smem(a.M, RL);
-    if (elay.total > 200 * 1024) return 0;
     auto kern = poly_bank_umma_kernel<PLANES, GUARD>;
     LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LLZ_CUDA_TRY(cudaFuncSetAttribute(poly_expand_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, elay.total));
     for (long long jc0 = jc_first; jc0 <= jc_last; jc0 += a.umma_slab_cycles) {
         UmmaGeom geo{};
         geo.jc0 = jc0;
@@ -635,16 +585,17 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         geo.n_phase_tiles = (a.L + kUPB - 1) / kUPB;
         geo.n_channels = n_channels;
         geo.nchunk_max = a.umma_nchunks;
-        geo.row_len = RL;
         geo.n_stages = n_stages;
-        // 1. expanded rows of the slab
-        dim3 egrid((unsigned)((geo.n_cycles + kERows - 1) / kERows), (unsigned)n_channels);
-        poly_expand_rows_kernel<<<egrid, kEThreads, (size_t)elay.total, stream>>>(a, geo, a.umma_rows);
+        // rows of a partial last cycle tile are read too (and discarded): the plane covers whole tiles
+        geo.plane_len = (((long long)geo.n_cycle_tiles * kUJB * a.M + ext) + 15) & ~15LL;
+        // 1. byte planes of the slab
+        dim3 sgrid((unsigned)((geo.plane_len + kSplitSpan - 1) / kSplitSpan), (unsigned)n_channels);
+        poly_split_planes_kernel<<<sgrid, kSplitThreads, 0, stream>>>(a, geo, a.umma_rows);
         LLZ_CUDA_TRY(cudaGetLastError());
-        // 2. the tensor map over them: [plane][channel][cycle][byte]
+        // 2. the tensor map over them: [plane][channel][cycle][byte], rows overlapping (stride M bytes)
         CUtensorMap map;
-        const cuuint64_t dims[4] = {(cuuint64_t)RL, (cuuint64_t)geo.n_cycles, (cuuint64_t)n_channels, 2};
-        const cuuint64_t strides[3] = {(cuuint64_t)RL, (cuuint64_t)RL * geo.n_cycles, (cuuint64_t)RL * geo.n_cycles * n_channels};
+        const cuuint64_t dims[4] = {(cuuint64_t)ext, (cuuint64_t)geo.n_cycle_tiles * kUJB, (cuuint64_t)n_channels, 2};
+        const cuuint64_t strides[3] = {(cuuint64_t)a.M, (cuuint64_t)geo.plane_len, (cuuint64_t)geo.plane_len * n_channels};
         const cuuint32_t box[4] = {(cuuint32_t)kUKC, (cuuint32_t)kUJB, 1, 1}, estr[4] = {1, 1, 1, 1};
         const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, a.umma_rows, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -660,7 +611,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 
 }  // namespace
 
-// 1 = launched, 0 = not applicable, -1 = error
+// 1 = launched, 0 = not applicable, -1 = error.  a.L / a.M / a.cbank / a.single_tap describe the REPLICATED bank.
 int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
     if (!a.umma_tiles || a.umma_nchunks <= 0 || !a.umma_rows || a.umma_slab_cycles <= 0) return 0;

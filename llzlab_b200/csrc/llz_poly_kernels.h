@@ -65,7 +65,7 @@ struct PolyLaunch {
     double umma_scale;         // g * gain ~ q * umma_scale for those digits (the gain is folded into the tables)
     int umma_ush;              // sum >> umma_ush (<< when negative) = the output value in 32.32 fixed point
     unsigned umma_thr32;       // first-level guard band in units of 2^-32 (exact mode)
-    unsigned char *umma_rows;  // workspace: poly_bank_umma_rows_bytes(a, channels, umma_slab_cycles) bytes
+    unsigned char *umma_rows;  // workspace (byte planes of a slab): poly_bank_umma_rows_bytes(a, channels, umma_slab_cycles) bytes
     int umma_slab_cycles;      // cycles per slab (multiple of 128)
 };
 

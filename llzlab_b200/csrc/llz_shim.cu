@@ -485,6 +485,9 @@ struct PolyBank {
     int umma_nchunks = 0;
     int umma_planes = 0, umma_shift = 0;   // digit planes (5 exact / 3 fast) and the scale 2^-shift of those tables
     double umma_eps = 0.0;                 // bound on |sum_k (g gain - q 2^-shift) x| for |x| <= 32768
+    int urep = 1;                          // the tcgen05 kernel sees the bank replicated urep times (llz_umma_tables.h)
+    double *d_cbank_u = nullptr;           // [L urep][Q]: the replicated bank (guard recompute, knife-edge taps)
+    int *d_single_u = nullptr;             // [L urep]
     unsigned char *d_umma_rows = nullptr;  // workspace: expanded input rows of one slab
     size_t umma_rows_cap = 0;
     signed char *d_imma_tiles = nullptr;   // int8 digit planes of the bank (llz_cuda_polybank_imma.cu)
@@ -535,6 +538,8 @@ void poly_destroy(PolyBank *b)
     cudaFree(b->d_imma_tiles);
     cudaFree(b->d_umma_tiles);
     cudaFree(b->d_umma_rows);
+    cudaFree(b->d_cbank_u);
+    cudaFree(b->d_single_u);
     cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     if (b->pinned_in) cudaFreeHost(b->pinned_in);
@@ -607,21 +612,38 @@ int poly_upload_plan(PolyBank *b)
         b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->imma_planes, &tiles, &b->imma_shift, &b->imma_eps);
         if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
     }
-    if ((b->acc == LLZ_CUDA_ACC_F64 || b->acc == LLZ_CUDA_ACC_F32) && L >= 16 && p.shift == 0 && p.frame_len == 0 &&
-        b->gain != 0.0 && isfinite(b->gain)) {
+    if ((b->acc == LLZ_CUDA_ACC_F64 || b->acc == LLZ_CUDA_ACC_F32) && p.shift == 0 && p.frame_len == 0 &&
+        b->gain != 0.0 && isfinite(b->gain) && (L0 > 1 || p.single_tap[0] < 0)) {
         // tcgen05.mma.kind::i8 (llz_cuda_polybank_umma.cu): digit planes of g * gain -- five for the exact mode (38-bit taps,
         // two-level guard), three for the fast mode (22-bit taps, no guard).  With the gain inside the taps the output
-        // value is (integer sum) * 2^-s and the kernel finishes it with integer instructions.
-        std::vector<double> cbg(cb);
-        for (double &v : cbg) v *= b->gain;
-        std::vector<signed char> utiles;
-        b->umma_planes = b->acc == LLZ_CUDA_ACC_F64 ? llz::kUPlanesExact : llz::kUPlanesFast;
-        double qsum = 0.0;
-        b->umma_nchunks = llz::poly_umma_build_tables(cbg.data(), (int)L, p.M * b->rep, (int)Q, b->umma_planes, &utiles, &b->umma_shift,
-                                                      &b->umma_eps, &qsum);
-        // the 32.32 fixed-point form of the largest possible sum must fit 64 bits
-        if (b->umma_nchunks > 0 && ldexp(qsum * 32768.0, 32 - b->umma_shift) >= ldexp(1.0, 62)) b->umma_nchunks = 0;
-        if (b->umma_nchunks > 0 && upload(&b->d_umma_tiles, utiles)) return -1;
+        // value is (integer sum) * 2^-s and the kernel finishes it with integer instructions.  The kernel sees the bank
+        // replicated urep times (rows of the sample operand then start on 16-byte boundaries, llz_umma_tables.h) -- also
+        // the decimating banks (L = 1), which become 64 phases of a cycle of 64 M samples.
+        b->urep = llz::umma_replication((int)L0, p.M);
+        const size_t UL = L0 * (size_t)b->urep;
+        const long long UM = (long long)p.M * b->urep;
+        const double cspan = 64.0 * p.M / (double)L0;          // sample span of a 64-phase tile: padded work (Q + cspan) / Q
+        if (UL * Q * sizeof(double) <= (64u << 20) && UM < (1LL << 24) && (Q + cspan) / Q <= 4.0) {
+            std::vector<double> cbu(UL * Q), cbg(UL * Q);
+            std::vector<int> single_u(UL);
+            for (size_t r = 0; r < UL; ++r) {
+                single_u[r] = p.single_tap[r % L0];
+                for (size_t k = 0; k < Q; ++k) {
+                    cbu[r * Q + k] = p.cbank[(r % L0) * Q + k];
+                    cbg[r * Q + k] = cbu[r * Q + k] * b->gain;
+                }
+            }
+            std::vector<signed char> utiles;
+            b->umma_planes = b->acc == LLZ_CUDA_ACC_F64 ? llz::kUPlanesExact : llz::kUPlanesFast;
+            double qsum = 0.0;
+            b->umma_nchunks = llz::poly_umma_build_tables(cbg.data(), (int)UL, (int)UM, (int)Q, b->umma_planes, &utiles, &b->umma_shift,
+                                                          &b->umma_eps, &qsum);
+            // the 32.32 fixed-point form of the largest possible sum must fit 64 bits
+            if (b->umma_nchunks > 0 && ldexp(qsum * 32768.0, 32 - b->umma_shift) >= ldexp(1.0, 62)) b->umma_nchunks = 0;
+            if (b->umma_nchunks > 0 && utiles.size() > (256u << 20)) b->umma_nchunks = 0;
+            if (b->umma_nchunks > 0 && (upload(&b->d_umma_tiles, utiles) || upload(&b->d_cbank_u, cbu) || upload(&b->d_single_u, single_u)))
+                return -1;
+        }
     }
     std::vector<int> order(p.order, p.order + Q), single(L);
     for (size_t r = 0; r < L; ++r) single[r] = p.single_tap[r % L0];
@@ -769,19 +791,25 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
     a.imma_scale = ldexp(1.0, -b->imma_shift);
     // first-level band of the integer evaluation: the (scaled) FP64 band plus the taps' rounding bound
     a.imma_thr = b->guard_thr * b->guard_scale + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
-    // tcgen05 exact mode for calls that fill the machine (a frame-sized call keeps the mma.sync tiles: no pre-pass,
+    // tcgen05 kernel for calls that fill the machine (a frame-sized call keeps the mma.sync / sliding tiles: no pre-pass,
     // no workspace, lower latency); LLZ_CUDA_TILES_INT8_TCGEN05 forces it
+    bool launched = false;
     if (b->d_umma_tiles && outs > 0 && (b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
-        const long long cycles = (a.o0 + outs - 1) / a.L - a.o0 / a.L + 1;
-        const long long n_tiles = (cycles + llz::kUJB - 1) / llz::kUJB * ((a.L + llz::kUPB - 1) / llz::kUPB) * cc;
+        PolyLaunch u = a;
+        u.L = p.L * b->urep;
+        u.M = p.M * b->urep;
+        u.cbank = b->d_cbank_u;
+        u.single_tap = b->d_single_u;
+        const long long cycles = (u.o0 + outs - 1) / u.L - u.o0 / u.L + 1;
+        const long long n_tiles = (cycles + llz::kUJB - 1) / llz::kUJB * ((u.L + llz::kUPB - 1) / llz::kUPB) * cc;
         const int sms = device_sm_count();
         if (sms <= 0) return -1;
         if (b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05 || n_tiles >= 4LL * sms) {
-            const size_t per_cycle = poly_bank_umma_rows_bytes(a, cc, 1);
+            const size_t per_cycle = (size_t)2 * cc * (size_t)u.M;
             long long slab = (long long)(tunables().umma_slab_mib * 1024 * 1024 / (double)per_cycle) / llz::kUJB * llz::kUJB;
             if (slab < llz::kUJB) slab = llz::kUJB;
             if (slab > cycles) slab = (cycles + llz::kUJB - 1) / llz::kUJB * llz::kUJB;
-            const size_t need = per_cycle * (size_t)slab;
+            const size_t need = poly_bank_umma_rows_bytes(u, cc, slab);
             if (need > b->umma_rows_cap) {
                 LLZ_CUDA_TRY(cudaDeviceSynchronize());                 // an earlier call may still read the old workspace
                 cudaFree(b->d_umma_rows);
@@ -790,19 +818,22 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
                 LLZ_CUDA_TRY(cudaMalloc(&b->d_umma_rows, need));
                 b->umma_rows_cap = need;
             }
-            a.umma_tiles = b->d_umma_tiles;
-            a.umma_nchunks = b->umma_nchunks;
-            a.umma_planes = b->umma_planes;
-            a.umma_scale = ldexp(1.0, -b->umma_shift);
-            a.umma_ush = b->umma_shift - 32;
+            u.umma_tiles = b->d_umma_tiles;
+            u.umma_nchunks = b->umma_nchunks;
+            u.umma_planes = b->umma_planes;
+            u.umma_scale = ldexp(1.0, -b->umma_shift);
+            u.umma_ush = b->umma_shift - 32;
             // first-level band: the (scaled) FP64 band, the taps' rounding bound, the bits the 32.32 form drops
             const double thr = b->guard_thr * b->guard_scale + 1.001 * b->umma_eps + ldexp(1.0, -31);
-            a.umma_thr32 = thr >= 0.4999 ? 0x7fffffffu : (unsigned)ceil(ldexp(thr, 32)) + 2u;
-            a.umma_rows = b->d_umma_rows;
-            a.umma_slab_cycles = (int)slab;
+            u.umma_thr32 = thr >= 0.4999 ? 0x7fffffffu : (unsigned)ceil(ldexp(thr, 32)) + 2u;
+            u.umma_rows = b->d_umma_rows;
+            u.umma_slab_cycles = (int)slab;
+            const int rc = poly_bank_umma_launch(u, cc, st);
+            if (rc < 0) return -1;
+            launched = rc == 1;
         }
     }
-    if (poly_launch(a, cc, st) != 0) return -1;
+    if (!launched && poly_launch(a, cc, st) != 0) return -1;
     if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
         b->chain_src = d_in + (n_in - p.hist_len);
     } else if (p.hist_len > 0) {

@@ -3,10 +3,13 @@
 // (tests/cpu/umma_emulate.cpp) all read the layout from here.
 //
 // Tile = 128 cycles (rows of the A operand = TMEM lanes) x 64 phases (rows of the B operand = TMEM columns).
-// A operand: the input as "expanded rows" -- row j holds the bytes of the samples  s = j*M - (Q-1) + b,  b < RL  (one
-// row per output cycle, two byte planes), so every operand row starts at a 16-byte boundary (TMA traps on an
-// unaligned innermost box coordinate: tools/probe_umma_i8.cu).  A phase tile reads the window  b in [w0, w0 + 128*chunks)
-// of the rows, w0 = 16*floor(c_lo/16); the c_lo % 16 bytes in front of its first useful sample meet zero taps.
+// A operand: row j (one output cycle) is the run of input bytes of the samples  s = j*M - (Q-1) + b,  two byte planes.  TMA
+// traps on an unaligned innermost box coordinate or row start (tools/probe_umma_i8.cu), so the kernel runs the bank
+// REPLICATED r times (L' = r L phases, M' = r M samples per cycle: the same outputs, see umma_replication) with M' a
+// multiple of 16: every row then starts at a 16-byte boundary of the plain byte planes of the input and the operand is a
+// tensor map with OVERLAPPING rows (row stride M' bytes < row extent) -- no expanded copy of the input exists.  A phase
+// tile reads the window  b in [w0, w0 + 128*chunks)  of the rows, w0 = 16*floor(c_lo/16); the c_lo % 16 bytes in front of
+// its first useful sample meet zero taps.
 // B operand: per phase tile and 128-byte chunk, five (exact mode) or three (fast mode) signed base-256 digit planes of the taps, each a [64 x 128 byte]
 // K-major SWIZZLE_128B block (8-row atoms of 1024 bytes, 16-byte chunk c of row r at position c ^ (r & 7)) -- the
 // layout a TMA box with CU_TENSOR_MAP_SWIZZLE_128B produces and the one the shared-memory matrix descriptor names.
@@ -60,11 +63,26 @@ LLZ_UMMA_HD inline UmmaPhaseTile umma_phase_tile(int L, int M, int Q, int p)
     return t;
 }
 
-// bytes of an expanded row that hold samples some tile needs, rounded up to 16 (boxes that reach beyond are zero filled)
-LLZ_UMMA_HD inline int umma_row_len(int L, int M, int Q)
+// bytes of a row that the widest-reaching phase tile reads (its boxes end at w0 + 128 * chunks)
+inline int umma_row_extent(int L, int M, int Q)
 {
-    const int c_hi_max = (int)(((long long)(L - 1) * M) / L);
-    return (c_hi_max + Q + 15) & ~15;
+    int ext = 0;
+    for (int p = 0; p * kUPB < L; ++p) {
+        const UmmaPhaseTile t = umma_phase_tile(L, M, Q, p);
+        if (t.w0 + kUKC * t.nchunks > ext) ext = t.w0 + kUKC * t.nchunks;
+    }
+    return ext;
+}
+
+// Replication factor r of the bank for this kernel: r M a multiple of 16 (aligned rows), r L >= 64 (one full phase tile),
+// then doubled while that removes padding of the last phase tile (r L a multiple of 64) and the tables stay small.
+inline int umma_replication(int L, int M)
+{
+    int r = 1;
+    while (((long long)r * M) % 16 != 0) r *= 2;
+    while ((long long)r * L < kUPB) r *= 2;
+    while (((long long)r * L) % kUPB != 0 && (long long)r * L < 16384) r *= 2;
+    return r;
 }
 
 // byte offset of element (row n, k byte kk) inside a [64 x 128] K-major SWIZZLE_128B block

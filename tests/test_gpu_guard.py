@@ -22,6 +22,9 @@ CASES = [
     ("resample", 160, 147, 0, 4, "poly_bank_umma_kernel (tcgen05): second look -> third level"),
     ("resample", 160, 147, 0, 2, "poly_bank_dmma_kernel"),
     ("resample", 160, 147, 0, 3, "poly_bank_kernel (DFMA register tile)"),
+    ("resample", 320, 147, 128, 4, "poly_bank_umma_kernel (tcgen05), Q = 257: 80 phase tiles of the 16-fold replicated bank"),
+    ("resample", 1, 3, 0, 4, "poly_bank_umma_kernel (tcgen05): decimating bank as 64 phases of a 192-sample cycle"),
+    ("decimate", 1, 4, 0, 4, "poly_bank_umma_kernel (tcgen05): llz_decimate's tap order"),
     ("resample", 320, 147, 128, 1, "poly_bank_imma_kernel, Q = 257"),
     ("resample", 320, 147, 128, 2, "poly_bank_dmma_kernel, Q = 257"),
     ("resample", 3, 2, 0, 0, "few phases: repeated rows on the phase-bank tiles"),

@@ -112,7 +112,7 @@ def test_bank_f32_within_one_lsb(zlib, port, cuda, L, M, win, k):
 
 
 @pytest.mark.parametrize("gain", [1.0, -2.5])
-@pytest.mark.parametrize("L,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0)])
+@pytest.mark.parametrize("L,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0), (1, 3, 0)])
 def test_bank_fast_mode_on_tcgen05(zlib, port, cuda, L, M, k, gain):
     """ACC_F32 on the tcgen05 kernel (llz_cuda_polybank_umma.cu with three int8 digit planes of the taps: exact products
     and sums, 22-bit taps, no guard): within 1 LSB of the reference, knife-edge phase exact, ragged two-call stream."""
@@ -297,7 +297,7 @@ def test_c3_shape_spot_checks(zlib, port, cuda):
 
 
 @pytest.mark.parametrize("tiles", [1, 2, 3, 4])
-@pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0)])
+@pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0), (1, 3, 0), (2, 1, 0), (1, 4, 0)])
 def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, L_, M, k, tiles):
     """The exact mode's four tile kernels: INT8 tensor cores through mma.sync (1) and through tcgen05 with TMEM
     accumulators (4) -- taps as five int8 digit planes, samples as two byte planes, exact s32 accumulation, a two-level
