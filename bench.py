@@ -361,9 +361,8 @@ class Workload:
     def _kernel_name(self):
         wl, f32 = self.wl, self.dtype == "f32"
         if not self.fir:
-            if wl["L"] == 1:
-                return "poly_slide_kernel", None, None
-            # large calls run the tcgen05 kernel (llz_cuda_polybank_umma.cu): 3 digit planes in the fast mode, 5 in the exact mode
+            # large calls run the tcgen05 kernel (llz_cuda_polybank_umma.cu): 3 digit planes in the fast mode, 5 in the exact
+            # mode; refresh_kernel() replaces this guess with what the library reports after the timed steps
             return ("poly_bank_umma_kernel<3>" if f32 else "poly_bank_umma_kernel<5>"), None, None
         t = "float" if f32 else "double"
         if self.fir_fft and wl["taps"] >= 545:
@@ -390,6 +389,18 @@ class Workload:
             self.bank.reset()
             self.bank.run(self.dx_all, self.x_stride, self.in_count, self.dy, self.out_count, self.stream)
 
+    def refresh_kernel(self):
+        """resampler workloads: the library reports the kernel that filtered the last call and its launches"""
+        if self.fir:
+            return
+        import ctypes as C
+        z = self.z
+        handle = self.bank.handle if self.bank is not None else self.job.bank(0)
+        n, buf = C.c_int(0), C.create_string_buffer(96)
+        if z.lib().llz_cuda_resample_bank_last_run(handle, C.byref(n), buf, 96) == 0 and buf.value:
+            self.kernel = buf.value.decode()
+            self.launches_per_step = n.value + (1 if self.halo else 0)
+
     def time_steps(self, steps: int, warmup: int, gather: int = 0, sample_clocks: bool = True):
         """CUDA events on the launching stream around `steps` steps, barrier + synchronize on both sides, max over ranks"""
         torch, D = self.torch, self.D
@@ -408,6 +419,7 @@ class Workload:
             sampler.sample_now()                    # the launches above are still running: a sample under load
         D.barrier()
         clocks = sampler.result() if sampler else None
+        self.refresh_kernel()
         ms_local = e0.elapsed_time(e1) / steps
         return D.max(ms_local), ms_local, clocks
 

@@ -178,6 +178,8 @@ int llz_cuda_resample_bank_run(unsigned long handle, const short *d_in, long lon
 int llz_cuda_resample_bank_run_host(unsigned long handle, const short *h_in, long long in_stride,
                                     long long n_in, short *h_out, long long out_stride,
                                     long long *n_out);
+/* kernel launches of the handle's last run call and the name of the kernel that did the filtering (reporting only) */
+int llz_cuda_resample_bank_last_run(unsigned long handle, int *launches, char *kernel, int kernel_cap);
 /* outputs that took the reference-order recompute (near-integer guard) since init */
 long long llz_cuda_resample_bank_guard_count(unsigned long handle);
 /* Verification knobs.  set_tiles picks the tile family of the phase-bank kernels (LLZ_CUDA_TILES_*).

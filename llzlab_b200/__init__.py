@@ -138,6 +138,7 @@ _SIGNATURES = [
     ("llz_cuda_resample_bank_run", C.c_int, [_ul, _vp, _ll, _ll, _vp, _ll, C.POINTER(_ll), _vp]),
     ("llz_cuda_resample_bank_run_host", C.c_int, [_ul, _vp, _ll, _ll, _vp, _ll, C.POINTER(_ll)]),
     ("llz_cuda_resample_bank_guard_count", _ll, [_ul]),
+    ("llz_cuda_resample_bank_last_run", C.c_int, [_ul, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     ("llz_cuda_resample_bank_set_tiles", C.c_int, [_ul, C.c_int]),
     ("llz_cuda_resample_bank_set_guard_scale", C.c_int, [_ul, C.c_double]),
     ("llz_cuda_shard_channels", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -511,6 +512,12 @@ class ResampleBank:
                                                      out_stride, C.byref(n_out)),
                "llz_cuda_resample_bank_run_host")
         return n_out.value
+
+    def last_run(self):
+        """(kernel launches, name of the filtering kernel) of the last run call"""
+        n, buf = C.c_int(0), C.create_string_buffer(96)
+        _check(lib().llz_cuda_resample_bank_last_run(self.handle, C.byref(n), buf, 96), "last_run")
+        return n.value, buf.value.decode()
 
     def guard_count(self) -> int:
         return _check(lib().llz_cuda_resample_bank_guard_count(self.handle), "guard_count")

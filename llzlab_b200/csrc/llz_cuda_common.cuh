@@ -25,6 +25,12 @@ namespace llz {
 // SM count of the CURRENT device, cached per device ordinal (a handle runs under a DeviceGuard, so the current device
 // is the handle's); -1 + error message on failure.  Thread-safe.
 int device_sm_count();
+// Every launch site of the resampler kernels reports its kernel here (thread-local); the shim hands the name and the
+// launch count of a handle's last call to llz_cuda_resample_bank_last_run (bench.py's gpu_launches and roofline.kernel).
+void note_launch(const char *kernel, int launches = 1);
+void note_reset();
+const char *noted_kernel();
+int noted_launches();
 
 // Measurement knobs.  The environment is read ONCE, when the first handle is created; llz_cuda_tune() overrides a value
 // afterwards.  Nothing on a launch path calls getenv.

@@ -495,6 +495,7 @@ int launch_bank_dmma_tile(const PolyLaunch &a, int n_channels, cudaStream_t stre
     const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
     if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
     kern<<<dim3((unsigned)blocks, (unsigned)n_channels), 64 * WN, smem, stream>>>(a, geo);
+    note_launch("poly_bank_dmma_kernel");
     LLZ_CUDA_TRY(cudaGetLastError());
     return 1;
 }
@@ -745,6 +746,7 @@ int launch_bank_hmma(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
     if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
     kern<<<dim3((unsigned)blocks, (unsigned)n_channels), kDmmaThreads, smem, stream>>>(a, geo);
+    note_launch("poly_bank_hmma_kernel");
     LLZ_CUDA_TRY(cudaGetLastError());
     return 1;
 }
@@ -777,6 +779,7 @@ int launch_bank(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     const long long blocks = (long long)geo.n_cycle_tiles * geo.n_phase_tiles;
     if (blocks > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
     kern<<<dim3((unsigned)blocks, (unsigned)n_channels), kBankThreads, smem, stream>>>(a, geo);
+    note_launch("poly_bank_kernel");
     LLZ_CUDA_TRY(cudaGetLastError());
     return 1;
 }

@@ -425,6 +425,7 @@ int poly_bank_imma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
     const long long tiles = (long long)geo.n_cycle_tiles * geo.n_phase_tiles * n_channels;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);           // persistent: one CTA per SM
     kern<<<grid, kIConsumers + kIProducers, smem, stream>>>(a, geo);
+    note_launch("poly_bank_imma_kernel");
     LLZ_CUDA_TRY(cudaGetLastError());
     return 1;
 }

@@ -592,6 +592,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         dim3 sgrid((unsigned)((geo.plane_len + kSplitSpan - 1) / kSplitSpan), (unsigned)n_channels);
         poly_split_planes_kernel<<<sgrid, kSplitThreads, 0, stream>>>(a, geo, a.umma_rows);
         LLZ_CUDA_TRY(cudaGetLastError());
+        note_launch("poly_split_planes_kernel");
         // 2. the tensor map over them: [plane][channel][cycle][byte], rows overlapping (stride M bytes)
         CUtensorMap map;
         const cuuint64_t dims[4] = {(cuuint64_t)ext, (cuuint64_t)geo.n_cycle_tiles * kUJB, (cuuint64_t)n_channels, 2};
@@ -605,6 +606,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);           // persistent: one CTA per SM
         kern<<<grid, kUThreads, smem, stream>>>(map, a, geo);
         LLZ_CUDA_TRY(cudaGetLastError());
+        note_launch(PLANES == kUPlanesExact ? "poly_bank_umma_kernel<5>" : "poly_bank_umma_kernel<3>");
     }
     return 1;
 }

@@ -268,6 +268,7 @@ int poly_update_history(const int16_t *x, long long x_stride, long long n_in, co
     if (hist_len <= 0 || n_channels <= 0) return 0;
     dim3 grid((hist_len + 255) / 256, n_channels);
     poly_history_kernel<<<grid, 256, 0, stream>>>(x, x_stride, n_in, hist_old, hist_new, hist_len);
+    note_launch("poly_history_kernel");
     LLZ_CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -348,6 +349,7 @@ int launch_slide(const PolyLaunch &a, int ntp, int n_channels, cudaStream_t stre
     const long long tiles = (a.n_out + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
     kern<<<dim3((unsigned)tiles, (unsigned)n_channels), kSlideThreads, smem, stream>>>(a, ntp, tap_stride);
+    note_launch("poly_slide_kernel");
     LLZ_CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -375,6 +377,7 @@ int launch_general(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     const long long tiles = (a.n_out + tile - 1) / tile;
     if (tiles > 0x7fffffffLL) { llz_set_error("resample launch too large"); return -1; }
     kern<<<dim3((unsigned)tiles, (unsigned)n_channels), kPolyThreads, smem, stream>>>(a, (int)tile);
+    note_launch("poly_general_kernel");
     LLZ_CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -10,6 +10,20 @@
 namespace llz {
 
 // ---- per-process state ---------------------------------------------------------------------------
+namespace {
+thread_local const char *t_kernel = "";
+thread_local int t_launches = 0;
+}
+void note_launch(const char *kernel, int launches)
+{
+    // the helpers either side of the filtering kernel count as launches but do not name the call
+    if (strcmp(kernel, "poly_history_kernel") != 0 && strcmp(kernel, "poly_split_planes_kernel") != 0) t_kernel = kernel;
+    t_launches += launches;
+}
+void note_reset() { t_kernel = ""; t_launches = 0; }
+const char *noted_kernel() { return t_kernel; }
+int noted_launches() { return t_launches; }
+
 int device_sm_count()
 {
     constexpr int kMaxDev = 64;

@@ -10,6 +10,7 @@
 // Tap design and polyphase planning stay in host C (llz_design.c).  There is no CPU data path: every
 // sample goes through the kernels of llz_cuda_fir.cu / llz_cuda_resample.cu, and without a CUDA
 // device the *_init functions fail with (unsigned long)-1.
+#include <stdio.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -485,6 +486,8 @@ struct PolyBank {
     int umma_nchunks = 0;
     int umma_planes = 0, umma_shift = 0;   // digit planes (5 exact / 3 fast) and the scale 2^-shift of those tables
     double umma_eps = 0.0;                 // bound on |sum_k (g gain - q 2^-shift) x| for |x| <= 32768
+    int last_launches = 0;                 // kernel launches and dominant kernel of the last run call
+    const char *last_kernel = "";
     int urep = 1;                          // the tcgen05 kernel sees the bank replicated urep times (llz_umma_tables.h)
     double *d_cbank_u = nullptr;           // [L urep][Q]: the replicated bank (guard recompute, knife-edge taps)
     int *d_single_u = nullptr;             // [L urep]
@@ -791,6 +794,7 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
     a.imma_scale = ldexp(1.0, -b->imma_shift);
     // first-level band of the integer evaluation: the (scaled) FP64 band plus the taps' rounding bound
     a.imma_thr = b->guard_thr * b->guard_scale + 1.001 * fabs(b->gain) * b->imma_eps + ldexp(fabs(b->gain), -36);
+    if (c0 == 0) note_reset();
     // tcgen05 kernel for calls that fill the machine (a frame-sized call keeps the mma.sync / sliding tiles: no pre-pass,
     // no workspace, lower latency); LLZ_CUDA_TILES_INT8_TCGEN05 forces it
     bool launched = false;
@@ -850,6 +854,8 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
         b->consumed += n_in;
         b->produced += outs;
     }
+    b->last_launches = noted_launches();
+    b->last_kernel = noted_kernel();
     return 0;
 }
 
@@ -1351,6 +1357,15 @@ extern "C" int llz_cuda_resample_bank_set_guard_scale(unsigned long handle, doub
     if (!b) return -1;
     if (!(scale >= 1.0) || scale > 1e12) { llz_set_error("guard scale must be in [1, 1e12] (got %g)", scale); return -1; }
     b->guard_scale = scale;
+    return 0;
+}
+
+extern "C" int llz_cuda_resample_bank_last_run(unsigned long handle, int *launches, char *kernel, int kernel_cap)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    if (launches) *launches = b->last_launches;
+    if (kernel && kernel_cap > 0) snprintf(kernel, (size_t)kernel_cap, "%s", b->last_kernel);
     return 0;
 }
 
