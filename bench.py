@@ -56,6 +56,35 @@ WORKLOADS = {
 }
 
 
+def umma_macs_per_output(L: int, M: int, Q: int, planes: int) -> float:
+    """int8 multiply-accumulates the tcgen05 phase-bank kernel executes per output sample: the tile geometry of
+    llzlab_b200/csrc/llz_umma_tables.h (replication, 64-phase tiles, K steps of 32 bytes, 2 x planes digit products)"""
+    r = 1
+    while (r * M) % 16:
+        r *= 2
+    while r * L < 64:
+        r *= 2
+    while (r * L) % 64 and r * L < 16384:
+        r *= 2
+    UL, UM = L * r, M * r
+    ksteps = 0
+    for p in range((UL + 63) // 64):
+        l0 = 64 * p
+        pbv = min(64, UL - l0)
+        c_lo, c_hi = (l0 * UM) // UL, ((l0 + pbv - 1) * UM) // UL
+        ksteps += (Q + (c_hi - c_lo) + (c_lo & 15) + 31) // 32
+    return ksteps * 2 * planes * 64 * 32 / UL
+
+
+def peaks_tensor():
+    """dense bf16 TFLOP/s measured on this pool (MEASURED_PEAKS.json); kind::i8 runs at twice the bf16 MAC rate"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured bf16 x 2 (MEASURED_PEAKS.json; tcgen05 kind::i8 = twice the bf16 rate)"
+    return 1590.0, "fallback bf16 x 2 (B200_PROFILING.md)"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -618,6 +647,17 @@ def measure(z, D: Dist, mg, name: str, dtype: str, algo: str, steps: int, warmup
                 fma_pipe["note"] += ("; the kernel evaluates the sums as exact integers on the tensor cores (tcgen05.mma.kind::i8, "
                                      "%d digit products per multiply-add), so the fraction is its speed relative to the FMA roof "
                                      "it no longer uses" % (6 if W.dtype == "f32" else 10))
+        tensor = None
+        if W.kernel.startswith("poly_bank_umma_kernel"):
+            planes = 3 if W.dtype == "f32" else 5
+            macs = umma_macs_per_output(wl["L"], wl["M"], W.q, planes)
+            bf16, tsrc = peaks_tensor()
+            tops = W.outs_rank * macs * 2.0 / (ms_local * 1e-3) / 1e12
+            tensor = {"achieved": tops, "peak": 2.0 * bf16, "unit": "TOP/s", "frac": tops / (2.0 * bf16), "peak_source": tsrc,
+                      "int8_macs_per_output": macs, "digit_products_per_mac": 2 * planes,
+                      "note": "executed int8 operations (2 x MACs of the issued 128x64x32 MMAs); an N = 64 MMA is bound by its "
+                              "shared-memory operand reads at 2/3 of the kind::i8 rate (tools/probe_umma_rate.cu: 48 cycles "
+                              "against 32), so 0.67 is this tile shape's ceiling"}
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -637,11 +677,19 @@ def measure(z, D: Dist, mg, name: str, dtype: str, algo: str, steps: int, warmup
                              + ("" if W.dx_all.numel() * W.es > 4 * 126e6 else "; outputs + inputs of consecutive steps still exceed L2" if (W.dx_all.numel() + W.dy.numel()) * W.es > 2 * 126e6 else " (fits: strong-scaled shard)"),
                        "input": "integer LCG noise generated on the device (SURVEY.md 8d)",
                        **({"fir_algo": f"overlap-save, {W.fft_desc}" if W.fir_fft else "direct form"} if W.fir else {})},
-            "roofline": {"kernel": W.kernel, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach_gbs / hbm_peak, "traffic": traffic if D.world == 1 else None, "peak_source": peak_src,
-                         "algorithmic": {"bytes_per_output": W.bytes_per_out, "flop_per_output": W.flop_per_out,
-                                         "outputs_per_launch": W.outs_rank},
-                         "fma_pipe": fma_pipe},
+            "roofline": ({"kernel": W.kernel, "bound": "tensor", "achieved": tensor["achieved"], "peak": tensor["peak"],
+                          "unit": "TOP/s", "frac": tensor["frac"], "traffic": traffic if D.world == 1 else None,
+                          "peak_source": tensor["peak_source"], "tensor": tensor,
+                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                                  "peak_source": peak_src},
+                          "algorithmic": {"bytes_per_output": W.bytes_per_out, "flop_per_output": W.flop_per_out,
+                                          "outputs_per_launch": W.outs_rank},
+                          "fma_pipe": fma_pipe} if tensor else
+                         {"kernel": W.kernel, "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": ach_gbs / hbm_peak, "traffic": traffic if D.world == 1 else None, "peak_source": peak_src,
+                          "algorithmic": {"bytes_per_output": W.bytes_per_out, "flop_per_output": W.flop_per_out,
+                                          "outputs_per_launch": W.outs_rank},
+                          "fma_pipe": fma_pipe}),
             "parity": parity_all[0] if D.world == 1 else {"ok": all(p["ok"] for p in parity_all), "per_rank": parity_all},
             "gpu_launches": W.launches_per_step * steps, "clocks": clocks,
         }

@@ -45,6 +45,12 @@ struct UmmaGeom {
     int n_cycle_tiles, n_phase_tiles, n_channels;
     int nchunk_max;                // chunks per phase tile in the tap tables
     long long plane_len;           // bytes of one channel's byte plane of the slab (a multiple of 16)
+    // Frames.  llz_interp restarts its window at every input frame (samples at or beyond the end of an output's own frame
+    // read as zero, llz_resample.c:515-523), so its planes hold the frames one after the other, each followed by zeros:
+    // frame f at byte f * frame_pitch, rows_per_frame rows each.  Everything else is one frame.
+    long long frame_pitch;         // bytes between frames in a plane (a multiple of 16); plane_len when there is one frame
+    long long frame_samples;       // samples of a frame that come from the stream (the rest of the pitch is zeros)
+    int n_frames, rows_per_frame;
     int n_stages;                  // A-operand stages that fit beside the resident taps (2..4)
 };
 
@@ -55,34 +61,38 @@ static_assert((kUPlanesExact + 1) * kUPB <= kUParkCol, "accumulators overlap the
 constexpr int kUMaxStages = 4;
 
 // ---- pre-pass: byte planes --------------------------------------------------------------------------------------------
-// planes[plane][channel][e] = byte `plane` of X(jc0*M - (Q-1) + e),  e < plane_len,  X = the stream sample of
-// llz_poly_kernels.h.  One CTA splits kSplitSpan consecutive samples of one channel: the span arrives by a bulk copy
-// (poly_stage_span: history, zeros and ragged ends are resolved there) and leaves as two coalesced byte streams.
+// planes[plane][channel][f * frame_pitch + e] = byte `plane` of X(S_base + f * frame_samples + e) for e < frame_samples,
+// zero for the rest of the pitch;  S_base = jc0*M - (Q-1) + shift,  X = the stream sample of llz_poly_kernels.h.  One
+// CTA splits kSplitSpan consecutive bytes of one frame of one channel: the span arrives by a bulk copy (poly_stage_span:
+// history, zeros and ragged ends are resolved there) and leaves as two coalesced byte streams.
 constexpr int kSplitSpan = 8192, kSplitThreads = 256;
 
 __global__ void __launch_bounds__(kSplitThreads)
-poly_split_planes_kernel(PolyLaunch a, UmmaGeom geo, unsigned char *planes)
+poly_split_planes_kernel(PolyLaunch a, UmmaGeom geo, unsigned char *planes, int spans_per_frame)
 {
     __shared__ __align__(16) int16_t raw[kSplitSpan + 16];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
     const int ch = blockIdx.y;
-    const long long e0 = (long long)blockIdx.x * kSplitSpan;
-    const int need = (int)min((long long)kSplitSpan, geo.plane_len - e0);
+    const long long f = blockIdx.x / spans_per_frame;
+    const long long e0 = (long long)(blockIdx.x % spans_per_frame) * kSplitSpan;    // first byte of the span within its frame
+    const int span = (int)min((long long)kSplitSpan, geo.frame_pitch - e0);          // a multiple of 16
+    const int need = (int)max(0LL, min((long long)span, geo.frame_samples - e0));    // samples that come from the stream
     const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
-    const long long S0 = geo.jc0 * (long long)a.M - (a.ctaps - 1) + e0;
-    bool bulk;
-    const int off = poly_stage_span<kSplitThreads>(a, xc, hc, S0, need, raw, &bar, tid, &bulk);
+    const long long S0 = geo.jc0 * (long long)a.M - (a.ctaps - 1) + a.shift + f * geo.frame_samples + e0;
+    bool bulk = false;
+    int off = 0;
+    if (need > 0) off = poly_stage_span<kSplitThreads>(a, xc, hc, S0, need, raw, &bar, tid, &bulk);
     __syncthreads();
     if (bulk) mbar_wait(&bar, 0);
-    unsigned char *lo = planes + (size_t)ch * geo.plane_len + e0;               // plane_len and kSplitSpan are multiples of 16
+    unsigned char *lo = planes + (size_t)ch * geo.plane_len + f * geo.frame_pitch + e0;
     unsigned char *hi = lo + (size_t)geo.n_channels * geo.plane_len;
-    for (int e = 4 * tid; e < need; e += 4 * kSplitThreads) {                   // need is a multiple of 16
+    for (int e = 4 * tid; e < span; e += 4 * kSplitThreads) {
         uint32_t lw = 0, hw = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const uint32_t v = (uint32_t)(uint16_t)raw[off + e + b];
+            const uint32_t v = (e + b < need) ? (uint32_t)(uint16_t)raw[off + e + b] : 0u;
             lw |= (v & 255u) << (8 * b);
             hw |= (v >> 8) << (8 * b);
         }
@@ -135,10 +145,10 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint64_t *bar)
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4, uint64_t *bar)
 {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
@@ -191,6 +201,12 @@ __device__ __forceinline__ int umma_finish(uint32_t lo, uint32_t hi, int ush, ui
     *near_nonzero_integer = n != 0 && dist < thr32;
     const int t = nf + (int)(nf < 0 && f != 0u);               // toward zero
     return min(max(t, -32768), 32767);
+}
+
+// first sample index an output must read as zero: the end of its own input frame (llz_interp), nothing otherwise
+__device__ __forceinline__ long long umma_frame_end(const PolyLaunch &a, long long o)
+{
+    return a.frame_len > 0 ? ((o * a.M) / a.L / a.frame_len + 1) * (long long)a.frame_len : LLONG_MAX;
 }
 
 // single-tap output: the integer sum is q * x exactly (q = round(g gain 2^s)); recover x, redo the reference's two
@@ -293,6 +309,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 ++run;
             }
             const int j0 = T.tile_j * kUJB;
+            const int f0 = j0 / geo.rows_per_frame, i0 = j0 - f0 * geo.rows_per_frame;   // first frame and row of the tile's box
             for (int c = 0; c < T.pt.nchunks; ++c) {
                 mbar_wait(&s_empty[buf], ph ^ 1u);                             // passes at once on the first lap
                 UTRACE(0, (int)(t - t_begin), c);
@@ -300,8 +317,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                     unsigned char *st = stages + (size_t)buf * kUAStage;
                     mbar_expect_tx(&s_full[buf], (uint32_t)kUAStage);
                     const int b0 = T.pt.w0 + kUKC * c;
-                    tma_load_4d(st, &rows_map, b0, j0, T.ch, 0, &s_full[buf]);
-                    tma_load_4d(st + kUAPlane, &rows_map, b0, j0, T.ch, 1, &s_full[buf]);
+                    tma_load_5d(st, &rows_map, b0, i0, f0, T.ch, 0, &s_full[buf]);
+                    tma_load_5d(st + kUAPlane, &rows_map, b0, i0, f0, T.ch, 1, &s_full[buf]);
                 }
                 __syncwarp();
                 if (++buf == S) { buf = 0; ph ^= 1u; }
@@ -475,8 +492,9 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                     const long long o = o_row + l;
                     if (o < a.o0 || o >= o_end) continue;
                     const int st = __ldg(a.single_tap + l0 + l);
-                    const long long base = (o * M) / L;
-                    ych[o - a.o0] = poly_finish(__dmul_rn(__dmul_rn((double)poly_sample(a, xc, hc, base - st), a.cbank[(long long)(l0 + l) * Q + st]), a.gain));
+                    const long long sidx = (o * M) / L + a.shift - st;
+                    const double xv = sidx < umma_frame_end(a, o) ? (double)poly_sample(a, xc, hc, sidx) : 0.0;
+                    ych[o - a.o0] = poly_finish(__dmul_rn(__dmul_rn(xv, a.cbank[(long long)(l0 + l) * Q + st]), a.gain));
                 }
             }
             UTRACE(warp - 2, tile_n, 3);
@@ -492,7 +510,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 int l = (lane == src) ? __ffs((int)hits) - 1 : 0;
                 l = __shfl_sync(0xffffffffu, l, src);
                 const long long o = (geo.jc0 + (long long)T.tile_j * kUJB + 32 * q + src) * (long long)L + l0 + l;   // warp-uniform
-                const long long base = (o * M) / L;
+                const long long base = (o * M) / L + a.shift;
+                const long long frame_end = umma_frame_end(a, o);
                 const double *row = a.cbank + (long long)(l0 + l) * Q;
                 double part = 0.0;
                 for (int k = lane; k < Q; k += 128) {          // four independent sample / tap loads in flight per lane
@@ -501,7 +520,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int kk = k + 32 * u;
-                        const bool in = kk < Q;
+                        const bool in = kk < Q && base - kk < frame_end;
                         xv[u] = in ? poly_sample(a, xc, hc, base - kk) : 0;
                         gv[u] = in ? row[kk] : 0.0;
                     }
@@ -549,11 +568,46 @@ EncodeTiledFn encode_tiled()
 
 }  // namespace
 
-// bytes of the byte-plane workspace for a slab of `cycles` cycles (of the replicated bank a.L / a.M)
+namespace {
+
+// plane geometry of a slab of `cycles` cycles (whole tiles of 128): one frame, or llz_interp's frames with their zero tails
+struct UmmaPlanes {
+    long long plane_len, frame_pitch, frame_samples;
+    int n_frames, rows_per_frame, ext;
+    bool ok;
+};
+
+UmmaPlanes umma_planes(const PolyLaunch &a, long long cycles)
+{
+    UmmaPlanes g{};
+    g.ext = umma_row_extent(a.L, a.M, a.ctaps);
+    const long long rows = (cycles + kUJB - 1) / kUJB * kUJB;
+    if (a.frame_len > 0) {
+        // rows must not straddle frames, and a tile's 128 rows must be whole frames or part of one
+        if (a.frame_len % a.M != 0) return g;
+        g.rows_per_frame = a.frame_len / a.M;
+        if (kUJB % g.rows_per_frame != 0 && g.rows_per_frame % kUJB != 0) return g;
+        g.n_frames = (int)((rows + g.rows_per_frame - 1) / g.rows_per_frame);
+        g.frame_samples = a.frame_len;
+        g.frame_pitch = ((long long)a.frame_len + g.ext + 15) & ~15LL;
+        g.plane_len = g.frame_pitch * g.n_frames;
+    } else {
+        if (rows > 0x7fffffffLL) return g;
+        g.rows_per_frame = (int)rows;
+        g.n_frames = 1;
+        g.plane_len = g.frame_pitch = g.frame_samples = (rows * a.M + g.ext + 15) & ~15LL;
+    }
+    g.ok = true;
+    return g;
+}
+
+}  // namespace
+
+// bytes of the byte-plane workspace for a slab of `cycles` cycles (of the replicated bank a.L / a.M); 0 = not applicable
 size_t poly_bank_umma_rows_bytes(const PolyLaunch &a, int n_channels, long long cycles)
 {
-    const long long plane_len = ((cycles * a.M + umma_row_extent(a.L, a.M, a.ctaps)) + 15) & ~15LL;
-    return (size_t)2 * n_channels * (size_t)plane_len;
+    const UmmaPlanes g = umma_planes(a, cycles);
+    return g.ok ? (size_t)2 * n_channels * (size_t)g.plane_len : 0;
 }
 
 namespace {
@@ -566,7 +620,6 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     const int sms = device_sm_count();
     if (sms <= 0) return -1;
     if (a.M % 16 != 0) return 0;                               // rows must start on 16-byte boundaries (umma_replication)
-    const int ext = umma_row_extent(a.L, a.M, a.ctaps);
     const long long jc_first = a.o0 / a.L, jc_last = (a.o0 + a.n_out - 1) / a.L;
     // shared memory: the resident taps, then as many 32 KB sample stages as fit (at least two)
     constexpr size_t kSmemMax = 227 * 1024, kBarBytes = 128;
@@ -586,19 +639,29 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         geo.n_channels = n_channels;
         geo.nchunk_max = a.umma_nchunks;
         geo.n_stages = n_stages;
-        // rows of a partial last cycle tile are read too (and discarded): the plane covers whole tiles
-        geo.plane_len = (((long long)geo.n_cycle_tiles * kUJB * a.M + ext) + 15) & ~15LL;
+        // rows of a partial last cycle tile are read too (and discarded): the planes cover whole tiles
+        const UmmaPlanes pl = umma_planes(a, geo.n_cycles);
+        if (!pl.ok) return 0;
+        geo.plane_len = pl.plane_len;
+        geo.frame_pitch = pl.frame_pitch;
+        geo.frame_samples = pl.frame_samples;
+        geo.n_frames = pl.n_frames;
+        geo.rows_per_frame = pl.rows_per_frame;
         // 1. byte planes of the slab
-        dim3 sgrid((unsigned)((geo.plane_len + kSplitSpan - 1) / kSplitSpan), (unsigned)n_channels);
-        poly_split_planes_kernel<<<sgrid, kSplitThreads, 0, stream>>>(a, geo, a.umma_rows);
+        const int spans_per_frame = (int)((geo.frame_pitch + kSplitSpan - 1) / kSplitSpan);
+        dim3 sgrid((unsigned)((long long)spans_per_frame * geo.n_frames), (unsigned)n_channels);
+        poly_split_planes_kernel<<<sgrid, kSplitThreads, 0, stream>>>(a, geo, a.umma_rows, spans_per_frame);
         LLZ_CUDA_TRY(cudaGetLastError());
         note_launch("poly_split_planes_kernel");
-        // 2. the tensor map over them: [plane][channel][cycle][byte], rows overlapping (stride M bytes)
+        // 2. the tensor map over them: [plane][channel][frame][row][byte], rows overlapping (stride M bytes); a tile's box is
+        // 128 rows of one frame, or whole frames of fewer rows each
         CUtensorMap map;
-        const cuuint64_t dims[4] = {(cuuint64_t)ext, (cuuint64_t)geo.n_cycle_tiles * kUJB, (cuuint64_t)n_channels, 2};
-        const cuuint64_t strides[3] = {(cuuint64_t)a.M, (cuuint64_t)geo.plane_len, (cuuint64_t)geo.plane_len * n_channels};
-        const cuuint32_t box[4] = {(cuuint32_t)kUKC, (cuuint32_t)kUJB, 1, 1}, estr[4] = {1, 1, 1, 1};
-        const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, a.umma_rows, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const int box_rows = geo.rows_per_frame < kUJB ? geo.rows_per_frame : kUJB;
+        const cuuint64_t dims[5] = {(cuuint64_t)pl.ext, (cuuint64_t)geo.rows_per_frame, (cuuint64_t)geo.n_frames, (cuuint64_t)n_channels, 2};
+        const cuuint64_t strides[4] = {(cuuint64_t)a.M, (cuuint64_t)geo.frame_pitch, (cuuint64_t)geo.plane_len,
+                                       (cuuint64_t)geo.plane_len * n_channels};
+        const cuuint32_t box[5] = {(cuuint32_t)kUKC, (cuuint32_t)box_rows, (cuuint32_t)(kUJB / box_rows), 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+        const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, a.umma_rows, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { llz_set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr); return -1; }
         // 3. the tiles
@@ -617,7 +680,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
     if (!a.umma_tiles || a.umma_nchunks <= 0 || !a.umma_rows || a.umma_slab_cycles <= 0) return 0;
-    if (a.shift != 0 || a.frame_len != 0 || a.n_out <= 0) return 0;
+    if (a.n_out <= 0) return 0;
     if (a.acc == LLZ_CUDA_ACC_F64 && a.umma_planes == kUPlanesExact) return umma_launch_slabs<kUPlanesExact, true>(a, n_channels, stream);
     if (a.acc == LLZ_CUDA_ACC_F32 && a.umma_planes == kUPlanesFast) return umma_launch_slabs<kUPlanesFast, false>(a, n_channels, stream);
     return 0;

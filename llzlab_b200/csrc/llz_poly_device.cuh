@@ -114,7 +114,7 @@ static __device__ __noinline__ double poly_reference_order_sum(const PolyLaunch 
     const int r = (int)(o % a.L);
     const long long base = (o * a.M) / a.L + a.shift;
     long long frame_end = LLONG_MAX;
-    if (a.frame_len > 0) frame_end = ((o / a.L) / a.frame_len + 1) * (long long)a.frame_len;
+    if (a.frame_len > 0) frame_end = ((base - a.shift) / a.frame_len + 1) * (long long)a.frame_len;   // of the output's own input frame
     const double *row = a.cbank + (long long)r * a.ctaps;
     double acc = 0.0;
     for (int t = 0; t < a.order_len; ++t) {

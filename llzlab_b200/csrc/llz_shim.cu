@@ -615,13 +615,14 @@ int poly_upload_plan(PolyBank *b)
         b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->imma_planes, &tiles, &b->imma_shift, &b->imma_eps);
         if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
     }
-    if ((b->acc == LLZ_CUDA_ACC_F64 || b->acc == LLZ_CUDA_ACC_F32) && p.shift == 0 && p.frame_len == 0 &&
-        b->gain != 0.0 && isfinite(b->gain) && (L0 > 1 || p.single_tap[0] < 0)) {
+    if ((b->acc == LLZ_CUDA_ACC_F64 || b->acc == LLZ_CUDA_ACC_F32) && b->gain != 0.0 && isfinite(b->gain) &&
+        (L0 > 1 || p.single_tap[0] < 0)) {
         // tcgen05.mma.kind::i8 (llz_cuda_polybank_umma.cu): digit planes of g * gain -- five for the exact mode (38-bit taps,
         // two-level guard), three for the fast mode (22-bit taps, no guard).  With the gain inside the taps the output
         // value is (integer sum) * 2^-s and the kernel finishes it with integer instructions.  The kernel sees the bank
         // replicated urep times (rows of the sample operand then start on 16-byte boundaries, llz_umma_tables.h) -- also
-        // the decimating banks (L = 1), which become 64 phases of a cycle of 64 M samples.
+        // the decimating banks (L = 1), which become 64 phases of a cycle of 64 M samples, and llz_interp (M = 1), whose
+        // frames lie one after the other in the sample planes, each followed by zeros.
         b->urep = llz::umma_replication((int)L0, p.M);
         const size_t UL = L0 * (size_t)b->urep;
         const long long UM = (long long)p.M * b->urep;
@@ -813,7 +814,12 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
             long long slab = (long long)(tunables().umma_slab_mib * 1024 * 1024 / (double)per_cycle) / llz::kUJB * llz::kUJB;
             if (slab < llz::kUJB) slab = llz::kUJB;
             if (slab > cycles) slab = (cycles + llz::kUJB - 1) / llz::kUJB * llz::kUJB;
+            if (p.frame_len > 0 && u.M > 0 && p.frame_len % u.M == 0) {        // whole frames per slab
+                const long long rpf = p.frame_len / u.M;
+                if (rpf > llz::kUJB) slab = (slab + rpf - 1) / rpf * rpf;
+            }
             const size_t need = poly_bank_umma_rows_bytes(u, cc, slab);
+            if (need == 0) goto no_umma;
             if (need > b->umma_rows_cap) {
                 LLZ_CUDA_TRY(cudaDeviceSynchronize());                 // an earlier call may still read the old workspace
                 cudaFree(b->d_umma_rows);
@@ -837,6 +843,7 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
             launched = rc == 1;
         }
     }
+no_umma:
     if (!launched && poly_launch(a, cc, st) != 0) return -1;
     if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
         b->chain_src = d_in + (n_in - p.hist_len);

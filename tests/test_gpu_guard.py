@@ -98,6 +98,25 @@ def test_widened_guard_band_interp_general_kernel(zlib, port, cuda):
     bank.close()
 
 
+def test_widened_guard_band_interp_on_tcgen05(zlib, port, cuda):
+    """llz_interp on the tcgen05 kernel: first-level hits take the warp's FP64 second look with the frame-local window,
+    what is still near an integer goes to the reference-order sum"""
+    torch = cuda
+    L_, C_ = 4, 2
+    bank = zlib.ResampleBank(zlib.KIND_INTERP, L_, 1, C_)
+    bank.set_tiles(zlib.TILES_INT8_TCGEN05)
+    plan = port.interp_plan(L_, 1)
+    n_in = plan.num_in * 6
+    x = np.stack([port.lcg_s16(n_in, 616 + c) for c in range(C_)])
+    bank.set_guard_scale(3e6)
+    got = run_bank(torch, bank, x, n_in * L_)
+    assert bank.last_run()[1].startswith("poly_bank_umma_kernel")
+    for c in range(C_):
+        assert np.array_equal(got[c], port.interp_run(plan, 1.0, x[c]))
+    assert bank.guard_count() >= n_in * L_ * C_ // 2000
+    bank.close()
+
+
 @pytest.mark.parametrize("kind,L_,M,k,tiles,what", CASES[:6] + CASES[7:9])
 def test_adversarial_near_integer_sums_with_the_production_band(zlib, port, cuda, kind, L_, M, k, tiles, what):
     """16 outputs per channel tuned to within a few ulps of a non-zero integer, half of them at or just above it and half

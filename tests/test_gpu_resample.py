@@ -248,6 +248,41 @@ def test_decimate_and_interp_banks(zlib, port, cuda):
             bank.close()
 
 
+@pytest.mark.parametrize("acc", ["exact", "fast"])
+@pytest.mark.parametrize("L_,win,gain", [(2, 0, 1.0), (3, 1, 0.8), (4, 1, -1.5), (16, 2, 1.0), (5, 1, 1.0)])
+def test_interp_bank_on_tcgen05(zlib, port, cuda, L_, win, gain, acc):
+    """llz_interp on the tcgen05 phase-bank kernel: the frames lie one after the other in the sample planes, each followed
+    by the zeros the reference's frame-local window reads (quirk R4), a tile's 128 rows are whole frames (5-D tensor map);
+    exact mode bit-identical to the reference frame loop, fast mode within 1 LSB.  Two calls of whole frames."""
+    torch = cuda
+    C_ = 3
+    p = port.interp_plan(L_, win)
+    bank = zlib.ResampleBank(zlib.KIND_INTERP, L_, 1, C_, gain=gain, win=win, acc=zlib.ACC_F64 if acc == "exact" else zlib.ACC_F32)
+    bank.set_tiles(zlib.TILES_INT8_TCGEN05)
+    frames = 7
+    n_in = p.num_in * frames
+    x = np.stack([port.lcg_s16(n_in, 80 + c) for c in range(C_)])
+    x[0, 1000:1100] = 32767                              # full scale across a frame boundary
+    want = np.stack([port.interp_run(p, gain, x[c]) for c in range(C_)]).astype(np.int32)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(C_, n_in * L_ + 8, dtype=torch.int16, device="cuda")
+    cut = p.num_in * 3
+    o1 = bank.run(dx, n_in, cut, dy, n_in * L_ + 8)
+    o2 = bank.run(dx.data_ptr() + 2 * cut, n_in, n_in - cut, dy.data_ptr() + 2 * o1, n_in * L_ + 8)
+    torch.cuda.synchronize()
+    assert (o1, o2) == (cut * L_, (n_in - cut) * L_)
+    launches, kernel = bank.last_run()
+    assert kernel.startswith("poly_bank_umma_kernel"), kernel
+    got = dy.cpu().numpy()
+    assert not got[:, n_in * L_:].any()
+    diff = np.abs(got[:, :n_in * L_].astype(np.int32) - want)
+    if acc == "exact":
+        assert not diff.any(), (L_, int(diff.max()), int((diff != 0).sum()))
+    else:
+        assert diff.max() <= 1 and (diff != 0).mean() <= 0.03
+    bank.close()
+
+
 def test_run_host_pipeline(zlib, port, cuda):
     torch = cuda
     L, M, C_ = 1, 3, 8
