@@ -51,6 +51,10 @@ WORKLOADS = {
                channels=16, n=230_400_000, taps=4095, fc=0.11, win=2, seed=12345, shard="time"),
     "c3": dict(kind="resample", desc="llz_resample 48 kHz -> 16 kHz (L=1, M=3, BLACKMAN, Q=134), 64 channels x 28.8 M samples (10 min)",
                channels=64, n=28_800_000, L=1, M=3, k=0, win=1, seed=777, shard="channel"),
+    # not a BASELINE config: the llz_interp sibling on the same kernel, for its throughput record
+    "interp4": dict(kind="resample", interp=True,
+                    desc="llz_interp x4 (12 kHz -> 48 kHz, L=4, BLACKMAN), 64 channels x 7,200,768 samples (10 min, 7032 frames of 1024)",
+                    channels=64, n=1024 * 7032, L=4, M=1, k=0, win=1, seed=777, shard="channel"),
     "c4": dict(kind="resample", desc="llz_resample 44.1 kHz -> 96 kHz (L=320, M=147, BLACKMAN, 256-tap bank: k=128, Q=257), 8 channels x 158.76 M samples (the full 1 h stream, 3375 frames of 47040)",
                channels=8, n=47_040 * 3375, L=320, M=147, k=128, win=1, seed=777, shard="time"),
 }
@@ -356,7 +360,12 @@ class Workload:
         else:
             self.tdt, self.es, self.np_dt, self.lcg_kind = torch.int16, 2, np.int16, 2
             acc = z.ACC_F32 if f32 else z.ACC_F64
-            if world > 1:
+            if wl.get("interp"):
+                if world > 1:
+                    raise RuntimeError("the interp workload is measured on one GPU only")
+                self.bank = z.ResampleBank(z.KIND_INTERP, wl["L"], 1, C_, win=wl["win"], acc=acc)
+                info = self.bank.info
+            elif world > 1:
                 self.job = z.MgpuJob.resample(mg, wl["L"], wl["M"], C_, self.mode, win=wl["win"], k_override=wl["k"], acc=acc)
                 info = z.bank_info(self.job.bank(0))
             else:
@@ -488,6 +497,24 @@ class Workload:
                     rec["windows"] += 1
             rec["snr_db"] = float(10 * np.log10(num / den)) if den > 0 else float("inf")
             rec["ok"] = rec["max_abs_diff"] <= tol and (self.dtype != "f32" or rec["snr_db"] >= 120.0)
+        elif wl.get("interp"):
+            L_ = wl["L"]
+            plan = P.interp_plan(L_, wl["win"])
+            F = plan.num_in
+            fast = self.dtype == "f32"
+            rec.update(tolerance=1 if fast else 0, tolerance_rule="|diff| <= 1 LSB (fast mode)" if fast else "bit-exact int16")
+            n_frames = self.in_count // F
+            for c in chans:
+                for f0 in sorted({0, n_frames // 3, 2 * n_frames // 3 + 1, n_frames - 2}):
+                    xs = self.dx_all[c, f0 * F:(f0 + 2) * F].cpu().numpy()
+                    want = P.interp_run(plan, 1.0, xs)
+                    got = self.dy[c, f0 * F * L_:(f0 + 2) * F * L_].cpu().numpy()
+                    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+                    rec["max_abs_diff"] = max(rec["max_abs_diff"], float(d.max()))
+                    rec["mismatches"] += int((d != 0).sum())
+                    rec["checked_outputs"] += len(want)
+                    rec["windows"] += 1
+            rec["ok"] = rec["max_abs_diff"] <= (1 if fast else 0)
         else:
             L_, M, Q = wl["L"], wl["M"], self.q
             plan = P.resample_plan(L_, M, wl["win"], wl["k"])
@@ -783,7 +810,8 @@ def run_cuda(args):
     # ---- every other BASELINE config, same run (device-timed, parity-checked; fewer steps) ----
     others = {}
     if args.workload is None and not args.headline_only:
-        for name, dtype in (("c2", "f32"), ("c3", "f64"), ("c3", "f32"), ("c4", "f64"), ("c4", "f32"), ("c5", "f64"), ("c5", "f32")):
+        extra = (("interp4", "f64"), ("interp4", "f32")) if D.world == 1 else ()
+        for name, dtype in (("c2", "f32"), ("c3", "f64"), ("c3", "f32"), ("c4", "f64"), ("c4", "f32"), ("c5", "f64"), ("c5", "f32")) + extra:
             key = f"{name}_{'f32' if dtype == 'f32' else ('f64' if WORKLOADS[name]['kind'] == 'fir' else 'exact')}"
             try:
                 rec = measure(z, D, mg, name, dtype, "auto", max(3, min(args.steps, 5)), 3, args, headline=False)

@@ -51,6 +51,7 @@ struct UmmaGeom {
     long long frame_pitch;         // bytes between frames in a plane (a multiple of 16); plane_len when there is one frame
     long long frame_samples;       // samples of a frame that come from the stream (the rest of the pitch is zeros)
     int n_frames, rows_per_frame;
+    int band;                      // row blocks (cycle tile x channel) per band of the tile walk
     int n_stages;                  // A-operand stages that fit beside the resident taps (2..4)
 };
 
@@ -209,13 +210,25 @@ __device__ __forceinline__ long long umma_frame_end(const PolyLaunch &a, long lo
     return a.frame_len > 0 ? ((o * a.M) / a.L / a.frame_len + 1) * (long long)a.frame_len : LLONG_MAX;
 }
 
-// single-tap output: the integer sum is q * x exactly (q = round(g gain 2^s)); recover x, redo the reference's two
-// products (x * g, then * gain) and finish in FP64 like the other kernels.  One copy of the division for all call sites.
-static __device__ __noinline__ int umma_single_tap(uint32_t lo, uint32_t hi, double scale, double g, double gain)
+// Single-tap output: the integer sum is q * x exactly (q = round(g gain 2^s)); recover x = sum / q, redo the reference's two
+// products (x * g, then * gain), saturate and truncate (llz_resample.c:594-601).  No division and no conversion instruction
+// (inv = 2^-s / (g gain) is computed once per phase tile; int64 -> double through the 2^52 trick, rounding and truncation
+// through magic-number additions): an interpolator by L has one such output in L, a call per output to a division routine
+// made llz_interp's finish pass three times as long as its MMAs.
+__device__ __forceinline__ int umma_single_tap(uint32_t lo, uint32_t hi, double inv, double g, double gain)
 {
-    const long long T = (long long)(((unsigned long long)hi << 32) | lo);
-    const double xr = rint((double)T * scale / (g * gain));
-    return poly_finish(__dmul_rn(__dmul_rn(xr, g), gain));
+    const double kMagic = 6755399441055744.0;                  // 1.5 * 2^52
+    const double dhi = __hiloint2double(0x43300000, (int)(hi ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+    const double dlo = __hiloint2double(0x43300000, (int)lo) - 4503599627370496.0;                   // 2^52
+    const double dT = fma(dhi, 4294967296.0, dlo);             // exact: |q x| < 2^53
+    const double xr = (dT * inv + kMagic) - kMagic;            // rint: |x| <= 2^15
+    const double v = __dmul_rn(__dmul_rn(xr, g), gain);
+    if (!(fabs(v) < 32769.0)) return v > 0.0 ? 32767 : -32768;
+    const double w = v + kMagic;
+    const int n = __double2loint(w);                           // rint(v)
+    const double d = v - (w - kMagic);
+    const int t = n - (int)(d < 0.0 && n > 0) + (int)(d > 0.0 && n < 0);   // toward zero
+    return min(max(t, -32768), 32767);
 }
 
 struct UmmaTile {
@@ -223,18 +236,38 @@ struct UmmaTile {
     UmmaPhaseTile pt;
 };
 
-// tiles in phase-major order: t = (tile_p * n_channels + ch) * n_cycle_tiles + tile_j.  A CTA walks a contiguous range, so
-// it changes its phase tile -- and reloads the resident taps -- at most once or twice per launch, and the CTAs that share a
-// block of expanded rows (one per phase tile) sweep the slab at the same pace (the rows are read from L2).
-__device__ __forceinline__ UmmaTile umma_tile(const PolyLaunch &a, const UmmaGeom &geo, long long t)
+// The tile walk.  A row block (cycle tile x channel, index r) is read by every phase tile; a phase tile's taps should stay
+// resident for many tiles.  So the slab is cut into BANDS of geo.band row blocks; within a band the tiles are numbered
+// phase-major, t = p * band_width + (r - band_start), and every CTA takes the same contiguous share of every band.  All CTAs
+// are then inside one band at any time -- its rows (tens of MB) are read from DRAM once and from L2 by all phase tiles --
+// and a CTA meets the same one or two phase tiles band after band (taps reloaded at most twice per band).  (Walking
+// the whole slab phase-major instead spread the 148 CTAs over as many different row blocks: with the 80 phase tiles of
+// config C4 every tile's samples then came from DRAM, 4.5 GB per 300 MB of planes by ncu.)
+// The walk costs a few additions per tile: the divisions (five 64-bit ones for a tile's coordinates and its phase-tile
+// geometry) are done once per band share and once per phase tile -- per tile they took longer than llz_interp's MMAs.
+template <typename Body>
+__device__ __forceinline__ void umma_walk(const PolyLaunch &a, const UmmaGeom &geo, Body &&body)
 {
+    const long long R = (long long)geo.n_cycle_tiles * geo.n_channels;
     UmmaTile T;
-    T.tile_j = (int)(t % geo.n_cycle_tiles);
-    const long long r = t / geo.n_cycle_tiles;
-    T.ch = (int)(r % geo.n_channels);
-    T.tile_p = (int)(r / geo.n_channels);
-    T.pt = umma_phase_tile(a.L, a.M, a.ctaps, T.tile_p);
-    return T;
+    T.tile_p = -1;
+    for (long long b0 = 0; b0 < R; b0 += geo.band) {
+        const long long bw = min((long long)geo.band, R - b0);
+        const long long nb = bw * geo.n_phase_tiles;
+        const long long t_begin = nb * blockIdx.x / gridDim.x, t_end = nb * (blockIdx.x + 1) / gridDim.x;
+        if (t_begin >= t_end) continue;
+        int p = (int)(t_begin / bw);
+        long long rb = t_begin - p * bw;                       // row block within the band
+        T.tile_j = (int)((b0 + rb) % geo.n_cycle_tiles);
+        T.ch = (int)((b0 + rb) / geo.n_cycle_tiles);
+        const int tj0 = (int)(b0 % geo.n_cycle_tiles), ch0 = (int)(b0 / geo.n_cycle_tiles);   // first row block of the band
+        for (long long t = t_begin; t < t_end; ++t) {
+            if (p != T.tile_p) { T.tile_p = p; T.pt = umma_phase_tile(a.L, a.M, a.ctaps, p); }
+            body(T);
+            if (++rb == bw) { rb = 0; ++p; T.tile_j = tj0; T.ch = ch0; }
+            else if (++T.tile_j == geo.n_cycle_tiles) { T.tile_j = 0; ++T.ch; }
+        }
+    }
 }
 
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer and TMEM owner (both walk their loops as whole
@@ -267,8 +300,6 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform for the compiler, too
-    const long long total = (long long)geo.n_phase_tiles * geo.n_cycle_tiles * geo.n_channels;
-    const long long t_begin = total * blockIdx.x / gridDim.x, t_end = total * (blockIdx.x + 1) / gridDim.x;
     const int S = geo.n_stages;
 
     if (tid == 0) {
@@ -292,9 +323,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         // ================================ TMA producer ================================
         const bool leader = elect_one();
         int buf = 0, run = 0, prev_p = -1;
-        uint32_t ph = 0;
-        for (long long t = t_begin; t < t_end; ++t) {
-            const UmmaTile T = umma_tile(a, geo, t);
+        uint32_t ph = 0, tile_n = 0;
+        umma_walk(a, geo, [&](const UmmaTile &T) {
             if (T.tile_p != prev_p) {
                 // new phase tile: its taps replace the resident ones once every MMA of the previous run has read them
                 if (run > 0) mbar_wait(b_free, (uint32_t)((run - 1) & 1));
@@ -312,7 +342,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             const int f0 = j0 / geo.rows_per_frame, i0 = j0 - f0 * geo.rows_per_frame;   // first frame and row of the tile's box
             for (int c = 0; c < T.pt.nchunks; ++c) {
                 mbar_wait(&s_empty[buf], ph ^ 1u);                             // passes at once on the first lap
-                UTRACE(0, (int)(t - t_begin), c);
+                UTRACE(0, tile_n, c);
                 if (leader) {
                     unsigned char *st = stages + (size_t)buf * kUAStage;
                     mbar_expect_tx(&s_full[buf], (uint32_t)kUAStage);
@@ -323,7 +353,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 __syncwarp();
                 if (++buf == S) { buf = 0; ph ^= 1u; }
             }
-        }
+            ++tile_n;
+        });
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         // With the loops inside `if (lane == 0)` every MMA sat in a divergence "waterfall" (ELECT / R2UR.BROADCAST /
@@ -332,8 +363,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         int buf = 0, run = 0, prev_p = -1;
         uint32_t ph = 0, tile_n = 0;
         const uint32_t taps_desc = umma_desc_lo(smem_u32(taps));
-        for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
-            const UmmaTile T = umma_tile(a, geo, t);
+        umma_walk(a, geo, [&](const UmmaTile &T) {
             if (T.tile_p != prev_p) {
                 if (run > 0 && leader) umma_commit(b_free);                    // the old taps are free once the MMAs so far are done
                 __syncwarp();
@@ -373,7 +403,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             if (leader) umma_commit(t_full);                                   // the tile's accumulators are complete
             __syncwarp();
             UTRACE(1, tile_n, 8);
-        }
+            ++tile_n;
+        });
     } else if (warp >= 4) {
         // ================================ epilogue ================================
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
@@ -382,8 +413,11 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         const int L = a.L, M = a.M, Q = a.ctaps;
         const long long o_end = a.o0 + a.n_out;
         uint32_t tile_n = 0;
-        for (long long t = t_begin; t < t_end; ++t, ++tile_n) {
-            const UmmaTile T = umma_tile(a, geo, t);
+        int st_p = -1, my_st = -1;
+        double my_g = 0.0, my_inv = 0.0, st_g0 = 0.0, st_inv0 = 0.0;
+        unsigned st_mask = 0, st_slow = 0;
+        bool st_same = true;
+        umma_walk(a, geo, [&](const UmmaTile &T) {
             const int l0 = T.pt.l0 + 32 * h, pbv = max(0, min(32, T.pt.pbv - 32 * h));
             const long long j = geo.jc0 + (long long)T.tile_j * kUJB + m;          // this thread's cycle
             const int16_t *xc = a.x ? a.x + (long long)T.ch * a.x_stride : nullptr;
@@ -396,10 +430,19 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
             // and g per output from global memory made the warps that own phase 0 the slowest part of the whole kernel:
             // 8700 cycles of finish per tile against 1800.)  A tap too small for the division to recover x exactly keeps
             // the slow path.
-            const int my_st = lane < pbv ? __ldg(a.single_tap + l0 + lane) : -1;
-            const double my_g = my_st >= 0 ? __ldg(a.cbank + (long long)(l0 + lane) * Q + my_st) : 0.0;
-            const unsigned st_mask = __ballot_sync(0xffffffffu, my_st >= 0);
-            const unsigned st_slow = __ballot_sync(0xffffffffu, my_st >= 0 && !(fabs(my_g * a.gain) >= a.umma_scale * 1048576.0));
+            if (T.tile_p != st_p) {                            // once per phase tile, not per tile (two dependent loads)
+                st_p = T.tile_p;
+                my_st = lane < pbv ? __ldg(a.single_tap + l0 + lane) : -1;
+                my_g = my_st >= 0 ? __ldg(a.cbank + (long long)(l0 + lane) * Q + my_st) : 0.0;
+                my_inv = my_st >= 0 ? a.umma_scale / (my_g * a.gain) : 0.0;
+                st_mask = __ballot_sync(0xffffffffu, my_st >= 0);
+                st_slow = __ballot_sync(0xffffffffu, my_st >= 0 && !(fabs(my_g * a.gain) >= a.umma_scale * 1048576.0));
+                // the usual case (rows of one knife-edge phase, replicated): one tap value for all of them, no shuffles
+                const int first = st_mask ? __ffs((int)st_mask) - 1 : 0;
+                st_g0 = __shfl_sync(0xffffffffu, my_g, first);
+                st_inv0 = __shfl_sync(0xffffffffu, my_inv, first);
+                st_same = __all_sync(0xffffffffu, my_st < 0 || my_g == st_g0);
+            }
 
             UTRACE(warp - 2, tile_n, 0);
             mbar_wait(t_full, tile_n & 1u);
@@ -460,8 +503,11 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 if ((st_fast >> (8 * cg)) & 255u) {            // warp-uniform, one tile in L / 64
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        if ((st_fast >> (8 * cg + e)) & 1u)
-                            y[e] = umma_single_tap(park[2 * e], park[2 * e + 1], a.umma_scale, __shfl_sync(0xffffffffu, my_g, 8 * cg + e), a.gain);
+                        if ((st_fast >> (8 * cg + e)) & 1u) {
+                            const double g = st_same ? st_g0 : __shfl_sync(0xffffffffu, my_g, 8 * cg + e);
+                            const double inv = st_same ? st_inv0 : __shfl_sync(0xffffffffu, my_inv, 8 * cg + e);
+                            y[e] = umma_single_tap(park[2 * e], park[2 * e + 1], inv, g, a.gain);
+                        }
                 }
                 uint32_t packed[4];
 #pragma unroll
@@ -498,7 +544,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 }
             }
             UTRACE(warp - 2, tile_n, 3);
-            if (!GUARD) continue;
+            ++tile_n;
+            if (!GUARD) return;
             __syncwarp();
 
             // Second look at the outputs that came within the (wide) band of the integer evaluation: the whole warp evaluates
@@ -540,7 +587,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 }
                 pending = __ballot_sync(0xffffffffu, hits != 0);
             }
-        }
+        });
     }
 
     // ---- teardown: every MMA has completed (the epilogue waited for the last tile), nobody touches TMEM any more ----
@@ -647,6 +694,9 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         geo.frame_samples = pl.frame_samples;
         geo.n_frames = pl.n_frames;
         geo.rows_per_frame = pl.rows_per_frame;
+        // band of the tile walk: row blocks whose samples (both planes) make up ~32 MB, at least 8
+        const long long block_bytes = 2LL * kUJB * a.M;
+        geo.band = (int)max(8LL, min((long long)geo.n_cycle_tiles * n_channels, (32LL << 20) / block_bytes));
         // 1. byte planes of the slab
         const int spans_per_frame = (int)((geo.frame_pitch + kSplitSpan - 1) / kSplitSpan);
         dim3 sgrid((unsigned)((long long)spans_per_frame * geo.n_frames), (unsigned)n_channels);

@@ -4,10 +4,16 @@
 import sys, os, ctypes
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch, llzlab_b200 as z
-C_, frames = 8, 100
-slab = float(sys.argv[1]) if len(sys.argv) > 1 else 96.0
+slab = float(sys.argv[1]) if len(sys.argv) > 1 else 256.0
+what = sys.argv[2] if len(sys.argv) > 2 else "c4"
+C_, frames = (8, 100) if what == "c4" else (64, 500)
 for acc, name in ((z.ACC_F64, "exact"), (z.ACC_F32, "fast")):
-    bank = z.ResampleBank(z.KIND_RESAMPLE, 320, 147, C_, k_override=128, acc=acc)
+    if what == "c4":
+        bank = z.ResampleBank(z.KIND_RESAMPLE, 320, 147, C_, k_override=128, acc=acc)
+    elif what == "c3":
+        bank = z.ResampleBank(z.KIND_RESAMPLE, 1, 3, C_, acc=acc)
+    else:
+        bank = z.ResampleBank(z.KIND_INTERP, 4, 1, C_, acc=acc)
     bank.set_tiles(4)
     n = bank.info.num_in * frames
     x = torch.empty(C_, n, dtype=torch.int16, device="cuda")
@@ -22,7 +28,7 @@ for acc, name in ((z.ACC_F64, "exact"), (z.ACC_F32, "fast")):
     assert z.lib().llz_debug_umma_trace(t.ctypes.data_as(ctypes.c_void_p)) == 0
     t = t.reshape(16, 16, 16)
     t0 = t[1, 0, 0]
-    print(name, "slab", slab)
+    print(what, name, "slab", slab, "taps per phase", bank.info.taps_per_phase)
     for n_ in range(1, 7):
         print(f" tile {n_}: producer stage-free {[int(v - t0) for v in t[0, n_, :3]]}")
         print(f"         issuer t_empty-done {int(t[1, n_, 0] - t0)} s_full-done {[int(v - t0) for v in t[1, n_, 1:4]]} issued {int(t[1, n_, 8] - t0)}")
