@@ -415,8 +415,10 @@ class Workload:
         return f"fir_tile_kernel<{t}>", None, None
 
     # ---- the timed step -------------------------------------------------------------------------------
-    def step(self, gather: int = 0, chunks: int = 4):
+    def step(self, gather: int = 0, chunks: int = 0):
         z = self.z
+        if chunks == 0:                                 # the copy-engine push exposes 1 / chunks of the transfer: use the most
+            chunks = 8 if gather == z.GATHER_COPY else 4
         if self.job is not None:
             self.job.run(self.n_total, [self.dx_all], [self.x_stride], [self.dy], [self.out_count], self.total_out,
                          gather, chunks, [self.stream])
@@ -617,7 +619,7 @@ def measure(z, D: Dist, mg, name: str, dtype: str, algo: str, steps: int, warmup
         try:
             mg.result_alloc(0, W.C_total * W.total_out * W.es)
             own = checksum64(W.dy)
-            for mode, key in ((z.GATHER_NCCL, "nccl_chunked_send_recv"), (z.GATHER_PEER, "peer_store_fused")):
+            for mode, key in ((z.GATHER_NCCL, "nccl_chunked_send_recv"), (z.GATHER_PEER, "peer_store_fused"), (z.GATHER_COPY, "copy_engine_push")):
                 try:
                     gms, _, _ = W.time_steps(max(3, min(steps, 10)), 2, mode, sample_clocks=False)
                     # every rank's region of the gathered result against that rank's own shard

@@ -235,6 +235,9 @@ enum {
                                   ncclSend/ncclRecv on a second stream while piece c+1 is computed                   */
     LLZ_CUDA_GATHER_PEER = 2,  /* the kernels store straight into the root's buffer over NVLink (peer mapping / CUDA
                                   IPC): compute and gather are one kernel, nothing is staged                         */
+    LLZ_CUDA_GATHER_COPY = 3,  /* pieces like GATHER_NCCL, pushed into the root's buffer through the peer mapping by the
+                                  rank's copy engine on a second stream: needs no SM, so it overlaps kernels that
+                                  occupy every SM (the persistent tcgen05 and overlap-save kernels)                  */
 };
 typedef struct {
     int first_channel, n_channels;   /* channels owned by the rank                                                  */

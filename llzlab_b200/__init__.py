@@ -30,7 +30,7 @@ FIR_AUTO, FIR_DIRECT, FIR_FFT = 0, 1, 2
 ACC_F64, ACC_F64_STRICT, ACC_F32 = 0, 1, 2
 TILES_AUTO, TILES_INT8, TILES_FP64_TENSOR, TILES_CUDA_CORE, TILES_INT8_TCGEN05 = 0, 1, 2, 3, 4
 SHARD_CHANNEL, SHARD_TIME = 0, 1
-GATHER_NONE, GATHER_NCCL, GATHER_PEER = 0, 1, 2
+GATHER_NONE, GATHER_NCCL, GATHER_PEER, GATHER_COPY = 0, 1, 2, 3
 KIND_DECIMATE, KIND_INTERP, KIND_RESAMPLE = 0, 1, 2
 PCM_S16, PCM_S24, PCM_F32 = 0, 1, 2
 PLANAR_S16, PLANAR_F32, PLANAR_F64 = 0, 1, 2

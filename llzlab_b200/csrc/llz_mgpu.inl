@@ -20,6 +20,11 @@
 //   LLZ_CUDA_GATHER_NCCL  each rank computes its shard in chunks (groups of whole channels / runs of whole work items)
 //                         into its own buffer; chunk c travels to the root by grouped ncclSend / ncclRecv on a second
 //                         stream while chunk c+1 is computed.  The root's own shard is computed in place.
+//   LLZ_CUDA_GATHER_COPY  chunks like GATHER_NCCL, but chunk c is PUSHED into the root's buffer through the peer mapping by
+//                         the rank's copy engine (cudaMemcpyAsync on the second stream): no SM is needed for the
+//                         transfer, so it overlaps the persistent tcgen05 / FFT kernels, which leave no room for an
+//                         NCCL kernel beside them (measured at N = 2: compute + NCCL gather = the SUM of the two for
+//                         the resampler configs).
 // NCCL is loaded at run time (dlopen "libnccl.so.2": inside a PyTorch process that is the copy torch already loaded),
 // so the single-GPU drop-in path has no NCCL dependency.
 #include <dlfcn.h>
@@ -597,15 +602,17 @@ extern "C" int llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const
     if (!j || !api) return -1;
     MgpuCtx *c = j->ctx;
     if (!d_in || !in_stride || n_total < 0) { llz_set_error("mgpu_job_run: bad arguments"); return -1; }
-    if (gather != LLZ_CUDA_GATHER_NONE && gather != LLZ_CUDA_GATHER_NCCL && gather != LLZ_CUDA_GATHER_PEER) {
+    if (gather != LLZ_CUDA_GATHER_NONE && gather != LLZ_CUDA_GATHER_NCCL && gather != LLZ_CUDA_GATHER_PEER &&
+        gather != LLZ_CUDA_GATHER_COPY) {
         llz_set_error("unknown gather mode %d", gather);
         return -1;
     }
     if (gather == LLZ_CUDA_GATHER_NONE && (!d_out || !out_stride)) { llz_set_error("mgpu_job_run: no output buffers"); return -1; }
-    if (gather == LLZ_CUDA_GATHER_NCCL && (!d_out || !out_stride)) { llz_set_error("mgpu_job_run: the NCCL gather stages each shard in d_out"); return -1; }
+    const bool staged = gather == LLZ_CUDA_GATHER_NCCL || gather == LLZ_CUDA_GATHER_COPY;   // shards staged in d_out, moved chunk by chunk
+    if (staged && (!d_out || !out_stride)) { llz_set_error("mgpu_job_run: the chunked gathers stage each shard in d_out"); return -1; }
     if (chunks < 1) chunks = 4;
     if (chunks > kMaxChunks) chunks = kMaxChunks;
-    if (gather != LLZ_CUDA_GATHER_NCCL) chunks = 1;
+    if (!staged) chunks = 1;
     const size_t es = job_elem_size(j);
     const long long total_out = job_total_out(j, n_total);
     const int root = c->result_root;
@@ -632,7 +639,7 @@ extern "C" int llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const
         st[i] = streams ? (cudaStream_t)streams[i] : nullptr;
         if (!d_in[i]) { llz_set_error("mgpu_job_run: null input for local slot %d", i); return -1; }
         x_own[i] = static_cast<const unsigned char *>(d_in[i]) + (size_t)sh[i].seg.halo * es;
-        const bool to_result = gather == LLZ_CUDA_GATHER_PEER || (gather == LLZ_CUDA_GATHER_NCCL && s.rank == root);
+        const bool to_result = gather == LLZ_CUDA_GATHER_PEER || (staged && s.rank == root);
         if (to_result) {
             if (!s.result_ptr) {
                 llz_set_error("mgpu_job_run: rank %d has no peer mapping of the result buffer (no NVLink / P2P path); use LLZ_CUDA_GATHER_NCCL", s.rank);
@@ -642,6 +649,10 @@ extern "C" int llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const
             y_stride[i] = result_stride;
         } else {
             if (!d_out[i]) { llz_set_error("mgpu_job_run: null output for local slot %d", i); return -1; }
+            if (gather == LLZ_CUDA_GATHER_COPY && !s.result_ptr) {
+                llz_set_error("mgpu_job_run: rank %d has no peer mapping of the result buffer (no NVLink / P2P path); use LLZ_CUDA_GATHER_NCCL", s.rank);
+                return -1;
+            }
             if (gather == LLZ_CUDA_GATHER_NCCL && out_stride[i] != sh[i].seg.out_count) {
                 llz_set_error("mgpu_job_run: the NCCL gather needs dense shard outputs (out_stride %lld, shard has %lld outputs)",
                               out_stride[i], sh[i].seg.out_count);
@@ -669,7 +680,7 @@ extern "C" int llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const
                 if (llz_cuda_resample_bank_set_history(j->bank[i], static_cast<const short *>(d_in[i]), in_stride[i], st[i]) != 0) return -1;
             }
         }
-        if (gather == LLZ_CUDA_GATHER_NCCL) {
+        if (staged) {
             // the gather stream must not start before the caller's stream has reached this call (buffer reuse)
             LLZ_CUDA_TRY(cudaEventRecord(s.ev_enter, st[i]));
             LLZ_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_enter, 0));
@@ -688,9 +699,18 @@ extern "C" int llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const
                 for (int k2 = k + 1; k2 < chunks; ++k2)
                     if (job_chunk(j, sh[i], granule, chunks, k2).cc > 0) last_group = false;
             if (job_run_chunk(j, i, p, x_own[i], in_stride[i], y_base[i], y_stride[i], st[i], last_group) != 0) return -1;
-            if (gather == LLZ_CUDA_GATHER_NCCL) {
+            if (staged) {
                 LLZ_CUDA_TRY(cudaEventRecord(s.ev_chunk[k], st[i]));
                 LLZ_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_chunk[k], 0));
+            }
+            if (gather == LLZ_CUDA_GATHER_COPY && s.rank != root && p.cc > 0 && p.out_len > 0) {
+                // push the chunk into its place in the root's buffer: copy engine, second stream
+                const unsigned char *src = y_base[i] + ((size_t)p.c0 * y_stride[i] + p.out0) * es;
+                unsigned char *dst = static_cast<unsigned char *>(s.result_ptr) +
+                                     ((size_t)(sh[i].first_channel + p.c0) * result_stride + sh[i].seg.out_start + p.out0) * es;
+                if (copy_planar(dst, (size_t)result_stride * es, src, (size_t)y_stride[i] * es, (size_t)p.out_len * es, (size_t)p.cc,
+                                    cudaMemcpyDeviceToDevice, s.s_comm) != 0)
+                    return -1;
             }
         }
         if (gather != LLZ_CUDA_GATHER_NCCL) continue;
@@ -739,7 +759,15 @@ extern "C" int llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const
             LLZ_CUDA_TRY(cudaEventRecord(s.ev_comm, s.s_comm));
             LLZ_CUDA_TRY(cudaStreamWaitEvent(st[i], s.ev_comm, 0));
         }
-    } else if (gather == LLZ_CUDA_GATHER_PEER && c->world > 1) {
+    } else if ((gather == LLZ_CUDA_GATHER_PEER || gather == LLZ_CUDA_GATHER_COPY) && c->world > 1) {
+        if (gather == LLZ_CUDA_GATHER_COPY) {
+            for (int i = 0; i < c->nlocal; ++i) {              // the pushes of this rank precede its "done"
+                MgpuSlot &s = c->slot[i];
+                DeviceGuard g(s.device);
+                LLZ_CUDA_TRY(cudaEventRecord(s.ev_comm, s.s_comm));
+                LLZ_CUDA_TRY(cudaStreamWaitEvent(st[i], s.ev_comm, 0));
+            }
+        }
         // every rank's kernels have stored into the root's buffer: a one-int all-reduce on the callers' streams orders
         // "all ranks done" after each rank's kernels (stores to peer memory are performed at kernel completion)
         LLZ_NCCL_TRY(api, api->GroupStart());

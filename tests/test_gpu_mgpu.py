@@ -66,7 +66,7 @@ def zlib_cuda_memcpy(torch, dst, src_ptr, nbytes):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("gather", [0, 1, 2])
+@pytest.mark.parametrize("gather", [0, 1, 2, 3])
 @pytest.mark.parametrize("mode,taps,C_,n,dtype", [(0, 127, 37, 60_000, "f64"), (1, 127, 3, 400_000, "f64"),
                                                    (1, 2049, 2, 300_000, "f32"), (0, 31, 9, 20_000, "f64")])
 def test_fir_job_is_byte_identical_to_the_one_gpu_call(zlib, port, cuda, mgpu, gather, mode, taps, C_, n, dtype):
@@ -90,7 +90,7 @@ def test_fir_job_is_byte_identical_to_the_one_gpu_call(zlib, port, cuda, mgpu, g
     assert got.tobytes() == want.tobytes(), (gather, mode, taps, float(np.abs(got - want).max()))
 
 
-@pytest.mark.parametrize("gather", [0, 1, 2])
+@pytest.mark.parametrize("gather", [0, 1, 2, 3])
 @pytest.mark.parametrize("mode,L_,M,k,C_,frames", [(0, 1, 3, 0, 9, 12), (1, 320, 147, 128, 2, 9), (1, 160, 147, 0, 3, 7),
                                                     (0, 160, 147, 0, 5, 3)])
 def test_resample_job_is_byte_identical_to_the_one_gpu_call_and_the_oracle(zlib, port, cuda, mgpu, gather, mode, L_, M, k,

@@ -41,14 +41,14 @@ def check(name, job, one_gpu_result, x, n):
     want_shard = one_gpu_result[sh.first_channel:sh.first_channel + sh.n_channels,
                                 sh.seg.out_start:sh.seg.out_start + sh.seg.out_count]
     es = x.element_size()
-    for gather, gname in ((z.GATHER_NONE, "none"), (z.GATHER_NCCL, "nccl"), (z.GATHER_PEER, "peer")):
+    for gather, gname in ((z.GATHER_NONE, "none"), (z.GATHER_NCCL, "nccl"), (z.GATHER_PEER, "peer"), (z.GATHER_COPY, "copy")):
         out = torch.zeros(sh.n_channels, sh.seg.out_count, dtype=x.dtype, device="cuda")
         if gather != z.GATHER_NONE:
             ctx.result_alloc(0, C_ * n_out * es)
         job.run(n, [xin], [hi - lo], [out], [sh.seg.out_count], n_out, gather, 4, [torch.cuda.current_stream().cuda_stream])
         torch.cuda.synchronize()
         good = True
-        if gather == z.GATHER_NONE or (gather == z.GATHER_NCCL and rank != 0):
+        if gather == z.GATHER_NONE or (gather in (z.GATHER_NCCL, z.GATHER_COPY) and rank != 0):
             good = bool(torch.equal(out, want_shard))
         if gather != z.GATHER_NONE and rank == 0:
             full = torch.empty(C_, n_out, dtype=x.dtype, device="cuda")
