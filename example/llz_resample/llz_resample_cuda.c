@@ -2,12 +2,18 @@
  * llz_resample_cuda -- command-line harness over libllzfilter_cuda with the flags and the output-length
  * semantics of the reference's example/llz_resample (main.c:22-130, llz_parseopt.c:164-297):
  *
- *   llz_resample_cuda -i in.wav -o out.wav [-t 0|1|2] [-u up] [-d down] [-g gain] [-w]
+ *   llz_resample_cuda -i in.wav -o out.wav [-t 0|1|2] [-u up] [-d down] [-g gain] [-w] [-c]
  *
  *   -w  whole-file mode: read all samples, zero-pad to the same frame count, and run them through the handle in
  *       ONE call of the batched entry point (llz_cuda_resample_bank_run_host) instead of one llz_resample call
  *       per frame.  The bytes written are identical (a call of any length continues the stream exactly like
  *       the frame loop); it only removes the per-frame PCIe round trips.
+ *
+ *   -c  channels mode: honour fmt.channels (libllzaudio/llz_wavfmt.h:22-38).  The reference filters a multi-channel file as
+ *       ONE interleaved mono stream (quirk R7, main.c:60-62), which mixes the channels; with -c every channel is resampled
+ *       on its own (a bank of fmt.channels channels) straight from the interleaved frames -- the de-interleave is fused
+ *       into the kernel's load stage (llz_cuda_resample_bank_run_pcm_host) -- and the frames are written interleaved
+ *       again.  Same frame count rule per channel as the default mode.  The default stays R7-compatible.
  *
  *   -t 0 decimate by -d, 1 interpolate by -u, 2 (default) resample by -u/-d; defaults 160/147, gain 1.
  *   Giving only -u sets down = 1, only -d sets up = 1 (llz_parseopt.c:137-141).  Window: BLACKMAN (main.c:67-75).
@@ -77,12 +83,12 @@ static void wav_write_header(FILE *fp, const wav_info_t *w, uint32_t data_bytes)
 int main(int argc, char **argv)
 {
     const char *in = NULL, *out = NULL;
-    int type = 2, up = 160, down = 147, got_up = 0, got_down = 0, quiet = 0, whole = 0;
+    int type = 2, up = 160, down = 147, got_up = 0, got_down = 0, quiet = 0, whole = 0, chmode = 0;
     double gain = 1.0;
     static struct option lopts[] = {{"help", 0, 0, 'h'}, {"input", 1, 0, 'i'}, {"output", 1, 0, 'o'}, {"type", 1, 0, 't'},
-                                    {"down", 1, 0, 'd'}, {"up", 1, 0, 'u'}, {"gain", 1, 0, 'g'}, {"quiet", 0, 0, 'q'}, {"whole", 0, 0, 'w'}, {0, 0, 0, 0}};
+                                    {"down", 1, 0, 'd'}, {"up", 1, 0, 'u'}, {"gain", 1, 0, 'g'}, {"quiet", 0, 0, 'q'}, {"whole", 0, 0, 'w'}, {"channels", 0, 0, 'c'}, {0, 0, 0, 0}};
     int c;
-    while ((c = getopt_long(argc, argv, "hqwi:o:t:d:u:g:", lopts, NULL)) != -1) {
+    while ((c = getopt_long(argc, argv, "hqwci:o:t:d:u:g:", lopts, NULL)) != -1) {
         switch (c) {
         case 'i': in = optarg; break;
         case 'o': out = optarg; break;
@@ -92,6 +98,7 @@ int main(int argc, char **argv)
         case 'g': gain = atof(optarg); break;
         case 'q': quiet = 1; break;
         case 'w': whole = 1; break;
+        case 'c': chmode = 1; break;
         default:
             fprintf(stderr, "usage: %s -i in.wav -o out.wav [-t 0|1|2] [-u up] [-d down] [-g gain]\n", argv[0]);
             return c == 'h' ? 0 : -1;
@@ -113,6 +120,43 @@ int main(int argc, char **argv)
     if (wav_read_info(fi, &w) != 0) return -1;
     if (w.format != 1) { fprintf(stderr, "error! unsupported WAVE file format.\n"); return -1; }
     fseek(fi, 44, SEEK_SET);
+
+    if (chmode) {
+        /* one bank channel per WAV channel, interleaved frames in and out */
+        if (w.bytes_per_sample != 2 || w.channels < 1) { fprintf(stderr, "error! -c needs 16-bit PCM\n"); return -1; }
+        const int C = w.channels;
+        unsigned long hb = type == 0 ? llz_cuda_decimate_bank_init(down, gain, BLACKMAN, C, LLZ_CUDA_ACC_F64)
+                         : type == 1 ? llz_cuda_interp_bank_init(up, gain, BLACKMAN, C, LLZ_CUDA_ACC_F64)
+                                     : llz_cuda_resample_bank_init(up, down, gain, BLACKMAN, 0, C, LLZ_CUDA_ACC_F64);
+        if (hb == (unsigned long)-1) { fprintf(stderr, "init failed: %s\n", llz_cuda_last_error()); return -1; }
+        llz_cuda_resample_info_t bi_;
+        llz_cuda_resample_bank_info(hb, &bi_);
+        long pos = ftell(fi);
+        fseek(fi, 0, SEEK_END);
+        long data_bytes = ftell(fi) - pos;
+        fseek(fi, pos, SEEK_SET);
+        if (data_bytes < 0) data_bytes = 0;
+        const long long pcm_frames = data_bytes / (2L * C);
+        const long long nframes = pcm_frames / bi_.num_in + 1;                 /* the reference's rule, per channel */
+        const long long n_in = nframes * bi_.num_in, cap = nframes * bi_.num_out;
+        short *xi = calloc((size_t)n_in * C, 2), *xo = malloc((size_t)cap * C * 2);
+        if (!xi || !xo) { fprintf(stderr, "out of memory\n"); return -1; }
+        if (fread(xi, 2 * (size_t)C, (size_t)pcm_frames, fi) != (size_t)pcm_frames) { fprintf(stderr, "short read\n"); return -1; }
+        long long n_out = 0;
+        if (llz_cuda_resample_bank_run_pcm_host(hb, xi, LLZ_CUDA_PCM_S16, n_in, xo, LLZ_CUDA_PCM_S16, cap, &n_out) != 0) {
+            fprintf(stderr, "run failed: %s\n", llz_cuda_last_error());
+            return -1;
+        }
+        w.samplerate = type == 0 ? w.samplerate / down : type == 1 ? w.samplerate * up : (uint32_t)(((uint64_t)w.samplerate * up) / down);
+        wav_write_header(fo, &w, (uint32_t)(n_out * C * 2));
+        fseek(fo, 44, SEEK_SET);
+        fwrite(xo, 2 * (size_t)C, (size_t)n_out, fo);
+        if (!quiet) printf("frames = %lld, channels = %d, output bytes = %lld\n", nframes, C, n_out * C * 2);
+        llz_resample_filter_uninit(hb);
+        free(xi); free(xo);
+        fclose(fi); fclose(fo);
+        return 0;
+    }
 
     unsigned long h;
     uint32_t rate_out;

@@ -178,6 +178,18 @@ int llz_cuda_resample_bank_run(unsigned long handle, const short *d_in, long lon
 int llz_cuda_resample_bank_run_host(unsigned long handle, const short *h_in, long long in_stride,
                                     long long n_in, short *h_out, long long out_stride,
                                     long long *n_out);
+/* Interleaved PCM frames in (formats: LLZ_CUDA_PCM_* below, channels = the bank's n_channels):
+ * d_frames holds n_frames frames; channel c of the bank filters sample c of every frame, converted to the int16 the
+ * resampler works on exactly as llz_cuda_pcm_deinterleave does (s16 as is, s24 >> 8, f32 trunc(clamp(x * 2^15))).
+ * The output is planar int16 like llz_cuda_resample_bank_run's.  For calls large enough for the tcgen05 kernel the
+ * de-interleave is FUSED into the kernel's load stage (its pre-pass gathers the channels straight out of the frames:
+ * no planar copy of the input is written); frame-sized calls de-interleave into a scratch buffer first.
+ * _host: file-sized jobs from and to host memory, interleaved frames out (any LLZ_CUDA_PCM_* format).               */
+int llz_cuda_resample_bank_run_pcm(unsigned long handle, const void *d_frames, int pcm_format, long long n_frames,
+                                   short *d_out, long long out_stride, long long *n_out, llz_cuda_stream_t stream);
+int llz_cuda_resample_bank_run_pcm_host(unsigned long handle, const void *h_frames, int in_format, long long n_frames,
+                                        void *h_out_frames, int out_format, long long out_cap_frames,
+                                        long long *n_out_frames);
 /* kernel launches of the handle's last run call and the name of the kernel that did the filtering (reporting only) */
 int llz_cuda_resample_bank_last_run(unsigned long handle, int *launches, char *kernel, int kernel_cap);
 /* outputs that took the reference-order recompute (near-integer guard) since init */

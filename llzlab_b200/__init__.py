@@ -139,6 +139,8 @@ _SIGNATURES = [
     ("llz_cuda_resample_bank_run_host", C.c_int, [_ul, _vp, _ll, _ll, _vp, _ll, C.POINTER(_ll)]),
     ("llz_cuda_resample_bank_guard_count", _ll, [_ul]),
     ("llz_cuda_resample_bank_last_run", C.c_int, [_ul, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    ("llz_cuda_resample_bank_run_pcm", C.c_int, [_ul, _vp, C.c_int, _ll, _vp, _ll, C.POINTER(_ll), _vp]),
+    ("llz_cuda_resample_bank_run_pcm_host", C.c_int, [_ul, _vp, C.c_int, _ll, _vp, C.c_int, _ll, C.POINTER(_ll)]),
     ("llz_cuda_resample_bank_set_tiles", C.c_int, [_ul, C.c_int]),
     ("llz_cuda_resample_bank_set_guard_scale", C.c_int, [_ul, C.c_double]),
     ("llz_cuda_shard_channels", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -511,6 +513,20 @@ class ResampleBank:
         _check(lib().llz_cuda_resample_bank_run_host(self.handle, _ptr(h_in), in_stride, n_in, _ptr(h_out),
                                                      out_stride, C.byref(n_out)),
                "llz_cuda_resample_bank_run_host")
+        return n_out.value
+
+    def run_pcm(self, d_frames, pcm_format: int, n_frames: int, d_out, out_stride: int, stream: int = 0) -> int:
+        """interleaved PCM frames (device) in, planar int16 out; returns the outputs per channel"""
+        n_out = _ll(0)
+        _check(lib().llz_cuda_resample_bank_run_pcm(self.handle, _ptr(d_frames), pcm_format, n_frames, _ptr(d_out), out_stride,
+                                                    C.byref(n_out), stream), "llz_cuda_resample_bank_run_pcm")
+        return n_out.value
+
+    def run_pcm_host(self, h_frames, in_format: int, n_frames: int, h_out, out_format: int, out_cap: int) -> int:
+        """interleaved PCM frames (host) in and out; returns the output frames"""
+        n_out = _ll(0)
+        _check(lib().llz_cuda_resample_bank_run_pcm_host(self.handle, _ptr(h_frames), in_format, n_frames, _ptr(h_out), out_format,
+                                                         out_cap, C.byref(n_out)), "llz_cuda_resample_bank_run_pcm_host")
         return n_out.value
 
     def last_run(self):

@@ -65,7 +65,9 @@ constexpr int kUMaxStages = 4;
 // planes[plane][channel][f * frame_pitch + e] = byte `plane` of X(S_base + f * frame_samples + e) for e < frame_samples,
 // zero for the rest of the pitch;  S_base = jc0*M - (Q-1) + shift,  X = the stream sample of llz_poly_kernels.h.  One
 // CTA splits kSplitSpan consecutive bytes of one frame of one channel: the span arrives by a bulk copy (poly_stage_span:
-// history, zeros and ragged ends are resolved there) and leaves as two coalesced byte streams.
+// history, zeros and ragged ends are resolved there) and leaves as two coalesced byte streams.  With interleaved PCM input
+// (llz_cuda_resample_bank_run_pcm: s16 / s24 / f32 frames of several channels) the same stage de-interleaves and converts:
+// the threads gather the channel's samples out of the frames, so no planar copy of the input is ever written.
 constexpr int kSplitSpan = 8192, kSplitThreads = 256;
 
 __global__ void __launch_bounds__(kSplitThreads)
@@ -79,7 +81,7 @@ poly_split_planes_kernel(PolyLaunch a, UmmaGeom geo, unsigned char *planes, int 
     const long long e0 = (long long)(blockIdx.x % spans_per_frame) * kSplitSpan;    // first byte of the span within its frame
     const int span = (int)min((long long)kSplitSpan, geo.frame_pitch - e0);          // a multiple of 16
     const int need = (int)max(0LL, min((long long)span, geo.frame_samples - e0));    // samples that come from the stream
-    const int16_t *xc = a.x ? a.x + (long long)ch * a.x_stride : nullptr;
+    const int16_t *xc = poly_channel_base(a, ch);              // planar row, or the channel's samples inside interleaved PCM frames
     const int16_t *hc = a.hist ? a.hist + (long long)ch * a.hist_len : nullptr;
     const long long S0 = geo.jc0 * (long long)a.M - (a.ctaps - 1) + a.shift + f * geo.frame_samples + e0;
     bool bulk = false;
@@ -420,7 +422,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         umma_walk(a, geo, [&](const UmmaTile &T) {
             const int l0 = T.pt.l0 + 32 * h, pbv = max(0, min(32, T.pt.pbv - 32 * h));
             const long long j = geo.jc0 + (long long)T.tile_j * kUJB + m;          // this thread's cycle
-            const int16_t *xc = a.x ? a.x + (long long)T.ch * a.x_stride : nullptr;
+            const int16_t *xc = poly_channel_base(a, T.ch);
             const int16_t *hc = a.hist ? a.hist + (long long)T.ch * a.hist_len : nullptr;
             int16_t *ych = a.y + (long long)T.ch * a.y_stride;
             // Single-tap (knife-edge) phases of this half tile, one bit per phase; lane e keeps the tap of phase l0 + e.  Such

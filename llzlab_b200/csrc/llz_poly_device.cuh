@@ -11,11 +11,34 @@ namespace llz {
 
 // ---- shared device helpers ---------------------------------------------------------------------
 
+// one interleaved PCM sample as the int16 the resampler filters: s16 as is, s24 >> 8, f32 trunc(clamp(x * 2^15)) -- the
+// conversions of llz_cuda_pcm.cu (llz_cuda_pcm_deinterleave to planar s16), so the fused path equals de-interleave + run
+__device__ __forceinline__ int pcm_load_s16(int fmt, const unsigned char *p)
+{
+    if (fmt == LLZ_CUDA_PCM_S16) return (int)*reinterpret_cast<const int16_t *>(p);
+    if (fmt == LLZ_CUDA_PCM_S24) return (int)(int16_t)((uint32_t)p[1] | ((uint32_t)p[2] << 8));
+    float v = *reinterpret_cast<const float *>(p) * 32768.0f;
+    v = fminf(fmaxf(v, -32768.0f), 32767.0f);
+    return __float2int_rz(v);
+}
+
+// base pointer of channel ch of this call's input (planar: its row; interleaved: its first sample)
+__device__ __forceinline__ const int16_t *poly_channel_base(const PolyLaunch &a, int ch)
+{
+    if (!a.x) return nullptr;
+    if (a.pcm_frame_bytes > 0) return reinterpret_cast<const int16_t *>(reinterpret_cast<const unsigned char *>(a.x) + (size_t)ch * a.pcm_sample_bytes);
+    return a.x + (long long)ch * a.x_stride;
+}
+
 __device__ __forceinline__ int poly_sample(const PolyLaunch &a, const int16_t *xc, const int16_t *hc,
                                            long long s)
 {
     const long long sp = s - a.in0;
-    if (sp >= 0) return (sp < a.n_in && xc) ? (int)xc[sp] : 0;
+    if (sp >= 0) {
+        if (sp >= a.n_in || !xc) return 0;
+        if (a.pcm_frame_bytes > 0) return pcm_load_s16(a.pcm_fmt, reinterpret_cast<const unsigned char *>(xc) + sp * a.pcm_frame_bytes);
+        return (int)xc[sp];
+    }
     if (hc && sp >= -(long long)a.hist_len) return (int)hc[a.hist_len + sp];
     return 0;
 }
@@ -47,7 +70,7 @@ __device__ __forceinline__ PolySpanPlan poly_span_plan(const PolyLaunch &a, cons
     long long lo_al = lo & ~7LL;                               // >= max(rel_al, 0): inside x, at or after raw[0]
     long long hi_al = (hi + 7) & ~7LL;
     if (hi_al > a.n_in) hi_al = hi & ~7LL;
-    p.tma = xc != nullptr && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && hi_al > lo_al;
+    p.tma = xc != nullptr && a.pcm_frame_bytes == 0 && (reinterpret_cast<uintptr_t>(xc) & 15u) == 0 && hi_al > lo_al;
     if (!p.tma) lo_al = hi_al = lo;                            // no aligned run: the two fringes meet at lo
     p.lo_al = lo_al;
     p.bytes = (uint32_t)(hi_al - lo_al) * 2u;

@@ -21,6 +21,10 @@ struct PolyLaunch {
     const int16_t *x;          // device planar input of this call (nullptr = zeros)
     long long x_stride;
     long long n_in;
+    // Interleaved PCM input (llz_cuda_resample_bank_run_pcm; only the tcgen05 path takes it): pcm_frame_bytes > 0 means x
+    // points at frames of that many bytes, channel c's sample at byte c * pcm_sample_bytes of a frame, format pcm_fmt
+    // (LLZ_CUDA_PCM_*); a channel's base pointer is then (char *)x + c * pcm_sample_bytes and x_stride is unused.
+    int pcm_frame_bytes, pcm_sample_bytes, pcm_fmt;
     const int16_t *hist;       // device [channels][hist_len]: samples just before x[0]; may be nullptr
     int hist_len;
     int16_t *y;

@@ -486,6 +486,16 @@ struct PolyBank {
     int umma_nchunks = 0;
     int umma_planes = 0, umma_shift = 0;   // digit planes (5 exact / 3 fast) and the scale 2^-shift of those tables
     double umma_eps = 0.0;                 // bound on |sum_k (g gain - q 2^-shift) x| for |x| <= 32768
+    // interleaved PCM input of the call in progress (llz_cuda_resample_bank_run_pcm), nullptr otherwise
+    const void *pcm_frames = nullptr;
+    int pcm_fmt = 0;
+    int16_t *d_pcm_tail = nullptr;         // [channels][hist_len]: the call's last samples de-interleaved, for the history
+    int16_t *d_pcm_planar = nullptr;       // scratch: small calls are de-interleaved first (pcm_planar_cap samples per channel)
+    long long pcm_planar_cap = 0;
+    void *d_pcm_io[2] = {nullptr, nullptr};   // host-frames entry point: device staging of a chunk's input / output frames
+    size_t pcm_io_cap[2] = {0, 0};
+    int16_t *d_pcm_out = nullptr;          // ... and its planar output
+    size_t pcm_out_cap = 0;
     int last_launches = 0;                 // kernel launches and dominant kernel of the last run call
     const char *last_kernel = "";
     int urep = 1;                          // the tcgen05 kernel sees the bank replicated urep times (llz_umma_tables.h)
@@ -542,6 +552,11 @@ void poly_destroy(PolyBank *b)
     cudaFree(b->d_umma_tiles);
     cudaFree(b->d_umma_rows);
     cudaFree(b->d_cbank_u);
+    cudaFree(b->d_pcm_tail);
+    cudaFree(b->d_pcm_planar);
+    cudaFree(b->d_pcm_io[0]);
+    cudaFree(b->d_pcm_io[1]);
+    cudaFree(b->d_pcm_out);
     cudaFree(b->d_single_u);
     cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
@@ -746,6 +761,8 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
     if (n_out) *n_out = outs;
     if (n_in == 0) return 0;
     if (outs > 0 && !d_out) { llz_set_error("null output pointer"); return -1; }
+    const bool pcm = b->pcm_frames != nullptr;
+    if (pcm && (c0 != 0 || cc != b->n_channels || defer_history)) { llz_set_error("internal: PCM input takes the whole bank"); return -1; }
     if (b->poisoned) { llz_set_error("resampler handle: an earlier host pipeline call failed half-way; reset the handle first"); return -1; }
     if (trail_enter(b->trail, st) != 0) return -1;
 
@@ -801,6 +818,13 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
     bool launched = false;
     if (b->d_umma_tiles && outs > 0 && (b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
         PolyLaunch u = a;
+        if (pcm) {                                             // the pre-pass gathers the channels out of the frames
+            const int bps = b->pcm_fmt == LLZ_CUDA_PCM_S16 ? 2 : b->pcm_fmt == LLZ_CUDA_PCM_S24 ? 3 : 4;
+            u.x = static_cast<const int16_t *>(b->pcm_frames);
+            u.pcm_sample_bytes = bps;
+            u.pcm_frame_bytes = bps * b->n_channels;
+            u.pcm_fmt = b->pcm_fmt;
+        }
         u.L = p.L * b->urep;
         u.M = p.M * b->urep;
         u.cbank = b->d_cbank_u;
@@ -844,7 +868,22 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
         }
     }
 no_umma:
+    if (pcm && !launched) { llz_set_error("internal: interleaved input reached a kernel that needs planar samples"); return -1; }
     if (!launched && poly_launch(a, cc, st) != 0) return -1;
+    if (pcm && p.hist_len > 0) {
+        // history from interleaved input: de-interleave the call's last samples, then the usual splice
+        const long long tail = n_in < p.hist_len ? n_in : p.hist_len;
+        const int bps = b->pcm_fmt == LLZ_CUDA_PCM_S16 ? 2 : b->pcm_fmt == LLZ_CUDA_PCM_S24 ? 3 : 4;
+        if (!b->d_pcm_tail) LLZ_CUDA_TRY(cudaMalloc(&b->d_pcm_tail, (size_t)p.hist_len * b->n_channels * sizeof(int16_t)));
+        const unsigned char *src = static_cast<const unsigned char *>(b->pcm_frames) + (size_t)(n_in - tail) * bps * b->n_channels;
+        if (llz_cuda_pcm_deinterleave(src, b->pcm_fmt, b->n_channels, tail, b->d_pcm_tail, LLZ_CUDA_PLANAR_S16, p.hist_len, st) != 0) return -1;
+        d_in = b->d_pcm_tail;
+        in_stride = p.hist_len;
+        const int16_t *old = b->hist_zero ? nullptr : b->d_hist[b->cur];
+        if (poly_update_history(d_in, in_stride, tail, old, b->d_hist[b->cur ^ 1], p.hist_len, cc, st) != 0) return -1;
+        b->cur ^= 1;
+        b->hist_zero = false;
+    } else
     if (defer_history && p.hist_len > 0 && n_in >= p.hist_len && b->n_channels == 1) {
         b->chain_src = d_in + (n_in - p.hist_len);
     } else if (p.hist_len > 0) {
@@ -1278,6 +1317,107 @@ extern "C" int llz_cuda_resample_bank_run(unsigned long handle, const short *d_i
     if (!d_in && n_in > 0) { llz_set_error("null input pointer"); return -1; }
     DeviceGuard g(b->device);
     return poly_run(b, d_in, in_stride, n_in, d_out, out_stride, n_out, (cudaStream_t)stream);
+}
+
+// ---- interleaved PCM frames in (fused into the load stage) ----
+namespace {
+
+int pcm_sample_bytes(int fmt) { return fmt == LLZ_CUDA_PCM_S16 ? 2 : fmt == LLZ_CUDA_PCM_S24 ? 3 : fmt == LLZ_CUDA_PCM_F32 ? 4 : 0; }
+
+// will poly_run_part put this call on the tcgen05 kernel (whose pre-pass reads the frames directly)?
+bool poly_pcm_fused(PolyBank *b, long long n_in)
+{
+    const llz_plan_t &p = b->plan;
+    if (!b->d_umma_tiles || !(b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) return false;
+    const long long outs = poly_out_len(b, n_in);
+    if (outs <= 0) return false;
+    PolyLaunch u{};
+    u.L = p.L * b->urep; u.M = p.M * b->urep; u.ctaps = p.ctaps; u.frame_len = p.frame_len;
+    if (poly_bank_umma_rows_bytes(u, b->n_channels, llz::kUJB) == 0) return false;
+    const long long cycles = (b->produced + outs - 1) / u.L - b->produced / u.L + 1;
+    const long long n_tiles = (cycles + llz::kUJB - 1) / llz::kUJB * ((u.L + llz::kUPB - 1) / llz::kUPB) * b->n_channels;
+    const int sms = device_sm_count();
+    return b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05 || (sms > 0 && n_tiles >= 4LL * sms);
+}
+
+}  // namespace
+
+extern "C" int llz_cuda_resample_bank_run_pcm(unsigned long handle, const void *d_frames, int pcm_format, long long n_frames,
+                                              short *d_out, long long out_stride, long long *n_out, llz_cuda_stream_t stream)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    if (pcm_sample_bytes(pcm_format) == 0) { llz_set_error("unknown PCM format %d", pcm_format); return -1; }
+    if (!d_frames && n_frames > 0) { llz_set_error("null input pointer"); return -1; }
+    if (n_frames < 0) { llz_set_error("negative frame count"); return -1; }
+    DeviceGuard g(b->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_frames > 0 && poly_pcm_fused(b, n_frames)) {
+        b->pcm_frames = d_frames;
+        b->pcm_fmt = pcm_format;
+        const int rc = poly_run(b, nullptr, 0, n_frames, d_out, out_stride, n_out, st);
+        b->pcm_frames = nullptr;
+        return rc;
+    }
+    // frame-sized calls: de-interleave first (llz_cuda_pcm.cu), then the planar kernels
+    if (n_frames > b->pcm_planar_cap) {
+        LLZ_CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(b->d_pcm_planar);
+        b->d_pcm_planar = nullptr;
+        b->pcm_planar_cap = 0;
+        LLZ_CUDA_TRY(cudaMalloc(&b->d_pcm_planar, (size_t)n_frames * b->n_channels * sizeof(int16_t)));
+        b->pcm_planar_cap = n_frames;
+    }
+    if (n_frames > 0 && llz_cuda_pcm_deinterleave(d_frames, pcm_format, b->n_channels, n_frames, b->d_pcm_planar, LLZ_CUDA_PLANAR_S16,
+                                                  n_frames, stream) != 0)
+        return -1;
+    return poly_run(b, b->d_pcm_planar, n_frames, n_frames, d_out, out_stride, n_out, st);
+}
+
+extern "C" int llz_cuda_resample_bank_run_pcm_host(unsigned long handle, const void *h_frames, int in_format, long long n_frames,
+                                                   void *h_out_frames, int out_format, long long out_cap_frames,
+                                                   long long *n_out_frames)
+{
+    PolyBank *b = as_poly(handle);
+    if (!b) return -1;
+    const int ibs = pcm_sample_bytes(in_format), obs = pcm_sample_bytes(out_format);
+    if (!ibs || !obs) { llz_set_error("unknown PCM format"); return -1; }
+    if (n_frames < 0 || (n_frames > 0 && (!h_frames || !h_out_frames))) { llz_set_error("run_pcm_host: bad arguments"); return -1; }
+    const llz_plan_t &p = b->plan;
+    const int C = b->n_channels;
+    const long long total_out = poly_out_len(b, n_frames);
+    if (n_out_frames) *n_out_frames = total_out;
+    if (total_out > out_cap_frames) { llz_set_error("run_pcm_host: %lld output frames, room for %lld", total_out, out_cap_frames); return -1; }
+    if (n_frames == 0) return 0;
+    DeviceGuard g(b->device);
+    // chunks of whole reference frames (keeps interp legal); one stream: this entry point is for file-sized jobs
+    long long chunk = (long long)(256.0 * 1024 * 1024 / ((double)ibs * C));
+    chunk = chunk / p.num_in * p.num_in;
+    if (chunk < p.num_in) chunk = p.num_in;
+    if (chunk > n_frames) chunk = n_frames;
+    const long long chunk_out = (long long)ceil((double)chunk * p.L / p.M) + 2;
+    const size_t need_in = (size_t)chunk * C * ibs, need_out = (size_t)chunk_out * C * obs, need_pl = (size_t)chunk_out * C * sizeof(int16_t);
+    if (need_in > b->pcm_io_cap[0]) { cudaFree(b->d_pcm_io[0]); b->pcm_io_cap[0] = 0; LLZ_CUDA_TRY(cudaMalloc(&b->d_pcm_io[0], need_in)); b->pcm_io_cap[0] = need_in; }
+    if (need_out > b->pcm_io_cap[1]) { cudaFree(b->d_pcm_io[1]); b->pcm_io_cap[1] = 0; LLZ_CUDA_TRY(cudaMalloc(&b->d_pcm_io[1], need_out)); b->pcm_io_cap[1] = need_out; }
+    if (need_pl > b->pcm_out_cap) { cudaFree(b->d_pcm_out); b->pcm_out_cap = 0; LLZ_CUDA_TRY(cudaMalloc(&b->d_pcm_out, need_pl)); b->pcm_out_cap = need_pl; }
+    long long done_out = 0;
+    for (long long f0 = 0; f0 < n_frames; f0 += chunk) {
+        const long long nf = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+        LLZ_CUDA_TRY(cudaMemcpyAsync(b->d_pcm_io[0], static_cast<const unsigned char *>(h_frames) + (size_t)f0 * C * ibs, (size_t)nf * C * ibs,
+                                     cudaMemcpyHostToDevice, nullptr));
+        long long outs = 0;
+        if (llz_cuda_resample_bank_run_pcm(handle, b->d_pcm_io[0], in_format, nf, b->d_pcm_out, chunk_out, &outs, nullptr) != 0) return -1;
+        if (outs > chunk_out) { llz_set_error("internal: chunk produced %lld outputs", outs); return -1; }
+        if (outs > 0) {
+            if (llz_cuda_pcm_interleave(b->d_pcm_out, LLZ_CUDA_PLANAR_S16, chunk_out, C, outs, b->d_pcm_io[1], out_format, nullptr) != 0) return -1;
+            LLZ_CUDA_TRY(cudaMemcpyAsync(static_cast<unsigned char *>(h_out_frames) + (size_t)done_out * C * obs, b->d_pcm_io[1],
+                                         (size_t)outs * C * obs, cudaMemcpyDeviceToHost, nullptr));
+        }
+        LLZ_CUDA_TRY(cudaStreamSynchronize(nullptr));
+        done_out += outs;
+    }
+    if (done_out != total_out) { llz_set_error("internal: %lld of %lld output frames", done_out, total_out); return -1; }
+    return 0;
 }
 
 static int poly_run_host_body(unsigned long handle, const short *h_in, long long in_stride,

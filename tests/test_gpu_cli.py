@@ -118,3 +118,32 @@ def test_other_cli_modes(sweep, args, port, cuda):
     if mode == 2 and os.path.exists(REF_CLI):
         run(REF_CLI, ["-i", "short.wav", "-o", f"r_{tag}.wav"] + args, d)
         assert open(d / f"r_{tag}.wav", "rb").read() == ours
+
+
+def test_cli_channels_mode_resamples_every_channel_on_its_own(tmp_path, port, cuda):
+    """-c: a stereo WAV is two channels, not one interleaved mono stream (quirk R7); each output channel must be the
+    reference's output for that input channel (zero-padded to the reference's frame count), interleaved again"""
+    if not os.path.exists(OUR_CLI):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(OUR_CLI)])
+    rate, seconds, C_ = 44100, 9, 2
+    n = rate * seconds
+    t = np.arange(n, dtype=np.float64) / rate
+    left = np.round(0.6 * 32767 * np.sin(2 * np.pi * (100.0 * t + 900.0 * t * t))).astype("<i2")
+    right = port.lcg_s16(n, 4242).astype("<i2")
+    frames = np.stack([left, right], axis=1)
+    hdr = b"RIFF" + struct.pack("<I", 36 + frames.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, C_, rate, rate * 2 * C_, 2 * C_, 16)
+    hdr += b"data" + struct.pack("<I", frames.nbytes)
+    with open(tmp_path / "stereo.wav", "wb") as f:
+        f.write(hdr)
+        f.write(frames.tobytes())
+    run(OUR_CLI, ["-i", "stereo.wav", "-o", "out.wav", "-q", "-c"], tmp_path)
+    out = open(tmp_path / "out.wav", "rb").read()
+    plan = port.resample_plan(160, 147, 1)
+    nfr = n // plan.num_in + 1
+    assert struct.unpack("<H", out[22:24])[0] == C_ and struct.unpack("<I", out[24:28])[0] == 48000
+    got = np.frombuffer(out[44:], dtype="<i2").reshape(-1, C_)
+    assert got.shape[0] == nfr * plan.num_out
+    for c, ch in enumerate((left, right)):
+        x = np.zeros(nfr * plan.num_in, np.int16)
+        x[:n] = ch
+        assert np.array_equal(got[:, c], port.resample_run(plan, 1.0, x, nfr * plan.num_out)), c

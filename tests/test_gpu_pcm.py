@@ -107,3 +107,70 @@ def test_bad_arguments(zlib, cuda):
     t = cuda.zeros(64, dtype=cuda.int16, device="cuda")
     assert L.llz_cuda_pcm_deinterleave(t.data_ptr(), 7, 2, 10, t.data_ptr(), 0, 10, None) == -1
     assert L.llz_cuda_pcm_deinterleave(t.data_ptr(), 0, 0, 10, t.data_ptr(), 0, 10, None) == -1
+
+
+@pytest.mark.parametrize("fmt", ["s16", "s24", "f32"])
+@pytest.mark.parametrize("kind,L_,M,C_", [("resample", 160, 147, 2), ("resample", 1, 3, 6), ("interp", 4, 1, 2)])
+def test_resampler_reads_interleaved_frames_directly(zlib, port, cuda, fmt, kind, L_, M, C_):
+    """llz_cuda_resample_bank_run_pcm: the de-interleave (and the s24 / f32 conversion) is fused into the load stage of the
+    tcgen05 kernel.  The result must be what de-interleaving first and running the planar entry point gives -- which for
+    s16 is the reference's output per channel, bit for bit -- across two calls (the history comes from interleaved input)."""
+    torch = cuda
+    if kind == "interp":
+        bank = zlib.ResampleBank(zlib.KIND_INTERP, L_, 1, C_)
+        ref = zlib.ResampleBank(zlib.KIND_INTERP, L_, 1, C_)
+        plan = port.interp_plan(L_, 1)
+    else:
+        bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, C_)
+        ref = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, C_)
+        plan = port.resample_plan(L_, M, 1)
+    bank.set_tiles(zlib.TILES_INT8_TCGEN05)
+    n = plan.num_in * 6
+    rng = np.random.default_rng(L_ * 100 + M + C_)
+    if fmt == "s16":
+        frames = rng.integers(-32768, 32768, size=(n, C_), dtype=np.int16)
+        planar = np.ascontiguousarray(frames.T)
+        raw, code = frames, zlib.PCM_S16
+    elif fmt == "s24":
+        v = rng.integers(-(1 << 23), 1 << 23, size=(n, C_), dtype=np.int32)
+        raw = np.zeros((n, C_, 3), np.uint8)
+        raw[..., 0], raw[..., 1], raw[..., 2] = v & 255, (v >> 8) & 255, (v >> 16) & 255
+        planar = np.ascontiguousarray((v >> 8).astype(np.int16).T)
+        code = zlib.PCM_S24
+    else:
+        f = (rng.random((n, C_), dtype=np.float32) * 2.2 - 1.1).astype(np.float32)        # some samples clip
+        raw, code = f, zlib.PCM_F32
+        planar = np.ascontiguousarray(np.trunc(np.clip(f * np.float32(32768.0), -32768.0, 32767.0)).astype(np.int16).T)
+    d_raw = torch.from_numpy(raw.view(np.uint8).reshape(-1).copy()).cuda()
+    bps = {"s16": 2, "s24": 3, "f32": 4}[fmt]
+    n_out = ref.out_len(n)
+    want = torch.zeros(C_, n_out, dtype=torch.int16, device="cuda")
+    ref.run(torch.from_numpy(planar).cuda(), n, n, want, n_out)
+    got = torch.zeros(C_, n_out, dtype=torch.int16, device="cuda")
+    cut = plan.num_in * 2
+    o1 = bank.run_pcm(d_raw, code, cut, got, n_out)
+    assert bank.last_run()[1].startswith("poly_bank_umma_kernel")
+    o2 = bank.run_pcm(d_raw.data_ptr() + cut * C_ * bps, code, n - cut, got.data_ptr() + 2 * o1, n_out)
+    torch.cuda.synchronize()
+    assert o1 + o2 == n_out
+    assert torch.equal(got, want)
+    if fmt == "s16" and kind == "resample":
+        for c in range(C_):
+            assert np.array_equal(got[c].cpu().numpy(), port.resample_run(plan, 1.0, planar[c], n_out))
+    bank.close(); ref.close()
+
+
+def test_run_pcm_host_stereo_file_sized_job(zlib, port, cuda):
+    """host frames in, host frames out (what the CLI's --channels mode calls): every channel of the interleaved result is
+    the reference's output for that channel"""
+    L_, M, C_ = 160, 147, 2
+    bank = zlib.ResampleBank(zlib.KIND_RESAMPLE, L_, M, C_)
+    plan = port.resample_plan(L_, M, 1)
+    n = plan.num_in * 40
+    frames = np.stack([port.lcg_s16(n, 900 + c) for c in range(C_)], axis=1).copy()
+    n_out = bank.out_len(n)
+    out = np.zeros((n_out, C_), np.int16)
+    assert bank.run_pcm_host(frames, zlib.PCM_S16, n, out, zlib.PCM_S16, n_out) == n_out
+    for c in range(C_):
+        assert np.array_equal(out[:, c], port.resample_run(plan, 1.0, np.ascontiguousarray(frames[:, c]), n_out))
+    bank.close()
