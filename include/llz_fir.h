@@ -48,7 +48,11 @@ void          llz_fir_filter_uninit(unsigned long handle);
  * llz_fir_filter: y[t] = sum_{i<flt_len} h[i]*x[t-i] for one frame (frame_len <= the init-time
  * frame_len); returns frame_len (llz_fir.c:582).  buf_in and buf_out may alias.
  * llz_fir_filter_flush: pushes zeros and emits the flt_len-1 tail samples; returns flt_len-1
- * (llz_fir.c:624).  Both return -1 on a CUDA error instead of asserting.                      */
+ * (llz_fir.c:624).  Both return -1 on a CUDA error instead of asserting.
+ * Bit-identical to the reference for FINITE input.  The kernel pads the taps to a multiple of 16 with zeros, which
+ * multiply up to 15 samples older than x[t-flt_len+1] that the reference never reads: an Inf or NaN there turns into
+ * NaN here (0 * Inf) in outputs the reference leaves finite.  The tolerance-mode banks (overlap-save) spread a
+ * non-finite sample over its whole block.                                                       */
 int llz_fir_filter(unsigned long handle, double *buf_in, double *buf_out, int frame_len);
 int llz_fir_filter_flush(unsigned long handle, double *buf_out);
 
