@@ -332,7 +332,8 @@ def test_c3_shape_spot_checks(zlib, port, cuda):
 
 
 @pytest.mark.parametrize("tiles", [1, 2, 3, 4])
-@pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0), (1, 3, 0), (2, 1, 0), (1, 4, 0)])
+@pytest.mark.parametrize("L_,M,k", [(160, 147, 0), (320, 147, 128), (147, 160, 0), (3, 2, 0), (1, 3, 0), (2, 1, 0), (1, 4, 0),
+                                    (513, 512, 0)])          # 513 x 32 phases: the last tcgen05 phase tile is half empty
 def test_bank_exact_mode_integer_and_fp64_tensor_tiles(zlib, port, cuda, L_, M, k, tiles):
     """The exact mode's four tile kernels: INT8 tensor cores through mma.sync (1) and through tcgen05 with TMEM
     accumulators (4) -- taps as five int8 digit planes, samples as two byte planes, exact s32 accumulation, a two-level
