@@ -298,6 +298,20 @@ int           llz_cuda_mgpu_job_run(unsigned long job, long long n_total, const 
                                     const llz_cuda_stream_t *streams);
 
 /* ======================================================================================== */
+/* IIR banks (drop-in: llz_iir.h)                                        */
+/* ======================================================================================== */
+/* n_channels independent direct-form IIR filters with the same coefficients (llz_iir.c:103-132), planar doubles on
+ * device pointers, asynchronous on `stream`; one GPU thread per channel (the recurrence is serial in time), the
+ * reference's operation order, bit-identical doubles.  The last N inputs and M outputs of every channel stay in the
+ * handle, so consecutive calls continue the streams.  a[0..M] (a[0] taken as 1), b[0..N] (NULL = zeros); M, N <= 32.
+ * d_x == NULL feeds zeros (the flush).  d_x and d_y may alias.                                                      */
+unsigned long llz_cuda_iir_bank_init(int M, const double *a, int N, const double *b, int n_channels);
+void          llz_cuda_iir_bank_uninit(unsigned long handle);
+int           llz_cuda_iir_bank_reset(unsigned long handle, llz_cuda_stream_t stream);
+int           llz_cuda_iir_bank_run(unsigned long handle, const double *d_x, long long x_stride, double *d_y,
+                                    long long y_stride, long long n, llz_cuda_stream_t stream);
+
+/* ======================================================================================== */
 /* Interleaved PCM frames <-> planar channels                           */
 /* ======================================================================================== */
 /* The reference filters a multi-channel WAV as one interleaved mono stream (quirk R7,

@@ -138,6 +138,14 @@ _SIGNATURES = [
     ("llz_cuda_resample_bank_run", C.c_int, [_ul, _vp, _ll, _ll, _vp, _ll, C.POINTER(_ll), _vp]),
     ("llz_cuda_resample_bank_run_host", C.c_int, [_ul, _vp, _ll, _ll, _vp, _ll, C.POINTER(_ll)]),
     ("llz_cuda_resample_bank_guard_count", _ll, [_ul]),
+    ("llz_cuda_iir_bank_init", _ul, [C.c_int, _dp, C.c_int, _dp, C.c_int]),
+    ("llz_cuda_iir_bank_uninit", None, [_ul]),
+    ("llz_cuda_iir_bank_reset", C.c_int, [_ul, _vp]),
+    ("llz_cuda_iir_bank_run", C.c_int, [_ul, _vp, _ll, _vp, _ll, _ll, _vp]),
+    ("llz_iir_filter_init", _ul, [C.c_int, _dp, C.c_int, _dp]),
+    ("llz_iir_filter_uninit", None, [_ul]),
+    ("llz_iir_filter", C.c_int, [_ul, _dp, _dp, C.c_int]),
+    ("llz_iir_filter_flush", C.c_int, [_ul, _dp]),
     ("llz_cuda_resample_bank_last_run", C.c_int, [_ul, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     ("llz_cuda_resample_bank_run_pcm", C.c_int, [_ul, _vp, C.c_int, _ll, _vp, _ll, C.POINTER(_ll), _vp]),
     ("llz_cuda_resample_bank_run_pcm_host", C.c_int, [_ul, _vp, C.c_int, _ll, _vp, C.c_int, _ll, C.POINTER(_ll)]),
@@ -464,6 +472,59 @@ class FirBank:
             self.close()
         except Exception:
             pass
+
+
+class IirBank:
+    """n independent direct-form IIR filters (llz_cuda_iir_bank_*), planar doubles on the device"""
+
+    def __init__(self, a, b, n_channels: int):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64) if b is not None else None
+        h = lib().llz_cuda_iir_bank_init(len(a) - 1, a.ctypes.data_as(_dp), (len(b) - 1) if b is not None else 0,
+                                         b.ctypes.data_as(_dp) if b is not None else None, n_channels)
+        self.handle = _handle(h, "llz_cuda_iir_bank_init")
+        self.n_channels = n_channels
+
+    def run(self, d_x, x_stride: int, d_y, y_stride: int, n: int, stream: int = 0):
+        _check(lib().llz_cuda_iir_bank_run(self.handle, _ptr(d_x), x_stride, _ptr(d_y), y_stride, n, stream), "llz_cuda_iir_bank_run")
+
+    def reset(self, stream: int = 0):
+        _check(lib().llz_cuda_iir_bank_reset(self.handle, stream), "llz_cuda_iir_bank_reset")
+
+    def close(self):
+        if self.handle:
+            lib().llz_cuda_iir_bank_uninit(self.handle)
+            self.handle = 0
+
+
+class IirFilter:
+    """the drop-in handle of llz_iir.h: host frames in, host frames out"""
+
+    def __init__(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64) if b is not None else None
+        self.N = (len(b) - 1) if b is not None else 0
+        h = lib().llz_iir_filter_init(len(a) - 1, a.ctypes.data_as(_dp), self.N, b.ctypes.data_as(_dp) if b is not None else None)
+        self.handle = _handle(h, "llz_iir_filter_init")
+
+    def filter(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        if lib().llz_iir_filter(self.handle, x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), len(x)) != len(x):
+            raise LlzError("llz_iir_filter: " + last_error())
+        return y
+
+    def flush(self) -> np.ndarray:
+        y = np.empty(max(self.N, 1), dtype=np.float64)
+        n = lib().llz_iir_filter_flush(self.handle, y.ctypes.data_as(_dp))
+        if n < 0:
+            raise LlzError("llz_iir_filter_flush: " + last_error())
+        return y[:n]
+
+    def close(self):
+        if self.handle:
+            lib().llz_iir_filter_uninit(self.handle)
+            self.handle = 0
 
 
 class ResampleBank:

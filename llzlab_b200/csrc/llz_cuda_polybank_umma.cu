@@ -105,18 +105,10 @@ poly_split_planes_kernel(PolyLaunch a, UmmaGeom geo, unsigned char *planes, int 
 }
 
 // ---- tcgen05 helpers ---------------------------------------------------------------------------------------------------
-// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row atoms of 128 bytes, 1024 bytes between atoms
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);           // start address >> 4
-    d |= (uint64_t)1 << 16;                                // leading byte offset: unused for swizzled K-major operands
-    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: the next 8-row group
-    d |= (uint64_t)1 << 46;                                // descriptor version of sm_100
-    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
-    return d;
-}
-
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row atoms of 128 bytes, 1024 bytes between atoms): bits 0-13
+// start address >> 4, 16-29 leading byte offset (unused for swizzled K-major operands: 1), 32-45 stride byte offset >> 4
+// (1024: the next 8-row group), 46 descriptor version of sm_100, 61-63 swizzle mode (2 = 128 B).  See umma_desc_lo /
+// kUDescHi below.
 // instruction descriptor: s32 accumulators; A = u8 (0) or s8 (1), B = s8; both K-major; N = 64, M = 128
 __host__ __device__ constexpr uint32_t umma_idesc(int a_signed)
 {

@@ -27,6 +27,8 @@
 #include "llz_imma_tables.h"
 #include "llz_poly_kernels.h"
 #include "llz_umma_tables.h"
+#include "llz_iir_kernels.h"
+#include "llz_iir.h"
 
 namespace {
 
@@ -1525,6 +1527,171 @@ extern "C" long long llz_cuda_resample_bank_guard_count(unsigned long handle)
     if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return -1; }
     LLZ_CUDA_TRY(cudaMemcpy(&v, b->d_guard, sizeof v, cudaMemcpyDeviceToHost));
     return (long long)v;
+}
+
+// ====================================================================================================
+// IIR banks and drop-in handles (llz_iir.h, llz_cuda.h): replaces llz_iir.c:38-156
+// ====================================================================================================
+namespace {
+
+constexpr uint32_t kMagicIir = 0x4C5A4949u;                 // "LZII"
+
+struct IirBank {
+    uint32_t magic = kMagicIir;
+    int device = 0;
+    int M = 0, N = 0, n_channels = 1;
+    double a[llz::kIirMaxOrder + 1] = {0}, b[llz::kIirMaxOrder + 1] = {0};
+    double *d_state = nullptr;          // [channels][2 * kIirMaxOrder]
+    // drop-in frames (one channel): page-locked staging + device frame, grown on demand; own stream
+    double *pinned = nullptr, *d_frame = nullptr;
+    int frame_cap = 0;
+    cudaStream_t s_frame = nullptr;
+};
+
+IirBank *as_iir(unsigned long handle)
+{
+    if (handle == 0 || handle == kFail) { llz_set_error("invalid IIR handle"); return nullptr; }
+    IirBank *b = reinterpret_cast<IirBank *>(handle);
+    if (b->magic != kMagicIir) { llz_set_error("handle is not an IIR handle"); return nullptr; }
+    return b;
+}
+
+void iir_destroy(IirBank *b)
+{
+    DeviceGuard g(b->device);
+    cudaFree(b->d_state);
+    cudaFree(b->d_frame);
+    if (b->pinned) cudaFreeHost(b->pinned);
+    if (b->s_frame) cudaStreamDestroy(b->s_frame);
+    b->magic = 0;
+    delete b;
+}
+
+int iir_run(IirBank *b, const double *d_x, long long x_stride, double *d_y, long long y_stride, long long n, cudaStream_t st)
+{
+    if (n < 0) { llz_set_error("negative sample count"); return -1; }
+    if (n == 0) return 0;
+    if (!d_y) { llz_set_error("null output pointer"); return -1; }
+    llz::IirLaunch a{};
+    a.M = b->M; a.N = b->N; a.n_channels = b->n_channels;
+    memcpy(a.a, b->a, sizeof a.a);
+    memcpy(a.b, b->b, sizeof a.b);
+    a.x = d_x; a.x_stride = x_stride; a.y = d_y; a.y_stride = y_stride; a.n = n;
+    a.state = b->d_state; a.state_stride = 2 * llz::kIirMaxOrder;
+    return llz::iir_launch(a, st);
+}
+
+int iir_frame_room(IirBank *b, int n)
+{
+    if (n <= b->frame_cap) return 0;
+    if (!b->s_frame) LLZ_CUDA_TRY(cudaStreamCreateWithFlags(&b->s_frame, cudaStreamNonBlocking));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    if (b->pinned) cudaFreeHost(b->pinned);
+    cudaFree(b->d_frame);
+    b->pinned = b->d_frame = nullptr;
+    b->frame_cap = 0;
+    const int cap = n < 4096 ? 4096 : n;
+    LLZ_CUDA_TRY(cudaHostAlloc(&b->pinned, sizeof(double) * (size_t)cap, cudaHostAllocDefault));
+    LLZ_CUDA_TRY(cudaMalloc(&b->d_frame, sizeof(double) * (size_t)cap));
+    b->frame_cap = cap;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" unsigned long llz_cuda_iir_bank_init(int M, const double *a, int N, const double *b, int n_channels)
+{
+    if (M < 0 || N < 0 || M > llz::kIirMaxOrder || N > llz::kIirMaxOrder) {
+        llz_set_error("IIR orders must be in [0, %d] (got M = %d, N = %d)", llz::kIirMaxOrder, M, N);
+        return kFail;
+    }
+    if (!a && M > 0) { llz_set_error("null pole coefficients"); return kFail; }
+    if (n_channels < 1 || n_channels > (1 << 24)) { llz_set_error("bad channel count %d", n_channels); return kFail; }
+    int dev = 0;
+    if (require_device(&dev) != 0) return kFail;
+    IirBank *h = new (std::nothrow) IirBank();
+    if (!h) { llz_set_error("out of memory"); return kFail; }
+    h->device = dev; h->M = M; h->N = N; h->n_channels = n_channels;
+    for (int i = 0; i <= M && a; ++i) h->a[i] = a[i];                      // a[0] is taken as 1 (llz_iir.c:52)
+    for (int i = 0; i <= N && b; ++i) h->b[i] = b[i];                      // b == NULL: all zero (llz_iir.c:56-60)
+    const size_t bytes = (size_t)n_channels * 2 * llz::kIirMaxOrder * sizeof(double);
+    cudaError_t e;
+    if ((e = cudaMalloc(&h->d_state, bytes)) != cudaSuccess || (e = cudaMemset(h->d_state, 0, bytes)) != cudaSuccess ||
+        (e = cudaDeviceSynchronize()) != cudaSuccess) {
+        llz_set_error("IIR bank init: %s", cudaGetErrorString(e));
+        iir_destroy(h);
+        return kFail;
+    }
+    return reinterpret_cast<unsigned long>(h);
+}
+
+extern "C" void llz_cuda_iir_bank_uninit(unsigned long handle)
+{
+    IirBank *b = as_iir(handle);
+    if (b) iir_destroy(b);
+}
+
+extern "C" int llz_cuda_iir_bank_reset(unsigned long handle, llz_cuda_stream_t stream)
+{
+    IirBank *b = as_iir(handle);
+    if (!b) return -1;
+    DeviceGuard g(b->device);
+    LLZ_CUDA_TRY(cudaMemsetAsync(b->d_state, 0, (size_t)b->n_channels * 2 * llz::kIirMaxOrder * sizeof(double), (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int llz_cuda_iir_bank_run(unsigned long handle, const double *d_x, long long x_stride, double *d_y,
+                                     long long y_stride, long long n, llz_cuda_stream_t stream)
+{
+    IirBank *b = as_iir(handle);
+    if (!b) return -1;
+    DeviceGuard g(b->device);
+    return iir_run(b, d_x, x_stride, d_y, y_stride, n, (cudaStream_t)stream);
+}
+
+extern "C" unsigned long llz_iir_filter_init(int M, double *a, int N, double *b)
+{
+    return llz_cuda_iir_bank_init(M, a, N, b, 1);
+}
+
+extern "C" void llz_iir_filter_uninit(unsigned long handle)
+{
+    llz_cuda_iir_bank_uninit(handle);
+}
+
+extern "C" int llz_iir_filter(unsigned long handle, double *x, double *y, int frame_len)
+{
+    IirBank *b = as_iir(handle);
+    if (!b) return -1;
+    if (b->n_channels != 1) { llz_set_error("llz_iir_filter needs a handle from llz_iir_filter_init"); return -1; }
+    if (frame_len < 0 || (frame_len > 0 && (!x || !y))) { llz_set_error("llz_iir_filter: bad arguments"); return -1; }
+    if (frame_len == 0) return 0;
+    DeviceGuard g(b->device);
+    if (iir_frame_room(b, frame_len) != 0) return -1;
+    const size_t bytes = sizeof(double) * (size_t)frame_len;
+    memcpy(b->pinned, x, bytes);
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->d_frame, b->pinned, bytes, cudaMemcpyHostToDevice, b->s_frame));
+    if (iir_run(b, b->d_frame, 0, b->d_frame, 0, frame_len, b->s_frame) != 0) return -1;      // in place: the tile is staged
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned, b->d_frame, bytes, cudaMemcpyDeviceToHost, b->s_frame));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    memcpy(y, b->pinned, bytes);
+    return frame_len;                                                       // llz_iir.c:143
+}
+
+extern "C" int llz_iir_filter_flush(unsigned long handle, double *y)
+{
+    IirBank *b = as_iir(handle);
+    if (!b) return -1;
+    if (b->n_channels != 1) { llz_set_error("llz_iir_filter_flush needs a handle from llz_iir_filter_init"); return -1; }
+    if (b->N == 0) return 0;
+    if (!y) { llz_set_error("llz_iir_filter_flush: null output"); return -1; }
+    DeviceGuard g(b->device);
+    if (iir_frame_room(b, b->N) != 0) return -1;
+    if (iir_run(b, nullptr, 0, b->d_frame, 0, b->N, b->s_frame) != 0) return -1;               // N zeros in (llz_iir.c:152-153)
+    LLZ_CUDA_TRY(cudaMemcpyAsync(b->pinned, b->d_frame, sizeof(double) * (size_t)b->N, cudaMemcpyDeviceToHost, b->s_frame));
+    LLZ_CUDA_TRY(cudaStreamSynchronize(b->s_frame));
+    memcpy(y, b->pinned, sizeof(double) * (size_t)b->N);
+    return b->N;                                                            // llz_iir.c:155
 }
 
 // ====================================================================================================

@@ -76,6 +76,8 @@ class Port:
         L.orc_fir_design.argtypes = [C.POINTER(_dp), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
         L.orc_fir_run.argtypes = [_dp, C.c_int, _dp, _dp, C.c_longlong, _dp, C.c_longlong]
         L.orc_fir_run.restype = None
+        L.orc_iir_run.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_longlong, _dp]
+        L.orc_iir_run.restype = None
         for f in (L.orc_resample_plan,):
             f.argtypes = [C.POINTER(_Plan), C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_decimate_plan.argtypes = [C.POINTER(_Plan), C.c_int, C.c_int]
@@ -136,6 +138,19 @@ class Port:
             hp = hist.ctypes.data_as(_dp)
         self.lib.orc_fir_run(h.ctypes.data_as(_dp), len(h), hp, x.ctypes.data_as(_dp), len(x),
                              y.ctypes.data_as(_dp), n_out)
+        return y
+
+    def iir_run(self, a: np.ndarray, b: np.ndarray, x: np.ndarray | None, n: int | None = None, state=None):
+        """llz_iir_filter over x (or n zeros when x is None: the flush); state = (xs, ys) arrays updated in place"""
+        a = np.ascontiguousarray(a, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        M, N = len(a) - 1, len(b) - 1
+        if state is None:
+            state = (np.zeros(N + 1), np.zeros(M + 1))
+        if x is not None:
+            x = np.ascontiguousarray(x, dtype=np.float64); n = len(x)
+        y = np.empty(n, dtype=np.float64)
+        self.lib.orc_iir_run(M, a.ctypes.data_as(_dp), N, b.ctypes.data_as(_dp), state[0].ctypes.data_as(_dp),
+                             state[1].ctypes.data_as(_dp), x.ctypes.data_as(_dp) if x is not None else None, n, y.ctypes.data_as(_dp))
         return y
 
     def resample_plan(self, L: int, M: int, win: int, k_override: int = 0) -> Plan | None:
@@ -239,8 +254,33 @@ class Ref:
         for name in ("decimate", "interp", "resample"):
             getattr(L, f"ref_llz_{name}").argtypes = [ul, C.c_void_p, C.c_int, C.c_void_p,
                                                       C.POINTER(C.c_int)]
+        if hasattr(L, "ref_llz_iir_filter_init"):
+            L.ref_llz_iir_filter_init.argtypes = [C.c_int, _dp, C.c_int, _dp]
+            L.ref_llz_iir_filter_init.restype = ul
+            L.ref_llz_iir_filter_uninit.argtypes = [ul]
+            L.ref_llz_iir_filter_uninit.restype = None
+            L.ref_llz_iir_filter.argtypes = [ul, _dp, _dp, C.c_int]
+            L.ref_llz_iir_filter_flush.argtypes = [ul, _dp]
         self._free = C.CDLL(None).free
         self._free.argtypes = [C.c_void_p]
+
+    def iir_stream(self, a: np.ndarray, b: np.ndarray, x: np.ndarray, frame: int = 1024, flush: bool = True) -> np.ndarray:
+        """the reference's llz_iir_filter frame by frame (+ llz_iir_filter_flush)"""
+        a = np.ascontiguousarray(a, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        M, N = len(a) - 1, len(b) - 1
+        h = self.lib.ref_llz_iir_filter_init(M, a.ctypes.data_as(_dp), N, b.ctypes.data_as(_dp))
+        out = []
+        for t0 in range(0, len(x), frame):
+            xi = np.ascontiguousarray(x[t0:t0 + frame]); yo = np.empty(len(xi))
+            self.lib.ref_llz_iir_filter(h, xi.ctypes.data_as(_dp), yo.ctypes.data_as(_dp), len(xi))
+            out.append(yo)
+        if flush and N > 0:
+            yo = np.empty(N)
+            self.lib.ref_llz_iir_filter_flush(h, yo.ctypes.data_as(_dp))
+            out.append(yo)
+        self.lib.ref_llz_iir_filter_uninit(h)
+        return np.concatenate(out) if out else np.empty(0)
 
     # -- design ------------------------------------------------------------------------------
     def window(self, N: int, win: int) -> np.ndarray:

@@ -159,6 +159,26 @@ void orc_fir_run(const double *h, int N, const double *hist,
     }
 }
 
+/* ------------------------------------------------------------------ IIR ------------------- */
+
+/* libllzfilter/llz_iir.c:103-132 as a whole-signal loop: y[n] = sum_{k<=N} b[k] x[n-k] - sum_{1<=k<=M} a[k] y[n-k], the b
+ * terms first, k ascending, every product and sum rounded separately (no contraction); xs / ys carry the N / M samples
+ * before x[0] / y[0] (oldest first, like the reference's shift buffers) and are updated for the next call */
+void orc_iir_run(int M, const double *a, int N, const double *b, double *xs, double *ys,
+                 const double *x, long long n, double *y)
+{
+    for (long long t = 0; t < n; t++) {
+        for (int i = 0; i < N; i++) xs[i] = xs[i + 1];               /* :115-117 */
+        xs[N] = x ? x[t] : 0.0;                                      /* x == NULL: the flush's zeros (:151) */
+        for (int i = 0; i < M; i++) ys[i] = ys[i + 1];               /* :119-120 */
+        double acc = 0.0;
+        for (int k = 0; k <= N; k++) { double p = b[k] * xs[N - k]; acc = acc + p; }    /* :122-123 */
+        for (int k = 1; k <= M; k++) { double p = a[k] * ys[M - k]; acc = acc - p; }    /* :124-125 */
+        ys[M] = acc;
+        y[t] = acc;
+    }
+}
+
 /* ------------------------------------------------------------------ plans ----------------- */
 
 static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }

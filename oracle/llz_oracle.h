@@ -36,6 +36,9 @@ int    orc_fir_design(double **h, int kind, int N, double fc1, double fc2, int w
 /* y[t] = sum_{i<N} h[i]*x[t-i], i ascending, separate mul and add: llz_fir.c:411-426, 547-584.
  * hist = the N-1 samples before x[0] (NULL = zeros).  n_out may exceed n_in (flush: x beyond
  * n_in reads as 0, llz_fir.c:590-625). */
+/* xs: N+1 doubles, ys: M+1 doubles of stream state (zero for a fresh filter) */
+void   orc_iir_run(int M, const double *a, int N, const double *b, double *xs, double *ys,
+                   const double *x, long long n, double *y);
 void   orc_fir_run(const double *h, int N, const double *hist,
                    const double *x, long long n_in, double *y, long long n_out);
 

@@ -20,7 +20,7 @@ llz_get_resample_framelen_bytes""".split()
 
 def declared_functions():
     names = set()
-    for hdr in ("llz_fir.h", "llz_resample.h", "llz_cuda.h"):
+    for hdr in ("llz_fir.h", "llz_resample.h", "llz_iir.h", "llz_cuda.h"):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported(zlib):
 
 
 def test_headers_compile_as_c_and_match_reference_names():
-    src = '#include "llz_fir.h"\n#include "llz_resample.h"\n#include "llz_cuda.h"\n' \
+    src = '#include "llz_fir.h"\n#include "llz_resample.h"\n#include "llz_iir.h"\n#include "llz_cuda.h"\n' \
           "int main(void){win_t w=BLACKMAN; return (int)w + HAMMING + KAISER + LLZ_RATIO_MAX - LLZ_DEFAULT_FRAMELEN;}\n"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                     "-x", "c", "-"], input=src.encode(), check=True)

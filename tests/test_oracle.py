@@ -195,3 +195,17 @@ def test_phase0_knife_edge(port):
     src = np.where(idx >= 0, x[np.maximum(idx, 0)], 0).astype(np.int32)
     expect = np.where(src > 0, src - 1, np.where(src < 0, src + 1, 0))
     assert np.array_equal(y[m].astype(np.int32), expect)
+
+
+@pytest.mark.parametrize("a,b", [([1.0, -1.8, 0.81], [0.2, 0.3, 0.2]), ([1.0, -0.5], [1.0]), ([1.0], [0.25, 0.25, 0.25, 0.25]),
+                                 ([1.0, -2.369513, 2.313988, -1.054665, 0.187379], [0.004824, 0.019297, 0.028946, 0.019297, 0.004824])])
+def test_iir_restatement_vs_reference(port, ref, a, b):
+    """llz_iir.c:103-156 frame by frame (+ flush) against the whole-signal restatement, bit for bit"""
+    a, b = np.array(a), np.array(b)
+    x = port.lcg_f64(6000, 77)
+    want = ref.iir_stream(a, b, x, frame=1024)
+    st = (np.zeros(len(b)), np.zeros(len(a)))
+    got = [port.iir_run(a, b, x, state=st)]
+    if len(b) > 1:
+        got.append(port.iir_run(a, b, None, len(b) - 1, state=st))
+    assert np.concatenate(got).tobytes() == want.tobytes()
