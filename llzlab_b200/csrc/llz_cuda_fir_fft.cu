@@ -274,7 +274,8 @@ static int fir_fft_launch_cfg(const FirFftLaunch<T> &a, int n_channels, long lon
 {
     if (fir_fft_run<T, WARPS, PACK, STAGE ? kStaged : kGather>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0)
         return -1;
-    return fir_fft_run<T, WARPS, PACK, kEdge>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
+    return fir_fft_run<T, WARPS, PACK, kEdge>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count,
+                                              a.side ? a.side : stream);
 }
 
 template <typename T>

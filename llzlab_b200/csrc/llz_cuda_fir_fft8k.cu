@@ -337,7 +337,7 @@ int fir_fft8k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     const int rc = stage ? fir_fft8k_run<T, false, true>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream)
                          : fir_fft8k_run<T, false, false>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream);
     if (rc != 0) return -1;
-    return fir_fft8k_run<T, true, false>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
+    return fir_fft8k_run<T, true, false>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, a.side ? a.side : stream);
 }
 
 template int fir_fft8k_launch<float>(FirFftLaunch<float>, int, cudaStream_t);

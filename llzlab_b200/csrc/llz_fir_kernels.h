@@ -57,6 +57,9 @@ struct FirFftLaunch {
     int skew;              // 8192- / 16384-point kernels: cycles by which warps 4..7 of a CTA trail warps 0..3 after the first exchange
     int n_channels;
     long long first_pair, items_per_channel, gap_start, gap_len;
+    // The edge items (first / last of every channel) are an independent launch: on `side` (already ordered after the
+    // caller's stream by the shim, which also joins it back) they run beside the interior items instead of after them.
+    cudaStream_t side;     // nullptr: everything on the caller's stream
 };
 
 template <typename T>

@@ -182,6 +182,8 @@ long long pick_chunk(long long n, int n_channels, double bytes_per_in_sample)
 // ---- FIR bank --------------------------------------------------------------------------------------
 struct FirBank {
     uint32_t magic = kMagicFir;
+    cudaStream_t s_side = nullptr;      // edge items + history update of the overlap-save path run beside the interior items
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int device = 0;
     int dtype = LLZ_CUDA_F64;
     int n_channels = 1;
@@ -226,6 +228,9 @@ void fir_destroy(FirBank *b)
     if (!b) return;
     DeviceGuard g(b->device);
     b->pipe.destroy();
+    if (b->s_side) cudaStreamDestroy(b->s_side);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->d_taps) cudaFree(b->d_taps);
     if (b->d_fft_H) cudaFree(b->d_fft_H);
     if (b->d_fft_tw) cudaFree(b->d_fft_tw);
@@ -423,9 +428,24 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
                (cc == 1 || ((in_stride * sizeof(T)) % 16 == 0 && (out_stride * sizeof(T)) % 16 == 0));
     const int algo = fir_effective_algo(b);
     if (algo < 0) return -1;
+    // Overlap-save banks: the edge items and the history update are independent of the interior items (they write other
+    // outputs / the other history buffer), so they run on a side stream beside them: fork here, join at the end.  On a
+    // strong-scaled shard (C2 at N = 8: 0.24 ms per step) the two extra launches in series were 10 % of the step.
+    cudaStream_t side = nullptr;
+    if (algo == LLZ_CUDA_FIR_ALGO_FFT && !defer_history && b->fft_size != 16384) {
+        if (!b->s_side) {
+            LLZ_CUDA_TRY(cudaStreamCreateWithFlags(&b->s_side, cudaStreamNonBlocking));
+            LLZ_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+            LLZ_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+        }
+        side = b->s_side;
+        LLZ_CUDA_TRY(cudaEventRecord(b->ev_fork, st));
+        LLZ_CUDA_TRY(cudaStreamWaitEvent(side, b->ev_fork, 0));
+    }
     if (algo == LLZ_CUDA_FIR_ALGO_FFT) {
         if (fir_fft_tables(b) != 0) return -1;
         FirFftLaunch<T> f{};
+        f.side = side;
         f.x = a.x; f.x_stride = in_stride; f.y = a.y; f.y_stride = out_stride; f.n = n;
         f.hist = a.hist; f.ntaps = b->flt_len;
         f.H = static_cast<const T *>(b->d_fft_H);
@@ -442,12 +462,16 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
         b->chain_src = a.x + (n - b->hist_len);                // the caller keeps d_in intact until the next call
     } else if (b->hist_len > 0) {
         T *next = static_cast<T *>(b->d_hist[b->cur ^ 1]) + (size_t)c0 * b->hist_len;
-        if (fir_update_history<T>(a.x, in_stride, n, a.hist, next, b->hist_len, cc, st) != 0) return -1;
+        if (fir_update_history<T>(a.x, in_stride, n, a.hist, next, b->hist_len, cc, side ? side : st) != 0) return -1;
         if (last) {
             b->cur ^= 1;
             b->hist_zero = false;
             b->chain_src = nullptr;                            // a deferred history has been folded into d_hist
         }
+    }
+    if (side) {
+        LLZ_CUDA_TRY(cudaEventRecord(b->ev_join, side));
+        LLZ_CUDA_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
     }
     return 0;
 }
@@ -500,6 +524,7 @@ struct PolyBank {
     size_t pcm_out_cap = 0;
     int last_launches = 0;                 // kernel launches and dominant kernel of the last run call
     const char *last_kernel = "";
+    bool umma_tried = false;               // poly_umma_prepare has run (tables exist iff umma_nchunks > 0)
     int urep = 1;                          // the tcgen05 kernel sees the bank replicated urep times (llz_umma_tables.h)
     double *d_cbank_u = nullptr;           // [L urep][Q]: the replicated bank (guard recompute, knife-edge taps)
     int *d_single_u = nullptr;             // [L urep]
@@ -579,6 +604,56 @@ int upload(T **dst, const std::vector<T> &src)
     return 0;
 }
 
+// Tables of the tcgen05 kernel, built by the first call that can use it (poly_umma_prepare): a drop-in handle that only
+// ever sees frame-sized calls never pays for them (C4: 10 MB of digit planes + 10 MB of replicated bank).
+// tcgen05.mma.kind::i8 (llz_cuda_polybank_umma.cu): digit planes of g * gain -- five for the exact mode (38-bit taps,
+// two-level guard), three for the fast mode (22-bit taps, no guard).  With the gain inside the taps the output value is
+// (integer sum) * 2^-s and the kernel finishes it with integer instructions.  The kernel sees the bank replicated urep
+// times (rows of the sample operand then start on 16-byte boundaries, llz_umma_tables.h) -- also the decimating banks
+// (L = 1), which become 64 phases of a cycle of 64 M samples, and llz_interp (M = 1), whose frames lie one after the
+// other in the sample planes, each followed by zeros.
+int poly_umma_prepare(PolyBank *b)
+{
+    if (b->umma_tried) return 0;
+    b->umma_tried = true;
+    const llz_plan_t &p = b->plan;
+    const size_t L0 = (size_t)p.crows, Q = (size_t)p.ctaps;
+    if (!((b->acc == LLZ_CUDA_ACC_F64 || b->acc == LLZ_CUDA_ACC_F32) && b->gain != 0.0 && isfinite(b->gain) &&
+          (L0 > 1 || p.single_tap[0] < 0)))
+        return 0;
+    auto upload = [](auto **dst, const auto &v) -> int {
+        LLZ_CUDA_TRY(cudaMalloc(dst, v.size() * sizeof(v[0])));
+        LLZ_CUDA_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    b->urep = llz::umma_replication((int)L0, p.M);
+    const size_t UL = L0 * (size_t)b->urep;
+    const long long UM = (long long)p.M * b->urep;
+    const double cspan = 64.0 * p.M / (double)L0;          // sample span of a 64-phase tile: padded work (Q + cspan) / Q
+    if (!(UL * Q * sizeof(double) <= (64u << 20) && UM < (1LL << 24) && (Q + cspan) / Q <= 4.0)) return 0;
+    std::vector<double> cbu(UL * Q), cbg(UL * Q);
+    std::vector<int> single_u(UL);
+    for (size_t r = 0; r < UL; ++r) {
+        single_u[r] = p.single_tap[r % L0];
+        for (size_t k = 0; k < Q; ++k) {
+            cbu[r * Q + k] = p.cbank[(r % L0) * Q + k];
+            cbg[r * Q + k] = cbu[r * Q + k] * b->gain;
+        }
+    }
+    std::vector<signed char> utiles;
+    b->umma_planes = b->acc == LLZ_CUDA_ACC_F64 ? llz::kUPlanesExact : llz::kUPlanesFast;
+    double qsum = 0.0;
+    int nchunks = llz::poly_umma_build_tables(cbg.data(), (int)UL, (int)UM, (int)Q, b->umma_planes, &utiles, &b->umma_shift, &b->umma_eps, &qsum);
+    // the 32.32 fixed-point form of the largest possible sum must fit 64 bits
+    if (nchunks > 0 && ldexp(qsum * 32768.0, 32 - b->umma_shift) >= ldexp(1.0, 62)) nchunks = 0;
+    if (nchunks > 0 && utiles.size() > (256u << 20)) nchunks = 0;
+    if (nchunks <= 0) return 0;
+    if (upload(&b->d_umma_tiles, utiles) || upload(&b->d_cbank_u, cbu) || upload(&b->d_single_u, single_u)) return -1;
+    LLZ_CUDA_TRY(cudaDeviceSynchronize());                     // pageable uploads: done before any stream reads them
+    b->umma_nchunks = nchunks;
+    return 0;
+}
+
 int poly_upload_plan(PolyBank *b)
 {
     const llz_plan_t &p = b->plan;
@@ -631,40 +706,6 @@ int poly_upload_plan(PolyBank *b)
         b->imma_planes = 5;
         b->imma_nchunks = llz::poly_imma_build_tables(cb.data(), (int)L, p.M * b->rep, (int)Q, b->imma_planes, &tiles, &b->imma_shift, &b->imma_eps);
         if (b->imma_nchunks > 0 && upload(&b->d_imma_tiles, tiles)) return -1;
-    }
-    if ((b->acc == LLZ_CUDA_ACC_F64 || b->acc == LLZ_CUDA_ACC_F32) && b->gain != 0.0 && isfinite(b->gain) &&
-        (L0 > 1 || p.single_tap[0] < 0)) {
-        // tcgen05.mma.kind::i8 (llz_cuda_polybank_umma.cu): digit planes of g * gain -- five for the exact mode (38-bit taps,
-        // two-level guard), three for the fast mode (22-bit taps, no guard).  With the gain inside the taps the output
-        // value is (integer sum) * 2^-s and the kernel finishes it with integer instructions.  The kernel sees the bank
-        // replicated urep times (rows of the sample operand then start on 16-byte boundaries, llz_umma_tables.h) -- also
-        // the decimating banks (L = 1), which become 64 phases of a cycle of 64 M samples, and llz_interp (M = 1), whose
-        // frames lie one after the other in the sample planes, each followed by zeros.
-        b->urep = llz::umma_replication((int)L0, p.M);
-        const size_t UL = L0 * (size_t)b->urep;
-        const long long UM = (long long)p.M * b->urep;
-        const double cspan = 64.0 * p.M / (double)L0;          // sample span of a 64-phase tile: padded work (Q + cspan) / Q
-        if (UL * Q * sizeof(double) <= (64u << 20) && UM < (1LL << 24) && (Q + cspan) / Q <= 4.0) {
-            std::vector<double> cbu(UL * Q), cbg(UL * Q);
-            std::vector<int> single_u(UL);
-            for (size_t r = 0; r < UL; ++r) {
-                single_u[r] = p.single_tap[r % L0];
-                for (size_t k = 0; k < Q; ++k) {
-                    cbu[r * Q + k] = p.cbank[(r % L0) * Q + k];
-                    cbg[r * Q + k] = cbu[r * Q + k] * b->gain;
-                }
-            }
-            std::vector<signed char> utiles;
-            b->umma_planes = b->acc == LLZ_CUDA_ACC_F64 ? llz::kUPlanesExact : llz::kUPlanesFast;
-            double qsum = 0.0;
-            b->umma_nchunks = llz::poly_umma_build_tables(cbg.data(), (int)UL, (int)UM, (int)Q, b->umma_planes, &utiles, &b->umma_shift,
-                                                          &b->umma_eps, &qsum);
-            // the 32.32 fixed-point form of the largest possible sum must fit 64 bits
-            if (b->umma_nchunks > 0 && ldexp(qsum * 32768.0, 32 - b->umma_shift) >= ldexp(1.0, 62)) b->umma_nchunks = 0;
-            if (b->umma_nchunks > 0 && utiles.size() > (256u << 20)) b->umma_nchunks = 0;
-            if (b->umma_nchunks > 0 && (upload(&b->d_umma_tiles, utiles) || upload(&b->d_cbank_u, cbu) || upload(&b->d_single_u, single_u)))
-                return -1;
-        }
     }
     std::vector<int> order(p.order, p.order + Q), single(L);
     for (size_t r = 0; r < L; ++r) single[r] = p.single_tap[r % L0];
@@ -744,6 +785,19 @@ long long poly_out_len(const PolyBank *b, long long n_in)
     return total_out - b->produced;
 }
 
+// is this call big enough for the tcgen05 kernel (at least 4 tiles per SM), or is the kernel forced?  Needs no tables.
+bool poly_umma_wanted(const PolyBank *b, long long outs, int cc)
+{
+    if (b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05) return true;
+    const llz_plan_t &p = b->plan;
+    const long long urep = llz::umma_replication(p.crows, p.M);
+    const long long UL = (long long)p.L * urep;
+    const long long cycles = (b->produced + outs - 1) / UL - b->produced / UL + 1;
+    const long long n_tiles = (cycles + llz::kUJB - 1) / llz::kUJB * ((UL + llz::kUPB - 1) / llz::kUPB) * cc;
+    const int sms = device_sm_count();
+    return sms > 0 && n_tiles >= 4LL * sms;
+}
+
 // defer_history (single-channel drop-in frames with n_in >= hist_len): leave the history where it is -- the tail of
 // d_in, which the caller keeps intact until the next call -- instead of copying it into d_hist
 // channels [c0, c0 + cc) of the bank; d_in / d_out point at channel c0.  `last` = the call completes the bank's step:
@@ -818,7 +872,10 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
     // tcgen05 kernel for calls that fill the machine (a frame-sized call keeps the mma.sync / sliding tiles: no pre-pass,
     // no workspace, lower latency); LLZ_CUDA_TILES_INT8_TCGEN05 forces it
     bool launched = false;
-    if (b->d_umma_tiles && outs > 0 && (b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
+    if (outs > 0 && (b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05) && poly_umma_wanted(b, outs, cc)) {
+        if (poly_umma_prepare(b) != 0) return -1;
+    }
+    if (b->d_umma_tiles && b->umma_nchunks > 0 && outs > 0 && (b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) {
         PolyLaunch u = a;
         if (pcm) {                                             // the pre-pass gathers the channels out of the frames
             const int bps = b->pcm_fmt == LLZ_CUDA_PCM_S16 ? 2 : b->pcm_fmt == LLZ_CUDA_PCM_S24 ? 3 : 4;
@@ -1330,9 +1387,10 @@ int pcm_sample_bytes(int fmt) { return fmt == LLZ_CUDA_PCM_S16 ? 2 : fmt == LLZ_
 bool poly_pcm_fused(PolyBank *b, long long n_in)
 {
     const llz_plan_t &p = b->plan;
-    if (!b->d_umma_tiles || !(b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) return false;
+    if (!(b->tiles == LLZ_CUDA_TILES_AUTO || b->tiles == LLZ_CUDA_TILES_INT8_TCGEN05)) return false;
     const long long outs = poly_out_len(b, n_in);
-    if (outs <= 0) return false;
+    if (outs <= 0 || !poly_umma_wanted(b, outs, b->n_channels)) return false;
+    if (poly_umma_prepare(b) != 0 || b->umma_nchunks <= 0) return false;
     PolyLaunch u{};
     u.L = p.L * b->urep; u.M = p.M * b->urep; u.ctaps = p.ctaps; u.frame_len = p.frame_len;
     if (poly_bank_umma_rows_bytes(u, b->n_channels, llz::kUJB) == 0) return false;
