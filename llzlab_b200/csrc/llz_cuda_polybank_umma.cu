@@ -55,10 +55,11 @@ struct UmmaGeom {
     int n_stages;                  // A-operand stages that fit beside the resident taps (2..4)
 };
 
-constexpr int kUThreads = 384, kUEpiThreads = 256;
+constexpr int kUThreads = 384, kUEpiThreads = 256;   // warpgroup 0: producer + issuer (96 registers), warpgroups 1-2: epilogue (200)
 constexpr int kUTmemCols = 512;
 constexpr int kUParkCol = 384;              // first of the 128 columns that hold the drained sums (two per output)
 static_assert((kUPlanesExact + 1) * kUPB <= kUParkCol, "accumulators overlap the parking columns");
+static_assert(2 * (kUPlanesFast + 1) * kUPB <= kUTmemCols, "two accumulator sets of the fast mode exceed tensor memory");
 constexpr int kUMaxStages = 4;
 
 // ---- pre-pass: byte planes --------------------------------------------------------------------------------------------
@@ -289,8 +290,15 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
     unsigned char *stages = smem_raw + (size_t)geo.nchunk_max * kBStage;        // n_stages x [A lo | A hi]
     uint64_t *s_full = reinterpret_cast<uint64_t *>(stages + (size_t)geo.n_stages * kUAStage);
     uint64_t *s_empty = s_full + kUMaxStages;
-    uint64_t *t_full = s_empty + kUMaxStages, *t_empty = t_full + 1, *b_full = t_full + 2, *b_free = t_full + 3;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_full + 4);
+    // accumulator hand-over.  Exact mode (six accumulators, one set): t_full[0] = "the tile's sums are complete", and one
+    // acc_free barrier PER ACCUMULATOR, released as soon as the epilogue has read that accumulator -- the issuer walks the
+    // first chunk plane-major, so it needs accumulator i + 1 only when it reaches digit plane i and starts the next tile
+    // after a third of the drain instead of all of it.  Fast mode (four accumulators): TWO sets of 256 columns,
+    // t_full[s] / t_empty[s]: the epilogue of a tile runs entirely under the MMAs of the next one.
+    uint64_t *t_full = s_empty + kUMaxStages, *t_empty = t_full + 2, *acc_free = t_full + 4;
+    uint64_t *b_full = acc_free + (kUPlanesExact + 1), *b_free = b_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_free + 1);
+    constexpr bool kTwoSets = PLANES == kUPlanesFast;          // 2 x 4 x 64 columns fit, 2 x 6 x 64 do not
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform for the compiler, too
@@ -298,8 +306,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 
     if (tid == 0) {
         for (int i = 0; i < kUMaxStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
-        mbar_init(t_full, 1);
-        mbar_init(t_empty, kUEpiThreads);
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kUEpiThreads); }
+        for (int i = 0; i <= kUPlanesExact; ++i) mbar_init(&acc_free[i], kUEpiThreads);
         mbar_init(b_full, 1);
         mbar_init(b_free, 1);
     }
@@ -313,6 +321,10 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
 
+    // the epilogue's accumulator-major drain keeps 32 64-bit sums live: its two warpgroups take the registers that the
+    // warpgroup of the two single-thread roles does not need
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (warp == 0) {
         // ================================ TMA producer ================================
         const bool leader = elect_one();
@@ -365,10 +377,14 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 prev_p = T.tile_p;
                 ++run;
             }
-            // the epilogue has drained the accumulators of the previous tile (passes at once for the first tile)
-            mbar_wait(t_empty, (tile_n & 1u) ^ 1u);
+            const uint32_t set = kTwoSets ? (tile_n & 1u) : 0u;
+            const uint32_t tacc = tmem + set * 256u;
+            if constexpr (kTwoSets) {
+                // the epilogue has finished with this set (two tiles ago; passes at once for the first two tiles)
+                mbar_wait(&t_empty[set], ((tile_n >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+            }
             UTRACE(1, tile_n, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;");
             for (int c = 0; c < T.pt.nchunks; ++c) {
                 mbar_wait(&s_full[buf], ph);
                 UTRACE(1, tile_n, 1 + c);
@@ -378,15 +394,22 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 const uint32_t d_b = taps_desc + (uint32_t)c * (kBStage >> 4);
                 const int ks_n = min(4, T.pt.ksteps - 4 * c);
                 if (leader) {
-                    for (int ks = 0; ks < ks_n; ++ks) {
-                        const uint32_t koff = (uint32_t)(2 * ks);              // 32 bytes of K per step, >> 4
-                        const bool first = c == 0 && ks == 0;
+                    // plane-major: digit plane i of every K step of the chunk, then plane i + 1 (sums are exact: any order)
 #pragma unroll
-                        for (int i = 0; i < PLANES; ++i) {
-                            const uint32_t b_i = d_b + (uint32_t)(i * (kUBPlane >> 4)) + koff;
+                    for (int i = 0; i < PLANES; ++i) {
+                        if (!kTwoSets && c == 0) {
+                            // accumulators i and i + 1 of the previous tile have been read (passes at once for the first tile)
+                            if (i == 0) mbar_wait(&acc_free[0], (tile_n & 1u) ^ 1u);
+                            mbar_wait(&acc_free[i + 1], (tile_n & 1u) ^ 1u);
+                            asm volatile("tcgen05.fence::after_thread_sync;");
+                        }
+                        const uint32_t b_i = d_b + (uint32_t)(i * (kUBPlane >> 4));
+                        for (int ks = 0; ks < ks_n; ++ks) {
+                            const uint32_t koff = (uint32_t)(2 * ks);          // 32 bytes of K per step, >> 4
+                            const bool first = c == 0 && ks == 0;
                             // digit i x low byte -> weight 256^i, digit i x high byte -> weight 256^(i+1)
-                            umma_i8(tmem + kUPB * i, d_lo + koff, b_i, umma_idesc(0), (first && i == 0) ? 0u : 1u);
-                            umma_i8(tmem + kUPB * (i + 1), d_hi + koff, b_i, umma_idesc(1), first ? 0u : 1u);
+                            umma_i8(tacc + kUPB * i, d_lo + koff, b_i + koff, umma_idesc(0), (first && i == 0) ? 0u : 1u);
+                            umma_i8(tacc + kUPB * (i + 1), d_hi + koff, b_i + koff, umma_idesc(1), first ? 0u : 1u);
                         }
                     }
                     umma_commit(&s_empty[buf]);                                // the stage is free once these MMAs have read it
@@ -394,13 +417,15 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 __syncwarp();
                 if (++buf == S) { buf = 0; ph ^= 1u; }
             }
-            if (leader) umma_commit(t_full);                                   // the tile's accumulators are complete
+            if (leader) umma_commit(&t_full[set]);                             // the tile's accumulators are complete
             __syncwarp();
             UTRACE(1, tile_n, 8);
             ++tile_n;
         });
-    } else if (warp >= 4) {
+    }
+    } else {
         // ================================ epilogue ================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
         const int h = (warp - 4) >> 2;                         // column half: phases 32h .. 32h + 31 of the tile
         const int m = 32 * q + lane;                           // accumulator row = cycle within the tile
@@ -438,39 +463,45 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                 st_same = __all_sync(0xffffffffu, my_st < 0 || my_g == st_g0);
             }
 
+            const uint32_t set = kTwoSets ? (tile_n & 1u) : 0u;
             UTRACE(warp - 2, tile_n, 0);
-            mbar_wait(t_full, tile_n & 1u);
+            mbar_wait(&t_full[set], kTwoSets ? ((tile_n >> 1) & 1u) : (tile_n & 1u));
             UTRACE(warp - 2, tile_n, 1);
             __syncwarp();                                      // the lanes leave the wait loop one by one; tcgen05.ld is .aligned
             asm volatile("tcgen05.fence::after_thread_sync;");
 
-            // ---- drain: accumulators -> one 64-bit integer per output, parked in the 128 TMEM columns the accumulators
-            // leave free (two columns per output).  Parking them in registers instead needs the whole pass unrolled 32 times;
-            // that code (and the three other roles' loops) no longer fit the instruction cache, and clock stamps showed
-            // the pass taking 60 cycles per output.
-            const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + 32 * h;
+            const uint32_t trow = tmem + set * 256u + ((uint32_t)(32 * q) << 16) + 32 * h;
             const uint32_t tpark = tmem + ((uint32_t)(32 * q) << 16) + kUParkCol + 64 * h;
-#pragma unroll 1
-            for (int cg = 0; cg < 4; ++cg) {
-                int acc[PLANES + 1][8];
+            if constexpr (!kTwoSets) {
+                // ---- drain (exact mode): accumulator by accumulator -> one 64-bit integer per output, each accumulator
+                // released as soon as it is read; the sums are then parked in the 128 TMEM columns the accumulators leave free
+                // (two columns per output).  Keeping them in registers through the finish pass instead needs that pass unrolled
+                // 32 times; that code (and the other roles' loops) no longer fit the instruction cache, and clock stamps
+                // showed 60 cycles per output.
+                long long T64[32];
 #pragma unroll
-                for (int d = 0; d <= PLANES; ++d) tmem_ld8(trow + kUPB * d + 8 * cg, acc[d]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint32_t park[16];
+                for (int d = 0; d <= PLANES; ++d) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    long long t64 = (long long)acc[0][e];
+                    for (int half = 0; half < 2; ++half) {     // sixteen columns at a time: 64 + 16 live registers
+                        uint32_t acc[16];
+                        tmem_ld16(trow + kUPB * d + 16 * half, acc);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int d = 1; d <= PLANES; ++d) t64 += (long long)acc[d][e] << (8 * d);
-                    park[2 * e] = (uint32_t)t64;
-                    park[2 * e + 1] = (uint32_t)(t64 >> 32);
+                        for (int e = 0; e < 16; ++e)
+                            T64[16 * half + e] = d == 0 ? (long long)(int)acc[e] : T64[16 * half + e] + ((long long)(int)acc[e] << (8 * d));
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    mbar_arrive(&acc_free[d]);
                 }
-                tmem_st16(tpark + 16 * cg, park);
+#pragma unroll
+                for (int cg = 0; cg < 4; ++cg) {
+                    uint32_t park[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { park[2 * e] = (uint32_t)T64[8 * cg + e]; park[2 * e + 1] = (uint32_t)(T64[8 * cg + e] >> 32); }
+                    tmem_st16(tpark + 16 * cg, park);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
-            // the accumulators have been read: the issuer may start the next tile
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            mbar_arrive(t_empty);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             UTRACE(warp - 2, tile_n, 2);
 
             // ---- finish ----
@@ -484,8 +515,24 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 #pragma unroll 1
             for (int cg = 0; cg < 4; ++cg) {
                 uint32_t park[16];
-                tmem_ld16(tpark + 16 * cg, park);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if constexpr (kTwoSets) {
+                    // fast mode: straight from this set's accumulators (the other set is being multiplied into)
+                    int acc[PLANES + 1][8];
+#pragma unroll
+                    for (int d = 0; d <= PLANES; ++d) tmem_ld8(trow + kUPB * d + 8 * cg, acc[d]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        long long t64 = (long long)acc[0][e];
+#pragma unroll
+                        for (int d = 1; d <= PLANES; ++d) t64 += (long long)acc[d][e] << (8 * d);
+                        park[2 * e] = (uint32_t)t64;
+                        park[2 * e + 1] = (uint32_t)(t64 >> 32);
+                    }
+                } else {
+                    tmem_ld16(tpark + 16 * cg, park);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                }
                 int y[8];
                 unsigned hit8 = 0;
 #pragma unroll
@@ -519,6 +566,10 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
                     }
                 }
                 hits |= hit8 << (8 * cg);
+            }
+            if constexpr (kTwoSets) {                          // this set's accumulators have been read: free for the tile after next
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                mbar_arrive(&t_empty[set]);
             }
             if (!row_in) hits = 0;
 
@@ -663,7 +714,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if (a.M % 16 != 0) return 0;                               // rows must start on 16-byte boundaries (umma_replication)
     const long long jc_first = a.o0 / a.L, jc_last = (a.o0 + a.n_out - 1) / a.L;
     // shared memory: the resident taps, then as many 32 KB sample stages as fit (at least two)
-    constexpr size_t kSmemMax = 227 * 1024, kBarBytes = 128;
+    constexpr size_t kSmemMax = 227 * 1024, kBarBytes = 256;
     const size_t taps_bytes = (size_t)a.umma_nchunks * umma_b_stage(PLANES);
     if (taps_bytes + 2 * kUAStage + kBarBytes + 1024 > kSmemMax) return 0;
     int n_stages = (int)((kSmemMax - kBarBytes - 1024 - taps_bytes) / kUAStage);
