@@ -8,6 +8,10 @@
 //   4. tcgen05.mma.cta_group::1.kind::i8 with M = 128, N = 64, K = 32, A = u8 or s8 (instruction descriptor bits 7-9),
 //      B = s8, s32 accumulators in TMEM; K steps by advancing the descriptor start address by 32 bytes;
 //   5. tcgen05.ld.32x32b: lane = accumulator row, column = accumulator column; row m of the A tile = atom m / 8, row m % 8.
+//   6. (mode 4) the A operand from tensor memory: tcgen05.cp.128x256b copies one K step (128 rows x 32 bytes) of the
+//      swizzled shared-memory tile into 8 TMEM columns, tcgen05.mma [d], [a_tmem], b_desc reads it from there; the
+//      products must equal mode 3's, and the copied columns are dumped (row m in lane m, bytes 4c..4c+3 of the K step in
+//      column c).
 // Prints PROBE_UMMA_I8_OK when the device result equals the host integer product.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o probe_umma_i8 probe_umma_i8.cu
 #include <cuda.h>
@@ -76,7 +80,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap, const signed char *b_tile
     if (tid == 0) { mbar_init(bar, 1); mbar_init(mma_bar, 1); }
     __syncwarp();
     if (warp == 0 && mode >= 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -111,7 +115,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap, const signed char *b_tile
     for (int i = tid; i < 2 * 16 * 1024; i += 128) a_dump[i] = sA[i];
     __syncthreads();
     if (mode < 2) {
-        if (warp == 0 && mode == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+        if (warp == 0 && mode == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
         return;
     }
     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -122,6 +126,12 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap, const signed char *b_tile
                 const uint64_t db = umma_desc(sB) + (uint64_t)((32 * ks) >> 4);
                 const uint32_t idesc = umma_idesc(plane);                    // plane 0: unsigned bytes, plane 1: signed
                 const uint32_t acc = ks > 0 ? 1u : 0u;
+                if (mode >= 4) {
+                    const uint32_t ta = tmem + 128 + 8 * (plane * 4 + ks);
+                    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(ta), "l"(da) : "memory");
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n"
+                                 ::"r"(tmem + 64 * plane), "r"(ta), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                } else
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
                              ::"r"(tmem + 64 * plane), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
             }
@@ -132,7 +142,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap, const signed char *b_tile
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (mode < 3) {
         __syncthreads();
-        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
         return;
     }
     // thread (warp w, lane l) owns accumulator row 32 w + l
@@ -147,9 +157,21 @@ probe_kernel(const __grid_constant__ CUtensorMap tmap, const signed char *b_tile
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             for (int e = 0; e < 16; ++e) d_out[(plane * kRows + tid) * kN + 16 * cg + e] = (int)v[e];
         }
+    if (mode >= 4) {                                  // dump the 64 columns the copies wrote: [lane][col]
+        for (int cg = 0; cg < 4; ++cg) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + 128 + 16 * cg;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int e = 0; e < 16; ++e) d_out[2 * kRows * kN + tid * 64 + 16 * cg + e] = (int)v[e];
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 int main(int argc, char **argv)
@@ -194,8 +216,8 @@ int main(int argc, char **argv)
     unsigned char *d_dump = nullptr;
     int *d_out = nullptr;
     CK(cudaMalloc(&d_dump, 2 * 16 * 1024));
-    CK(cudaMalloc(&d_out, 2 * kRows * kN * sizeof(int)));
-    CK(cudaMemset(d_out, 0xff, 2 * kRows * kN * sizeof(int)));
+    CK(cudaMalloc(&d_out, (2 * kRows * kN + kRows * 64) * sizeof(int)));
+    CK(cudaMemset(d_out, 0xff, (2 * kRows * kN + kRows * 64) * sizeof(int)));
     const int flags = argc > 3 ? atoi(argv[3]) : 0;    // 1: 16-byte aligned box coordinates; 2: no swizzle
     const int first_byte = (flags & 1) ? -1 : 3 * kM + 5;   // default: an unaligned start
     const size_t smem = 2 * 16 * 1024 + kN * kKB + 64;
@@ -207,7 +229,7 @@ int main(int argc, char **argv)
 
     auto row_start = [&](int r, int i) { return first_byte >= 0 ? first_byte + (r + 16 * i) * kM : 16 * r + 16 * kM * i; };
     std::vector<unsigned char> dump(2 * 16 * 1024);
-    std::vector<int> out(2 * kRows * kN);
+    std::vector<int> out(2 * kRows * kN + kRows * 64);
     CK(cudaMemcpy(dump.data(), d_dump, dump.size(), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out.data(), d_out, out.size() * sizeof(int), cudaMemcpyDeviceToHost));
     // 2 + 3: what the TMA boxes left in shared memory
@@ -237,6 +259,25 @@ int main(int argc, char **argv)
         }
     printf("tcgen05.mma kind::i8 (u8 x s8 and s8 x s8, M 128, N 64, 4 K steps) against the host product: %ld mismatches\n", bad_mma);
     if (bad_mma) printf("  sample: got %d %d %d, row 0\n", out[0], out[1], out[2]);
+    if (mode >= 4) {
+        // the copied operand: lane m, column 8*(plane*4+ks)+c should hold bytes k = 32 ks + 4 c .. + 3 of row m
+        long bad_cp = 0;
+        for (int plane = 0; plane < 2; ++plane)
+            for (int m = 0; m < kRows; ++m)
+                for (int ks = 0; ks < 4; ++ks)
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t want = 0;
+                        for (int b4 = 0; b4 < 4; ++b4) want |= (uint32_t)planes[plane * pitch + row_start(m >> 3, m & 7) + 32 * ks + 4 * c + b4] << (8 * b4);
+                        bad_cp += (uint32_t)out[2 * kRows * kN + m * 64 + 8 * (plane * 4 + ks) + c] != want;
+                    }
+        printf("tcgen05.cp.128x256b into TMEM (row m -> lane m, 4 bytes per column): %ld mismatching words\n", bad_cp);
+        if (bad_cp) {
+            printf("  lane 0, plane 0 columns:"); for (int c = 0; c < 16; ++c) printf(" %08x", (unsigned)out[2 * kRows * kN + c]); printf("\n  want bytes row 0:");
+            for (int k = 0; k < 64; ++k) printf("%s%02x", k % 4 ? "" : " ", planes[row_start(0, 0) + k]); printf("\n");
+            printf("  lane 1, plane 0 columns:"); for (int c = 0; c < 8; ++c) printf(" %08x", (unsigned)out[2 * kRows * kN + 64 + c]); printf("\n  want bytes row 1:");
+            for (int k = 0; k < 32; ++k) printf("%s%02x", k % 4 ? "" : " ", planes[row_start(0, 1) + k]); printf("\n");
+        }
+    }
     printf(bad_layout == 0 && bad_mma == 0 ? "PROBE_UMMA_I8_OK\n" : "PROBE_UMMA_I8_FAILED\n");
     return (bad_layout == 0 && bad_mma == 0) ? 0 : 1;
 }

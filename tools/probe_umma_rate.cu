@@ -36,7 +36,20 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t a_lo, uint32_t b_lo, ui
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}\n" ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi) : "memory");
 }
 
-// PATTERN 0: the kernel's (two A, five B, six accumulators of N columns); 1: one accumulator, K loop over 4 steps
+template <int KIND>
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n.reg .pred p;\n.reg .b64 db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 db, {%2, %5};\n"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ void cp_a(uint32_t a_tmem, uint32_t a_lo)
+{
+    asm volatile("{\n.reg .b64 da;\nmov.b64 da, {%1, %2};\ntcgen05.cp.cta_group::1.128x256b [%0], da;\n}\n" ::"r"(a_tmem), "r"(a_lo), "r"(kDescHi) : "memory");
+}
+
+// PATTERN 0: the kernel's (two A, five B, six accumulators of N columns); 1: one accumulator, K loop over 4 steps;
+// 2: pattern 0 with the A operand copied to tensor memory first (tcgen05.cp.128x256b, two copies per K step) and read
+//    from there by the ten MMAs
 template <int KIND, int N, int PATTERN>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int rounds, long long *out)
 {
@@ -72,7 +85,17 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int rounds, long long *out
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint32_t ko = 2 * ks;
-                    if (PATTERN == 0) {
+                    if (PATTERN == 2) {
+                        const uint32_t ta = tmem + 6 * N + 16 * (ks & 1);          // two K-step slots of 16 columns
+                        cp_a(ta, a0 + ko);
+                        cp_a(ta + 8, a1 + ko);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const uint32_t bi = b0 + (uint32_t)(i % 3) * kBPlane + ko;
+                            mma_ts<KIND>(tmem + N * i, ta, bi, idesc, 1u);
+                            mma_ts<KIND>(tmem + N * (i + 1), ta + 8, bi, idesc, 1u);
+                        }
+                    } else if (PATTERN == 0) {
 #pragma unroll
                         for (int i = 0; i < 5; ++i) {
                             const uint32_t bi = b0 + (uint32_t)(i % 3) * kBPlane + ko;
@@ -89,7 +112,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int rounds, long long *out
         __syncwarp();
         mbar_wait(&bar, 0);
         t1 = clock64();
-        n_mma = rounds * 4 * (PATTERN == 0 ? 10 : 1);
+        n_mma = rounds * 4 * (PATTERN == 1 ? 1 : 10);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -121,6 +144,7 @@ int main()
     CK(cudaMalloc(&d_out, sizeof(long long) * 2 * 148));
     for (int grid : {1, 148}) {
         if (run<0, 64, 0>("i8  N=64  kernel pattern (2 A x 5 B -> 6 acc)", grid, d_out)) return 1;
+        if (run<0, 64, 2>("i8  N=64  kernel pattern, A copied to TMEM", grid, d_out)) return 1;
         if (run<0, 64, 1>("i8  N=64  one accumulator, K loop", grid, d_out)) return 1;
         if (run<0, 128, 0>("i8  N=128 pattern (4 acc)", grid, d_out)) return 1;
         if (run<0, 128, 1>("i8  N=128 one accumulator", grid, d_out)) return 1;

@@ -33,5 +33,5 @@ for acc, name in ((z.ACC_F64, "exact"), (z.ACC_F32, "fast")):
         print(f" tile {n_}: producer stage-free {[int(v - t0) for v in t[0, n_, :3]]}")
         print(f"         issuer t_empty-done {int(t[1, n_, 0] - t0)} s_full-done {[int(v - t0) for v in t[1, n_, 1:4]]} issued {int(t[1, n_, 8] - t0)}")
         for w in range(2, 10):
-            print(f"         epi warp {w + 2}: wait-start {int(t[w, n_, 0] - t0)} t_full {int(t[w, n_, 1] - t0)} drained {int(t[w, n_, 2] - t0)} finished {int(t[w, n_, 3] - t0)}  per group (ld, math, store): {[int(t[w, n_, k + 1] - t[w, n_, k]) for k in range(3, 15)] if False else [int(t[w, n_, 4] - t[w, n_, 2])] + [int(t[w, n_, k + 1] - t[w, n_, k]) for k in range(4, 15)]}")
+            print(f"         epi warp {w + 2}: wait-start {int(t[w, n_, 0] - t0)} t_full {int(t[w, n_, 1] - t0)} drained {int(t[w, n_, 2] - t0)} finished {int(t[w, n_, 3] - t0)}")
     bank.close()
