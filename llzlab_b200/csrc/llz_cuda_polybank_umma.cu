@@ -173,7 +173,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8])
 // role, read back through llz_debug_umma_trace().  Compiled out of the product library.
 #ifdef LLZ_UMMA_TRACE
 __device__ long long g_umma_trace[16 * 16 * 16];
-#define UTRACE(r, n, k) do { if (blockIdx.x == 74 && (n) < 16 && lane == 0) g_umma_trace[((r) * 16 + (n)) * 16 + (k)] = clock64(); } while (0)
+__device__ long long g_umma_cta[2 * 148];      // per CTA: clock at entry and at exit of the last launch
+__device__ int g_umma_trace_cta = 74;
+#define UTRACE(r, n, k) do { if (blockIdx.x == g_umma_trace_cta && (n) < 16 && lane == 0) g_umma_trace[((r) * 16 + (n)) * 16 + (k)] = clock64(); } while (0)
 #else
 #define UTRACE(r, n, k) do { } while (0)
 #endif
@@ -302,6 +304,9 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform for the compiler, too
+#ifdef LLZ_UMMA_TRACE
+    if (tid == 0 && blockIdx.x < 148) g_umma_cta[2 * blockIdx.x] = clock64();
+#endif
     const int S = geo.n_stages;
 
     if (tid == 0) {
@@ -554,7 +559,8 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) packed[e >> 1] = (uint32_t)(uint16_t)y[e] | ((uint32_t)y[e + 1] << 16);
                 if (vec_ok) {
-                    reinterpret_cast<uint4 *>(yrow)[cg] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    // streaming store: the outputs must not push the band's samples (read by every phase tile) out of L2
+                    __stcs(reinterpret_cast<uint4 *>(yrow) + cg, make_uint4(packed[0], packed[1], packed[2], packed[3]));
                 } else if (row_in) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -635,6 +641,9 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         });
     }
 
+#ifdef LLZ_UMMA_TRACE
+    if (tid == 128 && blockIdx.x < 148) g_umma_cta[2 * blockIdx.x + 1] = clock64();
+#endif
     // ---- teardown: every MMA has completed (the epilogue waited for the last tile), nobody touches TMEM any more ----
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -741,7 +750,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         geo.rows_per_frame = pl.rows_per_frame;
         // band of the tile walk: row blocks whose samples (both planes) make up ~32 MB, at least 8
         const long long block_bytes = 2LL * kUJB * a.M;
-        geo.band = (int)max(8LL, min((long long)geo.n_cycle_tiles * n_channels, (32LL << 20) / block_bytes));
+        geo.band = (int)max(8LL, min((long long)geo.n_cycle_tiles * n_channels, ((long long)tunables().umma_band_mib << 20) / block_bytes));
         // 1. byte planes of the slab
         const int spans_per_frame = (int)((geo.frame_pitch + kSplitSpan - 1) / kSplitSpan);
         dim3 sgrid((unsigned)((long long)spans_per_frame * geo.n_frames), (unsigned)n_channels);
@@ -787,5 +796,13 @@ int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stre
 extern "C" int llz_debug_umma_trace(long long *host_out)
 {
     return cudaMemcpyFromSymbol(host_out, llz::g_umma_trace, sizeof(llz::g_umma_trace)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int llz_debug_umma_select(int cta)
+{
+    return cudaMemcpyToSymbol(llz::g_umma_trace_cta, &cta, sizeof(int)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int llz_debug_umma_cta(long long *host_out)
+{
+    return cudaMemcpyFromSymbol(host_out, llz::g_umma_cta, sizeof(llz::g_umma_cta)) == cudaSuccess ? 0 : -1;
 }
 #endif

@@ -6,7 +6,9 @@ sys.path.insert(0, os.getcwd())
 import numpy as np, torch, llzlab_b200 as z
 slab = float(sys.argv[1]) if len(sys.argv) > 1 else 256.0
 what = sys.argv[2] if len(sys.argv) > 2 else "c4"
-C_, frames = (8, 100) if what == "c4" else (64, 500)
+if len(sys.argv) > 3:
+    z.lib().llz_debug_umma_select(int(sys.argv[3]))          # which CTA stamps its roles (default 74)
+C_, frames = (8, 352) if what == "c4" else (64, 500)
 for acc, name in ((z.ACC_F64, "exact"), (z.ACC_F32, "fast")):
     if what == "c4":
         bank = z.ResampleBank(z.KIND_RESAMPLE, 320, 147, C_, k_override=128, acc=acc)
@@ -27,6 +29,13 @@ for acc, name in ((z.ACC_F64, "exact"), (z.ACC_F32, "fast")):
     t = np.zeros(16 * 16 * 16, dtype=np.int64)
     assert z.lib().llz_debug_umma_trace(t.ctypes.data_as(ctypes.c_void_p)) == 0
     t = t.reshape(16, 16, 16)
+    cta = np.zeros(2 * 148, dtype=np.int64)
+    if hasattr(z.lib(), "llz_debug_umma_cta") and z.lib().llz_debug_umma_cta(cta.ctypes.data_as(ctypes.c_void_p)) == 0:
+        dur = (cta[1::2] - cta[0::2]).astype(np.float64)
+        dur = dur[dur > 0]
+        order = np.argsort(-(cta[1::2] - cta[0::2]))
+        print("  slowest CTAs (id: cycles):", [(int(i), int(cta[2 * i + 1] - cta[2 * i])) for i in order[:12]], " fastest:", [(int(i), int(cta[2 * i + 1] - cta[2 * i])) for i in order[-6:]])
+        print(f"  CTA durations of the last launch (cycles, clocks are per SM): min {dur.min():.0f} mean {dur.mean():.0f} max {dur.max():.0f}  max/mean {dur.max() / dur.mean():.3f}")
     t0 = t[1, 0, 0]
     print(what, name, "slab", slab, "taps per phase", bank.info.taps_per_phase)
     for n_ in range(1, 7):
