@@ -38,6 +38,7 @@ struct Tunables {
     double pipe_slot_mib;   // staging-slot size of the *_run_host pipelines (LLZ_PIPE_SLOT_MB), default 64
     int slide_ru;           // force a tile variant of the sliding kernel: 11, 7, 5, 3; 0 = automatic (LLZ_SLIDE_RU)
     int fft8k_skew, fft16k_skew;   // warp-group skew of the 8192- / 16384-point kernels in cycles; < 0 = measured default
+    int umma_knife_cycles;  // extra cost of a phase tile with knife-edge outputs in the walk's shares (tuning)
     int umma_band_mib;      // samples per band of the tcgen05 kernel's tile walk (tuning)
     double umma_slab_mib;   // expanded-row workspace per slab of the tcgen05 phase-bank kernel (LLZ_UMMA_SLAB_MB)
     int fir_algo;           // process default for LLZ_CUDA_FIR_ALGO_AUTO banks: 0 auto, 1 direct, 2 overlap-save (LLZ_FIR_ALGO)

@@ -52,6 +52,7 @@ struct UmmaGeom {
     long long frame_samples;       // samples of a frame that come from the stream (the rest of the pitch is zeros)
     int n_frames, rows_per_frame;
     int band;                      // row blocks (cycle tile x channel) per band of the tile walk
+    long long weight_sum;          // sum of a.umma_weight over the phase tiles
     int n_stages;                  // A-operand stages that fit beside the resident taps (2..4)
 };
 
@@ -242,23 +243,47 @@ struct UmmaTile {
 // config C4 every tile's samples then came from DRAM, 4.5 GB per 300 MB of planes by ncu.)
 // The walk costs a few additions per tile: the divisions (five 64-bit ones for a tile's coordinates and its phase-tile
 // geometry) are done once per band share and once per phase tile -- per tile they took longer than llz_interp's MMAs.
+// Shares are cut by COST, not by tile count: a.umma_weight[p] (host: K steps of the phase tile, + 25 % when it contains a
+// knife-edge phase, whose epilogue is slower) -- a CTA keeps its phase tile, so with equal counts the CTAs that own the
+// expensive tiles finished 23 % after the mean (per-CTA clocks of the profiling build) and set the kernel's time.
+struct UmmaCut { int p; long long rb; };
+
+// first tile (phase-major within a band of width bw) whose starting weight is >= target
+__device__ __forceinline__ UmmaCut umma_locate(const int *weight, const UmmaGeom &geo, long long bw, long long target)
+{
+    long long cum = 0;
+    for (int p = 0; p < geo.n_phase_tiles; ++p) {
+        const long long w = weight[p];
+        if (target < cum + w * bw) {
+            UmmaCut c;
+            c.p = p;
+            c.rb = (target - cum + w - 1) / w;
+            if (c.rb == bw) { c.p = p + 1; c.rb = 0; }
+            return c;
+        }
+        cum += w * bw;
+    }
+    return UmmaCut{geo.n_phase_tiles, 0};
+}
+
 template <typename Body>
-__device__ __forceinline__ void umma_walk(const PolyLaunch &a, const UmmaGeom &geo, Body &&body)
+__device__ __forceinline__ void umma_walk(const PolyLaunch &a, const UmmaGeom &geo, const int *weight, Body &&body)
 {
     const long long R = (long long)geo.n_cycle_tiles * geo.n_channels;
     UmmaTile T;
     T.tile_p = -1;
     for (long long b0 = 0; b0 < R; b0 += geo.band) {
         const long long bw = min((long long)geo.band, R - b0);
-        const long long nb = bw * geo.n_phase_tiles;
-        const long long t_begin = nb * blockIdx.x / gridDim.x, t_end = nb * (blockIdx.x + 1) / gridDim.x;
-        if (t_begin >= t_end) continue;
-        int p = (int)(t_begin / bw);
-        long long rb = t_begin - p * bw;                       // row block within the band
+        const long long wtot = geo.weight_sum * bw;
+        const UmmaCut lo = umma_locate(weight, geo, bw, wtot * blockIdx.x / gridDim.x);
+        const UmmaCut hi = blockIdx.x + 1 == gridDim.x ? UmmaCut{geo.n_phase_tiles, 0}
+                                                       : umma_locate(weight, geo, bw, wtot * (blockIdx.x + 1) / gridDim.x);
+        int p = lo.p;
+        long long rb = lo.rb;                                  // row block within the band
         T.tile_j = (int)((b0 + rb) % geo.n_cycle_tiles);
         T.ch = (int)((b0 + rb) / geo.n_cycle_tiles);
         const int tj0 = (int)(b0 % geo.n_cycle_tiles), ch0 = (int)(b0 / geo.n_cycle_tiles);   // first row block of the band
-        for (long long t = t_begin; t < t_end; ++t) {
+        while (p < hi.p || (p == hi.p && rb < hi.rb)) {
             if (p != T.tile_p) { T.tile_p = p; T.pt = umma_phase_tile(a.L, a.M, a.ctaps, p); }
             body(T);
             if (++rb == bw) { rb = 0; ++p; T.tile_j = tj0; T.ch = ch0; }
@@ -300,6 +325,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
     uint64_t *t_full = s_empty + kUMaxStages, *t_empty = t_full + 2, *acc_free = t_full + 4;
     uint64_t *b_full = acc_free + (kUPlanesExact + 1), *b_free = b_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_free + 1);
+    int *s_weight = reinterpret_cast<int *>(tmem_slot + 2);                     // [n_phase_tiles]: tile costs for the walk (read per band)
     constexpr bool kTwoSets = PLANES == kUPlanesFast;          // 2 x 4 x 64 columns fit, 2 x 6 x 64 do not
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -309,6 +335,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
 #endif
     const int S = geo.n_stages;
 
+    for (int i = tid; i < geo.n_phase_tiles; i += kUThreads) s_weight[i] = __ldg(a.umma_weight + i);
     if (tid == 0) {
         for (int i = 0; i < kUMaxStages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kUEpiThreads); }
@@ -335,7 +362,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         const bool leader = elect_one();
         int buf = 0, run = 0, prev_p = -1;
         uint32_t ph = 0, tile_n = 0;
-        umma_walk(a, geo, [&](const UmmaTile &T) {
+        umma_walk(a, geo, s_weight, [&](const UmmaTile &T) {
             if (T.tile_p != prev_p) {
                 // new phase tile: its taps replace the resident ones once every MMA of the previous run has read them
                 if (run > 0) mbar_wait(b_free, (uint32_t)((run - 1) & 1));
@@ -374,7 +401,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         int buf = 0, run = 0, prev_p = -1;
         uint32_t ph = 0, tile_n = 0;
         const uint32_t taps_desc = umma_desc_lo(smem_u32(taps));
-        umma_walk(a, geo, [&](const UmmaTile &T) {
+        umma_walk(a, geo, s_weight, [&](const UmmaTile &T) {
             if (T.tile_p != prev_p) {
                 if (run > 0 && leader) umma_commit(b_free);                    // the old taps are free once the MMAs so far are done
                 __syncwarp();
@@ -441,7 +468,7 @@ poly_bank_umma_kernel(const __grid_constant__ CUtensorMap rows_map, PolyLaunch a
         double my_g = 0.0, my_inv = 0.0, st_g0 = 0.0, st_inv0 = 0.0;
         unsigned st_mask = 0, st_slow = 0;
         bool st_same = true;
-        umma_walk(a, geo, [&](const UmmaTile &T) {
+        umma_walk(a, geo, s_weight, [&](const UmmaTile &T) {
             const int l0 = T.pt.l0 + 32 * h, pbv = max(0, min(32, T.pt.pbv - 32 * h));
             const long long j = geo.jc0 + (long long)T.tile_j * kUJB + m;          // this thread's cycle
             const int16_t *xc = poly_channel_base(a, T.ch);
@@ -723,7 +750,10 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
     if (a.M % 16 != 0) return 0;                               // rows must start on 16-byte boundaries (umma_replication)
     const long long jc_first = a.o0 / a.L, jc_last = (a.o0 + a.n_out - 1) / a.L;
     // shared memory: the resident taps, then as many 32 KB sample stages as fit (at least two)
-    constexpr size_t kSmemMax = 227 * 1024, kBarBytes = 256;
+    const int n_ptiles = (a.L + kUPB - 1) / kUPB;
+    if (n_ptiles > 1024) return 0;
+    constexpr size_t kSmemMax = 227 * 1024;
+    const size_t kBarBytes = 256 + (((size_t)n_ptiles * sizeof(int) + 127) & ~(size_t)127);   // barriers, TMEM slot, tile weights
     const size_t taps_bytes = (size_t)a.umma_nchunks * umma_b_stage(PLANES);
     if (taps_bytes + 2 * kUAStage + kBarBytes + 1024 > kSmemMax) return 0;
     int n_stages = (int)((kSmemMax - kBarBytes - 1024 - taps_bytes) / kUAStage);
@@ -750,6 +780,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
         geo.rows_per_frame = pl.rows_per_frame;
         // band of the tile walk: row blocks whose samples (both planes) make up ~32 MB, at least 8
         const long long block_bytes = 2LL * kUJB * a.M;
+        geo.weight_sum = a.umma_weight_sum;
         geo.band = (int)max(8LL, min((long long)geo.n_cycle_tiles * n_channels, ((long long)tunables().umma_band_mib << 20) / block_bytes));
         // 1. byte planes of the slab
         const int spans_per_frame = (int)((geo.frame_pitch + kSplitSpan - 1) / kSplitSpan);
@@ -783,7 +814,7 @@ int umma_launch_slabs(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 // 1 = launched, 0 = not applicable, -1 = error.  a.L / a.M / a.cbank / a.single_tap describe the REPLICATED bank.
 int poly_bank_umma_launch(const PolyLaunch &a, int n_channels, cudaStream_t stream)
 {
-    if (!a.umma_tiles || a.umma_nchunks <= 0 || !a.umma_rows || a.umma_slab_cycles <= 0) return 0;
+    if (!a.umma_tiles || a.umma_nchunks <= 0 || !a.umma_rows || a.umma_slab_cycles <= 0 || !a.umma_weight || a.umma_weight_sum <= 0) return 0;
     if (a.n_out <= 0) return 0;
     if (a.acc == LLZ_CUDA_ACC_F64 && a.umma_planes == kUPlanesExact) return umma_launch_slabs<kUPlanesExact, true>(a, n_channels, stream);
     if (a.acc == LLZ_CUDA_ACC_F32 && a.umma_planes == kUPlanesFast) return umma_launch_slabs<kUPlanesFast, false>(a, n_channels, stream);

@@ -54,6 +54,7 @@ Tunables &tunables()
         e = getenv("LLZ_FFT16K_SKEW");
         v.fft16k_skew = (e && *e) ? atoi(e) : -1;
         v.umma_band_mib = 32;
+        v.umma_knife_cycles = 1000;
         e = getenv("LLZ_UMMA_SLAB_MB");
         v.umma_slab_mib = (e && atof(e) >= 1.0) ? atof(e) : 256.0;
         e = getenv("LLZ_FIR_ALGO");
@@ -165,6 +166,7 @@ extern "C" int llz_cuda_tune(const char *key, double value)
     if (strcmp(key, "slide_ru") == 0) { t.slide_ru = (int)value; return 0; }
     if (strcmp(key, "fft8k_skew") == 0) { t.fft8k_skew = (int)value; return 0; }
     if (strcmp(key, "fft16k_skew") == 0) { t.fft16k_skew = (int)value; return 0; }
+    if (strcmp(key, "umma_knife_cycles") == 0 && value >= 0 && value <= 100000) { t.umma_knife_cycles = (int)value; return 0; }
     if (strcmp(key, "umma_band_mib") == 0 && value >= 1 && value <= 4096) { t.umma_band_mib = (int)value; return 0; }
     if (strcmp(key, "umma_slab_mib") == 0 && value >= 1.0) { t.umma_slab_mib = value; return 0; }
     if (strcmp(key, "fir_algo") == 0 && value >= 0 && value <= 2) { t.fir_algo = (int)value; return 0; }

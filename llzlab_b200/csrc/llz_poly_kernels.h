@@ -64,6 +64,8 @@ struct PolyLaunch {
     // tcgen05 exact mode (llz_cuda_polybank_umma.cu): the same digit planes in the K-major SWIZZLE_128B layout of
     // llz_umma_tables.h, and the workspace of the call's expanded input rows; nullptr = not selected for this call
     const signed char *umma_tiles;
+    const int *umma_weight;    // [phase tiles of the replicated bank]: relative cost of a tile (shares of the walk)
+    long long umma_weight_sum;
     int umma_nchunks;          // chunks of 128 k bytes per phase tile
     int umma_planes;           // digit planes of umma_tiles: 5 (exact mode) or 3 (fast mode)
     double umma_scale;         // g * gain ~ q * umma_scale for those digits (the gain is folded into the tables)

@@ -528,6 +528,8 @@ struct PolyBank {
     int urep = 1;                          // the tcgen05 kernel sees the bank replicated urep times (llz_umma_tables.h)
     double *d_cbank_u = nullptr;           // [L urep][Q]: the replicated bank (guard recompute, knife-edge taps)
     int *d_single_u = nullptr;             // [L urep]
+    int *d_umma_weight = nullptr;          // [phase tiles]: relative tile cost for the kernel's walk
+    long long umma_weight_sum = 0;
     unsigned char *d_umma_rows = nullptr;  // workspace: expanded input rows of one slab
     size_t umma_rows_cap = 0;
     signed char *d_imma_tiles = nullptr;   // int8 digit planes of the bank (llz_cuda_polybank_imma.cu)
@@ -585,6 +587,7 @@ void poly_destroy(PolyBank *b)
     cudaFree(b->d_pcm_io[1]);
     cudaFree(b->d_pcm_out);
     cudaFree(b->d_single_u);
+    cudaFree(b->d_umma_weight);
     cudaFree(b->d_order); cudaFree(b->d_single); cudaFree(b->d_guard);
     cudaFree(b->d_hist[0]); cudaFree(b->d_hist[1]);
     if (b->pinned_in) cudaFreeHost(b->pinned_in);
@@ -648,7 +651,23 @@ int poly_umma_prepare(PolyBank *b)
     if (nchunks > 0 && ldexp(qsum * 32768.0, 32 - b->umma_shift) >= ldexp(1.0, 62)) nchunks = 0;
     if (nchunks > 0 && utiles.size() > (256u << 20)) nchunks = 0;
     if (nchunks <= 0) return 0;
-    if (upload(&b->d_umma_tiles, utiles) || upload(&b->d_cbank_u, cbu) || upload(&b->d_single_u, single_u)) return -1;
+    // relative cost of a phase tile for the kernel's walk
+    const int n_ptiles = (int)((UL + llz::kUPB - 1) / llz::kUPB);
+    std::vector<int> weight(n_ptiles);
+    b->umma_weight_sum = 0;
+    for (int pt = 0; pt < n_ptiles; ++pt) {
+        const llz::UmmaPhaseTile t = llz::umma_phase_tile((int)UL, (int)UM, (int)Q, pt);
+        bool knife = false;
+        for (int l = 0; l < t.pbv; ++l) knife = knife || single_u[t.l0 + l] >= 0;
+        // In cycles.  Measured (tools/umma_knife.py, per-CTA clocks of the profiling build): a tile's time does not follow its
+        // K steps (9 or 10: the three sample chunks are loaded either way), and the knife-edge tiles' slower epilogue shows
+        // in the fast mode only (+1000 cycles on 4500: 339 -> 392 Gsamples/s on C4); the exact mode's tiles are
+        // MMA-bound and weighting them costs 3 %.
+        weight[pt] = 4500 + ((knife && b->umma_planes == llz::kUPlanesFast) ? tunables().umma_knife_cycles : 0);
+        b->umma_weight_sum += weight[pt];
+    }
+    if (upload(&b->d_umma_tiles, utiles) || upload(&b->d_cbank_u, cbu) || upload(&b->d_single_u, single_u) || upload(&b->d_umma_weight, weight))
+        return -1;
     LLZ_CUDA_TRY(cudaDeviceSynchronize());                     // pageable uploads: done before any stream reads them
     b->umma_nchunks = nchunks;
     return 0;
@@ -912,6 +931,8 @@ int poly_run_part(PolyBank *b, const int16_t *d_in, long long in_stride, long lo
                 b->umma_rows_cap = need;
             }
             u.umma_tiles = b->d_umma_tiles;
+            u.umma_weight = b->d_umma_weight;
+            u.umma_weight_sum = b->umma_weight_sum;
             u.umma_nchunks = b->umma_nchunks;
             u.umma_planes = b->umma_planes;
             u.umma_scale = ldexp(1.0, -b->umma_shift);
