@@ -246,26 +246,6 @@ struct UmmaTile {
 // Shares are cut by COST, not by tile count: a.umma_weight[p] (host: K steps of the phase tile, + 25 % when it contains a
 // knife-edge phase, whose epilogue is slower) -- a CTA keeps its phase tile, so with equal counts the CTAs that own the
 // expensive tiles finished 23 % after the mean (per-CTA clocks of the profiling build) and set the kernel's time.
-struct UmmaCut { int p; long long rb; };
-
-// first tile (phase-major within a band of width bw) whose starting weight is >= target
-__device__ __forceinline__ UmmaCut umma_locate(const int *weight, const UmmaGeom &geo, long long bw, long long target)
-{
-    long long cum = 0;
-    for (int p = 0; p < geo.n_phase_tiles; ++p) {
-        const long long w = weight[p];
-        if (target < cum + w * bw) {
-            UmmaCut c;
-            c.p = p;
-            c.rb = (target - cum + w - 1) / w;
-            if (c.rb == bw) { c.p = p + 1; c.rb = 0; }
-            return c;
-        }
-        cum += w * bw;
-    }
-    return UmmaCut{geo.n_phase_tiles, 0};
-}
-
 template <typename Body>
 __device__ __forceinline__ void umma_walk(const PolyLaunch &a, const UmmaGeom &geo, const int *weight, Body &&body)
 {
@@ -275,9 +255,9 @@ __device__ __forceinline__ void umma_walk(const PolyLaunch &a, const UmmaGeom &g
     for (long long b0 = 0; b0 < R; b0 += geo.band) {
         const long long bw = min((long long)geo.band, R - b0);
         const long long wtot = geo.weight_sum * bw;
-        const UmmaCut lo = umma_locate(weight, geo, bw, wtot * blockIdx.x / gridDim.x);
+        const UmmaCut lo = umma_locate(weight, geo.n_phase_tiles, bw, wtot * blockIdx.x / gridDim.x);
         const UmmaCut hi = blockIdx.x + 1 == gridDim.x ? UmmaCut{geo.n_phase_tiles, 0}
-                                                       : umma_locate(weight, geo, bw, wtot * (blockIdx.x + 1) / gridDim.x);
+                                                       : umma_locate(weight, geo.n_phase_tiles, bw, wtot * (blockIdx.x + 1) / gridDim.x);
         int p = lo.p;
         long long rb = lo.rb;                                  // row block within the band
         T.tile_j = (int)((b0 + rb) % geo.n_cycle_tiles);

@@ -63,6 +63,29 @@ LLZ_UMMA_HD inline UmmaPhaseTile umma_phase_tile(int L, int M, int Q, int p)
     return t;
 }
 
+// Shares of the kernel's tile walk.  Within a band of bw row blocks the tiles are numbered phase-major; tile (p, rb) starts
+// at weight  bw * sum_{p' < p} w[p'] + rb * w[p].  umma_locate returns the first tile whose starting weight is >= target, so
+// consecutive targets  W c / G  (W = bw * sum w) cut the band into G shares that cover every tile exactly once
+// (tests/cpu/umma_emulate.cpp checks that).
+struct UmmaCut { int p; long long rb; };
+
+LLZ_UMMA_HD inline UmmaCut umma_locate(const int *weight, int n_phase_tiles, long long bw, long long target)
+{
+    long long cum = 0;
+    for (int p = 0; p < n_phase_tiles; ++p) {
+        const long long w = weight[p];
+        if (target < cum + w * bw) {
+            UmmaCut c;
+            c.p = p;
+            c.rb = (target - cum + w - 1) / w;
+            if (c.rb == bw) { c.p = p + 1; c.rb = 0; }
+            return c;
+        }
+        cum += w * bw;
+    }
+    return UmmaCut{n_phase_tiles, 0};
+}
+
 // bytes of a row that the widest-reaching phase tile reads (its boxes end at w0 + 128 * chunks)
 inline int umma_row_extent(int L, int M, int Q)
 {

@@ -131,6 +131,25 @@ int main(int argc, char **argv)
             }
         }
     }
+    // the walk's shares: for random weights, band widths and grid sizes the cuts cover every tile of a band exactly once
+    for (int trial = 0; trial < 200; ++trial) {
+        const int np = 1 + (int)(next() % 90), G = 1 + (int)(next() % 160);
+        const long long bw = 1 + (long long)(next() % 70);
+        std::vector<int> w(np);
+        long long wsum = 0;
+        for (auto &v : w) { v = 3000 + (int)(next() % 4000); wsum += v; }
+        long long covered = 0;
+        UmmaCut prev = umma_locate(w.data(), np, bw, 0);
+        if (prev.p != 0 || prev.rb != 0) { printf("walk: first share does not start at tile 0\n"); return 1; }
+        for (int c = 0; c < G; ++c) {
+            const UmmaCut hi = c + 1 == G ? UmmaCut{np, 0} : umma_locate(w.data(), np, bw, wsum * bw * (c + 1) / G);
+            const long long a0 = prev.p * bw + prev.rb, a1 = hi.p * bw + hi.rb;
+            if (a1 < a0) { printf("walk: share %d runs backwards\n", c); return 1; }
+            covered += a1 - a0;
+            prev = hi;
+        }
+        if (covered != (long long)np * bw) { printf("walk: %lld of %lld tiles covered\n", covered, (long long)np * bw); return 1; }
+    }
     printf("%.4f %.4f %lld %lld %d\n", worst, adversarial, acc_max, finish_bad, r);
     return 0;
 }
