@@ -1,41 +1,46 @@
-// llz_cuda_fir_fft16k.cu -- overlap-save FIR banks for very long filters (4609 .. 12289 taps) on sm_100a: a
-// 16384-point transform per CLUSTER OF TWO CTAs, exchanged through distributed shared memory.
-// Tolerance-mode arithmetic of llz_fir_filter / llz_conv (libllzfilter/llz_fir.c:411-426, 547-584).
+// llz_cuda_fir_fft16k.cu -- overlap-save FIR banks for long filters (2561 .. 12289 taps) on sm_100a: a 16384-point
+// transform per CTA, run as TWO ROUNDS of eight 1024-point sub-transforms with the half that does not fit the SM parked
+// in L2.  Tolerance-mode arithmetic of llz_fir_filter / llz_conv (libllzfilter/llz_fir.c:411-426, 547-584).
 //
 //   y[c][t] = sum_{i<N} h[i] * x[c][t-i]
 //
-// At 4095 taps the 8192-point kernel (llz_cuda_fir_fft8k.cu) keeps B = 8192 - 4096 outputs per block: half of
-// every transform is overlap.  A longer transform does not fit one SM in FP64 -- 16384 complex doubles are 256 KB and
-// 512 threads x 254 registers are twice the register file -- but it fits TWO: a thread-block cluster of 2 CTAs x 256
-// threads holds the 16384 points in the registers of 512 threads, and the two CTAs' 128 KB exchange buffers form one
-// distributed buffer.  B = 16384 - 4096 = 12288: 75 % instead of 50 % of every transform is output.
+// At 4095 taps the 8192-point kernel (llz_cuda_fir_fft8k.cu) keeps B = 8192 - 4096 outputs per block: half of every
+// transform is overlap.  With 16384 points B = 12288 (75 %): 57.4 instead of 80.6 FMA-pipe instructions and two thirds
+// of the shared-memory wavefronts per output -- the two pipes that bound these kernels.  16384 complex doubles are
+// 256 KB: twice the exchange buffer an SM can hold and, in registers, twice its register file.  Round 1 of this file
+// spread the item over a cluster of two CTAs and exchanged through distributed shared memory; tools/probe_l2_dsmem.cu
+// measures that path at 16 B/clk/SM (64 KB pushed + 64 KB pulled cost 8.1 k cycles with their cluster barriers)
+// against 44 B/clk/SM for a CTA writing 128 KB to a private L2-resident scratch and reading it back, so the cluster is
+// gone: ONE CTA of 256 threads owns the item and processes its 16 residues in two rounds.
 //
-//   * 16384 = 16 x 1024.  Cluster-wide thread t (= 256 * rank + tid) gathers z[t + 512 q + 1024 a] (q < 2, a < 16),
-//     runs two DFT-16 over a, and PUSHES residue b to the warp that owns it -- warp b mod 8 of CTA b / 8 -- with
-//     stores into the cluster's shared-memory window (mapa + st.shared::cluster): half of the 128 KB cross the
-//     SM-to-SM network; the hardware cluster barrier (arrive.release / wait.acquire) publishes them;
-//   * warp b then runs the 1024-point transform of llz_cuda_fir_fft.cu on its residue with the outer twiddle
-//     exp(-2 pi i b n_lo / 16384) folded in (warp-uniform part: the 1024-point table at index 2b; the rest merged with
-//     the four-step twiddle into a [b][16][32] table, this CTA's eight residues in shared memory), multiplies by the
-//     spectrum (its 16 KB slice arrives in the warp's own slice by TMA while the second DFT-32 runs), runs the
-//     inverse 1024-point transform and writes its slice; after a cluster barrier every thread PULLS its 32 points
-//     back (half from the peer CTA), and two DFT-16 with the conjugate outer twiddle folded in leave thread t holding
-//     outputs t + 512 q + 1024 a: coalesced streaming stores of the rows at or beyond the halo;
-//   * three cluster barriers per item; the next item's input span is prefetched into L2.
+//   * 16384 = 16 x 1024.  Thread tid gathers z[tid + 256 qq + 1024 a] (qq < 4, a < 16; z = x_A + i x_B, two consecutive
+//     blocks of one channel) in two passes of 32 points, runs two DFT-16 over a per pass and pushes residue b, row
+//     j = n_lo / 32 (n_lo = tid + 256 qq):  b < 8 into slice b of the 128 KB exchange buffer in shared memory,
+//     b >= 8 into the CTA's scratch in global memory (128 KB, written and read by this CTA only: it lives in L2);
+//   * round r (0, 1): warp w transforms residue b = w + 8 r -- reads its 32 x 32 points (shared memory / scratch), runs
+//     the 1024-point transform of llz_cuda_fir_fft.cu with the outer twiddle exp(-2 pi i b n_lo / 16384) folded in
+//     (warp-uniform part: the 1024-point table at index 2b; the rest merged with the four-step twiddle into a
+//     [b][16][32] table whose 8 KB for residue b arrive in the warp's part of shared memory by a TMA bulk copy issued
+//     a whole round earlier), multiplies by the spectrum (its 16 KB slice arrives in the warp's own exchange slice by
+//     TMA while the second DFT-32 runs), runs the inverse 1024-point transform and writes the result -- round 0 to the
+//     second half of the scratch, round 1 to its slice.  There is NO CTA-wide barrier between the push and the pull:
+//     2 x 2052 FMA-pipe instructions per thread during which the eight warps drift apart and one warp's exchanges hide
+//     behind another's butterflies;
+//   * after a barrier every thread pulls its 64 points back in two passes (b < 8 from the scratch, b >= 8 from shared
+//     memory), runs two DFT-16 per pass with the conjugate outer twiddle folded in, and holds outputs
+//     tid + 256 qq + 1024 a: coalesced streaming stores of the rows at or beyond the halo;
+//   * three __syncthreads per item; the next item's input span is prefetched into L2.
 //
-// Per thread and item: 2 x 144 (DFT-16) + 3 x 512 + 388 + 128 (H) + 2 x 208 (folded DFT-16) = 2756 FMA-pipe
-// instructions for 48 outputs at B = 12288: 57.4 per output (8192-point kernel: 80.6).
-// Verified on the host by tests/cpu/fft16k_emulate.cpp, on the device by tests/test_gpu_fir.py.
+// Per thread and item: 4 x 144 (DFT-16) + 2 x (3 x 512 + 388 + 128) + 4 x 208 (folded DFT-16) = 5512 FMA-pipe
+// instructions for 96 outputs at B = 12288: 57.4 per output (8192-point kernel: 80.6).
+// L2 traffic per item beyond the samples: 128 KB + 128 KB of scratch written and read, 256 KB of spectrum, 128 KB of
+// each twiddle table.
+// Verified on the host by tests/cpu/fft16k_emulate.cpp (same 16 x 1024 algebra and tables), on the device by
+// tests/test_gpu_fir.py.
 #include <stdlib.h>
-
-#include <type_traits>
-
-#include <cooperative_groups.h>
 
 #include "llz_fft32.cuh"
 #include "llz_fir_kernels.h"
-
-namespace cg = cooperative_groups;
 
 namespace llz {
 
@@ -43,45 +48,31 @@ template <typename T> struct Cplx16k;
 template <> struct Cplx16k<float>  { using type = float2; };
 template <> struct Cplx16k<double> { using type = double2; };
 
-constexpr int kFft16kThreads = 256;          // per CTA; the cluster has 512
+constexpr int kFft16kThreads = 256;
+constexpr int kFft16kSlice = kFftR * kFftR;             // points of one residue
 
 template <typename T>
 struct Fft16kSmem {
-    static constexpr size_t bars = 128;                                               // [b]: spectrum slice of warp b
+    static constexpr size_t bars = 256;                                               // [w]: spectrum slice, [8 + w]: twiddle table, [16 + w]: residue of warp w
     static constexpr size_t tabw = (size_t)kTwistEntries * kFftR * 2 * sizeof(T);
-    static constexpr size_t tab2 = (size_t)8 * kTwistEntries * kFftR * 2 * sizeof(T); // this CTA's eight residues
-    static constexpr size_t xbuf = (size_t)8192 * 2 * sizeof(T);                      // half of the cluster's buffer
+    static constexpr size_t tab2 = (size_t)8 * kTwistEntries * kFftR * 2 * sizeof(T); // the current round's eight residues
+    static constexpr size_t xbuf = (size_t)8 * kFft16kSlice * 2 * sizeof(T);          // eight slices of 32 x 32
     static constexpr size_t total = bars + tabw + tab2 + xbuf;
 };
 
-// ---- cluster primitives (PTX): the cooperative-groups cluster.sync() adds a full MEMBAR and an error barrier that
-// cost ~20 % of this kernel; the release / acquire pair on the hardware cluster barrier is all the exchange needs ------
-__device__ __forceinline__ void cluster_sync_ra()
+// the CTA's scratch: only this CTA reads it, and only after a __syncthreads that follows the writes -- L2 is the point
+// of coherence, so the loads bypass L1 (.cg) and the stores are ordinary write-back stores
+__device__ __forceinline__ double2 ld_scratch(const double2 *p)
 {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
 }
-// address of `p` (a shared-memory pointer of this CTA) in CTA `rank` of the cluster, shared::cluster window
-__device__ __forceinline__ uint32_t cluster_map(const void *p, int rank)
+__device__ __forceinline__ float2 ld_scratch(const float2 *p)
 {
-    uint32_t r;
-    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster(uint32_t addr, double2 v)
-{
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ void st_cluster(uint32_t addr, float2 v)
-{
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void ld_cluster(uint32_t addr, double2 &v)
-{
-    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void ld_cluster(uint32_t addr, float2 &v)
-{
-    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
 }
 
 template <typename T>
@@ -92,45 +83,65 @@ __device__ __forceinline__ T fir_fft16k_sample(const FirFftLaunch<T> &a, const T
     return T(0);
 }
 
-// EDGE = false: interior items (unguarded loads and stores); EDGE = true: first / last items of a channel
-template <typename T, bool EDGE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFft16kThreads, 1)
+// the WG warps of a group meet on the group's own named barrier (id 1 + g); barrier 0 is used once, before the loop
+__device__ __forceinline__ void group_sync(int g, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(threads) : "memory");
+}
+
+// EDGE = false: interior items (unguarded loads and stores); EDGE = true: first / last items of a channel.
+// WG = warps per group: the CTA's eight warps form 8 / WG groups that each own an item and share nothing but the
+// 1024-point twiddle table, so that one group's gather / push / pull / store phases (load/store-queue bound) run beside
+// the other group's butterflies.  A group of WG warps transforms the 16 residues in 16 / WG rounds.
+template <typename T, bool EDGE, int WG>
+__global__ void __launch_bounds__(kFft16kThreads, sizeof(T) == 4 ? 2 : 1)
 fir_fft16k_kernel(FirFftLaunch<T> a)
 {
     using C = typename Cplx16k<T>::type;
     using SM = Fft16kSmem<T>;
+    constexpr int GROUPS = 8 / WG, GT = 32 * WG;               // groups per CTA, threads per group
+    constexpr int NQ = 1024 / GT, PASSES = NQ / 2;             // n_lo = gtid + GT qq, qq < NQ; a pass holds qq = 2 p + u
+    constexpr int ROUNDS = 16 / WG;                            // round r: warp wg of the group transforms residue wg + WG r
+    constexpr int KEPT = 16 - WG;                              // residues whose results travel through the scratch
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     C *tabw_s = reinterpret_cast<C *>(smem_raw + SM::bars);                                  // [16][32]
-    C *tab2_s = reinterpret_cast<C *>(smem_raw + SM::bars + SM::tabw);                       // [8][16][32]
+    C *tab2_s = reinterpret_cast<C *>(smem_raw + SM::bars + SM::tabw);                       // [8 warps][16][32]
     C *xbuf = reinterpret_cast<C *>(smem_raw + SM::bars + SM::tabw + SM::tab2);              // 8 slices of 32 x 32
 
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tc = rank * kFft16kThreads + tid;        // cluster-wide thread
-    const int ws = tc >> 5;                            // cluster-wide warp = the residue b this warp transforms
-    const uint32_t xb[2] = {cluster_map(xbuf, 0), cluster_map(xbuf, 1)};      // the two halves of the cluster's buffer
+    const int g = warp / WG, wg = warp % WG, gtid = tid % GT;
+    constexpr uint32_t kTab2Bytes = (uint32_t)(kTwistEntries * kFftR * sizeof(C));
+    constexpr uint32_t kSliceBytes = (uint32_t)(kFft16kSlice * sizeof(C));
+    C *xg = xbuf + g * (WG * kFft16kSlice);                    // the group's WG slices
+    C *slice = xg + wg * kFft16kSlice;
+    C *tab2_w = tab2_s + warp * (kTwistEntries * kFftR);
+    const C *tab2_g = reinterpret_cast<const C *>(a.tw2) + wg * (kTwistEntries * kFftR);     // + WG r residues
+    // the group's scratch, 16 blocks of one residue: block b - WG takes residue b >= WG as pushed and, in place, its
+    // result (rounds 1 .. ROUNDS - 2; the last round's results stay in shared memory); blocks KEPT .. 15 take the
+    // results of round 0, whose input travelled through shared memory
+    C *scr = reinterpret_cast<C *>(a.scratch) + ((size_t)blockIdx.x * GROUPS + g) * (16 * kFft16kSlice);
 
     if (tid == 0)
-        for (int b = 0; b < 8; ++b) mbar_init(&bars[b], 1);
-    for (int i = tid; i < 8 * kTwistEntries * kFftR; i += kFft16kThreads) {
-        if (i < kTwistEntries * kFftR) tabw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
-        tab2_s[i] = reinterpret_cast<const C *>(a.tw2)[rank * (8 * kTwistEntries * kFftR) + i];
-    }
+        for (int b = 0; b < 24; ++b) mbar_init(&bars[b], 1);
+    for (int i = tid; i < kTwistEntries * kFftR; i += kFft16kThreads) tabw_s[i] = reinterpret_cast<const C *>(a.tw)[i];
     __syncthreads();
-    cluster_sync_ra();                                 // the peer CTA is resident: its shared memory may be written
+    // the table of the warp's round-0 residue; from here on every use of the table is followed by the fetch of the next one
+    if (lane == 0) {
+        mbar_expect_tx(&bars[8 + warp], kTab2Bytes);
+        tma_bulk_g2s(tab2_w, tab2_g, kTab2Bytes, &bars[8 + warp]);
+    }
 
-    const C *Hw = reinterpret_cast<const C *>(a.H) + ws * (kFftR * kFftR);     // [b][k1][k2]
-    const C *tab3 = reinterpret_cast<const C *>(a.tw3) + tc;                  // [q][e][t]
-    C *slice = xbuf + warp * (kFftR * kFftR);
+    const C *tab3 = reinterpret_cast<const C *>(a.tw3) + gtid;                // [q][e][t], n_lo = t + 512 q
     const int hl = a.halo, B = a.B;
+    const int zero_below = hl - (a.ntaps - 1);                                // < 512
     const long long total = a.items_per_channel * a.n_channels;
-    const long long n_clusters = gridDim.x >> 1;
+    const long long stride = (long long)gridDim.x * GROUPS;
     const int span_bytes = (kFft16kN + B) * (int)sizeof(T);
-    uint32_t h_phase = 0;
+    uint32_t h_phase = 0, t_phase = 0, s_phase = 0;
+    bool first = true;
 
-    for (long long item = blockIdx.x >> 1; item < total; item += n_clusters) {
+    for (long long item = (long long)blockIdx.x * GROUPS + g; item < total; item += stride) {
         const int ch = (int)(item / a.items_per_channel);
         long long pair = a.first_pair + (item - (long long)ch * a.items_per_channel);
         if constexpr (EDGE) { if (pair >= a.gap_start) pair += a.gap_len; }
@@ -140,156 +151,200 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
         T *yc = a.y + (long long)ch * a.y_stride;
 
         T re[32], im[32];
-        // ---- gather: register q*16 + a holds z[tc + 512 q + 1024 a] --------------------------------------------
-        if constexpr (!EDGE) {
-            const T *p = xc + s + tc;
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
+        // ---- gather, DFT-16 over a, push.  Half-pass qq (n_lo = gtid + GT qq) lives in registers 16 (qq & 1) + a; the
+        // loads of half-pass qq + 1 are issued before the transform and the push of half-pass qq, so that the global
+        // latency of one half hides behind the work of the other (all warps of a group are in this phase together)
+        [[maybe_unused]] const T *hc = nullptr;
+        if constexpr (EDGE) hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
+        auto gather_load = [&](int qq) {
+            const int O = 16 * (qq & 1);
+            if constexpr (!EDGE) {
+                const T *src = xc + s + gtid + GT * qq;
 #pragma unroll
                 for (int aa = 0; aa < 16; ++aa) {
-                    re[q * 16 + aa] = __ldg(p + 512 * q + 1024 * aa);
-                    im[q * 16 + aa] = __ldg(p + B + 512 * q + 1024 * aa);
+                    re[O + aa] = __ldg(src + 1024 * aa);
+                    im[O + aa] = __ldg(src + B + 1024 * aa);
                 }
-            if (a.prefetch && item + n_clusters < total) {
-                const long long nit = item + n_clusters;
-                const int nch = (int)(nit / a.items_per_channel);
-                const long long np = a.first_pair + (nit - (long long)nch * a.items_per_channel);
-                const char *src = reinterpret_cast<const char *>(a.x + (long long)nch * a.x_stride + np * (2LL * B) - hl);
-                for (int off = tc * 128; off < span_bytes; off += 2 * kFft16kThreads * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
+            } else {
+#pragma unroll
+                for (int aa = 0; aa < 16; ++aa) {
+                    const long long gg = s + gtid + GT * qq + 1024 * aa;
+                    re[O + aa] = fir_fft16k_sample(a, xc, hc, gg);
+                    im[O + aa] = fir_fft16k_sample(a, xc, hc, gg + B);
+                }
             }
-        } else {
-            const T *hc = a.hist ? a.hist + (long long)ch * (a.ntaps - 1) : nullptr;
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int aa = 0; aa < 16; ++aa) {
-                    const long long g = s + tc + 512 * q + 1024 * aa;
-                    re[q * 16 + aa] = fir_fft16k_sample(a, xc, hc, g);
-                    im[q * 16 + aa] = fir_fft16k_sample(a, xc, hc, g + B);
-                }
-        }
-        // the first halo - (N-1) samples of a block reach only discarded outputs: zeroed, so that every kept output is a
-        // function of its own N-1 predecessors alone, bit for bit (see llz_cuda_fir_fft.cu)
-        if (tc < hl - (a.ntaps - 1)) { re[0] = T(0); im[0] = T(0); }
-
-        // ---- DFT-16 over a; push residue b to its warp: slice b mod 8 of CTA b / 8, row j = ws + 16 q ----------
-        dft16<T, false, 0>(re, im);
-        dft16<T, false, 16>(re, im);
-        // own residues through ordinary shared-memory stores, the peer's through the cluster window
-        auto push = [&](auto rk) {
-            constexpr int RK = decltype(rk)::value;
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int off = (b * kFftR + ws + 16 * q) * kFftR + lane;
-                    C v; v.x = re[q * 16 + 8 * RK + b]; v.y = im[q * 16 + 8 * RK + b];
-                    xbuf[off] = v;
-                    C w; w.x = re[q * 16 + 8 * (RK ^ 1) + b]; w.y = im[q * 16 + 8 * (RK ^ 1) + b];
-                    st_cluster(xb[RK ^ 1] + (uint32_t)(off * sizeof(C)), w);
-                }
         };
-        if (rank == 0) push(std::integral_constant<int, 0>{}); else push(std::integral_constant<int, 1>{});
-        cluster_sync_ra();
-        // warps 4..7 trail their scheduler partners 0..3 by about one transform phase (see llz_cuda_fir_fft8k.cu)
-        if (a.skew > 0 && warp >= 4) {
+        gather_load(0);
+#pragma unroll
+        for (int qq = 0; qq < NQ; ++qq) {
+            if (qq + 1 < NQ) gather_load(qq + 1);
+            const int O = 16 * (qq & 1);
+            // the first halo - (N-1) samples of a block reach only discarded outputs: zeroed, so that every kept output is
+            // a function of its own N-1 predecessors alone, bit for bit (see llz_cuda_fir_fft.cu)
+            if (gtid + GT * qq < zero_below) { re[O] = T(0); im[O] = T(0); }
+            if (qq & 1) dft16<T, false, 16>(re, im); else dft16<T, false, 0>(re, im);
+            // the previous item's pulls have read every slice before this item's pushes overwrite them
+            if (qq == 0 && !first) group_sync(g, GT);
+            const int row = (wg + WG * qq) * kFftR + lane;                   // j = n_lo / 32, column lane
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                C v; v.x = re[O + b]; v.y = im[O + b];
+                if (b < WG) xg[b * kFft16kSlice + row] = v;
+                else        scr[(b - WG) * kFft16kSlice + row] = v;
+            }
+        }
+        first = false;
+        group_sync(g, GT);
+        // one group: warps 4..7 trail their scheduler partners 0..3 by about one transform phase (see
+        // llz_cuda_fir_fft8k.cu); two groups are out of phase by themselves
+        if (GROUPS == 1 && a.skew > 0 && warp >= 4) {
             const long long t0 = clock64();
             while (clock64() - t0 < a.skew) { }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const C v = slice[j * kFftR + lane]; re[j] = v.x; im[j] = v.y; }
-        __syncwarp();
 
-        // ---- warp ws: 1024-point forward transform of residue ws with the outer twiddle folded in -----------
-        dft32_twisted<T, false>(re, im, tabw_s + 2 * ws, kFftR);
+        // ---- rounds: warp wg transforms residue b = wg + WG r -----------------------------------------------------
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) {
+            const int b = wg + WG * r;
+            C *blk = scr + (size_t)(r == 0 ? KEPT + wg : b - WG) * kFft16kSlice + lane;      // result block (and input, r > 0)
+            // rounds after the first find their residue in the slice as well: the bulk copy from the scratch was issued
+            // when the previous round had finished with the slice
+            if (r > 0) {
+                mbar_wait(&bars[16 + warp], s_phase);
+                s_phase ^= 1;
+            }
 #pragma unroll
-        for (int k = 0; k < 32; ++k) { C v; v.x = re[k]; v.y = im[k]; slice[lane * kFftR + (k ^ lane)] = v; }
-        __syncwarp();
+            for (int j = 0; j < 32; ++j) { const C v = slice[j * kFftR + lane]; re[j] = v.x; im[j] = v.y; }
+            __syncwarp();
+
+            // 1024-point forward transform of residue b with the outer twiddle folded in
+            dft32_twisted<T, false>(re, im, tabw_s + 2 * b, kFftR);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) { const C v = slice[k * kFftR + (lane ^ k)]; re[k] = v.x; im[k] = v.y; }
-        __syncwarp();
-        // the slice is idle until the next exchange: fetch this warp's 32 x 32 bins of the spectrum into it
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&bars[warp], (uint32_t)(kFftR * kFftR * sizeof(C)));
-            tma_bulk_g2s(slice, Hw, (uint32_t)(kFftR * kFftR * sizeof(C)), &bars[warp]);
+            for (int k = 0; k < 32; ++k) { C v; v.x = re[k]; v.y = im[k]; slice[lane * kFftR + (k ^ lane)] = v; }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { const C v = slice[k * kFftR + (lane ^ k)]; re[k] = v.x; im[k] = v.y; }
+            __syncwarp();
+            // the slice is idle until the next exchange: fetch the residue's 32 x 32 bins of the spectrum into it
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bars[warp], kSliceBytes);
+                tma_bulk_g2s(slice, reinterpret_cast<const C *>(a.H) + b * kFft16kSlice, kSliceBytes, &bars[warp]);
+            }
+            mbar_wait(&bars[8 + warp], t_phase);
+            t_phase ^= 1;
+            dft32_twisted<T, false>(re, im, tab2_w + lane, kFftR);
+            __syncwarp();
+            // every lane is done with the table: the next round's residue replaces it (used a whole round from now)
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bars[8 + warp], kTab2Bytes);
+                tma_bulk_g2s(tab2_w, tab2_g + ((r + 1) % ROUNDS) * (WG * kTwistEntries * kFftR), kTab2Bytes, &bars[8 + warp]);
+            }
+
+            // spectrum, inverse 1024-point transform
+            mbar_wait(&bars[warp], h_phase);
+            h_phase ^= 1;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const C h = slice[k * kFftR + lane];
+                cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
+            }
+            __syncwarp();                                  // all lanes are done with the spectrum before the slice is reused
+            dft32<T, true>(re, im);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { C v; v.x = re[k]; v.y = im[k]; slice[lane * kFftR + (k ^ lane)] = v; }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { const C v = slice[k * kFftR + (lane ^ k)]; re[k] = v.x; im[k] = v.y; }
+            __syncwarp();
+            if (r < ROUNDS - 1 && lane == 0) {
+                // the slice is free until the next round: its residue comes in while the last DFT-32 and the stores run
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_expect_tx(&bars[16 + warp], kSliceBytes);
+                tma_bulk_g2s(slice, scr + (size_t)b * kFft16kSlice, kSliceBytes, &bars[16 + warp]);
+            }
+            dft32_twisted<T, true>(re, im, tabw_s + lane, kFftR);
+
+            if (r < ROUNDS - 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { C v; v.x = re[j]; v.y = im[j]; blk[j * kFftR] = v; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { C v; v.x = re[j]; v.y = im[j]; slice[j * kFftR + lane] = v; }
+            }
         }
-        dft32_twisted<T, false>(re, im, tab2_s + warp * (kTwistEntries * kFftR) + lane, kFftR);
-
-        // ---- spectrum, inverse 1024-point transform ---------------------------------------------------------------
-        mbar_wait(&bars[warp], h_phase);
-        h_phase ^= 1;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const C h = slice[k * kFftR + lane];
-            cmul_inplace<T, false>(re[k], im[k], h.x, h.y);
+        // the next item's input span into L2 -- now, not a whole item ahead: the CTAs' scratch (256 KB per group) has to
+        // stay in L2 beside whatever is prefetched, and an item-long lead (229 KB per group) pushed it out to DRAM
+        if constexpr (!EDGE) {
+            if (a.prefetch && item + stride < total) {
+                const long long nit = item + stride;
+                const int nch = (int)(nit / a.items_per_channel);
+                const long long np = a.first_pair + (nit - (long long)nch * a.items_per_channel);
+                const char *src = reinterpret_cast<const char *>(a.x + (long long)nch * a.x_stride + np * (2LL * B) - hl);
+                for (int off = gtid * 128; off < span_bytes; off += GT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off));
+            }
         }
-        __syncwarp();                                      // all lanes are done with the spectrum before the slice is reused
-        dft32<T, true>(re, im);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) { C v; v.x = re[k]; v.y = im[k]; slice[lane * kFftR + (k ^ lane)] = v; }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 32; ++k) { const C v = slice[k * kFftR + (lane ^ k)]; re[k] = v.x; im[k] = v.y; }
-        __syncwarp();
-        dft32_twisted<T, true>(re, im, tabw_s + lane, kFftR);
+        group_sync(g, GT);
 
-        // ---- write the slice; every thread pulls its 32 points back (half from the peer CTA) ----------------------
+        // ---- pull, DFT-16 over b with the conjugate outer twiddle folded in, scatter ---------------------------------
+        const int r0 = hl / GT;                            // rows of GT outputs below the halo are overlap
+        // half-pass qq again in registers 16 (qq & 1) + b, the loads of qq + 1 issued before the transform of qq
+        C e[2][8];
+        auto pull_load = [&](int qq) {
+            const int O = 16 * (qq & 1);
+            const int row = (wg + WG * qq) * kFftR + lane;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { C v; v.x = re[j]; v.y = im[j]; slice[j * kFftR + lane] = v; }
-        cluster_sync_ra();
-        auto pull = [&](auto rk) {
-            constexpr int RK = decltype(rk)::value;
+            for (int b = 0; b < 16; ++b) {
+                C v;
+                if (b < WG)        v = ld_scratch(scr + (KEPT + b) * kFft16kSlice + row);
+                else if (b < KEPT) v = ld_scratch(scr + (b - WG) * kFft16kSlice + row);
+                else               v = xg[(b - KEPT) * kFft16kSlice + row];
+                re[O + b] = v.x; im[O + b] = v.y;
+            }
+            // n_lo = gtid + GT qq = t + 512 q
+            const C *t3 = tab3 + (size_t)((GT * qq) >> 9) * (8 * 512) + ((GT * qq) & 511);
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int off = (b * kFftR + ws + 16 * q) * kFftR + lane;
-                    C w;
-                    ld_cluster(xb[RK ^ 1] + (uint32_t)(off * sizeof(C)), w);
-                    re[q * 16 + 8 * (RK ^ 1) + b] = w.x; im[q * 16 + 8 * (RK ^ 1) + b] = w.y;
-                    const C v = xbuf[off];
-                    re[q * 16 + 8 * RK + b] = v.x; im[q * 16 + 8 * RK + b] = v.y;
-                }
+            for (int i = 0; i < 8; ++i) e[qq & 1][i] = __ldg(t3 + i * 512);
         };
-        if (rank == 0) pull(std::integral_constant<int, 0>{}); else pull(std::integral_constant<int, 1>{});
-        cluster_sync_ra();                                 // the next item's pushes overwrite every slice of both CTAs
-
-        // ---- DFT-16 over b with the conjugate outer twiddle folded in ------------------------------------------------
-        {
-            C e[8];
+        pull_load(0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = __ldg(tab3 + i * 512);
-            dft16_twisted<T, true, 0>(re, im, e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] = __ldg(tab3 + (8 + i) * 512);
-            dft16_twisted<T, true, 16>(re, im, e);
-        }
-
-        // ---- scatter: rows (q + 2 a) at or beyond halo / 512 are the valid outputs ------------------------------------
-        T *qy = yc + o - hl + tc;
-        const int r0 = hl >> 9;
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int qq = 0; qq < NQ; ++qq) {
+            if (qq + 1 < NQ) pull_load(qq + 1);
+            const int O = 16 * (qq & 1);
+            if (qq & 1) dft16_twisted<T, true, 16>(re, im, e[1]); else dft16_twisted<T, true, 0>(re, im, e[0]);
+            T *qy = yc + o - hl + gtid + GT * qq;
 #pragma unroll
             for (int aa = 0; aa < 16; ++aa) {
-                const int off = 512 * q + 1024 * aa;
-                if (q + 2 * aa >= r0) {
+                const int off = 1024 * aa;
+                if (qq + NQ * aa >= r0) {
                     if constexpr (!EDGE) {
-                        __stcs(qy + off, re[q * 16 + aa]);
-                        __stcs(qy + B + off, im[q * 16 + aa]);
+                        __stcs(qy + off, re[O + aa]);
+                        __stcs(qy + B + off, im[O + aa]);
                     } else {
-                        const long long tA = o - hl + tc + off;
-                        if (tA < a.n) __stcs(qy + off, re[q * 16 + aa]);
-                        if (tA + B < a.n) __stcs(qy + B + off, im[q * 16 + aa]);
+                        const long long tA = o - hl + gtid + GT * qq + off;
+                        if (tA < a.n) __stcs(qy + off, re[O + aa]);
+                        if (tA + B < a.n) __stcs(qy + B + off, im[O + aa]);
                     }
                 }
             }
+        }
     }
+    // the table fetch issued by the last round is still in flight: it must land before the CTA's shared memory is released
+    mbar_wait(&bars[8 + warp], t_phase);
 }
 
-template <typename T, bool EDGE>
+template <typename T>
+size_t fir_fft16k_scratch_bytes(int sm_count)
+{
+    // one region of 16 residues x 1024 points per group of every resident CTA, for the interior and for the edge
+    // launch (they run side by side on two streams)
+    const size_t slots = (size_t)sm_count * 2;
+    return 2 * slots * 16 * kFft16kSlice * 2 * sizeof(T);
+}
+
+template <typename T, bool EDGE, int WG>
 static int fir_fft16k_run(FirFftLaunch<T> b, int n_channels, long long first, long long count, long long gap_start,
                           long long gap_len, int sm_count, cudaStream_t stream)
 {
@@ -300,12 +355,14 @@ static int fir_fft16k_run(FirFftLaunch<T> b, int n_channels, long long first, lo
     b.items_per_channel = count;
     b.gap_start = gap_start;
     b.gap_len = gap_len;
-    auto kern = fir_fft16k_kernel<T, EDGE>;
+    auto kern = fir_fft16k_kernel<T, EDGE, WG>;
+    constexpr int GROUPS = 8 / WG;
     LLZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long items = count * n_channels;
-    const long long slots = sm_count / 2;              // one cluster of two CTAs per pair of SMs
-    const unsigned clusters = (unsigned)(items < slots ? items : slots);
-    kern<<<2 * clusters, kFft16kThreads, smem, stream>>>(b);
+    const long long ctas = (long long)sm_count * (sizeof(T) == 4 ? 2 : 1), want = (items + GROUPS - 1) / GROUPS;
+    const unsigned grid = (unsigned)(want < ctas ? want : ctas);
+    if (EDGE) b.scratch = b.scratch + (size_t)sm_count * 2 * 16 * kFft16kSlice * 2;   // the second half of the scratch
+    kern<<<grid, kFft16kThreads, smem, stream>>>(b);
     LLZ_CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -316,6 +373,10 @@ int fir_fft16k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     if (a.n <= 0 || n_channels <= 0) return 0;
     if (a.ntaps < 1 || a.ntaps > kFirFft16kMaxTaps) {
         llz_set_error("16384-point overlap-save FIR kernel takes 1..%d taps, got %d", kFirFft16kMaxTaps, a.ntaps);
+        return -1;
+    }
+    if (!a.scratch) {
+        llz_set_error("internal: the 16384-point overlap-save kernel needs its scratch");
         return -1;
     }
     a.halo = (a.ntaps - 1 + 511) / 512 * 512;
@@ -329,12 +390,21 @@ int fir_fft16k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     if (sm_count <= 0) return -1;
     a.prefetch = 1;
     const int sk = tunables().fft16k_skew;                     // llz_cuda_tune("fft16k_skew", cycles); < 0: the measured default
-    a.skew = sk >= 0 ? sk : (sizeof(T) == 8 ? 1300 : 0);       // f64 +5 %, f32 none (profiles/r01_sweep_skew.txt)
-    if (fir_fft16k_run<T, false>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
-    return fir_fft16k_run<T, true>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, stream);
+    a.skew = sk >= 0 ? sk : (sizeof(T) == 8 ? 1300 : 0);
+    // warps per group: f64 (254 registers per thread, one CTA per SM) ...; f32 runs two CTAs of one group per SM
+    const int wg = tunables().fft16k_wg ? tunables().fft16k_wg : 8;
+    cudaStream_t es = a.side ? a.side : stream;
+    if constexpr (sizeof(T) == 8) if (wg == 4) {
+        if (fir_fft16k_run<T, false, 4>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
+        return fir_fft16k_run<T, true, 4>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, es);
+    }
+    if (fir_fft16k_run<T, false, 8>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
+    return fir_fft16k_run<T, true, 8>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, es);
 }
 
 template int fir_fft16k_launch<float>(FirFftLaunch<float>, int, cudaStream_t);
 template int fir_fft16k_launch<double>(FirFftLaunch<double>, int, cudaStream_t);
+template size_t fir_fft16k_scratch_bytes<float>(int);
+template size_t fir_fft16k_scratch_bytes<double>(int);
 
 }  // namespace llz

@@ -60,6 +60,7 @@ struct FirFftLaunch {
     // The edge items (first / last of every channel) are an independent launch: on `side` (already ordered after the
     // caller's stream by the shim, which also joins it back) they run beside the interior items instead of after them.
     cudaStream_t side;     // nullptr: everything on the caller's stream
+    T *scratch;            // 16384-point kernel only: fir_fft16k_scratch_bytes<T>() of device memory owned by the bank
 };
 
 template <typename T>
@@ -69,8 +70,11 @@ int fir_fft_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
 template <typename T>
 int fir_fft8k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
 
-// 16384-point variant (cluster of two CTAs); a.H is [16][32][32], a.tw2 [16][16][32], a.tw3 [2][8][512]
+// 16384-point variant (one CTA per item, two rounds of eight residues, half of the item parked in an L2-resident
+// scratch); a.H is [16][32][32], a.tw2 [16][16][32], a.tw3 [2][8][512]
 template <typename T>
 int fir_fft16k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream);
+template <typename T>
+size_t fir_fft16k_scratch_bytes(int sm_count);
 
 }  // namespace llz

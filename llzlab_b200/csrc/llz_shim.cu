@@ -199,6 +199,7 @@ struct FirBank {
     int algo = LLZ_CUDA_FIR_ALGO_AUTO;
     void *d_fft_H = nullptr, *d_fft_tw = nullptr;
     void *d_fft_tw2 = nullptr, *d_fft_tw3 = nullptr;     // 8192-point kernel (llz_cuda_fir_fft8k.cu)
+    void *d_fft_scratch = nullptr;                       // 16384-point kernel: the CTAs' L2-resident halves of their items
     int fft_size = 0;            // transform length the tables were built for: 1024, 8192 or 16384
     int fft_size_want = 0;       // llz_cuda_fir_bank_set_fft_size: 0 = by tap count
     StreamTrail trail;           // which stream touched the stream state last
@@ -236,6 +237,7 @@ void fir_destroy(FirBank *b)
     if (b->d_fft_tw) cudaFree(b->d_fft_tw);
     if (b->d_fft_tw2) cudaFree(b->d_fft_tw2);
     if (b->d_fft_tw3) cudaFree(b->d_fft_tw3);
+    if (b->d_fft_scratch) cudaFree(b->d_fft_scratch);
     if (b->d_hist[0]) cudaFree(b->d_hist[0]);
     if (b->d_hist[1]) cudaFree(b->d_hist[1]);
     if (b->pinned) cudaFreeHost(b->pinned);
@@ -392,6 +394,9 @@ int fir_fft_tables(FirBank *b)
         fft16k_make_twist3(t3.data());
         if (upload_as(&b->d_fft_tw2, t2, f32) != 0 || upload_as(&b->d_fft_tw3, t3, f32) != 0) return -1;
         fft16k_make_spectrum(b->h_host, b->flt_len, H.data());
+        const int sms = device_sm_count();
+        if (sms <= 0) return -1;
+        LLZ_CUDA_TRY(cudaMalloc(&b->d_fft_scratch, f32 ? fir_fft16k_scratch_bytes<float>(sms) : fir_fft16k_scratch_bytes<double>(sms)));
     } else if (b->fft_size == 8192) {
         std::vector<double> t2(2 * 8 * kTwistEntries * kFftR), t3(2 * 16 * 256);
         fft8k_make_twist2(t2.data());
@@ -432,7 +437,7 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
     // outputs / the other history buffer), so they run on a side stream beside them: fork here, join at the end.  On a
     // strong-scaled shard (C2 at N = 8: 0.24 ms per step) the two extra launches in series were 10 % of the step.
     cudaStream_t side = nullptr;
-    if (algo == LLZ_CUDA_FIR_ALGO_FFT && !defer_history && b->fft_size != 16384) {
+    if (algo == LLZ_CUDA_FIR_ALGO_FFT && !defer_history) {
         if (!b->s_side) {
             LLZ_CUDA_TRY(cudaStreamCreateWithFlags(&b->s_side, cudaStreamNonBlocking));
             LLZ_CUDA_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -452,6 +457,7 @@ int fir_run_typed(FirBank *b, const void *d_in, long long in_stride, void *d_out
         f.tw = static_cast<const T *>(b->d_fft_tw);
         f.tw2 = static_cast<const T *>(b->d_fft_tw2);
         f.tw3 = static_cast<const T *>(b->d_fft_tw3);
+        f.scratch = static_cast<T *>(b->d_fft_scratch);
         const int rc = b->fft_size == 16384 ? fir_fft16k_launch<T>(f, cc, st)
                        : b->fft_size == 8192 ? fir_fft8k_launch<T>(f, cc, st) : fir_fft_launch<T>(f, cc, st);
         if (rc != 0) return -1;
@@ -1107,8 +1113,8 @@ extern "C" int llz_cuda_fir_bank_set_fft_size(unsigned long handle, int fft_size
         // tables of another transform length are resident: drop them, the next run rebuilds
         DeviceGuard g(b->device);
         LLZ_CUDA_TRY(cudaDeviceSynchronize());
-        cudaFree(b->d_fft_H); cudaFree(b->d_fft_tw); cudaFree(b->d_fft_tw2); cudaFree(b->d_fft_tw3);
-        b->d_fft_H = b->d_fft_tw = b->d_fft_tw2 = b->d_fft_tw3 = nullptr;
+        cudaFree(b->d_fft_H); cudaFree(b->d_fft_tw); cudaFree(b->d_fft_tw2); cudaFree(b->d_fft_tw3); cudaFree(b->d_fft_scratch);
+        b->d_fft_H = b->d_fft_tw = b->d_fft_tw2 = b->d_fft_tw3 = b->d_fft_scratch = nullptr;
         b->fft_size = 0;
     }
     b->fft_size_want = fft_size;
