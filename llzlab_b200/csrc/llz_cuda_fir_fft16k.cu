@@ -75,6 +75,27 @@ __device__ __forceinline__ float2 ld_scratch(const float2 *p)
     return v;
 }
 
+// input samples are read once (twice where blocks overlap, by a neighbouring CTA at about the same time): evict_first
+// in L2, so that they do not push the CTAs' scratch out to DRAM
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ld_stream(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_stream(const float *p, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 template <typename T>
 __device__ __forceinline__ T fir_fft16k_sample(const FirFftLaunch<T> &a, const T *xc, const T *hc, long long g)
 {
@@ -100,7 +121,7 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
     using C = typename Cplx16k<T>::type;
     using SM = Fft16kSmem<T>;
     constexpr int GROUPS = 8 / WG, GT = 32 * WG;               // groups per CTA, threads per group
-    constexpr int NQ = 1024 / GT, PASSES = NQ / 2;             // n_lo = gtid + GT qq, qq < NQ; a pass holds qq = 2 p + u
+    constexpr int NQ = 1024 / GT;                              // n_lo = gtid + GT qq, qq < NQ: half-pass qq holds 16 points
     constexpr int ROUNDS = 16 / WG;                            // round r: warp wg of the group transforms residue wg + WG r
     constexpr int KEPT = 16 - WG;                              // residues whose results travel through the scratch
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -133,12 +154,19 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
     }
 
     const C *tab3 = reinterpret_cast<const C *>(a.tw3) + gtid;                // [q][e][t], n_lo = t + 512 q
+    // FP64: the thread's own outer twiddle exp(+2 pi i gtid / 16384), from the table's (cos, tan) entry of that angle
+    [[maybe_unused]] T w0r = T(1), w0i = T(0);
+    if constexpr (sizeof(T) == 8) {
+        const C cw = __ldg(tab3 + 4 * 512);
+        w0r = cw.x; w0i = cw.x * cw.y;
+    }
     const int hl = a.halo, B = a.B;
     const int zero_below = hl - (a.ntaps - 1);                                // < 512
     const long long total = a.items_per_channel * a.n_channels;
     const long long stride = (long long)gridDim.x * GROUPS;
     const int span_bytes = (kFft16kN + B) * (int)sizeof(T);
     uint32_t h_phase = 0, t_phase = 0, s_phase = 0;
+    [[maybe_unused]] const uint64_t pol_stream = l2_policy_evict_first();
     bool first = true;
 
     for (long long item = (long long)blockIdx.x * GROUPS + g; item < total; item += stride) {
@@ -162,8 +190,8 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
                 const T *src = xc + s + gtid + GT * qq;
 #pragma unroll
                 for (int aa = 0; aa < 16; ++aa) {
-                    re[O + aa] = __ldg(src + 1024 * aa);
-                    im[O + aa] = __ldg(src + B + 1024 * aa);
+                    re[O + aa] = ld_stream(src + 1024 * aa, pol_stream);
+                    im[O + aa] = ld_stream(src + B + 1024 * aa, pol_stream);
                 }
             } else {
 #pragma unroll
@@ -195,6 +223,9 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
         }
         first = false;
         group_sync(g, GT);
+        // the residues pushed to the scratch (generic-proxy stores of the whole group, ordered by the barrier) are read
+        // back by bulk copies (async proxy): one proxy fence per issuing thread, here where nothing of its own is in flight
+        if (lane == 0) asm volatile("fence.proxy.async;" ::: "memory");
         // one group: warps 4..7 trail their scheduler partners 0..3 by about one transform phase (see
         // llz_cuda_fir_fft8k.cu); two groups are out of phase by themselves
         if (GROUPS == 1 && a.skew > 0 && warp >= 4) {
@@ -260,7 +291,7 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
             __syncwarp();
             if (r < ROUNDS - 1 && lane == 0) {
                 // the slice is free until the next round: its residue comes in while the last DFT-32 and the stores run
-                asm volatile("fence.proxy.async;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&bars[16 + warp], kSliceBytes);
                 tma_bulk_g2s(slice, scr + (size_t)b * kFft16kSlice, kSliceBytes, &bars[16 + warp]);
             }
@@ -291,7 +322,7 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
         // ---- pull, DFT-16 over b with the conjugate outer twiddle folded in, scatter ---------------------------------
         const int r0 = hl / GT;                            // rows of GT outputs below the halo are overlap
         // half-pass qq again in registers 16 (qq & 1) + b, the loads of qq + 1 issued before the transform of qq
-        C e[2][8];
+        [[maybe_unused]] C e[2][8];
         auto pull_load = [&](int qq) {
             const int O = 16 * (qq & 1);
             const int row = (wg + WG * qq) * kFftR + lane;
@@ -304,16 +335,28 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
                 re[O + b] = v.x; im[O + b] = v.y;
             }
             // n_lo = gtid + GT qq = t + 512 q
-            const C *t3 = tab3 + (size_t)((GT * qq) >> 9) * (8 * 512) + ((GT * qq) & 511);
+            if constexpr (sizeof(T) == 4) {
+                const C *t3 = tab3 + (size_t)((GT * qq) >> 9) * (8 * 512) + ((GT * qq) & 511);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e[qq & 1][i] = __ldg(t3 + i * 512);
+                for (int i = 0; i < 8; ++i) e[qq & 1][i] = __ldg(t3 + i * 512);
+            }
         };
         pull_load(0);
 #pragma unroll
         for (int qq = 0; qq < NQ; ++qq) {
             if (qq + 1 < NQ) pull_load(qq + 1);
             const int O = 16 * (qq & 1);
-            if (qq & 1) dft16_twisted<T, true, 16>(re, im, e[1]); else dft16_twisted<T, true, 0>(re, im, e[0]);
+            if constexpr (sizeof(T) == 4) {
+                if (qq & 1) dft16_twisted<T, true, 16>(re, im, e[1]); else dft16_twisted<T, true, 0>(re, im, e[0]);
+            } else {
+                // FP64: this pass is bound by its L2 reads, not by the FP64 pipe -- the conjugate outer twiddle
+                // exp(+2 pi i n_lo / 16384) = w0 * exp(2 pi i GT qq / 16384) and its powers are computed, not read
+                constexpr double kCos[8] = {1.0, 0.9987954562051724, 0.9951847266721969, 0.989176509964781, 0.9807852804032304, 0.970031253194544, 0.9569403357322088, 0.9415440651830208};
+                constexpr double kSin[8] = {0.0, 0.049067674327418015, 0.0980171403295606, 0.14673047445536175, 0.19509032201612825, 0.24298017990326387, 0.29028467725446233, 0.33688985339222005};       // cos, sin (2 pi k / 128)
+                const T cr = (T)kCos[GT * qq / 128], ci = (T)kSin[GT * qq / 128];          // compile-time after unrolling
+                const T wr = fma(-w0i, ci, w0r * cr), wi = fma(w0i, cr, w0r * ci);
+                if (qq & 1) dft16_powers<T, true, 16>(re, im, wr, wi); else dft16_powers<T, true, 0>(re, im, wr, wi);
+            }
             T *qy = yc + o - hl + gtid + GT * qq;
 #pragma unroll
             for (int aa = 0; aa < 16; ++aa) {

@@ -344,6 +344,39 @@ LLZ_HD void dft16_twisted(T (&re)[32], T (&im)[32], const C (&e)[8])
     for (int i = 0; i < 16; ++i) { re[O + i] = ar[i]; im[O + i] = ai[i]; }
 }
 
+// X[k] = sum_a (x[a] * w^a) * exp(-+ 2*pi*i*a*k/16) with the powers of w = wr + i*wi (|w| = 1) built on the fly
+// instead of read from a folded table: 14 complex products for w^2 .. w^15 (every power a product of two powers of
+// depth <= 3: no long error chain), 15 to apply them, then the plain transform -- 264 instead of 208 FMA-pipe
+// instructions, and 16 bytes of table per transform (w) instead of 128.  Used where the table traffic costs more than
+// the arithmetic: the last pass of the FP64 16384-point kernel is bound by its L2 reads (llz_cuda_fir_fft16k.cu).
+template <typename T, bool INV, int O>
+LLZ_HD void dft16_powers(T (&re)[32], T (&im)[32], T wr, T wi)
+{
+    T pr[9], pi[9];                                      // w^1 .. w^8
+    pr[1] = wr; pi[1] = wi;
+    auto mul = [](T ar, T ai, T br, T bi, T &cr, T &ci) {
+        cr = fma_t<T>(-ai, bi, ar * br);
+        ci = fma_t<T>(ai, br, ar * bi);
+    };
+    mul(pr[1], pi[1], pr[1], pi[1], pr[2], pi[2]);
+    mul(pr[2], pi[2], pr[1], pi[1], pr[3], pi[3]);
+    mul(pr[2], pi[2], pr[2], pi[2], pr[4], pi[4]);
+    mul(pr[4], pi[4], pr[1], pi[1], pr[5], pi[5]);
+    mul(pr[4], pi[4], pr[2], pi[2], pr[6], pi[6]);
+    mul(pr[4], pi[4], pr[3], pi[3], pr[7], pi[7]);
+    mul(pr[4], pi[4], pr[4], pi[4], pr[8], pi[8]);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+        T qr, qi;
+        if (k <= 8) { qr = pr[k]; qi = pi[k]; }
+        else mul(pr[8], pi[8], pr[k - 8], pi[k - 8], qr, qi);
+        const T xr = re[O + k], xi = im[O + k];
+        re[O + k] = fma_t<T>(-xi, qi, xr * qr);
+        im[O + k] = fma_t<T>(xi, qr, xr * qi);
+    }
+    dft16<T, INV, O>(re, im);
+}
+
 // ---- host-side tables ---------------------------------------------------------------------------
 // tab[e][l], e < 16, l < 32: the folded twiddles of dft32_twisted for lane l, interleaved pairs (see above)
 inline void fft1024_make_twist_table(double *tab /* 16*32*2 */)

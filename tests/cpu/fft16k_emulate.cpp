@@ -1,6 +1,7 @@
-// Host emulation of the cluster-level 16384-point overlap-save algorithm of llzlab_b200/csrc/llz_cuda_fir_fft16k.cu:
-// the same dft16 / dft32 / folded-twiddle code and tables (llz_fft32.cuh compiles for the host); the 512 threads of
-// the two-CTA cluster run one after another and the (distributed) shared-memory exchanges become array permutations.
+// Host emulation of the 16384-point (16 x 1024) overlap-save algorithm of llzlab_b200/csrc/llz_cuda_fir_fft16k.cu:
+// the same dft16 / dft32 / folded-twiddle code and tables (llz_fft32.cuh compiles for the host); the 512 (thread,
+// half-pass pair) slots of the item run one after another and the exchanges through shared memory and the L2 scratch
+// become array permutations.
 // Checks one work item (two blocks of 16384 - halo outputs) against the direct sum.
 // Usage: fft16k_emulate <ntaps> <f32:0|1>   -> prints max |err| relative to sum|h|, exit 0 if within bound.
 #include <stdio.h>
@@ -83,8 +84,22 @@ static double run(int ntaps)
             for (int b = 0; b < 16; ++b) { re[t][q * 16 + b] = xr[b][w + 16 * q][lane]; im[t][q * 16 + b] = xi[b][w + 16 * q][lane]; }
         C2 e0[8], e1[8];
         for (int e = 0; e < 8; ++e) { e0[e] = tab3[(0 * 8 + e) * 512 + t]; e1[e] = tab3[(1 * 8 + e) * 512 + t]; }
-        dft16_twisted<T, true, 0>(re[t], im[t], e0);
-        dft16_twisted<T, true, 16>(re[t], im[t], e1);
+        if (sizeof(T) == 4) {
+            dft16_twisted<T, true, 0>(re[t], im[t], e0);
+            dft16_twisted<T, true, 16>(re[t], im[t], e1);
+        } else {
+            // FP64 kernel: the conjugate outer twiddle exp(+2 pi i n_lo / 16384) from the thread's own w0 (the table's
+            // (cos, tan) entry of the angle of n_lo mod 256) times a constant rotation, its powers built on the fly
+            const int t0 = t & 255;
+            const C2 cw = tab3[4 * 512 + t0];
+            const T w0r = cw.x, w0i = cw.x * cw.y;
+            for (int q = 0; q < 2; ++q) {
+                const int rot = t - t0 + 512 * q;                     // n_lo - t0: a multiple of 256
+                const T cr = (T)cos(2 * M_PI * rot / kFft16kN), ci = (T)sin(2 * M_PI * rot / kFft16kN);
+                const T wr = fma_t<T>(-w0i, ci, w0r * cr), wi = fma_t<T>(w0i, cr, w0r * ci);
+                if (q == 0) dft16_powers<T, true, 0>(re[t], im[t], wr, wi); else dft16_powers<T, true, 16>(re[t], im[t], wr, wi);
+            }
+        }
         for (int q = 0; q < 2; ++q)
             for (int a = 0; a < 16; ++a) {
                 const int m = t + 512 * q + 1024 * a;
