@@ -403,11 +403,21 @@ class Workload:
             # mode; refresh_kernel() replaces this guess with what the library reports after the timed steps
             return ("poly_bank_umma_kernel<3>" if f32 else "poly_bank_umma_kernel<5>"), None, None
         t = "float" if f32 else "double"
-        if self.fir_fft and wl["taps"] >= 545:
-            # 8192-point overlap-save kernel (llz_cuda_fir_fft8k.cu): one CTA of 256 threads turns 2*B outputs out of
-            # 2580 FMA-pipe instructions per thread
-            halo_pad = (wl["taps"] - 1 + 255) // 256 * 256
-            return f"fir_fft8k_kernel<{t}>", 2580.0 * 256 / (2 * (8192 - halo_pad)), "8192-point FFT per CTA"
+        if self.fir_fft:
+            # which overlap-save kernel: the library's work-item length says it (2 * (transform length - padded halo))
+            handle = self.bank.handle if self.bank is not None else self.bank_handle
+            blk = self.z._check(self.z.lib().llz_cuda_fir_bank_block_len(handle), "llz_cuda_fir_bank_block_len")
+            halo16 = (wl["taps"] - 1 + 511) // 512 * 512
+            halo8 = (wl["taps"] - 1 + 255) // 256 * 256
+            if blk == 2 * (16384 - halo16):
+                # 16384-point kernel (llz_cuda_fir_fft16k.cu): one CTA of 256 threads turns 2*B outputs out of 5512 (f32) /
+                # 5736 (f64: outer twiddles of the last pass computed instead of read) FMA-pipe instructions per thread
+                per_thread = 5512.0 if f32 else 5736.0
+                return f"fir_fft16k_kernel<{t}>", per_thread * 256 / blk, "16384-point FFT per CTA in two rounds, half of the item in an L2-resident scratch"
+            if blk == 2 * (8192 - halo8):
+                # 8192-point overlap-save kernel (llz_cuda_fir_fft8k.cu): one CTA of 256 threads turns 2*B outputs out of
+                # 2580 FMA-pipe instructions per thread
+                return f"fir_fft8k_kernel<{t}>", 2580.0 * 256 / blk, "8192-point FFT per CTA"
         if self.fir_fft:
             # overlap-save kernel (llz_cuda_fir_fft.cu): one warp turns 2*B outputs out of 1928 FMA-pipe instructions per lane
             halo_pad = (wl["taps"] - 1 + 31) // 32 * 32

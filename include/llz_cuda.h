@@ -67,8 +67,8 @@ enum {                                      /* FIR kernel family (tolerance-mode
     LLZ_CUDA_FIR_ALGO_DIRECT = 1, /* register-blocked sliding MAC: 2*N flop per output                       */
     LLZ_CUDA_FIR_ALGO_FFT    = 2, /* overlap-save in the bank's own type: a 1024-point transform per warp up
                                      to 544 taps (~35 FMA-pipe instructions per output at 127 taps), an
-                                     8192-point transform per CTA up to 4608 taps, a 16384-point transform
-                                     per cluster of two CTAs up to 12289 taps (~57 at 4095 taps);
+                                     8192-point transform per CTA up to 3328 (f64) / 2304 (f32) taps, a
+                                     16384-point transform per CTA up to 12289 taps (~57 at 4095 taps);
                                      |err| ~1e-15 (f64) / ~3e-7 (f32) of full scale against the direct sum,
                                      not bit-identical                                                      */
 };

@@ -36,7 +36,9 @@ constexpr int kFirFftMinTapsAuto = 48;   // below this the direct kernel is at l
 constexpr int kFirFftMaxTaps = 897;      // leaves B = 1024 - halo >= 128 valid outputs per block
 constexpr int kFirFft8kMinTapsAuto = 545;  // from here on the 8192-point kernel wins (profiles/r01_crossover_fft.txt)
 constexpr int kFirFft8kMaxTaps = 6145;   // leaves B = 8192 - halo >= 2048
-constexpr int kFirFft16kMinTapsAuto = 4609;  // from here on the 16384-point cluster kernel wins (profiles/r01_crossover_fft16k.txt)
+// from here on the 16384-point kernel wins (profiles/r02_crossover_fft16k.txt: f64 140 / 137 Gsamples/s at 3073 taps,
+// 115 / 134 at 4095; f32 286 / 283 at 2049, 264 / 274 at 2561)
+constexpr int kFirFft16kMinTapsAutoF64 = 3329, kFirFft16kMinTapsAutoF32 = 2305;
 constexpr int kFirFft16kMaxTaps = 12289; // leaves B = 16384 - halo >= 4096
 
 template <typename T>

@@ -346,14 +346,14 @@ int fir_effective_algo(const FirBank *b)
 }
 
 // transform length the overlap-save path uses for this bank: 1024 (one warp per item), 8192 (one CTA per item) or
-// 16384 (one cluster of two CTAs per item); llz_cuda_fir_bank_set_fft_size overrides the choice where the tap count allows it
+// 16384 (one CTA per item in two rounds, half of the item in an L2-resident scratch); llz_cuda_fir_bank_set_fft_size overrides the choice where the tap count allows it
 int fir_fft_size(const FirBank *b)
 {
     const int want = b->fft_size_want;
     if (want == 16384) return 16384;
     if (want == 8192 && b->flt_len <= kFirFft8kMaxTaps) return 8192;
     if (want == 1024 && b->flt_len <= kFirFftMaxTaps) return 1024;
-    if (b->flt_len >= kFirFft16kMinTapsAuto) return 16384;
+    if (b->flt_len >= (b->dtype == LLZ_CUDA_F32 ? kFirFft16kMinTapsAutoF32 : kFirFft16kMinTapsAutoF64)) return 16384;
     return b->flt_len >= kFirFft8kMinTapsAuto ? 8192 : 1024;
 }
 

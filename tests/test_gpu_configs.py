@@ -56,11 +56,11 @@ def test_c5_full_length_one_channel(zlib, port, cuda):
         want = port.fir_run(h, xw)[t0 - lo:]
         got = dy[t0:t0 + 200].cpu().numpy()
         assert np.abs(got - want).max() <= 1e-12, t0
-    # the same stream in two time segments with halo (C5's multi-GPU plan): the overlap-save kernel (AUTO keeps the
-    # 8192-point one at 4095 taps; the 16384-point cluster kernel takes over at 4609, profiles/r01_crossover_fft16k.txt)
-    # agrees to rounding -- its block grid starts at the segment -- and the direct kernel bit for bit
+    # the same stream in two time segments with halo (C5's multi-GPU plan): the overlap-save kernel (AUTO picks the
+    # 16384-point one at 4095 taps, profiles/r02_crossover_fft16k.txt) agrees to rounding -- its block grid starts at
+    # the segment -- and the direct kernel bit for bit
     blk = bank.block_len
-    assert bank.algo == zlib.FIR_FFT and blk == 2 * (8192 - 4096)       # the 8192-point kernel
+    assert bank.algo == zlib.FIR_FFT and blk == 2 * (16384 - 4096)      # the 16384-point kernel
     seg = zlib.shard_fir_segments(n, N, 2, 1)
     bank.reset()
     bank.set_history(dx.data_ptr() + 8 * (seg.in_start - seg.halo), n)
