@@ -37,7 +37,6 @@ int noted_launches();
 struct Tunables {
     double pipe_slot_mib;   // staging-slot size of the *_run_host pipelines (LLZ_PIPE_SLOT_MB), default 64
     int slide_ru;           // force a tile variant of the sliding kernel: 11, 7, 5, 3; 0 = automatic (LLZ_SLIDE_RU)
-    int fft16k_wg;          // 16384-point kernel, f64: warps per group, 8 (one group per CTA) or 4 (two); 0 = default (tuning)
     int fft8k_skew, fft16k_skew;   // warp-group skew of the 8192- / 16384-point kernels in cycles; < 0 = measured default
     int umma_knife_cycles;  // extra cost of a phase tile with knife-edge outputs in the walk's shares (tuning)
     int umma_band_mib;      // samples per band of the tcgen05 kernel's tile walk (tuning)

@@ -1,11 +1,12 @@
-// llz_cuda_fir_fft16k.cu -- overlap-save FIR banks for long filters (2561 .. 12289 taps) on sm_100a: a 16384-point
-// transform per CTA, run as TWO ROUNDS of eight 1024-point sub-transforms with the half that does not fit the SM parked
-// in L2.  Tolerance-mode arithmetic of llz_fir_filter / llz_conv (libllzfilter/llz_fir.c:411-426, 547-584).
+// llz_cuda_fir_fft16k.cu -- overlap-save FIR banks for long filters (3329 / 2305 .. 12289 taps, f64 / f32) on sm_100a:
+// a 16384-point transform per CTA, run as TWO ROUNDS of eight 1024-point sub-transforms with the half of the item that
+// does not fit the SM parked in L2.  Tolerance-mode arithmetic of llz_fir_filter / llz_conv
+// (libllzfilter/llz_fir.c:411-426, 547-584).
 //
 //   y[c][t] = sum_{i<N} h[i] * x[c][t-i]
 //
 // At 4095 taps the 8192-point kernel (llz_cuda_fir_fft8k.cu) keeps B = 8192 - 4096 outputs per block: half of every
-// transform is overlap.  With 16384 points B = 12288 (75 %): 57.4 instead of 80.6 FMA-pipe instructions and two thirds
+// transform is overlap.  With 16384 points B = 12288 (75 %): 57-60 instead of 80.6 FMA-pipe instructions and two thirds
 // of the shared-memory wavefronts per output -- the two pipes that bound these kernels.  16384 complex doubles are
 // 256 KB: twice the exchange buffer an SM can hold and, in registers, twice its register file.  Round 1 of this file
 // spread the item over a cluster of two CTAs and exchanged through distributed shared memory; tools/probe_l2_dsmem.cu
@@ -14,29 +15,41 @@
 // gone: ONE CTA of 256 threads owns the item and processes its 16 residues in two rounds.
 //
 //   * 16384 = 16 x 1024.  Thread tid gathers z[tid + 256 qq + 1024 a] (qq < 4, a < 16; z = x_A + i x_B, two consecutive
-//     blocks of one channel) in two passes of 32 points, runs two DFT-16 over a per pass and pushes residue b, row
-//     j = n_lo / 32 (n_lo = tid + 256 qq):  b < 8 into slice b of the 128 KB exchange buffer in shared memory,
-//     b >= 8 into the CTA's scratch in global memory (128 KB, written and read by this CTA only: it lives in L2);
-//   * round r (0, 1): warp w transforms residue b = w + 8 r -- reads its 32 x 32 points (shared memory / scratch), runs
+//     blocks of one channel) in four half-passes of 16 points -- the loads of half-pass qq + 1 are in flight while
+//     half-pass qq runs its DFT-16 over a and pushes residue b, row j = n_lo / 32 (n_lo = tid + 256 qq): b < 8 into
+//     slice b of the 128 KB exchange buffer in shared memory, b >= 8 into the CTA's scratch in global memory (written
+//     and read by this CTA only: it lives in L2; the input samples are loaded evict_first so that they do not push it
+//     out -- with them at normal priority 40 % more bytes went to DRAM than the call's outputs);
+//   * round r (0, 1): warp w transforms residue b = w + 8 r.  It finds the residue in its slice (round 0: pushed by the
+//     other warps; round 1: a TMA bulk copy from the scratch, issued when round 0 had finished with the slice), runs
 //     the 1024-point transform of llz_cuda_fir_fft.cu with the outer twiddle exp(-2 pi i b n_lo / 16384) folded in
 //     (warp-uniform part: the 1024-point table at index 2b; the rest merged with the four-step twiddle into a
-//     [b][16][32] table whose 8 KB for residue b arrive in the warp's part of shared memory by a TMA bulk copy issued
-//     a whole round earlier), multiplies by the spectrum (its 16 KB slice arrives in the warp's own exchange slice by
+//     [b][16][32] table whose 8 KB for residue b arrive in the warp's part of shared memory by a bulk copy issued a
+//     whole round earlier), multiplies by the spectrum (its 16 KB slice arrives in the warp's own exchange slice by
 //     TMA while the second DFT-32 runs), runs the inverse 1024-point transform and writes the result -- round 0 to the
-//     second half of the scratch, round 1 to its slice.  There is NO CTA-wide barrier between the push and the pull:
-//     2 x 2052 FMA-pipe instructions per thread during which the eight warps drift apart and one warp's exchanges hide
-//     behind another's butterflies;
-//   * after a barrier every thread pulls its 64 points back in two passes (b < 8 from the scratch, b >= 8 from shared
-//     memory), runs two DFT-16 per pass with the conjugate outer twiddle folded in, and holds outputs
-//     tid + 256 qq + 1024 a: coalesced streaming stores of the rows at or beyond the halo;
-//   * three __syncthreads per item; the next item's input span is prefetched into L2.
+//     scratch, round 1 to its slice.  There is NO CTA-wide barrier between the push and the pull: 2 x 2052 FMA-pipe
+//     instructions per thread during which the eight warps drift apart and one warp's exchanges hide behind another's
+//     butterflies (70 % of the FP64 issue rate inside the rounds);
+//   * after a barrier every thread pulls its 64 points back in four half-passes (b < 8 from the scratch, b >= 8 from
+//     shared memory; again one half-pass ahead), runs a DFT-16 per half-pass with the conjugate outer twiddle -- f32:
+//     folded in from the [2][8][512] table; f64: powers of the thread's own root computed on the fly (dft16_powers),
+//     because this phase is bound by what the SM can pull out of L2, not by the FP64 pipe -- and holds outputs
+//     tid + 256 qq + 1024 a: coalesced streaming stores of the rows at or beyond the halo; f64: half-pass 0 of the
+//     NEXT item is loaded under the last of these transforms;
+//   * three barriers per item; the next item's input span is prefetched into L2 late (under the pull, not an item
+//     ahead: what is prefetched competes with the scratch for L2).
 //
-// Per thread and item: 4 x 144 (DFT-16) + 2 x (3 x 512 + 388 + 128) + 4 x 208 (folded DFT-16) = 5512 FMA-pipe
-// instructions for 96 outputs at B = 12288: 57.4 per output (8192-point kernel: 80.6).
+// WG (warps per group) is a template parameter: the CTA's eight warps can also form two groups of four that own an item
+// each and run four rounds, so that one group's gather / pull phases (L2-bound) run beside the other's butterflies.
+// Measured and NOT instantiated: the scratch doubles to 76 MB over the chip, which this L2 no longer holds (DRAM traffic
+// 2.4 x the call's bytes, 94-98 against 133 Gsamples/s on C5 f64); one group's 38 MB stay resident.
+//
+// Per thread and item: 4 x 144 (DFT-16) + 2 x (3 x 512 + 388 + 128) + 4 x 208 (folded DFT-16; f64: 4 x 264) = 5512
+// (5736) FMA-pipe instructions for 96 outputs at B = 12288: 57.4 (59.8) per output (8192-point kernel: 80.6).
 // L2 traffic per item beyond the samples: 128 KB + 128 KB of scratch written and read, 256 KB of spectrum, 128 KB of
-// each twiddle table.
-// Verified on the host by tests/cpu/fft16k_emulate.cpp (same 16 x 1024 algebra and tables), on the device by
-// tests/test_gpu_fir.py.
+// the [b][16][32] table (f32: half of all that, plus 64 KB of the last pass's table).
+// Verified on the host by tests/cpu/fft16k_emulate.cpp (same 16 x 1024 algebra, tables and dft16_powers), on the device
+// by tests/test_gpu_fir.py.
 #include <stdlib.h>
 
 #include "llz_fft32.cuh"
@@ -406,9 +419,9 @@ fir_fft16k_kernel(FirFftLaunch<T> a)
 template <typename T>
 size_t fir_fft16k_scratch_bytes(int sm_count)
 {
-    // one region of 16 residues x 1024 points per group of every resident CTA, for the interior and for the edge
-    // launch (they run side by side on two streams)
-    const size_t slots = (size_t)sm_count * 2;
+    // one region of 16 residues x 1024 points per resident CTA, for the interior and for the edge launch (they run
+    // side by side on two streams)
+    const size_t slots = (size_t)sm_count * (sizeof(T) == 4 ? 2 : 1);
     return 2 * slots * 16 * kFft16kSlice * 2 * sizeof(T);
 }
 
@@ -429,7 +442,7 @@ static int fir_fft16k_run(FirFftLaunch<T> b, int n_channels, long long first, lo
     const long long items = count * n_channels;
     const long long ctas = (long long)sm_count * (sizeof(T) == 4 ? 2 : 1), want = (items + GROUPS - 1) / GROUPS;
     const unsigned grid = (unsigned)(want < ctas ? want : ctas);
-    if (EDGE) b.scratch = b.scratch + (size_t)sm_count * 2 * 16 * kFft16kSlice * 2;   // the second half of the scratch
+    if (EDGE) b.scratch = b.scratch + (size_t)ctas * GROUPS * 16 * kFft16kSlice * 2;   // the second half of the scratch
     kern<<<grid, kFft16kThreads, smem, stream>>>(b);
     LLZ_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -459,13 +472,7 @@ int fir_fft16k_launch(FirFftLaunch<T> a, int n_channels, cudaStream_t stream)
     a.prefetch = 1;
     const int sk = tunables().fft16k_skew;                     // llz_cuda_tune("fft16k_skew", cycles); < 0: the measured default
     a.skew = sk >= 0 ? sk : (sizeof(T) == 8 ? 1300 : 0);
-    // warps per group: f64 (254 registers per thread, one CTA per SM) ...; f32 runs two CTAs of one group per SM
-    const int wg = tunables().fft16k_wg ? tunables().fft16k_wg : 8;
     cudaStream_t es = a.side ? a.side : stream;
-    if constexpr (sizeof(T) == 8) if (wg == 4) {
-        if (fir_fft16k_run<T, false, 4>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
-        return fir_fft16k_run<T, true, 4>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, es);
-    }
     if (fir_fft16k_run<T, false, 8>(a, n_channels, p_lo, p_hi - p_lo, ppc, 0, sm_count, stream) != 0) return -1;
     return fir_fft16k_run<T, true, 8>(a, n_channels, 0, ppc - (p_hi - p_lo), p_lo, p_hi - p_lo, sm_count, es);
 }

@@ -53,7 +53,6 @@ Tunables &tunables()
         v.fft8k_skew = (e && *e) ? atoi(e) : -1;
         e = getenv("LLZ_FFT16K_SKEW");
         v.fft16k_skew = (e && *e) ? atoi(e) : -1;
-        v.fft16k_wg = 0;
         v.umma_band_mib = 32;
         v.umma_knife_cycles = 1000;
         e = getenv("LLZ_UMMA_SLAB_MB");
@@ -167,7 +166,6 @@ extern "C" int llz_cuda_tune(const char *key, double value)
     if (strcmp(key, "slide_ru") == 0) { t.slide_ru = (int)value; return 0; }
     if (strcmp(key, "fft8k_skew") == 0) { t.fft8k_skew = (int)value; return 0; }
     if (strcmp(key, "fft16k_skew") == 0) { t.fft16k_skew = (int)value; return 0; }
-    if (strcmp(key, "fft16k_wg") == 0 && (value == 0 || value == 4 || value == 8)) { t.fft16k_wg = (int)value; return 0; }
     if (strcmp(key, "umma_knife_cycles") == 0 && value >= 0 && value <= 100000) { t.umma_knife_cycles = (int)value; return 0; }
     if (strcmp(key, "umma_band_mib") == 0 && value >= 1 && value <= 4096) { t.umma_band_mib = (int)value; return 0; }
     if (strcmp(key, "umma_slab_mib") == 0 && value >= 1.0) { t.umma_slab_mib = value; return 0; }

@@ -55,7 +55,7 @@ def emu16k(tmp_path_factory):
 
 @pytest.mark.parametrize("ntaps", [2305, 4095, 12289])
 @pytest.mark.parametrize("f32", [0, 1])
-def test_cluster_level_16384_point_overlap_save(emu16k, ntaps, f32):
+def test_16384_point_overlap_save_in_two_rounds(emu16k, ntaps, f32):
     r = subprocess.run([emu16k, str(ntaps), str(f32)], capture_output=True, text=True)
     err = float(r.stdout.strip())
     assert r.returncode == 0 and err < (2e-6 if f32 else 1e-14), (ntaps, f32, err)

@@ -227,7 +227,7 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
 @pytest.mark.parametrize("N,size", [(898, 8192), (2049, 8192), (4095, 8192), (6145, 8192),
                                     (2305, 16384), (4095, 16384), (8191, 16384), (12289, 16384)])
 def test_fft8k_16k_bank_interior_and_edge_items(zlib, port, cuda, N, size):
-    """8192-point (one CTA per item) and 16384-point (one two-CTA cluster per item, distributed shared memory)
+    """8192-point (one CTA per item) and 16384-point (one CTA per item in two rounds, half of the item in an L2-resident scratch)
     overlap-save kernels: several interior items, history splice, ragged end"""
     torch = cuda
     rng = np.random.default_rng(N)
@@ -256,6 +256,17 @@ def test_fft8k_16k_bank_interior_and_edge_items(zlib, port, cuda, N, size):
         want2 = oracle_bank(port, h, np.concatenate([x, x[:, :20000]], axis=1))[:, n:]
         assert np.abs(dy2.cpu().numpy() - want2).max() <= tol, (N, dtype)
         bank.close()
+
+
+@pytest.mark.parametrize("dtype,N,size", [("f64", 544, 1024), ("f64", 545, 8192), ("f64", 3328, 8192), ("f64", 3329, 16384),
+                                          ("f64", 4095, 16384), ("f32", 2304, 8192), ("f32", 2305, 16384), ("f32", 4095, 16384)])
+def test_auto_transform_length_by_tap_count(zlib, cuda, dtype, N, size):
+    """LLZ_CUDA_FIR_ALGO_AUTO: the transform length follows the measured crossovers (profiles/r02_crossover_fft16k.txt)"""
+    bank = zlib.FirBank(2, zlib.F64 if dtype == "f64" else zlib.F32, kind=zlib.LPF, flt_len=N, fc1=0.2)
+    pad = {1024: 32, 8192: 256, 16384: 512}[size]
+    assert bank.algo == zlib.FIR_FFT
+    assert bank.block_len == 2 * (size - (N - 1 + pad - 1) // pad * pad)
+    bank.close()
 
 
 @pytest.mark.parametrize("dtype,N", [("f64", 129), ("f32", 129), ("f64", 2049)])

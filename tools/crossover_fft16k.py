@@ -1,4 +1,4 @@
-"""Where does the 16384-point cluster kernel overtake the 8192-point one?  (tuning of kFirFft16kMinTapsAuto)
+"""Where does the 16384-point kernel overtake the 8192-point one?  (tuning of kFirFft16kMinTapsAutoF64 / F32)
 Run under gpurun: python tools/crossover_fft16k.py"""
 import os
 import sys

@@ -96,7 +96,7 @@ def poly_case(name, kind, L_, M, k, acc, tiles, frames, C_=2, scale=1.0):
 
 
 torch.cuda.set_device(0)
-# FIR: direct (strict / fma / f32 blocked), overlap-save 1024 (staged f64, gather f32), 8192, 16384 (cluster + DSMEM)
+# FIR: direct (strict / fma / f32 blocked), overlap-save 1024 (staged f64, gather f32), 8192, 16384 (two rounds, L2 scratch)
 fir_case("fir_strict", 127, z.F64_STRICT, z.FIR_DIRECT, 9000)
 fir_case("fir_direct_f64", 127, z.F64, z.FIR_DIRECT, 9000)
 fir_case("fir_direct_f32", 513, z.F32, z.FIR_DIRECT, 9000)
