@@ -102,7 +102,10 @@ int llz_cuda_fir_bank_set_algo(unsigned long handle, int algo);
 /* the family the next _run will use: LLZ_CUDA_FIR_ALGO_DIRECT or LLZ_CUDA_FIR_ALGO_FFT */
 int llz_cuda_fir_bank_get_algo(unsigned long handle);
 /* transform length of the overlap-save family: 0 = by tap count (default), 1024, 8192 or 16384; fails when the
- * filter does not fit.  Crossover measurements and tests use it; results agree to rounding between lengths.    */
+ * filter does not fit.  Crossover measurements and tests use it; results agree to rounding between lengths.
+ * A bank on the 16384-point kernel owns a scratch in device memory (256 KB per resident CTA, twice: 76 MB on a
+ * B200), allocated by its first _run and freed with the handle: the half of every work item that does not fit
+ * shared memory waits there, in L2.                                                                             */
 int llz_cuda_fir_bank_set_fft_size(unsigned long handle, int fft_size);
 /* samples per work item of the kernel the next _run will use: 2*(1024 - halo), 2*(8192 - halo) or 2*(16384 - halo) for the
  * overlap-save kernels, 1 for the direct form.  A stream cut at multiples of this length (time segments with
