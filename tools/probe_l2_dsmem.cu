@@ -9,6 +9,7 @@
 //   mode 2: mode 0 and mode 1 together                                                                    [both]
 //   mode 3: cluster of two: push 64 KB into the partner's shared memory, cluster barrier, pull 64 KB back [DSMEM]
 //   mode 4: mode 3 with shared-memory traffic of the CTA's own (128 KB written + read) beside it          [DSMEM + local]
+//   mode 5: mode 0 with 128 KB ... 1 MB of scratch per CTA (19 ... 148 MB over the chip)                      [L2 capacity]
 // Prints bytes per clock and SM (clock64 of CTA 0) and GB/s over the whole chip (CUDA events).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o probe_l2_dsmem probe_l2_dsmem.cu
 #include <cuda_runtime.h>
@@ -56,6 +57,36 @@ __global__ void __launch_bounds__(kThreads, 1) l2_kernel(double2 *scratch, const
 #pragma unroll
             for (int i = 0; i < kPer; ++i) acc += v[i].y;
         }
+    }
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && tid == 0) *clk = t1 - t0;
+    if (acc == 12345.678) *sink = acc;
+}
+
+// mode 5: the scratch of mode 0 at growing size -- CHUNKS x 128 KB per CTA are written, then read back, per round: where
+// does the chip stop holding the CTAs' private scratch in L2?
+__global__ void __launch_bounds__(kThreads, 1) footprint_kernel(double2 *scratch, int chunks, int rounds, long long *clk, double *sink)
+{
+    double2 *mine = scratch + (size_t)blockIdx.x * chunks * (kThreads * kPer);
+    const int tid = threadIdx.x, other = (tid + 96) & (kThreads - 1);
+    double acc = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+        for (int c = 0; c < chunks; ++c) {
+            double2 *blk = mine + (size_t)c * (kThreads * kPer);
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) blk[i * kThreads + tid] = make_double2(acc + i, r);
+        }
+        __syncthreads();
+        for (int c = 0; c < chunks; ++c) {
+            const double2 *blk = mine + (size_t)c * (kThreads * kPer);
+            double2 v[kPer];
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) v[i] = ld_cg(blk + i * kThreads + other);
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) acc += v[i].x;
+        }
+        __syncthreads();
     }
     const long long t1 = clock64();
     if (blockIdx.x == 0 && tid == 0) *clk = t1 - t0;
@@ -159,6 +190,28 @@ int main()
         }
         printf("mode %d  %-72s %7.1f B/clk/SM  %8.1f GB/s chip  (%.0f clk per round, %.3f ms)\n", mode, what,
                bytes * rounds / (double)c, bytes * rounds * sms / (ms * 1e6), (double)c / rounds, ms);
+    }
+    // mode 5: footprint sweep
+    double2 *big;
+    const int max_chunks = 8;
+    CK(cudaMalloc(&big, (size_t)sms * max_chunks * kThreads * kPer * sizeof(double2)));
+    CK(cudaMemset(big, 0, (size_t)sms * max_chunks * kThreads * kPer * sizeof(double2)));
+    for (int chunks = 1; chunks <= max_chunks; chunks += (chunks < 4 ? 1 : 2)) {
+        float ms = 0.f;
+        const int rr = 400;
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaEventRecord(e0));
+            footprint_kernel<<<sms, kThreads>>>(big, chunks, rr, clk, sink);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        long long c = 0;
+        CK(cudaMemcpy(&c, clk, sizeof(c), cudaMemcpyDeviceToHost));
+        const double bytes = 2.0 * chunks * per_dir;
+        printf("mode 5  scratch %4d KB per CTA = %6.1f MB over the chip, written + read back   %7.1f B/clk/SM  %8.1f GB/s chip\n",
+               chunks * 128, chunks * 128.0 * sms / 1024, bytes * rr / (double)c, bytes * rr * sms / (ms * 1e6));
     }
     return 0;
 }
