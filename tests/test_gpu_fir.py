@@ -269,7 +269,7 @@ def test_auto_transform_length_by_tap_count(zlib, cuda, dtype, N, size):
     bank.close()
 
 
-@pytest.mark.parametrize("dtype,N", [("f64", 129), ("f32", 129), ("f64", 2049)])
+@pytest.mark.parametrize("dtype,N", [("f64", 129), ("f32", 129), ("f64", 2049), ("f64", 4095), ("f32", 2561)])
 def test_fft_bank_streaming_ragged_chunks(zlib, port, cuda, dtype, N):
     """overlap-save kernels: chunk sizes below / around the history and the block size, odd strides, flush, restart"""
     torch = cuda
