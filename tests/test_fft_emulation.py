@@ -53,7 +53,7 @@ def emu16k(tmp_path_factory):
     return build(tmp_path_factory, "fft16k_emulate")
 
 
-@pytest.mark.parametrize("ntaps", [2305, 4095, 12289])
+@pytest.mark.parametrize("ntaps", [2305, 3700, 4095, 12289])
 @pytest.mark.parametrize("f32", [0, 1])
 def test_16384_point_overlap_save_in_two_rounds(emu16k, ntaps, f32):
     r = subprocess.run([emu16k, str(ntaps), str(f32)], capture_output=True, text=True)
