@@ -225,7 +225,7 @@ def test_time_segments_with_halo_are_byte_identical(zlib, port, cuda):
 
 
 @pytest.mark.parametrize("N,size", [(898, 8192), (2049, 8192), (4095, 8192), (6145, 8192),
-                                    (2305, 16384), (4095, 16384), (8191, 16384), (12289, 16384)])
+                                    (2305, 16384), (3700, 16384), (4095, 16384), (8191, 16384), (12289, 16384)])
 def test_fft8k_16k_bank_interior_and_edge_items(zlib, port, cuda, N, size):
     """8192-point (one CTA per item) and 16384-point (one CTA per item in two rounds, half of the item in an L2-resident scratch)
     overlap-save kernels: several interior items, history splice, ragged end"""
