@@ -125,8 +125,9 @@ __device__ __forceinline__ void group_sync(int g, int threads)
 
 // EDGE = false: interior items (unguarded loads and stores); EDGE = true: first / last items of a channel.
 // WG = warps per group: the CTA's eight warps form 8 / WG groups that each own an item and share nothing but the
-// 1024-point twiddle table, so that one group's gather / push / pull / store phases (load/store-queue bound) run beside
-// the other group's butterflies.  A group of WG warps transforms the 16 residues in 16 / WG rounds.
+// 1024-point twiddle table; a group of WG warps transforms the 16 residues in 16 / WG rounds.  Only WG = 8 (one group,
+// two rounds) is instantiated: with two groups one group's gather / pull phases would run beside the other's
+// butterflies, but their scratch no longer stays in L2 (see the head of the file).
 template <typename T, bool EDGE, int WG>
 __global__ void __launch_bounds__(kFft16kThreads, sizeof(T) == 4 ? 2 : 1)
 fir_fft16k_kernel(FirFftLaunch<T> a)
