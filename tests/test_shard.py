@@ -36,7 +36,8 @@ def test_fir_segments(zlib, n, N, world):
     assert pos == n
 
 
-@pytest.mark.parametrize("n,N,g,world", [(691_200_000, 4095, 8192, 8), (100_003, 255, 1536, 4), (1000, 127, 1792, 2),
+@pytest.mark.parametrize("n,N,g,world", [(691_200_000, 4095, 8192, 8), (691_200_000, 4095, 24576, 8), (230_400_000, 4095, 24576, 4),
+                                         (100_003, 255, 1536, 4), (1000, 127, 1792, 2),
                                          (5, 3, 1, 8), (480_000, 127, 1792, 8)])
 def test_fir_segments_aligned(zlib, n, N, g, world):
     """every internal boundary is a multiple of the kernel's work-item length; the segments tile [0, n)"""
